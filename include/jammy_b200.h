@@ -1,0 +1,227 @@
+/*
+ * jammy_b200.h -- C-ABI of the B200-native (sm_100a) jammy_flows hot path.
+ *
+ * One shared library (libjammy_b200.so), plain pointers and sizes, no torch/C++ types in any signature.
+ * Every entry point replaces one interface of the reference (thoglu/jammy_flows v1.1.0, paths relative to
+ * /root/reference/jammy_flows/):
+ *
+ *   jf_subpdf_apply      <- layer plugin API  layers/layer_base.py:58-70 (`flow_mapping` / `inv_flow_mapping`
+ *                           with `[x, log_det]` and `extra_inputs`), chained over all layers of one sub-pdf exactly as
+ *                           the loops in main/default.py:998-1031 (log_pdf) and :1482-1506 (sampling) do, including
+ *                           the sub-pdf's base chart and the N(0,1) base log-density (main/default.py:1110-1117).
+ *   jf_mlp_forward       <- the parameter generator nn.Sequential(Linear,Tanh,...,Linear), main/default.py:654-670,
+ *                           called at main/default.py:956 / :1438 with cat([cond] + embedded previous targets).
+ *   jf_pdf_logpdf        <- pdf.forward / all_layer_inverse, main/default.py:1059-1117 and :879-1057.
+ *   jf_pdf_sample        <- pdf._obtain_sample / all_layer_forward, main/default.py:1533-1707 and :1373-1531
+ *                           (base normals are supplied by the caller, like `predefined_target_input`).
+ *   jf_pdf_logpdf_host / jf_pdf_sample_host
+ *                        <- the same two calls with HOST buffers: pipelined H2D -> kernels -> D2H (the end-to-end path).
+ *
+ * Ownership: the caller allocates every buffer (inputs, outputs, workspace) and passes raw device pointers
+ * (host pointers only for the *_host entries); the library never allocates or frees device memory.
+ * Threading: re-entrant, no global mutable state; all work is enqueued on the caller's `stream` (a cudaStream_t
+ * passed as void*).  No entry point synchronises the device except the *_host entries, which synchronise their
+ * internal streams before returning.
+ * Errors: return value 0 = ok, <0 = invalid/unsupported descriptor (JF_ERR_*), >0 = CUDA runtime error code.
+ * Numerical conditions (non-finite values, unconverged root finds, out-of-range inputs) are counted in the device
+ * array `status[JF_STATUS_WORDS]` and are read lazily by the caller (no implicit sync), mirroring the reference's
+ * fail-safes in layers/bisection_n_newton.py:84-133.
+ */
+#ifndef JAMMY_B200_H
+#define JAMMY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JF_ABI_VERSION 1
+
+#define JF_MAX_LAYERS 16
+#define JF_MAX_SUBPDFS 8
+#define JF_MAX_MLP_LINEAR 6
+#define JF_MAX_MLP_SEGMENTS 10
+#define JF_MAX_DIM 16      /* max intrinsic dimension of one Euclidean sub-pdf */
+#define JF_MAX_KDE 32      /* max num_kde of a "g" layer */
+#define JF_STATUS_WORDS 4
+
+/* dtype of all floating-point buffers of a call */
+#define JF_F32 0
+#define JF_F64 1
+
+/* direction */
+#define JF_DIR_LOGPDF 0 /* target -> base, reference `inv_flow_mapping` */
+#define JF_DIR_SAMPLE 1 /* base -> target, reference `flow_mapping` */
+
+/* layer kinds (reference layer codes, flow_options.py:25-240) */
+#define JF_LAYER_GF 1  /* "g" gf_block */
+#define JF_LAYER_FVM 2 /* "f" fisher_von_mises_2d ("n" alias) */
+
+/* inverse-CDF stage of "g" (gaussianization_flow.py:480-671) */
+#define JF_INV_ISIGMOID 0
+#define JF_INV_PARTLY_PRECISE 1
+#define JF_INV_FULL_PADE 2
+#define JF_INV_PARTLY_CRUDE 3
+
+/* normalisation handling of "g" */
+#define JF_NORM_NONE 0      /* fit_normalization=0: uniform weights */
+#define JF_NORM_RAW 1       /* fit_normalization=1, regulate_normalization=0: log-softmax of the raw values */
+#define JF_NORM_REGULATED 2 /* regulated into [n_min, n_min+n_max] first (gaussianization_flow.py:342) */
+
+/* status words */
+#define JF_STATUS_NONFINITE 0
+#define JF_STATUS_UNCONVERGED 1
+#define JF_STATUS_OUT_OF_RANGE 2
+#define JF_STATUS_ITERATIONS 3 /* total root-finder function evaluations (diagnostics) */
+
+/* error codes */
+#define JF_OK 0
+#define JF_ERR_BAD_DESC -1
+#define JF_ERR_UNSUPPORTED -2
+#define JF_ERR_BAD_ARG -3
+#define JF_ERR_WORKSPACE -4
+
+typedef struct JfLayerDesc {
+    int32_t kind;         /* JF_LAYER_* */
+    int32_t dim;          /* intrinsic dimension of the layer */
+    int32_t n_params;     /* length of the layer's slice in the sub-pdf parameter vector */
+    int32_t param_offset; /* start of that slice (layers are stored in flow order, main/default.py:1488) */
+    int32_t K;            /* g: num_kde */
+    int32_t hh_iter;      /* number of Householder reflections (g: in R^d; f: in R^3); 0 = no rotation */
+    int32_t inv_type;     /* g: JF_INV_* */
+    int32_t norm_mode;    /* g: JF_NORM_* */
+    int32_t has_offset;   /* g: model_offset (euclidean_base.py:34-75); offset params come first in the slice */
+    int32_t first;        /* s2: layer also applies the plane<->sphere base chart (sphere_base.py:637-648) */
+    int32_t reserved0;
+    int32_t reserved1;
+    double w_min, w_max; /* g: width bounds (gaussianization_flow.py:300-317) */
+    double n_min, n_max; /* g: norm bounds (gaussianization_flow.py:342) */
+    double z_sign;       /* f: z_scaling_factor (+1/-1, fvm_2d.py:96-99) */
+    double min_kappa;    /* f: kappa = exp(raw) + min_kappa (fvm_2d.py:123) */
+} JfLayerDesc;
+
+typedef struct JfSubPdfDesc {
+    int32_t manifold;   /* 'e' or 's' (ASCII) */
+    int32_t dim;        /* intrinsic dimension */
+    int32_t n_layers;
+    int32_t n_params;   /* sum of the layers' n_params */
+    JfLayerDesc layers[JF_MAX_LAYERS];
+} JfSubPdfDesc;
+
+typedef struct JfMlpDesc {
+    int32_t n_linear;                     /* number of Linear layers; tanh between them */
+    int32_t dims[JF_MAX_MLP_LINEAR + 1];  /* in, hidden..., out */
+    int32_t n_segments;                   /* input = concatenation of column blocks */
+    int32_t seg_cols[JF_MAX_MLP_SEGMENTS];
+} JfMlpDesc;
+
+/*
+ * Apply all layers of ONE sub-pdf to B rows.
+ *   in / out        [B, in_cols] / [B, out_cols] row-major with leading dimensions ld_in / ld_out (elements).
+ *                   LOGPDF: in = target coordinates (e: d; s2: theta,phi), out = base coordinates.
+ *                   SAMPLE: in = base normals, out = target coordinates.
+ *   params          raw parameters in the reference's `extra_inputs` order; element (j,row) is
+ *                   params[j*p_stride_param + row*p_stride_row].  p_stride_row == 0 means one shared vector
+ *                   (the reference's permanent nn.Parameters, broadcast over the batch).
+ *   logdet_in/out   [B]; in may be NULL (= 0).  out = in +/- the log-det terms (functional, in is not modified
+ *                   unless the two pointers alias -- reference tests/test_general.py:533-550).
+ *   logbase_in/out  [B] optional (NULL to skip): out = in + sum_j log N(z_j; 0,1) over this sub-pdf's base coords.
+ *   emb_out         optional [B, ld_emb]: embedding of the TARGET coordinates handed to later MLPs
+ *                   (`_embedding_conditional_return`, main/default.py:1050-1053): e -> identity (d), s2 -> (x,y,z).
+ */
+int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int direction,
+                    const void* in, int64_t ld_in,
+                    const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                    const void* logdet_in, void* logdet_out,
+                    const void* logbase_in, void* logbase_out,
+                    void* out, int64_t ld_out,
+                    void* emb_out, int64_t ld_emb,
+                    int64_t B, int32_t* status, void* stream);
+
+/*
+ * params = W_L * tanh(... tanh(W_1 * concat(segments) + b_1) ...) + b_L for B rows.
+ *   seg_ptrs[i]/seg_ld[i]  column block i: [B, seg_cols[i]] with leading dimension seg_ld[i].
+ *   weights_t[l]           TRANSPOSED weight of Linear l: [dims[l], dims[l+1]] row-major (= torch weight.t().contiguous()).
+ *   biases[l]              [dims[l+1]].
+ *   out                    element (j,row) at out[j*out_stride_param + row*out_stride_row].
+ */
+int jf_mlp_forward(const JfMlpDesc* desc, int dtype,
+                   const void* const* seg_ptrs, const int64_t* seg_ld,
+                   const void* const* weights_t, const void* const* biases,
+                   void* out, int64_t out_stride_param, int64_t out_stride_row,
+                   int64_t B, void* stream);
+
+/* ---- whole-pdf entries -------------------------------------------------------------------------------------------- */
+typedef struct JfPdfDesc {
+    int32_t abi_version; /* JF_ABI_VERSION */
+    int32_t dtype;       /* JF_F32 / JF_F64 */
+    int32_t n_sub;
+    int32_t cond_dim;    /* 0 = unconditional */
+    int32_t total_target_dim;
+    int32_t total_base_dim;
+    int32_t reserved0;
+    int32_t reserved1;
+    JfSubPdfDesc sub[JF_MAX_SUBPDFS];
+    int32_t target_col[JF_MAX_SUBPDFS]; /* first column of the sub-pdf in x (main/default.py:481-567) */
+    int32_t base_col[JF_MAX_SUBPDFS];   /* first column in the base-space tensor */
+    int32_t emb_dim[JF_MAX_SUBPDFS];    /* _embedding_conditional_return_num() */
+    int32_t has_mlp[JF_MAX_SUBPDFS];    /* 1: parameters come from mlp[k]; 0: shared vector */
+    JfMlpDesc mlp[JF_MAX_SUBPDFS];      /* n_segments/seg_cols are filled in by the library */
+} JfPdfDesc;
+
+typedef struct JfPdfParams {
+    const void* shared[JF_MAX_SUBPDFS];                       /* raw shared vector [n_params] or NULL */
+    const void* weights_t[JF_MAX_SUBPDFS][JF_MAX_MLP_LINEAR]; /* transposed Linear weights (device) */
+    const void* biases[JF_MAX_SUBPDFS][JF_MAX_MLP_LINEAR];
+} JfPdfParams;
+
+/* bytes of device workspace needed to process `chunk_rows` rows at a time */
+int64_t jf_pdf_workspace_bytes(const JfPdfDesc* desc, int64_t chunk_rows);
+
+/* log_pdf of B rows, all buffers on the device.  x [B, ldx], cond [B, ldc] or NULL.
+ * Outputs (any may be NULL): logp [B], logp_base [B], base [B, ld_base]. */
+int jf_pdf_logpdf(const JfPdfDesc* desc, const JfPdfParams* params,
+                  const void* x, int64_t ldx, const void* cond, int64_t ldc,
+                  void* logp, void* logp_base, void* base, int64_t ld_base,
+                  int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
+                  int32_t* status, void* stream);
+
+/* sampling: z [B, ldz] base normals -> x [B, ldx]; logp = log N(z) - logdet, logp_base = log N(z). */
+int jf_pdf_sample(const JfPdfDesc* desc, const JfPdfParams* params,
+                  const void* z, int64_t ldz, const void* cond, int64_t ldc,
+                  void* x, int64_t ldx, void* logp, void* logp_base,
+                  int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
+                  int32_t* status, void* stream);
+
+/* Same two calls with HOST buffers (pinned for full speed).  The library pipelines H2D copy, kernels and D2H copy
+ * over two internal streams in chunks of `chunk_rows`; `workspace` is device memory of
+ * jf_pdf_host_workspace_bytes(desc, chunk_rows) bytes.  Blocks until the results are in host memory. */
+int64_t jf_pdf_host_workspace_bytes(const JfPdfDesc* desc, int64_t chunk_rows);
+int jf_pdf_logpdf_host(const JfPdfDesc* desc, const JfPdfParams* params,
+                       const void* x_host, int64_t ldx, const void* cond_host, int64_t ldc,
+                       void* logp_host, void* logp_base_host, void* base_host, int64_t ld_base,
+                       int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
+                       int32_t* status);
+int jf_pdf_sample_host(const JfPdfDesc* desc, const JfPdfParams* params,
+                       const void* z_host, int64_t ldz, const void* cond_host, int64_t ldc,
+                       void* x_host, int64_t ldx, void* logp_host, void* logp_base_host,
+                       int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
+                       int32_t* status);
+
+/* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
+int jf_abi_version(void);
+/* FP64 DFMA / FP32 FFMA peak probe used as the roofline denominator of the compute-bound layer kernels:
+ * runs `iters` dependent FMA chains on every SM and returns the elapsed milliseconds (CUDA events) in *ms and the
+ * FMA count in *fma_count. */
+int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* stream);
+/* number of kernel launches issued by this library since process start (for bench.py's gpu_launches) */
+int64_t jf_launch_count(void);
+/* sizeof() of the ABI structs as compiled into the library (0: JfLayerDesc, 1: JfSubPdfDesc, 2: JfMlpDesc,
+ * 3: JfPdfDesc, 4: JfPdfParams); bindings assert these against their own mirrors. */
+int64_t jf_struct_size(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAMMY_B200_H */

@@ -1,0 +1,74 @@
+"""Build recipe of libjammy_b200.so (the C-ABI library, sm_100a only) -- plain nvcc, no torch headers.
+
+    python -m jammy_flows_b200.build            # (re)build if sources are newer than the library
+
+The library is built IN-TREE (jammy_flows_b200/libjammy_b200.so) so that it travels to the GPU box with the repo
+snapshot; it is git-ignored.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libjammy_b200.so")
+SOURCES = ["api.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libjammy_b200.so cannot be built (there is no CPU fallback)")
+    return nvcc
+
+
+def _newest_source_mtime():
+    newest = 0.0
+    for d in (CSRC, os.path.join(REPO_ROOT, "include")):
+        for f in os.listdir(d):
+            newest = max(newest, os.path.getmtime(os.path.join(d, f)))
+    return newest
+
+
+def needs_build():
+    return (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < _newest_source_mtime()
+
+
+def build(force=False, verbose=True):
+    if not force and not needs_build():
+        return LIB_PATH
+    objs = []
+    build_dir = os.path.join(PKG_DIR, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(build_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(out)
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed on %s" % src)
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc link failed")
+    with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        spills = [l for l in "\n".join(log).splitlines() if "spill" in l and "0 bytes spill stores, 0 bytes spill loads" not in l]
+        print("built %s (%d kernels report spills; see %s)" % (LIB_PATH, len(spills), os.path.join(build_dir, "ptxas.log")))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,517 @@
+// C-ABI entry points of libjammy_b200.so (see include/jammy_b200.h).  Host-side dispatch only; all math is in the
+// kernels.  Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include "subpdf_kernels.cuh"
+#include "mlp_kernels.cuh"
+
+using namespace jf;
+
+static std::atomic<int64_t> g_launches{0};
+
+#define JF_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+static inline int check_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? JF_OK : (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// jf_subpdf_apply
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+static void fill_common(SubPdfArgs<T>& a, const JfSubPdfDesc* desc, const void* in, int64_t ld_in, const void* params,
+                        int64_t sp, int64_t sr, const void* logdet_in, void* logdet_out, const void* logbase_in,
+                        void* logbase_out, void* out, int64_t ld_out, void* emb_out, int64_t ld_emb, int64_t B,
+                        int32_t* status) {
+    a.n_layers = desc->n_layers;
+    a.d = desc->dim;
+    a.B = B;
+    a.in = (const T*)in; a.ld_in = ld_in;
+    a.out = (T*)out; a.ld_out = ld_out;
+    a.params = (const T*)params; a.sj = sp; a.sr = sr;
+    a.logdet_in = (const T*)logdet_in; a.logdet_out = (T*)logdet_out;
+    a.logbase_in = (const T*)logbase_in; a.logbase_out = (T*)logbase_out;
+    a.emb_out = (T*)emb_out; a.ld_emb = ld_emb;
+    a.status = status;
+    a.tab_total = 0;
+}
+
+template <typename T, int D_, int K_>
+static int launch_gf(const GfChainArgs<T>& g, int direction, size_t smem, cudaStream_t st) {
+    const int threads = 256;
+    const int64_t blocks = (g.a.B + threads - 1) / threads;
+    if (direction == JF_DIR_LOGPDF) {
+        if (smem > 48 * 1024) JF_CUDA_OK(cudaFuncSetAttribute(gf_chain_kernel<T, D_, K_, JF_DIR_LOGPDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gf_chain_kernel<T, D_, K_, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, smem, st>>>(g);
+    } else {
+        if (smem > 48 * 1024) JF_CUDA_OK(cudaFuncSetAttribute(gf_chain_kernel<T, D_, K_, JF_DIR_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gf_chain_kernel<T, D_, K_, JF_DIR_SAMPLE><<<(unsigned)blocks, threads, smem, st>>>(g);
+    }
+    return check_launch();
+}
+
+template <typename T>
+static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, cudaStream_t st) {
+    const int d = desc->dim;
+    if (d < 1 || d > JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
+    bool all_k10 = true;
+    int tab = 0;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const JfLayerDesc& L = desc->layers[l];
+        if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_BAD_DESC;
+        if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
+        if (L.inv_type < 0 || L.inv_type > 3 || L.norm_mode < 0 || L.norm_mode > 2) return JF_ERR_BAD_DESC;
+        if (!(L.w_min > 0) || !(L.w_max > 0)) return JF_ERR_BAD_DESC;
+        const int expect = (L.has_offset ? d : 0) + L.hh_iter * d + (L.norm_mode != JF_NORM_NONE ? 3 : 2) * L.K * d;
+        if (expect != L.n_params) return JF_ERR_BAD_DESC;
+        GfLayerC<T>& c = g.layers[l];
+        c.K = L.K; c.d = d; c.hh_iter = L.hh_iter; c.inv_type = L.inv_type; c.norm_mode = L.norm_mode;
+        c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = tab;
+        c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = (T)L.n_min; c.n_max = (T)L.n_max;
+        tab += c.tab_size();
+        all_k10 = all_k10 && (L.K == 10);
+    }
+    g.a.tab_total = tab;
+    const size_t smem = (g.a.sr == 0) ? (size_t)tab * sizeof(T) : 0;
+    if (smem > 200 * 1024) return JF_ERR_UNSUPPORTED;
+#define JF_GF_CASE(DD) case DD: return launch_gf<T, DD, 10>(g, direction, smem, st);
+    if (all_k10) {
+        switch (d) {
+            JF_GF_CASE(1) JF_GF_CASE(2) JF_GF_CASE(3) JF_GF_CASE(4) JF_GF_CASE(5) JF_GF_CASE(6) JF_GF_CASE(8) JF_GF_CASE(10)
+            default: break;
+        }
+    }
+#undef JF_GF_CASE
+    return launch_gf<T, 0, 0>(g, direction, smem, st);
+}
+
+template <typename T>
+static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaStream_t st) {
+    if (desc->dim != 2) return JF_ERR_UNSUPPORTED;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const JfLayerDesc& L = desc->layers[l];
+        if (L.kind != JF_LAYER_FVM) return JF_ERR_UNSUPPORTED;
+        if ((l == 0) != (L.first != 0) && L.first != 0) return JF_ERR_BAD_DESC;   // only layer 0 may carry the chart
+        const int expect = (L.hh_iter > 0 ? L.hh_iter * 3 : 0) + 1;
+        if (expect != L.n_params) return JF_ERR_BAD_DESC;
+        FvmLayerC& c = g.layers[l];
+        c.add_rotation = L.hh_iter > 0; c.hh_iter = L.hh_iter; c.first = L.first; c.raw_off = L.param_offset;
+        c.z_sign = L.z_sign; c.min_kappa = L.min_kappa;
+    }
+    const int threads = 256;
+    const int64_t blocks = (g.a.B + threads - 1) / threads;
+    if (direction == JF_DIR_LOGPDF) s2_chain_kernel<T, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, 0, st>>>(g);
+    else s2_chain_kernel<T, JF_DIR_SAMPLE><<<(unsigned)blocks, threads, 0, st>>>(g);
+    return check_launch();
+}
+
+template <typename T>
+static int subpdf_apply_t(const JfSubPdfDesc* desc, int direction, const void* in, int64_t ld_in, const void* params,
+                          int64_t sp, int64_t sr, const void* logdet_in, void* logdet_out, const void* logbase_in,
+                          void* logbase_out, void* out, int64_t ld_out, void* emb_out, int64_t ld_emb, int64_t B,
+                          int32_t* status, cudaStream_t st) {
+    if (desc->manifold == 'e') {
+        GfChainArgs<T> g;
+        fill_common<T>(g.a, desc, in, ld_in, params, sp, sr, logdet_in, logdet_out, logbase_in, logbase_out, out, ld_out,
+                       emb_out, ld_emb, B, status);
+        return apply_gf<T>(desc, direction, g, st);
+    }
+    if (desc->manifold == 's') {
+        S2Args<T> g;
+        fill_common<T>(g.a, desc, in, ld_in, params, sp, sr, logdet_in, logdet_out, logbase_in, logbase_out, out, ld_out,
+                       emb_out, ld_emb, B, status);
+        return apply_s2<T>(desc, direction, g, st);
+    }
+    return JF_ERR_UNSUPPORTED;
+}
+
+extern "C" int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int direction, const void* in, int64_t ld_in,
+                               const void* params, int64_t p_stride_param, int64_t p_stride_row, const void* logdet_in,
+                               void* logdet_out, const void* logbase_in, void* logbase_out, void* out, int64_t ld_out,
+                               void* emb_out, int64_t ld_emb, int64_t B, int32_t* status, void* stream) {
+    if (desc == nullptr || in == nullptr || out == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
+    if (direction != JF_DIR_LOGPDF && direction != JF_DIR_SAMPLE) return JF_ERR_BAD_ARG;
+    if (desc->n_params > 0 && params == nullptr) return JF_ERR_BAD_ARG;
+    if (B < 0 || B > (int64_t)2147483647 * 256) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return subpdf_apply_t<double>(desc, direction, in, ld_in, params, p_stride_param, p_stride_row, logdet_in,
+                                      logdet_out, logbase_in, logbase_out, out, ld_out, emb_out, ld_emb, B, status, st);
+    if (dtype == JF_F32)
+        return subpdf_apply_t<float>(desc, direction, in, ld_in, params, p_stride_param, p_stride_row, logdet_in,
+                                     logdet_out, logbase_in, logbase_out, out, ld_out, emb_out, ld_emb, B, status, st);
+    return JF_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// jf_mlp_forward
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int TM>
+static int launch_mlp(const MlpArgs<T>& m, size_t smem, cudaStream_t st) {
+    JF_CUDA_OK(cudaFuncSetAttribute(mlp_kernel<T, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (m.B + TM - 1) / TM;
+    mlp_kernel<T, TM><<<(unsigned)blocks, 256, smem, st>>>(m);
+    return check_launch();
+}
+
+template <typename T>
+static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, const int64_t* seg_ld,
+                         const void* const* weights_t, const void* const* biases, void* out, int64_t so_p, int64_t so_r,
+                         int64_t B, cudaStream_t st) {
+    MlpArgs<T> m;
+    memset(&m, 0, sizeof(m));
+    m.n_linear = desc->n_linear;
+    int maxd = 0, in_sum = 0;
+    for (int l = 0; l <= desc->n_linear; ++l) {
+        if (desc->dims[l] < 1) return JF_ERR_BAD_DESC;
+        m.dims[l] = desc->dims[l];
+        if (l < desc->n_linear) maxd = desc->dims[l] > maxd ? desc->dims[l] : maxd;   // tiles hold input + hidden acts
+    }
+    m.n_segments = desc->n_segments;
+    for (int s = 0; s < desc->n_segments; ++s) {
+        m.seg_cols[s] = desc->seg_cols[s];
+        m.seg_ptr[s] = (const T*)seg_ptrs[s];
+        m.seg_ld[s] = seg_ld[s];
+        in_sum += desc->seg_cols[s];
+        if (seg_ptrs[s] == nullptr || desc->seg_cols[s] < 1) return JF_ERR_BAD_ARG;
+    }
+    if (in_sum != desc->dims[0]) return JF_ERR_BAD_DESC;
+    for (int l = 0; l < desc->n_linear; ++l) {
+        m.wt[l] = (const T*)weights_t[l];
+        m.bias[l] = (const T*)biases[l];
+        if (m.wt[l] == nullptr || m.bias[l] == nullptr) return JF_ERR_BAD_ARG;
+    }
+    m.out = (T*)out; m.so_p = so_p; m.so_r = so_r; m.B = B;
+    m.lda = maxd | 1;
+    auto need = [&](int tm) { return (size_t)(2 * tm * m.lda + kMlpKC * kMlpTN) * sizeof(T); };
+    const size_t cap = 200 * 1024;
+    if (need(64) <= cap) return launch_mlp<T, 64>(m, need(64), st);
+    if (need(32) <= cap) return launch_mlp<T, 32>(m, need(32), st);
+    if (need(16) <= cap) return launch_mlp<T, 16>(m, need(16), st);
+    return JF_ERR_UNSUPPORTED;
+}
+
+extern "C" int jf_mlp_forward(const JfMlpDesc* desc, int dtype, const void* const* seg_ptrs, const int64_t* seg_ld,
+                              const void* const* weights_t, const void* const* biases, void* out,
+                              int64_t out_stride_param, int64_t out_stride_row, int64_t B, void* stream) {
+    if (desc == nullptr || out == nullptr || seg_ptrs == nullptr || seg_ld == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_linear < 1 || desc->n_linear > JF_MAX_MLP_LINEAR) return JF_ERR_BAD_DESC;
+    if (desc->n_segments < 1 || desc->n_segments > JF_MAX_MLP_SEGMENTS) return JF_ERR_BAD_DESC;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return mlp_forward_t<double>(desc, seg_ptrs, seg_ld, weights_t, biases, out, out_stride_param, out_stride_row, B, st);
+    if (dtype == JF_F32)
+        return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights_t, biases, out, out_stride_param, out_stride_row, B, st);
+    return JF_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// whole-pdf orchestration (chunked; every launch on the caller's stream)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void combine_kernel(const T* a, const T* b, T sign_b, T* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + sign_b * b[i];
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static inline size_t esize(int dtype) { return dtype == JF_F64 ? 8 : 4; }
+
+struct WsLayout {
+    int64_t params, emb[JF_MAX_SUBPDFS], logdet, logbase, scratch, total;
+};
+
+static int ws_layout(const JfPdfDesc* d, int64_t chunk, WsLayout& w) {
+    if (d == nullptr || d->abi_version != JF_ABI_VERSION) return JF_ERR_BAD_DESC;
+    if (d->n_sub < 1 || d->n_sub > JF_MAX_SUBPDFS || chunk < 1) return JF_ERR_BAD_DESC;
+    const int64_t es = (int64_t)esize(d->dtype);
+    int64_t off = 0;
+    int pmax = 0;
+    for (int k = 0; k < d->n_sub; ++k)
+        if (d->has_mlp[k] && d->sub[k].n_params > pmax) pmax = d->sub[k].n_params;
+    w.params = off; off = align_up(off + (int64_t)pmax * chunk * es, 256);
+    for (int k = 0; k < d->n_sub; ++k) {
+        w.emb[k] = off;
+        if (d->sub[k].manifold != 'e') off = align_up(off + (int64_t)d->emb_dim[k] * chunk * es, 256);
+    }
+    w.logdet = off; off = align_up(off + chunk * es, 256);
+    w.logbase = off; off = align_up(off + chunk * es, 256);
+    const int maxcols = d->total_base_dim > d->total_target_dim ? d->total_base_dim : d->total_target_dim;
+    w.scratch = off; off = align_up(off + (int64_t)maxcols * chunk * es, 256);
+    w.total = off;
+    return JF_OK;
+}
+
+extern "C" int64_t jf_pdf_workspace_bytes(const JfPdfDesc* desc, int64_t chunk_rows) {
+    WsLayout w;
+    if (ws_layout(desc, chunk_rows, w) != JF_OK) return -1;
+    return w.total;
+}
+
+// direction-generic chunk loop.  `src` = x (logpdf) or z (sample); `dst` = base (logpdf) or x (sample).
+static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, const void* src, int64_t ld_src,
+                   const void* cond, int64_t ldc, void* dst, int64_t ld_dst, void* logp, void* logp_base, int64_t B,
+                   void* workspace, int64_t ws_bytes, int64_t chunk, int32_t* status, cudaStream_t st) {
+    WsLayout w;
+    int rc = ws_layout(d, chunk, w);
+    if (rc != JF_OK) return rc;
+    if (P == nullptr || src == nullptr || (d->cond_dim > 0 && cond == nullptr)) return JF_ERR_BAD_ARG;
+    if (workspace == nullptr || ws_bytes < w.total) return JF_ERR_WORKSPACE;
+    const int64_t es = (int64_t)esize(d->dtype);
+    char* ws = (char*)workspace;
+    const bool logpdf = direction == JF_DIR_LOGPDF;
+    for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+        const int64_t n = (B - r0 < chunk) ? (B - r0) : chunk;
+        const char* src_c = (const char*)src + r0 * ld_src * es;
+        char* dst_c;
+        int64_t ld_dst_c;
+        if (dst != nullptr) { dst_c = (char*)dst + r0 * ld_dst * es; ld_dst_c = ld_dst; }
+        else { dst_c = ws + w.scratch; ld_dst_c = logpdf ? d->total_base_dim : d->total_target_dim; }
+        // target-space coordinates of this chunk (input for logpdf, output for sampling): source of 'e' embeddings
+        const char* tgt_c = logpdf ? src_c : dst_c;
+        const int64_t ld_tgt = logpdf ? ld_src : ld_dst_c;
+        void* logdet = ws + w.logdet;
+        void* logbase = ws + w.logbase;
+        for (int k = 0; k < d->n_sub; ++k) {
+            const JfSubPdfDesc* sp = &d->sub[k];
+            const void* params = P->shared[k];
+            int64_t sj = 1, sr = 0;
+            if (d->has_mlp[k]) {
+                JfMlpDesc md = d->mlp[k];
+                const void* seg_ptr[JF_MAX_MLP_SEGMENTS];
+                int64_t seg_ld[JF_MAX_MLP_SEGMENTS];
+                int ns = 0;
+                if (d->cond_dim > 0) {
+                    md.seg_cols[ns] = d->cond_dim;
+                    seg_ptr[ns] = (const char*)cond + r0 * ldc * es;
+                    seg_ld[ns] = ldc;
+                    ++ns;
+                }
+                for (int j = 0; j < k; ++j) {
+                    if (ns >= JF_MAX_MLP_SEGMENTS) return JF_ERR_UNSUPPORTED;
+                    md.seg_cols[ns] = d->emb_dim[j];
+                    if (d->sub[j].manifold == 'e') {
+                        seg_ptr[ns] = tgt_c + (int64_t)d->target_col[j] * es;
+                        seg_ld[ns] = ld_tgt;
+                    } else {
+                        seg_ptr[ns] = ws + w.emb[j];
+                        seg_ld[ns] = d->emb_dim[j];
+                    }
+                    ++ns;
+                }
+                md.n_segments = ns;
+                rc = jf_mlp_forward(&md, d->dtype, seg_ptr, seg_ld, P->weights_t[k], P->biases[k], ws + w.params, chunk, 1,
+                                    n, st);
+                if (rc != JF_OK) return rc;
+                params = ws + w.params;
+                sj = chunk;
+                sr = 1;
+            } else if (sp->n_params > 0 && params == nullptr) {
+                return JF_ERR_BAD_ARG;
+            }
+            const int in_col = logpdf ? d->target_col[k] : d->base_col[k];
+            const int out_col = logpdf ? d->base_col[k] : d->target_col[k];
+            bool need_emb = false;
+            for (int j = k + 1; j < d->n_sub; ++j) need_emb = need_emb || d->has_mlp[j];
+            void* emb = (need_emb && sp->manifold != 'e') ? (void*)(ws + w.emb[k]) : nullptr;
+            rc = jf_subpdf_apply(sp, d->dtype, direction, src_c + (int64_t)in_col * es, ld_src, params, sj, sr,
+                                 k == 0 ? nullptr : logdet, logdet, k == 0 ? nullptr : logbase, logbase,
+                                 dst_c + (int64_t)out_col * es, ld_dst_c, emb, d->emb_dim[k], n, status, st);
+            if (rc != JF_OK) return rc;
+        }
+        // log p = log N(base) + logdet (log_pdf direction) / log N(z) - logdet (sampling direction)
+        if (logp != nullptr) {
+            const unsigned blocks = (unsigned)((n + 255) / 256);
+            if (d->dtype == JF_F64)
+                combine_kernel<double><<<blocks, 256, 0, st>>>((const double*)logbase, (const double*)logdet,
+                                                               logpdf ? 1.0 : -1.0, (double*)logp + r0, n);
+            else
+                combine_kernel<float><<<blocks, 256, 0, st>>>((const float*)logbase, (const float*)logdet,
+                                                              logpdf ? 1.f : -1.f, (float*)logp + r0, n);
+            rc = check_launch();
+            if (rc != JF_OK) return rc;
+        }
+        if (logp_base != nullptr)
+            JF_CUDA_OK(cudaMemcpyAsync((char*)logp_base + r0 * es, logbase, n * es, cudaMemcpyDeviceToDevice, st));
+    }
+    return JF_OK;
+}
+
+extern "C" int jf_pdf_logpdf(const JfPdfDesc* desc, const JfPdfParams* params, const void* x, int64_t ldx,
+                             const void* cond, int64_t ldc, void* logp, void* logp_base, void* base, int64_t ld_base,
+                             int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows, int32_t* status,
+                             void* stream) {
+    return pdf_run(desc, params, JF_DIR_LOGPDF, x, ldx, cond, ldc, base, ld_base, logp, logp_base, B, workspace,
+                   workspace_bytes, chunk_rows, status, (cudaStream_t)stream);
+}
+
+extern "C" int jf_pdf_sample(const JfPdfDesc* desc, const JfPdfParams* params, const void* z, int64_t ldz,
+                             const void* cond, int64_t ldc, void* x, int64_t ldx, void* logp, void* logp_base, int64_t B,
+                             void* workspace, int64_t workspace_bytes, int64_t chunk_rows, int32_t* status, void* stream) {
+    return pdf_run(desc, params, JF_DIR_SAMPLE, z, ldz, cond, ldc, x, ldx, logp, logp_base, B, workspace,
+                   workspace_bytes, chunk_rows, status, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host-buffer entries: H2D -> kernels -> D2H pipelined over two streams, two buffer sets
+// ---------------------------------------------------------------------------------------------------------------------
+struct HostWs {
+    int64_t src, cond, dst, logp, logp_base, inner, per_set, total;
+};
+
+static int host_ws_layout(const JfPdfDesc* d, int64_t chunk, HostWs& h) {
+    WsLayout w;
+    int rc = ws_layout(d, chunk, w);
+    if (rc != JF_OK) return rc;
+    const int64_t es = (int64_t)esize(d->dtype);
+    const int maxcols = d->total_base_dim > d->total_target_dim ? d->total_base_dim : d->total_target_dim;
+    int64_t off = 0;
+    h.src = off; off = align_up(off + (int64_t)maxcols * chunk * es, 256);
+    h.cond = off; off = align_up(off + (int64_t)(d->cond_dim > 0 ? d->cond_dim : 1) * chunk * es, 256);
+    h.dst = off; off = align_up(off + (int64_t)maxcols * chunk * es, 256);
+    h.logp = off; off = align_up(off + chunk * es, 256);
+    h.logp_base = off; off = align_up(off + chunk * es, 256);
+    h.inner = off; off = align_up(off + w.total, 256);
+    h.per_set = off;
+    h.total = 2 * off;
+    return JF_OK;
+}
+
+extern "C" int64_t jf_pdf_host_workspace_bytes(const JfPdfDesc* desc, int64_t chunk_rows) {
+    HostWs h;
+    if (host_ws_layout(desc, chunk_rows, h) != JF_OK) return -1;
+    return h.total;
+}
+
+static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction, const void* src_h, int64_t ld_src,
+                        const void* cond_h, int64_t ldc, void* dst_h, int64_t ld_dst, void* logp_h, void* logp_base_h,
+                        int64_t B, void* workspace, int64_t ws_bytes, int64_t chunk, int32_t* status) {
+    HostWs h;
+    int rc = host_ws_layout(d, chunk, h);
+    if (rc != JF_OK) return rc;
+    if (workspace == nullptr || ws_bytes < h.total) return JF_ERR_WORKSPACE;
+    if (src_h == nullptr || (d->cond_dim > 0 && cond_h == nullptr)) return JF_ERR_BAD_ARG;
+    WsLayout w;
+    ws_layout(d, chunk, w);
+    const int64_t es = (int64_t)esize(d->dtype);
+    const bool logpdf = direction == JF_DIR_LOGPDF;
+    const int src_cols = logpdf ? d->total_target_dim : d->total_base_dim;
+    const int dst_cols = logpdf ? d->total_base_dim : d->total_target_dim;
+    cudaStream_t st[2];
+    JF_CUDA_OK(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
+    JF_CUDA_OK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+    int64_t ci = 0;
+    for (int64_t r0 = 0; r0 < B && rc == JF_OK; r0 += chunk, ++ci) {
+        const int64_t n = (B - r0 < chunk) ? (B - r0) : chunk;
+        const int b = (int)(ci & 1);
+        char* set = (char*)workspace + (int64_t)b * h.per_set;
+        cudaStream_t s = st[b];
+        cudaError_t e = cudaMemcpy2DAsync(set + h.src, (size_t)src_cols * es, (const char*)src_h + r0 * ld_src * es,
+                                          (size_t)ld_src * es, (size_t)src_cols * es, (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && d->cond_dim > 0)
+            e = cudaMemcpy2DAsync(set + h.cond, (size_t)d->cond_dim * es, (const char*)cond_h + r0 * ldc * es,
+                                  (size_t)ldc * es, (size_t)d->cond_dim * es, (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+        rc = pdf_run(d, P, direction, set + h.src, src_cols, d->cond_dim > 0 ? set + h.cond : nullptr, d->cond_dim,
+                     set + h.dst, dst_cols, set + h.logp, logp_base_h ? set + h.logp_base : nullptr, n, set + h.inner,
+                     w.total, chunk, status, s);
+        if (rc != JF_OK) break;
+        if (dst_h != nullptr)
+            e = cudaMemcpy2DAsync((char*)dst_h + r0 * ld_dst * es, (size_t)ld_dst * es, set + h.dst, (size_t)dst_cols * es,
+                                  (size_t)dst_cols * es, (size_t)n, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && logp_h != nullptr)
+            e = cudaMemcpyAsync((char*)logp_h + r0 * es, set + h.logp, n * es, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && logp_base_h != nullptr)
+            e = cudaMemcpyAsync((char*)logp_base_h + r0 * es, set + h.logp_base, n * es, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+    }
+    cudaError_t e0 = cudaStreamSynchronize(st[0]);
+    cudaError_t e1 = cudaStreamSynchronize(st[1]);
+    cudaStreamDestroy(st[0]);
+    cudaStreamDestroy(st[1]);
+    if (rc != JF_OK) return rc;
+    if (e0 != cudaSuccess) return (int)e0;
+    if (e1 != cudaSuccess) return (int)e1;
+    return JF_OK;
+}
+
+extern "C" int jf_pdf_logpdf_host(const JfPdfDesc* desc, const JfPdfParams* params, const void* x_host, int64_t ldx,
+                                  const void* cond_host, int64_t ldc, void* logp_host, void* logp_base_host,
+                                  void* base_host, int64_t ld_base, int64_t B, void* workspace, int64_t workspace_bytes,
+                                  int64_t chunk_rows, int32_t* status) {
+    return pdf_run_host(desc, params, JF_DIR_LOGPDF, x_host, ldx, cond_host, ldc, base_host, ld_base, logp_host,
+                        logp_base_host, B, workspace, workspace_bytes, chunk_rows, status);
+}
+
+extern "C" int jf_pdf_sample_host(const JfPdfDesc* desc, const JfPdfParams* params, const void* z_host, int64_t ldz,
+                                  const void* cond_host, int64_t ldc, void* x_host, int64_t ldx, void* logp_host,
+                                  void* logp_base_host, int64_t B, void* workspace, int64_t workspace_bytes,
+                                  int64_t chunk_rows, int32_t* status) {
+    return pdf_run_host(desc, params, JF_DIR_SAMPLE, z_host, ldz, cond_host, ldc, x_host, ldx, logp_host, logp_base_host,
+                        B, workspace, workspace_bytes, chunk_rows, status);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int jf_abi_version(void) { return JF_ABI_VERSION; }
+extern "C" int64_t jf_launch_count(void) { return g_launches.load(); }
+extern "C" int64_t jf_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(JfLayerDesc);
+        case 1: return sizeof(JfSubPdfDesc);
+        case 2: return sizeof(JfMlpDesc);
+        case 3: return sizeof(JfPdfDesc);
+        case 4: return sizeof(JfPdfParams);
+        default: return -1;
+    }
+}
+
+template <typename T>
+__global__ void fma_probe_kernel(T* out, int iters, T a, T b) {
+    T acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = T(threadIdx.x) * T(1e-3) + T(i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    if (s == T(12345.678)) out[0] = s;
+}
+
+extern "C" int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* stream) {
+    if (ms == nullptr || fma_count == nullptr || iters < 1) return JF_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    JF_CUDA_OK(cudaGetDevice(&dev));
+    JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    void* buf = nullptr;
+    JF_CUDA_OK(cudaMalloc(&buf, 256));   // diagnostics only; the compute entry points never allocate
+    const int threads = 512, grid = sms * 4;
+    cudaEvent_t e0, e1;
+    JF_CUDA_OK(cudaEventCreate(&e0));
+    JF_CUDA_OK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; ++rep) {   // first pass warms up
+        JF_CUDA_OK(cudaEventRecord(e0, st));
+        if (dtype == JF_F64) fma_probe_kernel<double><<<grid, threads, 0, st>>>((double*)buf, iters, 1.0000001, 1e-9);
+        else fma_probe_kernel<float><<<grid, threads, 0, st>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+        check_launch();
+        JF_CUDA_OK(cudaEventRecord(e1, st));
+        JF_CUDA_OK(cudaEventSynchronize(e1));
+    }
+    JF_CUDA_OK(cudaEventElapsedTime(ms, e0, e1));
+    *fma_count = (double)grid * threads * (double)iters * 8.0;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return JF_OK;
+}

@@ -1,0 +1,118 @@
+// Parameter-generator MLP: params = W_L tanh(... tanh(W_1 [cond | embeddings] + b_1) ...) + b_L
+// (reference main/default.py:654-670, called at :956 / :1438).
+//
+// v1 kernel: one CTA owns TM rows end to end (input gather -> every Linear+tanh in shared memory -> last Linear
+// streamed to the caller's parameter buffer), so hidden activations never touch HBM.  The last layer writes
+// "param-major" ([P, rows]) so the consuming layer kernel reads coalesced.
+#pragma once
+#include "common.cuh"
+
+namespace jf {
+
+template <typename T>
+struct MlpArgs {
+    int n_linear;
+    int dims[JF_MAX_MLP_LINEAR + 1];
+    int n_segments;
+    int seg_cols[JF_MAX_MLP_SEGMENTS];
+    const T* seg_ptr[JF_MAX_MLP_SEGMENTS];
+    int64_t seg_ld[JF_MAX_MLP_SEGMENTS];
+    const T* wt[JF_MAX_MLP_LINEAR];   // [in, out] row-major
+    const T* bias[JF_MAX_MLP_LINEAR];
+    T* out; int64_t so_p, so_r;       // out[j*so_p + row*so_r]
+    int64_t B;
+    int lda;                          // odd leading dimension of the activation tiles
+};
+
+constexpr int kMlpTN = 64;   // output columns per pass
+constexpr int kMlpKC = 32;   // k-chunk of the weight tile
+
+template <typename T, int TM>
+__global__ void __launch_bounds__(256) mlp_kernel(const __grid_constant__ MlpArgs<T> m) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* act0 = reinterpret_cast<T*>(smem_raw);
+    T* act1 = act0 + (size_t)TM * m.lda;
+    T* sW = act1 + (size_t)TM * m.lda;   // [kMlpKC][kMlpTN]
+    constexpr int RPT = TM / 16;          // rows per thread
+    const int tid = threadIdx.x;
+    const int tx = tid & 15;              // row lane: rows tx + 16*i
+    const int ty = tid >> 4;              // column group: cols ty*4 .. ty*4+3
+    const int64_t row0 = (int64_t)blockIdx.x * TM;
+
+    // gather the concatenated input rows
+    {
+        const int in_dim = m.dims[0];
+        for (int e = tid; e < TM * in_dim; e += blockDim.x) {
+            const int r = e / in_dim;
+            int c = e - r * in_dim;
+            const int64_t row = row0 + r;
+            T v = 0;
+            if (row < m.B) {
+                int s = 0;
+                while (c >= m.seg_cols[s]) { c -= m.seg_cols[s]; ++s; }
+                v = m.seg_ptr[s][row * m.seg_ld[s] + c];
+            }
+            act0[(size_t)r * m.lda + (e - r * in_dim)] = v;
+        }
+    }
+    __syncthreads();
+
+    T* src = act0;
+    T* dst = act1;
+    for (int l = 0; l < m.n_linear; ++l) {
+        const int Kin = m.dims[l], N = m.dims[l + 1];
+        const bool last = (l == m.n_linear - 1);
+        const T* __restrict__ W = m.wt[l];
+        for (int n0 = 0; n0 < N; n0 += kMlpTN) {
+            T acc[RPT][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int n = n0 + ty * 4 + c;
+                const T b = (n < N) ? m.bias[l][n] : T(0);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) acc[i][c] = b;
+            }
+            for (int k0 = 0; k0 < Kin; k0 += kMlpKC) {
+                __syncthreads();   // previous tile fully consumed
+                for (int e = tid; e < kMlpKC * kMlpTN; e += blockDim.x) {
+                    const int kk = e / kMlpTN, nn = e - kk * kMlpTN;
+                    const int k = k0 + kk, n = n0 + nn;
+                    sW[e] = (k < Kin && n < N) ? W[(size_t)k * N + n] : T(0);
+                }
+                __syncthreads();
+                const int kend = min(kMlpKC, Kin - k0);
+#pragma unroll 4
+                for (int kk = 0; kk < kend; ++kk) {
+                    T bv[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) bv[c] = sW[kk * kMlpTN + ty * 4 + c];
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        const T av = src[(size_t)(tx + 16 * i) * m.lda + k0 + kk];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[i][c] = fma(av, bv[c], acc[i][c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int r = tx + 16 * i;
+                const int64_t row = row0 + r;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int n = n0 + ty * 4 + c;
+                    if (n >= N) continue;
+                    if (last) {
+                        if (row < m.B) m.out[(int64_t)n * m.so_p + row * m.so_r] = acc[i][c];
+                    } else {
+                        dst[(size_t)r * m.lda + n] = tanh(acc[i][c]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        T* t = src; src = dst; dst = t;
+    }
+}
+
+}  // namespace jf

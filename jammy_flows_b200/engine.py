@@ -1,0 +1,306 @@
+"""Host-side dispatch: compiles a `pdf` into the C-ABI descriptors and launches the sm_100a kernels.
+
+PyTorch is used for device memory (torch.empty), the current CUDA stream and, later, torch.distributed -- plumbing
+only.  Every number comes out of libjammy_b200.so; nothing here computes layer math and nothing falls back to
+eager PyTorch or the CPU.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+
+_DT = {torch.float32: _cabi.JF_F32, torch.float64: _cabi.JF_F64}
+DEFAULT_CHUNK_ROWS = 1 << 19
+
+_workspaces = {}
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "jammy_flows_b200: %s lives on '%s'. The hot path only exists as sm_100a CUDA kernels -- move the model and "
+            "its inputs to a CUDA device (there is no CPU fallback)." % (what, t.device))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# descriptors
+# ---------------------------------------------------------------------------------------------------------------------
+def fill_layer_desc(ld, desc, param_offset):
+    """python layer descriptor dict (layers.*.descriptor()) -> JfLayerDesc"""
+    ld.dim = desc["dim"]
+    ld.n_params = desc["n_params"]
+    ld.param_offset = param_offset
+    if desc["code"] == "g":
+        ld.kind = _cabi.JF_LAYER_GF
+        ld.K = desc["num_kde"]
+        ld.hh_iter = desc["hh_iter"]
+        ld.inv_type = desc["inv_type"]
+        ld.norm_mode = (_cabi.JF_NORM_NONE if not desc["fit_normalization"] else
+                        (_cabi.JF_NORM_REGULATED if desc["regulate_normalization"] else _cabi.JF_NORM_RAW))
+        ld.has_offset = desc["model_offset"]
+        ld.w_min, ld.w_max, ld.n_min, ld.n_max = desc["w_min"], desc["w_max"], desc["n_min"], desc["n_max"]
+    elif desc["code"] == "f":
+        ld.kind = _cabi.JF_LAYER_FVM
+        ld.hh_iter = desc["hh_iter"] if desc["add_rotation"] else 0
+        ld.first = desc["first"]
+        ld.z_sign = desc["z_sign"]
+        ld.min_kappa = desc["min_kappa"]
+    else:
+        raise NotImplementedError("no sm_100a kernel for layer code %r" % desc["code"])
+
+
+def fill_subpdf_desc(sd, manifold, dim, layer_descs):
+    if len(layer_descs) > _cabi.JF_MAX_LAYERS:
+        raise NotImplementedError("more than %d layers in one sub-pdf" % _cabi.JF_MAX_LAYERS)
+    sd.manifold = ord(manifold)
+    sd.dim = dim
+    sd.n_layers = len(layer_descs)
+    off = 0
+    for i, d in enumerate(layer_descs):
+        fill_layer_desc(sd.layers[i], d, off)
+        off += d["n_params"]
+    sd.n_params = off
+
+
+def compile_pdf(pdf, dtype):
+    """`pdf` -> JfPdfDesc (static structure only; parameter pointers are gathered per call)."""
+    if len(pdf.layer_list) > _cabi.JF_MAX_SUBPDFS:
+        raise NotImplementedError("more than %d sub-pdfs" % _cabi.JF_MAX_SUBPDFS)
+    d = _cabi.JfPdfDesc()
+    d.abi_version = _cabi.JF_ABI_VERSION
+    d.dtype = _DT[dtype]
+    d.n_sub = len(pdf.layer_list)
+    d.cond_dim = int(pdf.conditional_input_dim or 0)
+    d.total_target_dim = pdf.total_target_dim
+    d.total_base_dim = pdf.total_base_dim
+    for k, layers in enumerate(pdf.layer_list):
+        manifold = pdf.pdf_defs_list[k][0]
+        fill_subpdf_desc(d.sub[k], manifold, layers[0].dimension, [l.descriptor() for l in layers])
+        d.target_col[k] = pdf.target_dim_indices[k][0]
+        d.base_col[k] = pdf.base_dim_indices[k][0]
+        d.emb_dim[k] = layers[-1]._embedding_conditional_return_num()
+        mlp = pdf.mlp_predictors[k]
+        d.has_mlp[k] = 0 if mlp is None else 1
+        if mlp is not None:
+            linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
+            if len(linears) > _cabi.JF_MAX_MLP_LINEAR:
+                raise NotImplementedError("MLP deeper than %d Linear layers" % _cabi.JF_MAX_MLP_LINEAR)
+            d.mlp[k].n_linear = len(linears)
+            d.mlp[k].dims[0] = linears[0].in_features
+            for i, lin in enumerate(linears):
+                d.mlp[k].dims[i + 1] = lin.out_features
+    return d
+
+
+class ParamPack:
+    """Device pointers of one call (keeps the temporaries alive until the call has been enqueued)."""
+
+    def __init__(self, pdf, dtype, device):
+        self.keep = []
+        self.c = _cabi.JfPdfParams()
+        for k, layers in enumerate(pdf.layer_list):
+            mlp = pdf.mlp_predictors[k]
+            if mlp is None:
+                vecs = [l.packed_permanent_params() for l in layers]
+                vecs = [v for v in vecs if v is not None]
+                if len(vecs) > 0:
+                    vec = torch.cat([v.detach().to(device=device, dtype=dtype) for v in vecs]).contiguous()
+                    _require_cuda(vec, "parameters of sub-pdf %d" % k)
+                    self.keep.append(vec)
+                    self.c.shared[k] = vec.data_ptr()
+            else:
+                linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
+                for i, lin in enumerate(linears):
+                    wt = lin.weight.detach().to(device=device, dtype=dtype).t().contiguous()
+                    b = lin.bias.detach().to(device=device, dtype=dtype).contiguous()
+                    _require_cuda(wt, "MLP weights of sub-pdf %d" % k)
+                    self.keep += [wt, b]
+                    self.c.weights_t[k][i] = wt.data_ptr()
+                    self.c.biases[k][i] = b.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole-pdf calls
+# ---------------------------------------------------------------------------------------------------------------------
+def _prep_inputs(pdf, t, cond, what):
+    _require_cuda(t, what)
+    if t.dtype not in _DT:
+        raise TypeError("jammy_flows_b200 supports float32/float64, got %s" % t.dtype)
+    if t.dim() != 2:
+        raise ValueError("%s must be 2-dimensional (B, D)" % what)
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    if cond is not None:
+        if isinstance(cond, (list, tuple)):
+            raise NotImplementedError("per-sub-pdf conditional inputs (list) are not built yet")
+        _require_cuda(cond, "conditional_input")
+        assert cond.dtype == t.dtype and cond.device == t.device
+        if cond.stride(1) != 1:
+            cond = cond.contiguous()
+    return t, cond
+
+
+def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True):
+    """-> (log_pdf [B], log_pdf_base [B], base [B, D_base]) on x's device.  Reference: main/default.py:1059-1117."""
+    lib = _cabi.load()
+    x, cond = _prep_inputs(pdf, x, cond, "x")
+    B = x.shape[0]
+    dev, dt = x.device, x.dtype
+    desc = pdf._desc(dt)
+    chunk = int(chunk_rows or min(max(B, 1), DEFAULT_CHUNK_ROWS))
+    nbytes = lib.jf_pdf_workspace_bytes(C.byref(desc), chunk)
+    ws = _workspace(dev, nbytes)
+    logp = torch.empty(B, dtype=dt, device=dev)
+    logp_base = torch.empty(B, dtype=dt, device=dev)
+    base = torch.empty(B, pdf.total_base_dim, dtype=dt, device=dev) if want_base else None
+    pack = ParamPack(pdf, dt, dev)
+    status = pdf._status(dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_pdf_logpdf(C.byref(desc), C.byref(pack.c), _ptr(x), x.stride(0), _ptr(cond),
+                               cond.stride(0) if cond is not None else 0, _ptr(logp), _ptr(logp_base), _ptr(base),
+                               pdf.total_base_dim, B, _ptr(ws), ws.numel(), chunk, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_pdf_logpdf")
+    return logp, logp_base, base
+
+
+def pdf_sample(pdf, z, cond=None, chunk_rows=None):
+    """z [B, D_base] -> (x [B, D], log_pdf [B], log_pdf_base [B]).  Reference: main/default.py:1373-1531, :1533-1707."""
+    lib = _cabi.load()
+    z, cond = _prep_inputs(pdf, z, cond, "base sample")
+    B = z.shape[0]
+    dev, dt = z.device, z.dtype
+    desc = pdf._desc(dt)
+    chunk = int(chunk_rows or min(max(B, 1), DEFAULT_CHUNK_ROWS))
+    nbytes = lib.jf_pdf_workspace_bytes(C.byref(desc), chunk)
+    ws = _workspace(dev, nbytes)
+    x = torch.empty(B, pdf.total_target_dim, dtype=dt, device=dev)
+    logp = torch.empty(B, dtype=dt, device=dev)
+    logp_base = torch.empty(B, dtype=dt, device=dev)
+    pack = ParamPack(pdf, dt, dev)
+    status = pdf._status(dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_pdf_sample(C.byref(desc), C.byref(pack.c), _ptr(z), z.stride(0), _ptr(cond),
+                               cond.stride(0) if cond is not None else 0, _ptr(x), pdf.total_target_dim, _ptr(logp),
+                               _ptr(logp_base), B, _ptr(ws), ws.numel(), chunk, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_pdf_sample")
+    return x, logp, logp_base
+
+
+def _host_call(pdf, direction, src, cond, chunk_rows, device):
+    """HOST tensors in, HOST tensors out (pinned): the end-to-end path with copies inside the library call."""
+    lib = _cabi.load()
+    assert not src.is_cuda
+    dt = src.dtype
+    dev = torch.device(device)
+    B = src.shape[0]
+    desc = pdf._desc(dt)
+    chunk = int(chunk_rows or min(max(B, 1), 1 << 18))
+    nbytes = lib.jf_pdf_host_workspace_bytes(C.byref(desc), chunk)
+    ws = _workspace(dev, nbytes)
+    pack = ParamPack(pdf, dt, dev)
+    status = pdf._status(dev)
+    pin = dict(dtype=dt, pin_memory=True)
+    logp = torch.empty(B, **pin)
+    logp_base = torch.empty(B, **pin)
+    src = src.contiguous()
+    cond = cond.contiguous() if cond is not None else None
+    with torch.cuda.device(dev):
+        if direction == _cabi.JF_DIR_LOGPDF:
+            out = torch.empty(B, pdf.total_base_dim, **pin)
+            rc = lib.jf_pdf_logpdf_host(C.byref(desc), C.byref(pack.c), _ptr(src), src.stride(0), _ptr(cond),
+                                        cond.stride(0) if cond is not None else 0, _ptr(logp), _ptr(logp_base), _ptr(out),
+                                        pdf.total_base_dim, B, _ptr(ws), ws.numel(), chunk, _ptr(status))
+        else:
+            out = torch.empty(B, pdf.total_target_dim, **pin)
+            rc = lib.jf_pdf_sample_host(C.byref(desc), C.byref(pack.c), _ptr(src), src.stride(0), _ptr(cond),
+                                        cond.stride(0) if cond is not None else 0, _ptr(out), pdf.total_target_dim,
+                                        _ptr(logp), _ptr(logp_base), B, _ptr(ws), ws.numel(), chunk, _ptr(status))
+    _cabi.check(rc, "jf_pdf_*_host")
+    return out, logp, logp_base
+
+
+def pdf_logpdf_host(pdf, x_host, cond_host=None, chunk_rows=None, device="cuda"):
+    base, logp, logp_base = _host_call(pdf, _cabi.JF_DIR_LOGPDF, x_host, cond_host, chunk_rows, device)
+    return logp, logp_base, base
+
+
+def pdf_sample_host(pdf, z_host, cond_host=None, chunk_rows=None, device="cuda"):
+    return _host_call(pdf, _cabi.JF_DIR_SAMPLE, z_host, cond_host, chunk_rows, device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# layer plugin API: a one-layer flow program (reference layers/layer_base.py:58-70)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_single_layer(layer, direction, x, log_det, extra_inputs, **kw):
+    lib = _cabi.load()
+    if len(kw) > 0 and any(v for v in kw.values()):
+        raise NotImplementedError("layer keyword arguments %s are not supported by the CUDA path yet" % list(kw))
+    _require_cuda(x, "layer input")
+    dt, dev = x.dtype, x.device
+    x = x.contiguous()
+    B = x.shape[0]
+    sd = _cabi.JfSubPdfDesc()
+    fill_subpdf_desc(sd, layer.manifold, layer.dimension, [layer.descriptor()])
+    if extra_inputs is None:
+        params = layer.packed_permanent_params().detach().to(device=dev, dtype=dt).contiguous()
+        sj, sr = 1, 0
+    else:
+        params = extra_inputs.to(dt).contiguous()
+        assert params.shape[1] == layer.total_param_num, (params.shape, layer.total_param_num)
+        if params.shape[0] == 1:
+            sj, sr = 1, 0
+        else:
+            assert params.shape[0] == B
+            sj, sr = 1, params.stride(0)
+    out = torch.empty_like(x)
+    ld_in = log_det.to(dt).contiguous() if torch.is_tensor(log_det) else None
+    ld_out = torch.empty(B, dtype=dt, device=dev)
+    status = torch.zeros(_cabi.JF_STATUS_WORDS, dtype=torch.int32, device=dev)
+    d = _cabi.JF_DIR_LOGPDF if direction == "logpdf" else _cabi.JF_DIR_SAMPLE
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_apply(C.byref(sd), _DT[dt], d, _ptr(x), x.stride(0), _ptr(params), sj, sr, _ptr(ld_in),
+                                 _ptr(ld_out), None, None, _ptr(out), out.stride(0), None, 0, B, _ptr(status),
+                                 _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_apply")
+    if not torch.is_tensor(log_det):
+        ld_out = ld_out + log_det
+    return out, ld_out
+
+
+def s2_embedding(x):
+    """(theta, phi) -> (x, y, z) through the S2 kernel's embedding output (reference sphere_base.py:305-332)."""
+    lib = _cabi.load()
+    _require_cuda(x, "s2 coordinates")
+    dt, dev = x.dtype, x.device
+    x = x.contiguous()
+    B = x.shape[0]
+    sd = _cabi.JfSubPdfDesc()
+    fill_subpdf_desc(sd, "s", 2, [dict(code="f", dim=2, add_rotation=0, hh_iter=0, z_sign=-1.0, min_kappa=1e-10,
+                                       first=0, n_params=1)])
+    params = torch.zeros(1, dtype=dt, device=dev)
+    out = torch.empty_like(x)
+    emb = torch.empty(B, 3, dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_apply(C.byref(sd), _DT[dt], _cabi.JF_DIR_LOGPDF, _ptr(x), x.stride(0), _ptr(params), 1, 0,
+                                 None, None, None, None, _ptr(out), out.stride(0), _ptr(emb), 3, B, None,
+                                 _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_apply(embedding)")
+    return emb

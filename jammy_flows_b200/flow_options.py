@@ -1,0 +1,123 @@
+"""Layer registry and option validation for the B200 hot path.
+
+Mirrors the reference registry `jammy_flows/flow_options.py:25-240` (code -> module/type/kwargs with
+`(default, validator)` pairs), `obtain_default_options` (:242-257), `check_flow_option` (:259-274) and
+`obtain_overall_flow_info` (:276-286) for the layer codes that are on the hot path.
+
+Differences, all deliberate and documented in DESIGN.md:
+  * `"n"` is accepted as an alias of `"f"` with the reference's default `"f"` options.  The README headline
+    `pdf("e4+s2+e4", "gggg+n+gggg")` (reference README.md:15-17) does not construct in the reference snapshot
+    (`flow_options.py:254` asserts) because the old "n" layer was removed; the alias keeps that call a drop-in.
+  * codes that exist in the reference but are outside the hot-path scope ("h", "c", "w", "u") raise
+    NotImplementedError at construction instead of silently falling back to anything.
+"""
+from . import layers
+
+opts_dict = dict()
+
+# --- Euclidean: Gaussianization flow (reference flow_options.py:32-54) -------------------------------------------
+opts_dict["g"] = dict(module=layers.gf_block, type="e", kwargs=dict(
+    fit_normalization=(1, [0, 1]),
+    num_householder_iter=(-1, lambda x: (x == -1) or (x > 0)),
+    num_kde=(10, lambda x: x > 0),
+    inverse_function_type=("isigmoid", ["isigmoid", "inormal_partly_precise", "inormal_full_pade", "inormal_partly_crude"]),
+    replace_first_sigmoid_with_icdf=(1, [0, 1]),
+    skip_model_offset=(0, [0, 1]),
+    softplus_for_width=(0, [0, 1]),
+    upper_bound_for_widths=(100, lambda x: (x == -1) or x > 0),
+    lower_bound_for_widths=(0.01, lambda x: x > 0),
+    upper_bound_for_norms=(10, lambda x: (x == -1) or x > 0),
+    lower_bound_for_norms=(1, lambda x: x > 0),
+    center_mean=(0, [0, 1]),
+    clamp_widths=(0, [0, 1]),
+    width_smooth_saturation=(1, [0, 1]),
+    regulate_normalization=(1, [0, 1]),
+    add_skewness=(0, [0, 1]),
+    rotation_mode=("householder", ["householder", "triangular_combination", "angles", "cayley", "none"]),
+    nonlinear_stretch_type=("classic", ["classic", "rq_splines"]),
+))
+
+# --- S2: Fisher-von-Mises scaling (+ optional spline sub-flows) (reference flow_options.py:154-180) --------------
+opts_dict["f"] = dict(module=layers.fisher_von_mises_2d, type="s", kwargs=dict(
+    add_vertical_rq_spline_flow=(0, [0, 1]),
+    add_circular_rq_spline_flow=(0, [0, 1]),
+    add_correlated_rq_spline_flow=(0, [0, 1]),
+    circular_flow_defs=("oo", lambda x: type(x) == str),
+    vertical_flow_defs=("rr", lambda x: type(x) == str),
+    correlated_max_rank=(3, lambda x: (x >= 0)),
+    inverse_z_scaling=(1, [0, 1]),
+    boundary_cos_theta_identity_region=(0.0, lambda x: ((x >= 0) & (x < 1))),
+    spline_num_basis_functions=(5, lambda x: ((x > 0) | (x == -1))),
+    vertical_smooth=(0, [0, 1]),
+    vertical_restrict_max_min_width_height_ratio=(-1.0, lambda x: (x == -1.0) or (x > 0.0)),
+    vertical_fix_boundary_derivative=(1, lambda x: [0, 1]),
+    vertical_fix_first_width_n_height_to_zero=(0, [0, 1]),
+    vertical_also_fix_second_width_to_zero=(0, [0, 1]),
+    vertical_independent_width_height_parametrization=(0, [0, 1]),
+    circular_add_rotation=(0, [0, 1]),
+    min_kappa=(1e-10, lambda x: x > 0),
+    kappa_prediction=("direct_log_real_bounded", ["direct_log_real_bounded", "softplus_real_bounded", "log_bounded",
+                                                  "mu", "mu_squared", "quatvec", "quatvec_squared"]),
+    add_extra_rotation_inbetween=(0, [0, 1]),
+    add_rotation=(1, [0, 1]),
+    rotation_mode=("householder", ["householder", "angles", "xyz", "quaternion"]),
+    kappa_clamping=(0, [0, 1]),
+    num_householder_iter=(-1, lambda x: (x == -1) or (x > 0)),
+))
+
+# "n": alias of "f" (see module docstring / SURVEY.md F2)
+opts_dict["n"] = opts_dict["f"]
+
+# Codes of the reference that are deliberately out of the hot-path scope.
+OUT_OF_SCOPE = {
+    "h": "deprecated Gaussianization flow (reference flow_options.py:56)",
+    "c": "manifold CNF needs torchdiffeq, an ODE-solver workload outside the hot path",
+    "w": "simplex flow (experimental in the reference)",
+    "u": "simplex gumbel-softmax flow",
+}
+# Codes on the SURVEY.md section 8 'next' list that are not built yet in this round.
+NOT_YET_BUILT = {
+    "t": "affine/MVN layer (SURVEY.md section 8f rank 1)",
+    "r": "interval rational-quadratic spline (section 8a row a10)",
+    "o": "circular rational-quadratic spline (section 8a row a11)",
+    "m": "Moebius S1 layer (section 8a row a14)",
+    "v": "exponential-map S2 layer (section 8a row a15)",
+    "x": "Euclidean identity layer", "y": "spherical identity layer", "z": "interval identity layer",
+}
+
+
+def _lookup(flow_abbrevation):
+    if flow_abbrevation in OUT_OF_SCOPE:
+        raise NotImplementedError("flow layer '%s' is out of the B200 hot-path scope: %s"
+                                  % (flow_abbrevation, OUT_OF_SCOPE[flow_abbrevation]))
+    if flow_abbrevation in NOT_YET_BUILT:
+        raise NotImplementedError("flow layer '%s' has no sm_100a kernel yet: %s (there is no CPU fallback)"
+                                  % (flow_abbrevation, NOT_YET_BUILT[flow_abbrevation]))
+    assert (flow_abbrevation in opts_dict.keys()), "Unknown flow abbreviation for default options: %s" % flow_abbrevation
+    return opts_dict[flow_abbrevation]
+
+
+def obtain_default_options(flow_abbrevation):
+    """Default option dict of a layer code (reference flow_options.py:242-257)."""
+    entry = _lookup(flow_abbrevation)
+    return {k: entry["kwargs"][k][0] for k in entry["kwargs"].keys()}
+
+
+def check_flow_option(flow_abbrevation, opt_name, opt_val):
+    """Validate one option against its list/lambda validator (reference flow_options.py:259-274)."""
+    entry = _lookup(flow_abbrevation)
+    assert (opt_name in entry["kwargs"].keys()), \
+        ("option name %s not found in defined options for flow %s" % (opt_name, flow_abbrevation))
+    validator = entry["kwargs"][opt_name][1]
+    if hasattr(validator, "__call__"):
+        assert (validator(opt_val)), ("Lambda function check of configured option", opt_name, " failed with value ", opt_val)
+    elif type(validator) == list:
+        assert (opt_val in validator), ("Configured option ", opt_name, " with value ", opt_val,
+                                        " not part of allowed options: ", validator)
+    else:
+        raise Exception("Unknown value check type!", type(validator))
+
+
+def obtain_overall_flow_info():
+    """code -> {type, module} (reference flow_options.py:276-286)."""
+    return {k: dict(type=opts_dict[k]["type"], module=opts_dict[k]["module"]) for k in opts_dict.keys()}

@@ -1,0 +1,517 @@
+"""`jammy_flows_b200.pdf` -- drop-in for `jammy_flows.pdf` on the hot path (log_pdf / sampling / total entropy).
+
+Mirrors the reference class `jammy_flows/main/default.py:42-151`: same constructor signature, the same string DSL
+("e4+s2+e4", "gggg+f+gggg"), the same option-override semantics, index tables, MLP wiring, parameter names/shapes
+(`layer_list.{sub}.{layer}.*`, `mlp_predictors.{k}.{0,2}.{weight,bias}`) and return tuples.  What differs is the
+execution: instead of a Python loop over layer modules issuing hundreds of eager torch ops per layer, the layer graph
+is compiled once into a static flow program (C structs, include/jammy_b200.h) and executed by fused sm_100a kernels
+through the C-ABI.  There is no CPU / eager fallback: tensors must live on a CUDA device.
+"""
+import collections
+import copy
+
+import numpy
+import torch
+from torch import nn
+
+from . import engine
+from .flow_options import check_flow_option, obtain_default_options, obtain_overall_flow_info
+
+
+def list_from_str(spec):
+    """Reference: extra_functions.py:90-94."""
+    if spec == "":
+        return []
+    return list(tuple(map(int, spec.split("-"))))
+
+
+class _NoBackward(torch.autograd.Function):
+    """Marks outputs of the inference kernels: calling backward() fails loudly instead of silently giving no grads."""
+
+    @staticmethod
+    def forward(ctx, anchor, *outs):
+        return tuple(o.view_as(o) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            "jammy_flows_b200: the backward kernels (SURVEY.md K8, training config cfg5) are not built yet; "
+            "log_pdf/sample outputs are inference-only in this round.")
+
+
+class pdf(nn.Module):
+
+    def __init__(self, pdf_defs, flow_defs, options_overwrite=dict(), conditional_input_dim=None,
+                 amortization_mlp_dims="128", predict_log_normalization=False, join_poisson_and_pdf_description=False,
+                 hidden_mlp_dims_poisson="128", rank_of_mlp_mappings_poisson=0, amortization_mlp_use_custom_mode=False,
+                 amortization_mlp_ranks=0, amortization_mlp_highway_mode=0, amortize_everything=False,
+                 use_as_passthrough_instead_of_pdf=False, skip_mlp_initialization=False, verbose=False):
+        """Same parameters as the reference constructor (main/default.py:44-100)."""
+        super().__init__()
+        not_built = []
+        if amortization_mlp_use_custom_mode:
+            not_built.append("amortization_mlp_use_custom_mode (AmortizableMLP, SURVEY.md section 8f rank 4)")
+        if amortize_everything:
+            not_built.append("amortize_everything (fully amortized pdf, section 8f rank 4)")
+        if predict_log_normalization:
+            not_built.append("predict_log_normalization (Poisson log-lambda head)")
+        if use_as_passthrough_instead_of_pdf:
+            not_built.append("use_as_passthrough_instead_of_pdf")
+        if skip_mlp_initialization:
+            not_built.append("skip_mlp_initialization")
+        if type(conditional_input_dim) == list:
+            not_built.append("per-sub-pdf conditional_input_dim lists")
+        if len(not_built) > 0:
+            raise NotImplementedError("jammy_flows_b200.pdf: outside the hot path built so far: " + "; ".join(not_built))
+
+        self.amortization_mlp_use_custom_mode = amortization_mlp_use_custom_mode
+        self.predict_log_normalization = predict_log_normalization
+        self.join_poisson_and_pdf_description = join_poisson_and_pdf_description
+        self.amortization_mlp_highway_mode = amortization_mlp_highway_mode
+        self.amortize_everything = amortize_everything
+        self.use_as_passthrough_instead_of_pdf = use_as_passthrough_instead_of_pdf
+        self.skip_mlp_initialization = skip_mlp_initialization
+        self.total_number_amortizable_params = None
+
+        self.read_model_definition(pdf_defs, flow_defs, options_overwrite, conditional_input_dim, amortization_mlp_dims,
+                                   amortization_mlp_ranks, verbose=verbose)
+        self.init_flow_structure()
+        self.init_encoding_structure()
+        self.init_params()
+
+        self._desc_cache = {}
+        self._status_cache = {}
+        # RNG used by sample(): "numpy" reproduces the reference's host RNG bit for bit (main/default.py:1661-1668);
+        # "device" draws the normals with torch's Philox generator on the GPU (no host round trip).
+        self.rng_mode = "numpy"
+        self.chunk_rows = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # model definition (reference main/default.py:153-325)
+    # ------------------------------------------------------------------------------------------------------------------
+    def read_model_definition(self, pdf_defs, flow_defs, options_overwrite, conditional_input_dim, amortization_mlp_dims,
+                              amortization_mlp_ranks, verbose=False):
+        self.pdf_defs_list = pdf_defs.split("+")
+        self.flow_defs_list = flow_defs.split("+")
+        self.flow_opts = dict()
+        for ind, cur_flow_defs in enumerate(self.flow_defs_list):
+            self.flow_opts[ind] = []
+            for cur_flow_index, flow_abbrv in enumerate(cur_flow_defs):
+                opts = obtain_default_options(flow_abbrv)
+                for opt in opts.keys():
+                    check_flow_option(flow_abbrv, opt, opts[opt])
+                # three specificities, most specific wins: (sub, layer) tuple > sub index > layer code
+                found_specific = False
+                for k in options_overwrite.keys():
+                    if type(k) == tuple:
+                        assert (type(k[0]) == int and type(k[1]) == int), \
+                            "Require 2 ints for tuple-based flow definition! The first indexes the sub-manifold, the second the flow within the manifold."
+                        assert ((k[0] >= 0) and (k[0] < len(self.flow_defs_list))), \
+                            "Index of detailed options is outside allowed range of defined autoregressive structure."
+                        if k[0] != ind or k[1] != cur_flow_index:
+                            continue
+                        assert (len(options_overwrite[k]) == 1), "We have detailed flow definition per item, require length of 1 here."
+                        found_specific = True
+                        for detail_abbrv in options_overwrite[k].keys():
+                            assert (detail_abbrv == flow_abbrv)
+                            for detail_opt, val in options_overwrite[k][detail_abbrv].items():
+                                check_flow_option(flow_abbrv, detail_opt, val)
+                                opts[detail_opt] = val
+                if not found_specific:
+                    for k in options_overwrite.keys():
+                        if type(k) == int:
+                            assert ((k >= 0) and (k < len(self.flow_defs_list))), \
+                                "Index of detailed options is outside allowed range of defined autoregressive structure."
+                            if k != ind:
+                                continue
+                            for detail_abbrv in options_overwrite[k].keys():
+                                if detail_abbrv == flow_abbrv:
+                                    found_specific = True
+                                    for detail_opt, val in options_overwrite[k][detail_abbrv].items():
+                                        check_flow_option(flow_abbrv, detail_opt, val)
+                                        opts[detail_opt] = val
+                if not found_specific:
+                    for k in options_overwrite.keys():
+                        if k == flow_abbrv:
+                            for detail_opt, val in options_overwrite[k].items():
+                                check_flow_option(flow_abbrv, detail_opt, val)
+                                opts[detail_opt] = val
+                self.flow_opts[ind].append(opts)
+        if len(self.pdf_defs_list) != len(self.flow_defs_list):
+            raise Exception("PDF defs list has to be same length as flow defs list, but ... ", self.pdf_defs_list,
+                            self.flow_defs_list)
+        self.conditional_input_dim = conditional_input_dim
+        self.encoding_type = "single"
+        self.amortization_mlp_dims = amortization_mlp_dims
+        if type(self.amortization_mlp_dims) == str:
+            self.amortization_mlp_dims = [self.amortization_mlp_dims] * len(self.pdf_defs_list)
+        elif type(self.amortization_mlp_dims) != list:
+            raise Exception("Hidden MLP dimensions must be defined either str or list, received ",
+                            type(self.amortization_mlp_dims))
+        self.amortization_mlp_ranks = amortization_mlp_ranks
+        if len(self.amortization_mlp_dims) != len(self.pdf_defs_list):
+            raise Exception("hidden mlp dimension definitions for sub pdfs is wrong length (%d) .. requires length (%d)"
+                            % (len(self.amortization_mlp_dims), len(self.pdf_defs_list)))
+        self.layer_list = nn.ModuleList()
+        self.force_permanent_parameters_in_first_subpdf = 0
+        if self.conditional_input_dim is None:
+            self.force_permanent_parameters_in_first_subpdf = 1
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # layer graph (reference main/default.py:378-479)
+    # ------------------------------------------------------------------------------------------------------------------
+    def init_flow_structure(self):
+        self.num_parameter_list = []
+        flow_info = obtain_overall_flow_info()
+        for subflow_index, subflow_description in enumerate(self.pdf_defs_list):
+            self.num_parameter_list.append([])
+            self.layer_list.append(nn.ModuleList())
+            this_num_layers = len(self.flow_defs_list[subflow_index])
+            for layer_ind, layer_type in enumerate(self.flow_defs_list[subflow_index]):
+                if flow_info[layer_type]["type"] != subflow_description[0]:
+                    raise Exception("layer type ", layer_type, " is not compatible with flow type ", subflow_description)
+                this_kwargs = copy.deepcopy(self.flow_opts[subflow_index][layer_ind])
+                this_kwargs["use_permanent_parameters"] = \
+                    1 if (self.force_permanent_parameters_in_first_subpdf and subflow_index == 0) else 0
+                if "s" in subflow_description:
+                    this_kwargs["euclidean_to_sphere_as_first"] = 1 if layer_ind == 0 else 0
+                elif "e" in subflow_description:
+                    # last layer models the offset; a first (non-last) "g" layer swaps isigmoid for the inverse normal
+                    # CDF -- a single-layer sub-pdf therefore keeps isigmoid (reference :440-448)
+                    if layer_ind == (this_num_layers - 1) and this_kwargs["skip_model_offset"] == 0:
+                        this_kwargs["model_offset"] = 1
+                    elif layer_ind == 0:
+                        if layer_type == "g":
+                            if this_kwargs["replace_first_sigmoid_with_icdf"] > 0 and \
+                                    this_kwargs["inverse_function_type"] == "isigmoid":
+                                this_kwargs["inverse_function_type"] = "inormal_partly_precise"
+                else:
+                    raise NotImplementedError("manifold type '%s' has no sm_100a kernel yet" % subflow_description)
+                if "skip_model_offset" in this_kwargs:
+                    del this_kwargs["skip_model_offset"]
+                if layer_type == "g":
+                    del this_kwargs["replace_first_sigmoid_with_icdf"]
+                dim = int(subflow_description.split("_")[0][1:])
+                self.layer_list[subflow_index].append(flow_info[layer_type]["module"](dim, **this_kwargs))
+                self.num_parameter_list[subflow_index].append(self.layer_list[subflow_index][-1].get_total_param_num())
+        self.log_normalization = None
+        self.update_embedding_structure()
+
+    # reference main/default.py:481-567
+    def update_embedding_structure(self):
+        self.target_dims_intrinsic, self.target_dims_embedded, self.target_dims = [], [], []
+        self.target_dim_indices_intrinsic, self.target_dim_indices_embedded = [], []
+        self.target_dim_indices, self.base_dim_indices = [], []
+        tot_i = tot_e = tot = tot_b = 0
+        for ll in self.layer_list:
+            intr = [l.get_layer_intrinsic_target_dimension() for l in ll]
+            emb = [l.get_layer_embedded_target_dimension() for l in ll]
+            base = [l.get_layer_base_dimension() for l in ll]
+            use_emb = any(l.always_parametrize_in_embedding_space for l in ll)
+            for i in range(len(intr) - 1):
+                assert (intr[i] == intr[i + 1])
+            self.target_dims_intrinsic.append(intr[-1])
+            self.target_dims_embedded.append(emb[-1])
+            self.target_dims.append(emb[-1] if use_emb else intr[-1])
+            self.base_dim_indices.append((tot_b, tot_b + base[0]))
+            tot_b += base[0]
+            self.target_dim_indices_intrinsic.append((tot_i, tot_i + intr[-1]))
+            tot_i += intr[-1]
+            self.target_dim_indices_embedded.append((tot_e, tot_e + emb[-1]))
+            tot_e += emb[-1]
+            self.target_dim_indices.append((tot, tot + self.target_dims[-1]))
+            tot += self.target_dims[-1]
+        self.total_target_dim_intrinsic = tot_i
+        self.total_target_dim_embedded = tot_e
+        self.total_target_dim = tot
+        self.total_base_dim = tot_b
+        self._desc_cache = {}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # parameter generators (reference main/default.py:571-673): one nn.Sequential(Linear, Tanh, ..., Linear) per
+    # sub-pdf that has parameters and an input; in = cond_dim + embeddings of all previous sub-pdfs.
+    # ------------------------------------------------------------------------------------------------------------------
+    def init_encoding_structure(self):
+        self.mlp_predictors = nn.ModuleList()
+        self.log_normalization_mlp = None
+        prev_extra_input_num = 0
+        for pdf_index, _ in enumerate(self.pdf_defs_list):
+            emb_num = self.layer_list[pdf_index][-1]._embedding_conditional_return_num()
+            if pdf_index == 0 and self.conditional_input_dim is None:
+                self.mlp_predictors.append(None)
+                prev_extra_input_num += emb_num
+                continue
+            num_predicted_pars = sum(self.num_parameter_list[pdf_index])
+            if num_predicted_pars == 0:
+                self.mlp_predictors.append(None)
+                prev_extra_input_num += emb_num
+                continue
+            this_summary_dim = prev_extra_input_num
+            if self.conditional_input_dim is not None:
+                this_summary_dim += self.conditional_input_dim
+            hidden = list_from_str(self.amortization_mlp_dims[pdf_index])
+            mlp_in_dims = [this_summary_dim] + hidden
+            mlp_out_dims = hidden + [num_predicted_pars]
+            nn_list = []
+            for i in range(len(mlp_in_dims)):
+                nn_list.append(torch.nn.Linear(mlp_in_dims[i], mlp_out_dims[i]))
+                if i < (len(mlp_in_dims) - 1):
+                    nn_list.append(nn.Tanh())
+            self.mlp_predictors.append(torch.nn.Sequential(*nn_list))
+            prev_extra_input_num += emb_num
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # initialisation (reference main/default.py:1817-1952 and extra_functions.py:179-409 with data=None):
+    # desired layer params per sub-pdf; MLP weights kaiming-uniform / damping_factor, last bias := desired params.
+    # The RNG call order is kept so that equal seeds give the reference's parameters.
+    # ------------------------------------------------------------------------------------------------------------------
+    def init_params(self, data=None, damping_factor=1000.0, mvn_min_max_sv_ratio=1e-4):
+        if data is not None:
+            raise NotImplementedError("data-driven initialisation (SURVEY.md section 8f rank 3) is not built yet")
+        with torch.no_grad():
+            params_list = []
+            for subflow_index, subflow_description in enumerate(self.pdf_defs_list):
+                this_layer_list = self.layer_list[subflow_index]
+                if "e" in subflow_description:
+                    # reference traverses the chain in reverse order (extra_functions.py:199)
+                    rev = [l.get_desired_init_parameters() for l in list(this_layer_list)[::-1]]
+                    params_list.append(torch.cat(rev[::-1]))
+                else:
+                    params_list.append(torch.cat([l.get_desired_init_parameters() for l in this_layer_list]))
+            for ind, mlp_predictor in enumerate(self.mlp_predictors):
+                these_params = params_list[ind]
+                if len(these_params) == 0:
+                    continue
+                if mlp_predictor is not None:
+                    for internal_layer in mlp_predictor:
+                        if hasattr(internal_layer, "weight"):
+                            nn.init.kaiming_uniform_(internal_layer.weight.data, a=numpy.sqrt(5))
+                            fan_in, _ = nn.init._calculate_fan_in_and_fan_out(internal_layer.weight.data)
+                            bound = 1 / numpy.sqrt(fan_in)
+                            nn.init.uniform_(internal_layer.bias.data, -bound, bound)
+                            internal_layer.weight.data /= damping_factor
+                            internal_layer.bias.data /= damping_factor
+                    mlp_predictor[-1].bias.data = these_params.data.type(mlp_predictor[-1].bias.data.dtype)
+                else:
+                    tot_param_index = 0
+                    for layer in self.layer_list[ind]:
+                        n = layer.get_total_param_num()
+                        layer.init_params(these_params[tot_param_index:tot_param_index + n])
+                        tot_param_index += n
+        self._desc_cache = {}
+        return None
+
+    # reference main/default.py:724-830
+    def count_parameters(self, verbose=False):
+        n = 0
+        for p in self.parameters():
+            if p.requires_grad:
+                n += int(numpy.prod(p.size()))
+        if verbose:
+            print("total Conditional PDF pars: %d" % n)
+        return n
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------------------------------
+    def _desc(self, dtype):
+        d = self._desc_cache.get(dtype)
+        if d is None:
+            d = engine.compile_pdf(self, dtype)
+            self._desc_cache[dtype] = d
+        return d
+
+    def _status(self, device):
+        key = (device.type, device.index)
+        s = self._status_cache.get(key)
+        if s is None:
+            s = torch.zeros(4, dtype=torch.int32, device=device)
+            self._status_cache[key] = s
+        return s
+
+    def kernel_status(self, reset=True):
+        """Lazily read the device status counters (non-finite / unconverged / out-of-range / root-finder evaluations).
+        This is the only place that synchronises; it replaces the reference's per-iteration host checks
+        (layers/bisection_n_newton.py:95-133, main/default.py:1516)."""
+        out = dict(nonfinite=0, unconverged=0, out_of_range=0, evaluations=0)
+        for s in self._status_cache.values():
+            v = s.cpu().tolist()
+            out["nonfinite"] += v[0]
+            out["unconverged"] += v[1]
+            out["out_of_range"] += v[2]
+            out["evaluations"] += v[3]
+            if reset:
+                s.zero_()
+        return out
+
+    def obtain_current_dtype_n_device(self):
+        """Reference main/default.py:3275-3288."""
+        try:
+            first = next(self.parameters())
+        except StopIteration:
+            return None, None
+        return first.dtype, first.device
+
+    def get_total_embedding_dim(self):
+        return sum(ll[-1]._embedding_conditional_return_num() for ll in self.layer_list)
+
+    def _needs_transform(self):
+        return any(p[0] != "e" for p in self.pdf_defs_list)
+
+    def _anchor(self):
+        p = next(self.parameters(), None)
+        return p if p is not None else torch.zeros(1)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # log_pdf (reference main/default.py:1059-1117)
+    # ------------------------------------------------------------------------------------------------------------------
+    def forward(self, x, conditional_input=None, amortization_parameters=None, force_embedding_coordinates=False,
+                force_intrinsic_coordinates=False, only_last=False):
+        assert (self.use_as_passthrough_instead_of_pdf == False)
+        if amortization_parameters is not None or only_last:
+            raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
+        if force_embedding_coordinates and self._needs_transform():
+            raise NotImplementedError("force_embedding_coordinates for manifold sub-pdfs (chart kernels K9) not built yet")
+        if conditional_input is not None:
+            assert (x.shape[0] == conditional_input.shape[0]), "Evaluating input x and condititional input shape must be similar!"
+            assert (x.is_cuda == conditional_input.is_cuda), "input tensor *x* and *conditional_input* are on different devices"
+            assert (self.conditional_input_dim == conditional_input.shape[1])
+        else:
+            assert self.conditional_input_dim is None, "conditional pdf requires conditional_input"
+        assert (x.shape[1] == self.total_target_dim), (x.shape[1], self.total_target_dim)
+        log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            log_pdf, log_pdf_base, base_pos = _NoBackward.apply(self._anchor(), log_pdf, log_pdf_base, base_pos)
+        return log_pdf, log_pdf_base, base_pos
+
+    def all_layer_inverse(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
+                          force_intrinsic_coordinates=False, only_last=False):
+        """target -> base through every sub-pdf (reference main/default.py:879-1057)."""
+        logp, logp_base, base = engine.pdf_logpdf(self, x, data_summary, chunk_rows=self.chunk_rows)
+        return base, log_det + (logp - logp_base)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # sampling (reference main/default.py:1300-1371, :1533-1707)
+    # ------------------------------------------------------------------------------------------------------------------
+    def sample(self, conditional_input=None, samplesize=1, seed=None, allow_gradients=False,
+               amortization_parameters=None, force_embedding_coordinates=False, force_intrinsic_coordinates=False,
+               failsafe_crosscheck_tolerance=None, dtype=None, device=None, only_last=False):
+        assert (self.use_as_passthrough_instead_of_pdf == False)
+        if allow_gradients:
+            raise NotImplementedError("differentiable sampling needs the backward kernels (K8), not built yet")
+        with torch.no_grad():
+            return self._obtain_sample(conditional_input=conditional_input, seed=seed, samplesize=samplesize,
+                                       amortization_parameters=amortization_parameters,
+                                       force_embedding_coordinates=force_embedding_coordinates,
+                                       force_intrinsic_coordinates=force_intrinsic_coordinates,
+                                       failsafe_crosscheck_tolerance=failsafe_crosscheck_tolerance, device=device,
+                                       dtype=dtype, only_last=only_last)
+
+    def _obtain_sample(self, conditional_input=None, predefined_target_input=None, samplesize=1, seed=None,
+                       amortization_parameters=None, force_embedding_coordinates=False,
+                       force_intrinsic_coordinates=False, failsafe_crosscheck_tolerance=None, dtype=None, device=None,
+                       only_last=False):
+        if amortization_parameters is not None or only_last:
+            raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
+        if force_embedding_coordinates and self._needs_transform():
+            raise NotImplementedError("force_embedding_coordinates for manifold sub-pdfs (chart kernels K9) not built yet")
+        if failsafe_crosscheck_tolerance:
+            raise NotImplementedError("failsafe_crosscheck_tolerance (recheck_sampling) is not built yet")
+        used_sample_size = samplesize
+        if conditional_input is not None:
+            used_sample_size = conditional_input.shape[0]
+            data_type, used_device = conditional_input.dtype, conditional_input.device
+        else:
+            data_type, used_device = self.obtain_current_dtype_n_device()
+            if device is not None:
+                used_device = torch.device(device)
+            if dtype is not None:
+                data_type = dtype
+        assert ((data_type is not None) and (used_device is not None))
+        std_normal_samples = 0.0
+        if predefined_target_input is not None:
+            z = predefined_target_input
+            assert (used_device == z.device)
+            if conditional_input is not None:
+                assert (z.shape[0] == conditional_input.shape[0] and z.dtype == conditional_input.dtype)
+        else:
+            if self.rng_mode == "numpy":
+                # reference: host numpy RNG then H2D copy (main/default.py:1661-1668)
+                if seed is not None:
+                    numpy.random.seed(seed)
+                std_normal = numpy.random.normal(size=(used_sample_size, self.total_base_dim))
+                z = torch.from_numpy(std_normal).type(data_type).to(used_device)
+            else:
+                gen = None
+                if seed is not None:
+                    gen = torch.Generator(device=used_device)
+                    gen.manual_seed(seed)
+                z = torch.randn(used_sample_size, self.total_base_dim, dtype=data_type, device=used_device, generator=gen)
+            std_normal_samples = z
+        x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows)
+        return x, std_normal_samples, log_pdf, log_gauss
+
+    def all_layer_forward(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
+                          force_intrinsic_coordinates=False, only_last=False):
+        """base -> target through every sub-pdf (reference main/default.py:1373-1531)."""
+        xs, logp, logp_base = engine.pdf_sample(self, x, data_summary, chunk_rows=self.chunk_rows)
+        return xs, log_det + (logp_base - logp)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # entropy, total path only (reference main/default.py:2263-2369)
+    # ------------------------------------------------------------------------------------------------------------------
+    def entropy(self, sub_manifolds=[-1], conditional_input=None, force_embedding_coordinates=True,
+                force_intrinsic_coordinates=False, samplesize=100, failsafe_crosscheck_tolerance=None, dtype=None,
+                device=None):
+        if list(sub_manifolds) != [-1]:
+            raise NotImplementedError("marginal entropies (SURVEY.md section 8f rank 2) are not built yet")
+        if self._needs_transform() and force_embedding_coordinates:
+            raise NotImplementedError("entropy in embedding coordinates for manifold sub-pdfs needs chart kernels (K9)")
+        data_type, used_device = self.obtain_current_dtype_n_device()
+        if device is not None:
+            used_device = torch.device(device)
+        if dtype is not None:
+            data_type = dtype
+        if conditional_input is not None:
+            data_type, used_device = conditional_input.dtype, conditional_input.device
+            cond = conditional_input.repeat_interleave(samplesize, dim=0)
+            n = cond.shape[0]
+        else:
+            cond = None
+            n = samplesize
+        with torch.no_grad():
+            z = torch.randn(n, self.total_base_dim, dtype=data_type, device=used_device)   # reference :2914 (device RNG)
+            _, log_pdf, _ = engine.pdf_sample(self, z, cond, chunk_rows=self.chunk_rows)
+        return {"total": -log_pdf.reshape(-1, samplesize).mean(dim=1)}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # coordinate transforms (reference main/default.py:1737-1813): identity for Euclidean-only pdfs
+    # ------------------------------------------------------------------------------------------------------------------
+    def transform_target_space(self, target, log_det=0, transform_from="default", transform_to="embedding"):
+        if self._needs_transform() and transform_from != transform_to and \
+                not (set([transform_from, transform_to]) == set(["default", "intrinsic"])):
+            raise NotImplementedError("embedding <-> intrinsic chart kernels (K9) are not built yet")
+        return target, log_det
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # plain-dict program for the test oracle (no CUDA involved)
+    # ------------------------------------------------------------------------------------------------------------------
+    def export_program(self, dtype="float64"):
+        subs = []
+        for k, layers in enumerate(self.layer_list):
+            ranges, off = [], 0
+            for l in layers:
+                ranges.append((off, off + l.total_param_num))
+                off += l.total_param_num
+            mlp = self.mlp_predictors[k]
+            mlp_spec = None
+            names = []
+            if mlp is not None:
+                mlp_spec = dict(linear_indices=[i for i, m in enumerate(mlp) if isinstance(m, nn.Linear)])
+            else:
+                for li, l in enumerate(layers):
+                    names += ["layer_list.%d.%d.%s" % (k, li, n) for n in l.permanent_param_names()]
+            subs.append(dict(manifold=self.pdf_defs_list[k][0], layers=[l.descriptor() for l in layers],
+                             layer_param_ranges=ranges, mlp=mlp_spec, permanent_param_names=names,
+                             target_cols=self.target_dim_indices[k], base_cols=self.base_dim_indices[k]))
+        return dict(dtype=dtype, subpdfs=subs, conditional_input_dim=self.conditional_input_dim)

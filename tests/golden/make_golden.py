@@ -1,0 +1,149 @@
+"""Generate golden input/output vectors by running the UNMODIFIED reference (thoglu/jammy_flows at /root/reference).
+
+Run in the build container only:   python tests/golden/make_golden.py [case_name ...]
+
+The reference has no stored numeric fixtures of its own (its tests are self-consistency tests,
+reference: tests/test_general.py:393-556), so absolute parity is pinned by executing the reference here on seeded
+inputs and committing inputs, parameters (state_dict) and outputs as small .npz files.  Every `-m "not gpu"` oracle test
+and every `-m gpu` CUDA parity test reads these files; nothing reads /root/reference at test time.
+
+Per case the file holds
+  meta                json: pdf_defs, flow_defs, options_overwrite, conditional_input_dim, dtype, param-set description
+  param/<name>        reference state_dict entries (names are the de-facto checkpoint contract)
+  x, cond             evaluation inputs            -> logp, logp_base, base   (reference pdf.forward, main/default.py:1059)
+  z                   base-space normals           -> samp_x, samp_logp, samp_logp_base
+                      (reference pdf._obtain_sample(predefined_target_input=z), main/default.py:1533)
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+warnings.filterwarnings("ignore")
+
+from refshim import import_reference  # noqa: E402
+
+
+def s2_uniform(n, gen):
+    u = torch.rand(n, generator=gen, dtype=torch.float64)
+    theta = torch.acos(1.0 - 2.0 * u)
+    phi = torch.rand(n, generator=gen, dtype=torch.float64) * 2 * np.pi
+    return torch.stack([theta, phi], dim=1)
+
+
+def make_inputs(pdf_defs, n, gen, tails=False):
+    cols = []
+    for sub in pdf_defs.split("+"):
+        kind, dim = sub[0], int(sub.split("_")[0][1:])
+        if kind == "e":
+            v = 1.5 * torch.randn(n, dim, generator=gen, dtype=torch.float64)
+            if tails:
+                # a block of far-tail points +-(5..30): exercises the Pade tails / underflow handling
+                m = min(n // 10, 200)
+                mag = 5.0 + 25.0 * torch.rand(m, dim, generator=gen, dtype=torch.float64)
+                sgn = torch.where(torch.rand(m, dim, generator=gen) < 0.5, -1.0, 1.0).double()
+                v[:m] = mag * sgn
+            cols.append(v)
+        elif kind == "s" and dim == 2:
+            cols.append(s2_uniform(n, gen))
+        elif kind == "s" and dim == 1:
+            cols.append(torch.rand(n, 1, generator=gen, dtype=torch.float64) * 2 * np.pi)
+        elif kind == "i":
+            parts = sub.split("_")
+            lo, hi = (0.0, 1.0) if len(parts) == 1 else (float(parts[1]), float(parts[2]))
+            cols.append(lo + (hi - lo) * torch.rand(n, dim, generator=gen, dtype=torch.float64))
+        else:
+            raise ValueError(sub)
+    return torch.cat(cols, dim=1)
+
+
+CASES = {
+    # name: dict(pdf_defs, flow_defs, opts, cond_dim, dtype, n, perturb, tails)
+    # BASELINE.json configs[0]: e2 "gg" unconditional fp64
+    "cfg1_e2_gg": dict(pdf_defs="e2", flow_defs="gg", n=2000, tails=True),
+    "cfg1_e2_gg_perturbed": dict(pdf_defs="e2", flow_defs="gg", n=2000, tails=True, perturb=0.3),
+    # BASELINE.json configs[1]: README e4+s2+e4; "n" does not exist in this snapshot -> "f" defaults
+    "cfg2_e4s2e4_f": dict(pdf_defs="e4+s2+e4", flow_defs="gggg+f+gggg", n=1000),
+    "cfg2_e4s2e4_f_perturbed": dict(pdf_defs="e4+s2+e4", flow_defs="gggg+f+gggg", n=1000, perturb=0.3),
+    # g-layer unit cases: every inverse-CDF variant, d=1 (Q=-1 quirk), d=3, conditional (per-row params)
+    "g_e1_isigmoid": dict(pdf_defs="e1", flow_defs="g", n=500, tails=True, perturb=0.3),
+    "g_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=500, cond_dim=3, perturb=0.2),
+    "g_e2_partly_precise_all": dict(pdf_defs="e2", flow_defs="gg", n=500, tails=True, perturb=0.3,
+                                    opts={"g": {"inverse_function_type": "inormal_partly_precise"}}),
+    "g_e2_full_pade": dict(pdf_defs="e2", flow_defs="gg", n=500, tails=True, perturb=0.3,
+                           opts={"g": {"inverse_function_type": "inormal_full_pade"}}),
+    "g_e2_partly_crude": dict(pdf_defs="e2", flow_defs="gg", n=500, tails=True, perturb=0.3,
+                              opts={"g": {"inverse_function_type": "inormal_partly_crude"}}),
+    "g_e2_nonorm": dict(pdf_defs="e2", flow_defs="gg", n=500, perturb=0.3,
+                        opts={"g": {"fit_normalization": 0}}),
+    "g_e5_k7_cond_f32": dict(pdf_defs="e5", flow_defs="gg", n=500, cond_dim=2, perturb=0.1, dtype="float32",
+                             opts={"g": {"num_kde": 7}}),
+    "s2_f_uncond": dict(pdf_defs="s2", flow_defs="f", n=1000, perturb=0.5),
+    "s2_f_cond": dict(pdf_defs="s2", flow_defs="f", n=1000, cond_dim=2, perturb=0.3),
+}
+
+
+def build_case(jf, name, spec):
+    seed = 1
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    dtype = getattr(torch, spec.get("dtype", "float64"))
+    opts = spec.get("opts", {})
+    cond_dim = spec.get("cond_dim", None)
+    pdf = jf.pdf(spec["pdf_defs"], spec["flow_defs"], options_overwrite=opts, conditional_input_dim=cond_dim)
+    pdf = pdf.to(dtype)
+    gen = torch.Generator().manual_seed(1234)
+    if spec.get("perturb", 0.0) > 0:
+        # leave the near-identity init regime (default MLP weights are /1000: main/default.py:1924)
+        with torch.no_grad():
+            for _, p in pdf.named_parameters():
+                p.add_(spec["perturb"] * torch.randn(p.shape, generator=gen, dtype=torch.float64).to(p.dtype))
+    n = spec["n"]
+    x = make_inputs(spec["pdf_defs"], n, gen, tails=spec.get("tails", False)).to(dtype)
+    cond = None
+    if cond_dim is not None:
+        cond = torch.randn(n, cond_dim, generator=gen, dtype=torch.float64).to(dtype)
+    z = torch.randn(n, pdf.total_base_dim, generator=gen, dtype=torch.float64).to(dtype)
+    with torch.no_grad():
+        logp, logp_base, base = pdf(x, conditional_input=cond)
+        samp_x, _, samp_logp, samp_logp_base = pdf._obtain_sample(conditional_input=cond, predefined_target_input=z)
+        # the reference's own round trip (sample -> forward) as the yardstick for sampling parity
+        rt_logp, _, rt_base = pdf(samp_x, conditional_input=cond)
+    out = {
+        "meta": json.dumps(dict(name=name, pdf_defs=spec["pdf_defs"], flow_defs=spec["flow_defs"],
+                                options_overwrite={str(k): v for k, v in opts.items()},
+                                conditional_input_dim=cond_dim, dtype=spec.get("dtype", "float64"),
+                                perturb=spec.get("perturb", 0.0), seed=seed,
+                                reference="thoglu/jammy_flows v1.1.0 @ /root/reference, torch %s CPU" % torch.__version__)),
+        "x": x.numpy(), "z": z.numpy(),
+        "logp": logp.numpy(), "logp_base": logp_base.numpy(), "base": base.numpy(),
+        "samp_x": samp_x.numpy(), "samp_logp": samp_logp.numpy(), "samp_logp_base": samp_logp_base.numpy(),
+        "ref_roundtrip_base_err": np.abs((rt_base - z).numpy()).max(),
+        "ref_roundtrip_logp_err": np.abs((rt_logp - samp_logp).numpy()).max(),
+    }
+    if cond is not None:
+        out["cond"] = cond.numpy()
+    for k, v in pdf.state_dict().items():
+        out["param/" + k] = v.numpy()
+    return out
+
+
+def main():
+    jf = import_reference()
+    names = sys.argv[1:] or list(CASES.keys())
+    for name in names:
+        out = build_case(jf, name, CASES[name])
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-32s logp[0:2]=%s rt_base_err=%.2e rt_logp_err=%.2e  %.1f KB" % (
+            name, out["logp"][:2], out["ref_roundtrip_base_err"], out["ref_roundtrip_logp_err"],
+            os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()
