@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the jammy_flows hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): README flow pdf("e4+s2+e4", "gggg+n+gggg") in fp64, 10M rows per GPU.
+One "step" = one log_pdf pass over the batch + one sampling pass of the same number of rows ("fwd+inverse").
+`value` = rows per second through fwd+inverse with inputs resident in HBM; the per-direction rates are reported as
+`logpdf_evals_per_s` and `samples_per_s`.  `e2e` is the same step through the host-buffer C-ABI entries
+(jf_pdf_logpdf_host / jf_pdf_sample_host): pinned host inputs, H2D and D2H copies inside the timed region.
+
+    python bench.py                                  # 1 GPU, default steps
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference                 # CPU arm: the oracle port of the reference on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PDF_DEFS, FLOW_DEFS = "e4+s2+e4", "gggg+n+gggg"
+METRIC = "rows/s through log_pdf + sample (fwd+inverse), README e4+s2+e4 flow, fp64"
+UNIT = "rows/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# model + synthetic data (identical for both arms)
+# ---------------------------------------------------------------------------------------------------------------------
+def make_model(perturb=0.1):
+    """Reference default init (seed 1) plus a N(0, perturb^2) perturbation of every tensor: the default MLP weights
+    are /1000 (main/default.py:1924), so without it every row would get (almost) the same parameters."""
+    import jammy_flows_b200 as jfb
+    torch.manual_seed(1)
+    np.random.seed(1)
+    pdf = jfb.pdf(PDF_DEFS, FLOW_DEFS).double()
+    gen = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for q in pdf.parameters():
+            q.add_(perturb * torch.randn(q.shape, generator=gen, dtype=torch.float64))
+    return pdf
+
+
+def make_inputs(n, device, seed):
+    """x: e-dims 1.5*N(0,1), (theta,phi) uniform on S2; z: N(0,I)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = 1.5 * torch.randn(n, 10, generator=g, dtype=torch.float64, device=device)
+    x[:, 4] = torch.acos(1 - 2 * torch.rand(n, generator=g, dtype=torch.float64, device=device))
+    x[:, 5] = 2 * np.pi * torch.rand(n, generator=g, dtype=torch.float64, device=device)
+    z = torch.randn(n, 10, generator=g, dtype=torch.float64, device=device)
+    return x, z
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic work per row (restated in DESIGN.md "Kernels and rooflines")
+#   one "special" (exp/log/div/erfinv/tanh/...) = 30 fp64 flop-equivalents
+# ---------------------------------------------------------------------------------------------------------------------
+SPECIAL = 30.0
+K, D = 10, 4
+
+
+def flops_mlp(i, h, o):
+    return 2.0 * (i * h + h * o) + h * SPECIAL
+
+
+def flops_g_eval():
+    """one mixture evaluation of one element: K exp + K div (minimal formulation) + 3 log + ~8K FMA-class"""
+    return (2 * K + 5) * SPECIAL + 2.0 * (8 * K + 10)
+
+
+def flops_g_regulate_layer():
+    """per-row parameter regulation of one layer: 2*K*d values x 3 specials + Householder 2d^2 FMA"""
+    return 2 * K * D * 3 * SPECIAL + 2.0 * 2 * D * D
+
+
+ALG = {
+    # flop-equivalents per row for each kernel of the step; sampling kernels are scaled by measured evals/element
+    "mlp_s2": flops_mlp(4, 128, 10),
+    "mlp_e4": flops_mlp(7, 128, 548),
+    "g_logpdf_shared": 4 * D * flops_g_eval(),
+    "g_logpdf_perrow": 4 * D * flops_g_eval() + 4 * flops_g_regulate_layer(),
+    "s2": 40 * SPECIAL,
+    "bytes_logpdf": 10 * 8 + (1 + 1 + 10) * 8,      # 176 B/row at the API boundary
+    "bytes_sample": 10 * 8 + (10 + 1 + 1) * 8,
+}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [t.strip() for t in s.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, all host threads, bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, n_lp=20000, n_s=4000):
+    from oracle.jf_oracle import OraclePdf
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    pdf = make_model()
+    oracle = OraclePdf(pdf.export_program(), {k: v.numpy() for k, v in pdf.state_dict().items()})
+    x, z = make_inputs(max(n_lp, n_s), "cpu", 100)
+    x_lp, z_s = x[:n_lp], z[:n_s]
+    t_lp, t_s = [], []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            oracle.log_pdf(x_lp)
+            t1 = time.perf_counter()
+            oracle.sample(z_s)
+            t2 = time.perf_counter()
+            if it >= warmup:
+                t_lp.append(t1 - t0)
+                t_s.append(t2 - t1)
+    r_lp = n_lp / float(np.median(t_lp))
+    r_s = n_s / float(np.median(t_s))
+    value = 1.0 / (1.0 / r_lp + 1.0 / r_s)
+    sample = "log_pdf on %d rows + sample on %d rows per step (median of %d), torch CPU fp64" % (n_lp, n_s, steps)
+    return dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample,
+                logpdf_evals_per_s=r_lp, samples_per_s=r_s, seconds=float(sum(t_lp) + sum(t_s)))
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_arm(args.steps, min(args.warmup, 1))
+    ms = 1e3 * (1.0 / cb["logpdf_evals_per_s"] * 20000 + 1.0 / cb["samples_per_s"] * 4000)
+    line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=min(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload="README 10-d e4+s2+e4 'gggg+n+gggg' (n = alias of f), fp64; CPU arm runs the "
+                                     "oracle port of the reference on a bounded sample", rows_per_step=24000),
+                cpu_baseline=dict(kind=cb["kind"], cores=cb["cores"], sample=cb["sample"], value=cb["value"], unit=UNIT),
+                logpdf_evals_per_s=cb["logpdf_evals_per_s"], samples_per_s=cb["samples_per_s"],
+                e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
+    """Time every kernel of one step on its launching stream with CUDA events (full batch, chunked like the step) by
+    driving the per-stage C-ABI entries (jf_mlp_forward / jf_subpdf_apply) directly."""
+    import ctypes as C
+    from jammy_flows_b200 import _cabi, engine
+    dev = x.device
+    B = x.shape[0]
+    chunk = min(B, engine.DEFAULT_CHUNK_ROWS)
+    desc = pdf._desc(torch.float64)
+    pack = engine.ParamPack(pdf, torch.float64, dev)
+    st = engine._stream_ptr(dev)
+    pbuf = torch.empty(548 * chunk, dtype=torch.float64, device=dev)
+    emb = torch.empty(chunk, 3, dtype=torch.float64, device=dev)
+    out = torch.empty(chunk, 10, dtype=torch.float64, device=dev)
+    ld = torch.empty(chunk, dtype=torch.float64, device=dev)
+    lb = torch.empty(chunk, dtype=torch.float64, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    times = {}
+
+    def timed(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn()
+        e1.record()
+        assert rc == 0, (name, rc)
+        times.setdefault(name, []).append((e0, e1))
+
+    vp = lambda t, off=0: C.c_void_p(t.data_ptr() + off * 8)
+
+    def mlp(k, segs, n):
+        md = _cabi.JfMlpDesc()
+        C.memmove(C.byref(md), C.byref(desc.mlp[k]), C.sizeof(md))
+        md.n_segments = len(segs)
+        ptrs = (C.c_void_p * len(segs))(*[s[0] for s in segs])
+        lds = (C.c_int64 * len(segs))(*[s[1] for s in segs])
+        for i, s in enumerate(segs):
+            md.seg_cols[i] = s[2]
+        return lib.jf_mlp_forward(C.byref(md), _cabi.JF_F64, ptrs, lds, pack.c.weights_t[k], pack.c.biases[k], vp(pbuf),
+                                  chunk, 1, n, st)
+
+    def sub(k, direction, src, ld_src, col_in, col_out, shared, n, first):
+        params = C.c_void_p(pack.c.shared[k]) if shared else vp(pbuf)
+        return lib.jf_subpdf_apply(C.byref(desc.sub[k]), _cabi.JF_F64, direction, vp(src, col_in), ld_src, params,
+                                   1 if shared else chunk, 0 if shared else 1, None if first else vp(ld), vp(ld),
+                                   None if first else vp(lb), vp(lb), vp(out, col_out), 10,
+                                   vp(emb) if k == 1 else None, 3, n, vp(status), st)
+
+    for r0 in range(0, B, chunk):
+        n = min(chunk, B - r0)
+        xc, zc = x[r0:r0 + n], z[r0:r0 + n]
+        # log_pdf direction
+        timed("g_chain_logpdf[e4 shared]", lambda: sub(0, 0, xc, 10, 0, 0, True, n, True))
+        timed("mlp[4->128->10]", lambda: mlp(1, [(vp(xc), 10, 4)], n))
+        timed("s2_chain_logpdf[f]", lambda: sub(1, 0, xc, 10, 4, 4, False, n, False))
+        timed("mlp[7->128->548]", lambda: mlp(2, [(vp(xc), 10, 4), (vp(emb), 3, 3)], n))
+        timed("g_chain_logpdf[e4 per-row]", lambda: sub(2, 0, xc, 10, 6, 6, False, n, False))
+        # sampling direction
+        timed("g_chain_sample[e4 shared]", lambda: sub(0, 1, zc, 10, 0, 0, True, n, True))
+        timed("mlp[4->128->10]", lambda: mlp(1, [(vp(out), 10, 4)], n))
+        timed("s2_chain_sample[f]", lambda: sub(1, 1, zc, 10, 4, 4, False, n, False))
+        timed("mlp[7->128->548]", lambda: mlp(2, [(vp(out), 10, 4), (vp(emb), 3, 3)], n))
+        timed("g_chain_sample[e4 per-row]", lambda: sub(2, 1, zc, 10, 6, 6, False, n, False))
+    torch.cuda.synchronize()
+    alg = {
+        "g_chain_logpdf[e4 shared]": ALG["g_logpdf_shared"],
+        "g_chain_logpdf[e4 per-row]": ALG["g_logpdf_perrow"],
+        "g_chain_sample[e4 shared]": 4 * D * flops_g_eval() * evals_per_elem,
+        "g_chain_sample[e4 per-row]": 4 * D * flops_g_eval() * evals_per_elem + 4 * flops_g_regulate_layer(),
+        "mlp[4->128->10]": ALG["mlp_s2"], "mlp[7->128->548]": ALG["mlp_e4"],
+        "s2_chain_logpdf[f]": ALG["s2"], "s2_chain_sample[f]": ALG["s2"],
+    }
+    rows = []
+    total = 0.0
+    for name, evs in times.items():
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        total += ms
+        rows.append(dict(kernel=name, launches=len(evs), ms=ms, flop_equiv_per_row=alg[name]))
+    for r in rows:
+        r["share"] = r["ms"] / total
+        # each named kernel processed B rows in total per direction (the two small MLPs run in both directions)
+        nrows = B * (2 if r["kernel"].startswith("mlp") else 1)
+        r["achieved_tflops"] = r["flop_equiv_per_row"] * nrows / (r["ms"] * 1e-3) * 1e-12
+        r["avg_launch_ms"] = r["ms"] / r["launches"]
+    rows.sort(key=lambda r: -r["ms"])
+    return rows, total
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import ctypes as C
+    from jammy_flows_b200 import _cabi, engine
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _cabi.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    pdf = make_model().to(dev)
+    pdf.rng_mode = "device"
+    n = args.rows
+    x, z = make_inputs(n, dev, 100 + rank)      # every rank owns its own shard of rows (no data-path collective)
+    torch.cuda.synchronize()
+
+    def step():
+        with torch.no_grad():
+            logp, _, _ = engine.pdf_logpdf(pdf, x, want_base=True)
+            xs, slogp, _ = engine.pdf_sample(pdf, z)
+        return logp, xs
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    pdf.kernel_status()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.jf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        with torch.no_grad():
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            engine.pdf_logpdf(pdf, x, want_base=True)
+            eb.record()
+            engine.pdf_sample(pdf, z)
+        marks.append((ea, eb))
+    e1.record()
+    barrier()
+    launches = lib.jf_launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    lp_first_ms = float(np.mean([a.elapsed_time(b) for a, b in marks]))     # log_pdf part of a step
+    status = pdf.kernel_status()
+    evals_per_elem = status["evaluations"] / float(args.steps * n * 8) if status["evaluations"] else 0.0
+
+    # ---- end-to-end through the host-buffer C-ABI entries (pinned host memory in, results back on the host) ----
+    xh, zh = x.cpu().pin_memory(), z.cpu().pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        engine.pdf_logpdf_host(pdf, xh, device=dev)       # x (H2D) -> logp, logp_base, base (D2H)
+        engine.pdf_sample_host(pdf, zh, device=dev)       # z (H2D) -> x, logp, logp_base (D2H)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()                                        # blocks until the results are in host memory
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = 2 * n * 10 * 8
+    d2h = n * (10 + 2) * 8 + n * (10 + 2) * 8
+    del xh, zh
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
+    ms_probe, fma = C.c_float(0), C.c_double(0)
+    rc = lib.jf_probe_fma_peak(_cabi.JF_F64, 4096, C.byref(ms_probe), C.byref(fma), engine._stream_ptr(dev))
+    fp64_peak = 2.0 * fma.value / (ms_probe.value * 1e-3) * 1e-12 if rc == 0 else None
+    rows, total_kernel_ms = kernel_breakdown(pdf, x, z, lib, evals_per_elem)
+    top = rows[0]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = dict(bound="fp64", kernel=top["kernel"], achieved=top["achieved_tflops"], peak=fp64_peak, unit="TFLOP/s",
+                    frac=top["achieved_tflops"] / fp64_peak if fp64_peak else None, traffic=None,
+                    peak_source="DFMA probe kernel timed live (jf_probe_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
+                    flop_equiv_per_row=top["flop_equiv_per_row"], share_of_step=top["share"],
+                    avg_launch_ms=top["avg_launch_ms"],
+                    hbm=dict(achieved_gbs=(ALG["bytes_logpdf"] + ALG["bytes_sample"]) * n / (ms_per_step * 1e-3) * 1e-9,
+                             peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"),
+                    kernels=[{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rows])
+    cb = cpu_arm(3, 1) if world == 1 else None
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config=dict(workload="README 10-d e4+s2+e4 'gggg+n+gggg' ('n' = alias of 'f', SURVEY F2), fp64, "
+                                     "log_pdf + sample of %d rows per GPU per step" % n,
+                            rows_per_gpu=n, params=pdf.count_parameters(), parallelism="rows sharded, dp%d, no collective" % world,
+                            l2="inputs (%.0f MB per direction) exceed the 126 MB L2; no explicit flush" % (n * 80 / 1e6),
+                            param_set="reference default init (seed 1) + N(0,0.1^2) perturbation"),
+                logpdf_evals_per_s=world * n / (lp_first_ms * 1e-3),
+                samples_per_s=world * n / ((ms_per_step - lp_first_ms) * 1e-3),
+                newton_evals_per_element=evals_per_elem,
+                kernel_status=status, gpu_launches=int(launches), clocks=clock_info,
+                e2e=dict(value=world * n / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=e2e_ms),
+                roofline=roofline)
+    if cb is not None:
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "logpdf_evals_per_s",
+                                                    "samples_per_s")}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=10_000_000, help="rows per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include "subpdf_kernels.cuh"
+#include "gf_launch.cuh"
 #include "mlp_kernels.cuh"
 
 using namespace jf;
@@ -39,20 +40,6 @@ static void fill_common(SubPdfArgs<T>& a, const JfSubPdfDesc* desc, const void* 
     a.tab_total = 0;
 }
 
-template <typename T, int D_, int K_>
-static int launch_gf(const GfChainArgs<T>& g, int direction, size_t smem, cudaStream_t st) {
-    const int threads = 256;
-    const int64_t blocks = (g.a.B + threads - 1) / threads;
-    if (direction == JF_DIR_LOGPDF) {
-        if (smem > 48 * 1024) JF_CUDA_OK(cudaFuncSetAttribute(gf_chain_kernel<T, D_, K_, JF_DIR_LOGPDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gf_chain_kernel<T, D_, K_, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, smem, st>>>(g);
-    } else {
-        if (smem > 48 * 1024) JF_CUDA_OK(cudaFuncSetAttribute(gf_chain_kernel<T, D_, K_, JF_DIR_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gf_chain_kernel<T, D_, K_, JF_DIR_SAMPLE><<<(unsigned)blocks, threads, smem, st>>>(g);
-    }
-    return check_launch();
-}
-
 template <typename T>
 static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, cudaStream_t st) {
     const int d = desc->dim;
@@ -77,15 +64,10 @@ static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, 
     g.a.tab_total = tab;
     const size_t smem = (g.a.sr == 0) ? (size_t)tab * sizeof(T) : 0;
     if (smem > 200 * 1024) return JF_ERR_UNSUPPORTED;
-#define JF_GF_CASE(DD) case DD: return launch_gf<T, DD, 10>(g, direction, smem, st);
-    if (all_k10) {
-        switch (d) {
-            JF_GF_CASE(1) JF_GF_CASE(2) JF_GF_CASE(3) JF_GF_CASE(4) JF_GF_CASE(5) JF_GF_CASE(6) JF_GF_CASE(8) JF_GF_CASE(10)
-            default: break;
-        }
-    }
-#undef JF_GF_CASE
-    return launch_gf<T, 0, 0>(g, direction, smem, st);
+    const int rc = (direction == JF_DIR_LOGPDF) ? launch_gf_dir<T, JF_DIR_LOGPDF>(g, d, all_k10, smem, st)
+                                                : launch_gf_dir<T, JF_DIR_SAMPLE>(g, d, all_k10, smem, st);
+    if (rc != JF_OK) return rc;
+    return check_launch();
 }
 
 template <typename T>

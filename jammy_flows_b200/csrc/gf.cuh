@@ -115,10 +115,18 @@ JF_DEVINL void load_mix(Mix<T, KM>& mx, const GfLayerC<T>& c, int K, int j, bool
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
 struct MixVal {
-    T Sc, Ss, Sp;   // rescaled cdf / sf / pdf sums
+    T Sc, Ss, Sp;   // rescaled cdf / sf / pdf sums (Ss is the EXACT survival sum)
     T dc, ds, dp;   // shifts: log cdf = log Sc - dc, ...
+    T ex;           // softplus-threshold excess of the reference's sf: sf_ref = Ss + ex  (see mix_eval)
 };
 
+// Reference quirk that is part of the numerical contract: F.softplus(t) returns t for t > 20 (torch default
+// threshold), so for kernels with a_k < -20 the reference's log-terms drop the factor 1/(1+e^{a_k}):
+//   cdf_k = n e^{a}        (exact n e^{a} r)      -- a 2e-9 relative change of a term that is itself <= 2e-9: invisible
+//   sf_k  = n              (exact n r)            -- sf_ref = sf_exact + ex,  ex = sum_{a_k<-20} n_k e^{a_k} r_k <= 2e-9
+//   pdf_k = n e^{a}/w      (exact n e^{a} r^2/w)
+// so that cdf_ref + sf_ref = 1 + ex.  The kernel carries the exact sf (needed for an accurate Phi^-1 from the upper
+// tail) and the excess separately.
 template <typename T, int KM>
 JF_DEVINL MixVal<T> mix_eval(const Mix<T, KM>& mx, int K, T x) {
     T a[KM];
@@ -132,19 +140,23 @@ JF_DEVINL MixVal<T> mix_eval(const Mix<T, KM>& mx, int K, T x) {
     const bool all_neg = amax < T(0), all_pos = amin > T(0);
     const T delta = all_neg ? -amax : (all_pos ? amin : T(0));
     const T E = exp(-delta);
-    T Sc = 0, Ss = 0, Sp = 0;
+    T Sc = 0, Ss = 0, Sp = 0, ex = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const T u = exp(delta - fabs(a[k]));
-        const T r = T(1) / (T(1) + u * E);
+        const T e = u * E;
+        const T rx = T(1) / (T(1) + e);            // exact sigma(|a|)
+        const bool quirk = a[k] < T(-20);
+        const T r = quirk ? T(1) : rx;
         const T ur = u * r;
         const bool pos = a[k] >= T(0);
         Sc = fma(mx.n[k], pos ? r : ur, Sc);
-        Ss = fma(mx.n[k], pos ? ur : r, Ss);
+        Ss = fma(mx.n[k], pos ? ur : rx, Ss);
         Sp = fma(mx.n[k] * mx.iw[k], ur * r, Sp);
+        if (quirk) ex = fma(mx.n[k], e * rx, ex);
     }
     MixVal<T> v;
-    v.Sc = Sc; v.Ss = Ss; v.Sp = Sp;
+    v.Sc = Sc; v.Ss = Ss; v.Sp = Sp; v.ex = ex;
     v.dc = all_neg ? delta : T(0);
     v.ds = all_pos ? delta : T(0);
     v.dp = delta;
@@ -156,11 +168,11 @@ JF_DEVINL MixVal<T> mix_eval(const Mix<T, KM>& mx, int K, T x) {
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
 JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
-    const T lc = log(v.Sc) - v.dc, ls = log(v.Ss) - v.ds, lp = log(v.Sp) - v.dp;
+    const T lc = log(v.Sc) - v.dc, ls = log(v.Ss + v.ex) - v.ds, lp = log(v.Sp) - v.dp;
     if (type == JF_INV_ISIGMOID) {
         y = lc - ls;
-        // logaddexp(-ls,-lc) + lp = lp - lc - ls + log(cdf+sf), and cdf+sf == 1 up to rounding
-        logd = lp - lc - ls;
+        // logaddexp(-ls,-lc) + lp = lp - lc - ls + log(cdf+sf), and cdf_ref + sf_ref = 1 + ex (ex <= 2e-9)
+        logd = lp - lc - ls + v.ex;
         return;
     }
     const T eps = T(0.5e-7), pa = T(0.147);
@@ -171,7 +183,9 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
     const T F2 = sqrt(F * F - lnf / pa);
     const bool bulk = (cdf > eps) && (cdf < T(1) - eps);
     if (type != JF_INV_FULL_PADE && bulk) {
-        const T e = erfinv(T(2) * cdf - T(1));
+        // Phi^-1(cdf) = sqrt2*erfinv(2cdf-1) in the reference (torch Normal.icdf); evaluated here from the SMALLER tail
+        // with erfcinv so that the argument keeps full relative precision (2cdf-1 cancels catastrophically near 1).
+        const T e = (cdf <= T(0.5)) ? -erfcinv(T(2) * cdf) : erfcinv(T(2) * v.Ss * exp(-v.ds));
         y = T(1.4142135623730951) * e;
         logd = T(kLogSqrt2Pi) + e * e + lp;
         return;
@@ -202,8 +216,9 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
 template <typename T>
 JF_DEVINL void inv_stage_newton(int type, const MixVal<T>& v, T& y, T& dy) {
     if (type == JF_INV_ISIGMOID) {
-        y = log(v.Sc / v.Ss) + (v.ds - v.dc);
-        dy = v.Sp / (v.Sc * v.Ss);   // exp(lp - lc - ls): the shifts cancel exactly (dp = dc + ds)
+        const T ssq = v.Ss + v.ex;
+        y = log(v.Sc / ssq) + (v.ds - v.dc);
+        dy = v.Sp / (v.Sc * ssq);   // exp(lp - lc - ls): the shifts cancel exactly (dp = dc + ds)
         return;
     }
     T logd;
@@ -291,7 +306,7 @@ JF_DEVINL T gf_solve(const Mix<T, KM>& mx, int K, int type, T z, T& logd_out, in
         x = (inside && shrinking && finite_(xn)) ? xn : T(0.5) * (lo + hi);
     }
     if (type == JF_INV_ISIGMOID) {
-        logd = log(v.Sp / (v.Sc * v.Ss));
+        logd = log(v.Sp / (v.Sc * (v.Ss + v.ex))) + v.ex;
     } else {
         T y;
         inv_stage(type, v, y, logd);

@@ -1,0 +1,5 @@
+// explicit instantiation unit: "g"-chain kernels, double, JF_DIR_LOGPDF
+#include "gf_launch.cuh"
+namespace jf {
+JF_GF_LAUNCH_DIR_BODY(double, JF_DIR_LOGPDF)
+}

@@ -1,0 +1,222 @@
+"""GPU: size-independent properties at larger sizes, oracle parity on fresh inputs, edge cases, C-ABI entry points."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import jammy_flows_b200 as jfb
+from helpers import build_pdf, load_golden, rel_err, row_rel_err
+from jammy_flows_b200 import _cabi, engine
+from oracle.jf_oracle import OraclePdf
+
+pytestmark = pytest.mark.gpu
+
+
+def _perturbed(pdf_defs, flow_defs, scale=0.2, cond=None, seed=3, dtype=torch.float64, **kw):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    p = jfb.pdf(pdf_defs, flow_defs, conditional_input_dim=cond, **kw).to(dtype)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for q in p.parameters():
+            q.add_(scale * torch.randn(q.shape, generator=g, dtype=torch.float64).to(q.dtype))
+    return p
+
+
+def _inputs(p, n, seed=5, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    cols = []
+    for k, d in enumerate(p.pdf_defs_list):
+        if d[0] == "e":
+            cols.append(1.5 * torch.randn(n, p.target_dims[k], generator=g, dtype=torch.float64))
+        else:
+            u = torch.rand(n, generator=g, dtype=torch.float64)
+            cols.append(torch.stack([torch.acos(1 - 2 * u), 2 * np.pi * torch.rand(n, generator=g, dtype=torch.float64)], 1))
+    x = torch.cat(cols, 1).to(dtype)
+    z = torch.randn(n, p.total_base_dim, generator=g, dtype=torch.float64).to(dtype)
+    c = None
+    if p.conditional_input_dim:
+        c = torch.randn(n, p.conditional_input_dim, generator=g, dtype=torch.float64).to(dtype)
+    return x, z, c
+
+
+@pytest.mark.parametrize("defs", [("e2", "gg", None), ("e4+s2+e4", "gggg+n+gggg", None), ("e3+s2", "ggg+f", 5),
+                                  ("e6", "gg", 4), ("e7", "g", None), ("e10", "gg", 3)])
+def test_fresh_inputs_match_oracle(defs, lib_built):
+    """new seeded inputs/parameters (not the goldens): CUDA vs the pinned oracle, log_pdf and sampling"""
+    pdf_defs, flow_defs, cond_dim = defs
+    p = _perturbed(pdf_defs, flow_defs, cond=cond_dim)
+    n = 3000
+    x, z, c = _inputs(p, n)
+    o = OraclePdf(p.export_program(), {k: v.numpy() for k, v in p.state_dict().items()})
+    lp_o, lb_o, b_o = o.log_pdf(x, c)
+    xs_o, slp_o, _ = o.sample(z, c)
+    pc = p.cuda()
+    cc = c.cuda() if c is not None else None
+    with torch.no_grad():
+        lp, lb, b = pc(x.cuda(), conditional_input=cc)
+        xs, _, slp, _ = pc._obtain_sample(conditional_input=cc, predefined_target_input=z.cuda())
+    assert rel_err(lp.cpu().numpy(), lp_o.numpy()).max() < 1e-10
+    # base coordinates: 1e-10 except the inverse-normal conditioning of the oracle itself (see test_cuda_parity)
+    assert np.quantile(row_rel_err(b.cpu().numpy(), b_o.numpy()), 0.99) < 1e-10
+    assert row_rel_err(b.cpu().numpy(), b_o.numpy()).max() < 5e-9
+    assert row_rel_err(xs.cpu().numpy(), xs_o.numpy()).max() < 1e-9
+    assert rel_err(slp.cpu().numpy(), slp_o.numpy()).max() < 1e-9
+
+
+def test_round_trip_at_full_shard_size(lib_built):
+    """encode -> decode at 2M rows of the README flow: sample(z) then log_pdf(x) must return z and the same log_pdf"""
+    p = _perturbed("e4+s2+e4", "gggg+n+gggg", scale=0.1).cuda()
+    n = 2_000_000
+    z = torch.randn(n, 10, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+    with torch.no_grad():
+        x, _, logp, logp_base = p._obtain_sample(predefined_target_input=z)
+        rt_logp, rt_logp_base, rt_z = p(x)
+    err = (rt_z - z).abs().max(dim=1)[0] / z.abs().max(dim=1)[0].clamp(min=1)
+    assert float(err.max()) < 1e-7 and float(err.quantile(0.999)) < 1e-10
+    assert float(((rt_logp - logp).abs() / logp.abs().clamp(min=1)).max()) < 1e-8
+    st = p.kernel_status()
+    assert st["nonfinite"] == 0 and st["unconverged"] == 0
+    # theta in [0,pi], phi in [0,2pi]
+    assert float(x[:, 4].min()) >= 0 and float(x[:, 4].max()) <= np.pi
+    assert float(x[:, 5].min()) >= 0 and float(x[:, 5].max()) <= 2 * np.pi + 1e-12
+
+
+def test_chunking_and_sharding_do_not_change_results(lib_built):
+    """rows are independent: any chunk size / any row shard gives bit-identical results (the multi-GPU contract)"""
+    p = _perturbed("e4+s2+e4", "gggg+n+gggg", scale=0.1).cuda()
+    x, z, _ = _inputs(p, 10007)
+    x, z = x.cuda(), z.cuda()
+    with torch.no_grad():
+        ref = p(x)
+        p.chunk_rows = 1000
+        a = p(x)
+        p.chunk_rows = None
+        lo, hi = 1234, 7777
+        b = p(x[lo:hi])
+        xs_full = p._obtain_sample(predefined_target_input=z)[0]
+        xs_part = p._obtain_sample(predefined_target_input=z[lo:hi])[0]
+    for r, q in zip(ref, a):
+        assert torch.equal(r, q)
+    for r, q in zip(ref, b):
+        assert torch.equal(r[lo:hi], q)
+    assert torch.equal(xs_full[lo:hi], xs_part)
+
+
+def test_density_integrates_to_one_on_s2(lib_built):
+    """known-answer test of the reference (tests/test_spheres.py:80-130): the S2 density integrates to 1 within 1e-2"""
+    p = _perturbed("s2", "f", scale=0.5).cuda()
+    nt, nph = 600, 600
+    th = (torch.arange(nt, dtype=torch.float64) + 0.5) * np.pi / nt
+    ph = (torch.arange(nph, dtype=torch.float64) + 0.5) * 2 * np.pi / nph
+    T, P = torch.meshgrid(th, ph, indexing="ij")
+    x = torch.stack([T.reshape(-1), P.reshape(-1)], 1).cuda()
+    with torch.no_grad():
+        logp, _, _ = p(x)
+    integral = float((logp.exp() * torch.sin(x[:, 0])).sum() * (np.pi / nt) * (2 * np.pi / nph))
+    assert abs(integral - 1.0) < 1e-2
+
+
+def test_edge_cases(lib_built):
+    p = _perturbed("e2", "gg").cuda()
+    with torch.no_grad():
+        # empty batch
+        out = p(torch.zeros(0, 2, dtype=torch.float64, device="cuda"))
+        assert out[0].shape == (0,) and out[2].shape == (0, 2)
+        # single row, non-contiguous view, input not mutated (reference tests/test_general.py:512-519)
+        big = torch.randn(33, 5, dtype=torch.float64, device="cuda")
+        view = big[:, 1:3]
+        keep = view.clone()
+        a = p(view)
+        b = p(view.contiguous())
+        assert torch.equal(view, keep)
+        for r, q in zip(a, b):
+            assert torch.equal(r, q)
+        one = p(view[:1].contiguous())
+        assert torch.equal(one[0], a[0][:1])
+        # far tails stay finite (reference clamps nothing here; the rescaled mixture must not underflow)
+        far = torch.tensor([[1e4, -1e4], [-3e4, 2e4], [50.0, -50.0]], dtype=torch.float64, device="cuda")
+        lp, _, base = p(far)
+        assert torch.isfinite(lp).all() and torch.isfinite(base).all()
+        # NaN input is counted, not silently propagated
+        p.kernel_status()
+        bad = torch.tensor([[float("nan"), 0.0]], dtype=torch.float64, device="cuda")
+        p(bad)
+        assert p.kernel_status()["nonfinite"] == 1
+    # backward is not silently wrong: it raises
+    x = torch.randn(4, 2, dtype=torch.float64, device="cuda")
+    lp, _, _ = p(x)
+    with pytest.raises(NotImplementedError):
+        lp.sum().backward()
+
+
+def test_layer_plugin_api_matches_oracle_layer(lib_built):
+    """boundary #2: layer.inv_flow_mapping / flow_mapping with per-row `extra_inputs` (layers/layer_base.py:58-70)"""
+    from oracle import jf_oracle
+    from jammy_flows_b200.layers import gf_block, fisher_von_mises_2d
+    g = torch.Generator().manual_seed(9)
+    n = 777
+    layer = gf_block(3, num_kde=10, fit_normalization=1, regulate_normalization=1, inverse_function_type="isigmoid",
+                     model_offset=1)
+    extra = torch.randn(n, layer.total_param_num, generator=g, dtype=torch.float64) * 0.7
+    x = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    ld = torch.randn(n, generator=g, dtype=torch.float64)
+    ol = jf_oracle.GfLayer(layer.descriptor())
+    y_o, ld_o = ol.inverse(x, ld, extra)
+    y, ld_c = layer.inv_flow_mapping([x.cuda(), ld.cuda()], extra_inputs=extra.cuda())
+    assert rel_err(y.cpu().numpy(), y_o.numpy()).max() < 1e-10
+    assert rel_err(ld_c.cpu().numpy(), ld_o.numpy()).max() < 1e-10
+    assert torch.equal(ld, ld.clone())                       # log_det argument not overwritten
+    xb, ldb = layer.flow_mapping([y, ld_c], extra_inputs=extra.cuda())
+    assert rel_err(xb.cpu().numpy(), x.numpy()).max() < 1e-9
+    assert rel_err(ldb.cpu().numpy(), ld.numpy()).max() < 1e-9
+    f = fisher_von_mises_2d(2, euclidean_to_sphere_as_first=True)
+    extra = torch.randn(n, f.total_param_num, generator=g, dtype=torch.float64)
+    u = torch.rand(n, generator=g, dtype=torch.float64)
+    s = torch.stack([torch.acos(1 - 2 * u), 2 * np.pi * torch.rand(n, generator=g, dtype=torch.float64)], 1)
+    of = jf_oracle.FvmLayer(f.descriptor())
+    y_o, ld_o = of.inverse(s, torch.zeros(n, dtype=torch.float64), extra)
+    y, ld_c = f.inv_flow_mapping([s.cuda(), torch.zeros(n, dtype=torch.float64, device="cuda")], extra_inputs=extra.cuda())
+    assert rel_err(y.cpu().numpy(), y_o.numpy()).max() < 1e-10
+    assert rel_err(ld_c.cpu().numpy(), ld_o.numpy()).max() < 1e-10
+
+
+def test_host_buffer_entry_equals_device_entry(lib_built):
+    """jf_pdf_logpdf_host / jf_pdf_sample_host (pipelined H2D/D2H) give exactly the device-resident results"""
+    p = _perturbed("e4+s2+e4", "gggg+n+gggg", scale=0.1).cuda()
+    x, z, _ = _inputs(p, 50_000)
+    with torch.no_grad():
+        d_lp, d_lb, d_b = p(x.cuda())
+        d_x, _, d_slp, _ = p._obtain_sample(predefined_target_input=z.cuda())
+    h_lp, h_lb, h_b = engine.pdf_logpdf_host(p, x.pin_memory(), chunk_rows=7000)
+    h_x, h_slp, _ = engine.pdf_sample_host(p, z.pin_memory(), chunk_rows=7000)
+    assert torch.equal(h_lp, d_lp.cpu()) and torch.equal(h_b, d_b.cpu()) and torch.equal(h_lb, d_lb.cpu())
+    assert torch.equal(h_x, d_x.cpu()) and torch.equal(h_slp, d_slp.cpu())
+
+
+def test_sample_api_and_seeded_numpy_rng(lib_built):
+    """pdf.sample(): 4-tuple, numpy host RNG reproduces the reference's base normals for a seed (main/default.py:1661)"""
+    p = _perturbed("e2", "gg").cuda()
+    x, z, logp, logp_base = p.sample(samplesize=1000, seed=42)
+    np.random.seed(42)
+    z_ref = np.random.normal(size=(1000, 2))
+    assert np.array_equal(z.cpu().numpy(), z_ref)
+    assert x.shape == (1000, 2) and logp.shape == (1000,)
+    lp2, lb2, z2 = p(x)
+    assert rel_err(z2.cpu().numpy(), z_ref).max() < 1e-9 and rel_err(lp2.cpu().numpy(), logp.cpu().numpy()).max() < 1e-9
+    ent = p.entropy(samplesize=20000)
+    assert torch.isfinite(ent["total"]).all()
+
+
+def test_fp32_path_runs_and_matches_fp64(lib_built):
+    p64 = _perturbed("e6", "gggggg", scale=0.05, cond=8)
+    x, z, c = _inputs(p64, 4000)
+    import copy
+    p32 = copy.deepcopy(p64).float().cuda()
+    p64 = p64.cuda()
+    with torch.no_grad():
+        lp64, _, _ = p64(x.cuda(), conditional_input=c.cuda())
+        lp32, _, _ = p32(x.float().cuda(), conditional_input=c.float().cuda())
+    err = ((lp32.double() - lp64).abs() / lp64.abs().clamp(min=1)).cpu().numpy()
+    assert np.quantile(err, 0.99) < 1e-4 and err.max() < 1e-2     # fp32 input rounding propagates through 6 layers

@@ -1,0 +1,30 @@
+"""CPU: the oracle (oracle/jf_oracle.py) against the golden vectors produced by the unmodified reference.
+This is what pins the oracle (the reference has no stored fixtures of its own)."""
+import numpy as np
+import pytest
+
+from helpers import build_pdf, golden_names, load_golden, rel_err
+from oracle.jf_oracle import OraclePdf
+
+# the oracle uses the reference's own arithmetic (same torch ops), so it reproduces the goldens to rounding
+TOL = {"float64": 1e-12, "float32": 2e-6}
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_reference(name):
+    meta, params, data = load_golden(name)
+    pdf = build_pdf(meta)
+    o = OraclePdf(pdf.export_program(meta["dtype"]), params)
+    cond = data.get("cond")
+    tol = TOL[meta["dtype"]]
+    logp, logp_base, base = o.log_pdf(data["x"], cond)
+    ok = np.isfinite(data["logp"])
+    assert rel_err(logp.numpy(), data["logp"])[ok].max() < tol
+    assert rel_err(logp_base.numpy(), data["logp_base"])[ok].max() < tol
+    assert rel_err(base.numpy(), data["base"])[ok].max() < tol
+    xs, slogp, slogp_base = o.sample(data["z"], cond)
+    ok = np.isfinite(data["samp_logp"]) & np.isfinite(data["samp_x"]).all(axis=1)
+    # sampling goes through 25 bisections + <=20 Newton steps; allow the reference's own round-trip error
+    stol = max(tol, 10 * float(np.nan_to_num(data["ref_roundtrip_base_err"])))
+    assert rel_err(xs.numpy(), data["samp_x"])[ok].max() < max(stol, 1e-9 if meta["dtype"] == "float64" else 1e-4)
+    assert rel_err(slogp_base.numpy(), data["samp_logp_base"])[ok].max() < tol
