@@ -204,7 +204,7 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
     out = torch.empty(chunk, 10, dtype=torch.float64, device=dev)
     ld = torch.empty(chunk, dtype=torch.float64, device=dev)
     lb = torch.empty(chunk, dtype=torch.float64, device=dev)
-    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    status = torch.zeros(4, dtype=torch.int64, device=dev)
     times = {}
 
     def timed(name, fn):
@@ -225,7 +225,7 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         lds = (C.c_int64 * len(segs))(*[s[1] for s in segs])
         for i, s in enumerate(segs):
             md.seg_cols[i] = s[2]
-        return lib.jf_mlp_forward(C.byref(md), _cabi.JF_F64, ptrs, lds, pack.c.weights_t[k], pack.c.biases[k], vp(pbuf),
+        return lib.jf_mlp_forward(C.byref(md), _cabi.JF_F64, ptrs, lds, pack.c.weights[k], pack.c.biases[k], vp(pbuf),
                                   chunk, 1, n, st)
 
     def sub(k, direction, src, ld_src, col_in, col_out, shared, n, first):
@@ -335,7 +335,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     value = world * n / (ms_per_step * 1e-3)
     lp_first_ms = float(np.mean([a.elapsed_time(b) for a, b in marks]))     # log_pdf part of a step
     status = pdf.kernel_status()
-    evals_per_elem = status["evaluations"] / float(args.steps * n * 8) if status["evaluations"] else 0.0
+    evals_per_elem = status["evaluations"] / float(args.steps * n * 32) if status["evaluations"] else 0.0   # 8 g-layers x 4 dims
 
     # ---- end-to-end through the host-buffer C-ABI entries (pinned host memory in, results back on the host) ----
     xh, zh = x.cpu().pin_memory(), z.cpu().pin_memory()

@@ -24,7 +24,7 @@
  * internal streams before returning.
  * Errors: return value 0 = ok, <0 = invalid/unsupported descriptor (JF_ERR_*), >0 = CUDA runtime error code.
  * Numerical conditions (non-finite values, unconverged root finds, out-of-range inputs) are counted in the device
- * array `status[JF_STATUS_WORDS]` and are read lazily by the caller (no implicit sync), mirroring the reference's
+ * int64 array `status[JF_STATUS_WORDS]` and are read lazily by the caller (no implicit sync), mirroring the reference's
  * fail-safes in layers/bisection_n_newton.py:84-133.
  */
 #ifndef JAMMY_B200_H
@@ -137,18 +137,18 @@ int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int direction,
                     const void* logbase_in, void* logbase_out,
                     void* out, int64_t ld_out,
                     void* emb_out, int64_t ld_emb,
-                    int64_t B, int32_t* status, void* stream);
+                    int64_t B, int64_t* status, void* stream);
 
 /*
  * params = W_L * tanh(... tanh(W_1 * concat(segments) + b_1) ...) + b_L for B rows.
  *   seg_ptrs[i]/seg_ld[i]  column block i: [B, seg_cols[i]] with leading dimension seg_ld[i].
- *   weights_t[l]           TRANSPOSED weight of Linear l: [dims[l], dims[l+1]] row-major (= torch weight.t().contiguous()).
+ *   weights[l]             weight of Linear l in torch layout: [dims[l+1], dims[l]] row-major (= Linear.weight).
  *   biases[l]              [dims[l+1]].
  *   out                    element (j,row) at out[j*out_stride_param + row*out_stride_row].
  */
 int jf_mlp_forward(const JfMlpDesc* desc, int dtype,
                    const void* const* seg_ptrs, const int64_t* seg_ld,
-                   const void* const* weights_t, const void* const* biases,
+                   const void* const* weights, const void* const* biases,
                    void* out, int64_t out_stride_param, int64_t out_stride_row,
                    int64_t B, void* stream);
 
@@ -172,7 +172,7 @@ typedef struct JfPdfDesc {
 
 typedef struct JfPdfParams {
     const void* shared[JF_MAX_SUBPDFS];                       /* raw shared vector [n_params] or NULL */
-    const void* weights_t[JF_MAX_SUBPDFS][JF_MAX_MLP_LINEAR]; /* transposed Linear weights (device) */
+    const void* weights[JF_MAX_SUBPDFS][JF_MAX_MLP_LINEAR]; /* Linear.weight [out,in] (device) */
     const void* biases[JF_MAX_SUBPDFS][JF_MAX_MLP_LINEAR];
 } JfPdfParams;
 
@@ -185,14 +185,14 @@ int jf_pdf_logpdf(const JfPdfDesc* desc, const JfPdfParams* params,
                   const void* x, int64_t ldx, const void* cond, int64_t ldc,
                   void* logp, void* logp_base, void* base, int64_t ld_base,
                   int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
-                  int32_t* status, void* stream);
+                  int64_t* status, void* stream);
 
 /* sampling: z [B, ldz] base normals -> x [B, ldx]; logp = log N(z) - logdet, logp_base = log N(z). */
 int jf_pdf_sample(const JfPdfDesc* desc, const JfPdfParams* params,
                   const void* z, int64_t ldz, const void* cond, int64_t ldc,
                   void* x, int64_t ldx, void* logp, void* logp_base,
                   int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
-                  int32_t* status, void* stream);
+                  int64_t* status, void* stream);
 
 /* Same two calls with HOST buffers (pinned for full speed).  The library pipelines H2D copy, kernels and D2H copy
  * over two internal streams in chunks of `chunk_rows`; `workspace` is device memory of
@@ -202,12 +202,12 @@ int jf_pdf_logpdf_host(const JfPdfDesc* desc, const JfPdfParams* params,
                        const void* x_host, int64_t ldx, const void* cond_host, int64_t ldc,
                        void* logp_host, void* logp_base_host, void* base_host, int64_t ld_base,
                        int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
-                       int32_t* status);
+                       int64_t* status);
 int jf_pdf_sample_host(const JfPdfDesc* desc, const JfPdfParams* params,
                        const void* z_host, int64_t ldz, const void* cond_host, int64_t ldc,
                        void* x_host, int64_t ldx, void* logp_host, void* logp_base_host,
                        int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
-                       int32_t* status);
+                       int64_t* status);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 int jf_abi_version(void);

@@ -57,7 +57,7 @@ class JfPdfDesc(C.Structure):
 
 class JfPdfParams(C.Structure):
     _fields_ = [("shared", C.c_void_p * JF_MAX_SUBPDFS),
-                ("weights_t", (C.c_void_p * JF_MAX_MLP_LINEAR) * JF_MAX_SUBPDFS),
+                ("weights", (C.c_void_p * JF_MAX_MLP_LINEAR) * JF_MAX_SUBPDFS),
                 ("biases", (C.c_void_p * JF_MAX_MLP_LINEAR) * JF_MAX_SUBPDFS)]
 
 

@@ -6,6 +6,7 @@
 #include "subpdf_kernels.cuh"
 #include "gf_launch.cuh"
 #include "mlp_kernels.cuh"
+#include "mlp_dmma.cuh"
 
 using namespace jf;
 
@@ -26,7 +27,7 @@ template <typename T>
 static void fill_common(SubPdfArgs<T>& a, const JfSubPdfDesc* desc, const void* in, int64_t ld_in, const void* params,
                         int64_t sp, int64_t sr, const void* logdet_in, void* logdet_out, const void* logbase_in,
                         void* logbase_out, void* out, int64_t ld_out, void* emb_out, int64_t ld_emb, int64_t B,
-                        int32_t* status) {
+                        int64_t* status) {
     a.n_layers = desc->n_layers;
     a.d = desc->dim;
     a.B = B;
@@ -94,7 +95,7 @@ template <typename T>
 static int subpdf_apply_t(const JfSubPdfDesc* desc, int direction, const void* in, int64_t ld_in, const void* params,
                           int64_t sp, int64_t sr, const void* logdet_in, void* logdet_out, const void* logbase_in,
                           void* logbase_out, void* out, int64_t ld_out, void* emb_out, int64_t ld_emb, int64_t B,
-                          int32_t* status, cudaStream_t st) {
+                          int64_t* status, cudaStream_t st) {
     if (desc->manifold == 'e') {
         GfChainArgs<T> g;
         fill_common<T>(g.a, desc, in, ld_in, params, sp, sr, logdet_in, logdet_out, logbase_in, logbase_out, out, ld_out,
@@ -113,7 +114,7 @@ static int subpdf_apply_t(const JfSubPdfDesc* desc, int direction, const void* i
 extern "C" int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int direction, const void* in, int64_t ld_in,
                                const void* params, int64_t p_stride_param, int64_t p_stride_row, const void* logdet_in,
                                void* logdet_out, const void* logbase_in, void* logbase_out, void* out, int64_t ld_out,
-                               void* emb_out, int64_t ld_emb, int64_t B, int32_t* status, void* stream) {
+                               void* emb_out, int64_t ld_emb, int64_t B, int64_t* status, void* stream) {
     if (desc == nullptr || in == nullptr || out == nullptr) return JF_ERR_BAD_ARG;
     if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
     if (direction != JF_DIR_LOGPDF && direction != JF_DIR_SAMPLE) return JF_ERR_BAD_ARG;
@@ -141,9 +142,30 @@ static int launch_mlp(const MlpArgs<T>& m, size_t smem, cudaStream_t st) {
     return check_launch();
 }
 
+// fp64, one hidden layer of <= 128 units: the DMMA kernel.  Returns JF_ERR_UNSUPPORTED when the shape does not fit.
+template <int HP>
+static int launch_mlp2_dmma(const MlpArgs<double>& m, cudaStream_t st) {
+    const size_t smem = mlp2_dmma_smem(m.dims[0], HP);
+    if (smem > 220 * 1024) return JF_ERR_UNSUPPORTED;
+    JF_CUDA_OK(cudaFuncSetAttribute(mlp2_dmma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (m.B + kDmmaRows - 1) / kDmmaRows;
+    mlp2_dmma_kernel<HP><<<(unsigned)blocks, 256, smem, st>>>(m);
+    return check_launch();
+}
+static int try_mlp2_dmma(const MlpArgs<double>& m, cudaStream_t st) {
+    if (m.n_linear != 2) return JF_ERR_UNSUPPORTED;
+    const int Kin = m.dims[0], H = m.dims[1];
+    if (H > 128 || (H & 1) || Kin > 256) return JF_ERR_UNSUPPORTED;
+    if (H <= 32) return launch_mlp2_dmma<32>(m, st);
+    if (H <= 64) return launch_mlp2_dmma<64>(m, st);
+    return launch_mlp2_dmma<128>(m, st);
+}
+template <typename T>
+static int try_mlp2_dmma(const MlpArgs<T>&, cudaStream_t) { return JF_ERR_UNSUPPORTED; }
+
 template <typename T>
 static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, const int64_t* seg_ld,
-                         const void* const* weights_t, const void* const* biases, void* out, int64_t so_p, int64_t so_r,
+                         const void* const* weights, const void* const* biases, void* out, int64_t so_p, int64_t so_r,
                          int64_t B, cudaStream_t st) {
     MlpArgs<T> m;
     memset(&m, 0, sizeof(m));
@@ -164,13 +186,17 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
     }
     if (in_sum != desc->dims[0]) return JF_ERR_BAD_DESC;
     for (int l = 0; l < desc->n_linear; ++l) {
-        m.wt[l] = (const T*)weights_t[l];
+        m.wt[l] = (const T*)weights[l];
         m.bias[l] = (const T*)biases[l];
         if (m.wt[l] == nullptr || m.bias[l] == nullptr) return JF_ERR_BAD_ARG;
     }
     m.out = (T*)out; m.so_p = so_p; m.so_r = so_r; m.B = B;
     m.lda = maxd | 1;
-    auto need = [&](int tm) { return (size_t)(2 * tm * m.lda + kMlpKC * kMlpTN) * sizeof(T); };
+    if (sizeof(T) == 8) {
+        const int rc = try_mlp2_dmma(m, st);
+        if (rc != JF_ERR_UNSUPPORTED) return rc;
+    }
+    auto need = [&](int tm) { return (size_t)(2 * tm * m.lda + kMlpKC * kMlpLDW) * sizeof(T); };
     const size_t cap = 200 * 1024;
     if (need(64) <= cap) return launch_mlp<T, 64>(m, need(64), st);
     if (need(32) <= cap) return launch_mlp<T, 32>(m, need(32), st);
@@ -179,7 +205,7 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
 }
 
 extern "C" int jf_mlp_forward(const JfMlpDesc* desc, int dtype, const void* const* seg_ptrs, const int64_t* seg_ld,
-                              const void* const* weights_t, const void* const* biases, void* out,
+                              const void* const* weights, const void* const* biases, void* out,
                               int64_t out_stride_param, int64_t out_stride_row, int64_t B, void* stream) {
     if (desc == nullptr || out == nullptr || seg_ptrs == nullptr || seg_ld == nullptr) return JF_ERR_BAD_ARG;
     if (desc->n_linear < 1 || desc->n_linear > JF_MAX_MLP_LINEAR) return JF_ERR_BAD_DESC;
@@ -187,9 +213,9 @@ extern "C" int jf_mlp_forward(const JfMlpDesc* desc, int dtype, const void* cons
     if (B == 0) return JF_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == JF_F64)
-        return mlp_forward_t<double>(desc, seg_ptrs, seg_ld, weights_t, biases, out, out_stride_param, out_stride_row, B, st);
+        return mlp_forward_t<double>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st);
     if (dtype == JF_F32)
-        return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights_t, biases, out, out_stride_param, out_stride_row, B, st);
+        return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st);
     return JF_ERR_BAD_ARG;
 }
 
@@ -239,7 +265,7 @@ extern "C" int64_t jf_pdf_workspace_bytes(const JfPdfDesc* desc, int64_t chunk_r
 // direction-generic chunk loop.  `src` = x (logpdf) or z (sample); `dst` = base (logpdf) or x (sample).
 static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, const void* src, int64_t ld_src,
                    const void* cond, int64_t ldc, void* dst, int64_t ld_dst, void* logp, void* logp_base, int64_t B,
-                   void* workspace, int64_t ws_bytes, int64_t chunk, int32_t* status, cudaStream_t st) {
+                   void* workspace, int64_t ws_bytes, int64_t chunk, int64_t* status, cudaStream_t st) {
     WsLayout w;
     int rc = ws_layout(d, chunk, w);
     if (rc != JF_OK) return rc;
@@ -288,7 +314,7 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
                     ++ns;
                 }
                 md.n_segments = ns;
-                rc = jf_mlp_forward(&md, d->dtype, seg_ptr, seg_ld, P->weights_t[k], P->biases[k], ws + w.params, chunk, 1,
+                rc = jf_mlp_forward(&md, d->dtype, seg_ptr, seg_ld, P->weights[k], P->biases[k], ws + w.params, chunk, 1,
                                     n, st);
                 if (rc != JF_OK) return rc;
                 params = ws + w.params;
@@ -327,7 +353,7 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
 
 extern "C" int jf_pdf_logpdf(const JfPdfDesc* desc, const JfPdfParams* params, const void* x, int64_t ldx,
                              const void* cond, int64_t ldc, void* logp, void* logp_base, void* base, int64_t ld_base,
-                             int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows, int32_t* status,
+                             int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows, int64_t* status,
                              void* stream) {
     return pdf_run(desc, params, JF_DIR_LOGPDF, x, ldx, cond, ldc, base, ld_base, logp, logp_base, B, workspace,
                    workspace_bytes, chunk_rows, status, (cudaStream_t)stream);
@@ -335,7 +361,7 @@ extern "C" int jf_pdf_logpdf(const JfPdfDesc* desc, const JfPdfParams* params, c
 
 extern "C" int jf_pdf_sample(const JfPdfDesc* desc, const JfPdfParams* params, const void* z, int64_t ldz,
                              const void* cond, int64_t ldc, void* x, int64_t ldx, void* logp, void* logp_base, int64_t B,
-                             void* workspace, int64_t workspace_bytes, int64_t chunk_rows, int32_t* status, void* stream) {
+                             void* workspace, int64_t workspace_bytes, int64_t chunk_rows, int64_t* status, void* stream) {
     return pdf_run(desc, params, JF_DIR_SAMPLE, z, ldz, cond, ldc, x, ldx, logp, logp_base, B, workspace,
                    workspace_bytes, chunk_rows, status, (cudaStream_t)stream);
 }
@@ -373,7 +399,7 @@ extern "C" int64_t jf_pdf_host_workspace_bytes(const JfPdfDesc* desc, int64_t ch
 
 static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction, const void* src_h, int64_t ld_src,
                         const void* cond_h, int64_t ldc, void* dst_h, int64_t ld_dst, void* logp_h, void* logp_base_h,
-                        int64_t B, void* workspace, int64_t ws_bytes, int64_t chunk, int32_t* status) {
+                        int64_t B, void* workspace, int64_t ws_bytes, int64_t chunk, int64_t* status) {
     HostWs h;
     int rc = host_ws_layout(d, chunk, h);
     if (rc != JF_OK) return rc;
@@ -426,7 +452,7 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
 extern "C" int jf_pdf_logpdf_host(const JfPdfDesc* desc, const JfPdfParams* params, const void* x_host, int64_t ldx,
                                   const void* cond_host, int64_t ldc, void* logp_host, void* logp_base_host,
                                   void* base_host, int64_t ld_base, int64_t B, void* workspace, int64_t workspace_bytes,
-                                  int64_t chunk_rows, int32_t* status) {
+                                  int64_t chunk_rows, int64_t* status) {
     return pdf_run_host(desc, params, JF_DIR_LOGPDF, x_host, ldx, cond_host, ldc, base_host, ld_base, logp_host,
                         logp_base_host, B, workspace, workspace_bytes, chunk_rows, status);
 }
@@ -434,7 +460,7 @@ extern "C" int jf_pdf_logpdf_host(const JfPdfDesc* desc, const JfPdfParams* para
 extern "C" int jf_pdf_sample_host(const JfPdfDesc* desc, const JfPdfParams* params, const void* z_host, int64_t ldz,
                                   const void* cond_host, int64_t ldc, void* x_host, int64_t ldx, void* logp_host,
                                   void* logp_base_host, int64_t B, void* workspace, int64_t workspace_bytes,
-                                  int64_t chunk_rows, int32_t* status) {
+                                  int64_t chunk_rows, int64_t* status) {
     return pdf_run_host(desc, params, JF_DIR_SAMPLE, z_host, ldz, cond_host, ldc, x_host, ldx, logp_host, logp_base_host,
                         B, workspace, workspace_bytes, chunk_rows, status);
 }

@@ -17,7 +17,7 @@ struct MlpArgs {
     int seg_cols[JF_MAX_MLP_SEGMENTS];
     const T* seg_ptr[JF_MAX_MLP_SEGMENTS];
     int64_t seg_ld[JF_MAX_MLP_SEGMENTS];
-    const T* wt[JF_MAX_MLP_LINEAR];   // [in, out] row-major
+    const T* wt[JF_MAX_MLP_LINEAR];   // torch Linear.weight layout: [out, in] row-major
     const T* bias[JF_MAX_MLP_LINEAR];
     T* out; int64_t so_p, so_r;       // out[j*so_p + row*so_r]
     int64_t B;
@@ -26,13 +26,14 @@ struct MlpArgs {
 
 constexpr int kMlpTN = 64;   // output columns per pass
 constexpr int kMlpKC = 32;   // k-chunk of the weight tile
+constexpr int kMlpLDW = kMlpTN + 1;   // padded row stride of the weight tile (conflict-free transposing store)
 
 template <typename T, int TM>
 __global__ void __launch_bounds__(256) mlp_kernel(const __grid_constant__ MlpArgs<T> m) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* act0 = reinterpret_cast<T*>(smem_raw);
     T* act1 = act0 + (size_t)TM * m.lda;
-    T* sW = act1 + (size_t)TM * m.lda;   // [kMlpKC][kMlpTN]
+    T* sW = act1 + (size_t)TM * m.lda;   // [kMlpKC][kMlpLDW]
     constexpr int RPT = TM / 16;          // rows per thread
     const int tid = threadIdx.x;
     const int tx = tid & 15;              // row lane: rows tx + 16*i
@@ -75,9 +76,9 @@ __global__ void __launch_bounds__(256) mlp_kernel(const __grid_constant__ MlpArg
             for (int k0 = 0; k0 < Kin; k0 += kMlpKC) {
                 __syncthreads();   // previous tile fully consumed
                 for (int e = tid; e < kMlpKC * kMlpTN; e += blockDim.x) {
-                    const int kk = e / kMlpTN, nn = e - kk * kMlpTN;
+                    const int nn = e / kMlpKC, kk = e - nn * kMlpKC;     // k fastest: coalesced reads of W[n][k]
                     const int k = k0 + kk, n = n0 + nn;
-                    sW[e] = (k < Kin && n < N) ? W[(size_t)k * N + n] : T(0);
+                    sW[kk * kMlpLDW + nn] = (k < Kin && n < N) ? W[(size_t)n * Kin + k] : T(0);
                 }
                 __syncthreads();
                 const int kend = min(kMlpKC, Kin - k0);
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) mlp_kernel(const __grid_constant__ MlpArg
                 for (int kk = 0; kk < kend; ++kk) {
                     T bv[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) bv[c] = sW[kk * kMlpTN + ty * 4 + c];
+                    for (int c = 0; c < 4; ++c) bv[c] = sW[kk * kMlpLDW + ty * 4 + c];
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
                         const T av = src[(size_t)(tx + 16 * i) * m.lda + k0 + kk];

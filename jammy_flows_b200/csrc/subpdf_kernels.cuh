@@ -17,7 +17,7 @@ struct SubPdfArgs {
     const T* logdet_in;  T* logdet_out;
     const T* logbase_in; T* logbase_out;
     T* emb_out; int64_t ld_emb;
-    int32_t* status;
+    int64_t* status;
     int tab_total;   // size of the processed table (elements) in shared mode
 };
 

@@ -129,11 +129,11 @@ class ParamPack:
             else:
                 linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
                 for i, lin in enumerate(linears):
-                    wt = lin.weight.detach().to(device=device, dtype=dtype).t().contiguous()
+                    wt = lin.weight.detach().to(device=device, dtype=dtype).contiguous()
                     b = lin.bias.detach().to(device=device, dtype=dtype).contiguous()
                     _require_cuda(wt, "MLP weights of sub-pdf %d" % k)
                     self.keep += [wt, b]
-                    self.c.weights_t[k][i] = wt.data_ptr()
+                    self.c.weights[k][i] = wt.data_ptr()
                     self.c.biases[k][i] = b.data_ptr()
 
 
@@ -273,7 +273,7 @@ def run_single_layer(layer, direction, x, log_det, extra_inputs, **kw):
     out = torch.empty_like(x)
     ld_in = log_det.to(dt).contiguous() if torch.is_tensor(log_det) else None
     ld_out = torch.empty(B, dtype=dt, device=dev)
-    status = torch.zeros(_cabi.JF_STATUS_WORDS, dtype=torch.int32, device=dev)
+    status = torch.zeros(_cabi.JF_STATUS_WORDS, dtype=torch.int64, device=dev)
     d = _cabi.JF_DIR_LOGPDF if direction == "logpdf" else _cabi.JF_DIR_SAMPLE
     with torch.cuda.device(dev):
         rc = lib.jf_subpdf_apply(C.byref(sd), _DT[dt], d, _ptr(x), x.stride(0), _ptr(params), sj, sr, _ptr(ld_in),

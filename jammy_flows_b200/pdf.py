@@ -325,7 +325,7 @@ class pdf(nn.Module):
         key = (device.type, device.index)
         s = self._status_cache.get(key)
         if s is None:
-            s = torch.zeros(4, dtype=torch.int32, device=device)
+            s = torch.zeros(4, dtype=torch.int64, device=device)
             self._status_cache[key] = s
         return s
 

@@ -67,3 +67,16 @@ def icdf_conditioning(base, dtype):
     |z| > 5.33) the Pade tail takes over, which is well conditioned, so the term is capped there."""
     z = np.minimum(np.abs(np.asarray(base, dtype=np.float64)), 5.4)
     return 4.0 * EPS[dtype] * np.sqrt(2.0 * np.pi) * np.exp(0.5 * z * z)
+
+
+def base_tolerance(p, dtype, base_ref):
+    """per-row tolerance for base coordinates: relative tolerance + inverse-normal-CDF conditioning of the reference
+    for the sub-pdfs whose last-applied stage (layer 0) is an inverse normal CDF"""
+    tol = REL_TOL[dtype] * np.maximum(1.0, np.abs(base_ref).max(axis=1))
+    extra = np.zeros(base_ref.shape[0])
+    for k, layers in enumerate(p.layer_list):
+        l0 = layers[0]
+        if getattr(l0, "inverse_function_type", "isigmoid") in ("inormal_partly_precise", "inormal_partly_crude"):
+            b0, b1 = p.base_dim_indices[k]
+            extra = np.maximum(extra, icdf_conditioning(base_ref[:, b0:b1], dtype).max(axis=1))
+    return tol + extra

@@ -14,7 +14,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REL_TOL, build_pdf, golden_names, icdf_conditioning, load_golden, rel_err, row_rel_err
+from helpers import (REL_TOL, base_tolerance, build_pdf, golden_names, icdf_conditioning, load_golden, rel_err,
+                     row_rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -29,15 +30,7 @@ def _cuda_model(name):
 
 
 def _base_tolerance(p, meta, base_ref):
-    """per-row tolerance for base coordinates: relative tolerance + inverse-normal-CDF conditioning of the reference"""
-    tol = REL_TOL[meta["dtype"]] * np.maximum(1.0, np.abs(base_ref).max(axis=1))
-    extra = np.zeros(base_ref.shape[0])
-    for k, layers in enumerate(p.layer_list):
-        l0 = layers[0]
-        if getattr(l0, "inverse_function_type", "isigmoid") in ("inormal_partly_precise", "inormal_partly_crude"):
-            b0, b1 = p.base_dim_indices[k]
-            extra = np.maximum(extra, icdf_conditioning(base_ref[:, b0:b1], meta["dtype"]).max(axis=1))
-    return tol + extra
+    return base_tolerance(p, meta["dtype"], base_ref)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -49,18 +42,34 @@ def test_logpdf_matches_reference_golden(name, lib_built):
     logp, logp_base, base = logp.cpu().numpy(), logp_base.cpu().numpy(), base.cpu().numpy()
     ok = np.isfinite(data["logp"])
     base_err = np.abs(base - data["base"]).max(axis=1)
-    assert (base_err[ok] <= _base_tolerance(p, meta, data["base"])[ok]).all(), base_err[ok].max()
-    logp_tol = tol
-    if "full_pade" in str(meta["options_overwrite"]):
-        logp_tol = max(tol, float(data["ref_roundtrip_logp_err"]))
     if meta["dtype"] == "float32":
-        # fp32: log N(z) inherits z*dz from the conditioning term above
-        cond_term = (np.abs(data["base"]) * icdf_conditioning(data["base"], "float32")).sum(axis=1)
-        assert (np.abs(logp - data["logp"])[ok] <= (tol * np.maximum(1, np.abs(data["logp"])) + cond_term)[ok]).all()
+        # fp32 (SURVEY.md F3 decision): the yardstick is the fp64 oracle on the same fp32-rounded inputs/parameters.
+        # The fp32 reference itself is noisy here: measured against that yardstick it is off by up to 2.6e-2 in log_pdf
+        # and 1.6 in a base coordinate (rows next to the |z|=5.33 bulk/Pade switch, where rounding flips the branch);
+        # the fp32 kernel is compared at 1e-5 relative + the fp32 inverse-normal conditioning, away from that switch.
+        from oracle.jf_oracle import OraclePdf
+        o64 = OraclePdf(p.export_program("float64"), {k: v.cpu().numpy() for k, v in p.state_dict().items()})
+        lp64, _, b64 = o64.log_pdf(data["x"].astype(np.float64), data["cond"].astype(np.float64) if "cond" in data else None)
+        lp64, b64 = lp64.numpy(), b64.numpy()
+        calm = ok & (np.abs(b64).max(axis=1) < 5.0)
+        berr = np.abs(base - b64).max(axis=1)
+        btol = tol * np.maximum(1.0, np.abs(b64).max(axis=1)) + icdf_conditioning(b64, "float32").max(axis=1)
+        assert (berr[calm] <= btol[calm]).all(), (berr[calm] / btol[calm]).max()
+        assert (np.abs(logp - lp64)[calm] <= 10 * tol * np.maximum(1, np.abs(lp64))[calm]).all()
+        assert np.median(np.abs(logp - lp64)[calm] / np.maximum(1, np.abs(lp64))[calm]) < tol
+        # the fp32 golden of the reference agrees at the same level on the rows where the reference itself is sane
+        sane = calm & (np.abs(data["logp"] - lp64) <= 10 * tol * np.maximum(1, np.abs(lp64)))
+        assert sane.sum() > 0.9 * ok.sum()
+        assert (np.abs(logp - data["logp"])[sane] <= 20 * tol * np.maximum(1, np.abs(lp64))[sane]).all()
+        assert np.abs(logp - lp64)[ok].max() < 0.1        # rows at the branch switch: bounded, not wild
     else:
+        assert (base_err[ok] <= _base_tolerance(p, meta, data["base"])[ok]).all(), base_err[ok].max()
+        logp_tol = tol
+        if "full_pade" in str(meta["options_overwrite"]):
+            logp_tol = max(tol, float(data["ref_roundtrip_logp_err"]))
         assert rel_err(logp, data["logp"])[ok].max() < logp_tol
-        # log N(base) on its own inherits z*dz of the ill-conditioned entries
-        cond_term = (np.abs(data["base"]) * (base_err[:, None] + 0 * data["base"])).sum(axis=1)
+        # log N(base) on its own inherits z*dz of the ill-conditioned entries (it cancels in log_pdf)
+        cond_term = (np.abs(data["base"]) * base_err[:, None]).sum(axis=1)
         assert (np.abs(logp_base - data["logp_base"])[ok] <= (tol * np.maximum(1, np.abs(data["logp_base"])) + cond_term)[ok]).all()
     st = p.kernel_status()
     assert st["nonfinite"] == int((~ok).sum())

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import jammy_flows_b200 as jfb
-from helpers import build_pdf, load_golden, rel_err, row_rel_err
+from helpers import base_tolerance, build_pdf, load_golden, rel_err, row_rel_err
 from jammy_flows_b200 import _cabi, engine
 from oracle.jf_oracle import OraclePdf
 
@@ -58,9 +58,9 @@ def test_fresh_inputs_match_oracle(defs, lib_built):
         lp, lb, b = pc(x.cuda(), conditional_input=cc)
         xs, _, slp, _ = pc._obtain_sample(conditional_input=cc, predefined_target_input=z.cuda())
     assert rel_err(lp.cpu().numpy(), lp_o.numpy()).max() < 1e-10
-    # base coordinates: 1e-10 except the inverse-normal conditioning of the oracle itself (see test_cuda_parity)
-    assert np.quantile(row_rel_err(b.cpu().numpy(), b_o.numpy()), 0.99) < 1e-10
-    assert row_rel_err(b.cpu().numpy(), b_o.numpy()).max() < 5e-9
+    # base coordinates: 1e-10 plus the inverse-normal conditioning of the oracle itself (helpers.icdf_conditioning)
+    berr = np.abs(b.cpu().numpy() - b_o.numpy()).max(axis=1)
+    assert (berr <= base_tolerance(p, "float64", b_o.numpy())).all(), berr.max()
     assert row_rel_err(xs.cpu().numpy(), xs_o.numpy()).max() < 1e-9
     assert rel_err(slp.cpu().numpy(), slp_o.numpy()).max() < 1e-9
 
@@ -74,10 +74,17 @@ def test_round_trip_at_full_shard_size(lib_built):
         x, _, logp, logp_base = p._obtain_sample(predefined_target_input=z)
         rt_logp, rt_logp_base, rt_z = p(x)
     err = (rt_z - z).abs().max(dim=1)[0] / z.abs().max(dim=1)[0].clamp(min=1)
-    assert float(err.max()) < 1e-7 and float(err.quantile(0.999)) < 1e-10
-    assert float(((rt_logp - logp).abs() / logp.abs().clamp(min=1)).max()) < 1e-8
+    # the reference's inverse-normal stage switches from Phi^-1 to its Pade tail at cdf = 1 -/+ 0.5e-7 (|z| = 5.33) with
+    # a jump of ~3e-2 (gaussianization_flow.py:497-536): base points inside that gap have no pre-image, in the reference
+    # as well as here.  ~2e-7 of all normals are affected; they are excluded from the tight bound and only bounded.
+    calm = z[:, [0, 1, 2, 3, 6, 7, 8, 9]].abs().max(dim=1)[0] < 5.2
+    n_wild = int((~calm).sum())
+    assert n_wild < 20
+    assert float(err[calm].max()) < 1e-7 and float(err[calm].quantile(0.999)) < 1e-10
+    assert float(err.max()) < 0.1
+    assert float(((rt_logp - logp).abs() / logp.abs().clamp(min=1))[calm].max()) < 1e-8
     st = p.kernel_status()
-    assert st["nonfinite"] == 0 and st["unconverged"] == 0
+    assert st["nonfinite"] == 0 and st["unconverged"] <= n_wild
     # theta in [0,pi], phi in [0,2pi]
     assert float(x[:, 4].min()) >= 0 and float(x[:, 4].max()) <= np.pi
     assert float(x[:, 5].min()) >= 0 and float(x[:, 5].max()) <= 2 * np.pi + 1e-12
