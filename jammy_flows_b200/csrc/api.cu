@@ -269,6 +269,8 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
     WsLayout w;
     int rc = ws_layout(d, chunk, w);
     if (rc != JF_OK) return rc;
+    if (B == 0) return JF_OK;
+    if (B < 0) return JF_ERR_BAD_ARG;
     if (P == nullptr || src == nullptr || (d->cond_dim > 0 && cond == nullptr)) return JF_ERR_BAD_ARG;
     if (workspace == nullptr || ws_bytes < w.total) return JF_ERR_WORKSPACE;
     const int64_t es = (int64_t)esize(d->dtype);

@@ -181,11 +181,15 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
     const T lnf = lc + ls + T(1.3862943611198906);   // log 4
     const T F = pc + lnf * T(0.5);
     const T F2 = sqrt(F * F - lnf / pa);
-    const bool bulk = (cdf > eps) && (cdf < T(1) - eps);
+    // upper bulk limit tested on the exact survival function (cdf < 1-eps <=> sf > eps): in fp32 1-eps rounds to 1 and
+    // a cdf that rounds to 1-ulp would otherwise enter the bulk branch with an underflowed tail
+    const T sfx = v.Ss * exp(-v.ds);
+    const bool upper = !(sfx > eps);   // reference: cdf >= 1 - eps
+    const bool bulk = (cdf > eps) && !upper;
     if (type != JF_INV_FULL_PADE && bulk) {
         // Phi^-1(cdf) = sqrt2*erfinv(2cdf-1) in the reference (torch Normal.icdf); evaluated here from the SMALLER tail
         // with erfcinv so that the argument keeps full relative precision (2cdf-1 cancels catastrophically near 1).
-        const T e = (cdf <= T(0.5)) ? -erfcinv(T(2) * cdf) : erfcinv(T(2) * v.Ss * exp(-v.ds));
+        const T e = (cdf <= T(0.5)) ? -erfcinv(T(2) * cdf) : erfcinv(T(2) * sfx);
         y = T(1.4142135623730951) * e;
         logd = T(kLogSqrt2Pi) + e * e + lp;
         return;
@@ -193,7 +197,7 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
     if (type == JF_INV_PARTLY_CRUDE) {
         const T s = -T(2) * (ls + lc);
         const T tail = sqrt(s) - T(0.4717);
-        y = (cdf >= T(1) - eps) ? tail : -tail;
+        y = upper ? tail : -tail;
         logd = -T(0.5) * log(s) - ls - lc + lp;
         return;
     }
@@ -208,7 +212,7 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
         total = lnum - lden - ls - lc + log(fabs(T(1) - T(2) * cdf));
     }
     if (type == JF_INV_FULL_PADE) y = (cdf <= T(0.5)) ? -pade : pade;
-    else y = (cdf >= T(1) - eps) ? pade : -pade;
+    else y = upper ? pade : -pade;
     logd = total + lp;
 }
 

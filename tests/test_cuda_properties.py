@@ -77,7 +77,9 @@ def test_round_trip_at_full_shard_size(lib_built):
     # the reference's inverse-normal stage switches from Phi^-1 to its Pade tail at cdf = 1 -/+ 0.5e-7 (|z| = 5.33) with
     # a jump of ~3e-2 (gaussianization_flow.py:497-536): base points inside that gap have no pre-image, in the reference
     # as well as here.  ~2e-7 of all normals are affected; they are excluded from the tight bound and only bounded.
-    calm = z[:, [0, 1, 2, 3, 6, 7, 8, 9]].abs().max(dim=1)[0] < 5.2
+    # Likewise the S2 chart clamps cos(theta) to 1-1e-6 on the way back (sphere_base.py:498-502), so plane radii above
+    # sqrt(-2 log 5e-7) = 5.39 cannot round trip (5e-7 of all rows).
+    calm = (z[:, [0, 1, 2, 3, 6, 7, 8, 9]].abs().max(dim=1)[0] < 5.2) & (z[:, 4:6].norm(dim=1) < 5.3)
     n_wild = int((~calm).sum())
     assert n_wild < 20
     assert float(err[calm].max()) < 1e-7 and float(err[calm].quantile(0.999)) < 1e-10
@@ -121,7 +123,8 @@ def test_density_integrates_to_one_on_s2(lib_built):
     x = torch.stack([T.reshape(-1), P.reshape(-1)], 1).cuda()
     with torch.no_grad():
         logp, _, _ = p(x)
-    integral = float((logp.exp() * torch.sin(x[:, 0])).sum() * (np.pi / nt) * (2 * np.pi / nph))
+    # in intrinsic (theta, phi) coordinates the density already carries the sin(theta) area factor
+    integral = float(logp.exp().sum() * (np.pi / nt) * (2 * np.pi / nph))
     assert abs(integral - 1.0) < 1e-2
 
 
@@ -210,7 +213,8 @@ def test_sample_api_and_seeded_numpy_rng(lib_built):
     z_ref = np.random.normal(size=(1000, 2))
     assert np.array_equal(z.cpu().numpy(), z_ref)
     assert x.shape == (1000, 2) and logp.shape == (1000,)
-    lp2, lb2, z2 = p(x)
+    with torch.no_grad():
+        lp2, lb2, z2 = p(x)
     assert rel_err(z2.cpu().numpy(), z_ref).max() < 1e-9 and rel_err(lp2.cpu().numpy(), logp.cpu().numpy()).max() < 1e-9
     ent = p.entropy(samplesize=20000)
     assert torch.isfinite(ent["total"]).all()
