@@ -149,7 +149,7 @@ static int launch_mlp2_dmma(const MlpArgs<double>& m, cudaStream_t st) {
     if (smem > 220 * 1024) return JF_ERR_UNSUPPORTED;
     JF_CUDA_OK(cudaFuncSetAttribute(mlp2_dmma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = (m.B + kDmmaRows - 1) / kDmmaRows;
-    mlp2_dmma_kernel<HP><<<(unsigned)blocks, 256, smem, st>>>(m);
+    mlp2_dmma_kernel<HP><<<(unsigned)blocks, kDmmaThreads, smem, st>>>(m);
     return check_launch();
 }
 static int try_mlp2_dmma(const MlpArgs<double>& m, cudaStream_t st) {
