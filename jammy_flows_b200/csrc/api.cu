@@ -45,7 +45,7 @@ template <typename T>
 static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, cudaStream_t st) {
     const int d = desc->dim;
     if (d < 1 || d > JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
-    bool all_k10 = true;
+    int kmax = 1;
     int tab = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
         const JfLayerDesc& L = desc->layers[l];
@@ -60,13 +60,13 @@ static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, 
         c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = tab;
         c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = (T)L.n_min; c.n_max = (T)L.n_max;
         tab += c.tab_size();
-        all_k10 = all_k10 && (L.K == 10);
+        kmax = L.K > kmax ? L.K : kmax;
     }
     g.a.tab_total = tab;
     const size_t smem = (g.a.sr == 0) ? (size_t)tab * sizeof(T) : 0;
     if (smem > 200 * 1024) return JF_ERR_UNSUPPORTED;
-    const int rc = (direction == JF_DIR_LOGPDF) ? launch_gf_dir<T, JF_DIR_LOGPDF>(g, d, all_k10, smem, st)
-                                                : launch_gf_dir<T, JF_DIR_SAMPLE>(g, d, all_k10, smem, st);
+    const int rc = (direction == JF_DIR_LOGPDF) ? launch_gf_dir<T, JF_DIR_LOGPDF>(g, d, kmax, smem, st)
+                                                : launch_gf_dir<T, JF_DIR_SAMPLE>(g, d, kmax, smem, st);
     if (rc != JF_OK) return rc;
     return check_launch();
 }

@@ -1,12 +1,26 @@
 // Gaussianization-flow layer "g": device math.
 //
 // What it computes is fixed by the reference (layers/euclidean/gaussianization_flow.py, cited per function); HOW is
-// B200-first: one thread owns one row, the K mixture parameters of the current dimension live in registers, the
+// B200-first: one thread owns one row; the regulated mixture parameters of the current (layer, dimension) sit in
+// shared memory (one CTA-wide table for shared parameters, per-thread conflict-free slots for per-row parameters); the
 // logistic mixture is evaluated in LINEAR space with a single rescaling exponent (1 exp + 1 reciprocal per kernel
-// instead of the reference's softplus + 3 logsumexp = 4 exp + 1 log1p per kernel), and the sampling direction is a
+// instead of the reference's softplus + 3 logsumexp = 4 exp + 1 log1p per kernel); the sampling direction is a
 // register-resident bracketed Newton iteration (no [B,K,d] temporaries, no host sync per iteration).
+//
+// Code size matters here: the first version unrolled every K loop and inlined every special function, which gave
+// 200 KB of SASS per kernel and an instruction-fetch bound kernel (ncu: stall_no_instruction 5.8 per issue, see
+// profiles/).  Loops over K are therefore rolled (unroll 2) and the cold inverse-CDF branches are not inlined.
 #pragma once
 #include "common.cuh"
+
+// unroll factor of the loops over the K mixture kernels: enough independent exp/div chains in flight to hide the
+// DFMA latency, small enough to keep the Newton iteration inside the instruction cache
+#ifndef JF_K_UNROLL
+#define JF_K_UNROLL 2
+#endif
+#define JF_PRAGMA_(x) _Pragma(#x)
+#define JF_PRAGMA(x) JF_PRAGMA_(x)
+#define JF_UNROLL_K JF_PRAGMA(unroll JF_K_UNROLL)
 
 namespace jf {
 
@@ -24,13 +38,15 @@ struct GfLayerC {
     __host__ __device__ int raw_m() const { return raw_hh() + hh_iter * d; }
     __host__ __device__ int raw_w() const { return raw_m() + K * d; }
     __host__ __device__ int raw_n() const { return raw_w() + K * d; }
-    // processed table block: [offset d][vhat hh_iter*d][m K*d][w K*d][iw K*d][n K*d]
+    // processed table block: [offset d][vhat hh_iter*d][m K*d][w K*d][iw K*d][n K*d][mmin d][mmax d]
     __host__ __device__ int tab_hh() const { return tab_off + d; }
     __host__ __device__ int tab_m() const { return tab_hh() + hh_iter * d; }
     __host__ __device__ int tab_w() const { return tab_m() + K * d; }
     __host__ __device__ int tab_iw() const { return tab_w() + K * d; }
     __host__ __device__ int tab_n() const { return tab_iw() + K * d; }
-    __host__ __device__ int tab_size() const { return d + hh_iter * d + 4 * K * d; }
+    __host__ __device__ int tab_mmin() const { return tab_n() + K * d; }
+    __host__ __device__ int tab_mmax() const { return tab_mmin() + d; }
+    __host__ __device__ int tab_size() const { return d + hh_iter * d + 4 * K * d + 2 * d; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -49,77 +65,94 @@ JF_DEVINL T regulate_norm(T raw, T n_min, T n_max) {
     return n_min + n_max / (T(1) + exp(-raw));
 }
 
-template <typename T, int KM>
-struct Mix {
-    T m[KM], w[KM], iw[KM], n[KM];
+// View of the K regulated mixture parameters of one (layer, dimension).  Both homes of the parameters are shared
+// memory, so the view holds 32-bit shared-window byte addresses and the loads are explicit ld.shared (a generic pointer
+// would compile to LD with address-space resolution):
+//   shared parameters: the CTA-wide table (stride d elements between consecutive k, broadcast reads);
+//   per-row parameters: this thread's slots (stride blockDim.x elements, conflict-free reads).
+template <typename T>
+struct MixView {
+    unsigned m, iw, n;   // byte addresses of element k = 0
+    unsigned skb;        // byte stride between consecutive k
+    int K;
+    T mmin, mmax;        // hull of the means
 };
 
-// Load the K mixture parameters of dimension j for this thread's row.
-//   processed: from the shared-memory table (already regulated; stride 1)
-//   raw:       from global/shared raw parameters (element i at p[i*sj]) and regulate on the fly
-template <typename T, int KM>
-JF_DEVINL void load_mix(Mix<T, KM>& mx, const GfLayerC<T>& c, int K, int j, bool processed, const T* tab,
-                        const T* p, int64_t sj) {
-    const int d = c.d;
-    if (processed) {
-        const T* tm = tab + c.tab_m() + j;
-        const T* tw = tab + c.tab_w() + j;
-        const T* ti = tab + c.tab_iw() + j;
-        const T* tn = tab + c.tab_n() + j;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            mx.m[k] = tm[k * d];
-            mx.w[k] = tw[k * d];
-            mx.iw[k] = ti[k * d];
-            mx.n[k] = tn[k * d];
-        }
-    } else {
-        const T* pm = p + (int64_t)(c.raw_m() + j) * sj;
-        const T* pw = p + (int64_t)(c.raw_w() + j) * sj;
-        const T* pn = p + (int64_t)(c.raw_n() + j) * sj;
-        T rw[KM], rn[KM];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            mx.m[k] = pm[(int64_t)k * d * sj];
-            rw[k] = pw[(int64_t)k * d * sj];
-            rn[k] = (c.norm_mode != JF_NORM_NONE) ? pn[(int64_t)k * d * sj] : T(0);
-        }
-        T nsum = 0, nmax = -Num<T>::big;
-        if (c.norm_mode == JF_NORM_RAW) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) nmax = tmax(nmax, rn[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            regulate_width(rw[k], c.w_min, c.inv_w_max, mx.w[k], mx.iw[k]);
-            T g;
-            if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(rn[k], c.n_min, c.n_max);
-            else if (c.norm_mode == JF_NORM_RAW) g = exp(rn[k] - nmax);
-            else g = T(1);
-            mx.n[k] = g;
-            nsum += g;
-        }
-        T inv = T(1) / nsum;
-#pragma unroll
-        for (int k = 0; k < K; ++k) mx.n[k] *= inv;
+JF_DEVINL double lds(unsigned addr, double) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+JF_DEVINL float lds(unsigned addr, float) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <typename T> JF_DEVINL T mv_m(const MixView<T>& v, int k) { return lds(v.m + k * v.skb, T()); }
+template <typename T> JF_DEVINL T mv_iw(const MixView<T>& v, int k) { return lds(v.iw + k * v.skb, T()); }
+template <typename T> JF_DEVINL T mv_n(const MixView<T>& v, int k) { return lds(v.n + k * v.skb, T()); }
+JF_DEVINL unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Per-row parameters: read the raw values of dimension j (coalesced, param-major), regulate, write this thread's slots.
+//   slots layout: field f in {m, iw, n}, element k at slots[(f*K + k)*T + tid]   (T = blockDim.x)
+// NOTE: the asm loads above are not ordered against these C++ stores by the compiler; the slots are only read through
+// mix_eval/gf_solve, which are separate (noinline) functions called after this one returns.
+template <typename T>
+__device__ __noinline__ MixView<T> regulate_to_slots(const GfLayerC<T>& c, int K, int j, const T* p, int64_t sj, T* slots) {
+    const int d = c.d, nt = blockDim.x;
+    T* sm = slots + threadIdx.x;
+    T* si = sm + (size_t)K * nt;
+    T* sn = si + (size_t)K * nt;
+    const T* pm = p + (int64_t)(c.raw_m() + j) * sj;
+    const T* pw = p + (int64_t)(c.raw_w() + j) * sj;
+    const T* pn = p + (int64_t)(c.raw_n() + j) * sj;
+    const int64_t step = (int64_t)d * sj;
+    T nmax = -Num<T>::big;
+    if (c.norm_mode == JF_NORM_RAW) {
+        for (int k = 0; k < K; ++k) nmax = tmax(nmax, pn[k * step]);
     }
+    T nsum = 0, mmin = Num<T>::big, mmax = -Num<T>::big;
+    JF_UNROLL_K
+    for (int k = 0; k < K; ++k) {
+        const T m = pm[k * step];
+        T w, iw;
+        regulate_width(pw[k * step], c.w_min, c.inv_w_max, w, iw);
+        T g;
+        if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(pn[k * step], c.n_min, c.n_max);
+        else if (c.norm_mode == JF_NORM_RAW) g = exp(pn[k * step] - nmax);
+        else g = T(1);
+        nsum += g;
+        mmin = tmin(mmin, m);
+        mmax = tmax(mmax, m);
+        sm[(size_t)k * nt] = m;
+        si[(size_t)k * nt] = iw;
+        sn[(size_t)k * nt] = g;
+    }
+    const T inv = T(1) / nsum;
+    for (int k = 0; k < K; ++k) sn[(size_t)k * nt] *= inv;
+    MixView<T> v;
+    v.m = smem_addr(sm); v.iw = smem_addr(si); v.n = smem_addr(sn);
+    v.skb = (unsigned)(nt * sizeof(T)); v.K = K; v.mmin = mmin; v.mmax = mmax;
+    return v;
+}
+
+template <typename T>
+JF_DEVINL MixView<T> table_view(const GfLayerC<T>& c, int K, int j, const T* tab) {
+    MixView<T> v;
+    v.m = smem_addr(tab + c.tab_m() + j); v.iw = smem_addr(tab + c.tab_iw() + j); v.n = smem_addr(tab + c.tab_n() + j);
+    v.skb = (unsigned)(c.d * sizeof(T)); v.K = K;
+    v.mmin = tab[c.tab_mmin() + j]; v.mmax = tab[c.tab_mmax() + j];
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K-logistic mixture: log CDF / log SF / log PDF  (reference gaussianization_flow.py:389-454)
 //   a_k = (x - m_k)/w_k ;  cdf = sum n_k sigma(a_k) ; sf = sum n_k sigma(-a_k) ; pdf = sum n_k sigma(a_k) sigma(-a_k)/w_k
-// Linear-space evaluation with ONE shared rescaling exponent delta = min_k |a_k| when all a_k have the same sign
-// (x outside the hull of the means), so nothing underflows however far out x is:
+// Linear-space evaluation with ONE shared rescaling exponent delta = min_k |a_k| when x lies outside the hull of the
+// means (all a_k of one sign), so nothing underflows however far out x is:
 //   u_k = exp(delta - |a_k|) in (0,1],  e_k = exp(-|a_k|) = u_k * exp(-delta),  r_k = 1/(1+e_k)
 //   sigma(|a|) = r,  sigma(-|a|) = e r.   Results are returned as (S, shift) with log X = log S - shift.
-// ---------------------------------------------------------------------------------------------------------------------
-template <typename T>
-struct MixVal {
-    T Sc, Ss, Sp;   // rescaled cdf / sf / pdf sums (Ss is the EXACT survival sum)
-    T dc, ds, dp;   // shifts: log cdf = log Sc - dc, ...
-    T ex;           // softplus-threshold excess of the reference's sf: sf_ref = Ss + ex  (see mix_eval)
-};
-
+//
 // Reference quirk that is part of the numerical contract: F.softplus(t) returns t for t > 20 (torch default
 // threshold), so for kernels with a_k < -20 the reference's log-terms drop the factor 1/(1+e^{a_k}):
 //   cdf_k = n e^{a}        (exact n e^{a} r)      -- a 2e-9 relative change of a term that is itself <= 2e-9: invisible
@@ -127,36 +160,54 @@ struct MixVal {
 //   pdf_k = n e^{a}/w      (exact n e^{a} r^2/w)
 // so that cdf_ref + sf_ref = 1 + ex.  The kernel carries the exact sf (needed for an accurate Phi^-1 from the upper
 // tail) and the excess separately.
-template <typename T, int KM>
-JF_DEVINL MixVal<T> mix_eval(const Mix<T, KM>& mx, int K, T x) {
-    T a[KM];
-    T amax = -Num<T>::big, amin = Num<T>::big;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        a[k] = (x - mx.m[k]) * mx.iw[k];
-        amax = tmax(amax, a[k]);
-        amin = tmin(amin, a[k]);
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct MixVal {
+    T Sc, Ss, Sp;   // rescaled cdf / sf / pdf sums (Ss is the EXACT survival sum)
+    T dc, ds, dp;   // shifts: log cdf = log Sc - dc, ...
+    T ex;           // softplus-threshold excess of the reference's sf: sf_ref = Ss + ex
+    T Sd;           // rescaled derivative of the pdf sum (same shift as Sp), for the third-order root step
+    T E;            // exp(-delta)
+};
+
+template <typename T>
+JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
+    const int K = mv.K;
+    const bool all_neg = x < mv.mmin, all_pos = x > mv.mmax;   // 1/w > 0: sign(a_k) = sign(x - m_k)
+    T delta = 0;
+    if (all_neg || all_pos) {
+        delta = Num<T>::big;
+        for (int k = 0; k < K; ++k) delta = tmin(delta, fabs((x - mv_m(mv, k)) * mv_iw(mv, k)));
     }
-    const bool all_neg = amax < T(0), all_pos = amin > T(0);
-    const T delta = all_neg ? -amax : (all_pos ? amin : T(0));
-    const T E = exp(-delta);
-    T Sc = 0, Ss = 0, Sp = 0, ex = 0;
-#pragma unroll
+    const T E = (delta > T(0)) ? exp_neg(-delta) : T(1);
+    // four class sums instead of per-term selects: "big" = n*sigma(|a|), "small" = n*sigma(-|a|) (rescaled), by sign of a
+    T big_p = 0, small_p = 0, big_n = 0, small_n = 0, Sp = 0, ex = 0, qc = 0, Sd = 0;
+    JF_UNROLL_K
     for (int k = 0; k < K; ++k) {
-        const T u = exp(delta - fabs(a[k]));
+        const T iw = mv_iw(mv, k), n = mv_n(mv, k);
+        const T a = (x - mv_m(mv, k)) * iw;
+        const T u = exp_neg(delta - fabs(a));
         const T e = u * E;
-        const T rx = T(1) / (T(1) + e);            // exact sigma(|a|)
-        const bool quirk = a[k] < T(-20);
-        const T r = quirk ? T(1) : rx;
-        const T ur = u * r;
-        const bool pos = a[k] >= T(0);
-        Sc = fma(mx.n[k], pos ? r : ur, Sc);
-        Ss = fma(mx.n[k], pos ? ur : rx, Ss);
-        Sp = fma(mx.n[k] * mx.iw[k], ur * r, Sp);
-        if (quirk) ex = fma(mx.n[k], e * rx, ex);
+        const T rx = rcp_1to2(T(1) + e);           // exact sigma(|a|)
+        const T nr = n * rx, nur = nr * u;
+        const T pt = nur * iw * rx;                 // pdf term n sigma(a) sigma(-a) / w
+        // d/dx of the pdf term: pt * (sigma(-a) - sigma(a)) / w = -+ pt * iw * rx * (1 - e)
+        const T dt = pt * iw * (rx - e * rx);
+        if (a >= T(0)) { big_p += nr; small_p += nur; Sd -= dt; }
+        else           { big_n += nr; small_n += nur; Sd += dt; }
+        Sp += pt;
+        // softplus-threshold quirk (a < -20): the reference uses r = 1 instead of rx in the cdf and pdf terms and in
+        // the sf term; q = 1 - rx = e*rx <= 2e-9
+        const T q = (a < T(-20)) ? e * rx : T(0);
+        const T nq = n * q;
+        ex += nq;                                   // sf_ref - sf_exact
+        qc = fma(nq, u, qc);                        // cdf_ref - cdf_exact (rescaled like small_n)
+        Sp = fma(nq * u * iw, T(1) + rx, Sp);       // pdf_ref - pdf_exact
     }
+    const T Sc = big_p + small_n + qc;
+    const T Ss = small_p + big_n;
     MixVal<T> v;
-    v.Sc = Sc; v.Ss = Ss; v.Sp = Sp; v.ex = ex;
+    v.Sc = Sc; v.Ss = Ss; v.Sp = Sp; v.ex = ex; v.Sd = Sd; v.E = E;
     v.dc = all_neg ? delta : T(0);
     v.ds = all_pos ? delta : T(0);
     v.dp = delta;
@@ -166,24 +217,14 @@ JF_DEVINL MixVal<T> mix_eval(const Mix<T, KM>& mx, int K, T x) {
 // ---------------------------------------------------------------------------------------------------------------------
 // inverse-CDF stage and its log-derivative (reference gaussianization_flow.py:480-560 and :568-671)
 // ---------------------------------------------------------------------------------------------------------------------
+// the three inverse-normal variants: cold (only layer 0 of a sub-pdf uses them), kept out of line
 template <typename T>
-JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
-    const T lc = log(v.Sc) - v.dc, ls = log(v.Ss + v.ex) - v.ds, lp = log(v.Sp) - v.dp;
-    if (type == JF_INV_ISIGMOID) {
-        y = lc - ls;
-        // logaddexp(-ls,-lc) + lp = lp - lc - ls + log(cdf+sf), and cdf_ref + sf_ref = 1 + ex (ex <= 2e-9)
-        logd = lp - lc - ls + v.ex;
-        return;
-    }
+__device__ __noinline__ void inv_stage_inormal(int type, T lc, T ls, T lp, T sfx, T& y, T& logd) {
     const T eps = T(0.5e-7), pa = T(0.147);
     const T pc = T(2.0 / (kPi * 0.147));
     const T cdf = exp(lc);
-    const T lnf = lc + ls + T(1.3862943611198906);   // log 4
-    const T F = pc + lnf * T(0.5);
-    const T F2 = sqrt(F * F - lnf / pa);
     // upper bulk limit tested on the exact survival function (cdf < 1-eps <=> sf > eps): in fp32 1-eps rounds to 1 and
     // a cdf that rounds to 1-ulp would otherwise enter the bulk branch with an underflowed tail
-    const T sfx = v.Ss * exp(-v.ds);
     const bool upper = !(sfx > eps);   // reference: cdf >= 1 - eps
     const bool bulk = (cdf > eps) && !upper;
     if (type != JF_INV_FULL_PADE && bulk) {
@@ -202,6 +243,9 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
         return;
     }
     // Pade branch (tails of "partly_precise", everything for "full_pade")
+    const T lnf = lc + ls + T(1.3862943611198906);   // log 4
+    const T F = pc + lnf * T(0.5);
+    const T F2 = sqrt(F * F - lnf / pa);
     const T pade = sqrt(tmax(T(0), T(2) * (F2 - F)));
     T total;
     if (cdf > T(0.49999) && cdf < T(0.50001)) {
@@ -216,90 +260,179 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
     logd = total + lp;
 }
 
-// value and plain derivative for the Newton iteration (reference :685-695)
 template <typename T>
-JF_DEVINL void inv_stage_newton(int type, const MixVal<T>& v, T& y, T& dy) {
+JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
     if (type == JF_INV_ISIGMOID) {
+        // y = log cdf - log sf_ref ; logaddexp(-ls,-lc) + lp = lp - lc - ls + log(cdf+sf), cdf_ref + sf_ref = 1 + ex
         const T ssq = v.Ss + v.ex;
         y = log(v.Sc / ssq) + (v.ds - v.dc);
-        dy = v.Sp / (v.Sc * ssq);   // exp(lp - lc - ls): the shifts cancel exactly (dp = dc + ds)
+        logd = log(v.Sp / (v.Sc * ssq)) + v.ex;     // the shifts cancel exactly (dp = dc + ds)
         return;
     }
-    T logd;
+    const T lc = log(v.Sc) - v.dc, ls = log(v.Ss + v.ex) - v.ds, lp = log(v.Sp) - v.dp;
+    inv_stage_inormal<T>(type, lc, ls, lp, v.Ss * exp(-v.ds), y, logd);
+}
+
+// one element of the log_pdf direction: y and log dy/dx (kept out of line: one copy per kernel, not one per dimension)
+template <typename T>
+__device__ __noinline__ void gf_eval_logpdf(const MixView<T>& mv, int type, T x, T& y, T& logd) {
+    const MixVal<T> v = mix_eval<T>(mv, x);
     inv_stage(type, v, y, logd);
-    dy = exp(logd);
 }
 
 // log(Phi(t)/Phi(-t)): the logistic-scale target that corresponds to a Gaussian-scale target t
 template <typename T>
-JF_DEVINL T logit_phi(T t) {
+__device__ __noinline__ T logit_phi(T t) {
     const T at = fabs(t);
     const T lim = sizeof(T) == 8 ? T(25) : T(12);
     if (at < lim) {
         const T r = T(0.70710678118654752);
-        return log(erfc(-t * r)) - log(erfc(t * r));
+        return log(erfc(-t * r) / erfc(t * r));
     }
     const T v = T(0.5) * at * at + log(at) + T(kLogSqrt2Pi);
     return t > 0 ? v : -v;
 }
 
+// 1/x for a positive normal x (hardware seed + two Newton steps; no special-case handling)
+JF_DEVINL double rcp_pos(double x) { return rcp_1to2(x); }
+JF_DEVINL float rcp_pos(float x) { return 1.0f / x; }
+
 // ---------------------------------------------------------------------------------------------------------------------
-// Root of  y(x) = z  for one element (reference: 25 bisections on [-1e5,1e5] + <=20 masked Newton steps,
-// gaussianization_flow.py:921 + bisection_n_newton.py:11-135).  Same root, different trajectory:
-//   * analytic bracket: with t the logistic-scale target, every kernel satisfies sigma((x-m_k)/w_k) <= sigma(t) for
-//     x <= min_k(m_k + t w_k) and >= sigma(t) for x >= max_k(m_k + t w_k), so the mixture root lies in between;
-//   * safeguarded Newton inside the bracket (bisect when a step leaves it or |f| does not shrink);
-//   * stops when |dx| <= 1e-14 + 4 eps |x| (fp64), i.e. at least as tight as the reference's 1e-14 row-sum test.
-// Returns the root, the log-derivative at the root and the number of function evaluations.
+// Root finding for the sampling direction (reference: 25 bisections on [-1e5,1e5] + <=20 masked Newton steps,
+// gaussianization_flow.py:921 + bisection_n_newton.py:11-135).  Same root, different trajectory.
+//
+// Every bulk root is found in LOGIT space: y(x) = z with y = logit(cdf) (isigmoid) or y = Phi^-1(cdf) (inverse-normal
+// variants inside their bulk region, |z| < Phi^-1(1-0.5e-7) = 5.3267) is the root of
+//        L(x) = log(cdf(x)/sf(x)) = t,      t = z  or  t = log(Phi(z)/Phi(-z)),
+// so the iteration never evaluates erfinv or the Pade branches.
+//   * analytic bracket: every kernel satisfies sigma((x-m_k)/w_k) <= sigma(t) for x <= min_k(m_k + t w_k) and
+//     >= sigma(t) for x >= max_k(m_k + t w_k), so the mixture root lies in between;
+//   * third-order (Halley) steps from sum_k n_k (m_k + t w_k), safeguarded by the bracket (bisect when a step leaves
+//     it or |f| does not shrink);
+//   * a step shorter than 1e-7 of the local scale lands within ~1e-21 of the root: it is accepted WITHOUT a confirming
+//     evaluation, and log y' / log pdf are carried to the new point to first order (error ~1e-14).
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T, int KM>
-JF_DEVINL T gf_solve(const Mix<T, KM>& mx, int K, int type, T z, T& logd_out, int& evals, bool& converged) {
-    // logistic-scale targets with safety margins for the non-exact inverse-CDF variants
-    T t_lo, t_hi;
-    if (type == JF_INV_ISIGMOID) {
-        t_lo = t_hi = z;
-    } else {
-        const T marg = (type == JF_INV_PARTLY_CRUDE ? T(0.6) : T(0.05)) + T(0.02) * fabs(z);
-        t_lo = logit_phi(z - marg);
-        t_hi = logit_phi(z + marg);
-    }
-    T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0;
-    const T t_mid = T(0.5) * (t_lo + t_hi);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        lo = tmin(lo, fma(t_lo, mx.w[k], mx.m[k]));
-        hi = tmax(hi, fma(t_hi, mx.w[k], mx.m[k]));
-        x = fma(mx.n[k], fma(t_mid, mx.w[k], mx.m[k]), x);
-        wmax = tmax(wmax, mx.w[k]);
+template <typename T>
+struct LogitRoot {
+    T x;          // root
+    T logd;       // log dL/dx at the root (+ the reference's softplus excess when use_ex)
+    T lpdf;       // log pdf at the root
+    int evals;
+    bool converged;
+};
+
+template <typename T>
+__device__ __noinline__ LogitRoot<T> solve_logit(const MixView<T>& mv, T t, bool use_ex) {
+    T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0, wmin = Num<T>::big;
+    for (int k = 0; k < mv.K; ++k) {
+        const T m = mv_m(mv, k), w = rcp_pos(mv_iw(mv, k));
+        const T c = fma(t, w, m);
+        lo = tmin(lo, c);
+        hi = tmax(hi, c);
+        x = fma(mv_n(mv, k), c, x);
+        wmax = tmax(wmax, w);
+        wmin = tmin(wmin, w);
     }
     {
         const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
-        lo -= pad;
-        hi += pad;
-        // keep inside the reference's search interval
-        lo = tmax(lo, T(-1e5));
-        hi = tmin(hi, T(1e5));
+        lo = tmax(lo - pad, T(-1e5));   // keep inside the reference's search interval
+        hi = tmin(hi + pad, T(1e5));
         x = clampv(x, lo, hi);
     }
     const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
-    T fprev = Num<T>::big;
-    T logd = 0, f = 0;
+    const T early = (sizeof(T) == 8 ? T(1e-7) : T(1e-3));
+    LogitRoot<T> out;
+    out.converged = false;
+    out.evals = 0;
+    T fprev = Num<T>::big, f = 0;
+    const int kMaxIt = 64;
+#pragma unroll 1
+    for (int it = 0; it < kMaxIt; ++it) {
+        const MixVal<T> v = mix_eval<T>(mv, x);
+        ++out.evals;
+        const T ssq = use_ex ? (v.Ss + v.ex) : v.Ss;
+        const T ics = rcp_pos(v.Sc * ssq);
+        const T dy = v.Sp * ics;                              // L'(x): the rescaling shifts cancel (dp = dc + ds)
+        f = log(v.Sc * v.Sc * ics) + (v.ds - v.dc) - t;       // log(Sc/ssq)
+        // L'' = p'/(c s) - (p/(c s))^2 (s - c) with the true (unscaled) s - c
+        const T smc = (v.dc > T(0)) ? (ssq - v.Sc * v.E) : ((v.ds > T(0)) ? (ssq * v.E - v.Sc) : (ssq - v.Sc));
+        const T d2 = v.Sd * ics - dy * dy * smc;
+        const T den = T(2) * dy * dy - f * d2;                // Halley: dx = 2 f L' / (2 L'^2 - f L'')
+        const T dx = (den > dy * dy) ? (T(2) * f * dy * rcp_pos(den)) : (f * rcp_pos(dy));
+        if (f < T(0)) lo = x; else hi = x;
+        const T xn = x - dx;
+        const bool inside = (xn > lo) && (xn < hi);
+        const T adx = fabs(dx);
+        const bool tiny = adx <= tol_abs + tol_rel * fabs(x);
+        if ((inside && adx * dy <= early && adx <= early * wmin) || tiny) {
+            const bool step = inside;                          // tiny but outside the bracket: stay
+            out.x = step ? xn : x;
+            const T sdx = step ? dx : T(0);
+            out.logd = log(dy) + (use_ex ? v.ex : T(0)) - sdx * d2 * rcp_pos(dy);
+            out.lpdf = log(v.Sp) - v.dp - sdx * v.Sd * rcp_pos(v.Sp);
+            out.converged = true;
+            return out;
+        }
+        if (hi - lo <= tol_abs + tol_rel * fabs(x)) {
+            out.x = x; out.logd = log(dy) + (use_ex ? v.ex : T(0)); out.lpdf = log(v.Sp) - v.dp;
+            out.converged = fabs(f) <= Num<T>::target_prec;
+            return out;
+        }
+        const bool shrinking = fabs(f) < T(0.75) * fprev;
+        fprev = fabs(f);
+        x = (inside && shrinking && finite_(xn)) ? xn : T(0.5) * (lo + hi);
+    }
+    // iteration budget exhausted (non-finite parameters): report the last point
+    {
+        const MixVal<T> v = mix_eval<T>(mv, x);
+        const T ssq = use_ex ? (v.Ss + v.ex) : v.Ss;
+        out.x = x;
+        out.logd = log(v.Sp / (v.Sc * ssq)) + (use_ex ? v.ex : T(0));
+        out.lpdf = log(v.Sp) - v.dp;
+        out.converged = false;
+    }
+    return out;
+}
+
+// General (slow) path: safeguarded Newton directly on y(x) = z with a confirming evaluation.  Only used for targets in
+// the Pade tails of the inverse-normal variants (|z| > 5.32, ~1e-7 of all normals) and for "inormal_full_pade".
+template <typename T>
+__device__ __noinline__ T solve_general(const MixView<T>& mv, int type, T z, T& logd_out, int& evals, bool& converged) {
+    const T marg = (type == JF_INV_PARTLY_CRUDE ? T(0.6) : T(0.05)) + T(0.02) * fabs(z);
+    const T t_lo = logit_phi<T>(z - marg), t_hi = logit_phi<T>(z + marg);
+    T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0;
+    const T t_mid = T(0.5) * (t_lo + t_hi);
+    for (int k = 0; k < mv.K; ++k) {
+        const T m = mv_m(mv, k), w = T(1) / mv_iw(mv, k);
+        lo = tmin(lo, fma(t_lo, w, m));
+        hi = tmax(hi, fma(t_hi, w, m));
+        x = fma(mv_n(mv, k), fma(t_mid, w, m), x);
+        wmax = tmax(wmax, w);
+    }
+    {
+        const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
+        lo = tmax(lo - pad, T(-1e5));
+        hi = tmin(hi + pad, T(1e5));
+        x = clampv(x, lo, hi);
+    }
+    const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
+    T fprev = Num<T>::big, f = 0;
     converged = false;
     evals = 0;
     MixVal<T> v;
     const int kMaxIt = 64;
+#pragma unroll 1
     for (int it = 0; it < kMaxIt; ++it) {
-        v = mix_eval<T, KM>(mx, K, x);
+        v = mix_eval<T>(mv, x);
         ++evals;
-        T y, dy;
-        inv_stage_newton(type, v, y, dy);
+        T y, logd;
+        inv_stage(type, v, y, logd);
         f = y - z;
         if (f < T(0)) lo = x; else hi = x;
-        const T dx = f / dy;
-        T xn = x - dx;
+        const T dx = f / exp(logd);
+        const T xn = x - dx;
         const bool inside = (xn > lo) && (xn < hi);
         if (fabs(dx) <= tol_abs + tol_rel * fabs(x)) {
-            // converged: the evaluation at x is (to <=1e-14) the evaluation at the root
             if (inside) x = xn;
             converged = true;
             break;
@@ -309,16 +442,29 @@ JF_DEVINL T gf_solve(const Mix<T, KM>& mx, int K, int type, T z, T& logd_out, in
         fprev = fabs(f);
         x = (inside && shrinking && finite_(xn)) ? xn : T(0.5) * (lo + hi);
     }
-    if (type == JF_INV_ISIGMOID) {
-        logd = log(v.Sp / (v.Sc * (v.Ss + v.ex))) + v.ex;
-    } else {
-        T y;
-        inv_stage(type, v, y, logd);
-    }
-    logd_out = logd;
-    // reference semantics: report elements whose residual exceeds 1e-7 (fp64) / 1e-4 (fp32)
-    if (!(fabs(f) <= Num<T>::target_prec)) converged = false;
+    T y;
+    inv_stage(type, v, y, logd_out);
+    if (!(fabs(f) <= Num<T>::target_prec)) converged = false;   // reference: warn above 1e-7 (fp64) / 1e-4 (fp32)
     return x;
+}
+
+// Root of y(x) = z for one element: returns x, log y'(x), the number of mixture evaluations and the convergence flag.
+template <typename T>
+JF_DEVINL T gf_solve(const MixView<T>& mv, int type, T z, T& logd_out, int& evals, bool& converged) {
+    if (type == JF_INV_ISIGMOID) {
+        const LogitRoot<T> r = solve_logit<T>(mv, z, true);
+        logd_out = r.logd; evals = r.evals; converged = r.converged;
+        return r.x;
+    }
+    // bulk region of the inverse-normal variants: Phi^-1(cdf) = z  <=>  logit(cdf) = logit(Phi(z))
+    if (type != JF_INV_FULL_PADE && fabs(z) < T(5.32)) {
+        const LogitRoot<T> r = solve_logit<T>(mv, logit_phi<T>(z), false);
+        // log y' = log sqrt(2 pi) + erfinv(2cdf-1)^2 + log pdf with erfinv(2cdf-1) = z/sqrt2 at the root
+        logd_out = T(kLogSqrt2Pi) + T(0.5) * z * z + r.lpdf;
+        evals = r.evals; converged = r.converged;
+        return r.x;
+    }
+    return solve_general<T>(mv, type, z, logd_out, evals, converged);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -330,6 +476,7 @@ JF_DEVINL T gf_solve(const Mix<T, KM>& mx, int K, int type, T z, T& logd_out, in
 template <typename T, int DM>
 JF_DEVINL void householder_apply(T* x, int d, int n_iter, bool transpose, bool processed, const T* vtab,
                                  const T* p, int64_t sj) {
+#pragma unroll 1
     for (int ii = 0; ii < n_iter; ++ii) {
         const int i = transpose ? ii : (n_iter - 1 - ii);
         T v[DM];
@@ -373,12 +520,12 @@ __device__ void gf_build_table(const GfLayerC<T>& c, const T* raw /*stride 1*/, 
         tab[c.tab_w() + e] = w;
         tab[c.tab_iw() + e] = iw;
     }
-    // normalisation needs the sum over k for each dimension
+    // normalisation and the hull of the means need a pass over k for each dimension
     for (int j = tid; j < d; j += nthreads) {
         T nmax = -Num<T>::big;
         if (c.norm_mode == JF_NORM_RAW)
             for (int k = 0; k < K; ++k) nmax = tmax(nmax, raw[c.raw_n() + k * d + j]);
-        T sum = 0;
+        T sum = 0, mmin = Num<T>::big, mmax = -Num<T>::big;
         for (int k = 0; k < K; ++k) {
             T g;
             if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(raw[c.raw_n() + k * d + j], c.n_min, c.n_max);
@@ -386,18 +533,23 @@ __device__ void gf_build_table(const GfLayerC<T>& c, const T* raw /*stride 1*/, 
             else g = T(1);
             tab[c.tab_n() + k * d + j] = g;
             sum += g;
+            mmin = tmin(mmin, raw[c.raw_m() + k * d + j]);
+            mmax = tmax(mmax, raw[c.raw_m() + k * d + j]);
         }
         const T inv = T(1) / sum;
         for (int k = 0; k < K; ++k) tab[c.tab_n() + k * d + j] *= inv;
+        tab[c.tab_mmin() + j] = mmin;
+        tab[c.tab_mmax() + j] = mmax;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// One layer on one row.  `p`: this row's raw parameter slice base (element i at p[i*sj]); `tab`: processed table.
+// One layer on one row.  `p`: this row's raw parameter slice base (element i at p[i*sj]); `tab`: processed table;
+// `slots`: per-thread parameter slots (per-row mode).
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T, int DM, int KM>
+template <typename T, int DM>
 JF_DEVINL void gf_layer_logpdf(T* x, T& logdet, const GfLayerC<T>& c, int d, int K, bool processed, const T* tab,
-                               const T* p, int64_t sj) {
+                               const T* p, int64_t sj, T* slots) {
     if (c.has_offset) {
 #pragma unroll
         for (int j = 0; j < d; ++j) x[j] -= processed ? tab[c.tab_off + j] : p[(int64_t)(c.raw_off + j) * sj];
@@ -405,31 +557,28 @@ JF_DEVINL void gf_layer_logpdf(T* x, T& logdet, const GfLayerC<T>& c, int d, int
     if (c.hh_iter > 0)
         householder_apply<T, DM>(x, d, c.hh_iter, true, processed, tab + c.tab_hh(), p + (int64_t)c.raw_hh() * sj, sj);
     T ld = 0;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < d; ++j) {
-        Mix<T, KM> mx;
-        load_mix<T, KM>(mx, c, K, j, processed, tab, p, sj);
-        const MixVal<T> v = mix_eval<T, KM>(mx, K, x[j]);
+        const MixView<T> mv = processed ? table_view<T>(c, K, j, tab) : regulate_to_slots<T>(c, K, j, p, sj, slots);
         T y, logd;
-        inv_stage(c.inv_type, v, y, logd);
+        gf_eval_logpdf<T>(mv, c.inv_type, x[j], y, logd);
         x[j] = y;
         ld += logd;
     }
     logdet += ld;
 }
 
-template <typename T, int DM, int KM>
+template <typename T, int DM>
 JF_DEVINL void gf_layer_sample(T* x, T& logdet, const GfLayerC<T>& c, int d, int K, bool processed, const T* tab,
-                               const T* p, int64_t sj, int& n_evals, int& n_unconv) {
+                               const T* p, int64_t sj, T* slots, int& n_evals, int& n_unconv) {
     T ld = 0;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < d; ++j) {
-        Mix<T, KM> mx;
-        load_mix<T, KM>(mx, c, K, j, processed, tab, p, sj);
+        const MixView<T> mv = processed ? table_view<T>(c, K, j, tab) : regulate_to_slots<T>(c, K, j, p, sj, slots);
         T logd;
         int ev;
         bool conv;
-        x[j] = gf_solve<T, KM>(mx, K, c.inv_type, x[j], logd, ev, conv);
+        x[j] = gf_solve<T>(mv, c.inv_type, x[j], logd, ev, conv);
         ld += logd;
         n_evals += ev;
         n_unconv += conv ? 0 : 1;

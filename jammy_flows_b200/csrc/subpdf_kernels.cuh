@@ -29,14 +29,15 @@ struct GfChainArgs {
 
 // Euclidean sub-pdf: chain of "g" layers.
 //   D_ > 0: compile-time dimension (row vector fully in registers); D_ == 0: run-time d <= JF_MAX_DIM.
-//   K_ > 0: compile-time num_kde for ALL layers;                     K_ == 0: run-time K <= JF_MAX_KDE.
-template <typename T, int D_, int K_, int DIR>
-__global__ void __launch_bounds__(256) gf_chain_kernel(const __grid_constant__ GfChainArgs<T> g) {
+//   num_kde is a run-time value (rolled loops over K).
+// Dynamic shared memory: the processed table (shared parameters) or 3*Kmax*blockDim.x per-thread slots (per-row).
+template <typename T, int D_, int DIR>
+__global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant__ GfChainArgs<T> g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
+    T* slots = tab;
     const SubPdfArgs<T>& a = g.a;
     constexpr int DM = D_ > 0 ? D_ : JF_MAX_DIM;
-    constexpr int KM = K_ > 0 ? K_ : JF_MAX_KDE;
     const int d = D_ > 0 ? D_ : a.d;
     const bool shared_params = (a.sr == 0);
 
@@ -62,8 +63,7 @@ __global__ void __launch_bounds__(256) gf_chain_kernel(const __grid_constant__ G
             for (int j = 0; j < d; ++j) a.emb_out[row * a.ld_emb + j] = x[j];
         }
         for (int l = a.n_layers - 1; l >= 0; --l) {
-            const int K = K_ > 0 ? K_ : g.layers[l].K;
-            gf_layer_logpdf<T, DM, KM>(x, logdet, g.layers[l], d, K, shared_params, tab, prow, a.sj);
+            gf_layer_logpdf<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots);
         }
 #pragma unroll
         for (int j = 0; j < d; ++j) zsq = fma(x[j], x[j], zsq);
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256) gf_chain_kernel(const __grid_constant__ G
         for (int j = 0; j < d; ++j) zsq = fma(x[j], x[j], zsq);
         int n_evals = 0, n_unconv = 0;
         for (int l = 0; l < a.n_layers; ++l) {
-            const int K = K_ > 0 ? K_ : g.layers[l].K;
-            gf_layer_sample<T, DM, KM>(x, logdet, g.layers[l], d, K, shared_params, tab, prow, a.sj, n_evals, n_unconv);
+            gf_layer_sample<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots, n_evals,
+                                   n_unconv);
         }
         if (a.emb_out) {
 #pragma unroll
