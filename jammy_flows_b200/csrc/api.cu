@@ -399,6 +399,15 @@ extern "C" int64_t jf_pdf_host_workspace_bytes(const JfPdfDesc* desc, int64_t ch
     return h.total;
 }
 
+// strided [n, cols] copy; collapses to ONE linear copy when both sides are dense (a 2-D copy of millions of 80-byte
+// rows is an order of magnitude slower on the copy engines)
+static cudaError_t copy_rows(void* dst, int64_t ld_dst, const void* src, int64_t ld_src, int64_t cols, int64_t n,
+                             int64_t es, cudaMemcpyKind kind, cudaStream_t s) {
+    if (ld_dst == cols && ld_src == cols)
+        return cudaMemcpyAsync(dst, src, (size_t)(n * cols * es), kind, s);
+    return cudaMemcpy2DAsync(dst, (size_t)(ld_dst * es), src, (size_t)(ld_src * es), (size_t)(cols * es), (size_t)n, kind, s);
+}
+
 static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction, const void* src_h, int64_t ld_src,
                         const void* cond_h, int64_t ldc, void* dst_h, int64_t ld_dst, void* logp_h, void* logp_base_h,
                         int64_t B, void* workspace, int64_t ws_bytes, int64_t chunk, int64_t* status) {
@@ -422,19 +431,19 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
         const int b = (int)(ci & 1);
         char* set = (char*)workspace + (int64_t)b * h.per_set;
         cudaStream_t s = st[b];
-        cudaError_t e = cudaMemcpy2DAsync(set + h.src, (size_t)src_cols * es, (const char*)src_h + r0 * ld_src * es,
-                                          (size_t)ld_src * es, (size_t)src_cols * es, (size_t)n, cudaMemcpyHostToDevice, s);
+        cudaError_t e = copy_rows(set + h.src, src_cols, (const char*)src_h + r0 * ld_src * es, ld_src, src_cols, n, es,
+                                  cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && d->cond_dim > 0)
-            e = cudaMemcpy2DAsync(set + h.cond, (size_t)d->cond_dim * es, (const char*)cond_h + r0 * ldc * es,
-                                  (size_t)ldc * es, (size_t)d->cond_dim * es, (size_t)n, cudaMemcpyHostToDevice, s);
+            e = copy_rows(set + h.cond, d->cond_dim, (const char*)cond_h + r0 * ldc * es, ldc, d->cond_dim, n, es,
+                          cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { rc = (int)e; break; }
         rc = pdf_run(d, P, direction, set + h.src, src_cols, d->cond_dim > 0 ? set + h.cond : nullptr, d->cond_dim,
                      set + h.dst, dst_cols, set + h.logp, logp_base_h ? set + h.logp_base : nullptr, n, set + h.inner,
                      w.total, chunk, status, s);
         if (rc != JF_OK) break;
         if (dst_h != nullptr)
-            e = cudaMemcpy2DAsync((char*)dst_h + r0 * ld_dst * es, (size_t)ld_dst * es, set + h.dst, (size_t)dst_cols * es,
-                                  (size_t)dst_cols * es, (size_t)n, cudaMemcpyDeviceToHost, s);
+            e = copy_rows((char*)dst_h + r0 * ld_dst * es, ld_dst, set + h.dst, dst_cols, dst_cols, n, es,
+                          cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess && logp_h != nullptr)
             e = cudaMemcpyAsync((char*)logp_h + r0 * es, set + h.logp, n * es, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess && logp_base_h != nullptr)
