@@ -24,6 +24,10 @@
 
 namespace jf {
 
+// 1/x for a positive normal x (hardware seed + two Newton steps; no special-case handling)
+JF_DEVINL double rcp_pos_(double x) { return rcp_1to2(x); }
+JF_DEVINL float rcp_pos_(float x) { return 1.0f / x; }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Layer constants (host fills from JfLayerDesc)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -52,17 +56,21 @@ struct GfLayerC {
 // ---------------------------------------------------------------------------------------------------------------------
 // Parameter regulation (reference gaussianization_flow.py:23-47, 300-317, 342, 406)
 // ---------------------------------------------------------------------------------------------------------------------
-// width:  log_w = log(w_min + 1/(1/w_max + exp(-raw)))  ->  w and 1/w
+// width:  w = w_min + 1/(1/w_max + exp(-raw))  ->  1/w = q/(w_min q + 1), q = 1/w_max + exp(-raw)   (one exp, one rcp)
+template <typename T>
+JF_DEVINL T regulate_inv_width(T raw, T w_min, T inv_w_max) {
+    const T q = inv_w_max + exp_clamped(-raw);
+    return q * rcp_pos_(fma(w_min, q, T(1)));
+}
 template <typename T>
 JF_DEVINL void regulate_width(T raw, T w_min, T inv_w_max, T& w, T& iw) {
-    T q = inv_w_max + exp(-raw);
-    w = w_min + T(1) / q;
-    iw = T(1) / w;
+    iw = regulate_inv_width(raw, w_min, inv_w_max);
+    w = T(1) / iw;
 }
 // norm (unnormalised, linear space): exp(log_n_regulated) = n_min + n_max * sigmoid(raw)
 template <typename T>
 JF_DEVINL T regulate_norm(T raw, T n_min, T n_max) {
-    return n_min + n_max / (T(1) + exp(-raw));
+    return fma(n_max, rcp_pos_(T(1) + exp_clamped(-raw)), n_min);
 }
 
 // View of the K regulated mixture parameters of one (layer, dimension).  Both homes of the parameters are shared
@@ -107,24 +115,31 @@ __device__ __noinline__ MixView<T> regulate_to_slots(const GfLayerC<T>& c, int K
     const T* pw = p + (int64_t)(c.raw_w() + j) * sj;
     const T* pn = p + (int64_t)(c.raw_n() + j) * sj;
     const int64_t step = (int64_t)d * sj;
+    // phase 1: raw values -> slots.  A pure copy loop keeps 3*8 independent global loads in flight per thread, so the
+    // L2/HBM latency of the parameter stream is paid once per (layer, dim) and not once per k.
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+        sm[(size_t)k * nt] = pm[k * step];
+        si[(size_t)k * nt] = pw[k * step];
+        sn[(size_t)k * nt] = (c.norm_mode != JF_NORM_NONE) ? pn[k * step] : T(0);
+    }
+    // phase 2: regulate in place (own slots only: no synchronisation needed)
     T nmax = -Num<T>::big;
     if (c.norm_mode == JF_NORM_RAW) {
-        for (int k = 0; k < K; ++k) nmax = tmax(nmax, pn[k * step]);
+        for (int k = 0; k < K; ++k) nmax = tmax(nmax, sn[(size_t)k * nt]);
     }
     T nsum = 0, mmin = Num<T>::big, mmax = -Num<T>::big;
     JF_UNROLL_K
     for (int k = 0; k < K; ++k) {
-        const T m = pm[k * step];
-        T w, iw;
-        regulate_width(pw[k * step], c.w_min, c.inv_w_max, w, iw);
+        const T m = sm[(size_t)k * nt];
+        const T iw = regulate_inv_width(si[(size_t)k * nt], c.w_min, c.inv_w_max);
         T g;
-        if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(pn[k * step], c.n_min, c.n_max);
-        else if (c.norm_mode == JF_NORM_RAW) g = exp(pn[k * step] - nmax);
+        if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(sn[(size_t)k * nt], c.n_min, c.n_max);
+        else if (c.norm_mode == JF_NORM_RAW) g = exp(sn[(size_t)k * nt] - nmax);
         else g = T(1);
         nsum += g;
         mmin = tmin(mmin, m);
         mmax = tmax(mmax, m);
-        sm[(size_t)k * nt] = m;
         si[(size_t)k * nt] = iw;
         sn[(size_t)k * nt] = g;
     }
@@ -293,9 +308,7 @@ __device__ __noinline__ T logit_phi(T t) {
     return t > 0 ? v : -v;
 }
 
-// 1/x for a positive normal x (hardware seed + two Newton steps; no special-case handling)
-JF_DEVINL double rcp_pos(double x) { return rcp_1to2(x); }
-JF_DEVINL float rcp_pos(float x) { return 1.0f / x; }
+template <typename T> JF_DEVINL T rcp_pos(T x) { return rcp_pos_(x); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Root finding for the sampling direction (reference: 25 bisections on [-1e5,1e5] + <=20 masked Newton steps,
