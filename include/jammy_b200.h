@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define JF_ABI_VERSION 1
+#define JF_ABI_VERSION 2
 
 #define JF_MAX_LAYERS 16
 #define JF_MAX_SUBPDFS 8
@@ -45,6 +45,8 @@ extern "C" {
 #define JF_MAX_DIM 16      /* max intrinsic dimension of one Euclidean sub-pdf */
 #define JF_MAX_KDE 32      /* max num_kde of a "g" layer */
 #define JF_STATUS_WORDS 4
+#define JF_MAX_NESTED 4    /* spline sub-flows (vertical + circular) of one "f" layer */
+#define JF_MAX_BINS 32     /* max num_basis_functions of a rational-quadratic spline */
 
 /* dtype of all floating-point buffers of a call */
 #define JF_F32 0
@@ -56,7 +58,20 @@ extern "C" {
 
 /* layer kinds (reference layer codes, flow_options.py:25-240) */
 #define JF_LAYER_GF 1  /* "g" gf_block */
-#define JF_LAYER_FVM 2 /* "f" fisher_von_mises_2d ("n" alias) */
+#define JF_LAYER_FVM 2 /* "f" fisher_von_mises_2d ("n" alias), optionally with vertical/circular spline sub-flows */
+#define JF_LAYER_RQS 3      /* "r" rational_quadratic_spline on an interval */
+#define JF_LAYER_S1SPLINE 4 /* "o" spline_1d on the circle */
+#define JF_LAYER_MOEBIUS 5  /* "m" moebius on the circle */
+#define JF_LAYER_EXPMAP 6   /* "v" exponential_map_s2 (exponential potential) */
+
+/* spline variants (layers/spline_fns.py:45-186 / :361-559 / :561-760) */
+#define JF_SPLINE_PLAIN 0
+#define JF_SPLINE_SMOOTH 1
+#define JF_SPLINE_CIRCULAR 2
+/* where the knot derivatives of a spline come from */
+#define JF_BD_PARAMS 0   /* all from parameters */
+#define JF_BD_FIXED 1    /* boundary derivatives fixed (fix_boundary_derivatives > 0) */
+#define JF_BD_PERIODIC 2 /* "o", not smooth: first derivative copied to the end (splines_1d.py:176) */
 
 /* inverse-CDF stage of "g" (gaussianization_flow.py:480-671) */
 #define JF_INV_ISIGMOID 0
@@ -82,6 +97,26 @@ extern "C" {
 #define JF_ERR_BAD_ARG -3
 #define JF_ERR_WORKSPACE -4
 
+/* One rational-quadratic spline transformation as an "r" / "o" layer configures it
+ * (layers/intervals/rational_quadratic_spline.py:62-178, layers/spheres/splines_1d.py:9-109). */
+typedef struct JfSplineDesc {
+    int32_t kind;              /* JF_SPLINE_* */
+    int32_t n_bins;            /* num_basis_functions */
+    int32_t n_w, n_h, n_d;     /* raw width / height / derivative parameters in the slice, in this order */
+    int32_t fix_first;         /* fix_first_width_n_height_to_zero */
+    int32_t fix_second;        /* also_fix_second_width_to_zero */
+    int32_t indep;             /* independent_width_height_parametrization: heights += widths */
+    int32_t bd_mode;           /* JF_BD_* */
+    int32_t natural_direction; /* "o": which direction is the closed-form one (splines_1d.py:162-164) */
+    int32_t param_offset;      /* nested in "f": offset from the first sub-flow parameter; else 0 */
+    int32_t reserved;
+    double lo, hi;             /* support = image */
+    double min_w, min_h, min_d;
+    double bd_fixed;           /* softplus^-1 of the fixed boundary derivative (rational_quadratic_spline.py:117-120) */
+    double max_ratio;          /* restrict_max_min_width_height_ratio, <= 0: off */
+    double reserved1;
+} JfSplineDesc;
+
 typedef struct JfLayerDesc {
     int32_t kind;         /* JF_LAYER_* */
     int32_t dim;          /* intrinsic dimension of the layer */
@@ -92,17 +127,22 @@ typedef struct JfLayerDesc {
     int32_t inv_type;     /* g: JF_INV_* */
     int32_t norm_mode;    /* g: JF_NORM_* */
     int32_t has_offset;   /* g: model_offset (euclidean_base.py:34-75); offset params come first in the slice */
-    int32_t first;        /* s2: layer also applies the plane<->sphere base chart (sphere_base.py:637-648) */
-    int32_t reserved0;
-    int32_t reserved1;
+    int32_t first;        /* s1/s2/interval: layer also applies the base chart of the sub-pdf (sphere_base.py:637-648,
+                             interval_base.py:61-79) */
+    int32_t natural_direction; /* o, m, v */
+    int32_t max_iter;     /* v: max_num_newton_iter */
+    int32_t n_vertical;   /* f: number of nested "r" sub-flows, spline[0 .. n_vertical) */
+    int32_t n_circular;   /* f: number of nested "o" sub-flows, spline[n_vertical .. n_vertical+n_circular) */
     double w_min, w_max; /* g: width bounds (gaussianization_flow.py:300-317) */
     double n_min, n_max; /* g: norm bounds (gaussianization_flow.py:342) */
     double z_sign;       /* f: z_scaling_factor (+1/-1, fvm_2d.py:96-99) */
     double min_kappa;    /* f: kappa = exp(raw) + min_kappa (fvm_2d.py:123) */
+    double lo, hi;       /* r: interval boundaries */
+    JfSplineDesc spline[JF_MAX_NESTED]; /* r, o: spline[0]; f: nested sub-flows */
 } JfLayerDesc;
 
 typedef struct JfSubPdfDesc {
-    int32_t manifold;   /* 'e' or 's' (ASCII) */
+    int32_t manifold;   /* 'e', 's' or 'i' (ASCII) */
     int32_t dim;        /* intrinsic dimension */
     int32_t n_layers;
     int32_t n_params;   /* sum of the layers' n_params */
@@ -119,7 +159,7 @@ typedef struct JfMlpDesc {
 /*
  * Apply all layers of ONE sub-pdf to B rows.
  *   in / out        [B, in_cols] / [B, out_cols] row-major with leading dimensions ld_in / ld_out (elements).
- *                   LOGPDF: in = target coordinates (e: d; s2: theta,phi), out = base coordinates.
+ *                   LOGPDF: in = target coordinates (e: d; s2: theta,phi; s1: angle; interval: x), out = base coordinates.
  *                   SAMPLE: in = base normals, out = target coordinates.
  *   params          raw parameters in the reference's `extra_inputs` order; element (j,row) is
  *                   params[j*p_stride_param + row*p_stride_row].  p_stride_row == 0 means one shared vector
@@ -128,7 +168,8 @@ typedef struct JfMlpDesc {
  *                   unless the two pointers alias -- reference tests/test_general.py:533-550).
  *   logbase_in/out  [B] optional (NULL to skip): out = in + sum_j log N(z_j; 0,1) over this sub-pdf's base coords.
  *   emb_out         optional [B, ld_emb]: embedding of the TARGET coordinates handed to later MLPs
- *                   (`_embedding_conditional_return`, main/default.py:1050-1053): e -> identity (d), s2 -> (x,y,z).
+ *                   (`_embedding_conditional_return`, main/default.py:1050-1053): e/interval -> identity (d),
+ *                   s2 -> (x,y,z), s1 -> (cos, sin).
  */
 int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int direction,
                     const void* in, int64_t ld_in,
@@ -218,7 +259,7 @@ int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* 
 /* number of kernel launches issued by this library since process start (for bench.py's gpu_launches) */
 int64_t jf_launch_count(void);
 /* sizeof() of the ABI structs as compiled into the library (0: JfLayerDesc, 1: JfSubPdfDesc, 2: JfMlpDesc,
- * 3: JfPdfDesc, 4: JfPdfParams); bindings assert these against their own mirrors. */
+ * 3: JfPdfDesc, 4: JfPdfParams, 5: JfSplineDesc); bindings assert these against their own mirrors. */
 int64_t jf_struct_size(int which);
 
 #ifdef __cplusplus

@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libjammy_b200.so")
 
 # ---- constants (keep in sync with include/jammy_b200.h; checked by tests/test_cabi_symbols.py) -----------------------
-JF_ABI_VERSION = 1
+JF_ABI_VERSION = 2
 JF_MAX_LAYERS = 16
 JF_MAX_SUBPDFS = 8
 JF_MAX_MLP_LINEAR = 6
@@ -18,21 +18,35 @@ JF_MAX_MLP_SEGMENTS = 10
 JF_MAX_DIM = 16
 JF_MAX_KDE = 32
 JF_STATUS_WORDS = 4
+JF_MAX_NESTED = 4
+JF_MAX_BINS = 32
 JF_F32, JF_F64 = 0, 1
 JF_DIR_LOGPDF, JF_DIR_SAMPLE = 0, 1
-JF_LAYER_GF, JF_LAYER_FVM = 1, 2
+JF_LAYER_GF, JF_LAYER_FVM, JF_LAYER_RQS, JF_LAYER_S1SPLINE, JF_LAYER_MOEBIUS, JF_LAYER_EXPMAP = 1, 2, 3, 4, 5, 6
+JF_SPLINE_PLAIN, JF_SPLINE_SMOOTH, JF_SPLINE_CIRCULAR = 0, 1, 2
+JF_BD_PARAMS, JF_BD_FIXED, JF_BD_PERIODIC = 0, 1, 2
 JF_NORM_NONE, JF_NORM_RAW, JF_NORM_REGULATED = 0, 1, 2
 JF_STATUS_NONFINITE, JF_STATUS_UNCONVERGED, JF_STATUS_OUT_OF_RANGE, JF_STATUS_ITERATIONS = 0, 1, 2, 3
 ERRORS = {-1: "JF_ERR_BAD_DESC (invalid descriptor)", -2: "JF_ERR_UNSUPPORTED (no kernel for this configuration)",
           -3: "JF_ERR_BAD_ARG (invalid argument)", -4: "JF_ERR_WORKSPACE (workspace missing or too small)"}
 
 
+class JfSplineDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_bins", C.c_int32), ("n_w", C.c_int32), ("n_h", C.c_int32), ("n_d", C.c_int32),
+                ("fix_first", C.c_int32), ("fix_second", C.c_int32), ("indep", C.c_int32), ("bd_mode", C.c_int32),
+                ("natural_direction", C.c_int32), ("param_offset", C.c_int32), ("reserved", C.c_int32),
+                ("lo", C.c_double), ("hi", C.c_double), ("min_w", C.c_double), ("min_h", C.c_double),
+                ("min_d", C.c_double), ("bd_fixed", C.c_double), ("max_ratio", C.c_double), ("reserved1", C.c_double)]
+
+
 class JfLayerDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_params", C.c_int32), ("param_offset", C.c_int32),
                 ("K", C.c_int32), ("hh_iter", C.c_int32), ("inv_type", C.c_int32), ("norm_mode", C.c_int32),
-                ("has_offset", C.c_int32), ("first", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+                ("has_offset", C.c_int32), ("first", C.c_int32), ("natural_direction", C.c_int32),
+                ("max_iter", C.c_int32), ("n_vertical", C.c_int32), ("n_circular", C.c_int32),
                 ("w_min", C.c_double), ("w_max", C.c_double), ("n_min", C.c_double), ("n_max", C.c_double),
-                ("z_sign", C.c_double), ("min_kappa", C.c_double)]
+                ("z_sign", C.c_double), ("min_kappa", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
+                ("spline", JfSplineDesc * JF_MAX_NESTED)]
 
 
 class JfSubPdfDesc(C.Structure):
@@ -103,7 +117,7 @@ def load():
         fn.argtypes = args
     if lib.jf_abi_version() != JF_ABI_VERSION:
         raise RuntimeError("libjammy_b200.so ABI version %d != binding %d" % (lib.jf_abi_version(), JF_ABI_VERSION))
-    for which, st in enumerate((JfLayerDesc, JfSubPdfDesc, JfMlpDesc, JfPdfDesc, JfPdfParams)):
+    for which, st in enumerate((JfLayerDesc, JfSubPdfDesc, JfMlpDesc, JfPdfDesc, JfPdfParams, JfSplineDesc)):
         if lib.jf_struct_size(which) != C.sizeof(st):
             raise RuntimeError("ABI struct %s: library sizeof %d != binding %d"
                                % (st.__name__, lib.jf_struct_size(which), C.sizeof(st)))

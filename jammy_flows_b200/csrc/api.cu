@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include "subpdf_kernels.cuh"
 #include "gf_launch.cuh"
 #include "mlp_kernels.cuh"
@@ -71,23 +72,119 @@ static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, 
     return check_launch();
 }
 
+// JfSplineDesc -> device constants.  `rel_off`: extra offset added to the descriptor's param_offset.
+template <typename T>
+static int fill_spline(SplineC<T>& c, const JfSplineDesc& d, int rel_off) {
+    if (d.n_bins < 1 || d.n_bins > JF_MAX_BINS) return JF_ERR_UNSUPPORTED;
+    if (d.kind < JF_SPLINE_PLAIN || d.kind > JF_SPLINE_CIRCULAR || d.bd_mode < JF_BD_PARAMS || d.bd_mode > JF_BD_PERIODIC)
+        return JF_ERR_BAD_DESC;
+    if (d.kind == JF_SPLINE_SMOOTH && d.n_bins > 3) return JF_ERR_UNSUPPORTED;     // reference: 2 or 3 bins only
+    if (d.kind == JF_SPLINE_CIRCULAR && d.n_bins != 2) return JF_ERR_UNSUPPORTED;
+    if (!(d.hi > d.lo) || d.min_w * d.n_bins > 1.0 || d.min_h * d.n_bins > 1.0) return JF_ERR_BAD_DESC;
+    // parameter counts implied by the options (rational_quadratic_spline.py:98-157, splines_1d.py:38-94)
+    const bool mirror = d.kind == JF_SPLINE_SMOOTH && d.n_bins == 3;
+    const int L = d.n_bins - (mirror ? 1 : 0);
+    const int zw = d.fix_first ? (d.fix_second ? 2 : 1) : 0, zh = d.fix_first ? 1 : 0;
+    int nd;
+    if (d.kind == JF_SPLINE_PLAIN) nd = d.bd_mode == JF_BD_FIXED ? d.n_bins - 1 : (d.bd_mode == JF_BD_PERIODIC ? d.n_bins : d.n_bins + 1);
+    else if (d.kind == JF_SPLINE_SMOOTH) nd = d.bd_mode == JF_BD_FIXED ? 0 : 2;
+    else nd = 0;
+    if (d.n_w != L - zw || d.n_h != L - zh || d.n_d != nd || d.n_w < 0) return JF_ERR_BAD_DESC;
+    c.kind = d.kind; c.n_bins = d.n_bins; c.n_w = d.n_w; c.n_h = d.n_h; c.n_d = d.n_d;
+    c.fix_first = d.fix_first; c.fix_second = d.fix_second; c.indep = d.indep; c.bd_mode = d.bd_mode;
+    c.natural_direction = d.natural_direction; c.raw_off = d.param_offset + rel_off; c.pad_ = 0;
+    c.lo = (T)d.lo; c.hi = (T)d.hi; c.min_w = (T)d.min_w; c.min_h = (T)d.min_h; c.min_d = (T)d.min_d;
+    c.bd_fixed = (T)d.bd_fixed;
+    c.ln_max_ratio = T(-1);
+    if (d.max_ratio > 0.0) {
+        if (d.n_bins < 2) return JF_ERR_BAD_DESC;
+        const double l = (log(d.max_ratio) - log((double)(d.n_bins - 1))) / 2.0;
+        if (!(l > 0.0)) return JF_ERR_BAD_DESC;
+        c.ln_max_ratio = (T)l;
+    }
+    return JF_OK;
+}
+
 template <typename T>
 static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaStream_t st) {
     if (desc->dim != 2) return JF_ERR_UNSUPPORTED;
+    int n_sp = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
         const JfLayerDesc& L = desc->layers[l];
-        if (L.kind != JF_LAYER_FVM) return JF_ERR_UNSUPPORTED;
-        if ((l == 0) != (L.first != 0) && L.first != 0) return JF_ERR_BAD_DESC;   // only layer 0 may carry the chart
-        const int expect = (L.hh_iter > 0 ? L.hh_iter * 3 : 0) + 1;
-        if (expect != L.n_params) return JF_ERR_BAD_DESC;
+        if (L.kind != JF_LAYER_FVM && L.kind != JF_LAYER_EXPMAP) return JF_ERR_UNSUPPORTED;
+        if (L.first != 0 && l != 0) return JF_ERR_BAD_DESC;   // only layer 0 may carry the chart
         FvmLayerC& c = g.layers[l];
+        memset(&c, 0, sizeof(c));
+        c.kind = L.kind;
         c.add_rotation = L.hh_iter > 0; c.hh_iter = L.hh_iter; c.first = L.first; c.raw_off = L.param_offset;
-        c.z_sign = L.z_sign; c.min_kappa = L.min_kappa;
+        const int n_hh = L.hh_iter > 0 ? L.hh_iter * 3 : 0;
+        if (L.kind == JF_LAYER_FVM) {
+            c.z_sign = L.z_sign; c.min_kappa = L.min_kappa;
+            if (L.n_vertical < 0 || L.n_circular < 0 || L.n_vertical + L.n_circular > JF_MAX_NESTED) return JF_ERR_BAD_DESC;
+            if (n_sp + L.n_vertical + L.n_circular > kS2MaxSplines) return JF_ERR_UNSUPPORTED;
+            c.v_first = n_sp; c.n_vertical = L.n_vertical;
+            c.c_first = n_sp + L.n_vertical; c.n_circular = L.n_circular;
+            int expect = n_hh + 1, off = 0;
+            for (int i = 0; i < L.n_vertical + L.n_circular; ++i) {
+                if (L.spline[i].param_offset != off) return JF_ERR_BAD_DESC;
+                const int rc = fill_spline<T>(g.splines[n_sp], L.spline[i], 0);
+                if (rc != JF_OK) return rc;
+                off += g.splines[n_sp].n_params();
+                ++n_sp;
+            }
+            expect += off;
+            if (expect != L.n_params) return JF_ERR_BAD_DESC;
+        } else {
+            if (L.K < 1 || L.K > kMaxExpComp) return JF_ERR_UNSUPPORTED;
+            if (n_hh + 5 * L.K != L.n_params) return JF_ERR_BAD_DESC;
+            c.K = L.K; c.natural_direction = L.natural_direction; c.max_iter = L.max_iter > 0 ? L.max_iter : 1000;
+        }
     }
-    const int threads = 256;
+    const int threads = 128;
     const int64_t blocks = (g.a.B + threads - 1) / threads;
     if (direction == JF_DIR_LOGPDF) s2_chain_kernel<T, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, 0, st>>>(g);
     else s2_chain_kernel<T, JF_DIR_SAMPLE><<<(unsigned)blocks, threads, 0, st>>>(g);
+    return check_launch();
+}
+
+// one-dimensional sub-pdfs: interval ("r") and circle ("o", "m")
+template <typename T>
+static int apply_chain1(const JfSubPdfDesc* desc, int direction, Chain1Args<T>& g, cudaStream_t st) {
+    if (desc->dim != 1) return JF_ERR_UNSUPPORTED;
+    g.manifold = desc->manifold;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const JfLayerDesc& L = desc->layers[l];
+        Layer1C<T>& c = g.layers[l];
+        memset(&c, 0, sizeof(c));
+        if (L.first != 0 && l != 0) return JF_ERR_BAD_DESC;
+        c.kind = L.kind; c.first = L.first; c.raw_off = L.param_offset; c.natural_direction = L.natural_direction;
+        if (desc->manifold == 'i') {
+            if (L.kind != JF_LAYER_RQS) return JF_ERR_UNSUPPORTED;
+            if (!(L.hi > L.lo)) return JF_ERR_BAD_DESC;
+            c.lo = (T)L.lo; c.hi = (T)L.hi;
+            const int rc = fill_spline<T>(c.sp, L.spline[0], 0);
+            if (rc != JF_OK) return rc;
+            if (c.sp.n_params() != L.n_params) return JF_ERR_BAD_DESC;
+        } else {
+            if (L.hh_iter < 0 || L.hh_iter > 8) return JF_ERR_UNSUPPORTED;
+            c.hh_iter = L.hh_iter;
+            if (L.kind == JF_LAYER_S1SPLINE) {
+                const int rc = fill_spline<T>(c.sp, L.spline[0], 0);
+                if (rc != JF_OK) return rc;
+                if (c.sp.n_params() + 2 * L.hh_iter != L.n_params) return JF_ERR_BAD_DESC;
+            } else if (L.kind == JF_LAYER_MOEBIUS) {
+                if (L.K < 1 || L.K > kMaxMoebius) return JF_ERR_UNSUPPORTED;
+                if (4 * L.K + 2 * L.hh_iter != L.n_params) return JF_ERR_BAD_DESC;
+                c.K = L.K;
+            } else {
+                return JF_ERR_UNSUPPORTED;
+            }
+        }
+    }
+    const int threads = 128;
+    const int64_t blocks = (g.a.B + threads - 1) / threads;
+    if (direction == JF_DIR_LOGPDF) chain1_kernel<T, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, 0, st>>>(g);
+    else chain1_kernel<T, JF_DIR_SAMPLE><<<(unsigned)blocks, threads, 0, st>>>(g);
     return check_launch();
 }
 
@@ -101,6 +198,12 @@ static int subpdf_apply_t(const JfSubPdfDesc* desc, int direction, const void* i
         fill_common<T>(g.a, desc, in, ld_in, params, sp, sr, logdet_in, logdet_out, logbase_in, logbase_out, out, ld_out,
                        emb_out, ld_emb, B, status);
         return apply_gf<T>(desc, direction, g, st);
+    }
+    if ((desc->manifold == 's' && desc->dim == 1) || desc->manifold == 'i') {
+        Chain1Args<T> g;
+        fill_common<T>(g.a, desc, in, ld_in, params, sp, sr, logdet_in, logdet_out, logbase_in, logbase_out, out, ld_out,
+                       emb_out, ld_emb, B, status);
+        return apply_chain1<T>(desc, direction, g, st);
     }
     if (desc->manifold == 's') {
         S2Args<T> g;
@@ -246,7 +349,7 @@ static int ws_layout(const JfPdfDesc* d, int64_t chunk, WsLayout& w) {
     w.params = off; off = align_up(off + (int64_t)pmax * chunk * es, 256);
     for (int k = 0; k < d->n_sub; ++k) {
         w.emb[k] = off;
-        if (d->sub[k].manifold != 'e') off = align_up(off + (int64_t)d->emb_dim[k] * chunk * es, 256);
+        if (d->sub[k].manifold == 's') off = align_up(off + (int64_t)d->emb_dim[k] * chunk * es, 256);
     }
     w.logdet = off; off = align_up(off + chunk * es, 256);
     w.logbase = off; off = align_up(off + chunk * es, 256);
@@ -306,7 +409,7 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
                 for (int j = 0; j < k; ++j) {
                     if (ns >= JF_MAX_MLP_SEGMENTS) return JF_ERR_UNSUPPORTED;
                     md.seg_cols[ns] = d->emb_dim[j];
-                    if (d->sub[j].manifold == 'e') {
+                    if (d->sub[j].manifold != 's') {
                         seg_ptr[ns] = tgt_c + (int64_t)d->target_col[j] * es;
                         seg_ld[ns] = ld_tgt;
                     } else {
@@ -329,7 +432,7 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
             const int out_col = logpdf ? d->base_col[k] : d->target_col[k];
             bool need_emb = false;
             for (int j = k + 1; j < d->n_sub; ++j) need_emb = need_emb || d->has_mlp[j];
-            void* emb = (need_emb && sp->manifold != 'e') ? (void*)(ws + w.emb[k]) : nullptr;
+            void* emb = (need_emb && sp->manifold == 's') ? (void*)(ws + w.emb[k]) : nullptr;
             rc = jf_subpdf_apply(sp, d->dtype, direction, src_c + (int64_t)in_col * es, ld_src, params, sj, sr,
                                  k == 0 ? nullptr : logdet, logdet, k == 0 ? nullptr : logbase, logbase,
                                  dst_c + (int64_t)out_col * es, ld_dst_c, emb, d->emb_dim[k], n, status, st);
@@ -488,6 +591,7 @@ extern "C" int64_t jf_struct_size(int which) {
         case 2: return sizeof(JfMlpDesc);
         case 3: return sizeof(JfPdfDesc);
         case 4: return sizeof(JfPdfParams);
+        case 5: return sizeof(JfSplineDesc);
         default: return -1;
     }
 }

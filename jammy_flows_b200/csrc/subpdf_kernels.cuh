@@ -1,25 +1,11 @@
 // Sub-pdf kernels: all layers of one sub-pdf, fused, one thread per row.
 #pragma once
+#include "subpdf_args.cuh"
 #include "gf.cuh"
 #include "s2.cuh"
+#include "chain1.cuh"
 
 namespace jf {
-
-template <typename T>
-struct SubPdfArgs {
-    // geometry
-    int n_layers, d;
-    int64_t B;
-    // io
-    const T* in;  int64_t ld_in;
-    T* out;       int64_t ld_out;
-    const T* params; int64_t sj, sr;   // element (j,row) at params[j*sj + row*sr]; sr == 0: shared
-    const T* logdet_in;  T* logdet_out;
-    const T* logbase_in; T* logbase_out;
-    T* emb_out; int64_t ld_emb;
-    int64_t* status;
-    int tab_total;   // size of the processed table (elements) in shared mode
-};
 
 template <typename T>
 struct GfChainArgs {
@@ -100,10 +86,13 @@ __global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant_
     }
 }
 
+constexpr int kS2MaxSplines = 8;   // nested spline sub-flows of all "f" layers of one sub-pdf
+
 template <typename T>
 struct S2Args {
     SubPdfArgs<T> a;
     FvmLayerC layers[JF_MAX_LAYERS];
+    SplineC<T> splines[kS2MaxSplines];
 };
 
 // S2 sub-pdf: chain of "f" layers; the first layer carries the plane<->sphere base chart.
@@ -116,6 +105,7 @@ __global__ void __launch_bounds__(256) s2_chain_kernel(const __grid_constant__ S
     T logdet = a.logdet_in ? a.logdet_in[row] : T(0);
     const T* prow = a.params + row * a.sr;
     T zsq;
+    int oor = 0, evals = 0, unconv = 0;
     if (DIR == JF_DIR_LOGPDF) {
         if (a.emb_out) {
             T e[3], dummy = 0;
@@ -124,11 +114,17 @@ __global__ void __launch_bounds__(256) s2_chain_kernel(const __grid_constant__ S
             a.emb_out[row * a.ld_emb + 1] = e[1];
             a.emb_out[row * a.ld_emb + 2] = e[2];
         }
-        for (int l = a.n_layers - 1; l >= 0; --l) fvm_logpdf<T>(c0, c1, logdet, g.layers[l], prow, a.sj);
+        for (int l = a.n_layers - 1; l >= 0; --l) {
+            if (g.layers[l].kind == JF_LAYER_EXPMAP) v_layer<T>(true, c0, c1, logdet, g.layers[l], prow, a.sj, evals, unconv);
+            else fvm_logpdf<T>(c0, c1, logdet, g.layers[l], g.splines, prow, a.sj, oor);
+        }
         zsq = c0 * c0 + c1 * c1;
     } else {
         zsq = c0 * c0 + c1 * c1;
-        for (int l = 0; l < a.n_layers; ++l) fvm_sample<T>(c0, c1, logdet, g.layers[l], prow, a.sj);
+        for (int l = 0; l < a.n_layers; ++l) {
+            if (g.layers[l].kind == JF_LAYER_EXPMAP) v_layer<T>(false, c0, c1, logdet, g.layers[l], prow, a.sj, evals, unconv);
+            else fvm_sample<T>(c0, c1, logdet, g.layers[l], g.splines, prow, a.sj, oor);
+        }
         if (a.emb_out) {
             T e[3], dummy = 0;
             s2_to_embedding(c0, c1, e, dummy);
@@ -140,6 +136,9 @@ __global__ void __launch_bounds__(256) s2_chain_kernel(const __grid_constant__ S
     a.out[row * a.ld_out + 0] = c0;
     a.out[row * a.ld_out + 1] = c1;
     if (!finite_(c0) || !finite_(c1) || !finite_(logdet)) status_add(a.status, JF_STATUS_NONFINITE, 1);
+    if (oor) status_add(a.status, JF_STATUS_OUT_OF_RANGE, oor);
+    if (unconv) status_add(a.status, JF_STATUS_UNCONVERGED, unconv);
+    status_add_warp(a.status, JF_STATUS_ITERATIONS, evals);
     if (a.logdet_out) a.logdet_out[row] = logdet;
     if (a.logbase_out) {
         const T prev = a.logbase_in ? a.logbase_in[row] : T(0);

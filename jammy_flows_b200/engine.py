@@ -63,8 +63,50 @@ def fill_layer_desc(ld, desc, param_offset):
         ld.first = desc["first"]
         ld.z_sign = desc["z_sign"]
         ld.min_kappa = desc["min_kappa"]
+        nested = list(desc.get("vertical", [])) + list(desc.get("circular", []))
+        if len(nested) > _cabi.JF_MAX_NESTED:
+            raise NotImplementedError("more than %d nested spline sub-flows" % _cabi.JF_MAX_NESTED)
+        ld.n_vertical = len(desc.get("vertical", []))
+        ld.n_circular = len(desc.get("circular", []))
+        for i, sp in enumerate(nested):
+            fill_spline_desc(ld.spline[i], sp)
+    elif desc["code"] == "r":
+        ld.kind = _cabi.JF_LAYER_RQS
+        ld.first = desc["first"]
+        ld.lo, ld.hi = desc["lo"], desc["hi"]
+        fill_spline_desc(ld.spline[0], desc["spline"])
+    elif desc["code"] == "o":
+        ld.kind = _cabi.JF_LAYER_S1SPLINE
+        ld.hh_iter = desc["hh_iter"] if desc["add_rotation"] else 0
+        ld.first = desc["first"]
+        ld.natural_direction = desc["natural_direction"]
+        fill_spline_desc(ld.spline[0], desc["spline"])
+    elif desc["code"] == "m":
+        ld.kind = _cabi.JF_LAYER_MOEBIUS
+        ld.hh_iter = desc["hh_iter"] if desc["add_rotation"] else 0
+        ld.first = desc["first"]
+        ld.natural_direction = desc["natural_direction"]
+        ld.K = desc["K"]
+    elif desc["code"] == "v":
+        ld.kind = _cabi.JF_LAYER_EXPMAP
+        ld.hh_iter = desc["hh_iter"] if desc["add_rotation"] else 0
+        ld.first = desc["first"]
+        ld.natural_direction = desc["natural_direction"]
+        ld.K = desc["K"]
+        ld.max_iter = desc["max_iter"]
     else:
         raise NotImplementedError("no sm_100a kernel for layer code %r" % desc["code"])
+
+
+_SPLINE_KINDS = {"plain": _cabi.JF_SPLINE_PLAIN, "smooth": _cabi.JF_SPLINE_SMOOTH, "circular": _cabi.JF_SPLINE_CIRCULAR}
+
+
+def fill_spline_desc(sd, spec):
+    """python spline spec (layers._spline_options._spline_spec) -> JfSplineDesc"""
+    sd.kind = _SPLINE_KINDS[spec["kind"]]
+    for name in ("n_bins", "n_w", "n_h", "n_d", "fix_first", "fix_second", "indep", "bd_mode", "natural_direction",
+                 "param_offset", "lo", "hi", "min_w", "min_h", "min_d", "bd_fixed", "max_ratio"):
+        setattr(sd, name, spec[name])
 
 
 def fill_subpdf_desc(sd, manifold, dim, layer_descs):

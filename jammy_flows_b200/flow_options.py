@@ -65,6 +65,50 @@ opts_dict["f"] = dict(module=layers.fisher_von_mises_2d, type="s", kwargs=dict(
     num_householder_iter=(-1, lambda x: (x == -1) or (x > 0)),
 ))
 
+# --- S1: Moebius (reference flow_options.py:95-101) and circular spline (:104-118) ---------------------------------
+opts_dict["m"] = dict(module=layers.moebius, type="s", kwargs=dict(
+    add_rotation=(0, [0, 1]),
+    num_basis_functions=(5, lambda x: x > 0),
+    natural_direction=(0, [0, 1]),
+))
+opts_dict["o"] = dict(module=layers.spline_1d, type="s", kwargs=dict(
+    add_rotation=(1, [0, 1]),
+    num_basis_functions=(2, lambda x: x > 0),
+    natural_direction=(1, [0, 1]),
+    fix_boundary_derivatives=(-1.0, lambda x: (x == -1.0) or (x > 0.0)),
+    smooth_second_derivative=(1, [0, 1]),
+    fix_first_width_n_height_to_zero=(0, [0, 1]),
+    also_fix_second_width_to_zero=(0, [0, 1]),
+    independent_width_height_parametrization=(0, [0, 1]),
+    min_width=(1e-4, lambda x: x > 0),
+    min_height=(1e-4, lambda x: x > 0),
+    min_derivative=(1e-4, lambda x: x > 0),
+))
+
+# --- S2: exponential-map flow (reference flow_options.py:126-135) --------------------------------------------------
+opts_dict["v"] = dict(module=layers.exponential_map_s2, type="s", kwargs=dict(
+    exp_map_type=("exponential", ["linear", "quadratic", "splines", "exponential"]),
+    num_components=(10, lambda x: x > 0),
+    natural_direction=(0, [0, 1]),
+    add_rotation=(0, [0, 1]),
+    max_num_newton_iter=(1000, lambda x: x > 0),
+    mean_parametrization=("old", ["old", "householder"]),
+))
+
+# --- Interval: rational-quadratic spline (reference flow_options.py:188-201) ----------------------------------------
+opts_dict["r"] = dict(module=layers.rational_quadratic_spline, type="i", kwargs=dict(
+    num_basis_functions=(5, lambda x: x > 0),
+    fix_boundary_derivatives=(-1.0, lambda x: (x == -1.0) or (x > 0.0)),
+    smooth_second_derivative=(0, lambda x: (type(x) == int) & (x >= 0)),
+    restrict_max_min_width_height_ratio=(-1.0, lambda x: (x == -1.0) or (x > 0.0)),
+    fix_first_width_n_height_to_zero=(0, [0, 1]),
+    also_fix_second_width_to_zero=(0, [0, 1]),
+    independent_width_height_parametrization=(0, [0, 1]),
+    min_width=(1e-4, lambda x: x > 0),
+    min_height=(1e-4, lambda x: x > 0),
+    min_derivative=(1e-4, lambda x: x > 0),
+))
+
 # "n": alias of "f" (see module docstring / SURVEY.md F2)
 opts_dict["n"] = opts_dict["f"]
 
@@ -78,10 +122,6 @@ OUT_OF_SCOPE = {
 # Codes on the SURVEY.md section 8 'next' list that are not built yet in this round.
 NOT_YET_BUILT = {
     "t": "affine/MVN layer (SURVEY.md section 8f rank 1)",
-    "r": "interval rational-quadratic spline (section 8a row a10)",
-    "o": "circular rational-quadratic spline (section 8a row a11)",
-    "m": "Moebius S1 layer (section 8a row a14)",
-    "v": "exponential-map S2 layer (section 8a row a15)",
     "x": "Euclidean identity layer", "y": "spherical identity layer", "z": "interval identity layer",
 }
 

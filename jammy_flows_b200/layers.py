@@ -243,8 +243,8 @@ class fisher_von_mises_2d(layer_base):
         if dimension != 2:
             raise Exception("2-D Flow")
         unsupported = []
-        if add_vertical_rq_spline_flow or add_circular_rq_spline_flow or add_correlated_rq_spline_flow:
-            unsupported.append("vertical/circular/correlated rq-spline sub-flows")
+        if add_correlated_rq_spline_flow:
+            unsupported.append("correlated rq-spline sub-flow (needs the AmortizableMLP path, SURVEY.md section 8f rank 4)")
         if kappa_prediction != "direct_log_real_bounded" or kappa_clamping:
             unsupported.append("kappa_prediction=%s kappa_clamping=%d" % (kappa_prediction, kappa_clamping))
         if add_rotation and rotation_mode != "householder":
@@ -253,9 +253,14 @@ class fisher_von_mises_2d(layer_base):
             unsupported.append("add_extra_rotation_inbetween=1")
         if boundary_cos_theta_identity_region != 0.0:
             unsupported.append("boundary_cos_theta_identity_region")
+        if add_circular_rq_spline_flow and circular_add_rotation:
+            # reference fvm_2d.py:207 asserts the same
+            raise AssertionError("Currently not allowing additional S-1 rotations (circular_add_rotation must be 0)")
         if len(unsupported) > 0:
             raise NotImplementedError("'f' layer options without an sm_100a kernel yet (SURVEY.md section 8a row a13): "
                                       + ", ".join(unsupported) + " -- there is no CPU fallback")
+        if spline_num_basis_functions == -1:
+            assert (vertical_smooth == 1), "num_basis_functions=-1 means alternating 2/3 as basis functions and requires smooth splines."
         self.euclidean_to_sphere_as_first = euclidean_to_sphere_as_first
         self.use_permanent_parameters = use_permanent_parameters
         self.add_rotation = add_rotation
@@ -275,12 +280,57 @@ class fisher_von_mises_2d(layer_base):
             self.loglike_kappa = nn.Parameter(torch.randn(1).unsqueeze(0))
         self.total_param_num += 1
 
+        # nested pass-through sub-flows (reference fvm_2d.py:158-225: `pdf("i1_-1.00_1.00", vertical_flow_defs, ...)`
+        # and `pdf("s1", circular_flow_defs, ...)` with amortize_everything / use_as_passthrough_instead_of_pdf).
+        # Only their static spline configuration is needed here; they hold no parameters and draw no random numbers.
+        self.add_vertical_rq_spline_flow = add_vertical_rq_spline_flow
+        self.add_circular_rq_spline_flow = add_circular_rq_spline_flow
+        self.vertical_layers, self.circular_layers = [], []
+        self.total_num_vertical_params = 0
+        if add_vertical_rq_spline_flow:
+            bound = float("%.2f" % (1.0 - boundary_cos_theta_identity_region))
+            for cur_r, code in enumerate(vertical_flow_defs):
+                assert code == "r", "vertical_flow_defs may only contain 'r' layers"
+                nb = spline_num_basis_functions
+                if spline_num_basis_functions == -1:
+                    nb = 3 if cur_r % 2 == 1 else 2
+                self.vertical_layers.append(rational_quadratic_spline(
+                    1, num_basis_functions=nb, low_boundary=-bound, high_boundary=bound,
+                    fix_boundary_derivatives=-1.0 if vertical_fix_boundary_derivative == 0 else 1.0,
+                    smooth_second_derivative=vertical_smooth,
+                    restrict_max_min_width_height_ratio=vertical_restrict_max_min_width_height_ratio,
+                    fix_first_width_n_height_to_zero=vertical_fix_first_width_n_height_to_zero,
+                    also_fix_second_width_to_zero=vertical_also_fix_second_width_to_zero,
+                    independent_width_height_parametrization=vertical_independent_width_height_parametrization))
+            self.total_num_vertical_params = sum(l.total_param_num for l in self.vertical_layers)
+            self.total_param_num += self.total_num_vertical_params
+            if use_permanent_parameters:
+                self.vertical_flow_params = nn.Parameter(torch.randn(1, self.total_num_vertical_params))
+        self.total_num_circular_params = 0
+        if add_circular_rq_spline_flow:
+            for code in circular_flow_defs:
+                assert code == "o", "circular_flow_defs may only contain 'o' layers"
+                self.circular_layers.append(spline_1d(
+                    1, euclidean_to_sphere_as_first=False, add_rotation=0, num_basis_functions=2,
+                    smooth_second_derivative=1,
+                    fix_first_width_n_height_to_zero=vertical_fix_first_width_n_height_to_zero,
+                    also_fix_second_width_to_zero=vertical_also_fix_second_width_to_zero,
+                    independent_width_height_parametrization=vertical_independent_width_height_parametrization))
+            self.total_num_circular_params = sum(l.total_param_num for l in self.circular_layers)
+            self.total_param_num += self.total_num_circular_params
+            if use_permanent_parameters:
+                self.circular_flow_params = nn.Parameter(torch.randn(1, self.total_num_circular_params))
+        if len(self.vertical_layers) + len(self.circular_layers) > 4:
+            raise NotImplementedError("more than 4 nested spline sub-flows in one 'f' layer (JF_MAX_NESTED)")
+
     # reference sphere_base.py:712-730 + fvm_2d.py:747-773
     def get_desired_init_parameters(self):
         par_list = []
         if self.num_householder_params > 0:
             par_list.append(torch.randn((self.num_householder_params)))
         par_list.append(torch.randn((1)) - 3.0)
+        par_list += [l.get_desired_init_parameters() for l in self.vertical_layers]
+        par_list += [l.get_desired_init_parameters() for l in self.circular_layers]
         return torch.cat(par_list)
 
     def init_params(self, params):
@@ -289,14 +339,407 @@ class fisher_von_mises_2d(layer_base):
         if self.add_rotation:
             self.householder_params.data = params[:n].reshape(1, n)
         self.loglike_kappa.data = params[n:n + 1].reshape(1, 1)
+        nv, nc = self.total_num_vertical_params, self.total_num_circular_params
+        if self.add_vertical_rq_spline_flow:
+            self.vertical_flow_params.data = params[n + 1:n + 1 + nv].reshape(1, nv)
+        if self.add_circular_rq_spline_flow:
+            self.circular_flow_params.data = params[n + 1 + nv:n + 1 + nv + nc].reshape(1, nc)
 
     def permanent_param_names(self):
-        return (["householder_params"] if self.num_householder_params > 0 else []) + ["loglike_kappa"]
+        names = (["householder_params"] if self.num_householder_params > 0 else []) + ["loglike_kappa"]
+        if self.add_vertical_rq_spline_flow:
+            names.append("vertical_flow_params")
+        if self.add_circular_rq_spline_flow:
+            names.append("circular_flow_params")
+        return names
 
     def descriptor(self):
+        off, vertical, circular = 0, [], []
+        for l in self.vertical_layers:
+            vertical.append(dict(l.spline_spec(), param_offset=off))
+            off += l.total_param_num
+        for l in self.circular_layers:
+            circular.append(dict(l.spline_spec(), param_offset=off))
+            off += l.total_param_num
         return dict(code="f", dim=2, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
                     z_sign=float(self.z_scaling_factor), min_kappa=float(self.min_kappa),
-                    first=int(self.euclidean_to_sphere_as_first), n_params=self.total_param_num)
+                    first=int(self.euclidean_to_sphere_as_first), vertical=vertical, circular=circular,
+                    n_params=self.total_param_num)
+
+    def _embedding_conditional_return(self, x):
+        from . import engine
+        if x.shape[1] == self.dimension:
+            return engine.s2_embedding(x)
+        return x
+
+    def _embedding_conditional_return_num(self):
+        return self.dimension + 1
+
+    def _get_layer_base_dimension(self):
+        if self.always_parametrize_in_embedding_space and not self.euclidean_to_sphere_as_first:
+            return self.dimension + 1
+        return self.dimension
+
+
+# =====================================================================================================================
+# rational-quadratic splines: option bookkeeping shared by "r" and "o"
+# =====================================================================================================================
+class _spline_options:
+    """Parameter counts and the static spline descriptor.  Reference: layers/intervals/rational_quadratic_spline.py:98-178
+    and layers/spheres/splines_1d.py:38-109 (the two constructors differ only in the derivative bookkeeping)."""
+
+    def _setup_spline(self, periodic, num_basis_functions, min_width, min_height, min_derivative,
+                      fix_boundary_derivatives, smooth_second_derivative, restrict_max_min_width_height_ratio,
+                      fix_first_width_n_height_to_zero, also_fix_second_width_to_zero,
+                      independent_width_height_parametrization, use_permanent_parameters):
+        self.num_basis_functions = num_basis_functions
+        self.num_width_params = num_basis_functions
+        self.num_height_params = num_basis_functions
+        self.fix_first_width_n_height_to_zero = fix_first_width_n_height_to_zero
+        self.also_fix_second_width_to_zero = also_fix_second_width_to_zero
+        if fix_first_width_n_height_to_zero:
+            self.num_width_params = num_basis_functions - 1
+            self.num_height_params = num_basis_functions - 1
+            if also_fix_second_width_to_zero > 0:
+                self.num_width_params -= 1
+        self.fix_boundary_derivatives = fix_boundary_derivatives
+        self.smooth_second_derivative = smooth_second_derivative
+        self.boundary_log_derivs_fixed_value = 0.0
+        if fix_boundary_derivatives > 0.0:
+            self.boundary_log_derivs_fixed_value = float(numpy.log(numpy.exp(fix_boundary_derivatives - min_derivative) - 1.0))
+        self.deriv_num_bd_subtraction = 0
+        if periodic:
+            # widths/heights Parameters are created BEFORE the derivative bookkeeping in splines_1d.py:56-63
+            if use_permanent_parameters:
+                self.rel_log_widths = nn.Parameter(torch.randn(self.num_width_params).type(torch.double).unsqueeze(0))
+                self.rel_log_heights = nn.Parameter(torch.randn(self.num_height_params).type(torch.double).unsqueeze(0))
+            if smooth_second_derivative == 1:
+                assert (num_basis_functions == 2), "Only support 2 basis functions for smooth derivative!"
+                self.deriv_num_bd_subtraction = 3
+            elif fix_boundary_derivatives > 0.0:
+                self.deriv_num_bd_subtraction = 2
+                assert (fix_boundary_derivatives > min_derivative), "Fixed boundary derivative should be larger than min derivative!"
+            else:
+                self.deriv_num_bd_subtraction = 1
+        else:
+            if smooth_second_derivative == 1:
+                assert ((num_basis_functions == 2) or (num_basis_functions == 3)), "Only support 2/3 basis functions for smooth derivative!"
+                if num_basis_functions == 2:
+                    self.deriv_num_bd_subtraction = 3 if fix_boundary_derivatives > 0.0 else 1
+                else:
+                    self.deriv_num_bd_subtraction = 4 if fix_boundary_derivatives > 0.0 else 2
+            elif fix_boundary_derivatives > 0.0:
+                self.deriv_num_bd_subtraction = 2
+                assert (fix_boundary_derivatives > min_derivative)
+        self.num_derivative_params = num_basis_functions + 1 - self.deriv_num_bd_subtraction
+        if smooth_second_derivative and num_basis_functions == 3:
+            self.num_width_params -= 1
+            self.num_height_params -= 1
+        if use_permanent_parameters:
+            if not periodic:
+                self.rel_log_widths = nn.Parameter(torch.randn(self.num_width_params).type(torch.double).unsqueeze(0))
+                self.rel_log_heights = nn.Parameter(torch.randn(self.num_height_params).type(torch.double).unsqueeze(0))
+            if self.num_derivative_params > 0:
+                self.rel_log_derivatives = nn.Parameter(torch.randn(self.num_derivative_params).type(torch.double).unsqueeze(0))
+        self.total_param_num += self.num_width_params + self.num_height_params + self.num_derivative_params
+        self.min_width, self.min_height, self.min_derivative = min_width, min_height, min_derivative
+        self.restrict_max_min_width_height_ratio = restrict_max_min_width_height_ratio
+        self.independent_width_height_parametrization = independent_width_height_parametrization
+        self._periodic = periodic
+
+    def _spline_spec(self, lo, hi, natural_direction):
+        if self.smooth_second_derivative:
+            kind = "circular" if self._periodic else "smooth"
+        else:
+            kind = "plain"
+        if self.fix_boundary_derivatives > 0.0 and kind != "circular":
+            bd_mode = 1
+        elif self._periodic and kind == "plain":
+            bd_mode = 2
+        else:
+            bd_mode = 0
+        return dict(kind=kind, n_bins=self.num_basis_functions, n_w=self.num_width_params, n_h=self.num_height_params,
+                    n_d=self.num_derivative_params, fix_first=int(self.fix_first_width_n_height_to_zero),
+                    fix_second=int(self.also_fix_second_width_to_zero),
+                    indep=int(self.independent_width_height_parametrization), bd_mode=bd_mode,
+                    bd_fixed=float(self.boundary_log_derivs_fixed_value), lo=float(lo), hi=float(hi),
+                    min_w=float(self.min_width), min_h=float(self.min_height), min_d=float(self.min_derivative),
+                    max_ratio=float(self.restrict_max_min_width_height_ratio), natural_direction=int(natural_direction),
+                    param_offset=0)
+
+    def _spline_init(self):
+        n = self.num_width_params + self.num_height_params + self.num_derivative_params
+        return torch.zeros(n) if self.smooth_second_derivative else torch.ones(n) * 0.54
+
+    def _spline_init_params(self, params):
+        c = 0
+        self.rel_log_widths.data[0, :] = params[c:c + self.num_width_params]
+        c += self.num_width_params
+        self.rel_log_heights.data[0, :] = params[c:c + self.num_height_params]
+        c += self.num_height_params
+        if self.num_derivative_params > 0:
+            self.rel_log_derivatives.data[0, :] = params[c:c + self.num_derivative_params]
+
+    def _spline_names(self):
+        return ["rel_log_widths", "rel_log_heights"] + (["rel_log_derivatives"] if self.num_derivative_params > 0 else [])
+
+
+# =====================================================================================================================
+# Interval: rational-quadratic spline "r"
+# =====================================================================================================================
+class rational_quadratic_spline(layer_base, _spline_options):
+    """Symbol "r".  Reference: layers/intervals/rational_quadratic_spline.py:62-178 (constructor),
+    layers/intervals/interval_base.py:8-31.  Parameter slice: [widths][heights][derivatives]."""
+
+    code = "r"
+    manifold = "i"
+
+    def __init__(self, dimension, num_basis_functions=10, euclidean_to_interval_as_first=0, use_permanent_parameters=0,
+                 low_boundary=0, high_boundary=1.0, min_width=1e-4, min_height=1e-4, min_derivative=1e-4,
+                 fix_boundary_derivatives=-1.0, smooth_second_derivative=0, restrict_max_min_width_height_ratio=-1.0,
+                 fix_first_width_n_height_to_zero=0, also_fix_second_width_to_zero=0,
+                 independent_width_height_parametrization=0):
+        super().__init__(dimension=dimension)
+        assert (self.dimension == 1)
+        if num_basis_functions > 32:
+            raise NotImplementedError("'r' with more than 32 basis functions (JF_MAX_BINS)")
+        self.use_permanent_parameters = use_permanent_parameters
+        self.low_boundary, self.high_boundary = low_boundary, high_boundary
+        self.interval_width = high_boundary - low_boundary
+        self.euclidean_to_interval_as_first = euclidean_to_interval_as_first
+        assert (self.high_boundary > self.low_boundary)
+        self._setup_spline(False, num_basis_functions, min_width, min_height, min_derivative, fix_boundary_derivatives,
+                           smooth_second_derivative, restrict_max_min_width_height_ratio,
+                           fix_first_width_n_height_to_zero, also_fix_second_width_to_zero,
+                           independent_width_height_parametrization, use_permanent_parameters)
+
+    def get_desired_init_parameters(self):
+        return self._spline_init()
+
+    def init_params(self, params):
+        assert (len(params) == self.total_param_num)
+        self._spline_init_params(params)
+
+    def permanent_param_names(self):
+        return self._spline_names()
+
+    def spline_spec(self):
+        return self._spline_spec(self.low_boundary, self.high_boundary, 1)
+
+    def descriptor(self):
+        return dict(code="r", dim=1, first=int(self.euclidean_to_interval_as_first), lo=float(self.low_boundary),
+                    hi=float(self.high_boundary), spline=self.spline_spec(), n_params=self.total_param_num)
+
+    def _embedding_conditional_return(self, x):
+        return x
+
+    def _embedding_conditional_return_num(self):
+        return self.dimension
+
+    def _get_layer_base_dimension(self):
+        return self.dimension
+
+    def transform_target_space(self, x, log_det=0.0, transform_from="default", transform_to="embedding"):
+        return x, log_det
+
+
+# =====================================================================================================================
+# S1 layers: "o" (circular spline) and "m" (Moebius)
+# =====================================================================================================================
+class _s1_base(layer_base):
+    """Reference: layers/spheres/sphere_base.py:42-110 with dimension 1 (rotation = Householder reflections in R^2,
+    parameters first in the layer slice)."""
+
+    manifold = "s"
+
+    def _setup_s1(self, euclidean_to_sphere_as_first, add_rotation, use_permanent_parameters):
+        self.euclidean_to_sphere_as_first = euclidean_to_sphere_as_first
+        self.use_permanent_parameters = use_permanent_parameters
+        self.add_rotation = add_rotation
+        self.num_householder_iter = 0
+        self.num_householder_params = 0
+        if add_rotation:
+            self.num_householder_iter = 2
+            self.num_householder_params = 4
+        if use_permanent_parameters and self.num_householder_params > 0:
+            self.householder_params = nn.Parameter(torch.randn((1, self.num_householder_params)))
+        self.total_param_num += self.num_householder_params
+
+    def _embedding_conditional_return(self, x):
+        if x.shape[1] == self.dimension:
+            return torch.cat([torch.cos(x), torch.sin(x)], dim=1)
+        return x
+
+    def _embedding_conditional_return_num(self):
+        return self.dimension + 1
+
+    def _get_layer_base_dimension(self):
+        if self.always_parametrize_in_embedding_space and not self.euclidean_to_sphere_as_first:
+            return self.dimension + 1
+        return self.dimension
+
+
+class spline_1d(_s1_base, _spline_options):
+    """Symbol "o".  Reference: layers/spheres/splines_1d.py:9-109."""
+
+    code = "o"
+
+    def __init__(self, dimension=1, euclidean_to_sphere_as_first=True, add_rotation=1, natural_direction=1,
+                 use_permanent_parameters=False, num_basis_functions=2, min_width=1e-4, min_height=1e-4,
+                 min_derivative=1e-4, fix_boundary_derivatives=-1.0, smooth_second_derivative=0,
+                 fix_first_width_n_height_to_zero=0, also_fix_second_width_to_zero=0,
+                 independent_width_height_parametrization=0):
+        super().__init__(dimension=1)
+        if dimension != 1:
+            raise Exception("The moebius flow is defined for dimension 1, but dimension %d is handed over" % (dimension))
+        if num_basis_functions > 32:
+            raise NotImplementedError("'o' with more than 32 basis functions (JF_MAX_BINS)")
+        self._setup_s1(euclidean_to_sphere_as_first, add_rotation, use_permanent_parameters)
+        self.natural_direction = natural_direction
+        self._setup_spline(True, num_basis_functions, min_width, min_height, min_derivative, fix_boundary_derivatives,
+                           smooth_second_derivative, -1.0, fix_first_width_n_height_to_zero,
+                           also_fix_second_width_to_zero, independent_width_height_parametrization,
+                           use_permanent_parameters)
+
+    def get_desired_init_parameters(self):
+        par_list = []
+        if self.num_householder_params > 0:
+            par_list.append(torch.randn((self.num_householder_params)))
+        par_list.append(self._spline_init())
+        return torch.cat(par_list)
+
+    def init_params(self, params):
+        assert (len(params) == self.total_param_num)
+        n = self.num_householder_params
+        if self.add_rotation:
+            self.householder_params.data = params[:n].reshape(1, n)
+        self._spline_init_params(params[n:])
+
+    def permanent_param_names(self):
+        return (["householder_params"] if self.num_householder_params > 0 else []) + self._spline_names()
+
+    def spline_spec(self):
+        return self._spline_spec(0.0, 2 * math.pi, self.natural_direction)
+
+    def descriptor(self):
+        return dict(code="o", dim=1, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
+                    first=int(self.euclidean_to_sphere_as_first), natural_direction=int(self.natural_direction),
+                    spline=self.spline_spec(), n_params=self.total_param_num)
+
+
+class moebius(_s1_base):
+    """Symbol "m".  Reference: layers/spheres/moebius_1d.py:8-55.  Parameter slice: [householder 4][K x (x, y, log-radius,
+    log-weight)]."""
+
+    code = "m"
+
+    def __init__(self, dimension=1, euclidean_to_sphere_as_first=True, add_rotation=0, natural_direction=0,
+                 use_permanent_parameters=False, use_moebius_xyz_parametrization=True, num_basis_functions=5):
+        super().__init__(dimension=1)
+        if dimension != 1:
+            raise Exception("The moebius flow is defined for dimension 1, but dimension %d is handed over" % (dimension))
+        if not use_moebius_xyz_parametrization:
+            raise NotImplementedError("'m' with use_moebius_xyz_parametrization=0 has no sm_100a kernel")
+        if num_basis_functions > 16:
+            raise NotImplementedError("'m' with more than 16 basis functions")
+        self._setup_s1(euclidean_to_sphere_as_first, add_rotation, use_permanent_parameters)
+        self.num_basis_functions = num_basis_functions
+        self.num_omega_pars = 4
+        self.total_param_num += self.num_basis_functions * self.num_omega_pars
+        if use_permanent_parameters:
+            self.moebius_pars = nn.Parameter(torch.randn(self.num_basis_functions, self.num_omega_pars).type(torch.double).unsqueeze(0))
+        self.natural_direction = natural_direction
+
+    def get_desired_init_parameters(self):
+        par_list = []
+        if self.num_householder_params > 0:
+            par_list.append(torch.randn((self.num_householder_params)))
+        par_list.append(torch.randn((self.num_basis_functions * self.num_omega_pars)))
+        return torch.cat(par_list)
+
+    def init_params(self, params):
+        assert (len(params) == self.total_param_num)
+        n = self.num_householder_params
+        if self.add_rotation:
+            self.householder_params.data = params[:n].reshape(1, n)
+        self.moebius_pars.data = params[n:].reshape(1, self.num_basis_functions, self.num_omega_pars)
+
+    def permanent_param_names(self):
+        return (["householder_params"] if self.num_householder_params > 0 else []) + ["moebius_pars"]
+
+    def descriptor(self):
+        return dict(code="m", dim=1, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
+                    first=int(self.euclidean_to_sphere_as_first), natural_direction=int(self.natural_direction),
+                    K=self.num_basis_functions, n_params=self.total_param_num)
+
+
+# =====================================================================================================================
+# S2: exponential-map flow "v"
+# =====================================================================================================================
+class exponential_map_s2(layer_base):
+    """Symbol "v" with the exponential potential.  Reference: layers/spheres/exponential_map_s2.py:64-151.
+    Parameter slice: [householder iter*3][potential_pars 5 x K: mean xyz, log-weight, log-beta]."""
+
+    code = "v"
+    manifold = "s"
+
+    def __init__(self, dimension, euclidean_to_sphere_as_first=False, use_permanent_parameters=False,
+                 exp_map_type="linear", natural_direction=0, num_components=10, add_rotation=0,
+                 max_num_newton_iter=1000, mean_parametrization="old"):
+        super().__init__(dimension=dimension)
+        if dimension != 2:
+            raise Exception("The moebius flow should be used for dimension 2!")
+        unsupported = []
+        if exp_map_type != "exponential":
+            unsupported.append("exp_map_type=%s" % exp_map_type)
+        if mean_parametrization != "old":
+            unsupported.append("mean_parametrization=%s" % mean_parametrization)
+        if num_components > 16:
+            unsupported.append("num_components > 16")
+        if len(unsupported) > 0:
+            raise NotImplementedError("'v' layer options without an sm_100a kernel yet (SURVEY.md section 8a row a15): "
+                                      + ", ".join(unsupported) + " -- there is no CPU fallback")
+        self.euclidean_to_sphere_as_first = euclidean_to_sphere_as_first
+        self.use_permanent_parameters = use_permanent_parameters
+        self.add_rotation = add_rotation
+        self.num_householder_iter = 0
+        self.num_householder_params = 0
+        if add_rotation:
+            self.num_householder_iter = dimension + 1
+            self.num_householder_params = self.num_householder_iter * (dimension + 1)
+        if use_permanent_parameters and self.num_householder_params > 0:
+            self.householder_params = nn.Parameter(torch.randn((1, self.num_householder_params)))
+        self.total_param_num += self.num_householder_params
+        self.num_components = num_components
+        self.exp_map_type = exp_map_type
+        self.natural_direction = natural_direction
+        self.max_num_newton_iter = max_num_newton_iter
+        self.num_potential_pars = 3 + 2
+        if use_permanent_parameters:
+            self.potential_pars = nn.Parameter(torch.randn(self.num_potential_pars, self.num_components).unsqueeze(0))
+        self.total_param_num += self.num_potential_pars * self.num_components
+
+    def get_desired_init_parameters(self):
+        par_list = []
+        if self.num_householder_params > 0:
+            par_list.append(torch.randn((self.num_householder_params)))
+        par_list.append(torch.randn((self.num_potential_pars * self.num_components)))
+        return torch.cat(par_list)
+
+    def init_params(self, params):
+        assert (len(params) == self.total_param_num)
+        n = self.num_householder_params
+        if self.add_rotation:
+            self.householder_params.data = params[:n].reshape(1, n)
+        self.potential_pars.data = params[n:].reshape(1, self.num_potential_pars, self.num_components)
+
+    def permanent_param_names(self):
+        return (["householder_params"] if self.num_householder_params > 0 else []) + ["potential_pars"]
+
+    def descriptor(self):
+        return dict(code="v", dim=2, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
+                    first=int(self.euclidean_to_sphere_as_first), natural_direction=int(self.natural_direction),
+                    K=self.num_components, max_iter=int(self.max_num_newton_iter), n_params=self.total_param_num)
 
     def _embedding_conditional_return(self, x):
         from . import engine

@@ -175,6 +175,15 @@ class pdf(nn.Module):
                     1 if (self.force_permanent_parameters_in_first_subpdf and subflow_index == 0) else 0
                 if "s" in subflow_description:
                     this_kwargs["euclidean_to_sphere_as_first"] = 1 if layer_ind == 0 else 0
+                elif "i" in subflow_description:
+                    # reference main/default.py:414-432: boundaries from the sub-pdf definition "i1_lo_hi"
+                    interval_boundaries = subflow_description.split("_")[1:]
+                    if len(interval_boundaries) == 0:
+                        this_kwargs["low_boundary"], this_kwargs["high_boundary"] = 0.0, 1.0
+                    else:
+                        this_kwargs["low_boundary"] = float(interval_boundaries[0])
+                        this_kwargs["high_boundary"] = float(interval_boundaries[1])
+                    this_kwargs["euclidean_to_interval_as_first"] = 1 if layer_ind == 0 else 0
                 elif "e" in subflow_description:
                     # last layer models the offset; a first (non-last) "g" layer swaps isigmoid for the inverse normal
                     # CDF -- a single-layer sub-pdf therefore keeps isigmoid (reference :440-448)

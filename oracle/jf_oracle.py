@@ -228,6 +228,350 @@ class GfLayer:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Rational-quadratic splines (shared by "r", "o" and the sub-flows of "f")
+# ---------------------------------------------------------------------------------------------------------------------
+def _softplus(t):
+    return F.softplus(t)
+
+
+def _knots(raw, lo, hi, floor, max_ratio):
+    """raw [B,n] -> (knot positions [B,n+1], bin sizes [B,n]): softmax with a floor, cumulated, ends pinned to lo/hi and
+    the sizes recomputed as knot differences.  Reference: layers/spline_fns.py:77-111 (same in :400-424, :595-616)."""
+    n = raw.shape[-1]
+    if max_ratio > 0.0:
+        ln_max = (math.log(max_ratio) - math.log(n - 1)) / 2.0                       # spline_fns.py:79-84
+        raw = 2.0 * torch.sigmoid(raw) * ln_max - ln_max
+    frac = floor + (1.0 - floor * n) * torch.softmax(raw, dim=-1)
+    cum = F.pad(torch.cumsum(frac, dim=-1), pad=(1, 0), value=0.0)
+    cum = (hi - lo) * cum + lo
+    cum[..., 0] = lo
+    cum[..., -1] = hi
+    return cum, cum[..., 1:] - cum[..., :-1]
+
+
+def _rq_apply(x, kx, w, ky, h, d, inverse):
+    """Evaluate the monotone rational-quadratic spline with knots (kx, ky), bin sizes (w, h) and knot derivatives d at
+    x [B,1].  Returns (y, log|dy/dx|) -- for inverse=True the value returned is MINUS the forward log-derivative at the
+    pre-image, exactly as the reference does.  Reference: spline_fns.py:113-186 (bin search :13-19)."""
+    search = (ky if inverse else kx).clone()
+    search[..., -1] += 1e-6
+    idx = (x >= search).sum(dim=-1, keepdim=True) - 1
+    b = x.shape[0]
+    ex = lambda t: t.expand(b, -1) if t.shape[0] == 1 else t
+    kx, w, ky, h, d = ex(kx), ex(w), ex(ky), ex(h), ex(d)
+    g = lambda t: t.gather(-1, idx)
+    x0, wk, y0, hk = g(kx), g(w), g(ky), g(h)
+    s = g(h / w)
+    d0, d1 = g(d), g(d[..., 1:])
+    if inverse:
+        dy = x - y0
+        t = d0 + d1 - 2 * s
+        qa = dy * t + hk * (s - d0)
+        qb = hk * d0 - dy * t
+        qc = -s * dy
+        disc = qb.pow(2) - 4 * qa * qc
+        assert (disc >= 0).all()
+        xi = (2 * qc) / (-qb - torch.sqrt(disc))
+        out = xi * wk + x0
+    else:
+        xi = (x - x0) / wk
+        out = None
+    xx = xi * (1 - xi)
+    den = s + (d0 + d1 - 2 * s) * xx
+    if not inverse:
+        out = y0 + hk * (s * xi.pow(2) + d0 * xx) / den
+    num = s.pow(2) * (d1 * xi.pow(2) + 2 * s * xx + d0 * (1 - xi).pow(2))
+    lad = torch.log(num) - 2 * torch.log(den)
+    return out, (-lad if inverse else lad)
+
+
+class Spline:
+    """One 1-d spline transformation as configured by an "r" or "o" layer.  `spec` keys: kind (plain | smooth |
+    circular), n_bins, n_w, n_h, n_d, fix_first, fix_second, indep, bd_mode (0 derivatives are parameters, 1 boundary
+    derivatives fixed to softplus^-1 value bd_fixed, 2 periodic: first copied to the end), lo, hi, min_w, min_h, min_d,
+    max_ratio."""
+
+    def __init__(self, spec):
+        self.s = spec
+
+    def unpack(self, p):
+        """Raw layer parameters -> (raw widths [B,n], raw heights [B,n], raw derivatives or None).
+        Reference: layers/intervals/rational_quadratic_spline.py:180-246, layers/spheres/splines_1d.py:111-170."""
+        s = self.s
+        uw = p[:, :s["n_w"]]
+        uh = p[:, s["n_w"]:s["n_w"] + s["n_h"]]
+        ud = p[:, s["n_w"] + s["n_h"]:s["n_w"] + s["n_h"] + s["n_d"]] if s["n_d"] > 0 else None
+        zero = torch.zeros(p.shape[0], 1, dtype=p.dtype)
+        if s["fix_first"]:
+            uh = torch.cat([zero, uh], dim=1)
+            uw = torch.cat([zero, zero, uw] if s["fix_second"] else [zero, uw], dim=1)
+        if s["indep"]:
+            uh = uw + uh
+        if s["kind"] == "smooth" and s["n_bins"] == 3:
+            uw = torch.cat([uw, uw[:, 0:1]], dim=1)
+            uh = torch.cat([uh, uh[:, 0:1]], dim=1)
+        assert uw.shape[1] == s["n_bins"] and uh.shape[1] == s["n_bins"], (uw.shape, uh.shape, s)
+        fixed = torch.full((p.shape[0], 1), float(s["bd_fixed"]), dtype=p.dtype)
+        if s["kind"] == "plain":
+            if s["bd_mode"] == 1:
+                ud = torch.cat([fixed, ud, fixed], dim=-1) if ud is not None else torch.cat([fixed, fixed], dim=-1)
+            elif s["bd_mode"] == 2:
+                ud = torch.cat([ud, ud[:, 0:1]], dim=-1)
+        elif s["kind"] == "smooth":
+            if s["bd_mode"] == 1:
+                ud = torch.cat([fixed, fixed], dim=-1)
+        return uw, uh, ud
+
+    def apply(self, x, p, inverse):
+        s = self.s
+        uw, uh, ud = self.unpack(p)
+        lo, hi = s["lo"], s["hi"]
+        kx, w = _knots(uw, lo, hi, s["min_w"], s["max_ratio"])
+        ky, h = _knots(uh, lo, hi, s["min_h"], s["max_ratio"])
+        if s["kind"] == "plain":
+            return _rq_apply(x, kx, w, ky, h, s["min_d"] + _softplus(ud), inverse)
+        if s["kind"] == "smooth":
+            return _rq_apply(x, kx, w, ky, h, self._smooth_derivs(w, h, s["min_d"] + _softplus(ud)), inverse)
+        return self._circular(x, kx, w, ky, h, inverse)
+
+    @staticmethod
+    def _smooth_derivs(w, h, bd):
+        """Interior knot derivatives that make the second derivative continuous (2 bins, or 3 symmetric bins).
+        Reference: spline_fns.py:426-484."""
+        n = w.shape[-1]
+        if n == 1:
+            return bd
+        if n == 2:
+            h1, h2, w1, w2 = h[..., :1], h[..., 1:], w[..., :1], w[..., 1:]
+            hs = h1 + h2
+            half = 0.5 * ((h1 / hs) * (h2 / w2 - bd[..., 1:]) + (h2 / hs) * (h1 / w1 - bd[..., :1]))
+            q = -(h1 * h2) * ((h1 / hs) * (1.0 / w1 ** 2) + (h2 / hs) * (1.0 / w2 ** 2))
+            mid = half + (half ** 2 - q).sqrt()
+            return torch.cat([bd[..., :1], mid, bd[..., 1:]], dim=-1)
+        assert n == 3
+        w1, w2, h1, h2 = w[..., 0:1], w[..., 1:2], h[..., 0:1], h[..., 1:2]
+        cd = w1 * w2 * (2 * h1 + h2)
+        pp = h2 * (bd[..., :1] * w1 * w2 - h1 * (w1 + w2)) / cd
+        q = -h1 * h2 * (h1 * w2 ** 2 + h2 * w1 ** 2) / (cd * w1 * w2)
+        mid = -pp / 2.0 + torch.sqrt((-pp / 2.0) ** 2 - q)
+        return torch.cat([bd[..., :1], mid, mid, bd[..., 1:]], dim=-1)
+
+    @staticmethod
+    def _circular(x, kx, w, ky, h, inverse):
+        """Two-bin periodic spline with one common knot derivative and a shift that keeps the map centred.
+        Reference: spline_fns.py:618-668 and :727-759."""
+        two_pi = 2 * math.pi
+        w1, w2, h1, h2 = w[..., :1], w[..., 1:], h[..., :1], h[..., 1:]
+        hp, wp = h1 * h2, w1 * w2
+        root = torch.sqrt(hp * (8 * ((h2 * w1) ** 2 + (h1 * w2) ** 2) + (9 * (w1 + w2) ** 2 - 16 * wp) * hp))
+        res = (hp * (w1 + w2) + root) / (4 * (h1 + h2) * wp)
+        d = torch.cat([res, res, res], dim=-1)
+        a = -math.pi + w1 / 2.0
+        ab = a + w2
+        corr = two_pi - (h1 + h2 * a * (a * h1 - res * w1 * ab) / (h1 * w2 ** 2 + 2 * (h1 - res * w1) * a * ab))
+        shift_in = corr if inverse else (math.pi - w1 / 2.0)
+        u = x - shift_in
+        u = torch.where(u < 0.0, u + two_pi, u)
+        out, lad = _rq_apply(u, kx, w, ky, h, d, inverse)
+        out = out + ((math.pi - w1 / 2.0) if inverse else corr)
+        out = torch.where(out > two_pi, out - two_pi, out)
+        out = torch.where(x == 0.0, torch.zeros_like(out), out)
+        out = torch.where(x == two_pi, torch.full_like(out, two_pi), out)
+        return out, lad
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# interval sub-pdfs: erf chart + "r"
+# ---------------------------------------------------------------------------------------------------------------------
+class RLayer:
+    """rational_quadratic_spline on [lo,hi].  `spec` keys: spline, first, lo, hi.
+    Reference: layers/intervals/rational_quadratic_spline.py:180-400, layers/intervals/interval_base.py:33-79."""
+
+    def __init__(self, spec):
+        self.s = spec
+        self.sp = Spline(spec["spline"])
+
+    def inverse(self, x, log_det, p):
+        x = torch.clamp(x, min=-1.0, max=1.0)                       # rational_quadratic_spline.py:297-298 (sic)
+        x, lad = self.sp.apply(x, p, True)
+        log_det = log_det + lad.sum(dim=-1)
+        x = torch.clamp(x, min=-1.0, max=1.0)
+        if self.s["first"]:                                         # interval_base.py:47-59
+            width = self.s["hi"] - self.s["lo"]
+            z = torch.erfinv(2.0 * ((x - self.s["lo"]) / width) - 1.0) * math.sqrt(2.0)
+            log_det = log_det - (-(z[:, 0] ** 2) / 2.0 - 0.5 * math.log(2 * math.pi) + math.log(width))
+            x = z
+        return x, log_det
+
+    def forward(self, x, log_det, p):
+        if self.s["first"]:                                         # interval_base.py:33-45
+            width = self.s["hi"] - self.s["lo"]
+            log_det = log_det - (x[:, 0] ** 2) / 2.0 - 0.5 * math.log(2 * math.pi) + math.log(width)
+            x = (0.5 + 0.5 * torch.erf(x / math.sqrt(2.0))) * width + self.s["lo"]
+        x = torch.clamp(x, min=-1.0, max=1.0)
+        x, lad = self.sp.apply(x, p, False)
+        log_det = log_det + lad.sum(dim=-1)
+        return torch.clamp(x, min=-1.0, max=1.0), log_det
+
+    def embedding(self, x):
+        return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# S1 sub-pdfs: chart, rotation in R^2, "o" and "m"
+# ---------------------------------------------------------------------------------------------------------------------
+def _safe_angle_2pi(x, margin=1e-7):
+    """Reference: spline_fns.py:22-43."""
+    return torch.clamp(x, min=margin, max=2 * math.pi - margin)
+
+
+def s1_from_embedding(e):
+    """(x,y) -> angle in [0,2pi].  Reference: sphere_base.py:248-266."""
+    a = torch.acos(e[:, 0:1] / torch.sqrt((e ** 2).sum(dim=1, keepdim=True)))
+    return torch.where(e[:, 1:2] < 0, 2 * math.pi - a, a)
+
+
+class S1Layer:
+    """Common part of the S1 layers.  Reference: sphere_base.py:601-695 (rotation wrapper), :460-480 / :529-539 chart."""
+
+    def __init__(self, spec):
+        self.s = spec
+
+    def _rot(self, p):
+        n = self.s["hh_iter"] * 2 if self.s["add_rotation"] else 0
+        return (householder_matrix(p[:, :n].reshape(-1, self.s["hh_iter"], 2)) if n > 0 else None), p[:, n:]
+
+    def inverse(self, x, log_det, p):
+        q, rest = self._rot(p)
+        if q is not None:
+            e = torch.cat([torch.cos(x), torch.sin(x)], dim=1)
+            e = torch.einsum("bji,bj->bi", q.expand(e.shape[0], -1, -1), e)
+            x = s1_from_embedding(e)
+        x, log_det = self._inner(x, log_det, rest, logpdf=True)
+        if self.s["first"]:
+            sign = torch.where(x > math.pi, -1.0, 1.0).to(x.dtype)
+            y = torch.where(sign > 0, x, 2 * math.pi - x)
+            eps = 1e-5 if x.dtype == torch.float32 else 1e-8
+            y = torch.where(y <= 0.0, torch.full_like(y, eps), y)
+            y = torch.where(y >= 2 * math.pi, torch.full_like(y, 2 * math.pi - eps), y)
+            z = math.sqrt(2.0) * torch.erfinv(1.0 - y / math.pi)
+            log_det = log_det - math.log(math.sqrt(2.0 * math.pi)) + (z[:, 0] ** 2) / 2.0
+            x = z * sign
+        return x, log_det
+
+    def forward(self, x, log_det, p):
+        q, rest = self._rot(p)
+        if self.s["first"]:
+            r = torch.sqrt((x ** 2).sum(dim=1, keepdim=True))
+            keep = (x >= 0).to(x.dtype)
+            log_det = log_det + math.log(math.sqrt(2.0 * math.pi)) - (r[:, 0] ** 2) / 2.0
+            a = math.pi * (1.0 - torch.erf(r / math.sqrt(2.0)))
+            x = keep * a + (1.0 - keep) * (2 * math.pi - a)
+        x, log_det = self._inner(x, log_det, rest, logpdf=False)
+        if q is not None:
+            e = torch.cat([torch.cos(x), torch.sin(x)], dim=1)
+            e = torch.einsum("bij,bj->bi", q.expand(e.shape[0], -1, -1), e)
+            x = s1_from_embedding(e)
+        return x, log_det
+
+    def embedding(self, x):
+        return torch.cat([torch.cos(x), torch.sin(x)], dim=1)
+
+
+class OLayer(S1Layer):
+    """spline_1d.  Reference: layers/spheres/splines_1d.py:111-306."""
+
+    def __init__(self, spec):
+        super().__init__(spec)
+        self.sp = Spline(spec["spline"])
+
+    def _inner(self, x, log_det, p, logpdf):
+        if logpdf:
+            x = _safe_angle_2pi(x)
+            x, lad = self.sp.apply(x, p, self.s["natural_direction"] != 0)
+            return _safe_angle_2pi(x), log_det + lad.sum(dim=-1)
+        x = torch.clamp(x, min=0.0, max=2 * math.pi)
+        x, lad = self.sp.apply(x, p, self.s["natural_direction"] == 0)
+        return torch.clamp(x, min=0.0, max=2 * math.pi), log_det + lad.sum(dim=-1)
+
+
+class MLayer(S1Layer):
+    """moebius.  `spec` keys: K (num_basis_functions), natural_direction.  Reference: moebius_1d.py:57-259."""
+
+    def _omega(self, pars):
+        ll = pars[:, :, 2:3]
+        length = 0.001 + torch.exp(math.log(0.999 - 0.001) - torch.logsumexp(
+            torch.cat([torch.zeros_like(ll), -ll], dim=2), dim=2, keepdim=True))
+        vec = pars[:, :, :2] / (pars[:, :, :2] ** 2).sum(dim=2, keepdim=True).sqrt() * length
+        return length, vec
+
+    def trafo(self, x, pars):
+        cx, sx = torch.cos(x)[:, None, :], torch.sin(x)[:, None, :]
+        length, vec = self._omega(pars)
+        ox, oy = vec[:, :, 0:1], vec[:, :, 1:2]
+        om = 1.0 - length ** 2
+        cmp, smp = np.cos(-np.pi), np.sin(-np.pi)
+        opo = 1.0 + length ** 2 - 2 * (cx * ox + sx * oy)
+        opo_mp = 1.0 + length ** 2 - 2 * (cmp * ox + smp * oy)
+        rot = -math.pi - torch.atan2(om * (smp - oy) - oy * opo_mp, om * (cmp - ox) - ox * opo_mp)
+        yv = om * (sx - oy) - oy * opo
+        xv = om * (cx - ox) - ox * opo
+        xp = torch.cos(rot) * xv - torch.sin(rot) * yv
+        yp = torch.sin(rot) * xv + torch.cos(rot) * yv
+        at = torch.atan2(yp, xp)[:, :, -1:] + math.pi
+        ln = pars[:, :, 3:4]
+        return torch.sum(at * torch.exp(ln - torch.logsumexp(ln, dim=1, keepdim=True)), dim=1) - math.pi
+
+    def deriv(self, x, pars):
+        cx, sx = torch.cos(x)[:, None, :], torch.sin(x)[:, None, :]
+        length, vec = self._omega(pars)
+        om = 1.0 - length ** 2
+        opo = 1.0 + length ** 2 - 2 * (cx * vec[:, :, 0:1] + sx * vec[:, :, 1:2])
+        ln = pars[:, :, 3:4]
+        return torch.exp(torch.logsumexp(torch.log(om / opo) + ln - torch.logsumexp(ln, dim=1, keepdim=True), dim=1))
+
+    def _solve(self, target, pars):
+        """20 bisections on [-pi,pi] + <=20 Newton steps.  Reference: bisection_n_newton.py:137-256."""
+        b = target.shape[0]
+        pars = pars.expand(b, -1, -1)
+        lo = torch.full_like(target, -math.pi)
+        hi = torch.full_like(target, math.pi)
+        mid = None
+        for _ in range(20):
+            mid = (hi + lo) / 2.0
+            val = self.trafo(mid, pars)
+            right = val < target
+            ok = torch.abs(val - target) <= 1e-6 * torch.abs(target)
+            lo = torch.where(ok, mid, torch.where(right, mid, lo))
+            hi = torch.where(ok, mid, torch.where(right, hi, mid))
+        x = mid
+        active = torch.ones(b, dtype=torch.bool)
+        for _ in range(20):
+            if not bool(active.any()):
+                break
+            upd = (self.trafo(x[active], pars[active]) - target[active]) / self.deriv(x[active], pars[active])
+            x = x.clone()
+            x[active] = x[active] - upd
+            idx = active.nonzero(as_tuple=True)[0]
+            active = active.clone()
+            active[idx] = torch.abs(upd).sum(dim=1) >= 1e-14
+        return x
+
+    def _inner(self, x, log_det, p, logpdf):
+        pars = p.reshape(p.shape[0], self.s["K"], 4)
+        x = torch.where(x > math.pi, x - 2 * math.pi, x)
+        direct = (self.s["natural_direction"] == 0) if logpdf else (self.s["natural_direction"] != 0)
+        if direct:
+            ld = torch.log(self.deriv(x, pars)).sum(dim=-1)
+            x = self.trafo(x, pars)
+        else:
+            x = self._solve(x, pars)
+            ld = -torch.log(self.deriv(x, pars)).sum(dim=-1)
+        x = torch.where(x < 0, 2 * math.pi + x, x)
+        return x, log_det + ld
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # S2: charts + "f" layer (Householder rotation in R^3 + von-Mises-Fisher z-scaling), default options
 # ---------------------------------------------------------------------------------------------------------------------
 def s2_to_embedding(x, log_det):
@@ -269,11 +613,53 @@ def s2_plane_to_sphere(x, log_det):
 
 
 class FvmLayer:
-    """fisher_von_mises_2d with the sub-flow options off (reference defaults, flow_options.py:154-180).
-    `spec` keys: add_rotation, hh_iter, z_sign, min_kappa, first (chart to the plane as first layer of the sub-pdf)."""
+    """fisher_von_mises_2d (reference flow_options.py:154-180), with the optional vertical ("r...") and circular
+    ("o...") spline sub-flows.  `spec` keys: add_rotation, hh_iter, z_sign, min_kappa, first (chart to the plane as
+    first layer of the sub-pdf), vertical / circular (lists of spline specs; parameters follow kappa in that order)."""
 
     def __init__(self, spec):
         self.s = spec
+        self.vertical = [Spline(v) for v in spec.get("vertical", [])]
+        self.circular = [Spline(v) for v in spec.get("circular", [])]
+
+    @staticmethod
+    def _window(c):
+        """Reference: fvm_2d.py:267-271."""
+        return torch.where(c <= 0, 6 * c ** 5 + 15 * c ** 4 + 10 * c ** 3 + 1.0, -6 * c ** 5 + 15 * c ** 4 - 10 * c ** 3 + 1.0)
+
+    def _sub_params(self, p):
+        n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
+        o = n_hh + 1
+        nv = sum(v.s["n_w"] + v.s["n_h"] + v.s["n_d"] for v in self.vertical)
+        nc = sum(v.s["n_w"] + v.s["n_h"] + v.s["n_d"] for v in self.circular)
+        return p[:, o:o + nv], p[:, o + nv:o + nv + nc]
+
+    @staticmethod
+    def _chain(splines, x, log_det, p, logpdf, angle):
+        """Pass-through chain of nested layers (main/default.py:998-1031 reversed / :1482-1506 in order)."""
+        offs, o = [], 0
+        for sp in splines:
+            n = sp.s["n_w"] + sp.s["n_h"] + sp.s["n_d"]
+            offs.append((o, o + n))
+            o += n
+        order = reversed(range(len(splines))) if logpdf else range(len(splines))
+        for i in order:
+            sp, (a, b) = splines[i], offs[i]
+            if angle:       # "o": splines_1d.py:111-306
+                if logpdf:
+                    x = _safe_angle_2pi(x)
+                    x, lad = sp.apply(x, p[:, a:b], sp.s["natural_direction"] != 0)
+                    x = _safe_angle_2pi(x)
+                else:
+                    x = torch.clamp(x, min=0.0, max=2 * math.pi)
+                    x, lad = sp.apply(x, p[:, a:b], sp.s["natural_direction"] == 0)
+                    x = torch.clamp(x, min=0.0, max=2 * math.pi)
+            else:           # "r": rational_quadratic_spline.py:180-400
+                x = torch.clamp(x, min=-1.0, max=1.0)
+                x, lad = sp.apply(x, p[:, a:b], logpdf)
+                x = torch.clamp(x, min=-1.0, max=1.0)
+            log_det = log_det + lad.sum(dim=-1)
+        return x, log_det
 
     def _split(self, p):
         n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
@@ -296,10 +682,18 @@ class FvmLayer:
         log_det = log_det + (torch.log(2 * kappa) + kappa * (s * ct + 1) - safe)[:, 0]
         ret = s * ((1.0 + torch.exp(-2 * kappa) - 2 * torch.exp(kappa * (s * ct - 1))) / (-1 + torch.exp(-2 * kappa)))
         ret = torch.where(kappa < (1e-4 if x.dtype == torch.float32 else 1e-8), ct, ret)
-        ret = _safe_costheta(_safe_costheta(ret))
+        ret = _safe_costheta(ret)
+        angle = x[:, 1:]
+        pv, pc = self._sub_params(p)
+        if len(self.circular) > 0:                                              # fvm_2d.py:413-427
+            angle, log_det = self._chain(self.circular, angle, log_det, pc.expand(x.shape[0], -1) * self._window(ret),
+                                         True, True)
+        if len(self.vertical) > 0:                                              # fvm_2d.py:430-432
+            ret, log_det = self._chain(self.vertical, ret, log_det, pv, True, False)
+        ret = _safe_costheta(ret)
         theta = torch.acos(ret)
         log_det = log_det - torch.log(torch.sin(_safe_angle(theta[:, 0])))
-        x = torch.cat([theta, x[:, 1:]], dim=1)
+        x = torch.cat([theta, angle], dim=1)
         if self.s["first"]:
             x, log_det = s2_sphere_to_plane(x, log_det)
         return x, log_det
@@ -312,13 +706,20 @@ class FvmLayer:
             x, log_det = s2_plane_to_sphere(x, log_det)
         ct = torch.cos(x[:, :1])
         log_det = log_det + torch.log(torch.sin(_safe_angle(x[:, 0])))
+        angle = x[:, 1:]
+        pv, pc = self._sub_params(p)
+        if len(self.vertical) > 0:                                              # fvm_2d.py:591-592
+            ct, log_det = self._chain(self.vertical, ct, log_det, pv, False, False)
+        if len(self.circular) > 0:                                              # fvm_2d.py:595-607
+            angle, log_det = self._chain(self.circular, angle, log_det, pc.expand(x.shape[0], -1) * self._window(ct),
+                                         False, True)
         kappa = kappa.expand(x.shape[0], -1)
         log_det = log_det - torch.log(kappa * s * ct + kappa / torch.tanh(kappa))[:, 0]
         ret = s * (1.0 + (1.0 / kappa) * torch.log(0.5 * (1.0 + s * ct) + (0.5 - 0.5 * s * ct) * torch.exp(-2.0 * kappa)))
         ret = torch.where(kappa < (1e-4 if x.dtype == torch.float32 else 1e-8), ct, ret)
         theta = torch.acos(_safe_costheta(ret))
         log_det = log_det - torch.log(torch.sin(_safe_angle(theta[:, 0])))
-        x = torch.cat([theta, x[:, 1:]], dim=1)
+        x = torch.cat([theta, angle], dim=1)
         if q is not None:
             e, log_det = s2_to_embedding(x, log_det)
             e = torch.einsum("bij,bj->bi", q.expand(e.shape[0], -1, -1), e)
@@ -330,7 +731,141 @@ class FvmLayer:
         return s2_to_embedding(x, torch.zeros(x.shape[0], dtype=x.dtype))[0]
 
 
-LAYER_TYPES = {"g": GfLayer, "f": FvmLayer}
+# ---------------------------------------------------------------------------------------------------------------------
+# S2: exponential-map flow "v" (exponential potential)
+# ---------------------------------------------------------------------------------------------------------------------
+class VLayer:
+    """exponential_map_s2 with exp_map_type="exponential", mean_parametrization="old".
+    `spec` keys: add_rotation, hh_iter, first, natural_direction, K, max_iter.
+    Reference: layers/spheres/exponential_map_s2.py:248-442 (map and Jacobian), :446-528 (directions),
+    layers/bisection_n_newton.py:394-465 (inverse), rotation/chart wrapper sphere_base.py:601-695."""
+
+    def __init__(self, spec):
+        self.s = spec
+
+    def _split(self, p):
+        n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
+        q = householder_matrix(p[:, :n_hh].reshape(-1, self.s["hh_iter"], 3)) if n_hh > 0 else None
+        return q, p[:, n_hh:].reshape(p.shape[0], 5, self.s["K"])
+
+    @staticmethod
+    def _log_map(base, g, jac_g):
+        """Unit tangent at `base` towards g, the projection of g on it, and both Jacobians w.r.t. base (:153-214)."""
+        tn = (g ** 2).sum(dim=1, keepdim=True).sqrt()
+        nh = g / tn
+        ca = (nh * base).sum(dim=1, keepdim=True)
+        alpha = torch.arccos(ca)
+        sa = torch.sin(alpha)
+        th = (nh - base * ca) / sa
+        proj = (g * th).sum(dim=1, keepdim=True)
+        d_t_base = torch.diag_embed((-ca / sa).repeat(1, 3))
+        d_t_theta = ((base - nh * ca) / sa ** 2).unsqueeze(-1)
+        inv_sq = -1.0 / torch.sqrt(1.0 - ca ** 2)
+        jt = d_t_base + d_t_theta @ (inv_sq * nh).unsqueeze(1)
+        jp = (jt * g.unsqueeze(-1)).sum(dim=1, keepdim=True)
+        d_theta_norm = (inv_sq * base).unsqueeze(1)
+        d_norm_unnorm = (-g / tn ** 2).unsqueeze(-1) @ nh.unsqueeze(1) + torch.diag_embed(1.0 / tn.repeat(1, 3))
+        d_t_norm = torch.diag_embed(1.0 / sa.repeat(1, 3))
+        jt = jt + d_t_theta @ d_theta_norm @ d_norm_unnorm @ jac_g
+        jt = jt + d_t_norm @ d_norm_unnorm @ jac_g
+        jp = jp + (th.unsqueeze(-1) * jac_g).sum(dim=1, keepdim=True)
+        return th, proj, jt, jp
+
+    def map(self, x, pars):
+        """-> (y, (J B)^T (J B) [B,2,2], J [B,3,3]).  Reference :248-442."""
+        norm = (pars[:, :3, :] ** 2).sum(dim=1, keepdim=True).sqrt()
+        mu = pars[:, :3, :] / norm
+        fake = -torch.log(1.0 + (math.e - 1.0) * torch.exp(-norm / 10.0)) + 1.0
+        lw = pars[:, 3:4, :] - torch.logsumexp(pars[:, 3:4, :], dim=2, keepdim=True) + fake.log()
+        w = lw.exp()
+        xm = (x[:, :, None] * mu).sum(dim=1, keepdim=True)
+        beta = pars[:, 4:5, :].exp()
+        e = torch.exp(beta * (xm - 1.0))
+        g = (w * mu * e).sum(dim=-1)
+        jac_g = torch.einsum("biu,bju->bij", beta * w * mu * e, mu)
+        th, proj, jt, jp = self._log_map(x, g, jac_g)
+        y = x * torch.cos(proj) + th * torch.sin(proj)
+        first = torch.diag_embed(torch.cos(proj).repeat(1, 3)) + (-x * torch.sin(proj)).unsqueeze(-1) @ jp
+        second = jt * torch.sin(proj.unsqueeze(-1)) + (th * torch.cos(proj)).unsqueeze(-1) @ jp
+        jac = first + second
+        basis = torch.cat([th.unsqueeze(2), torch.cross(x, th, dim=1).unsqueeze(2)], dim=2)
+        pj = torch.bmm(jac, basis)
+        return y, torch.bmm(pj.permute(0, 2, 1), pj), jac
+
+    def _solve(self, target, pars):
+        """Damped descent on the sphere: start (0,0,-1), step 0.4 x Newton length, stop at 1e-12.  Reference
+        bisection_n_newton.py:394-465 with exponential_map_s2.py:216-246 as the tangent finder."""
+        b = target.shape[0]
+        pars = pars.expand(b, -1, -1)
+        prev = torch.zeros_like(target)
+        prev[:, 2] = -1.0
+        active = torch.ones(b, dtype=torch.bool)
+        for _ in range(self.s["max_iter"]):
+            y, _, jac = self.map(prev[active], pars[active])
+            tg = target[active]
+            fn = -(y * tg).sum(dim=-1, keepdim=True) + 1.0
+            res = -torch.bmm(jac.permute(0, 2, 1), tg.unsqueeze(2)).squeeze(-1)
+            gn = (res ** 2).sum(dim=1, keepdim=True).sqrt()
+            base, tdir = prev[active], -(res / gn)
+            ca = (tdir * base).sum(dim=1, keepdim=True)
+            conv = ca >= 1
+            alt = torch.zeros_like(base)
+            alt[:, 0] = 1.0
+            ca = torch.where(conv, (tdir * alt).sum(dim=1, keepdim=True), ca)
+            alpha = torch.arccos(ca)
+            ub = torch.where(conv, alt, base)
+            vs = (tdir - ub * ca) / torch.sin(alpha)
+            alpha = torch.where(conv, torch.zeros_like(alpha), alpha)
+            step = -(fn / (vs * res).sum(dim=1, keepdim=True))
+            step = torch.where(alpha == 0, torch.zeros_like(step), step)
+            prev = prev.clone()
+            prev[active] = base * torch.cos(0.4 * step) + vs * torch.sin(0.4 * step)
+            idx = active.nonzero(as_tuple=True)[0]
+            active = active.clone()
+            active[idx] = torch.abs(step[:, 0]) >= 1e-12
+            if not bool(active.any()):
+                break
+        return prev
+
+    def _inner(self, x, log_det, pars, logpdf):
+        e, log_det = s2_to_embedding(x, log_det)
+        direct = (self.s["natural_direction"] == 0) if logpdf else (self.s["natural_direction"] != 0)
+        if direct:
+            y, m2, _ = self.map(e, pars.expand(e.shape[0], -1, -1))
+            log_det = log_det + 0.5 * torch.slogdet(m2)[1]
+        else:
+            y = self._solve(e, pars)
+            _, m2, _ = self.map(y, pars.expand(e.shape[0], -1, -1))
+            log_det = log_det - 0.5 * torch.slogdet(m2)[1]
+        return s2_from_embedding(y, log_det)
+
+    def inverse(self, x, log_det, p):
+        q, pars = self._split(p)
+        if q is not None:
+            e, log_det = s2_to_embedding(x, log_det)
+            e = torch.einsum("bji,bj->bi", q.expand(e.shape[0], -1, -1), e)
+            x, log_det = s2_from_embedding(e, log_det)
+        x, log_det = self._inner(x, log_det, pars, True)
+        if self.s["first"]:
+            x, log_det = s2_sphere_to_plane(x, log_det)
+        return x, log_det
+
+    def forward(self, x, log_det, p):
+        q, pars = self._split(p)
+        if self.s["first"]:
+            x, log_det = s2_plane_to_sphere(x, log_det)
+        x, log_det = self._inner(x, log_det, pars, False)
+        if q is not None:
+            e, log_det = s2_to_embedding(x, log_det)
+            e = torch.einsum("bij,bj->bi", q.expand(e.shape[0], -1, -1), e)
+            x, log_det = s2_from_embedding(e, log_det)
+        return x, log_det
+
+    def embedding(self, x):
+        return s2_to_embedding(x, torch.zeros(x.shape[0], dtype=x.dtype))[0]
+
+
+LAYER_TYPES = {"v": VLayer, "g": GfLayer, "f": FvmLayer, "r": RLayer, "o": OLayer, "m": MLayer}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

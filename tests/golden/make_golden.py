@@ -62,6 +62,11 @@ def make_inputs(pdf_defs, n, gen, tails=False):
     return torch.cat(cols, dim=1)
 
 
+CFG3_F = {"add_vertical_rq_spline_flow": 1, "spline_num_basis_functions": -1, "vertical_smooth": 1,
+          "vertical_flow_defs": "rr", "circular_flow_defs": "oo", "vertical_fix_boundary_derivative": 1,
+          "add_circular_rq_spline_flow": 1, "circular_add_rotation": 0, "vertical_fix_first_width_n_height_to_zero": 1,
+          "vertical_also_fix_second_width_to_zero": 1, "vertical_independent_width_height_parametrization": 1}
+
 CASES = {
     # name: dict(pdf_defs, flow_defs, opts, cond_dim, dtype, n, perturb, tails)
     # BASELINE.json configs[0]: e2 "gg" unconditional fp64
@@ -85,6 +90,40 @@ CASES = {
                              opts={"g": {"num_kde": 7}}),
     "s2_f_uncond": dict(pdf_defs="s2", flow_defs="f", n=1000, perturb=0.5),
     "s2_f_cond": dict(pdf_defs="s2", flow_defs="f", n=1000, cond_dim=2, perturb=0.3),
+    # BASELINE.json configs[2]: s2 "f" with smooth vMF-scaled spline sub-flows + i1 "r" (docs/suggested_settings.rst:52-73)
+    "cfg3_s2i1_fr": dict(pdf_defs="s2+i1", flow_defs="f+r", n=1000, opts={"f": CFG3_F}),
+    "cfg3_s2i1_fr_perturbed": dict(pdf_defs="s2+i1", flow_defs="f+r", n=1000, perturb=0.3, opts={"f": CFG3_F}),
+    # spline unit cases: interval "r" (plain / fixed boundary derivs / smooth 2 and 3 bins / restricted ratio), custom
+    # interval boundaries, conditional (per-row parameters)
+    "r_i1_rr_cond": dict(pdf_defs="i1_-0.5_0.8", flow_defs="rr", n=500, cond_dim=2, perturb=0.5),
+    "r_i1_fixed_bd": dict(pdf_defs="i1", flow_defs="rr", n=500, perturb=0.5,
+                          opts={"r": {"fix_boundary_derivatives": 1.0, "num_basis_functions": 8}}),
+    "r_i1_smooth23": dict(pdf_defs="i1", flow_defs="rr", n=500, perturb=0.5,
+                          opts={(0, 0): {"r": {"smooth_second_derivative": 1, "num_basis_functions": 2}},
+                                (0, 1): {"r": {"smooth_second_derivative": 1, "num_basis_functions": 3,
+                                               "fix_boundary_derivatives": 1.0}}}),
+    "r_i1_ratio": dict(pdf_defs="i1", flow_defs="r", n=500, perturb=0.5,
+                       opts={"r": {"restrict_max_min_width_height_ratio": 50.0, "fix_first_width_n_height_to_zero": 1,
+                                   "independent_width_height_parametrization": 1}}),
+    # S1: circular splines (default smooth + rotation; plain periodic; plain fixed; reversed direction) and Moebius
+    "o_s1_default": dict(pdf_defs="s1", flow_defs="oo", n=500, perturb=0.5),
+    "o_s1_plain_cond": dict(pdf_defs="s1", flow_defs="oo", n=500, cond_dim=2, perturb=0.3,
+                            opts={(0, 0): {"o": {"smooth_second_derivative": 0, "num_basis_functions": 5}},
+                                  (0, 1): {"o": {"smooth_second_derivative": 0, "num_basis_functions": 4,
+                                                 "fix_boundary_derivatives": 1.0, "natural_direction": 0,
+                                                 "add_rotation": 0}}}),
+    "m_s1_default": dict(pdf_defs="s1", flow_defs="mm", n=500, perturb=0.3),
+    "m_s1_natural_cond": dict(pdf_defs="s1", flow_defs="m", n=500, cond_dim=2, perturb=0.3,
+                              opts={"m": {"natural_direction": 1, "add_rotation": 1}}),
+    # f with plain (non-smooth) 5-bin sub-flows, conditional
+    "s2_f_plain_subflows_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3,
+                                     opts={"f": {"add_vertical_rq_spline_flow": 1, "add_circular_rq_spline_flow": 1,
+                                                 "vertical_flow_defs": "r", "circular_flow_defs": "o"}}),
+    # "v": exponential-map flow (fp64 only in the reference), unconditional and as the conditional tail of cfg4
+    "s2_v_uncond": dict(pdf_defs="s2", flow_defs="v", n=500, perturb=0.0),
+    "s2_vv_rot": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0, opts={"v": {"add_rotation": 1, "num_components": 4}}),
+    "s2_v_natural": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"natural_direction": 1}}),
+    "cfg4_e6s2_gv_small": dict(pdf_defs="e6+s2", flow_defs="gggggg+v", n=300, cond_dim=64, perturb=0.02),
 }
 
 

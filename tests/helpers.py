@@ -26,7 +26,13 @@ def load_golden(name):
 
 
 def _opts(meta):
-    return {k: v for k, v in meta["options_overwrite"].items()}
+    """options_overwrite as stored in the golden's json: keys are layer codes, or str() of an int / (int, int) tuple"""
+    import ast
+    out = {}
+    for k, v in meta["options_overwrite"].items():
+        key = ast.literal_eval(k) if (k.startswith("(") or k.lstrip("-").isdigit()) else k
+        out[key] = v
+    return out
 
 
 def build_pdf(meta, params=None, seed=None):

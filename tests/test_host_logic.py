@@ -70,7 +70,9 @@ def test_unsupported_fails_loudly():
     with pytest.raises(NotImplementedError):
         jfb.pdf("e2", "gc")          # out of scope layer code
     with pytest.raises(NotImplementedError):
-        jfb.pdf("s1", "m")           # not built yet: must not fall back to anything
+        jfb.pdf("e2", "gt")          # not built yet: must not fall back to anything
+    with pytest.raises(NotImplementedError):
+        jfb.pdf("s2", "v", options_overwrite={"v": {"exp_map_type": "splines"}})
     with pytest.raises(Exception):
         jfb.pdf("e2", "f")           # layer/manifold mismatch (main/default.py:397-398)
 

@@ -17,6 +17,10 @@ def test_oracle_reproduces_reference(name):
     o = OraclePdf(pdf.export_program(meta["dtype"]), params)
     cond = data.get("cond")
     tol = TOL[meta["dtype"]]
+    if "natural" in name:
+        # natural_direction=1: the log_pdf direction itself is an iterative inverse (stop criterion 1e-12 on the step),
+        # so two implementations agree only to the reference's own round-trip error
+        tol = max(tol, 10 * float(data["ref_roundtrip_base_err"]))
     logp, logp_base, base = o.log_pdf(data["x"], cond)
     ok = np.isfinite(data["logp"])
     assert rel_err(logp.numpy(), data["logp"])[ok].max() < tol
