@@ -82,7 +82,9 @@ def base_tolerance(p, dtype, base_ref):
     extra = np.zeros(base_ref.shape[0])
     for k, layers in enumerate(p.layer_list):
         l0 = layers[0]
-        if getattr(l0, "inverse_function_type", "isigmoid") in ("inormal_partly_precise", "inormal_partly_crude"):
+        # the base charts of intervals and of S1 are erfinv-based too (interval_base.py:52, sphere_base.py:474)
+        if getattr(l0, "inverse_function_type", "isigmoid") in ("inormal_partly_precise", "inormal_partly_crude") \
+                or getattr(l0, "code", "") in ("r", "o", "m"):
             b0, b1 = p.base_dim_indices[k]
             extra = np.maximum(extra, icdf_conditioning(base_ref[:, b0:b1], dtype).max(axis=1))
     return tol + extra

@@ -63,14 +63,19 @@ def test_logpdf_matches_reference_golden(name, lib_built):
         assert (np.abs(logp - data["logp"])[sane] <= 20 * tol * np.maximum(1, np.abs(lp64))[sane]).all()
         assert np.abs(logp - lp64)[ok].max() < 0.1        # rows at the branch switch: bounded, not wild
     else:
-        assert (base_err[ok] <= _base_tolerance(p, meta, data["base"])[ok]).all(), base_err[ok].max()
-        logp_tol = tol
+        extra = 0.0
+        if "natural" in name:
+            # natural_direction=1: the log_pdf direction is itself an iterative inverse; the reference's descent stops on
+            # 1 - y.target (cancellation floor ~1e-8), so it is only as accurate as its own round trip (6.7e-8 here)
+            extra = 10 * float(data["ref_roundtrip_base_err"])
+        assert (base_err[ok] <= (_base_tolerance(p, meta, data["base"]) + extra)[ok]).all(), base_err[ok].max()
+        logp_tol = tol + extra
         if "full_pade" in str(meta["options_overwrite"]):
             logp_tol = max(tol, float(data["ref_roundtrip_logp_err"]))
         assert rel_err(logp, data["logp"])[ok].max() < logp_tol
         # log N(base) on its own inherits z*dz of the ill-conditioned entries (it cancels in log_pdf)
         cond_term = (np.abs(data["base"]) * base_err[:, None]).sum(axis=1)
-        assert (np.abs(logp_base - data["logp_base"])[ok] <= (tol * np.maximum(1, np.abs(data["logp_base"])) + cond_term)[ok]).all()
+        assert (np.abs(logp_base - data["logp_base"])[ok] <= ((tol + extra) * np.maximum(1, np.abs(data["logp_base"])) + cond_term)[ok]).all()
     st = p.kernel_status()
     assert st["nonfinite"] == int((~ok).sum())
 
@@ -93,7 +98,9 @@ def test_sample_matches_reference_golden(name, lib_built):
     print("\n%s: |x-x_ref| %.2e  |logp-logp_ref| %.2e  own round trip: base %.2e logp %.2e  (reference's own: %.2e / %.2e)"
           % (name, ex, el, rt, rtl, ref_rt, ref_rt_lp))
     assert ex < max(tol, 10 * ref_rt), (ex, ref_rt)
-    assert el < max(tol, 10 * ref_rt_lp), (el, ref_rt_lp)
+    # log p is compared at two slightly different points when the reference's sample is off by its own inverse error
+    # ("v": descent stops on 1 - y.target, cancellation floor ~1e-7): allow |grad log p| ~ O(1) times that displacement
+    assert el < max(tol, 10 * ref_rt_lp, 10 * ref_rt), (el, ref_rt_lp, ref_rt)
     assert rel_err(logp_base.cpu().numpy(), data["samp_logp_base"])[ok].max() < tol
     assert rt < max(100 * tol, 10 * ref_rt)
     st = p.kernel_status()
