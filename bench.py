@@ -217,6 +217,8 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
 
     vp = lambda t, off=0: C.c_void_p(t.data_ptr() + off * 8)
 
+    mlp_ws = {}
+
     def mlp(k, segs, n):
         md = _cabi.JfMlpDesc()
         C.memmove(C.byref(md), C.byref(desc.mlp[k]), C.sizeof(md))
@@ -225,8 +227,13 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         lds = (C.c_int64 * len(segs))(*[s[1] for s in segs])
         for i, s in enumerate(segs):
             md.seg_cols[i] = s[2]
-        return lib.jf_mlp_forward(C.byref(md), _cabi.JF_F64, ptrs, lds, pack.c.weights[k], pack.c.biases[k], vp(pbuf),
-                                  chunk, 1, n, st)
+        # same entry the whole-pdf path uses: tcgen05 int8-sliced kernel, last-layer slices prepared once per sub-pdf
+        nws = lib.jf_mlp_workspace_bytes(C.byref(md), _cabi.JF_F64)
+        prepared = 1 if k in mlp_ws else 0
+        if k not in mlp_ws:
+            mlp_ws[k] = torch.zeros(max(int(nws), 16), dtype=torch.uint8, device=dev)
+        return lib.jf_mlp_forward_ws(C.byref(md), _cabi.JF_F64, ptrs, lds, pack.c.weights[k], pack.c.biases[k], vp(pbuf),
+                                     chunk, 1, n, C.c_void_p(mlp_ws[k].data_ptr()), nws, prepared, st)
 
     def sub(k, direction, src, ld_src, col_in, col_out, shared, n, first):
         params = C.c_void_p(pack.c.shared[k]) if shared else vp(pbuf)
@@ -271,6 +278,12 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         nrows = B * (2 if r["kernel"].startswith("mlp") else 1)
         r["achieved_tflops"] = r["flop_equiv_per_row"] * nrows / (r["ms"] * 1e-3) * 1e-12
         r["avg_launch_ms"] = r["ms"] / r["launches"]
+        if r["kernel"].startswith("mlp"):
+            # tcgen05 path: 28 int8 slice-pair GEMMs of 128 x N(padded to 64) x 128 per row block (csrc/mlp_i8.cuh)
+            n_out = int(r["kernel"].split("->")[-1].rstrip("]"))
+            n_pad = (n_out + 63) // 64 * 64
+            r["path"] = "tcgen05 kind::i8, 7 int8 slices (28 pair GEMMs), int32 TMEM accumulators"
+            r["int8_tops"] = 28 * 2.0 * 128 * n_pad * nrows / (r["ms"] * 1e-3) * 1e-12
     rows.sort(key=lambda r: -r["ms"])
     return rows, total
 

@@ -193,6 +193,17 @@ int jf_mlp_forward(const JfMlpDesc* desc, int dtype,
                    void* out, int64_t out_stride_param, int64_t out_stride_row,
                    int64_t B, void* stream);
 
+/* Same, with caller-provided device workspace of jf_mlp_workspace_bytes(desc, dtype) bytes (0: none needed).  With a
+ * workspace the fp64 one-hidden-layer (128) case runs on the tcgen05 tensor cores: the last-layer weights are split
+ * once into int8 slices (kept in the workspace; `prepared` != 0 reuses the slices of the previous call, i.e. the same
+ * weights) and the 128 x N contraction is evaluated exactly in int8 x int8 -> int32 on TMEM accumulators. */
+int64_t jf_mlp_workspace_bytes(const JfMlpDesc* desc, int dtype);
+int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype,
+                      const void* const* seg_ptrs, const int64_t* seg_ld,
+                      const void* const* weights, const void* const* biases,
+                      void* out, int64_t out_stride_param, int64_t out_stride_row,
+                      int64_t B, void* workspace, int64_t workspace_bytes, int prepared, void* stream);
+
 /* ---- whole-pdf entries -------------------------------------------------------------------------------------------- */
 typedef struct JfPdfDesc {
     int32_t abi_version; /* JF_ABI_VERSION */

@@ -8,6 +8,8 @@
 #include "gf_launch.cuh"
 #include "mlp_kernels.cuh"
 #include "mlp_dmma.cuh"
+#include "mlp_i8.cuh"
+#include <cstdlib>
 
 using namespace jf;
 
@@ -266,10 +268,55 @@ static int try_mlp2_dmma(const MlpArgs<double>& m, cudaStream_t st) {
 template <typename T>
 static int try_mlp2_dmma(const MlpArgs<T>&, cudaStream_t) { return JF_ERR_UNSUPPORTED; }
 
+// fp64, hidden width 128, <= 16 inputs: the tcgen05 (int8-sliced, exact) kernel.  Needs the caller's workspace for the
+// pre-sliced last-layer weights; `prepared` skips the slicing pass (same weights as the previous call on this stream).
+constexpr int kI8NS = 7;
+static int i8_tn() {       // output-tile width: 64 (default; N = 32 MMAs run at the same 32 cycles: A-read bound) or 32
+    static const int tn = [] { const char* e = getenv("JF_I8_TN"); return (e != nullptr && atoi(e) == 32) ? 32 : 64; }();
+    return tn;
+}
+static bool i8_eligible(const JfMlpDesc* d, int dtype) {
+    static const bool off = [] { const char* e = getenv("JF_MLP_PATH"); return e != nullptr && strcmp(e, "dmma") == 0; }();
+    return !off && dtype == JF_F64 && d->n_linear == 2 && d->dims[1] == kI8H && d->dims[0] >= 1 && d->dims[0] <= kI8MaxKin &&
+           d->dims[2] >= 1;
+}
+static int64_t i8_ws_bytes(int N) {
+    const int64_t a = i8_prep_bytes<kI8NS, 32>(N), b = i8_prep_bytes<kI8NS, 64>(N);
+    return a > b ? a : b;
+}
+template <int TN>
+static int launch_mlp2_i8_tn(const MlpArgs<double>& m, void* ws, int prepared, cudaStream_t st) {
+    using Cfg = I8Cfg<kI8NS, TN>;
+    const int N = m.dims[2], n_tiles = (N + TN - 1) / TN;
+    if (!prepared) {
+        mlp_i8_prep_kernel<kI8NS, TN><<<n_tiles, 128, 0, st>>>(m.wt[1], N, (unsigned char*)ws);
+        const int rc = check_launch();
+        if (rc != JF_OK) return rc;
+    }
+    int dev = 0, sms = 0, smem_max = 0;
+    JF_CUDA_OK(cudaGetDevice(&dev));
+    JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    JF_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int n_slots = kI8MaxSlots;
+    while (n_slots > kI8NS && Cfg::smem_bytes(m.dims[0], n_slots) > smem_max) --n_slots;
+    if (n_slots < kI8NS + 1) return JF_ERR_UNSUPPORTED;
+    const int smem = Cfg::smem_bytes(m.dims[0], n_slots);
+    JF_CUDA_OK(cudaFuncSetAttribute(mlp2_i8_kernel<kI8NS, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t blocks = (m.B + kI8Rows - 1) / kI8Rows;
+    const unsigned grid = (unsigned)(blocks < sms ? blocks : sms);     // persistent: one CTA per SM
+    static const int dbg = [] { const char* e = getenv("JF_I8_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
+    mlp2_i8_kernel<kI8NS, TN><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots, dbg);
+    return check_launch();
+}
+static int launch_mlp2_i8(const MlpArgs<double>& m, void* ws, int prepared, cudaStream_t st) {
+    return i8_tn() == 64 ? launch_mlp2_i8_tn<64>(m, ws, prepared, st) : launch_mlp2_i8_tn<32>(m, ws, prepared, st);
+}
+static int launch_mlp2_i8(const MlpArgs<float>&, void*, int, cudaStream_t) { return JF_ERR_UNSUPPORTED; }
+
 template <typename T>
 static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, const int64_t* seg_ld,
                          const void* const* weights, const void* const* biases, void* out, int64_t so_p, int64_t so_r,
-                         int64_t B, cudaStream_t st) {
+                         int64_t B, cudaStream_t st, void* ws = nullptr, int64_t ws_bytes = 0, int prepared = 0) {
     MlpArgs<T> m;
     memset(&m, 0, sizeof(m));
     m.n_linear = desc->n_linear;
@@ -295,6 +342,9 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
     }
     m.out = (T*)out; m.so_p = so_p; m.so_r = so_r; m.B = B;
     m.lda = maxd | 1;
+    if (ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
+        ws_bytes >= i8_ws_bytes(desc->dims[2]))
+        return launch_mlp2_i8(m, ws, prepared, st);
     if (sizeof(T) == 8) {
         const int rc = try_mlp2_dmma(m, st);
         if (rc != JF_ERR_UNSUPPORTED) return rc;
@@ -322,6 +372,29 @@ extern "C" int jf_mlp_forward(const JfMlpDesc* desc, int dtype, const void* cons
     return JF_ERR_BAD_ARG;
 }
 
+extern "C" int64_t jf_mlp_workspace_bytes(const JfMlpDesc* desc, int dtype) {
+    if (desc == nullptr) return -1;
+    return i8_eligible(desc, dtype) ? i8_ws_bytes(desc->dims[2]) : 0;
+}
+
+extern "C" int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype, const void* const* seg_ptrs, const int64_t* seg_ld,
+                                 const void* const* weights, const void* const* biases, void* out,
+                                 int64_t out_stride_param, int64_t out_stride_row, int64_t B, void* workspace,
+                                 int64_t workspace_bytes, int prepared, void* stream) {
+    if (desc == nullptr || out == nullptr || seg_ptrs == nullptr || seg_ld == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_linear < 1 || desc->n_linear > JF_MAX_MLP_LINEAR) return JF_ERR_BAD_DESC;
+    if (desc->n_segments < 1 || desc->n_segments > JF_MAX_MLP_SEGMENTS) return JF_ERR_BAD_DESC;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return mlp_forward_t<double>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st,
+                                     workspace, workspace_bytes, prepared);
+    if (dtype == JF_F32)
+        return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st,
+                                    workspace, workspace_bytes, prepared);
+    return JF_ERR_BAD_ARG;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // whole-pdf orchestration (chunked; every launch on the caller's stream)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -335,7 +408,7 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 static inline size_t esize(int dtype) { return dtype == JF_F64 ? 8 : 4; }
 
 struct WsLayout {
-    int64_t params, emb[JF_MAX_SUBPDFS], logdet, logbase, scratch, total;
+    int64_t params, emb[JF_MAX_SUBPDFS], mlp[JF_MAX_SUBPDFS], mlp_bytes[JF_MAX_SUBPDFS], logdet, logbase, scratch, total;
 };
 
 static int ws_layout(const JfPdfDesc* d, int64_t chunk, WsLayout& w) {
@@ -350,6 +423,15 @@ static int ws_layout(const JfPdfDesc* d, int64_t chunk, WsLayout& w) {
     for (int k = 0; k < d->n_sub; ++k) {
         w.emb[k] = off;
         if (d->sub[k].manifold == 's') off = align_up(off + (int64_t)d->emb_dim[k] * chunk * es, 256);
+    }
+    for (int k = 0; k < d->n_sub; ++k) {
+        w.mlp[k] = off;
+        w.mlp_bytes[k] = 0;
+        if (d->has_mlp[k]) {
+            JfMlpDesc md = d->mlp[k];           // jf_mlp_workspace_bytes only looks at n_linear / dims
+            const int64_t nb = jf_mlp_workspace_bytes(&md, d->dtype);
+            if (nb > 0) { w.mlp_bytes[k] = nb; off = align_up(off + nb, 256); }
+        }
     }
     w.logdet = off; off = align_up(off + chunk * es, 256);
     w.logbase = off; off = align_up(off + chunk * es, 256);
@@ -419,8 +501,10 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
                     ++ns;
                 }
                 md.n_segments = ns;
-                rc = jf_mlp_forward(&md, d->dtype, seg_ptr, seg_ld, P->weights[k], P->biases[k], ws + w.params, chunk, 1,
-                                    n, st);
+                // the sliced last-layer weights are prepared by the first chunk and reused by the later ones
+                rc = jf_mlp_forward_ws(&md, d->dtype, seg_ptr, seg_ld, P->weights[k], P->biases[k], ws + w.params, chunk,
+                                       1, n, w.mlp_bytes[k] > 0 ? ws + w.mlp[k] : nullptr, w.mlp_bytes[k], r0 > 0 ? 1 : 0,
+                                       st);
                 if (rc != JF_OK) return rc;
                 params = ws + w.params;
                 sj = chunk;

@@ -351,7 +351,8 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
             v_eval(r, xn, yn, Jn, hn);
             ++evals;
             mn = T(1) - (yn[0] * tg[0] + yn[1] * tg[1] + yn[2] * tg[2]);
-            if (mn <= merit || converged) { ok = true; break; }
+            // near the root 1 - y.tg is pure rounding noise (~1e-16): trust the Newton step there
+            if (mn <= merit || converged || nrm < T(1e-5)) { ok = true; break; }
             scale *= T(0.5);
         }
         if (!ok) break;
@@ -361,7 +362,7 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
         merit = mn;
         if (converged) break;
     }
-    if (!(merit <= (sizeof(T) == 8 ? T(1e-13) : T(1e-5)))) converged = false;
+    if (!(merit <= (sizeof(T) == 8 ? T(1e-10) : T(1e-5)))) converged = false;
 }
 
 // reference exponential_map_s2.py:446-528 wrapped by sphere_base.py:601-695
