@@ -21,6 +21,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints exactly ONE line on stdout (the JSON); NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) goes
+# to stdout as well, so it is silenced unless explicitly kept
+if os.environ.get("JF_KEEP_NCCL_DEBUG") is None:
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
