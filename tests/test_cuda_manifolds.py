@@ -57,8 +57,10 @@ def test_cfg3_five_million_point_round_trip(lib_built):
     def emb(a):
         return torch.stack([a[:, 0].sin() * a[:, 1].cos(), a[:, 0].sin() * a[:, 1].sin(), a[:, 0].cos(), a[:, 2]], 1)
     err = (emb(x) - emb(x2)).abs().max(dim=1)[0]
-    # rows whose base point lies beyond the chart clamps (|z| > 5.3, 1e-6 cos(theta) clamp) have no exact pre-image
-    calm = (base.abs().max(dim=1)[0] < 5.2)
+    # The S2 chart clamps cos(theta) to +-(1 - 1e-6) (sphere_base.py:498-502): plane radii above sqrt(-2 log 5e-7) = 5.39
+    # or below 1e-3 have no exact pre-image (5e-7 of all rows each), in the reference as well as here.
+    r_s2 = base[:, :2].norm(dim=1)
+    calm = (r_s2 < 5.3) & (r_s2 > 2e-3) & (base[:, 2].abs() < 5.2)
     print("\ncfg3: 5M rows log_pdf %.1f ms (%.2e evals/s), inverse %.1f ms; round trip max |x-x'| %.2e (calm rows), "
           "99.9%% %.2e, excluded %d" % ((t1 - t0) * 1e3, n / (t1 - t0), (t2 - t1) * 1e3, float(err[calm].max()),
                                        float(err[calm].quantile(0.999)) if n <= 16_000_000 else -1, int((~calm).sum())))
@@ -118,7 +120,8 @@ def test_cfg4_four_million_rows_conditional(lib_built):
         torch.cuda.synchronize()
     t2 = time.perf_counter()
     err = (rt_z - z).abs().max(dim=1)[0] / z.abs().max(dim=1)[0].clamp(min=1)
-    calm = (z[:, :6].abs().max(dim=1)[0] < 5.2) & (z[:, 6:].norm(dim=1) < 5.2)
+    r_s2 = z[:, 6:].norm(dim=1)      # chart clamps: see test_cfg3_five_million_point_round_trip
+    calm = (z[:, :6].abs().max(dim=1)[0] < 5.2) & (r_s2 < 5.2) & (r_s2 > 2e-3)
     st = pc.kernel_status()
     print("\ncfg4: 4M rows sample %.1f ms (%.2e samples/s), log_pdf %.1f ms (%.2e evals/s); round trip max %.2e, status %s"
           % ((t1 - t0) * 1e3, n / (t1 - t0), (t2 - t1) * 1e3, n / (t2 - t1), float(err[calm].max()), st))
