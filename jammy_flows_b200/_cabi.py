@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libjammy_b200.so")
+# JF_LIB_PATH: experiment variants of the same library built by tools/build_variants.py (never another implementation)
+LIB_PATH = os.environ.get("JF_LIB_PATH") or os.path.join(PKG_DIR, "libjammy_b200.so")
 
 # ---- constants (keep in sync with include/jammy_b200.h; checked by tests/test_cabi_symbols.py) -----------------------
 JF_ABI_VERSION = 2

@@ -38,17 +38,20 @@ def needs_build():
     return (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < _newest_source_mtime()
 
 
-def build(force=False, verbose=True):
-    if not force and not needs_build():
+def build(force=False, verbose=True, extra_flags=(), out=None, tag=""):
+    """Build the library.  `extra_flags` / `out` / `tag` build an experiment variant next to the product library
+    (selected at run time with JF_LIB_PATH, tools/ only)."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
+    lib_path = out or LIB_PATH
     objs = []
-    build_dir = os.path.join(PKG_DIR, "build")
+    build_dir = os.path.join(PKG_DIR, "build" + (("_" + tag) if tag else ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
@@ -57,7 +60,7 @@ def build(force=False, verbose=True):
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
@@ -66,8 +69,8 @@ def build(force=False, verbose=True):
         f.write("\n".join(log))
     if verbose:
         spills = [l for l in "\n".join(log).splitlines() if "spill" in l and "0 bytes spill stores, 0 bytes spill loads" not in l]
-        print("built %s (%d kernels report spills; see %s)" % (LIB_PATH, len(spills), os.path.join(build_dir, "ptxas.log")))
-    return LIB_PATH
+        print("built %s (%d kernels report spills; see %s)" % (lib_path, len(spills), os.path.join(build_dir, "ptxas.log")))
+    return lib_path
 
 
 if __name__ == "__main__":

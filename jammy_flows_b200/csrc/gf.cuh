@@ -13,10 +13,11 @@
 #pragma once
 #include "common.cuh"
 
-// unroll factor of the loops over the K mixture kernels: enough independent exp/div chains in flight to hide the
-// DFMA latency, small enough to keep the Newton iteration inside the instruction cache
+// unroll factor of the loops over the K mixture kernels.  Measured on B200 (tools/build_variants.py + tools/kbench.py):
+// rolled (1) beats 2 by 4-14 % and 4 by 25 % on the sampling kernels -- the kernels are instruction-cache bound
+// (ncu stall_no_instruction), not latency bound (an Estrin-scheme exp with a 3x shorter dependency chain gains nothing)
 #ifndef JF_K_UNROLL
-#define JF_K_UNROLL 2
+#define JF_K_UNROLL 1
 #endif
 #define JF_PRAGMA_(x) _Pragma(#x)
 #define JF_PRAGMA(x) JF_PRAGMA_(x)

@@ -1,0 +1,14 @@
+"""Build experiment variants of libjammy_b200.so (different -D tuning flags) into jammy_flows_b200/variants/."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jammy_flows_b200 import build as B
+VARIANTS = {
+    "unroll2": ["-DJF_K_UNROLL=2"],
+    "estrin": ["-DJF_EXP_ESTRIN=1"],
+    "unroll4": ["-DJF_K_UNROLL=4"],
+    "estrin_unroll4": ["-DJF_EXP_ESTRIN=1", "-DJF_K_UNROLL=4"],
+}
+d = os.path.join(B.PKG_DIR, "variants")
+os.makedirs(d, exist_ok=True)
+for name in (sys.argv[1:] or VARIANTS):
+    B.build(force=True, extra_flags=VARIANTS[name], out=os.path.join(d, "lib_%s.so" % name), tag=name)
