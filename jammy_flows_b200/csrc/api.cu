@@ -270,26 +270,33 @@ static int try_mlp2_dmma(const MlpArgs<T>&, cudaStream_t) { return JF_ERR_UNSUPP
 
 // fp64, hidden width 128, <= 16 inputs: the tcgen05 (int8-sliced, exact) kernel.  Needs the caller's workspace for the
 // pre-sliced last-layer weights; `prepared` skips the slicing pass (same weights as the previous call on this stream).
-constexpr int kI8NS = 7;
+constexpr int kI8NS = 7;      // fp64: 7 int8 slices (54 fractional bits)
+constexpr int kI8NSF32 = 4;   // fp32: 4 int8 slices (30 fractional bits > the 24-bit significand)
 static int i8_tn() {       // output-tile width: 64 (default; N = 32 MMAs run at the same 32 cycles: A-read bound) or 32
     static const int tn = [] { const char* e = getenv("JF_I8_TN"); return (e != nullptr && atoi(e) == 32) ? 32 : 64; }();
     return tn;
 }
 static bool i8_eligible(const JfMlpDesc* d, int dtype) {
     static const bool off = [] { const char* e = getenv("JF_MLP_PATH"); return e != nullptr && strcmp(e, "dmma") == 0; }();
-    return !off && dtype == JF_F64 && d->n_linear == 2 && d->dims[1] == kI8H && d->dims[0] >= 1 && d->dims[0] <= kI8MaxKin &&
-           d->dims[2] >= 1;
+    if (off || d->n_linear != 2 || d->dims[1] != kI8H || d->dims[0] < 1 || d->dims[2] < 1) return false;
+    if (dtype == JF_F64) return d->dims[0] <= kI8MaxKin;
+    if (dtype == JF_F32) return d->dims[0] <= kI8MaxKinF32;
+    return false;
 }
-static int64_t i8_ws_bytes(int N) {
-    const int64_t a = i8_prep_bytes<kI8NS, 32>(N), b = i8_prep_bytes<kI8NS, 64>(N);
+static int64_t i8_ws_bytes(int N, int dtype) {
+    if (dtype == JF_F64) {
+        const int64_t a = i8_prep_bytes<kI8NS, 32>(N), b = i8_prep_bytes<kI8NS, 64>(N);
+        return a > b ? a : b;
+    }
+    const int64_t a = i8_prep_bytes<kI8NSF32, 32>(N), b = i8_prep_bytes<kI8NSF32, 64>(N);
     return a > b ? a : b;
 }
-template <int TN>
-static int launch_mlp2_i8_tn(const MlpArgs<double>& m, void* ws, int prepared, cudaStream_t st) {
-    using Cfg = I8Cfg<kI8NS, TN>;
+template <typename T, int NS, int TN>
+static int launch_mlp2_i8_tn(const MlpArgs<T>& m, void* ws, int prepared, cudaStream_t st) {
+    using Cfg = I8Cfg<NS, TN>;
     const int N = m.dims[2], n_tiles = (N + TN - 1) / TN;
     if (!prepared) {
-        mlp_i8_prep_kernel<kI8NS, TN><<<n_tiles, 128, 0, st>>>(m.wt[1], N, (unsigned char*)ws);
+        mlp_i8_prep_kernel<T, NS, TN><<<n_tiles, 128, 0, st>>>(m.wt[1], N, (unsigned char*)ws);
         const int rc = check_launch();
         if (rc != JF_OK) return rc;
     }
@@ -298,20 +305,24 @@ static int launch_mlp2_i8_tn(const MlpArgs<double>& m, void* ws, int prepared, c
     JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     JF_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int n_slots = kI8MaxSlots;
-    while (n_slots > kI8NS && Cfg::smem_bytes(m.dims[0], n_slots) > smem_max) --n_slots;
-    if (n_slots < kI8NS + 1) return JF_ERR_UNSUPPORTED;
-    const int smem = Cfg::smem_bytes(m.dims[0], n_slots);
-    JF_CUDA_OK(cudaFuncSetAttribute(mlp2_i8_kernel<kI8NS, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    while (n_slots > NS && Cfg::smem_bytes(m.dims[0], n_slots, (int)sizeof(T)) > smem_max) --n_slots;
+    if (n_slots < NS + 1) return JF_ERR_UNSUPPORTED;
+    const int smem = Cfg::smem_bytes(m.dims[0], n_slots, (int)sizeof(T));
+    JF_CUDA_OK(cudaFuncSetAttribute(mlp2_i8_kernel<T, NS, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t blocks = (m.B + kI8Rows - 1) / kI8Rows;
     const unsigned grid = (unsigned)(blocks < sms ? blocks : sms);     // persistent: one CTA per SM
     static const int dbg = [] { const char* e = getenv("JF_I8_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
-    mlp2_i8_kernel<kI8NS, TN><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots, dbg);
+    mlp2_i8_kernel<T, NS, TN><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots, dbg);
     return check_launch();
 }
 static int launch_mlp2_i8(const MlpArgs<double>& m, void* ws, int prepared, cudaStream_t st) {
-    return i8_tn() == 64 ? launch_mlp2_i8_tn<64>(m, ws, prepared, st) : launch_mlp2_i8_tn<32>(m, ws, prepared, st);
+    return i8_tn() == 64 ? launch_mlp2_i8_tn<double, kI8NS, 64>(m, ws, prepared, st)
+                         : launch_mlp2_i8_tn<double, kI8NS, 32>(m, ws, prepared, st);
 }
-static int launch_mlp2_i8(const MlpArgs<float>&, void*, int, cudaStream_t) { return JF_ERR_UNSUPPORTED; }
+static int launch_mlp2_i8(const MlpArgs<float>& m, void* ws, int prepared, cudaStream_t st) {
+    return i8_tn() == 64 ? launch_mlp2_i8_tn<float, kI8NSF32, 64>(m, ws, prepared, st)
+                         : launch_mlp2_i8_tn<float, kI8NSF32, 32>(m, ws, prepared, st);
+}
 
 template <typename T>
 static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, const int64_t* seg_ld,
@@ -343,7 +354,7 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
     m.out = (T*)out; m.so_p = so_p; m.so_r = so_r; m.B = B;
     m.lda = maxd | 1;
     if (ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
-        ws_bytes >= i8_ws_bytes(desc->dims[2]))
+        ws_bytes >= i8_ws_bytes(desc->dims[2], sizeof(T) == 8 ? JF_F64 : JF_F32))
         return launch_mlp2_i8(m, ws, prepared, st);
     if (sizeof(T) == 8) {
         const int rc = try_mlp2_dmma(m, st);
@@ -374,7 +385,7 @@ extern "C" int jf_mlp_forward(const JfMlpDesc* desc, int dtype, const void* cons
 
 extern "C" int64_t jf_mlp_workspace_bytes(const JfMlpDesc* desc, int dtype) {
     if (desc == nullptr) return -1;
-    return i8_eligible(desc, dtype) ? i8_ws_bytes(desc->dims[2]) : 0;
+    return i8_eligible(desc, dtype) ? i8_ws_bytes(desc->dims[2], dtype) : 0;
 }
 
 extern "C" int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype, const void* const* seg_ptrs, const int64_t* seg_ld,

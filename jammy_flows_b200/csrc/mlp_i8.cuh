@@ -32,7 +32,8 @@ constexpr int kI8Rows = 128;      // rows per CTA = UMMA M
 constexpr int kI8H = 128;         // hidden width = K (bytes per slice row)
 constexpr int kI8Threads = 512;    // 16 warps: 0 MMA issue, 1 W2 producer, 2 TMEM alloc, 4-15 epilogue; all 16 in the prologue
 constexpr int kI8EpiWarps = 12;
-constexpr int kI8MaxKin = 16;
+constexpr int kI8MaxKin = 16;     // fp64: inputs of a row live in registers
+constexpr int kI8MaxKinF32 = 96;  // fp32: inputs are streamed from shared memory
 constexpr int kI8MaxSlots = 12;   // ring of W2-slice buffers (as many as fit next to the A slices, >= NS + 1)
 
 template <int NS, int TN>
@@ -48,8 +49,8 @@ struct I8Cfg {
     static constexpr int offB = offA + NS * kSliceBytesA;
     // after the n_slots W2-slice buffers: 512 B of mbarriers + tmem pointer, 4*TN doubles of per-tile constants,
     // W1^T [Kin][128] + b1[128] doubles, the gathered inputs [128][Kin|1]
-    __host__ __device__ static constexpr int tail_bytes(int kin) { return 512 + 4 * TN * 8 + (kin + 1) * kI8H * 8 + kI8Rows * (kin | 1) * 8; }
-    __host__ __device__ static constexpr int smem_bytes(int kin, int n_slots) { return offB + n_slots * kSliceBytesB + tail_bytes(kin); }
+    __host__ __device__ static constexpr int tail_bytes(int kin, int es) { return 512 + 4 * TN * 8 + (kin + 1) * kI8H * es + kI8Rows * (kin | 1) * es; }
+    __host__ __device__ static constexpr int smem_bytes(int kin, int n_slots, int es) { return offB + n_slots * kSliceBytesB + tail_bytes(kin, es); }
 };
 
 // bytes of device workspace for the pre-sliced W2 of an [N, 128] last layer: tiles + per-column scale (double)
@@ -135,6 +136,12 @@ JF_DEVINL double tanh_abs(double x) {
     return x < 0.0 ? -t : t;
 }
 
+JF_DEVINL float tanh_abs(float x) {
+    const float e = expf(-2.0f * fabsf(x));
+    const float t = (1.0f - e) / (1.0f + e);
+    return x < 0.0f ? -t : t;
+}
+
 // balanced base-256 digits of the fixed-point value round(v * 2^FA): byte s of the result is digit s (two's complement
 // int8), s = 0 least significant.  v + C makes every digit an unsigned byte (carries included), ^C recentres it.
 template <int NS>
@@ -143,11 +150,18 @@ JF_DEVINL unsigned long long to_digits(double v) {
     const long long q = __double2ll_rn(v * (double)(1ull << (8 * NS - 2)));
     return ((unsigned long long)q + C) ^ C;
 }
+template <int NS>
+JF_DEVINL unsigned long long to_digits(float v) {      // NS <= 4: 32-bit fixed point (|v| <= 1 -> |q| <= 2^(8NS-2))
+    static_assert(NS <= 4, "fp32 operands carry 24 bits: at most 4 slices");
+    constexpr unsigned C = 0x80808080u >> (8 * (4 - NS));
+    const int q = __float2int_rn(v * (float)(1u << (8 * NS - 2)));
+    return (unsigned long long)(((unsigned)q + C) ^ C);
+}
 
 // ---- prep: W2 [N,128] fp64 -> NS int8 slices per tile of TN output columns, in the UMMA smem layout -------------------
 // ws layout: [tile][slice q][TN*128 bytes], then double scale[n_tiles*TN] (= 2^e_j * 2^-12; 0 for padded columns)
-template <int NS, int TN>
-__global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const double* __restrict__ W2, int N, unsigned char* ws) {
+template <typename T, int NS, int TN>
+__global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const T* __restrict__ W2, int N, unsigned char* ws) {
     const int tile = blockIdx.x, n_tiles = gridDim.x;
     double* scl = reinterpret_cast<double*>(ws + (size_t)n_tiles * NS * TN * kI8H);
     __shared__ double s_inv[TN];
@@ -155,7 +169,7 @@ __global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const double* __restri
         const int j = tile * TN + jj;
         double mx = 0.0;
         if (j < N)
-            for (int k = 0; k < kI8H; ++k) mx = fmax(mx, fabs(W2[(size_t)j * kI8H + k]));
+            for (int k = 0; k < kI8H; ++k) mx = fmax(mx, fabs((double)W2[(size_t)j * kI8H + k]));
         int e = 0;
         if (mx > 0.0) { frexp(mx, &e); }                 // mx = f * 2^e, f in [0.5,1)  =>  |W/2^e| < 1
         s_inv[jj] = ldexp(1.0, -e);
@@ -166,7 +180,7 @@ __global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const double* __restri
     for (int idx = threadIdx.x; idx < TN * kI8H; idx += blockDim.x) {
         const int jj = idx / kI8H, k = idx - jj * kI8H;
         const int j = tile * TN + jj;
-        const double w = (j < N) ? W2[(size_t)j * kI8H + k] * s_inv[jj] : 0.0;
+        const T w = (j < N) ? (T)((double)W2[(size_t)j * kI8H + k] * s_inv[jj]) : T(0);   // power-of-two scaling: exact
         const unsigned long long dg = to_digits<NS>(w);
         const int off = (k >> 4) * (TN / 8) * 128 + (jj >> 3) * 128 + (jj & 7) * 16 + (k & 15);
 #pragma unroll
@@ -181,8 +195,8 @@ __global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const double* __restri
 // (free-running MMA 0.53 ms + free-running LDTM 0.40 ms = 0.98 ms together, profiles/), so a double-buffered or
 // level-major accumulator scheme only adds hand-shakes.  What does overlap with the next tile's MMAs is the fp64
 // scale/bias and the global stores, which run after TMEM has been handed back.
-template <int NS, int TN>
-__global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_constant__ MlpArgs<double> m,
+template <typename T, int NS, int TN>
+__global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_constant__ MlpArgs<T> m,
                                                                  const unsigned char* __restrict__ wsB, int n_slots,
                                                                  int dbg) {
     using Cfg = I8Cfg<NS, TN>;
@@ -203,9 +217,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
     const uint32_t bar_a_free = bar0 + 8 * 48;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 448);
     double* sE = reinterpret_cast<double*>(smem + offBar + 512);   // [2][2][TN]: scale, b2 of the current / next tile
-    double* sW1 = sE + 4 * TN;                                     // [Kin][128]
-    double* sB1 = sW1 + (size_t)Kin * kI8H;
-    double* sIn = sB1 + kI8H;                                      // [128][Kin|1]
+    T* sW1 = reinterpret_cast<T*>(sE + 4 * TN);                    // [Kin][128]
+    T* sB1 = sW1 + (size_t)Kin * kI8H;
+    T* sIn = sB1 + kI8H;                                           // [128][Kin|1]
     const int ldin = Kin | 1;
     // W2 tiles are visited in a per-CTA rotated order so that the CTAs do not all hit the same L2 lines at once
     const int tile_rot = (int)(blockIdx.x % (unsigned)n_tiles);
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
     int mm_slot0 = 0, mm_wrap0 = 0;
     uint32_t tile_par = 0;                                           // parity of the running tile index (all roles)
     const double* scl_g = reinterpret_cast<const double*>(wsB + (size_t)n_tiles * NS * TN * kI8H);
-    const double* __restrict__ b2_g = m.bias[1];
+    const T* __restrict__ b2_g = m.bias[1];
     constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kI8Rows >> 4) << 24);
 
 #pragma unroll 1
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
             const int r = e / Kin;
             int c = e - r * Kin;
             const int64_t row = row0 + r;
-            double v = 0.0;
+            T v = T(0);
             if (row < m.B) {
                 int sg = 0;
                 while (c >= m.seg_cols[sg]) { c -= m.seg_cols[sg]; ++sg; }
@@ -279,9 +293,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
         // ---- prologue: layer 1 + tanh + digits -> A slices ----
         if (!(dbg & 8)) {
             const int r = (warp & 3) * 32 + lane, quarter = warp >> 2;    // thread = (row, quarter of the hidden units)
-            double in[kI8MaxKin];
+            T in[kI8MaxKin];                                               // fp64 path only (Kin <= 16)
+            if (sizeof(T) == 8) {
 #pragma unroll
-            for (int i = 0; i < kI8MaxKin; ++i) in[i] = (i < Kin) ? sIn[r * ldin + i] : 0.0;
+                for (int i = 0; i < kI8MaxKin; ++i) in[i] = (i < Kin) ? sIn[r * ldin + i] : T(0);
+            }
             const uint32_t a_row = sbase + Cfg::offA + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {                              // 16 hidden units per chunk
@@ -290,14 +306,30 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
                     unsigned long long dg[4];
+                    if (sizeof(T) == 8) {
 #pragma unroll
-                    for (int uu = 0; uu < 4; ++uu) {
-                        const int u = chunk * 16 + gq * 4 + uu;
-                        double z = sB1[u];
+                        for (int uu = 0; uu < 4; ++uu) {
+                            const int u = chunk * 16 + gq * 4 + uu;
+                            T z = sB1[u];
 #pragma unroll
-                        for (int i = 0; i < kI8MaxKin; ++i)
-                            if (i < Kin) z = fma(in[i], sW1[i * kI8H + u], z);
-                        dg[uu] = to_digits<NS>(tanh_abs(z));
+                            for (int i = 0; i < kI8MaxKin; ++i)
+                                if (i < Kin) z = fma(in[i], sW1[i * kI8H + u], z);
+                            dg[uu] = to_digits<NS>(tanh_abs(z));
+                        }
+                    } else {
+                        // fp32: many inputs (conditional input + embeddings): stream them from shared memory, 4 units at once
+                        const int u0 = chunk * 16 + gq * 4;
+                        T z0 = sB1[u0], z1 = sB1[u0 + 1], z2 = sB1[u0 + 2], z3 = sB1[u0 + 3];
+                        const T* xin = sIn + r * ldin;
+#pragma unroll 4
+                        for (int i = 0; i < Kin; ++i) {
+                            const T xi = xin[i];
+                            const T* wrow = sW1 + i * kI8H + u0;
+                            z0 = fma(xi, wrow[0], z0); z1 = fma(xi, wrow[1], z1);
+                            z2 = fma(xi, wrow[2], z2); z3 = fma(xi, wrow[3], z3);
+                        }
+                        dg[0] = to_digits<NS>(tanh_abs(z0)); dg[1] = to_digits<NS>(tanh_abs(z1));
+                        dg[2] = to_digits<NS>(tanh_abs(z2)); dg[3] = to_digits<NS>(tanh_abs(z3));
                     }
                     // 4x4 byte transposes: word s of the result holds digit s of units 0..3 (byte b = unit b)
                     {
@@ -307,7 +339,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
                         lo[gq][0] = __byte_perm(x01, x23, 0x5410); lo[gq][1] = __byte_perm(x01, x23, 0x7632);
                         lo[gq][2] = __byte_perm(y01, y23, 0x5410); lo[gq][3] = __byte_perm(y01, y23, 0x7632);
                     }
-                    {
+                    if (NS > 4) {
                         const uint32_t a0 = (uint32_t)(dg[0] >> 32), a1 = (uint32_t)(dg[1] >> 32),
                                        a2 = (uint32_t)(dg[2] >> 32), a3 = (uint32_t)(dg[3] >> 32);
                         const uint32_t x01 = __byte_perm(a0, a1, 0x5140), y01 = __byte_perm(a0, a1, 0x7362);
@@ -321,7 +353,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
                     const uint32_t addr = a_row + (NS - 1 - sd) * Cfg::kSliceBytesA + chunk * Cfg::kLboA;
                     uint32_t w0, w1, w2, w3;
                     if (sd < 4) { w0 = lo[0][sd]; w1 = lo[1][sd]; w2 = lo[2][sd]; w3 = lo[3][sd]; }
-                    else { w0 = hi[0][sd - 4]; w1 = hi[1][sd - 4]; w2 = hi[2][sd - 4]; w3 = hi[3][sd - 4]; }
+                    else { w0 = hi[0][sd & 3]; w1 = hi[1][sd & 3]; w2 = hi[2][sd & 3]; w3 = hi[3][sd & 3]; }
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
                 }
             }
@@ -380,9 +412,14 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
                 if (et < 2 * TN) {
                     const int which = et / TN, jj = et - which * TN;
                     const int n = tile_of(t) * TN + jj;
-                    const double* src = which == 0 ? (scl_g + n) : (b2_g + (n < N ? n : N - 1));
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sE + ((t & 1) * 2 + which) * TN + jj);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                    if (which == 0) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(scl_g + n) : "memory");
+                    } else {        // b2 has the caller's element size: 8 or 4 bytes into the 8-byte cell
+                        const T* src = b2_g + (n < N ? n : N - 1);
+                        if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+                    }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
@@ -390,7 +427,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
             uint32_t par = tile_par;
             for (int t = 0; t < n_tiles; ++t, par ^= 1u) {
                 if (t + 1 < n_tiles) fetch_consts(t + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
-                double acc_d[kMine][8];
+                T acc_d[kMine][8];
                 const uint32_t tbase = tmem + ((uint32_t)(lq * 32) << 16);
                 mbar_wait(bar_lvl_full(0), par);
                 tc_fence_after();
@@ -404,13 +441,21 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            // Horner over the levels in fp64; int32 -> double without I2F: the bit pattern of 2^52 + 2^31 + v
-                            // minus that bias is exact.  7 roundings at 2^-53 relative: far below the 2^-8NS truncation.
-                            double sacc = __hiloint2double(0x43300000, v[NS - 1][j] ^ 0x80000000) - 4503601774854144.0;
+                            if (sizeof(T) == 8) {
+                                // Horner over the levels in fp64; int32 -> double without I2F: the bit pattern of 2^52 + 2^31 + v
+                                // minus that bias is exact.  7 roundings at 2^-53 relative: far below the 2^-8NS truncation.
+                                double sacc = __hiloint2double(0x43300000, v[NS - 1][j] ^ 0x80000000) - 4503601774854144.0;
 #pragma unroll
-                            for (int l = NS - 2; l >= 0; --l)
-                                sacc = fma(sacc, 0.00390625, __hiloint2double(0x43300000, v[l][j] ^ 0x80000000) - 4503601774854144.0);
-                            acc_d[i][j] = sacc;
+                                for (int l = NS - 2; l >= 0; --l)
+                                    sacc = fma(sacc, 0.00390625, __hiloint2double(0x43300000, v[l][j] ^ 0x80000000) - 4503601774854144.0);
+                                acc_d[i][j] = (T)sacc;
+                            } else {
+                                // fp32: the level sums (< 2^24) are exact floats; Horner in fp32 (NS roundings at 2^-24)
+                                float sacc = (float)v[NS - 1][j];
+#pragma unroll
+                                for (int l = NS - 2; l >= 0; --l) sacc = fmaf(sacc, 0.00390625f, (float)v[l][j]);
+                                acc_d[i][j] = (T)sacc;
+                            }
                         }
                     }
                 }
@@ -428,7 +473,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int n = n0 + c * 8 + j;
-                            const double o = fma(acc_d[i][j], sc[c * 8 + j], sc[TN + c * 8 + j]);
+                            T o;
+                            if (sizeof(T) == 8) o = (T)fma((double)acc_d[i][j], sc[c * 8 + j], sc[TN + c * 8 + j]);
+                            else o = (T)fmaf((float)acc_d[i][j], (float)sc[c * 8 + j], reinterpret_cast<const float*>(sc + TN + c * 8 + j)[0]);
                             if (n < N && row < m.B) m.out[(int64_t)n * m.so_p + row * m.so_r] = o;
                         }
                     }
