@@ -181,6 +181,23 @@ int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int direction,
                     int64_t B, int64_t* status, void* stream);
 
 /*
+ * Training: gradient of the log_pdf of ONE Euclidean "g" sub-pdf with respect to its PER-ROW raw parameters (what the
+ * reference obtains from autograd through gaussianization_flow.py:995-1057 / :699-861 / :389-454); the caller chains it
+ * into the parameter generator's backward (main/default.py:956).
+ *   x            [B, d] target coordinates (ld_x), as passed to jf_subpdf_apply in the LOGPDF direction
+ *   params       per-row raw parameters, element (j,row) at params[j*p_stride_param + row*p_stride_row], p_stride_row != 0
+ *   grad_logp    [B] upstream gradient of log p = log N(base) + logdet per row, or NULL (= 1)
+ *   grad_params  out, indexed like params
+ * Rows whose base point lies in the Pade tails of an inverse-normal stage (|z| > 5.33, ~1e-7 of all rows) get a zero
+ * gradient for that stage and are counted in status[JF_STATUS_OUT_OF_RANGE].
+ */
+int jf_subpdf_backward(const JfSubPdfDesc* desc, int dtype,
+                       const void* x, int64_t ld_x,
+                       const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                       const void* grad_logp, void* grad_params,
+                       int64_t B, int64_t* status, void* stream);
+
+/*
  * params = W_L * tanh(... tanh(W_1 * concat(segments) + b_1) ...) + b_L for B rows.
  *   seg_ptrs[i]/seg_ld[i]  column block i: [B, seg_cols[i]] with leading dimension seg_ld[i].
  *   weights[l]             weight of Linear l in torch layout: [dims[l+1], dims[l]] row-major (= Linear.weight).

@@ -81,6 +81,7 @@ _vp, _i64, _i32p = C.c_void_p, C.c_int64, C.POINTER(C.c_int32)
 SYMBOLS = {
     "jf_subpdf_apply": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp,
                                   _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "jf_subpdf_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
     "jf_mlp_forward": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
                                  C.POINTER(_vp), _vp, _i64, _i64, _i64, _vp]),
     "jf_mlp_workspace_bytes": (_i64, [C.POINTER(JfMlpDesc), C.c_int]),

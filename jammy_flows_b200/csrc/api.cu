@@ -9,6 +9,7 @@
 #include "mlp_kernels.cuh"
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
+#include "gf_bwd.cuh"
 #include <cstdlib>
 
 using namespace jf;
@@ -233,6 +234,59 @@ extern "C" int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int directio
     if (dtype == JF_F32)
         return subpdf_apply_t<float>(desc, direction, in, ld_in, params, p_stride_param, p_stride_row, logdet_in,
                                      logdet_out, logbase_in, logbase_out, out, ld_out, emb_out, ld_emb, B, status, st);
+    return JF_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// jf_subpdf_backward: per-row parameter gradients of the log_pdf of a Euclidean "g" sub-pdf
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int subpdf_backward_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, const void* params, int64_t sp,
+                             int64_t sr, const void* grad_logp, void* grad_params, int64_t B, int64_t* status,
+                             cudaStream_t st) {
+    GfBwdArgs<T> g;
+    fill_common<T>(g.a, desc, x, ld_x, params, sp, sr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, B, status);
+    g.grad_logp = (const T*)grad_logp;
+    g.grad_params = (T*)grad_params;
+    const int d = desc->dim;
+    if (d < 1 || d > kBwdMaxDim) return JF_ERR_UNSUPPORTED;
+    int kmax = 1;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const JfLayerDesc& L = desc->layers[l];
+        if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_UNSUPPORTED;
+        if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
+        if (L.inv_type == JF_INV_FULL_PADE || L.inv_type == JF_INV_PARTLY_CRUDE) return JF_ERR_UNSUPPORTED;
+        const int expect = (L.has_offset ? d : 0) + L.hh_iter * d + (L.norm_mode != JF_NORM_NONE ? 3 : 2) * L.K * d;
+        if (expect != L.n_params) return JF_ERR_BAD_DESC;
+        GfLayerC<T>& c = g.layers[l];
+        c.K = L.K; c.d = d; c.hh_iter = L.hh_iter; c.inv_type = L.inv_type; c.norm_mode = L.norm_mode;
+        c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = 0;
+        c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = (T)L.n_min; c.n_max = (T)L.n_max;
+        kmax = L.K > kmax ? L.K : kmax;
+    }
+    const int threads = 128;
+    const size_t smem = (size_t)3 * kmax * threads * sizeof(T);
+    if (smem > 48 * 1024)
+        JF_CUDA_OK(cudaFuncSetAttribute(gf_chain_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (B + threads - 1) / threads;
+    gf_chain_backward_kernel<T><<<(unsigned)blocks, threads, smem, st>>>(g);
+    return check_launch();
+}
+
+extern "C" int jf_subpdf_backward(const JfSubPdfDesc* desc, int dtype, const void* x, int64_t ld_x, const void* params,
+                                  int64_t p_stride_param, int64_t p_stride_row, const void* grad_logp, void* grad_params,
+                                  int64_t B, int64_t* status, void* stream) {
+    if (desc == nullptr || x == nullptr || params == nullptr || grad_params == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
+    if (desc->manifold != 'e') return JF_ERR_UNSUPPORTED;
+    if (p_stride_row == 0) return JF_ERR_UNSUPPORTED;      // shared (permanent) parameters: no backward kernel yet
+    if (B < 0) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return subpdf_backward_t<double>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, B, status, st);
+    if (dtype == JF_F32)
+        return subpdf_backward_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, B, status, st);
     return JF_ERR_BAD_ARG;
 }
 

@@ -1,0 +1,263 @@
+// Backward of the Euclidean "g"-chain log_pdf (training, BASELINE configs[4]): per-row gradient of
+//   log p(x) = sum_j log N(z_j) + sum_layers sum_j log y'(v_j)
+// with respect to the PER-ROW raw parameters the MLP emitted (the reference gets these from autograd through
+// gaussianization_flow.py:995-1057, :699-861, :389-454; here they are closed-form, one thread per row, nothing stored
+// in HBM but the inputs and the gradient buffer).
+//
+//   forward (recomputed): for l = L-1 .. 0:  u = x - offset_l ; v = Q_l^T u ; (y_j, l_j) = stage_l(v_j) ; x = y
+//                         the pre-stage vectors v of every layer are kept in local memory (L*d values)
+//   backward: ybar = -z * g_row (from the base density), lbar = g_row; for l = 0 .. L-1:
+//       per dimension: closed-form derivatives of the K-logistic mixture and of the inverse-CDF stage with respect to
+//           v, the means, 1/w and the weights, chained through the width / norm regulators to the raw parameters;
+//       rotation: the Householder reflections are involutions, so their inputs are recovered by re-applying them to
+//           the output -- no intermediate is stored; gradients with respect to the reflection vectors in closed form;
+//       offset: minus the input gradient.
+// Supported stages: isigmoid and inormal_partly_precise (bulk and Pade tails); per-row parameters only.
+#pragma once
+#include "gf.cuh"
+#include "subpdf_args.cuh"
+
+namespace jf {
+
+template <typename T>
+struct GfBwdArgs {
+    SubPdfArgs<T> a;           // in = targets x, params = raw per-row parameters; out / logdet / logbase unused
+    const T* grad_logp;        // [B] upstream gradient of log_pdf (NULL = 1)
+    T* grad_params;            // same indexing as params: element (i,row) at grad_params[i*sj + row*sr]
+    GfLayerC<T> layers[JF_MAX_LAYERS];
+};
+
+// regulated parameters of (layer, dimension j) into this thread's slots WITHOUT normalising the weights; returns their sum
+template <typename T>
+__device__ __noinline__ T bwd_regulate(const GfLayerC<T>& c, int K, int j, const T* p, int64_t sj, T* slots) {
+    const int d = c.d, nt = blockDim.x;
+    T* sm = slots + threadIdx.x;
+    T* si = sm + (size_t)K * nt;
+    T* sn = si + (size_t)K * nt;
+    const T* pm = p + (int64_t)(c.raw_m() + j) * sj;
+    const T* pw = p + (int64_t)(c.raw_w() + j) * sj;
+    const T* pn = p + (int64_t)(c.raw_n() + j) * sj;
+    const int64_t step = (int64_t)d * sj;
+    T nmax = -Num<T>::big;
+    if (c.norm_mode == JF_NORM_RAW)
+        for (int k = 0; k < K; ++k) nmax = tmax(nmax, pn[k * step]);
+    T G = 0;
+    for (int k = 0; k < K; ++k) {
+        sm[(size_t)k * nt] = pm[k * step];
+        si[(size_t)k * nt] = regulate_inv_width(pw[k * step], c.w_min, c.inv_w_max);
+        T g;
+        if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(pn[k * step], c.n_min, c.n_max);
+        else if (c.norm_mode == JF_NORM_RAW) g = exp(pn[k * step] - nmax);
+        else g = T(1);
+        sn[(size_t)k * nt] = g;
+        G += g;
+    }
+    return G;
+}
+
+// backward of one element: v -> (y, l).  gy, gl: upstream gradients of y and l.  Writes the raw-parameter gradients of
+// this (layer, dimension) and returns the gradient with respect to v.  Returns false for rows outside the bulk.
+template <typename T>
+__device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j, T v, T gy, T gl, T G, const T* slots,
+                                              T* gp /* grad_params row base */, int64_t sj, T& vbar) {
+    const int nt = blockDim.x;
+    const T* sm = slots + threadIdx.x;
+    const T* si = sm + (size_t)K * nt;
+    const T* sn = si + (size_t)K * nt;
+    const T invG = T(1) / G;
+    // ---- pass 1: common rescaling exponent (all kernels on one side of v) ----
+    bool any_pos = false, any_neg = false;
+    T delta = Num<T>::big;
+    for (int k = 0; k < K; ++k) {
+        const T a = (v - sm[(size_t)k * nt]) * si[(size_t)k * nt];
+        any_pos = any_pos || (a >= T(0));
+        any_neg = any_neg || (a < T(0));
+        delta = tmin(delta, fabs(a));
+    }
+    const bool all_neg = !any_pos, all_pos = !any_neg;
+    if (!(all_neg || all_pos)) delta = T(0);
+    const T E = exp(-delta);
+    // ---- pass 2: the rescaled sums (csrc/gf.cuh mix_eval without the softplus-threshold bookkeeping) ----
+    T Sc = 0, Ss = 0, Sp = 0, Sd = 0;
+    for (int k = 0; k < K; ++k) {
+        const T iw = si[(size_t)k * nt], n = sn[(size_t)k * nt] * invG;
+        const T a = (v - sm[(size_t)k * nt]) * iw;
+        const T u = exp(delta - fabs(a)), e = u * E;
+        const T rx = T(1) / (T(1) + e);
+        const T big = n * rx, small = big * u;
+        if (a >= T(0)) { Sc += big; Ss += small; } else { Sc += small; Ss += big; }
+        const T pt = small * iw * rx;                 // n sigma (1-sigma) / w, rescaled by 1/E
+        Sp += pt;
+        Sd += (a >= T(0) ? -pt : pt) * iw * (T(1) - e) * rx;
+    }
+    // true values: C = Sc*e^-dc, S = Ss*e^-ds, p = Sp*E, p' = Sd*E  (dc = delta if all_neg, ds = delta if all_pos)
+    const T fC = all_neg ? T(1) : E, fS = all_pos ? T(1) : E;     // what is left of E after dividing by C resp. S
+    T y_coefC, y_coefS;     // coefficients of (dC/dtheta)/E and (dS/dtheta)/E
+    T nC, nS;               // coefficients of sigma_k and (1 - sigma_k) in their side-dependent rescaled form
+    T nC_true = 0;          // coefficient of the TRUE sigma_k (terms that depend on C itself, not on log C)
+    if (c.inv_type == JF_INV_ISIGMOID) {
+        y_coefC = (gy - gl) * fC / Sc;
+        y_coefS = -(gy + gl) * fS / Ss;
+        nC = (gy - gl) / Sc;
+        nS = -(gy + gl) / Ss;
+    } else {
+        const T Ct = Sc * (all_neg ? E : T(1)), St = Ss * (all_pos ? E : T(1));
+        const T eps = T(0.5e-7);
+        if (c.inv_type != JF_INV_PARTLY_PRECISE) { vbar = T(0); return false; }
+        const bool upper = !(St > eps), lower = !(Ct > eps);
+        if (!upper && !lower) {
+            // bulk: y = Phi^-1(C), l = log sqrt(2 pi) + y^2/2 + log p   (gaussianization_flow.py:499-500, :604-606)
+            const T er = (Ct <= T(0.5)) ? -erfcinv(T(2) * Ct) : erfcinv(T(2) * St);
+            const T y = T(1.4142135623730951) * er;
+            const T D = T(2.5066282746310002) * exp(er * er);      // 1/phi(y)
+            nC_true = (gy + gl * y) * D;                            // d/dC of gy*y + gl*l
+            y_coefC = nC_true * E;
+            y_coefS = T(0);
+            nC = T(0);
+            nS = T(0);
+        } else {
+            // Pade tails (gaussianization_flow.py:507-536, :608-636): with L = log C + log S + log 4, F = c + L/2,
+            // F2 = sqrt(F^2 - L/a):  y = +-sqrt(2 (F2 - F)),
+            // l = log(F2 - F + 1/a) - log sqrt(8) - 1/2 log(F2 - F) - log F2 - log S - log C + log|1 - 2C| + log p
+            const T pa = T(0.147), pc = T(2.0 / (kPi * 0.147));
+            const T Lf = (log(Sc) - (all_neg ? delta : T(0))) + (log(Ss) - (all_pos ? delta : T(0))) + T(1.3862943611198906);
+            const T F = pc + Lf * T(0.5);
+            const T F2 = sqrt(F * F - Lf / pa);
+            const T dF2 = (F - T(1) / pa) / (T(2) * F2);           // dF2/dL ; dF/dL = 1/2
+            const T diff = F2 - F;
+            const T yv = (upper ? T(1) : T(-1)) * sqrt(tmax(T(0), T(2) * diff));
+            const T dy = (dF2 - T(0.5)) / yv;
+            const T dl = (dF2 - T(0.5)) / (diff + T(1) / pa) - T(0.5) * (dF2 - T(0.5)) / diff - dF2 / F2;
+            const T gL = gy * dy + gl * dl;
+            nC_true = -T(2) * gl / (T(1) - T(2) * Ct);             // d/dC of gl*log|1 - 2C|
+            y_coefC = (gL - gl) * fC / Sc + nC_true * E;
+            y_coefS = (gL - gl) * fS / Ss;
+            nC = (gL - gl) / Sc;
+            nS = (gL - gl) / Ss;
+        }
+    }
+    const T cCS = y_coefC - y_coefS;                                // dC/dtheta = -dS/dtheta for v, m, 1/w
+    const T glp = gl / Sp;
+    vbar = cCS * Sp + glp * Sd;
+    // ---- pass 3: per-kernel gradients ----
+    T nbar_dot = 0;                                                 // sum_k nbar_k n_k (normalisation Jacobian)
+    const int d = c.d;
+    T* gm = gp + (int64_t)(c.raw_m() + j) * sj;
+    T* gw = gp + (int64_t)(c.raw_w() + j) * sj;
+    T* gn = gp + (int64_t)(c.raw_n() + j) * sj;
+    const int64_t step = (int64_t)d * sj;
+    for (int k = 0; k < K; ++k) {
+        const T m = sm[(size_t)k * nt], iw = si[(size_t)k * nt], g = sn[(size_t)k * nt], n = g * invG;
+        const T a = (v - m) * iw;
+        const T u = exp(delta - fabs(a)), e = u * E;
+        const T rx = T(1) / (T(1) + e);
+        const T t = u * rx * rx;                                    // sigma (1-sigma) / E
+        const T om2s = (a >= T(0) ? -(T(1) - e) : (T(1) - e)) * rx; // 1 - 2 sigma
+        const T mbar = n * (-cCS * t * iw - glp * t * om2s * iw * iw);
+        const T iwbar = n * (cCS * t * (v - m) + glp * t * (T(1) + om2s * a));
+        // sigma_k and 1 - sigma_k: rescaled like the sums they are divided by (sigC, sigS) and true (sig_t)
+        const T sigC = (a >= T(0)) ? rx : u * rx, sigS = (a >= T(0)) ? u * rx : rx;
+        const T sig_t = (a >= T(0)) ? rx : u * rx * E;
+        const T nbar = nC * sigC + nS * sigS + nC_true * sig_t + glp * t * iw;
+        nbar_dot = fma(nbar, n, nbar_dot);
+        gm[k * step] = mbar;
+        // 1/w = q/(w_min q + 1), q = 1/w_max + exp(-raw): d(1/w)/d raw = -(q - 1/w_max) (1 - w_min/w)^2
+        const T om = T(1) - c.w_min * iw;
+        const T q = iw / om;
+        gw[k * step] = -iwbar * (q - c.inv_w_max) * om * om;
+        if (c.norm_mode != JF_NORM_NONE) gn[k * step] = nbar;       // finished below (needs nbar_dot)
+    }
+    if (c.norm_mode != JF_NORM_NONE) {
+        for (int k = 0; k < K; ++k) {
+            const T g = sn[(size_t)k * nt];
+            const T gbar = (gn[k * step] - nbar_dot) * invG;        // n_k = g_k / G
+            T dg;
+            if (c.norm_mode == JF_NORM_REGULATED) { const T s = (g - c.n_min) / c.n_max; dg = c.n_max * s * (T(1) - s); }
+            else dg = g;
+            gn[k * step] = gbar * dg;
+        }
+    }
+    return true;
+}
+
+constexpr int kBwdMaxDim = JF_MAX_DIM;
+
+template <typename T>
+__global__ void __launch_bounds__(128) gf_chain_backward_kernel(const __grid_constant__ GfBwdArgs<T> g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* slots = reinterpret_cast<T*>(smem_raw);
+    const SubPdfArgs<T>& a = g.a;
+    const int d = a.d, L = a.n_layers;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.B) return;
+    const T* prow = a.params + row * a.sr;
+    T* grow = g.grad_params + row * a.sr;
+    const int64_t sj = a.sj;
+    T x[kBwdMaxDim];
+    T vs[JF_MAX_LAYERS * kBwdMaxDim];                 // pre-stage vectors of every layer (local memory)
+    for (int j = 0; j < d; ++j) x[j] = a.in[row * a.ld_in + j];
+    // ---- forward, recomputed ----
+    for (int l = L - 1; l >= 0; --l) {
+        const GfLayerC<T>& c = g.layers[l];
+        if (c.has_offset)
+            for (int j = 0; j < d; ++j) x[j] -= prow[(int64_t)(c.raw_off + j) * sj];
+        if (c.hh_iter > 0)
+            householder_apply<T, kBwdMaxDim>(x, d, c.hh_iter, true, false, nullptr, prow + (int64_t)c.raw_hh() * sj, sj);
+        for (int j = 0; j < d; ++j) {
+            vs[l * kBwdMaxDim + j] = x[j];
+            const MixView<T> mv = regulate_to_slots<T>(c, c.K, j, prow, sj, slots);
+            T y, logd;
+            gf_eval_logpdf<T>(mv, c.inv_type, x[j], y, logd);
+            x[j] = y;
+        }
+    }
+    // ---- backward ----
+    const T gr = g.grad_logp ? g.grad_logp[row] : T(1);
+    T xb[kBwdMaxDim];
+    for (int j = 0; j < d; ++j) xb[j] = -x[j] * gr;   // d/dz of sum_j log N(z_j)
+    int n_bad = 0;
+    for (int l = 0; l < L; ++l) {
+        const GfLayerC<T>& c = g.layers[l];
+        T v[kBwdMaxDim];
+        for (int j = 0; j < d; ++j) {
+            v[j] = vs[l * kBwdMaxDim + j];
+            const T G = bwd_regulate<T>(c, c.K, j, prow, sj, slots);
+            T vbar;
+            if (!gf_elem_backward<T>(c, c.K, j, v[j], xb[j], gr, G, slots, grow, sj, vbar)) {
+                ++n_bad;
+                for (int k = 0; k < c.K; ++k) {       // no stage gradient for rows in the Pade tails
+                    grow[(int64_t)(c.raw_m() + k * d + j) * sj] = T(0);
+                    grow[(int64_t)(c.raw_w() + k * d + j) * sj] = T(0);
+                    if (c.norm_mode != JF_NORM_NONE) grow[(int64_t)(c.raw_n() + k * d + j) * sj] = T(0);
+                }
+            }
+            xb[j] = vbar;
+        }
+        // rotation v = H_{n-1} ... H_0 u : go back reflection by reflection (each one is its own inverse)
+        for (int i = c.hh_iter - 1; i >= 0; --i) {
+            const T* pv = prow + (int64_t)(c.raw_hh() + i * d) * sj;
+            T* gv = grow + (int64_t)(c.raw_hh() + i * d) * sj;
+            T s = 0, aa = 0, bb = 0;
+            for (int j = 0; j < d; ++j) {
+                const T w = pv[(int64_t)j * sj];
+                s = fma(w, w, s);
+                aa = fma(w, v[j], aa);                // v . x_out  ( = -(v . x_in) )
+                bb = fma(w, xb[j], bb);
+            }
+            const T is = T(1) / s;
+            const T ain = -aa;                        // v . x_in, since x_in = x_out - 2 (v.x_out)/s v
+            for (int j = 0; j < d; ++j) {
+                const T w = pv[(int64_t)j * sj];
+                const T xin = v[j] - T(2) * aa * is * w;
+                gv[(int64_t)j * sj] = -T(2) * is * (bb * xin + ain * xb[j]) + T(4) * ain * bb * is * is * w;
+                xb[j] -= T(2) * bb * is * w;
+                v[j] = xin;
+            }
+        }
+        if (c.has_offset)
+            for (int j = 0; j < d; ++j) grow[(int64_t)(c.raw_off + j) * sj] = -xb[j];
+    }
+    if (n_bad) status_add(a.status, JF_STATUS_OUT_OF_RANGE, n_bad);
+}
+
+}  // namespace jf

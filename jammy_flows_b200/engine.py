@@ -346,3 +346,87 @@ def s2_embedding(x):
                                  _stream_ptr(dev))
     _cabi.check(rc, "jf_subpdf_apply(embedding)")
     return emb
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training path (BASELINE configs[4]): differentiable log_pdf for conditional pdfs made of Euclidean "g" sub-pdfs.
+# The layer chain runs in the fused kernels in both directions (jf_subpdf_apply / jf_subpdf_backward); the parameter
+# generator stays a torch module so that its backward is torch's own (plain library GEMMs, cuBLAS).  Its last Linear is
+# evaluated transposed ([P, B] = W2 h^T + b2), which IS the param-major layout the layer kernels read coalesced.
+# ---------------------------------------------------------------------------------------------------------------------
+def supports_backward(pdf):
+    """True when every sub-pdf is Euclidean, made of "g" layers with a stage the backward kernel covers, and gets its
+    parameters from an MLP (conditional pdf)."""
+    if pdf.conditional_input_dim is None:
+        return False
+    for k, layers in enumerate(pdf.layer_list):
+        if pdf.pdf_defs_list[k][0] != "e" or pdf.mlp_predictors[k] is None:
+            return False
+        for l in layers:
+            if getattr(l, "code", "") != "g" or l.inverse_function_type not in ("isigmoid", "inormal_partly_precise"):
+                return False
+    return True
+
+
+class _SubPdfLogPdf(torch.autograd.Function):
+    """log p_k(x_k | params) = log N(base) + logdet of one Euclidean sub-pdf; differentiable w.r.t. the per-row params."""
+
+    @staticmethod
+    def forward(ctx, params_t, x_k, sub_desc, status):
+        lib = _cabi.load()
+        B, d = x_k.shape
+        dt, dev = x_k.dtype, x_k.device
+        base = torch.empty(B, d, dtype=dt, device=dev)
+        logdet = torch.empty(B, dtype=dt, device=dev)
+        logbase = torch.empty(B, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.jf_subpdf_apply(C.byref(sub_desc), _DT[dt], _cabi.JF_DIR_LOGPDF, _ptr(x_k), x_k.stride(0),
+                                     _ptr(params_t), params_t.stride(0), 1, None, _ptr(logdet), None, _ptr(logbase),
+                                     _ptr(base), d, None, 0, B, _ptr(status), _stream_ptr(dev))
+        _cabi.check(rc, "jf_subpdf_apply")
+        ctx.save_for_backward(params_t, x_k)
+        ctx.sub_desc, ctx.status = sub_desc, status
+        ctx.mark_non_differentiable(base, logbase)
+        return logdet + logbase, logbase, base
+
+    @staticmethod
+    def backward(ctx, g_logp, g_logbase, g_base):
+        lib = _cabi.load()
+        params_t, x_k = ctx.saved_tensors
+        B = x_k.shape[0]
+        dt, dev = x_k.dtype, x_k.device
+        grad = torch.empty_like(params_t)
+        g = g_logp.contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.jf_subpdf_backward(C.byref(ctx.sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
+                                        params_t.stride(0), 1, _ptr(g), _ptr(grad), B, _ptr(ctx.status), _stream_ptr(dev))
+        _cabi.check(rc, "jf_subpdf_backward")
+        return grad, None, None, None
+
+
+def pdf_logpdf_trainable(pdf, x, cond):
+    """-> (log_pdf [B] with autograd history, log_pdf_base [B], base [B, D]).  Reference: main/default.py:1059-1117 with
+    `torch.is_grad_enabled()`; the conditioning on earlier sub-pdfs uses the data x (no gradient flows through it)."""
+    x, cond = _prep_inputs(pdf, x, cond, "x")
+    dt, dev = x.dtype, x.device
+    desc = pdf._desc(dt)
+    status = pdf._status(dev)
+    logp, logp_base, bases = None, None, []
+    prev = []
+    for k, layers in enumerate(pdf.layer_list):
+        mlp = pdf.mlp_predictors[k]
+        t0, t1 = pdf.target_dim_indices[k]
+        x_k = x[:, t0:t1]
+        inp = torch.cat([cond] + prev, dim=1) if len(prev) > 0 else cond
+        h = inp
+        mods = list(mlp)
+        for m in mods[:-1]:
+            h = m(h)
+        last = mods[-1]
+        params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())        # [P, B], param-major
+        lp_k, lb_k, base_k = _SubPdfLogPdf.apply(params_t, x_k, desc.sub[k], status)
+        logp = lp_k if logp is None else logp + lp_k
+        logp_base = lb_k if logp_base is None else logp_base + lb_k
+        bases.append(base_k)
+        prev.append(x_k)
+    return logp, logp_base, torch.cat(bases, dim=1)

@@ -35,8 +35,9 @@ class _NoBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(
-            "jammy_flows_b200: the backward kernels (SURVEY.md K8, training config cfg5) are not built yet; "
-            "log_pdf/sample outputs are inference-only in this round.")
+            "jammy_flows_b200: backward kernels exist for conditional pdfs made of Euclidean 'g' sub-pdfs (isigmoid / "
+            "inormal_partly_precise stages, SURVEY.md K8 / cfg5); this pdf contains other layers or permanent "
+            "parameters, whose outputs are inference-only in this round.")
 
 
 class pdf(nn.Module):
@@ -388,8 +389,12 @@ class pdf(nn.Module):
         else:
             assert self.conditional_input_dim is None, "conditional pdf requires conditional_input"
         assert (x.shape[1] == self.total_target_dim), (x.shape[1], self.total_target_dim)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad and engine.supports_backward(self):
+            # training path: fused forward AND backward layer kernels, torch autograd only for the parameter generator
+            return engine.pdf_logpdf_trainable(self, x, conditional_input)
         log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if needs_grad:
             log_pdf, log_pdf_base, base_pos = _NoBackward.apply(self._anchor(), log_pdf, log_pdf_base, base_pos)
         return log_pdf, log_pdf_base, base_pos
 

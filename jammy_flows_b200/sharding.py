@@ -49,3 +49,22 @@ def max_over_ranks(value, device="cpu", group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def allreduce_gradients(module, group=None, average=True):
+    """Data-parallel training step: ONE all-reduce over a flat bucket of every parameter gradient
+    (cfg5: 422 410 fp32 values = 1.7 MB, latency bound on NVLink/NVSwitch), then scatter back.  NCCL for GPU tensors,
+    gloo for CPU tensors (tests)."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if len(grads) == 0:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel()

@@ -124,6 +124,10 @@ CASES = {
     "s2_vv_rot": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0, opts={"v": {"add_rotation": 1, "num_components": 4}}),
     "s2_v_natural": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"natural_direction": 1}}),
     "cfg4_e6s2_gv_small": dict(pdf_defs="e6+s2", flow_defs="gggggg+v", n=300, cond_dim=64, perturb=0.02),
+    # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
+    "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
+    "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
+    "train_e2e2_cond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=200, cond_dim=2, perturb=0.2, grads=True),
 }
 
 
@@ -169,6 +173,13 @@ def build_case(jf, name, spec):
         out["cond"] = cond.numpy()
     for k, v in pdf.state_dict().items():
         out["param/" + k] = v.numpy()
+    if spec.get("grads", False):
+        # reference autograd: d mean(log_pdf) / d (every parameter)
+        pdf.zero_grad()
+        lp, _, _ = pdf(x, conditional_input=cond)
+        lp.mean().backward()
+        for k, p_ in pdf.named_parameters():
+            out["grad/" + k] = p_.grad.detach().numpy()
     return out
 
 

@@ -21,7 +21,7 @@ def load_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = json.loads(str(g["meta"]))
     params = {k[6:]: g[k] for k in g.files if k.startswith("param/")}
-    data = {k: g[k] for k in g.files if not k.startswith("param/") and k != "meta"}
+    data = {k: g[k] for k in g.files if not k.startswith("param/") and k != "meta"}   # includes "grad/<name>" entries
     return meta, params, data
 
 
