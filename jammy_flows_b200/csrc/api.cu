@@ -345,7 +345,7 @@ static int64_t i8_ws_bytes(int N, int dtype) {
     const int64_t a = i8_prep_bytes<kI8NSF32, 32>(N), b = i8_prep_bytes<kI8NSF32, 64>(N);
     return a > b ? a : b;
 }
-template <typename T, int NS, int TN>
+template <typename T, int NS, int TN, int KR>
 static int launch_mlp2_i8_tn(const MlpArgs<T>& m, void* ws, int prepared, cudaStream_t st) {
     using Cfg = I8Cfg<NS, TN>;
     const int N = m.dims[2], n_tiles = (N + TN - 1) / TN;
@@ -362,20 +362,22 @@ static int launch_mlp2_i8_tn(const MlpArgs<T>& m, void* ws, int prepared, cudaSt
     while (n_slots > NS && Cfg::smem_bytes(m.dims[0], n_slots, (int)sizeof(T)) > smem_max) --n_slots;
     if (n_slots < NS + 1) return JF_ERR_UNSUPPORTED;
     const int smem = Cfg::smem_bytes(m.dims[0], n_slots, (int)sizeof(T));
-    JF_CUDA_OK(cudaFuncSetAttribute(mlp2_i8_kernel<T, NS, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    JF_CUDA_OK(cudaFuncSetAttribute(mlp2_i8_kernel<T, NS, TN, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t blocks = (m.B + kI8Rows - 1) / kI8Rows;
     const unsigned grid = (unsigned)(blocks < sms ? blocks : sms);     // persistent: one CTA per SM
     static const int dbg = [] { const char* e = getenv("JF_I8_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
-    mlp2_i8_kernel<T, NS, TN><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots, dbg);
+    mlp2_i8_kernel<T, NS, TN, KR><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots, dbg);
     return check_launch();
 }
 static int launch_mlp2_i8(const MlpArgs<double>& m, void* ws, int prepared, cudaStream_t st) {
-    return i8_tn() == 64 ? launch_mlp2_i8_tn<double, kI8NS, 64>(m, ws, prepared, st)
-                         : launch_mlp2_i8_tn<double, kI8NS, 32>(m, ws, prepared, st);
+    if (i8_tn() == 32) return launch_mlp2_i8_tn<double, kI8NS, 32, 16>(m, ws, prepared, st);
+    // <= 8 inputs (cfg2: 4 and 7): half the input registers, 17 % less prologue time (register pressure at 128 regs/thread)
+    return m.dims[0] <= 8 ? launch_mlp2_i8_tn<double, kI8NS, 64, 8>(m, ws, prepared, st)
+                          : launch_mlp2_i8_tn<double, kI8NS, 64, 16>(m, ws, prepared, st);
 }
 static int launch_mlp2_i8(const MlpArgs<float>& m, void* ws, int prepared, cudaStream_t st) {
-    return i8_tn() == 64 ? launch_mlp2_i8_tn<float, kI8NSF32, 64>(m, ws, prepared, st)
-                         : launch_mlp2_i8_tn<float, kI8NSF32, 32>(m, ws, prepared, st);
+    return i8_tn() == 64 ? launch_mlp2_i8_tn<float, kI8NSF32, 64, 1>(m, ws, prepared, st)
+                         : launch_mlp2_i8_tn<float, kI8NSF32, 32, 1>(m, ws, prepared, st);
 }
 
 template <typename T>

@@ -32,7 +32,7 @@ constexpr int kI8Rows = 128;      // rows per CTA = UMMA M
 constexpr int kI8H = 128;         // hidden width = K (bytes per slice row)
 constexpr int kI8Threads = 512;    // 16 warps: 0 MMA issue, 1 W2 producer, 2 TMEM alloc, 4-15 epilogue; all 16 in the prologue
 constexpr int kI8EpiWarps = 12;
-constexpr int kI8MaxKin = 16;     // fp64: inputs of a row live in registers
+constexpr int kI8MaxKin = 16;     // fp64: inputs of a row live in registers (kernel instantiated for 8 and 16: -17 % prologue time at 8)
 constexpr int kI8MaxKinF32 = 96;  // fp32: inputs are streamed from shared memory
 constexpr int kI8MaxSlots = 12;   // ring of W2-slice buffers (as many as fit next to the A slices, >= NS + 1)
 
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const T* __restrict__ 
 // (free-running MMA 0.53 ms + free-running LDTM 0.40 ms = 0.98 ms together, profiles/), so a double-buffered or
 // level-major accumulator scheme only adds hand-shakes.  What does overlap with the next tile's MMAs is the fp64
 // scale/bias and the global stores, which run after TMEM has been handed back.
-template <typename T, int NS, int TN>
+template <typename T, int NS, int TN, int KR>
 __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_constant__ MlpArgs<T> m,
                                                                  const unsigned char* __restrict__ wsB, int n_slots,
                                                                  int dbg) {
@@ -293,10 +293,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
         // ---- prologue: layer 1 + tanh + digits -> A slices ----
         if (!(dbg & 8)) {
             const int r = (warp & 3) * 32 + lane, quarter = warp >> 2;    // thread = (row, quarter of the hidden units)
-            T in[kI8MaxKin];                                               // fp64 path only (Kin <= 16)
+            T in[KR];                                                      // fp64 path only (Kin <= KR <= 16)
             if (sizeof(T) == 8) {
 #pragma unroll
-                for (int i = 0; i < kI8MaxKin; ++i) in[i] = (i < Kin) ? sIn[r * ldin + i] : T(0);
+                for (int i = 0; i < KR; ++i) in[i] = (i < Kin) ? sIn[r * ldin + i] : T(0);
             }
             const uint32_t a_row = sbase + Cfg::offA + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll 1
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
                             const int u = chunk * 16 + gq * 4 + uu;
                             T z = sB1[u];
 #pragma unroll
-                            for (int i = 0; i < kI8MaxKin; ++i)
+                            for (int i = 0; i < KR; ++i)
                                 if (i < Kin) z = fma(in[i], sW1[i * kI8H + u], z);
                             dg[uu] = to_digits<NS>(tanh_abs(z));
                         }
