@@ -63,6 +63,13 @@ extern "C" {
 #define JF_LAYER_S1SPLINE 4 /* "o" spline_1d on the circle */
 #define JF_LAYER_MOEBIUS 5  /* "m" moebius on the circle */
 #define JF_LAYER_EXPMAP 6   /* "v" exponential_map_s2 (exponential potential) */
+#define JF_LAYER_MVN 7      /* "t" mvn_block: affine layer with a lower-triangular matrix; cov_type in inv_type */
+
+/* covariance type of "t" (layers/euclidean/multivariate_normal.py:56), stored in JfLayerDesc.inv_type */
+#define JF_COV_IDENTITY 0
+#define JF_COV_DIAGONAL_SYMMETRIC 1
+#define JF_COV_DIAGONAL 2
+#define JF_COV_FULL 3
 
 /* spline variants (layers/spline_fns.py:45-186 / :361-559 / :561-760) */
 #define JF_SPLINE_PLAIN 0
@@ -124,7 +131,7 @@ typedef struct JfLayerDesc {
     int32_t param_offset; /* start of that slice (layers are stored in flow order, main/default.py:1488) */
     int32_t K;            /* g: num_kde */
     int32_t hh_iter;      /* number of Householder reflections (g: in R^d; f: in R^3); 0 = no rotation */
-    int32_t inv_type;     /* g: JF_INV_* */
+    int32_t inv_type;     /* g: JF_INV_* ; t: JF_COV_* */
     int32_t norm_mode;    /* g: JF_NORM_* */
     int32_t has_offset;   /* g: model_offset (euclidean_base.py:34-75); offset params come first in the slice */
     int32_t first;        /* s1/s2/interval: layer also applies the base chart of the sub-pdf (sphere_base.py:637-648,

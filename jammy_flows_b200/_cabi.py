@@ -23,7 +23,8 @@ JF_MAX_NESTED = 4
 JF_MAX_BINS = 32
 JF_F32, JF_F64 = 0, 1
 JF_DIR_LOGPDF, JF_DIR_SAMPLE = 0, 1
-JF_LAYER_GF, JF_LAYER_FVM, JF_LAYER_RQS, JF_LAYER_S1SPLINE, JF_LAYER_MOEBIUS, JF_LAYER_EXPMAP = 1, 2, 3, 4, 5, 6
+JF_LAYER_GF, JF_LAYER_FVM, JF_LAYER_RQS, JF_LAYER_S1SPLINE, JF_LAYER_MOEBIUS, JF_LAYER_EXPMAP, JF_LAYER_MVN = 1, 2, 3, 4, 5, 6, 7
+JF_COV_IDENTITY, JF_COV_DIAGONAL_SYMMETRIC, JF_COV_DIAGONAL, JF_COV_FULL = 0, 1, 2, 3
 JF_SPLINE_PLAIN, JF_SPLINE_SMOOTH, JF_SPLINE_CIRCULAR = 0, 1, 2
 JF_BD_PARAMS, JF_BD_FIXED, JF_BD_PERIODIC = 0, 1, 2
 JF_NORM_NONE, JF_NORM_RAW, JF_NORM_REGULATED = 0, 1, 2

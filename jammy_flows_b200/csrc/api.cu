@@ -53,13 +53,25 @@ static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, 
     int tab = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
         const JfLayerDesc& L = desc->layers[l];
-        if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_BAD_DESC;
+        if (L.dim != d) return JF_ERR_BAD_DESC;
+        if (!(L.w_min > 0) || !(L.w_max > 0)) return JF_ERR_BAD_DESC;
+        GfLayerC<T>& c = g.layers[l];
+        if (L.kind == JF_LAYER_MVN) {           // "t": inv_type carries the covariance type
+            if (L.inv_type < JF_COV_IDENTITY || L.inv_type > JF_COV_FULL) return JF_ERR_BAD_DESC;
+            const int ncov = L.inv_type == JF_COV_IDENTITY ? 0 : (L.inv_type == JF_COV_DIAGONAL_SYMMETRIC ? 1
+                             : (L.inv_type == JF_COV_DIAGONAL ? d : d + d * (d - 1) / 2));
+            if ((L.has_offset ? d : 0) + ncov != L.n_params) return JF_ERR_BAD_DESC;
+            c.kind = 1; c.K = 1; c.d = d; c.hh_iter = 0; c.inv_type = L.inv_type; c.norm_mode = JF_NORM_NONE;
+            c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = tab;
+            c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = 0; c.n_max = 0;
+            continue;
+        }
+        if (L.kind != JF_LAYER_GF) return JF_ERR_BAD_DESC;
         if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
         if (L.inv_type < 0 || L.inv_type > 3 || L.norm_mode < 0 || L.norm_mode > 2) return JF_ERR_BAD_DESC;
-        if (!(L.w_min > 0) || !(L.w_max > 0)) return JF_ERR_BAD_DESC;
         const int expect = (L.has_offset ? d : 0) + L.hh_iter * d + (L.norm_mode != JF_NORM_NONE ? 3 : 2) * L.K * d;
         if (expect != L.n_params) return JF_ERR_BAD_DESC;
-        GfLayerC<T>& c = g.layers[l];
+        c.kind = 0;
         c.K = L.K; c.d = d; c.hh_iter = L.hh_iter; c.inv_type = L.inv_type; c.norm_mode = L.norm_mode;
         c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = tab;
         c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = (T)L.n_min; c.n_max = (T)L.n_max;
@@ -260,6 +272,7 @@ static int subpdf_backward_t(const JfSubPdfDesc* desc, const void* x, int64_t ld
         if (expect != L.n_params) return JF_ERR_BAD_DESC;
         GfLayerC<T>& c = g.layers[l];
         c.K = L.K; c.d = d; c.hh_iter = L.hh_iter; c.inv_type = L.inv_type; c.norm_mode = L.norm_mode;
+        c.kind = 0;
         c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = 0;
         c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = (T)L.n_min; c.n_max = (T)L.n_max;
         kmax = L.K > kmax ? L.K : kmax;

@@ -35,6 +35,7 @@ JF_DEVINL float rcp_pos_(float x) { return 1.0f / x; }
 template <typename T>
 struct GfLayerC {
     int K, d, hh_iter, inv_type, norm_mode, has_offset;
+    int kind;      // 0: "g" gf_block, 1: "t" mvn_block (inv_type then holds the cov_type: 0 identity, 1 diagonal_symmetric, 2 diagonal, 3 full)
     int raw_off;   // start of the layer's slice in the raw parameter vector
     int tab_off;   // start of the layer's block in the processed shared-memory table
     T w_min, inv_w_max, n_min, n_max;
@@ -51,7 +52,7 @@ struct GfLayerC {
     __host__ __device__ int tab_n() const { return tab_iw() + K * d; }
     __host__ __device__ int tab_mmin() const { return tab_n() + K * d; }
     __host__ __device__ int tab_mmax() const { return tab_mmin() + d; }
-    __host__ __device__ int tab_size() const { return d + hh_iter * d + 4 * K * d + 2 * d; }
+    __host__ __device__ int tab_size() const { return kind == 1 ? 0 : d + hh_iter * d + 4 * K * d + 2 * d; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -603,6 +604,84 @@ JF_DEVINL void gf_layer_sample(T* x, T& logdet, const GfLayerC<T>& c, int d, int
     if (c.has_offset) {
 #pragma unroll
         for (int j = 0; j < d; ++j) x[j] += processed ? tab[c.tab_off + j] : p[(int64_t)(c.raw_off + j) * sj];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "t": affine layer x = L z + offset with a lower-triangular L (reference layers/euclidean/multivariate_normal.py:228-272,
+// layers/matrix_fns.py:4-145, offset handling euclidean_base.py:34-75).  Raw slice: [offset d][log-diagonal 1 | d][lower
+// entries d(d-1)/2, stored sub-diagonal by sub-diagonal starting at the bottom-left corner].  The diagonal is the same
+// bounded exponential as the "g" widths.  The reference inverts L through cofactors; forward substitution is the same
+// map.  Parameters are read raw in both modes (p with stride sj; shared vectors have sj = 1).
+// ---------------------------------------------------------------------------------------------------------------------
+JF_DEVINL int mvn_lower_index(int d, int i, int j) {      // entry of L[i][j], i > j, inside `lower_triangular_entries`
+    const int ind = d - 1 - (i - j);                        // which sub-diagonal (0 = bottom-left corner, 1 entry)
+    return ind * (ind + 1) / 2 + j;
+}
+
+template <typename T, int DM>
+JF_DEVINL void mvn_layer_logpdf(T* x, T& logdet, const GfLayerC<T>& c, int d, const T* p, int64_t sj) {
+    if (c.has_offset) {
+#pragma unroll
+        for (int j = 0; j < d; ++j) x[j] -= p[(int64_t)(c.raw_off + j) * sj];
+    }
+    const int cov = c.inv_type;
+    if (cov == 0) return;
+    const T* q = p + (int64_t)(c.raw_off + (c.has_offset ? d : 0)) * sj;
+    if (cov == 1) {
+        T w, iw;
+        regulate_width(q[0], c.w_min, c.inv_w_max, w, iw);
+#pragma unroll
+        for (int j = 0; j < d; ++j) x[j] *= iw;
+        logdet -= T(d) * log(w);
+        return;
+    }
+    T ld = 0;
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+        T w, iw;
+        regulate_width(q[(int64_t)i * sj], c.w_min, c.inv_w_max, w, iw);
+        T acc = x[i];
+        if (cov == 3) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) acc = fma(-q[(int64_t)(d + mvn_lower_index(d, i, j)) * sj], x[j], acc);
+        }
+        x[i] = acc * iw;
+        ld += log(w);
+    }
+    logdet -= ld;
+}
+
+template <typename T, int DM>
+JF_DEVINL void mvn_layer_sample(T* x, T& logdet, const GfLayerC<T>& c, int d, const T* p, int64_t sj) {
+    const int cov = c.inv_type;
+    const T* q = p + (int64_t)(c.raw_off + (c.has_offset ? d : 0)) * sj;
+    if (cov == 1) {
+        T w, iw;
+        regulate_width(q[0], c.w_min, c.inv_w_max, w, iw);
+#pragma unroll
+        for (int j = 0; j < d; ++j) x[j] *= w;
+        logdet += T(d) * log(w);
+    } else if (cov >= 2) {
+        T ld = 0;
+#pragma unroll
+        for (int ii = 0; ii < d; ++ii) {                    // bottom row first: x[i] only needs the old x[j], j <= i
+            const int i = d - 1 - ii;
+            T w, iw;
+            regulate_width(q[(int64_t)i * sj], c.w_min, c.inv_w_max, w, iw);
+            T acc = x[i] * w;
+            if (cov == 3) {
+#pragma unroll
+                for (int j = 0; j < i; ++j) acc = fma(q[(int64_t)(d + mvn_lower_index(d, i, j)) * sj], x[j], acc);
+            }
+            x[i] = acc;
+            ld += log(w);
+        }
+        logdet += ld;
+    }
+    if (c.has_offset) {
+#pragma unroll
+        for (int j = 0; j < d; ++j) x[j] += p[(int64_t)(c.raw_off + j) * sj];
     }
 }
 

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant_
 
     if (shared_params) {
         // permanent parameters: regulate once per CTA into shared memory (broadcast reads afterwards)
-        for (int l = 0; l < a.n_layers; ++l) gf_build_table<T>(g.layers[l], a.params, tab, threadIdx.x, blockDim.x);
+        for (int l = 0; l < a.n_layers; ++l)
+            if (g.layers[l].kind == 0) gf_build_table<T>(g.layers[l], a.params, tab, threadIdx.x, blockDim.x);
         __syncthreads();
     }
 
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant_
             for (int j = 0; j < d; ++j) a.emb_out[row * a.ld_emb + j] = x[j];
         }
         for (int l = a.n_layers - 1; l >= 0; --l) {
-            gf_layer_logpdf<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots);
+            if (g.layers[l].kind == 1) mvn_layer_logpdf<T, DM>(x, logdet, g.layers[l], d, prow, a.sj);
+            else gf_layer_logpdf<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots);
         }
 #pragma unroll
         for (int j = 0; j < d; ++j) zsq = fma(x[j], x[j], zsq);
@@ -58,8 +60,9 @@ __global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant_
         for (int j = 0; j < d; ++j) zsq = fma(x[j], x[j], zsq);
         int n_evals = 0, n_unconv = 0;
         for (int l = 0; l < a.n_layers; ++l) {
-            gf_layer_sample<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots, n_evals,
-                                   n_unconv);
+            if (g.layers[l].kind == 1) mvn_layer_sample<T, DM>(x, logdet, g.layers[l], d, prow, a.sj);
+            else gf_layer_sample<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots,
+                                        n_evals, n_unconv);
         }
         if (a.emb_out) {
 #pragma unroll

@@ -57,6 +57,11 @@ def fill_layer_desc(ld, desc, param_offset):
                         (_cabi.JF_NORM_REGULATED if desc["regulate_normalization"] else _cabi.JF_NORM_RAW))
         ld.has_offset = desc["model_offset"]
         ld.w_min, ld.w_max, ld.n_min, ld.n_max = desc["w_min"], desc["w_max"], desc["n_min"], desc["n_max"]
+    elif desc["code"] == "t":
+        ld.kind = _cabi.JF_LAYER_MVN
+        ld.inv_type = desc["cov"]
+        ld.has_offset = desc["model_offset"]
+        ld.w_min, ld.w_max = desc["w_min"], desc["w_max"]
     elif desc["code"] == "f":
         ld.kind = _cabi.JF_LAYER_FVM
         ld.hh_iter = desc["hh_iter"] if desc["add_rotation"] else 0

@@ -37,6 +37,17 @@ opts_dict["g"] = dict(module=layers.gf_block, type="e", kwargs=dict(
     nonlinear_stretch_type=("classic", ["classic", "rq_splines"]),
 ))
 
+# --- Euclidean: affine / multivariate-normal layer (reference flow_options.py:76-86) ------------------------------
+opts_dict["t"] = dict(module=layers.mvn_block, type="e", kwargs=dict(
+    skip_model_offset=(0, [0, 1]),
+    softplus_for_width=(0, [0, 1]),
+    upper_bound_for_widths=(100, lambda x: (x == -1) or x > 0),
+    lower_bound_for_widths=(0.01, lambda x: x > 0),
+    clamp_widths=(0, [0, 1]),
+    width_smooth_saturation=(1, [0, 1]),
+    cov_type=("diagonal", ["identity", "diagonal_symmetric", "diagonal", "full"]),
+))
+
 # --- S2: Fisher-von-Mises scaling (+ optional spline sub-flows) (reference flow_options.py:154-180) --------------
 opts_dict["f"] = dict(module=layers.fisher_von_mises_2d, type="s", kwargs=dict(
     add_vertical_rq_spline_flow=(0, [0, 1]),
@@ -121,7 +132,6 @@ OUT_OF_SCOPE = {
 }
 # Codes on the SURVEY.md section 8 'next' list that are not built yet in this round.
 NOT_YET_BUILT = {
-    "t": "affine/MVN layer (SURVEY.md section 8f rank 1)",
     "x": "Euclidean identity layer", "y": "spherical identity layer", "z": "interval identity layer",
 }
 

@@ -217,6 +217,110 @@ class gf_block(layer_base):
 
 
 # =====================================================================================================================
+# Euclidean: affine layer "t"
+# =====================================================================================================================
+COV_TYPES = {"identity": 0, "diagonal_symmetric": 1, "diagonal": 2, "full": 3}
+
+
+class mvn_block(layer_base):
+    """Affine flow (multivariate normal), symbol "t".
+
+    Reference: layers/euclidean/multivariate_normal.py:48-190 (constructor / parameters), layers/matrix_fns.py:4-145
+    (lower-triangular matrix), layers/euclidean/euclidean_base.py:9-31 (offset).  Parameter slice:
+    [offset d (last layer only)] [log-diagonal: 1 | d] [lower-triangular entries d(d-1)/2, cov_type="full" only]."""
+
+    code = "t"
+    manifold = "e"
+
+    def __init__(self, dimension, cov_type="full", use_permanent_parameters=False, model_offset=0,
+                 width_smooth_saturation=1, lower_bound_for_widths=0.01, upper_bound_for_widths=100,
+                 softplus_for_width=0, clamp_widths=0):
+        super().__init__(dimension=dimension)
+        if softplus_for_width or clamp_widths or not width_smooth_saturation or upper_bound_for_widths <= 0:
+            raise NotImplementedError("'t' layer with a non-default width regulator has no sm_100a kernel "
+                                      "(SURVEY.md section 8f rank 1) -- there is no CPU fallback")
+        assert cov_type in COV_TYPES, cov_type
+        assert lower_bound_for_widths > 0.0
+        self.use_permanent_parameters = use_permanent_parameters
+        self.model_offset = model_offset
+        self.cov_type = cov_type
+        self.width_min, self.width_max = lower_bound_for_widths, upper_bound_for_widths
+        # RNG call order as in the reference: offsets (euclidean_base), then the covariance parameters
+        self.offsets = None
+        if self.model_offset:
+            self.offsets = torch.zeros(dimension).type(torch.double).unsqueeze(0)
+            if use_permanent_parameters:
+                self.offsets = nn.Parameter(torch.randn(dimension).type(torch.double).unsqueeze(0))
+            self.total_param_num += dimension
+        n_low = int(dimension * (dimension - 1) / 2)
+        if cov_type == "diagonal_symmetric":
+            if use_permanent_parameters:
+                self.single_diagonal_log = nn.Parameter(torch.randn(1, 1).type(torch.double))
+            self.total_param_num += 1
+        elif cov_type == "diagonal":
+            if use_permanent_parameters:
+                self.full_diagonal_log = nn.Parameter(torch.randn(1, dimension).type(torch.double))
+            self.total_param_num += dimension
+        elif cov_type == "full":
+            if use_permanent_parameters:
+                self.full_diagonal_log = nn.Parameter(torch.randn(1, dimension).type(torch.double))
+                self.lower_triangular_entries = nn.Parameter(torch.randn(1, n_low).type(torch.double))
+            self.total_param_num += dimension + n_low
+
+    def _n_cov(self):
+        return self.total_param_num - (self.dimension if self.model_offset else 0)
+
+    def get_desired_init_parameters(self):
+        par_list = []
+        if self.model_offset:
+            par_list.append(torch.ones(self.dimension) * 0.001)
+        par_list.append(torch.zeros(self._n_cov()))
+        return torch.cat(par_list)
+
+    def init_params(self, params):
+        assert (len(params) == self.total_param_num), (len(params), self.total_param_num)
+        assert (self.use_permanent_parameters == 1)
+        d = self.dimension
+        if self.model_offset:
+            self.offsets.data = params[:d]
+            params = params[d:]
+        if self.cov_type == "diagonal_symmetric":
+            self.single_diagonal_log.data = torch.reshape(params[:1], [1, 1])
+        elif self.cov_type == "diagonal":
+            self.full_diagonal_log.data = torch.reshape(params[:d], [1, d])
+        elif self.cov_type == "full":
+            self.full_diagonal_log.data = torch.reshape(params[:d], [1, d])
+            self.lower_triangular_entries.data = torch.reshape(params[d:], [1, int(d * (d - 1) / 2)])
+
+    def permanent_param_names(self):
+        names = ["offsets"] if self.model_offset else []
+        if self.cov_type == "diagonal_symmetric":
+            names.append("single_diagonal_log")
+        elif self.cov_type == "diagonal":
+            names.append("full_diagonal_log")
+        elif self.cov_type == "full":
+            names += ["full_diagonal_log", "lower_triangular_entries"]
+        return names
+
+    def descriptor(self):
+        return dict(code="t", dim=self.dimension, cov_type=self.cov_type, cov=COV_TYPES[self.cov_type],
+                    model_offset=int(self.model_offset), w_min=float(self.width_min), w_max=float(self.width_max),
+                    n_params=self.total_param_num)
+
+    def _embedding_conditional_return(self, x):
+        return x
+
+    def _embedding_conditional_return_num(self):
+        return self.dimension
+
+    def _get_layer_base_dimension(self):
+        return self.dimension
+
+    def transform_target_space(self, x, log_det=0.0, transform_from="default", transform_to="embedding"):
+        return x, log_det
+
+
+# =====================================================================================================================
 # S2: Fisher-von-Mises layer "f" (reference defaults: Householder rotation + vMF z-scaling)
 # =====================================================================================================================
 class fisher_von_mises_2d(layer_base):

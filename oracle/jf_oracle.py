@@ -228,6 +228,76 @@ class GfLayer:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Affine layer "t"
+# ---------------------------------------------------------------------------------------------------------------------
+class MvnLayer:
+    """mvn_block.  `spec` keys: dim, cov_type, model_offset, w_min, w_max.
+    Reference: layers/euclidean/multivariate_normal.py:191-272, layers/matrix_fns.py:4-145, euclidean_base.py:34-75."""
+
+    def __init__(self, spec):
+        self.s = spec
+        self.d = spec["dim"]
+
+    def _lower(self, log_diag, low):
+        """Lower-triangular matrix: exp(log_diag) on the diagonal, `low` filled sub-diagonal by sub-diagonal starting at
+        the bottom-left corner (matrix_fns.py:27-44)."""
+        d = self.d
+        m = torch.diag_embed(torch.exp(log_diag))
+        pos = 0
+        for ind in range(d - 1):
+            n = ind + 1
+            m = m + torch.diag_embed(low[:, pos:pos + n], offset=-(d - 1 - ind))
+            pos += n
+        return m
+
+    def _split(self, p):
+        s, d = self.s, self.d
+        off = None
+        if s["model_offset"]:
+            off, p = p[:, :d], p[:, d:]
+        return off, p
+
+    def inverse(self, x, log_det, p):
+        off, p = self._split(p)
+        if off is not None:
+            x = x - off
+        ct = self.s["cov_type"]
+        if ct == "identity":
+            return x, log_det
+        if ct == "diagonal_symmetric":
+            lw = _bounded_log_fn(p, self.s["w_min"], self.s["w_max"], center=True)
+            return torch.exp(-lw) * x, log_det - self.d * lw.sum(dim=-1)
+        lw = _bounded_log_fn(p[:, :self.d], self.s["w_min"], self.s["w_max"], center=True)
+        if ct == "diagonal":
+            return torch.exp(-lw) * x, log_det - lw.sum(dim=-1)
+        m = self._lower(lw, p[:, self.d:]).expand(x.shape[0], -1, -1)
+        z = torch.linalg.solve_triangular(m, x.unsqueeze(-1), upper=False).squeeze(-1)
+        return z, log_det - lw.sum(dim=-1)
+
+    def forward(self, z, log_det, p):
+        off, p = self._split(p)
+        ct = self.s["cov_type"]
+        if ct == "identity":
+            x = z
+        elif ct == "diagonal_symmetric":
+            lw = _bounded_log_fn(p, self.s["w_min"], self.s["w_max"], center=True)
+            x, log_det = torch.exp(lw) * z, log_det + self.d * lw.sum(dim=-1)
+        else:
+            lw = _bounded_log_fn(p[:, :self.d], self.s["w_min"], self.s["w_max"], center=True)
+            if ct == "diagonal":
+                x = torch.exp(lw) * z
+            else:
+                x = torch.einsum("bij,bj->bi", self._lower(lw, p[:, self.d:]).expand(z.shape[0], -1, -1), z)
+            log_det = log_det + lw.sum(dim=-1)
+        if off is not None:
+            x = x + off
+        return x, log_det
+
+    def embedding(self, x):
+        return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Rational-quadratic splines (shared by "r", "o" and the sub-flows of "f")
 # ---------------------------------------------------------------------------------------------------------------------
 def _softplus(t):
@@ -865,7 +935,7 @@ class VLayer:
         return s2_to_embedding(x, torch.zeros(x.shape[0], dtype=x.dtype))[0]
 
 
-LAYER_TYPES = {"v": VLayer, "g": GfLayer, "f": FvmLayer, "r": RLayer, "o": OLayer, "m": MLayer}
+LAYER_TYPES = {"t": MvnLayer, "v": VLayer, "g": GfLayer, "f": FvmLayer, "r": RLayer, "o": OLayer, "m": MLayer}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

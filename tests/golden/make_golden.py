@@ -124,6 +124,11 @@ CASES = {
     "s2_vv_rot": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0, opts={"v": {"add_rotation": 1, "num_components": 4}}),
     "s2_v_natural": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"natural_direction": 1}}),
     "cfg4_e6s2_gv_small": dict(pdf_defs="e6+s2", flow_defs="gggggg+v", n=300, cond_dim=64, perturb=0.02),
+    # "t": affine layer (the docs' recommended Euclidean recipe is "g...gt" with cov_type="full", suggested_settings.rst:14-41)
+    "t_e3_ggt_full": dict(pdf_defs="e3", flow_defs="ggt", n=500, tails=True, perturb=0.3, opts={"t": {"cov_type": "full"}}),
+    "t_e4_gt_cond_diag": dict(pdf_defs="e4", flow_defs="gt", n=500, cond_dim=2, perturb=0.2),
+    "t_e2e3_sym_identity": dict(pdf_defs="e2+e3", flow_defs="t+gt", n=500, perturb=0.3,
+                                opts={0: {"t": {"cov_type": "diagonal_symmetric"}}, 1: {"t": {"cov_type": "identity"}}}),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),

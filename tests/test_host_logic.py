@@ -70,7 +70,7 @@ def test_unsupported_fails_loudly():
     with pytest.raises(NotImplementedError):
         jfb.pdf("e2", "gc")          # out of scope layer code
     with pytest.raises(NotImplementedError):
-        jfb.pdf("e2", "gt")          # not built yet: must not fall back to anything
+        jfb.pdf("e2", "gx")          # not built yet: must not fall back to anything
     with pytest.raises(NotImplementedError):
         jfb.pdf("s2", "v", options_overwrite={"v": {"exp_map_type": "splines"}})
     with pytest.raises(Exception):
