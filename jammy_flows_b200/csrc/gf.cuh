@@ -187,7 +187,8 @@ struct MixVal {
     T E;            // exp(-delta)
 };
 
-template <typename T>
+// NEED_D: also accumulate the derivative of the pdf sum (only the sampling root finder uses it)
+template <typename T, bool NEED_D = true>
 JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
     const int K = mv.K;
     const bool all_neg = x < mv.mmin, all_pos = x > mv.mmax;   // 1/w > 0: sign(a_k) = sign(x - m_k)
@@ -208,18 +209,22 @@ JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
         const T rx = rcp_1to2(T(1) + e);           // exact sigma(|a|)
         const T nr = n * rx, nur = nr * u;
         const T pt = nur * iw * rx;                 // pdf term n sigma(a) sigma(-a) / w
-        // d/dx of the pdf term: pt * (sigma(-a) - sigma(a)) / w = -+ pt * iw * rx * (1 - e)
-        const T dt = pt * iw * (rx - e * rx);
-        if (a >= T(0)) { big_p += nr; small_p += nur; Sd -= dt; }
-        else           { big_n += nr; small_n += nur; Sd += dt; }
+        if (a >= T(0)) { big_p += nr; small_p += nur; }
+        else           { big_n += nr; small_n += nur; }
+        if (NEED_D) {
+            // d/dx of the pdf term: pt * (sigma(-a) - sigma(a)) / w = -+ pt * iw * rx * (1 - e)
+            const T dt = pt * iw * (rx - e * rx);
+            Sd += (a >= T(0)) ? -dt : dt;
+        }
         Sp += pt;
-        // softplus-threshold quirk (a < -20): the reference uses r = 1 instead of rx in the cdf and pdf terms and in
-        // the sf term; q = 1 - rx = e*rx <= 2e-9
-        const T q = (a < T(-20)) ? e * rx : T(0);
-        const T nq = n * q;
-        ex += nq;                                   // sf_ref - sf_exact
-        qc = fma(nq, u, qc);                        // cdf_ref - cdf_exact (rescaled like small_n)
-        Sp = fma(nq * u * iw, T(1) + rx, Sp);       // pdf_ref - pdf_exact
+        // softplus-threshold quirk (a < -20, rare: a kernel more than 20 widths to the right of x): the reference uses
+        // r = 1 instead of rx in the cdf and pdf terms and in the sf term; q = 1 - rx = e*rx <= 2e-9
+        if (a < T(-20)) {
+            const T nq = n * e * rx;
+            ex += nq;                                   // sf_ref - sf_exact
+            qc = fma(nq, u, qc);                        // cdf_ref - cdf_exact (rescaled like small_n)
+            Sp = fma(nq * u * iw, T(1) + rx, Sp);       // pdf_ref - pdf_exact
+        }
     }
     const T Sc = big_p + small_n + qc;
     const T Ss = small_p + big_n;
@@ -293,7 +298,7 @@ JF_DEVINL void inv_stage(int type, const MixVal<T>& v, T& y, T& logd) {
 // one element of the log_pdf direction: y and log dy/dx (kept out of line: one copy per kernel, not one per dimension)
 template <typename T>
 __device__ __noinline__ void gf_eval_logpdf(const MixView<T>& mv, int type, T x, T& y, T& logd) {
-    const MixVal<T> v = mix_eval<T>(mv, x);
+    const MixVal<T> v = mix_eval<T, false>(mv, x);
     inv_stage(type, v, y, logd);
 }
 
