@@ -22,6 +22,8 @@
  * Threading: re-entrant, no global mutable state; all work is enqueued on the caller's `stream` (a cudaStream_t
  * passed as void*).  No entry point synchronises the device except the *_host entries, which synchronise their
  * internal streams before returning.
+ * ABI history: v2 added JfSplineDesc and the spline / S1 / "v" / "t" layer kinds; v3 added the non-default "g" options
+ * (rotation_mode, width_mode, width_clamp, skew, center_mean, stretch, clamp_lo/hi in JfLayerDesc).
  * Errors: return value 0 = ok, <0 = invalid/unsupported descriptor (JF_ERR_*), >0 = CUDA runtime error code.
  * Numerical conditions (non-finite values, unconverged root finds, out-of-range inputs) are counted in the device
  * int64 array `status[JF_STATUS_WORDS]` and are read lazily by the caller (no implicit sync), mirroring the reference's
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define JF_ABI_VERSION 2
+#define JF_ABI_VERSION 3
 
 #define JF_MAX_LAYERS 16
 #define JF_MAX_SUBPDFS 8
@@ -91,6 +93,22 @@ extern "C" {
 #define JF_NORM_RAW 1       /* fit_normalization=1, regulate_normalization=0: log-softmax of the raw values */
 #define JF_NORM_REGULATED 2 /* regulated into [n_min, n_min+n_max] first (gaussianization_flow.py:342) */
 
+/* rotation of "g" (gaussianization_flow.py:141-205, :711-800) */
+#define JF_ROT_HOUSEHOLDER 0 /* hh_iter reflections (default) */
+#define JF_ROT_NONE 1
+#define JF_ROT_ANGLES 2      /* chain of d(d-1)/2 Givens rotations */
+#define JF_ROT_CAYLEY 3      /* d = 2, one parameter */
+#define JF_ROT_TRIANGULAR 4  /* triangular_combination: unit lower x zero-sum diagonal x unit upper, d(d-1)+d-1 parameters */
+
+/* width regulator of "g" (gaussianization_flow.py:264-317) */
+#define JF_WIDTH_SMOOTH 0   /* w = w_min + 1/(1/w_max + exp(-raw))   (width_smooth_saturation=1, default) */
+#define JF_WIDTH_EXP 1      /* w = w_min + exp(raw) */
+#define JF_WIDTH_SOFTPLUS 2 /* w = w_min + softplus(raw) */
+
+/* non-linear stretch of "g" */
+#define JF_STRETCH_CLASSIC 0 /* logistic mixture CDF + inverse-CDF stage */
+#define JF_STRETCH_RQS 1     /* rational-quadratic spline with linear tails (spline_fns.py:188-358) */
+
 /* status words */
 #define JF_STATUS_NONFINITE 0
 #define JF_STATUS_UNCONVERGED 1
@@ -140,11 +158,18 @@ typedef struct JfLayerDesc {
     int32_t max_iter;     /* v: max_num_newton_iter */
     int32_t n_vertical;   /* f: number of nested "r" sub-flows, spline[0 .. n_vertical) */
     int32_t n_circular;   /* f: number of nested "o" sub-flows, spline[n_vertical .. n_vertical+n_circular) */
+    int32_t rotation_mode; /* g: JF_ROT_* (0 = Householder, the default) */
+    int32_t width_mode;    /* g: JF_WIDTH_* */
+    int32_t width_clamp;   /* g: clamp_widths: raw width parameter clamped into [clamp_lo, clamp_hi] first */
+    int32_t skew;          /* g: add_skewness (one more K*d block of log skew exponents at the end of the slice) */
+    int32_t center_mean;   /* g: only K-1 means per dimension are parameters (gaussianization_flow.py:841-848) */
+    int32_t stretch;       /* g: JF_STRETCH_* */
     double w_min, w_max; /* g: width bounds (gaussianization_flow.py:300-317) */
     double n_min, n_max; /* g: norm bounds (gaussianization_flow.py:342) */
     double z_sign;       /* f: z_scaling_factor (+1/-1, fvm_2d.py:96-99) */
     double min_kappa;    /* f: kappa = exp(raw) + min_kappa (fvm_2d.py:123) */
     double lo, hi;       /* r: interval boundaries */
+    double clamp_lo, clamp_hi; /* g: see width_clamp (clamp_hi may be +inf) */
     JfSplineDesc spline[JF_MAX_NESTED]; /* r, o: spline[0]; f: nested sub-flows */
 } JfLayerDesc;
 

@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JF_LIB_PATH") or os.path.join(PKG_DIR, "libjammy_b200.so")
 
 # ---- constants (keep in sync with include/jammy_b200.h; checked by tests/test_cabi_symbols.py) -----------------------
-JF_ABI_VERSION = 2
+JF_ABI_VERSION = 3
 JF_MAX_LAYERS = 16
 JF_MAX_SUBPDFS = 8
 JF_MAX_MLP_LINEAR = 6
@@ -28,6 +28,9 @@ JF_COV_IDENTITY, JF_COV_DIAGONAL_SYMMETRIC, JF_COV_DIAGONAL, JF_COV_FULL = 0, 1,
 JF_SPLINE_PLAIN, JF_SPLINE_SMOOTH, JF_SPLINE_CIRCULAR = 0, 1, 2
 JF_BD_PARAMS, JF_BD_FIXED, JF_BD_PERIODIC = 0, 1, 2
 JF_NORM_NONE, JF_NORM_RAW, JF_NORM_REGULATED = 0, 1, 2
+JF_ROT_HOUSEHOLDER, JF_ROT_NONE, JF_ROT_ANGLES, JF_ROT_CAYLEY, JF_ROT_TRIANGULAR = 0, 1, 2, 3, 4
+JF_WIDTH_SMOOTH, JF_WIDTH_EXP, JF_WIDTH_SOFTPLUS = 0, 1, 2
+JF_STRETCH_CLASSIC, JF_STRETCH_RQS = 0, 1
 JF_STATUS_NONFINITE, JF_STATUS_UNCONVERGED, JF_STATUS_OUT_OF_RANGE, JF_STATUS_ITERATIONS = 0, 1, 2, 3
 ERRORS = {-1: "JF_ERR_BAD_DESC (invalid descriptor)", -2: "JF_ERR_UNSUPPORTED (no kernel for this configuration)",
           -3: "JF_ERR_BAD_ARG (invalid argument)", -4: "JF_ERR_WORKSPACE (workspace missing or too small)"}
@@ -46,8 +49,11 @@ class JfLayerDesc(C.Structure):
                 ("K", C.c_int32), ("hh_iter", C.c_int32), ("inv_type", C.c_int32), ("norm_mode", C.c_int32),
                 ("has_offset", C.c_int32), ("first", C.c_int32), ("natural_direction", C.c_int32),
                 ("max_iter", C.c_int32), ("n_vertical", C.c_int32), ("n_circular", C.c_int32),
+                ("rotation_mode", C.c_int32), ("width_mode", C.c_int32), ("width_clamp", C.c_int32),
+                ("skew", C.c_int32), ("center_mean", C.c_int32), ("stretch", C.c_int32),
                 ("w_min", C.c_double), ("w_max", C.c_double), ("n_min", C.c_double), ("n_max", C.c_double),
                 ("z_sign", C.c_double), ("min_kappa", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
+                ("clamp_lo", C.c_double), ("clamp_hi", C.c_double),
                 ("spline", JfSplineDesc * JF_MAX_NESTED)]
 
 

@@ -6,6 +6,7 @@
 #include <cmath>
 #include "subpdf_kernels.cuh"
 #include "gf_launch.cuh"
+#include "gfx.cuh"
 #include "mlp_kernels.cuh"
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
@@ -45,10 +46,102 @@ static void fill_common(SubPdfArgs<T>& a, const JfSubPdfDesc* desc, const void* 
     a.tab_total = 0;
 }
 
+// "g" layer with any non-default option -> general chain kernel (csrc/gfx.cuh)
+static bool gf_layer_is_default(const JfLayerDesc& L) {
+    return L.rotation_mode == JF_ROT_HOUSEHOLDER && L.width_mode == JF_WIDTH_SMOOTH && !L.width_clamp && !L.skew &&
+           !L.center_mean && L.stretch == JF_STRETCH_CLASSIC;
+}
+
+// number of rotation parameters of a "g" layer, -1: invalid
+static int gf_rotation_params(const JfLayerDesc& L, int d) {
+    switch (L.rotation_mode) {
+        case JF_ROT_HOUSEHOLDER: return L.hh_iter * d;
+        case JF_ROT_NONE: return 0;
+        case JF_ROT_ANGLES: return d > 1 ? d * (d - 1) / 2 : 0;
+        case JF_ROT_CAYLEY: return d > 1 ? (d == 2 ? 1 : -1) : 0;
+        case JF_ROT_TRIANGULAR: return d - 1 + d * (d - 1);
+        default: return -1;
+    }
+}
+
+template <typename T>
+static int fill_mvn(GfLayerC<T>& c, const JfLayerDesc& L, int d, int tab) {
+    if (L.inv_type < JF_COV_IDENTITY || L.inv_type > JF_COV_FULL) return JF_ERR_BAD_DESC;
+    if (!(L.w_min > 0) || !(L.w_max > 0)) return JF_ERR_BAD_DESC;
+    const int ncov = L.inv_type == JF_COV_IDENTITY ? 0 : (L.inv_type == JF_COV_DIAGONAL_SYMMETRIC ? 1
+                     : (L.inv_type == JF_COV_DIAGONAL ? d : d + d * (d - 1) / 2));
+    if ((L.has_offset ? d : 0) + ncov != L.n_params) return JF_ERR_BAD_DESC;
+    c.kind = 1; c.K = 1; c.d = d; c.hh_iter = 0; c.inv_type = L.inv_type; c.norm_mode = JF_NORM_NONE;
+    c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = tab;
+    c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = 0; c.n_max = 0;
+    return JF_OK;
+}
+
+template <typename T>
+static int apply_gfx(const JfSubPdfDesc* desc, int direction, const SubPdfArgs<T>& a, cudaStream_t st) {
+    const int d = desc->dim;
+    GfxChainArgs<T> g;
+    memset(&g, 0, sizeof(g));
+    g.a = a;
+    int kmax = 1;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const JfLayerDesc& L = desc->layers[l];
+        if (L.dim != d) return JF_ERR_BAD_DESC;
+        GfxLayerC<T>& c = g.layers[l];
+        if (L.kind == JF_LAYER_MVN) {
+            const int rc = fill_mvn<T>(c.base, L, d, 0);
+            if (rc != JF_OK) return rc;
+            continue;
+        }
+        if (L.kind != JF_LAYER_GF) return JF_ERR_BAD_DESC;
+        if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
+        if (L.inv_type < 0 || L.inv_type > 3 || L.norm_mode < 0 || L.norm_mode > 2) return JF_ERR_BAD_DESC;
+        if (L.width_mode < JF_WIDTH_SMOOTH || L.width_mode > JF_WIDTH_SOFTPLUS) return JF_ERR_BAD_DESC;
+        if (L.stretch != JF_STRETCH_CLASSIC && L.stretch != JF_STRETCH_RQS) return JF_ERR_BAD_DESC;
+        if (!(L.w_min > 0)) return JF_ERR_BAD_DESC;
+        if (L.width_mode == JF_WIDTH_SMOOTH && L.stretch == JF_STRETCH_CLASSIC && !(L.w_max > 0)) return JF_ERR_BAD_DESC;
+        const int n_rot = gf_rotation_params(L, d);
+        if (n_rot < 0) return JF_ERR_BAD_DESC;
+        const int kd = L.K * d;
+        int off = L.param_offset + (L.has_offset ? d : 0);
+        c.base.kind = 0; c.base.K = L.K; c.base.d = d; c.base.hh_iter = L.rotation_mode == JF_ROT_HOUSEHOLDER ? L.hh_iter : 0;
+        c.base.inv_type = L.inv_type; c.base.norm_mode = L.norm_mode; c.base.has_offset = L.has_offset;
+        c.base.raw_off = L.param_offset; c.base.tab_off = 0;
+        c.base.w_min = (T)L.w_min; c.base.inv_w_max = (T)(L.w_max > 0 ? 1.0 / L.w_max : 0.0);
+        c.base.n_min = (T)L.n_min; c.base.n_max = (T)L.n_max;
+        c.rot_mode = L.rotation_mode; c.width_mode = L.width_mode; c.width_clamp = L.width_clamp; c.skew = L.skew;
+        c.center_mean = L.center_mean; c.stretch = L.stretch;
+        c.clamp_lo = (T)L.clamp_lo; c.clamp_hi = (T)L.clamp_hi;
+        c.off_rot = off; off += n_rot;
+        if (L.stretch == JF_STRETCH_RQS) {
+            if (L.K * 1e-3 > 1.0) return JF_ERR_BAD_DESC;
+            c.off_m = off; off += kd;                 // log_widths [d,K]
+            c.off_w = off; off += kd;                 // log_heights [d,K]
+            c.off_n = off; off += (L.K + 1) * d;      // log_derivatives [d,K+1]
+            c.off_s = off; off += 4 * d;              // boundary_points [d,4]
+            c.skew = 0; c.center_mean = 0;
+        } else {
+            if (L.center_mean && L.K < 2) return JF_ERR_BAD_DESC;
+            c.off_m = off; off += (L.K - (L.center_mean ? 1 : 0)) * d;
+            c.off_w = off; off += kd;
+            c.off_n = off; if (L.norm_mode != JF_NORM_NONE) off += kd;
+            c.off_s = off; if (L.skew) off += kd;
+        }
+        if (off - L.param_offset != L.n_params) return JF_ERR_BAD_DESC;
+        kmax = L.K > kmax ? L.K : kmax;
+    }
+    const int rc = launch_gfx<T>(g, direction, kmax, st);
+    if (rc != JF_OK) return rc;
+    return check_launch();
+}
+
 template <typename T>
 static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, cudaStream_t st) {
     const int d = desc->dim;
     if (d < 1 || d > JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
+    for (int l = 0; l < desc->n_layers; ++l)
+        if (desc->layers[l].kind == JF_LAYER_GF && !gf_layer_is_default(desc->layers[l]))
+            return apply_gfx<T>(desc, direction, g.a, st);
     int kmax = 1;
     int tab = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
@@ -57,13 +150,8 @@ static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, 
         if (!(L.w_min > 0) || !(L.w_max > 0)) return JF_ERR_BAD_DESC;
         GfLayerC<T>& c = g.layers[l];
         if (L.kind == JF_LAYER_MVN) {           // "t": inv_type carries the covariance type
-            if (L.inv_type < JF_COV_IDENTITY || L.inv_type > JF_COV_FULL) return JF_ERR_BAD_DESC;
-            const int ncov = L.inv_type == JF_COV_IDENTITY ? 0 : (L.inv_type == JF_COV_DIAGONAL_SYMMETRIC ? 1
-                             : (L.inv_type == JF_COV_DIAGONAL ? d : d + d * (d - 1) / 2));
-            if ((L.has_offset ? d : 0) + ncov != L.n_params) return JF_ERR_BAD_DESC;
-            c.kind = 1; c.K = 1; c.d = d; c.hh_iter = 0; c.inv_type = L.inv_type; c.norm_mode = JF_NORM_NONE;
-            c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = tab;
-            c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = 0; c.n_max = 0;
+            const int rc = fill_mvn<T>(c, L, d, tab);
+            if (rc != JF_OK) return rc;
             continue;
         }
         if (L.kind != JF_LAYER_GF) return JF_ERR_BAD_DESC;
@@ -266,6 +354,7 @@ static int subpdf_backward_t(const JfSubPdfDesc* desc, const void* x, int64_t ld
     for (int l = 0; l < desc->n_layers; ++l) {
         const JfLayerDesc& L = desc->layers[l];
         if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_UNSUPPORTED;
+        if (!gf_layer_is_default(L)) return JF_ERR_UNSUPPORTED;   // the closed-form backward covers the default options
         if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
         if (L.inv_type == JF_INV_FULL_PADE || L.inv_type == JF_INV_PARTLY_CRUDE) return JF_ERR_UNSUPPORTED;
         const int expect = (L.has_offset ? d : 0) + L.hh_iter * d + (L.norm_mode != JF_NORM_NONE ? 3 : 2) * L.K * d;

@@ -57,6 +57,16 @@ def fill_layer_desc(ld, desc, param_offset):
                         (_cabi.JF_NORM_REGULATED if desc["regulate_normalization"] else _cabi.JF_NORM_RAW))
         ld.has_offset = desc["model_offset"]
         ld.w_min, ld.w_max, ld.n_min, ld.n_max = desc["w_min"], desc["w_max"], desc["n_min"], desc["n_max"]
+        from .layers import ROT_MODES, WIDTH_MODES
+        ld.rotation_mode = ROT_MODES[desc.get("rotation_mode", "householder")]
+        ld.width_mode = WIDTH_MODES[desc.get("width_mode", "smooth")]
+        clamp = desc.get("width_clamp")
+        ld.width_clamp = 0 if clamp is None else 1
+        ld.clamp_lo, ld.clamp_hi = (0.0, 0.0) if clamp is None else (clamp[0], clamp[1])
+        ld.skew = desc.get("add_skewness", 0)
+        ld.center_mean = desc.get("center_mean", 0)
+        ld.stretch = (_cabi.JF_STRETCH_RQS if desc.get("stretch", "classic") == "rq_splines"
+                      else _cabi.JF_STRETCH_CLASSIC)
     elif desc["code"] == "t":
         ld.kind = _cabi.JF_LAYER_MVN
         ld.inv_type = desc["cov"]
@@ -369,6 +379,8 @@ def supports_backward(pdf):
             return False
         for l in layers:
             if getattr(l, "code", "") != "g" or l.inverse_function_type not in ("isigmoid", "inormal_partly_precise"):
+                return False
+            if not l.is_default_kernel_config:
                 return False
     return True
 

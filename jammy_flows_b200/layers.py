@@ -77,12 +77,19 @@ class layer_base(nn.Module):
 # =====================================================================================================================
 # Euclidean: Gaussianization flow "g"
 # =====================================================================================================================
+ROT_MODES = {"householder": 0, "none": 1, "angles": 2, "cayley": 3, "triangular_combination": 4}
+WIDTH_MODES = {"smooth": 0, "exp": 1, "softplus": 2}
+
+
 class gf_block(layer_base):
     """Gaussianization-flow block, symbol "g".
 
     Reference: layers/euclidean/gaussianization_flow.py:50-386 (constructor / parameter layout),
     layers/euclidean/euclidean_base.py:9-31 (offset handling).  Parameter slice order inside `extra_inputs`:
-    [offset d (last layer only)] [vs: iter*d] [means K*d] [log_widths K*d] [log_weights K*d].
+      [offset d (last layer only)] [rotation] then
+      classic:     [means (K-center_mean)*d] [log_widths K*d] [log_weights K*d (fit_normalization)] [log_skew K*d (add_skewness)]
+      rq_splines:  [log_widths d*K] [log_heights d*K] [log_derivatives d*(K+1)] [boundary_points d*4]
+    rotation: householder iter*d | angles d(d-1)/2 | cayley 1 (d=2) | triangular_combination d(d-1)+d-1 | none 0.
     """
 
     code = "g"
@@ -94,76 +101,158 @@ class gf_block(layer_base):
                  upper_bound_for_widths=100, lower_bound_for_norms=1, upper_bound_for_norms=10, center_mean=0,
                  clamp_widths=0, regulate_normalization=0, add_skewness=0, rotation_mode="householder"):
         super().__init__(dimension=dimension)
-        unsupported = []
-        if nonlinear_stretch_type != "classic":
-            unsupported.append("nonlinear_stretch_type=%s" % nonlinear_stretch_type)
-        if rotation_mode != "householder":
-            unsupported.append("rotation_mode=%s" % rotation_mode)
-        if add_skewness:
-            unsupported.append("add_skewness=1")
-        if center_mean:
-            unsupported.append("center_mean=1")
-        if softplus_for_width or clamp_widths or not width_smooth_saturation:
-            unsupported.append("non-default width regulator")
-        if upper_bound_for_widths <= 0 or upper_bound_for_norms <= 0:
-            unsupported.append("unbounded widths/norms")
-        if len(unsupported) > 0:
-            raise NotImplementedError("'g' layer options without an sm_100a kernel yet (SURVEY.md section 8f rank 1): "
-                                      + ", ".join(unsupported) + " -- there is no CPU fallback")
         assert inverse_function_type in INV_TYPES
         assert lower_bound_for_widths > 0.0
-
+        if nonlinear_stretch_type not in ("classic", "rq_splines"):
+            raise Exception("Unknown non linear stretch type: %s" % nonlinear_stretch_type)
+        if rotation_mode not in ROT_MODES:
+            # the reference silently applies no rotation for an unknown mode; only "none" is documented for that
+            raise Exception("Unknown rotation_mode: %s" % rotation_mode)
+        d = dimension
         self.use_permanent_parameters = use_permanent_parameters
         self.model_offset = model_offset
+        self.nonlinear_stretch_type = nonlinear_stretch_type
         self.inverse_function_type = inverse_function_type
         self.num_kde = num_kde
         self.fit_normalization = fit_normalization
         self.regulate_normalization = regulate_normalization
+        self.add_skewness = add_skewness
+        self.center_mean = int(center_mean)
         self.width_min = lower_bound_for_widths
-        self.width_max = upper_bound_for_widths
+        self.width_max = upper_bound_for_widths if upper_bound_for_widths > 0 else None
+        self.width_smooth_saturation = width_smooth_saturation
+        if self.width_smooth_saturation:
+            assert (self.width_max is not None), "We require a maximum saturation level for smooth saturation!"
+        self.softplus_for_width = softplus_for_width
+        self.clamp_widths = clamp_widths
         self.lower_bound_for_norms = lower_bound_for_norms
         self.upper_bound_for_norms = upper_bound_for_norms
         self.rotation_mode = rotation_mode
-        self.householder_iter = dimension if num_householder_iter == -1 else num_householder_iter
-        self.use_householder = self.householder_iter > 0
-        self.num_householder_params = self.householder_iter * dimension if self.use_householder else 0
-        self.num_params_datapoints = num_kde * dimension
+        if fit_normalization and regulate_normalization and nonlinear_stretch_type == "classic":
+            assert upper_bound_for_norms > 0, "regulate_normalization needs a positive upper_bound_for_norms"
+        # width regulator variant and the clamp applied to the raw value (reference gaussianization_flow.py:264-317)
+        classic = nonlinear_stretch_type == "classic"
+        self.width_mode = "softplus" if softplus_for_width else ("smooth" if width_smooth_saturation else "exp")
+        self.width_clamp = None
+        if classic and clamp_widths:
+            lo = float(numpy.log(0.01 * self.width_min))
+            if self.width_mode == "smooth":
+                hi = float(numpy.log(self.width_max) * 3.0)
+            else:
+                hi = float(numpy.log(self.width_max)) if self.width_max is not None else float("inf")
+            self.width_clamp = (lo, hi)
         # initialisation from the Gaussianization-flow paper (reference gaussianization_flow.py:233-234)
         self.init_log_width = numpy.log((4. * numpy.sqrt(math.pi) / ((math.pi ** 4) * num_kde)) ** 0.2)
+        self.num_params_datapoints = num_kde * d
 
         # RNG call order below mirrors the reference constructor so that equal seeds give equal parameters
         self.offsets = None
         if self.model_offset:
-            self.offsets = torch.zeros(dimension).type(torch.double).unsqueeze(0)
+            self.offsets = torch.zeros(d).type(torch.double).unsqueeze(0)
             if use_permanent_parameters:
-                self.offsets = nn.Parameter(torch.randn(dimension).type(torch.double).unsqueeze(0))
-            self.total_param_num += dimension
-        if self.use_householder and use_permanent_parameters:
-            self.vs = nn.Parameter(torch.randn(self.householder_iter, dimension).unsqueeze(0))
-        self.total_param_num += self.num_householder_params
-        if use_permanent_parameters:
-            self.kde_means = nn.Parameter(torch.randn(num_kde, dimension).unsqueeze(0))
-        self.total_param_num += self.num_params_datapoints
-        if use_permanent_parameters:
-            self.kde_log_widths = nn.Parameter(torch.ones(num_kde, dimension).unsqueeze(0) * self.init_log_width)
-        self.total_param_num += self.num_params_datapoints
-        if fit_normalization:
+                self.offsets = nn.Parameter(torch.randn(d).type(torch.double).unsqueeze(0))
+            self.total_param_num += d
+        # ---- rotation (reference :141-205) ----
+        self.householder_iter = 0
+        self.use_householder = False
+        self.num_householder_params = 0
+        self.num_rotation_params = 0
+        if rotation_mode == "triangular_combination":
+            self.num_triangle_params = int(d - 1 + d * (d - 1))
+            self.num_rotation_params = self.num_triangle_params
+            if use_permanent_parameters and d > 1:
+                self.triangle_trafo_pars = nn.Parameter(torch.randn(self.num_triangle_params).unsqueeze(0))
+        elif rotation_mode == "householder":
+            self.householder_iter = d if num_householder_iter == -1 else num_householder_iter
+            self.use_householder = self.householder_iter > 0
+            if self.use_householder:
+                if use_permanent_parameters:
+                    self.vs = nn.Parameter(torch.randn(self.householder_iter, d).unsqueeze(0))
+                self.num_householder_params = self.householder_iter * d
+            self.num_rotation_params = self.num_householder_params
+        elif rotation_mode == "angles":
+            self.num_angle_pars = 0
+            if d > 1:
+                self.num_angle_pars = int(d * (d - 1) / 2)
+                if use_permanent_parameters:
+                    self.angle_pars = nn.Parameter(torch.randn((1, self.num_angle_pars)))
+            self.num_rotation_params = self.num_angle_pars
+        elif rotation_mode == "cayley":
+            self.num_cayley_pars = 0
+            if d > 1:
+                self.num_cayley_pars = 1
+                assert (d == 2), "Cayley requires 2 dims at the moment"
+                if use_permanent_parameters:
+                    # the reference constructor creates `cayley_pars` and then fails in init_params
+                    # (gaussianization_flow.py:1193 indexes a 1-d tensor with two indices): cayley only works amortised
+                    raise IndexError("rotation_mode='cayley' with permanent parameters fails in the reference's "
+                                     "init_params (gaussianization_flow.py:1193); use it in a conditional sub-pdf")
+            self.num_rotation_params = self.num_cayley_pars
+        self.total_param_num += self.num_rotation_params
+        # ---- non-linear stretch (reference :218-386) ----
+        if classic:
+            self.total_param_num_means = (num_kde - self.center_mean) * d
             if use_permanent_parameters:
-                self.kde_log_weights = nn.Parameter(torch.randn(num_kde, dimension).unsqueeze(0))
+                self.kde_means = nn.Parameter(torch.randn(num_kde - self.center_mean, d).unsqueeze(0))
+            self.total_param_num += self.total_param_num_means
+            if use_permanent_parameters:
+                self.kde_log_widths = nn.Parameter(torch.ones(num_kde, d).unsqueeze(0) * self.init_log_width)
             self.total_param_num += self.num_params_datapoints
+            if fit_normalization:
+                if use_permanent_parameters:
+                    self.kde_log_weights = nn.Parameter(torch.randn(num_kde, d).unsqueeze(0))
+                self.total_param_num += self.num_params_datapoints
+            if add_skewness:
+                if use_permanent_parameters:
+                    self.kde_log_skew_exponents = nn.Parameter(torch.randn(num_kde, d).unsqueeze(0))
+                self.total_param_num += self.num_params_datapoints
+        else:
+            if use_permanent_parameters:
+                self.log_widths = nn.Parameter(torch.randn(d, num_kde).unsqueeze(0))
+                self.log_heights = nn.Parameter(torch.randn(d, num_kde).unsqueeze(0))
+                self.log_derivatives = nn.Parameter(torch.randn(d, num_kde + 1).unsqueeze(0))
+                self.boundary_points = nn.Parameter(torch.randn(d, 4).unsqueeze(0))
+            self.total_param_num += (num_kde * d) * 2 + (num_kde + 1) * d + 4 * d
+        if num_kde > 32:
+            raise NotImplementedError("'g' with num_kde > 32 (JF_MAX_KDE)")
+
+    @property
+    def is_default_kernel_config(self):
+        """True when the layer runs on the specialised (fast) chain kernel; the other options use the general one."""
+        return (self.nonlinear_stretch_type == "classic" and self.rotation_mode == "householder"
+                and not self.add_skewness and not self.center_mean and self.width_mode == "smooth"
+                and self.width_clamp is None)
 
     # ---- reference euclidean_base.py:77-104, gaussianization_flow.py:1116-1210 -----------------------------------
     def get_desired_init_parameters(self):
         par_list = []
+        d = self.dimension
         if self.model_offset:
-            par_list.append(torch.ones(self.dimension) * 0.001)
-        if self.num_householder_params > 0:
-            par_list.append(torch.randn(self.householder_iter * self.dimension))
-        par_list.append(torch.randn(self.num_params_datapoints))
-        par_list.append(torch.ones(self.num_params_datapoints) * self.init_log_width)
-        if self.fit_normalization:
-            par_list.append(torch.ones(self.num_params_datapoints))
+            par_list.append(torch.ones(d) * 0.001)
+        if self.rotation_mode == "householder":
+            if self.num_householder_params > 0:
+                par_list.append(torch.randn(self.householder_iter * d))
+        elif self.rotation_mode != "none":
+            par_list.append(torch.zeros(self.num_rotation_params))
+        if self.nonlinear_stretch_type == "classic":
+            par_list.append(torch.randn(self.total_param_num_means))
+            par_list.append(torch.ones(self.num_params_datapoints) * self.init_log_width)
+            if self.fit_normalization:
+                par_list.append(torch.ones(self.num_params_datapoints))
+            if self.add_skewness:
+                par_list.append(torch.zeros(self.num_params_datapoints))
+        else:
+            par_list.append(torch.ones(self.num_kde * d))
+            par_list.append(torch.ones(self.num_kde * d))
+            par_list.append(torch.ones((self.num_kde + 1) * d) * 0.54135)   # softplus^-1(1)
+            par_list.append(torch.Tensor(d * [-1.0, 1.0, -1.0, 1.0]))
         return torch.cat(par_list)
+
+    def _rotation_param_name(self):
+        if self.num_rotation_params == 0:
+            return None
+        return {"householder": "vs", "angles": "angle_pars", "cayley": "cayley_pars",
+                "triangular_combination": "triangle_trafo_pars"}[self.rotation_mode]
 
     def init_params(self, params):
         assert (len(params) == self.total_param_num), (len(params), self.total_param_num)
@@ -173,25 +262,50 @@ class gf_block(layer_base):
         if self.model_offset:
             self.offsets.data = params[:d]
             c = d
-        if self.use_householder:
-            self.vs.data = torch.reshape(params[c:c + self.num_householder_params], [1, self.householder_iter, d])
-            c += self.num_householder_params
-        self.kde_means.data = torch.reshape(params[c:c + k * d], [1, k, d])
-        c += k * d
-        self.kde_log_widths.data = torch.reshape(params[c:c + k * d], [1, k, d])
-        c += k * d
-        if self.fit_normalization:
-            self.kde_log_weights.data = torch.reshape(params[c:c + k * d], [1, k, d])
+        if self.rotation_mode == "householder":
+            if self.use_householder:
+                self.vs.data = torch.reshape(params[c:c + self.num_householder_params], [1, self.householder_iter, d])
+                c += self.num_householder_params
+        elif self.num_rotation_params > 0:
+            getattr(self, self._rotation_param_name()).data = torch.reshape(
+                params[c:c + self.num_rotation_params], [1, self.num_rotation_params])
+            c += self.num_rotation_params
+        if self.nonlinear_stretch_type == "classic":
+            n = self.total_param_num_means
+            self.kde_means.data = torch.reshape(params[c:c + n], [1, k - self.center_mean, d])
+            c += n
+            self.kde_log_widths.data = torch.reshape(params[c:c + k * d], [1, k, d])
+            c += k * d
+            if self.fit_normalization:
+                self.kde_log_weights.data = torch.reshape(params[c:c + k * d], [1, k, d])
+                c += k * d
+            if self.add_skewness:
+                self.kde_log_skew_exponents.data = torch.reshape(params[c:c + k * d], [1, k, d])
+                c += k * d
+        else:
+            self.log_widths.data = torch.reshape(params[c:c + k * d], [1, d, k])
+            c += k * d
+            self.log_heights.data = torch.reshape(params[c:c + k * d], [1, d, k])
+            c += k * d
+            self.log_derivatives.data = torch.reshape(params[c:c + (k + 1) * d], [1, d, k + 1])
+            c += (k + 1) * d
+            self.boundary_points.data = torch.reshape(params[c:c + 4 * d], [1, d, 4])
 
     def permanent_param_names(self):
         names = []
         if self.model_offset:
             names.append("offsets")
-        if self.use_householder:
-            names.append("vs")
-        names += ["kde_means", "kde_log_widths"]
-        if self.fit_normalization:
-            names.append("kde_log_weights")
+        rot = self._rotation_param_name()
+        if rot is not None:
+            names.append(rot)
+        if self.nonlinear_stretch_type == "classic":
+            names += ["kde_means", "kde_log_widths"]
+            if self.fit_normalization:
+                names.append("kde_log_weights")
+            if self.add_skewness:
+                names.append("kde_log_skew_exponents")
+        else:
+            names += ["log_widths", "log_heights", "log_derivatives", "boundary_points"]
         return names
 
     def descriptor(self):
@@ -199,8 +313,12 @@ class gf_block(layer_base):
                     inverse_function_type=self.inverse_function_type, inv_type=INV_TYPES[self.inverse_function_type],
                     fit_normalization=int(self.fit_normalization),
                     regulate_normalization=int(self.regulate_normalization), model_offset=int(self.model_offset),
-                    w_min=float(self.width_min), w_max=float(self.width_max),
+                    w_min=float(self.width_min), w_max=float(self.width_max if self.width_max is not None else -1.0),
                     n_min=float(self.lower_bound_for_norms), n_max=float(self.upper_bound_for_norms),
+                    rotation_mode=self.rotation_mode, n_rot=int(self.num_rotation_params),
+                    width_mode=self.width_mode, width_clamp=self.width_clamp,
+                    add_skewness=int(bool(self.add_skewness)), center_mean=self.center_mean,
+                    stretch=self.nonlinear_stretch_type, default_kernel=bool(self.is_default_kernel_config),
                     n_params=self.total_param_num)
 
     def _embedding_conditional_return(self, x):

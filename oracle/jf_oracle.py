@@ -64,17 +64,119 @@ def _safe_costheta(x, margin=None):
 # ---------------------------------------------------------------------------------------------------------------------
 # Gaussianization-flow layer "g"
 # ---------------------------------------------------------------------------------------------------------------------
+def _lower_unit(d, low, upper=False):
+    """Unit-diagonal triangular matrix from `low` (sub-diagonals from the bottom-left corner, matrix_fns.py:27-52);
+    upper=True transposes it."""
+    m = torch.eye(d, dtype=low.dtype).unsqueeze(0).repeat(low.shape[0], 1, 1)
+    pos = 0
+    for ind in range(d - 1):
+        n = ind + 1
+        m = m + torch.diag_embed(low[:, pos:pos + n], offset=-(d - 1 - ind))
+        pos += n
+    return m.permute(0, 2, 1) if upper else m
+
+
+def _log_one_plus_exp_x_to_a_minus_1(x, a):
+    """log(((1+e^x)^a - 1)/(1+e^x)^a), branch by branch as the reference: extra_functions.py:14-61."""
+    sp = a * F.softplus(x)
+    small = x <= -20
+    res = torch.where(small, torch.log(a) + x, torch.zeros_like(x))
+    large = sp > 20
+    res = torch.where((~small) & large, sp, res)
+    tiny = sp < 1e-8
+    res = torch.where((~small) & tiny, torch.log(sp), res)
+    mid = (~small) & (~large) & (~tiny)
+    res = torch.where(mid, torch.log(torch.exp(sp) - 1.0), res)
+    return res - sp
+
+
 class GfLayer:
     """One gf_block.  `spec` keys: dim, num_kde, hh_iter, inverse_function_type, fit_normalization,
-    regulate_normalization, model_offset, w_min, w_max, n_min, n_max."""
+    regulate_normalization, model_offset, w_min, w_max, n_min, n_max, rotation_mode, width_mode, width_clamp,
+    add_skewness, center_mean, stretch."""
 
     def __init__(self, spec):
         self.s = spec
         self.d = spec["dim"]
         self.k = spec["num_kde"]
 
-    # -- parameter unpacking: [offset d][hh iter*d][means K*d][log_w K*d][log_n K*d]
-    #    Reference: layers/euclidean/euclidean_base.py:34-50, gaussianization_flow.py:699-861
+    # -- width regulator variants.  Reference: gaussianization_flow.py:264-317
+    def _log_width(self, raw):
+        s = self.s
+        mode = s.get("width_mode", "smooth")
+        clamp = s.get("width_clamp")
+        if clamp is not None:
+            raw = torch.clamp(raw, min=clamp[0], max=(None if math.isinf(clamp[1]) else clamp[1]))
+        if mode == "smooth":
+            return _bounded_log_fn(raw, s["w_min"], s["w_max"], center=True)
+        if mode == "softplus":
+            return torch.log(F.softplus(raw) + s["w_min"])
+        return torch.log(torch.exp(raw) + s["w_min"])
+
+    # -- rotation parameters -> (mode, payload).  Reference: gaussianization_flow.py:711-800
+    def _rotation(self, p, i):
+        s, d = self.s, self.d
+        mode = s.get("rotation_mode", "householder")
+        if mode == "householder":
+            if s["hh_iter"] > 0:
+                n = s["hh_iter"] * d
+                return ("matrix", householder_matrix(p[:, i:i + n].reshape(-1, s["hh_iter"], d))), i + n
+            return None, i
+        if mode == "none" or d == 1:
+            return None, i
+        if mode == "angles":
+            n = d * (d - 1) // 2
+            ang = p[:, i:i + n]
+            eye = torch.eye(d, dtype=p.dtype).unsqueeze(0).repeat(p.shape[0], 1, 1)
+            q = eye
+            import itertools
+            for ind, (a, b) in enumerate(itertools.combinations(range(d), 2)):
+                g = eye.clone()
+                g[:, a, a] = torch.cos(ang[:, ind])
+                g[:, b, b] = g[:, a, a]
+                g[:, a, b] = torch.sin(ang[:, ind])
+                g[:, b, a] = -g[:, a, b]
+                q = torch.bmm(g, q)
+            return ("matrix", q), i + n
+        if mode == "cayley":
+            c = p[:, i:i + 1]
+            f = 1.0 / (1.0 + c ** 2)
+            q = torch.diag_embed(((1.0 - c ** 2) * f).repeat(1, 2))
+            q[:, 0:1, 1:2] = (-2.0 * c * f).unsqueeze(-1)
+            q[:, 1:2, 0:1] = (2.0 * c * f).unsqueeze(-1)
+            return ("matrix", q), i + 1
+        if mode == "triangular_combination":
+            npm = d * (d - 1) // 2
+            left = p[:, i:i + npm]
+            mid = p[:, i + npm:i + npm + d - 1]
+            right = p[:, i + npm + d - 1:i + 2 * npm + d - 1]
+            return ("tri", (left, mid, right)), i + 2 * npm + d - 1
+        raise ValueError(mode)
+
+    def _rotate(self, rot, x, inverse):
+        """inverse=True: log_pdf direction (gaussianization_flow.py:1004-1055); False: sampling (:942-987)."""
+        if rot is None:
+            return x
+        kind, pay = rot
+        b = x.shape[0]
+        if kind == "matrix":
+            q = pay.expand(b, -1, -1)
+            return torch.einsum("bji,bj->bi", q, x) if inverse else torch.einsum("bij,bj->bi", q, x)
+        left, mid, right = pay
+        d = self.d
+        lm = _lower_unit(d, left).expand(b, -1, -1)
+        um = _lower_unit(d, right, upper=True).expand(b, -1, -1)
+        diag = torch.cat([mid, -mid.sum(dim=1, keepdim=True)], dim=1)
+        if inverse:
+            x = torch.linalg.solve_triangular(lm, x.unsqueeze(-1), upper=False, unitriangular=True).squeeze(-1)
+            x = x / torch.exp(diag)
+            return torch.linalg.solve_triangular(um, x.unsqueeze(-1), upper=True, unitriangular=True).squeeze(-1)
+        x = torch.einsum("bij,bj->bi", um, x)
+        x = x * torch.exp(diag)
+        return torch.einsum("bij,bj->bi", lm, x)
+
+    # -- parameter unpacking: [offset d][rotation][means][log_w][log_n][log_skew]  /  rq_splines layout
+    #    Reference: layers/euclidean/euclidean_base.py:34-50, gaussianization_flow.py:699-909
     def unpack(self, p):
         s, d, k = self.s, self.d, self.k
         i = 0
@@ -82,14 +184,26 @@ class GfLayer:
         if s["model_offset"]:
             offset = p[:, :d]
             i = d
-        q = None
-        if s["hh_iter"] > 0:
-            n = s["hh_iter"] * d
-            q = householder_matrix(p[:, i:i + n].reshape(-1, s["hh_iter"], d))
-            i += n
-        means = p[:, i:i + k * d].reshape(-1, k, d)
-        i += k * d
-        log_w = _bounded_log_fn(p[:, i:i + k * d].reshape(-1, k, d), s["w_min"], s["w_max"], center=True)
+        rot, i = self._rotation(p, i)
+        if s.get("stretch", "classic") == "rq_splines":
+            lw = p[:, i:i + d * k].reshape(-1, d, k)
+            i += d * k
+            lh = p[:, i:i + d * k].reshape(-1, d, k)
+            i += d * k
+            ld = p[:, i:i + d * (k + 1)].reshape(-1, d, k + 1)
+            i += d * (k + 1)
+            bp = p[:, i:i + 4 * d].reshape(-1, d, 4)
+            i += 4 * d
+            assert i == p.shape[1], (i, p.shape)
+            left = bp[:, :, 0:1]
+            right = left + torch.exp(bp[:, :, 1:2]) + 0.5
+            bottom = bp[:, :, 2:3]
+            top = bottom + torch.exp(bp[:, :, 3:4]) + 0.5
+            return offset, rot, ("rqs", (lw, lh, ld, left, right, bottom, top))
+        cm = int(s.get("center_mean", 0))
+        means = p[:, i:i + (k - cm) * d].reshape(-1, k - cm, d)
+        i += (k - cm) * d
+        log_w = self._log_width(p[:, i:i + k * d].reshape(-1, k, d))
         i += k * d
         if s["fit_normalization"]:
             log_n = p[:, i:i + k * d].reshape(-1, k, d)
@@ -98,19 +212,95 @@ class GfLayer:
                 log_n = _bounded_log_fn(log_n, s["n_min"], s["n_max"], center=False)
         else:
             log_n = torch.zeros_like(log_w)
+        log_s = None
+        if s.get("add_skewness", 0):
+            log_s = _bounded_log_fn(p[:, i:i + k * d].reshape(-1, k, d), 0.1, 9.0, center=True)
+            i += k * d
+        if cm:
+            nw = log_n.exp()
+            new_mean = -(means * nw[:, :-1, :]).sum(dim=1, keepdim=True) / nw[:, -1:, :]
+            means = torch.cat([means, new_mean], dim=1)
         assert i == p.shape[1], (i, p.shape)
-        return offset, q, means, log_w, log_n
+        return offset, rot, ("classic", (means, log_w, log_n, log_s))
 
-    # -- K-logistic mixture in log space.  Reference: gaussianization_flow.py:389-454 (add_skewness=0 branch)
+    # -- K-logistic mixture in log space.  Reference: gaussianization_flow.py:389-454
     @staticmethod
-    def mixture(x, means, log_w, log_n):
+    def mixture(x, means, log_w, log_n, log_s=None):
         a = (x.unsqueeze(1) - means) / torch.exp(log_w)
         nrm = log_n - torch.logsumexp(log_n, dim=1, keepdim=True)
-        sp = F.softplus(-a)
-        log_cdf = torch.logsumexp(-sp + nrm, dim=1)
-        log_sf = torch.logsumexp(-a - sp + nrm, dim=1)
-        log_pdf = torch.logsumexp(-a - log_w - 2.0 * sp + nrm, dim=1)
-        return log_cdf, log_sf, log_pdf
+        if log_s is None:
+            sp = F.softplus(-a)
+            log_cdf = torch.logsumexp(-sp + nrm, dim=1)
+            log_sf = torch.logsumexp(-a - sp + nrm, dim=1)
+            log_pdf = torch.logsumexp(-a - log_w - 2.0 * sp + nrm, dim=1)
+            return log_cdf, log_sf, log_pdf
+        # skewed kernels: the first K//2 are sigmoid(a)^s, the rest mirrored (gaussianization_flow.py:363-372, 417-442)
+        k = means.shape[1]
+        sgn = torch.ones(1, k, 1, dtype=x.dtype)
+        sgn[:, k // 2:, :] = -1.0
+        se = torch.exp(log_s)
+        log_pdf = torch.logsumexp(-sgn * a - log_w + log_s - (se + 1.0) * F.softplus(-sgn * a) + nrm, dim=1)
+        pos = (sgn > 0).expand_as(a)
+        lc = torch.where(pos, -se * F.softplus(-a), _log_one_plus_exp_x_to_a_minus_1(a, se.expand_as(a)))
+        ls = torch.where(pos, _log_one_plus_exp_x_to_a_minus_1(-a, se.expand_as(a)), -se * F.softplus(a))
+        return torch.logsumexp(lc + nrm, dim=1), torch.logsumexp(ls + nrm, dim=1), log_pdf
+
+    # -- rational-quadratic spline with linear tails.  Reference: layers/spline_fns.py:188-358
+    @staticmethod
+    def rqs_linear_ext(x, pars, inverse):
+        lw, lh, ld, left, right, bottom, top = pars
+        k = lw.shape[-1]
+        x = x.unsqueeze(-1)
+
+        def knots(raw, lo, hi):
+            w = 1e-3 + (1.0 - 1e-3 * k) * F.softmax(raw, dim=-1)
+            c = F.pad(torch.cumsum(w, dim=-1), pad=(1, 0), mode="constant", value=0.0)
+            c = (hi - lo) * c + lo
+            return c, c[..., 1:] - c[..., :-1]
+
+        cw, w = knots(lw, left, right)
+        ch, h = knots(lh, bottom, top)
+        der = 1e-3 + F.softplus(ld)
+        b = x.shape[0]
+        cw, w, ch, h, der = (t.expand(b, -1, -1) for t in (cw, w, ch, h, der))
+        left, right, bottom, top = (t.expand(b, -1, -1) for t in (left, right, bottom, top))
+        idx = torch.sum(x >= (ch if inverse else cw), dim=-1, keepdim=True) - 1
+        idx = torch.clamp(idx, 0, k - 1)
+        g = lambda t: t.gather(-1, idx)
+        x0, wk, y0, hk = g(cw), g(w), g(ch), g(h)
+        delta = g(h / w)
+        d0, d1 = g(der), g(der[..., 1:])
+        if inverse:
+            dy = x - y0
+            qa = dy * (d0 + d1 - 2 * delta) + hk * (delta - d0)
+            qb = hk * d0 - dy * (d0 + d1 - 2 * delta)
+            qc = -delta * dy
+            root = (2 * qc) / (-qb - torch.sqrt(qb.pow(2) - 4 * qa * qc))
+            out = root * wk + x0
+            tt = root * (1 - root)
+            den = delta + (d0 + d1 - 2 * delta) * tt
+            num = delta.pow(2) * (d1 * root.pow(2) + 2 * delta * tt + d0 * (1 - root).pow(2))
+            lad = -(torch.log(num) - 2 * torch.log(den))
+            lo_off = cw[..., 0:1] - ch[..., 0:1] / der[..., 0:1]
+            out = torch.where(x <= bottom, x / der[..., 0:1] + lo_off, out)
+            hi_off = cw[..., -1:] - ch[..., -1:] / der[..., -1:]
+            out = torch.where(x >= top, x / der[..., -1:] + hi_off, out)
+            lad = torch.where(x <= bottom, -torch.log(der[..., 0:1]), lad)
+            lad = torch.where(x >= top, -torch.log(der[..., -1:]), lad)
+        else:
+            th = (x - x0) / wk
+            tt = th * (1 - th)
+            den = delta + (d0 + d1 - 2 * delta) * tt
+            out = y0 + hk * (delta * th.pow(2) + d0 * tt) / den
+            num = delta.pow(2) * (d1 * th.pow(2) + 2 * delta * tt + d0 * (1 - th).pow(2))
+            lad = torch.log(num) - 2 * torch.log(den)
+            lo_off = ch[..., 0:1] - cw[..., 0:1] * der[..., 0:1]
+            out = torch.where(x <= left, x * der[..., 0:1] + lo_off, out)
+            hi_off = ch[..., -1:] - cw[..., -1:] * der[..., -1:]
+            out = torch.where(x >= right, x * der[..., -1:] + hi_off, out)
+            lad = torch.where(x <= left, torch.log(der[..., 0:1]), lad)
+            lad = torch.where(x >= right, torch.log(der[..., -1:]), lad)
+        return out.squeeze(-1), lad.squeeze(-1)
 
     # -- inverse-CDF stage.  Reference: gaussianization_flow.py:480-560
     def value(self, log_cdf, log_sf):
@@ -170,24 +360,39 @@ class GfLayer:
 
     # -- log_pdf direction.  Reference: euclidean_base.py:34-50 + gaussianization_flow.py:995-1057
     def inverse(self, x, log_det, p):
-        offset, q, means, log_w, log_n = self.unpack(p)
+        offset, rot, (kind, pars) = self.unpack(p)
         if offset is not None:
             x = x - offset
-        if q is not None:
-            x = torch.einsum("bji,bj->bi", q.expand(x.shape[0], -1, -1), x)       # Q^T x
-        lc, ls, lp = self.mixture(x, means, log_w, log_n)
+        x = self._rotate(rot, x, inverse=True)
+        if kind == "rqs":
+            y, lad = self.rqs_linear_ext(x, pars, inverse=False)
+            return y, log_det + lad.sum(dim=-1)
+        lc, ls, lp = self.mixture(x, *pars)
         return self.value(lc, ls), log_det + self.log_deriv(lc, ls, lp).sum(dim=-1)
 
     # -- sampling direction: 25 bisections on [-1e5,1e5] then <=20 Newton steps, tolerance 1e-14 on the row sum.
     #    Reference: gaussianization_flow.py:911-989 + layers/bisection_n_newton.py:11-135
     def forward(self, z, log_det, p):
-        offset, q, means, log_w, log_n = self.unpack(p)
+        offset, rot, (kind, pars) = self.unpack(p)
         b = z.shape[0]
+        if kind == "rqs":
+            x, lad = self.rqs_linear_ext(z, pars, inverse=True)
+            log_det = log_det + lad.sum(dim=-1)
+            x = self._rotate(rot, x, inverse=False)
+            if offset is not None:
+                x = x + offset
+            return x, log_det
+        means, log_w, log_n, log_s = pars
         means, log_w, log_n = (t.expand(b, -1, -1) for t in (means, log_w, log_n))
+        if log_s is not None:
+            log_s = log_s.expand(b, -1, -1)
 
         def f(xx, sel=None):
-            m, w, n = (means, log_w, log_n) if sel is None else (means[sel], log_w[sel], log_n[sel])
-            lc, ls, lp = self.mixture(xx, m, w, n)
+            if sel is None:
+                m, w, n, sk = means, log_w, log_n, log_s
+            else:
+                m, w, n, sk = means[sel], log_w[sel], log_n[sel], (None if log_s is None else log_s[sel])
+            lc, ls, lp = self.mixture(xx, m, w, n, sk)
             return self.value(lc, ls), lc, ls, lp
 
         lo = torch.full_like(z, -1e5)
@@ -217,8 +422,7 @@ class GfLayer:
             active[idx] = still
         _, lc, ls, lp = f(x)
         log_det = log_det - self.log_deriv(lc, ls, lp).sum(dim=-1)
-        if q is not None:
-            x = torch.einsum("bij,bj->bi", q.expand(b, -1, -1), x)              # Q x
+        x = self._rotate(rot, x, inverse=False)
         if offset is not None:
             x = x + offset
         return x, log_det

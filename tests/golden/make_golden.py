@@ -129,6 +129,36 @@ CASES = {
     "t_e4_gt_cond_diag": dict(pdf_defs="e4", flow_defs="gt", n=500, cond_dim=2, perturb=0.2),
     "t_e2e3_sym_identity": dict(pdf_defs="e2+e3", flow_defs="t+gt", n=500, perturb=0.3,
                                 opts={0: {"t": {"cov_type": "diagonal_symmetric"}}, 1: {"t": {"cov_type": "identity"}}}),
+    # non-default "g" options (the reference's own option sweep: tests/test_general.py:307-320)
+    "g_e3_angles_cond": dict(pdf_defs="e3", flow_defs="gg", n=400, cond_dim=2, perturb=0.2, tails=True,
+                             opts={"g": {"rotation_mode": "angles"}}),
+    "g_e4_angles": dict(pdf_defs="e4", flow_defs="gg", n=400, perturb=0.3, opts={"g": {"rotation_mode": "angles"}}),
+    "g_e2_cayley": dict(pdf_defs="e2", flow_defs="gg", n=400, perturb=0.3, tails=True,
+                        opts={"g": {"rotation_mode": "cayley"}}),
+    "g_e2_cayley_cond": dict(pdf_defs="e2", flow_defs="g", n=300, cond_dim=2, perturb=0.2,
+                             opts={"g": {"rotation_mode": "cayley"}}),
+    "g_e3_tri_cond": dict(pdf_defs="e3", flow_defs="gg", n=400, cond_dim=2, perturb=0.2,
+                          opts={"g": {"rotation_mode": "triangular_combination"}}),
+    "g_e4_tri": dict(pdf_defs="e4", flow_defs="gg", n=400, perturb=0.3, tails=True,
+                     opts={"g": {"rotation_mode": "triangular_combination"}}),
+    "g_e2_softplus_width": dict(pdf_defs="e2", flow_defs="gg", n=400, perturb=0.3, tails=True,
+                                opts={"g": {"softplus_for_width": 1}}),
+    "g_e2_clamp_widths": dict(pdf_defs="e2", flow_defs="gg", n=400, perturb=0.3, opts={"g": {"clamp_widths": 1}}),
+    "g_e2_unbounded_clamp_cond": dict(pdf_defs="e2", flow_defs="gg", n=400, cond_dim=2, perturb=0.2,
+                                      opts={"g": {"upper_bound_for_widths": -1, "clamp_widths": 1,
+                                                  "width_smooth_saturation": 0}}),
+    "g_e2_softplus_clamp": dict(pdf_defs="e2", flow_defs="g", n=300, perturb=0.3,
+                                opts={"g": {"softplus_for_width": 1, "clamp_widths": 1}}),
+    "g_e2_skew": dict(pdf_defs="e2", flow_defs="gg", n=400, perturb=0.3, tails=True, opts={"g": {"add_skewness": 1}}),
+    "g_e3_skew_cond": dict(pdf_defs="e3", flow_defs="gg", n=400, cond_dim=2, perturb=0.2,
+                           opts={"g": {"add_skewness": 1}}),
+    "g_e2_rqs": dict(pdf_defs="e2", flow_defs="gg", n=400, perturb=0.3, tails=True,
+                     opts={"g": {"nonlinear_stretch_type": "rq_splines"}}),
+    "g_e3_rqs_cond": dict(pdf_defs="e3", flow_defs="gg", n=400, cond_dim=2, perturb=0.2,
+                          opts={"g": {"nonlinear_stretch_type": "rq_splines"}}),
+    "g_e2_center_mean": dict(pdf_defs="e2", flow_defs="gg", n=300, perturb=0.3, opts={"g": {"center_mean": 1}}),
+    "g_e2_center_mean_cond": dict(pdf_defs="e2", flow_defs="gg", n=300, cond_dim=2, perturb=0.2,
+                                  opts={"g": {"center_mean": 1}}),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
