@@ -310,6 +310,21 @@ int jf_pdf_sample_host(const JfPdfDesc* desc, const JfPdfParams* params,
                        int64_t B, void* workspace, int64_t workspace_bytes, int64_t chunk_rows,
                        int64_t* status);
 
+/* Target-space charts of all sub-pdfs in one pass: what the reference's `force_embedding_coordinates` does before the
+ * log_pdf chain and after the sampling chain (pdf.transform_target_space, main/default.py:1737-1813 with
+ * layers/spheres/sphere_base.py:242-332; Euclidean and interval sub-pdfs are copied).
+ *   to_embedding != 0: in [B, total intrinsic dim] (s2: theta,phi; s1: angle) -> out [B, total embedded dim]
+ *                      (s2: x,y,z; s1: cos,sin); logdet_out = logdet_in + sum over s2 sub-pdfs of log sin(theta)
+ *   to_embedding == 0: the inverse charts; logdet_out = logdet_in - sum log sin(theta)
+ * logdet_in may be NULL (= 0), logdet_out may be NULL. */
+int jf_pdf_transform_target(const JfPdfDesc* desc, int to_embedding,
+                            const void* in, int64_t ld_in, void* out, int64_t ld_out,
+                            const void* logdet_in, void* logdet_out, int64_t B, void* stream);
+
+/* out[r] = log(mean_c exp(in[r*cols + c])) for r < rows: the S x S cross-evaluation reduce of the marginal entropies
+ * (pdf.entropy with sub_manifolds, main/default.py:2444-2448).  Device buffers. */
+int jf_row_logmeanexp(int dtype, const void* in, int64_t rows, int64_t cols, void* out, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 int jf_abi_version(void);
 /* FP64 DFMA / FP32 FFMA peak probe used as the roofline denominator of the compute-bound layer kernels:

@@ -7,6 +7,7 @@
 #include "subpdf_kernels.cuh"
 #include "gf_launch.cuh"
 #include "gfx.cuh"
+#include "chart.cuh"
 #include "mlp_kernels.cuh"
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
@@ -835,6 +836,54 @@ extern "C" int jf_pdf_sample_host(const JfPdfDesc* desc, const JfPdfParams* para
 // ---------------------------------------------------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int transform_target(const JfPdfDesc* desc, int to_embedding, const void* in, int64_t ld_in, void* out,
+                            int64_t ld_out, const void* logdet_in, void* logdet_out, int64_t B, cudaStream_t st) {
+    ChartArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.n_sub = desc->n_sub; a.to_embedding = to_embedding ? 1 : 0;
+    int ci = 0, ce = 0;   // running intrinsic / embedded column
+    for (int k = 0; k < desc->n_sub; ++k) {
+        const JfSubPdfDesc& s = desc->sub[k];
+        const bool sphere = s.manifold == 's';
+        if (sphere && s.dim != 1 && s.dim != 2) return JF_ERR_UNSUPPORTED;
+        a.kind[k] = sphere ? s.dim : 0;
+        a.dim[k] = s.dim;
+        a.in_col[k] = to_embedding ? ci : ce;
+        a.out_col[k] = to_embedding ? ce : ci;
+        ci += s.dim;
+        ce += s.dim + (sphere ? 1 : 0);
+    }
+    a.in = (const T*)in; a.ld_in = ld_in; a.out = (T*)out; a.ld_out = ld_out;
+    a.logdet_in = (const T*)logdet_in; a.logdet_out = (T*)logdet_out; a.B = B;
+    const int64_t blocks = (B + 255) / 256;
+    chart_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
+    return check_launch();
+}
+
+extern "C" int jf_pdf_transform_target(const JfPdfDesc* desc, int to_embedding, const void* in, int64_t ld_in, void* out,
+                                       int64_t ld_out, const void* logdet_in, void* logdet_out, int64_t B, void* stream) {
+    if (desc == nullptr || desc->abi_version != JF_ABI_VERSION) return JF_ERR_BAD_DESC;
+    if (desc->n_sub < 1 || desc->n_sub > JF_MAX_SUBPDFS) return JF_ERR_BAD_DESC;
+    if (B < 0 || (B > 0 && (in == nullptr || out == nullptr))) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (desc->dtype == JF_F64) return transform_target<double>(desc, to_embedding, in, ld_in, out, ld_out, logdet_in, logdet_out, B, st);
+    if (desc->dtype == JF_F32) return transform_target<float>(desc, to_embedding, in, ld_in, out, ld_out, logdet_in, logdet_out, B, st);
+    return JF_ERR_BAD_ARG;
+}
+
+extern "C" int jf_row_logmeanexp(int dtype, const void* in, int64_t rows, int64_t cols, void* out, void* stream) {
+    if (rows < 0 || cols < 1 || (rows > 0 && (in == nullptr || out == nullptr))) return JF_ERR_BAD_ARG;
+    if (rows == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t blocks = (rows * 32 + 255) / 256;
+    if (dtype == JF_F64) row_logmeanexp_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)in, rows, cols, (double*)out);
+    else if (dtype == JF_F32) row_logmeanexp_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)in, rows, cols, (float*)out);
+    else return JF_ERR_BAD_ARG;
+    return check_launch();
+}
+
 extern "C" int jf_abi_version(void) { return JF_ABI_VERSION; }
 extern "C" int64_t jf_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t jf_struct_size(int which) {

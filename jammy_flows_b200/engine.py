@@ -261,6 +261,108 @@ def pdf_sample(pdf, z, cond=None, chunk_rows=None):
     return x, logp, logp_base
 
 
+def pdf_transform_target(pdf, target, log_det=None, to_embedding=True):
+    """Charts of every sub-pdf in one launch: intrinsic -> embedding coordinates (to_embedding) or back.
+    Returns (new target, log_det [B]).  Reference: main/default.py:1737-1813, sphere_base.py:242-332."""
+    lib = _cabi.load()
+    _require_cuda(target, "target")
+    if target.dtype not in _DT:
+        raise TypeError("jammy_flows_b200 supports float32/float64, got %s" % target.dtype)
+    if target.stride(1) != 1:
+        target = target.contiguous()
+    B = target.shape[0]
+    dev, dt = target.device, target.dtype
+    n_in = pdf.total_target_dim_intrinsic if to_embedding else pdf.total_target_dim_embedded
+    n_out = pdf.total_target_dim_embedded if to_embedding else pdf.total_target_dim_intrinsic
+    assert target.shape[1] == n_in, (target.shape[1], n_in)
+    desc = pdf._desc(dt)
+    out = torch.empty(B, n_out, dtype=dt, device=dev)
+    ld_in = None
+    if torch.is_tensor(log_det):
+        ld_in = log_det.to(device=dev, dtype=dt).expand(B).contiguous()
+    ld_out = torch.empty(B, dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_pdf_transform_target(C.byref(desc), 1 if to_embedding else 0, _ptr(target), target.stride(0),
+                                         _ptr(out), n_out, _ptr(ld_in), _ptr(ld_out), B, _stream_ptr(dev))
+    _cabi.check(rc, "jf_pdf_transform_target")
+    if log_det is not None and not torch.is_tensor(log_det) and log_det != 0:
+        ld_out = ld_out + log_det
+    return out, ld_out
+
+
+def subpdf_logpdf(pdf, k, x_k, cond_segments, embedding_coordinates=False):
+    """log p_k(x_k | conditioning) [R] of ONE sub-pdf: its parameter generator (if any) on the column blocks
+    `cond_segments` = [conditional input] + embedded earlier targets, then its layer chain in the log_pdf direction.
+    x_k: [R, d_k] in default (intrinsic) coordinates, or in embedding coordinates when `embedding_coordinates` (the chart
+    and its log-det are then applied first).  This is one step of the reference's
+    `all_layer_inverse_individual_subdims` (main/default.py:2713-2901); used by the marginal entropies."""
+    lib = _cabi.load()
+    _require_cuda(x_k, "x")
+    dt, dev = x_k.dtype, x_k.device
+    R = x_k.shape[0]
+    desc = pdf._desc(dt)
+    st = _stream_ptr(dev)
+    chart_ld = None
+    if embedding_coordinates and pdf.pdf_defs_list[k][0] == "s":
+        one = _cabi.JfPdfDesc()
+        one.abi_version, one.dtype, one.n_sub = desc.abi_version, desc.dtype, 1
+        C.memmove(C.byref(one.sub[0]), C.byref(desc.sub[k]), C.sizeof(_cabi.JfSubPdfDesc))
+        d_k = desc.sub[k].dim
+        x_in = x_k.contiguous()
+        x_k = torch.empty(R, d_k, dtype=dt, device=dev)
+        chart_ld = torch.empty(R, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.jf_pdf_transform_target(C.byref(one), 0, _ptr(x_in), x_in.stride(0), _ptr(x_k), d_k, None,
+                                             _ptr(chart_ld), R, st)
+        _cabi.check(rc, "jf_pdf_transform_target")
+    x_k = x_k.contiguous() if x_k.stride(1) != 1 else x_k
+    pack = ParamPack(pdf, dt, dev)
+    n_par = desc.sub[k].n_params
+    if pdf.mlp_predictors[k] is None:
+        params, sp, sr = C.c_void_p(pack.c.shared[k]), 1, 0
+        keep = None
+    else:
+        segs = [s if s.stride(1) == 1 else s.contiguous() for s in cond_segments]
+        md = _cabi.JfMlpDesc()
+        C.memmove(C.byref(md), C.byref(desc.mlp[k]), C.sizeof(md))
+        md.n_segments = len(segs)
+        for i, sg in enumerate(segs):
+            assert sg.shape[0] == R and sg.dtype == dt
+            md.seg_cols[i] = sg.shape[1]
+        ptrs = (C.c_void_p * len(segs))(*[sg.data_ptr() for sg in segs])
+        lds = (C.c_int64 * len(segs))(*[sg.stride(0) for sg in segs])
+        keep = torch.empty(max(n_par, 1), R, dtype=dt, device=dev)          # param-major [P, R]
+        nws = lib.jf_mlp_workspace_bytes(C.byref(md), _DT[dt])
+        ws = torch.zeros(max(int(nws), 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.jf_mlp_forward_ws(C.byref(md), _DT[dt], ptrs, lds, pack.c.weights[k], pack.c.biases[k], _ptr(keep),
+                                       R, 1, R, _ptr(ws), nws, 0, st)
+        _cabi.check(rc, "jf_mlp_forward_ws")
+        params, sp, sr = _ptr(keep), R, 1
+    d_base = pdf.base_dim_indices[k][1] - pdf.base_dim_indices[k][0]
+    base = torch.empty(R, d_base, dtype=dt, device=dev)
+    logdet = torch.empty(R, dtype=dt, device=dev)
+    logbase = torch.empty(R, dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_apply(C.byref(desc.sub[k]), _DT[dt], _cabi.JF_DIR_LOGPDF, _ptr(x_k), x_k.stride(0), params, sp,
+                                 sr, _ptr(chart_ld), _ptr(logdet), None, _ptr(logbase), _ptr(base), d_base, None, 0, R,
+                                 _ptr(pdf._status(dev)), st)
+    _cabi.check(rc, "jf_subpdf_apply")
+    return logdet + logbase
+
+
+def row_logmeanexp(t):
+    """[R, S] -> [R]: log(mean(exp(row))) on the device (jf_row_logmeanexp)."""
+    lib = _cabi.load()
+    _require_cuda(t, "log-probabilities")
+    t = t.contiguous()
+    out = torch.empty(t.shape[0], dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        rc = lib.jf_row_logmeanexp(_DT[t.dtype], _ptr(t), t.shape[0], t.shape[1], _ptr(out), _stream_ptr(t.device))
+    _cabi.check(rc, "jf_row_logmeanexp")
+    return out
+
+
 def _host_call(pdf, direction, src, cond, chunk_rows, device):
     """HOST tensors in, HOST tensors out (pinned): the end-to-end path with copies inside the library call."""
     lib = _cabi.load()

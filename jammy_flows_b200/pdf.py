@@ -380,20 +380,28 @@ class pdf(nn.Module):
         assert (self.use_as_passthrough_instead_of_pdf == False)
         if amortization_parameters is not None or only_last:
             raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
-        if force_embedding_coordinates and self._needs_transform():
-            raise NotImplementedError("force_embedding_coordinates for manifold sub-pdfs (chart kernels K9) not built yet")
         if conditional_input is not None:
             assert (x.shape[0] == conditional_input.shape[0]), "Evaluating input x and condititional input shape must be similar!"
             assert (x.is_cuda == conditional_input.is_cuda), "input tensor *x* and *conditional_input* are on different devices"
             assert (self.conditional_input_dim == conditional_input.shape[1])
         else:
             assert self.conditional_input_dim is None, "conditional pdf requires conditional_input"
+        chart_log_det = None
+        if force_embedding_coordinates:
+            # reference main/default.py:906-909: embedding -> default coordinates first, its log-det joins the flow's
+            assert (x.shape[1] == self.total_target_dim_embedded), (x.shape[1], self.total_target_dim_embedded)
+            if self._needs_transform():
+                x, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=False)
+        elif force_intrinsic_coordinates:
+            assert (x.shape[1] == self.total_target_dim_intrinsic)
         assert (x.shape[1] == self.total_target_dim), (x.shape[1], self.total_target_dim)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad and engine.supports_backward(self):
             # training path: fused forward AND backward layer kernels, torch autograd only for the parameter generator
             return engine.pdf_logpdf_trainable(self, x, conditional_input)
         log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows)
+        if chart_log_det is not None:
+            log_pdf = log_pdf + chart_log_det
         if needs_grad:
             log_pdf, log_pdf_base, base_pos = _NoBackward.apply(self._anchor(), log_pdf, log_pdf_base, base_pos)
         return log_pdf, log_pdf_base, base_pos
@@ -401,6 +409,8 @@ class pdf(nn.Module):
     def all_layer_inverse(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
                           force_intrinsic_coordinates=False, only_last=False):
         """target -> base through every sub-pdf (reference main/default.py:879-1057)."""
+        if force_embedding_coordinates and self._needs_transform():
+            x, log_det = engine.pdf_transform_target(self, x, log_det, to_embedding=False)
         logp, logp_base, base = engine.pdf_logpdf(self, x, data_summary, chunk_rows=self.chunk_rows)
         return base, log_det + (logp - logp_base)
 
@@ -427,8 +437,6 @@ class pdf(nn.Module):
                        only_last=False):
         if amortization_parameters is not None or only_last:
             raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
-        if force_embedding_coordinates and self._needs_transform():
-            raise NotImplementedError("force_embedding_coordinates for manifold sub-pdfs (chart kernels K9) not built yet")
         if failsafe_crosscheck_tolerance:
             raise NotImplementedError("failsafe_crosscheck_tolerance (recheck_sampling) is not built yet")
         used_sample_size = samplesize
@@ -463,49 +471,114 @@ class pdf(nn.Module):
                 z = torch.randn(used_sample_size, self.total_base_dim, dtype=data_type, device=used_device, generator=gen)
             std_normal_samples = z
         x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows)
+        if force_embedding_coordinates and self._needs_transform():
+            # reference main/default.py:1522-1524: default -> embedding coordinates, log p = log N(z) - (logdet + chart)
+            x, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)
+            log_pdf = log_pdf - chart_log_det
         return x, std_normal_samples, log_pdf, log_gauss
 
     def all_layer_forward(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
                           force_intrinsic_coordinates=False, only_last=False):
         """base -> target through every sub-pdf (reference main/default.py:1373-1531)."""
         xs, logp, logp_base = engine.pdf_sample(self, x, data_summary, chunk_rows=self.chunk_rows)
-        return xs, log_det + (logp_base - logp)
+        log_det = log_det + (logp_base - logp)
+        if force_embedding_coordinates and self._needs_transform():
+            xs, log_det = engine.pdf_transform_target(self, xs, log_det, to_embedding=True)
+        return xs, log_det
 
     # ------------------------------------------------------------------------------------------------------------------
     # entropy, total path only (reference main/default.py:2263-2369)
     # ------------------------------------------------------------------------------------------------------------------
     def entropy(self, sub_manifolds=[-1], conditional_input=None, force_embedding_coordinates=True,
                 force_intrinsic_coordinates=False, samplesize=100, failsafe_crosscheck_tolerance=None, dtype=None,
-                device=None):
-        if list(sub_manifolds) != [-1]:
-            raise NotImplementedError("marginal entropies (SURVEY.md section 8f rank 2) are not built yet")
-        if self._needs_transform() and force_embedding_coordinates:
-            raise NotImplementedError("entropy in embedding coordinates for manifold sub-pdfs needs chart kernels (K9)")
+                device=None, _base_samples=None):
+        """Monte-Carlo entropies (reference main/default.py:2263-2454): "total" = -mean log p over `samplesize` samples
+        per conditional row; sub-manifold k: -mean_i log( mean_j p_k(x_k^i | x_<k^j) ), an S x S cross-evaluation of
+        sub-pdf k (`engine.subpdf_logpdf`) reduced on the device (`jf_row_logmeanexp`)."""
+        if failsafe_crosscheck_tolerance:
+            raise NotImplementedError("failsafe_crosscheck_tolerance (recheck_sampling) is not built yet")
+        for subdim in sub_manifolds:
+            if subdim != -1:
+                assert (subdim >= 0 and subdim < len(self.layer_list))
+        if force_embedding_coordinates == False:
+            print("#### CAUTION: Calculating entropy without forcing embedding coordinates. This might lead to undesired "
+                  "and wrong entropies when using manifold PDFs!#############")
         data_type, used_device = self.obtain_current_dtype_n_device()
         if device is not None:
             used_device = torch.device(device)
         if dtype is not None:
             data_type = dtype
+        S = samplesize
         if conditional_input is not None:
+            assert (self.conditional_input_dim is not None)
             data_type, used_device = conditional_input.dtype, conditional_input.device
-            cond = conditional_input.repeat_interleave(samplesize, dim=0)
-            n = cond.shape[0]
+            cond = conditional_input.repeat_interleave(S, dim=0)
+            batch = conditional_input.shape[0]
         else:
+            assert (self.conditional_input_dim is None), "We require conditional input, since this is a conditional PDF."
             cond = None
-            n = samplesize
+            batch = 1
+        n = S * batch
+        use_emb = bool(force_embedding_coordinates) and self._needs_transform()
+        out = dict()
         with torch.no_grad():
-            z = torch.randn(n, self.total_base_dim, dtype=data_type, device=used_device)   # reference :2914 (device RNG)
-            _, log_pdf, _ = engine.pdf_sample(self, z, cond, chunk_rows=self.chunk_rows)
-        return {"total": -log_pdf.reshape(-1, samplesize).mean(dim=1)}
+            if _base_samples is not None:      # test hook, like `predefined_target_input` of _obtain_sample
+                z = _base_samples
+                assert z.shape == (n, self.total_base_dim)
+            else:
+                z = torch.randn(n, self.total_base_dim, dtype=data_type, device=used_device)   # reference :2914 (device RNG)
+            x, log_pdf, _ = engine.pdf_sample(self, z, cond, chunk_rows=self.chunk_rows)
+            emb = x
+            if self._needs_transform():
+                emb, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)
+                if use_emb:
+                    log_pdf = log_pdf - chart_log_det
+            for sub_mf in sub_manifolds:
+                if sub_mf == -1:
+                    out["total"] = -log_pdf.reshape(-1, S).mean(dim=1)
+                    continue
+                e0, e1 = self.target_dim_indices_embedded[sub_mf]
+                t0, t1 = self.target_dim_indices[sub_mf]
+                x_k = emb[:, e0:e1] if use_emb else x[:, t0:t1]
+                if sub_mf == 0:
+                    lp = engine.subpdf_logpdf(self, 0, x_k, [cond] if cond is not None else [], use_emb)
+                    out[0] = -lp.reshape(-1, S).mean(dim=1)
+                    continue
+                prev = emb[:, :e0]
+                d_k = x_k.shape[1]
+                per_b = max(1, (1 << 19) // (S * S))          # conditional rows per launch: <= 2^19 cross rows
+                vals = []
+                for b0 in range(0, batch, per_b):
+                    b1 = min(batch, b0 + per_b)
+                    nb = b1 - b0
+                    rows = slice(b0 * S, b1 * S)
+                    # row (b, i, j): earlier targets and conditional input of sample j, sub-pdf k coordinates of sample i
+                    first = prev[rows].reshape(nb, S, e0).repeat(1, S, 1).reshape(-1, e0)
+                    final = x_k[rows].reshape(nb, S, d_k).repeat_interleave(S, dim=1).reshape(-1, d_k)
+                    segs = [first]
+                    if cond is not None:
+                        segs = [cond[rows].repeat_interleave(S, dim=0), first]
+                    lp = engine.subpdf_logpdf(self, sub_mf, final, segs, use_emb)
+                    vals.append(engine.row_logmeanexp(lp.reshape(-1, S)).reshape(nb, S).mean(dim=1))
+                out[sub_mf] = -torch.cat(vals)
+        return out
 
     # ------------------------------------------------------------------------------------------------------------------
     # coordinate transforms (reference main/default.py:1737-1813): identity for Euclidean-only pdfs
     # ------------------------------------------------------------------------------------------------------------------
     def transform_target_space(self, target, log_det=0, transform_from="default", transform_to="embedding"):
-        if self._needs_transform() and transform_from != transform_to and \
-                not (set([transform_from, transform_to]) == set(["default", "intrinsic"])):
-            raise NotImplementedError("embedding <-> intrinsic chart kernels (K9) are not built yet")
-        return target, log_det
+        """"default" coordinates are the intrinsic ones here (always_parametrize_in_embedding_space is not supported),
+        so only intrinsic <-> embedding moves anything; Euclidean and interval sub-pdfs are identities."""
+        for name in (transform_from, transform_to):
+            if name not in ("default", "intrinsic", "embedding"):
+                raise Exception("Unknown transformation space! .. ", name, "Allowed: default/intrinsic/embedding")
+        squeeze = target.dim() == 1
+        new_target = target.unsqueeze(0) if squeeze else target
+        src_emb, dst_emb = transform_from == "embedding", transform_to == "embedding"
+        assert (new_target.shape[1] == (self.total_target_dim_embedded if src_emb else self.total_target_dim_intrinsic))
+        if src_emb != dst_emb and self._needs_transform():
+            new_target, log_det = engine.pdf_transform_target(self, new_target, log_det, to_embedding=dst_emb)
+        return (new_target.squeeze(0) if squeeze else new_target), log_det
 
     # ------------------------------------------------------------------------------------------------------------------
     # plain-dict program for the test oracle (no CUDA involved)

@@ -1177,6 +1177,88 @@ class OraclePdf:
             if sp["permanent_param_names"] else torch.zeros(0, dtype=self.dtype)
         return vec.unsqueeze(0)
 
+    def transform_target(self, x, to_embedding):
+        """intrinsic <-> embedding charts of all sub-pdfs; returns (new x, chart log_det).
+        Reference: main/default.py:1737-1813, sphere_base.py:242-332, :796-841 (e / i sub-pdfs: identity)."""
+        x = torch.as_tensor(np.asarray(x)).to(self.dtype)
+        log_det = torch.zeros(x.shape[0], dtype=self.dtype)
+        out, col = [], 0
+        for sp in self.prog["subpdfs"]:
+            d = sp["target_cols"][1] - sp["target_cols"][0]
+            sphere = sp["manifold"] == "s"
+            n_in = d + (1 if (sphere and not to_embedding) else 0)
+            cur = x[:, col:col + n_in]
+            col += n_in
+            if sphere and d == 2:
+                cur, log_det = s2_to_embedding(cur, log_det) if to_embedding else s2_from_embedding(cur, log_det)
+            elif sphere and d == 1:
+                cur = torch.cat([torch.cos(cur), torch.sin(cur)], dim=1) if to_embedding else s1_from_embedding(cur)
+            out.append(cur)
+        return torch.cat(out, dim=1), log_det
+
+    def log_pdf_embedding(self, x_emb, cond=None):
+        """pdf.forward(..., force_embedding_coordinates=True).  Reference: main/default.py:906-909."""
+        x, ld = self.transform_target(x_emb, to_embedding=False)
+        logp, logp_base, base = self.log_pdf(x, cond)
+        return logp + ld, logp_base, base
+
+    def sample_embedding(self, z, cond=None):
+        """pdf._obtain_sample(..., force_embedding_coordinates=True).  Reference: main/default.py:1522-1524."""
+        x, logp, logp_base = self.sample(z, cond)
+        xe, ld = self.transform_target(x, to_embedding=True)
+        return xe, logp - ld, logp_base
+
+    def subpdf_log_pdf(self, k, x_k, cond, prev_emb):
+        """log p_k(x_k | cond, embedded earlier targets) of one sub-pdf (default coordinates).
+        Reference: one iteration of main/default.py:2783-2870 (all_layer_inverse_individual_subdims)."""
+        sp, layers = self.prog["subpdfs"][k], self.subs[k]
+        b = x_k.shape[0]
+        p = self._sub_params(k, cond, prev_emb, b)
+        log_det = torch.zeros(b, dtype=self.dtype)
+        cur = x_k
+        for li in reversed(range(len(layers))):
+            o0, o1 = sp["layer_param_ranges"][li]
+            cur, log_det = layers[li].inverse(cur, log_det, p[:, o0:o1])
+        return (-0.5 * cur ** 2 - LOG_SQRT_2PI).sum(dim=-1) + log_det
+
+    def entropy(self, z, cond, samplesize, sub_manifolds, embedding=True):
+        """pdf.entropy on given base normals z [batch*S, D] (cond: [batch, C] or None).
+        Reference: main/default.py:2263-2454 (total and marginal entropies)."""
+        S = samplesize
+        z = torch.as_tensor(np.asarray(z)).to(self.dtype)
+        cond = None if cond is None else torch.as_tensor(np.asarray(cond)).to(self.dtype)
+        cr = None if cond is None else cond.repeat_interleave(S, dim=0)
+        x, logp, _ = self.sample(z, cr)
+        subs = self.prog["subpdfs"]
+        out = {}
+
+        def chart(k, xk):
+            """-log sin(theta) of an S2 sub-pdf in embedding coordinates"""
+            if embedding and subs[k]["manifold"] == "s" and xk.shape[1] == 2:
+                return -torch.log(torch.sin(_safe_angle(xk[:, 0])))
+            return torch.zeros(xk.shape[0], dtype=self.dtype)
+
+        embs = [self.subs[k][-1].embedding(x[:, sp["target_cols"][0]:sp["target_cols"][1]]) for k, sp in enumerate(subs)]
+        for sm in sub_manifolds:
+            if sm == -1:
+                tot = logp + sum(chart(k, x[:, sp["target_cols"][0]:sp["target_cols"][1]]) for k, sp in enumerate(subs))
+                out["total"] = -tot.reshape(-1, S).mean(dim=1)
+                continue
+            t0, t1 = subs[sm]["target_cols"]
+            xk = x[:, t0:t1]
+            if sm == 0:
+                lp = self.subpdf_log_pdf(0, xk, cr, []) + chart(0, xk)
+                out[0] = -lp.reshape(-1, S).mean(dim=1)
+                continue
+            nb = x.shape[0] // S
+            rep_first = lambda t: t.reshape(nb, S, -1).repeat(1, S, 1).reshape(nb * S * S, -1)
+            final = xk.reshape(nb, S, -1).repeat_interleave(S, dim=1).reshape(nb * S * S, -1)
+            prev = [rep_first(e) for e in embs[:sm]]
+            crr = None if cr is None else cr.repeat_interleave(S, dim=0)
+            lp = (self.subpdf_log_pdf(sm, final, crr, prev) + chart(sm, final)).reshape(-1, S, S)
+            out[sm] = -(torch.logsumexp(lp, dim=-1) - math.log(float(S))).mean(dim=1)
+        return out
+
     def log_pdf(self, x, cond=None):
         x = torch.as_tensor(np.asarray(x)).to(self.dtype)
         cond = None if cond is None else torch.as_tensor(np.asarray(cond)).to(self.dtype)

@@ -159,6 +159,9 @@ CASES = {
     "g_e2_center_mean": dict(pdf_defs="e2", flow_defs="gg", n=300, perturb=0.3, opts={"g": {"center_mean": 1}}),
     "g_e2_center_mean_cond": dict(pdf_defs="e2", flow_defs="gg", n=300, cond_dim=2, perturb=0.2,
                                   opts={"g": {"center_mean": 1}}),
+    # force_embedding_coordinates (what pdf.entropy uses by default): charts before / after the chain
+    "emb_e2s2e2_cond": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=300, cond_dim=2, perturb=0.3, emb=True),
+    "emb_s1s2i1": dict(pdf_defs="s1+s2+i1", flow_defs="m+v+r", n=300, perturb=0.0, emb=True),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
@@ -204,6 +207,29 @@ def build_case(jf, name, spec):
         "ref_roundtrip_base_err": np.nanmax(np.abs((rt_base - z).numpy())),
         "ref_roundtrip_logp_err": np.nanmax(np.abs((rt_logp - samp_logp).numpy())),
     }
+    if spec.get("emb", False):
+        with torch.no_grad():
+            x_emb, _ = pdf.transform_target_space(x, 0.0, transform_from="default", transform_to="embedding")
+            logp_e, _, base_e = pdf(x_emb, conditional_input=cond, force_embedding_coordinates=True)
+            sx_e, _, slogp_e, _ = pdf._obtain_sample(conditional_input=cond, predefined_target_input=z,
+                                                     force_embedding_coordinates=True)
+        # entropies incl. marginal ones (main/default.py:2263-2454); the base normals are the global-RNG draw of
+        # all_layer_forward_individual_subdims_incl_sampling (:2914), reproduced here from the same seed
+        S, nb = 12, (3 if cond is not None else 1)
+        subs = [-1] + list(range(len(spec["pdf_defs"].split("+"))))
+        c_small = cond[:nb] if cond is not None else None
+        for flag, tag in ((True, "emb"), (False, "intr")):
+            torch.manual_seed(77)
+            with torch.no_grad():
+                ent = pdf.entropy(sub_manifolds=subs, conditional_input=c_small, samplesize=S,
+                                  force_embedding_coordinates=flag)
+            for k_, v_ in ent.items():
+                out["ent_%s_%s" % (tag, k_)] = v_.numpy()
+        torch.manual_seed(77)
+        out["ent_z"] = torch.randn(size=(S * nb, pdf.total_base_dim), dtype=dtype).numpy()
+        out["ent_S"] = np.int64(S)
+        out.update({"x_emb": x_emb.numpy(), "logp_emb": logp_e.numpy(), "base_emb": base_e.numpy(),
+                    "samp_x_emb": sx_e.numpy(), "samp_logp_emb": slogp_e.numpy()})
     if cond is not None:
         out["cond"] = cond.numpy()
     for k, v in pdf.state_dict().items():

@@ -106,3 +106,50 @@ def test_sample_matches_reference_golden(name, lib_built):
     st = p.kernel_status()
     if meta["dtype"] == "float64":
         assert st["unconverged"] == 0
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("emb_")])
+def test_embedding_coordinates_match_reference_golden(name, lib_built):
+    """force_embedding_coordinates in forward / _obtain_sample / entropy and pdf.transform_target_space
+    (reference main/default.py:906-913, :1522-1529, :1737-1813, :2263-2369) through the chart kernel."""
+    meta, data, p, t, cond = _cuda_model(name)
+    tol = REL_TOL[meta["dtype"]]
+    ref_rt = float(np.nan_to_num(data["ref_roundtrip_base_err"], nan=0.0))
+    with torch.no_grad():
+        xe, ld = p.transform_target_space(t(data["x"]), 0.0, transform_from="default", transform_to="embedding")
+        assert np.abs(xe.cpu().numpy() - data["x_emb"]).max() < 1e-14
+        back, ld2 = p.transform_target_space(t(data["x_emb"]), 0.0, transform_from="embedding", transform_to="intrinsic")
+        assert np.abs(back.cpu().numpy() - data["x"]).max() < 1e-7          # acos near the poles
+        assert torch.allclose(ld, -ld2, atol=1e-9)
+        logp, _, base = p(t(data["x_emb"]), conditional_input=cond, force_embedding_coordinates=True)
+        ok = np.isfinite(data["logp_emb"])
+        extra = 10 * ref_rt if "v" in meta["flow_defs"] else 0.0
+        assert rel_err(logp.cpu().numpy(), data["logp_emb"])[ok].max() < tol + extra
+        assert (np.abs(base.cpu().numpy() - data["base_emb"]).max(axis=1)[ok]
+                <= (base_tolerance(p, meta["dtype"], data["base_emb"]) + extra)[ok]).all()
+        x, _, slogp, _ = p._obtain_sample(conditional_input=cond, predefined_target_input=t(data["z"]),
+                                          force_embedding_coordinates=True)
+        assert x.shape[1] == p.total_target_dim_embedded
+        assert row_rel_err(x.cpu().numpy(), data["samp_x_emb"]).max() < max(tol, 10 * ref_rt)
+        assert rel_err(slogp.cpu().numpy(), data["samp_logp_emb"]).max() < max(tol, 10 * ref_rt)
+        # entropy (total): -mean log p over device-RNG samples, in embedding coordinates by default
+        torch.manual_seed(5)
+        n = 64
+        c_small = cond[:3] if cond is not None else None
+        ent = p.entropy(conditional_input=c_small, samplesize=n)["total"]
+        torch.manual_seed(5)
+        rows = n * (3 if cond is not None else 1)
+        z = torch.randn(rows, p.total_base_dim, dtype=base.dtype, device=base.device)
+        cr = c_small.repeat_interleave(n, dim=0) if cond is not None else None
+        _, _, lp, _ = p._obtain_sample(conditional_input=cr, predefined_target_input=z, force_embedding_coordinates=True)
+        assert torch.allclose(ent, -lp.reshape(-1, n).mean(dim=1), rtol=1e-12, atol=1e-12)
+        # marginal entropies against the reference, on the reference's own base normals
+        nb = 3 if cond is not None else 1
+        S = int(data["ent_S"])
+        subs = [-1] + list(range(len(meta["pdf_defs"].split("+"))))
+        for flag, tag in ((True, "emb"), (False, "intr")):
+            ent = p.entropy(sub_manifolds=subs, conditional_input=None if cond is None else cond[:nb], samplesize=S,
+                            force_embedding_coordinates=flag, _base_samples=t(data["ent_z"]))
+            for k_, v_ in ent.items():
+                ref = data["ent_%s_%s" % (tag, k_)]
+                assert rel_err(v_.cpu().numpy(), ref).max() < max(tol, 10 * ref_rt), (tag, k_)

@@ -32,3 +32,32 @@ def test_oracle_reproduces_reference(name):
     stol = max(tol, 10 * float(np.nan_to_num(data["ref_roundtrip_base_err"])))
     assert rel_err(xs.numpy(), data["samp_x"])[ok].max() < max(stol, 1e-9 if meta["dtype"] == "float64" else 1e-4)
     assert rel_err(slogp_base.numpy(), data["samp_logp_base"])[ok].max() < tol
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("emb_")])
+def test_oracle_embedding_coordinates(name):
+    """force_embedding_coordinates: charts before the log_pdf chain / after the sampling chain."""
+    meta, params, data = load_golden(name)
+    pdf = build_pdf(meta)
+    o = OraclePdf(pdf.export_program(meta["dtype"]), params)
+    cond = data.get("cond")
+    xe, _ = o.transform_target(data["x"], to_embedding=True)
+    assert np.abs(xe.numpy() - data["x_emb"]).max() < 1e-14
+    back, _ = o.transform_target(data["x_emb"], to_embedding=False)
+    assert np.abs(back.numpy() - data["x"]).max() < 1e-7          # acos near the poles
+    logp, _, base = o.log_pdf_embedding(data["x_emb"], cond)
+    assert rel_err(logp.numpy(), data["logp_emb"]).max() < 1e-12
+    assert rel_err(base.numpy(), data["base_emb"]).max() < 1e-12
+    xs, slogp, _ = o.sample_embedding(data["z"], cond)
+    stol = max(1e-9, 10 * float(data["ref_roundtrip_base_err"]))
+    assert rel_err(xs.numpy(), data["samp_x_emb"]).max() < stol
+    assert rel_err(slogp.numpy(), data["samp_logp_emb"]).max() < stol
+    # entropies (total + every marginal), both coordinate conventions, on the reference's own base normals
+    nb = 3 if cond is not None else 1
+    S = int(data["ent_S"])
+    subs = [-1] + list(range(len(meta["pdf_defs"].split("+"))))
+    for flag, tag in ((True, "emb"), (False, "intr")):
+        ent = o.entropy(data["ent_z"], None if cond is None else cond[:nb], S, subs, embedding=flag)
+        for k_, v_ in ent.items():
+            ref = data["ent_%s_%s" % (tag, k_)]
+            assert rel_err(v_.numpy(), ref).max() < max(1e-10, 10 * float(data["ref_roundtrip_base_err"])), (tag, k_)
