@@ -187,6 +187,37 @@ struct MixVal {
     T E;            // exp(-delta)
 };
 
+// softplus-threshold quirk terms (see above) for the kernels with a_k < -20: rare (a kernel more than 20 widths to the
+// right of x), so they are recomputed here, out of line, instead of riding along in the hot loop as predicated
+// instructions.  The reference uses r = 1 instead of rx in the cdf, pdf and sf terms; q = 1 - rx = e*rx <= 2e-9.
+#ifndef JF_QUIRK_OUTLINE
+#define JF_QUIRK_OUTLINE 0
+#endif
+template <typename T>
+__device__ __noinline__ void mix_quirk(const MixView<T>& mv, T x, T delta, T E, T& ex, T& qc, T& Sp) {
+#pragma unroll 1
+    for (int k = 0; k < mv.K; ++k) {
+        const T iw = mv_iw(mv, k);
+        const T a = (x - mv_m(mv, k)) * iw;
+        if (a < T(-20)) {
+            const T u = exp_neg(delta - fabs(a));
+            const T e = u * E;
+            const T rx = rcp_1to2(T(1) + e);
+            const T nq = mv_n(mv, k) * e * rx;
+            ex += nq;                                   // sf_ref - sf_exact
+            qc = fma(nq, u, qc);                        // cdf_ref - cdf_exact (rescaled like small_n)
+            Sp = fma(nq * u * iw, T(1) + rx, Sp);       // pdf_ref - pdf_exact
+        }
+    }
+}
+
+// x with the sign of -s (s != NaN): flips the sign bit of x when s >= 0
+JF_DEVINL double neg_if_nonneg(double x, double s) {
+    const int hs = __double2hiint(s);
+    return __hiloint2double(__double2hiint(x) ^ (~hs & 0x80000000), __double2loint(x));
+}
+JF_DEVINL float neg_if_nonneg(float x, float s) { return s >= 0.f ? -x : x; }
+
 // NEED_D: also accumulate the derivative of the pdf sum (only the sampling root finder uses it)
 template <typename T, bool NEED_D = true>
 JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
@@ -195,11 +226,15 @@ JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
     T delta = 0;
     if (all_neg || all_pos) {
         delta = Num<T>::big;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) delta = tmin(delta, fabs((x - mv_m(mv, k)) * mv_iw(mv, k)));
     }
     const T E = (delta > T(0)) ? exp_neg(-delta) : T(1);
     // four class sums instead of per-term selects: "big" = n*sigma(|a|), "small" = n*sigma(-|a|) (rescaled), by sign of a
     T big_p = 0, small_p = 0, big_n = 0, small_n = 0, Sp = 0, ex = 0, qc = 0, Sd = 0;
+#if JF_QUIRK_OUTLINE
+    T amin = 0;
+#endif
     JF_UNROLL_K
     for (int k = 0; k < K; ++k) {
         const T iw = mv_iw(mv, k), n = mv_n(mv, k);
@@ -213,10 +248,17 @@ JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
         else           { big_n += nr; small_n += nur; }
         if (NEED_D) {
             // d/dx of the pdf term: pt * (sigma(-a) - sigma(a)) / w = -+ pt * iw * rx * (1 - e)
+#if JF_QUIRK_OUTLINE
+            Sd += neg_if_nonneg(pt * iw * (rx - e * rx), a);
+#else
             const T dt = pt * iw * (rx - e * rx);
             Sd += (a >= T(0)) ? -dt : dt;
+#endif
         }
         Sp += pt;
+#if JF_QUIRK_OUTLINE
+        amin = tmin(amin, a);
+#else
         // softplus-threshold quirk (a < -20, rare: a kernel more than 20 widths to the right of x): the reference uses
         // r = 1 instead of rx in the cdf and pdf terms and in the sf term; q = 1 - rx = e*rx <= 2e-9
         if (a < T(-20)) {
@@ -225,7 +267,11 @@ JF_DEVINL MixVal<T> mix_eval(const MixView<T>& mv, T x) {
             qc = fma(nq, u, qc);                        // cdf_ref - cdf_exact (rescaled like small_n)
             Sp = fma(nq * u * iw, T(1) + rx, Sp);       // pdf_ref - pdf_exact
         }
+#endif
     }
+#if JF_QUIRK_OUTLINE
+    if (amin < T(-20)) mix_quirk<T>(mv, x, delta, E, ex, qc, Sp);
+#endif
     const T Sc = big_p + small_n + qc;
     const T Ss = small_p + big_n;
     MixVal<T> v;
@@ -341,9 +387,107 @@ struct LogitRoot {
     bool converged;
 };
 
+// fp32 pre-solve of L(x) = t (sampling direction, fp64 kernels only): up to three Halley steps with the mixture evaluated
+// in single precision on the FP32 / MUFU pipes (ex2.approx, rcp.approx, lg2.approx), which idle while the FP64 pipe is
+// the bound of this kernel.  Its result is only the STARTING POINT of the fp64 iteration below -- accuracy and the
+// acceptance test live entirely there -- but it lands within ~1e-6 widths of the root, so the fp64 loop needs one or
+// two mixture evaluations instead of three or four (measured, profiles/).  Anything non-finite falls back to x0.
+#ifndef JF_PRESOLVE_F32
+#define JF_PRESOLVE_F32 1
+#endif
+JF_DEVINL float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+JF_DEVINL float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+JF_DEVINL float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#ifndef JF_PRE_CVT
+#define JF_PRE_CVT 0      // 0: F2F.F32.F64 of the full double; 1: integer re-bias of the high word (20 mantissa bits)
+#endif
+#ifndef JF_PRE_ITERS
+#define JF_PRE_ITERS 3
+#endif
+#ifndef JF_PRE_BRACKET32
+#define JF_PRE_BRACKET32 0
+#endif
+// shared-memory double -> float for the pre-solve
+JF_DEVINL float lds_as_f32(unsigned addr) {
+#if JF_PRE_CVT
+    unsigned h;
+    asm("ld.shared.u32 %0, [%1+4];" : "=r"(h) : "r"(addr));
+    const unsigned ex = h & 0x7ff00000u;
+    const unsigned mag = (ex >= 0x38100000u && ex <= 0x47e00000u) ? (((h << 3) ^ 0x40000000u) & 0x7fffffffu) : 0u;
+    return __uint_as_float(mag | (h & 0x80000000u));
+#else
+    return (float)lds(addr, double());
+#endif
+}
+
+static __device__ __noinline__ double presolve_f32(const MixView<double>& mv, double t, double x0, double lo, double hi) {
+    const int K = mv.K;
+    const float tf = (float)t, lof = (float)lo, hif = (float)hi;
+    float x = (float)x0;
+#pragma unroll 1
+    for (int it = 0; it < JF_PRE_ITERS; ++it) {
+        float Sc = 0.f, Ss = 0.f, Sp = 0.f, Sd = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const float iw = lds_as_f32(mv.iw + k * mv.skb), n = lds_as_f32(mv.n + k * mv.skb);
+            const float a = (x - lds_as_f32(mv.m + k * mv.skb)) * iw;
+            const float e = ex2_approx(-fabsf(a) * 1.4426950408889634f);
+            const float r = rcp_approx(1.f + e);
+            const float nr = n * r, ner = nr * e;
+            const bool pos = a >= 0.f;
+            Sc += pos ? nr : ner;
+            Ss += pos ? ner : nr;
+            const float pt = ner * r * iw;
+            Sp += pt;
+            const float dt = pt * iw * (r - e * r);
+            Sd += pos ? -dt : dt;
+        }
+        const float ics = rcp_approx(Sc * Ss);
+        const float dy = Sp * ics;
+        const float f = (lg2_approx(Sc) - lg2_approx(Ss)) * 0.6931471805599453f - tf;
+        const float d2 = Sd * ics - dy * dy * (Ss - Sc);
+        const float den = 2.f * dy * dy - f * d2;
+        const float dx = (den > dy * dy) ? (2.f * f * dy * rcp_approx(den)) : (f * rcp_approx(dy));
+        const float xn = x - dx;
+        if (!(xn > lof && xn < hif)) break;      // also catches NaN: keep the last good point
+        x = xn;
+        if (fabsf(dx) <= 2e-6f * fabsf(x) + 1e-30f) break;
+    }
+    const double xr = (double)x;
+    return (xr > lo && xr < hi) ? xr : x0;
+}
+
+template <typename T> JF_DEVINL T presolve(const MixView<T>&, T, T x0, T, T) { return x0; }
+#if JF_PRESOLVE_F32
+template <> JF_DEVINL double presolve<double>(const MixView<double>& mv, double t, double x0, double lo, double hi) {
+    // the fp32 stage has no rescaling exponent: only where exp(-|t|) and the tails stay inside the fp32 range
+    return (fabs(t) < 60.0) ? presolve_f32(mv, t, x0, lo, hi) : x0;
+}
+#endif
+
 template <typename T>
 __device__ __noinline__ LogitRoot<T> solve_logit(const MixView<T>& mv, T t, bool use_ex) {
     T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0, wmin = Num<T>::big;
+    T bracket_eps = T(64) * Num<T>::eps;
+#if JF_PRESOLVE_F32 && JF_PRE_BRACKET32
+    if constexpr (sizeof(T) == 8) {
+        // the bracket only safeguards the iteration: single precision (padded accordingly) is enough
+        float lof = 1e30f, hif = -1e30f, xf = 0.f, wmaxf = 0.f, wminf = 1e30f;
+        const float tf = (float)t;
+        for (int k = 0; k < mv.K; ++k) {
+            const float m = lds_as_f32(mv.m + k * mv.skb), w = rcp_approx(lds_as_f32(mv.iw + k * mv.skb));
+            const float c = fmaf(tf, w, m);
+            lof = fminf(lof, c);
+            hif = fmaxf(hif, c);
+            xf = fmaf(lds_as_f32(mv.n + k * mv.skb), c, xf);
+            wmaxf = fmaxf(wmaxf, w);
+            wminf = fminf(wminf, w);
+        }
+        lo = lof; hi = hif; x = xf; wmax = wmaxf; wmin = wminf;
+        bracket_eps = T(1e-5);
+    } else
+#endif
+#pragma unroll 1
     for (int k = 0; k < mv.K; ++k) {
         const T m = mv_m(mv, k), w = rcp_pos(mv_iw(mv, k));
         const T c = fma(t, w, m);
@@ -354,13 +498,16 @@ __device__ __noinline__ LogitRoot<T> solve_logit(const MixView<T>& mv, T t, bool
         wmin = tmin(wmin, w);
     }
     {
-        const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
+        const T pad = T(1e-3) * wmax + bracket_eps * (fabs(lo) + fabs(hi));
         lo = tmax(lo - pad, T(-1e5));   // keep inside the reference's search interval
         hi = tmin(hi + pad, T(1e5));
         x = clampv(x, lo, hi);
     }
+    x = presolve<T>(mv, t, x, lo, hi);
     const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
-    const T early = (sizeof(T) == 8 ? T(1e-7) : T(1e-3));
+    // a third-order step of relative length s (in widths) lands within ~s^3 of the root, and log y' / log pdf carried to
+    // first order are off by ~s^2: 2e-6 -> 1e-17 / 4e-12 (fp64).  The fp32 pre-solve typically leaves s ~ 1e-6.
+    const T early = (sizeof(T) == 8 ? T(JF_PRESOLVE_F32 ? 2e-6 : 1e-7) : T(1e-3));
     LogitRoot<T> out;
     out.converged = false;
     out.evals = 0;
@@ -688,6 +835,22 @@ JF_DEVINL void mvn_layer_sample(T* x, T& logdet, const GfLayerC<T>& c, int d, co
 #pragma unroll
         for (int j = 0; j < d; ++j) x[j] += p[(int64_t)(c.raw_off + j) * sj];
     }
+}
+
+// out-of-line wrappers for the chain kernels: "t" layers are rare next to "g" layers and their code (regulators, logs)
+// would otherwise sit in the middle of the hot loop's instruction stream.  The row vector is copied so that the caller's
+// registers do not become an address-taken local array.
+template <typename T, int DM>
+__device__ __noinline__ void mvn_layer_cold(bool logpdf, T* xs, T* logdet, const GfLayerC<T>* c, int d, const T* p, int64_t sj) {
+    T x[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) x[j] = (j < d) ? xs[j] : T(0);
+    T ld = *logdet;
+    if (logpdf) mvn_layer_logpdf<T, DM>(x, ld, *c, d, p, sj);
+    else mvn_layer_sample<T, DM>(x, ld, *c, d, p, sj);
+#pragma unroll
+    for (int j = 0; j < DM; ++j) if (j < d) xs[j] = x[j];
+    *logdet = ld;
 }
 
 }  // namespace jf

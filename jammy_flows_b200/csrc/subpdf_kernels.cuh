@@ -50,7 +50,14 @@ __global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant_
             for (int j = 0; j < d; ++j) a.emb_out[row * a.ld_emb + j] = x[j];
         }
         for (int l = a.n_layers - 1; l >= 0; --l) {
-            if (g.layers[l].kind == 1) mvn_layer_logpdf<T, DM>(x, logdet, g.layers[l], d, prow, a.sj);
+            if (g.layers[l].kind == 1) {
+                T tmp[DM];
+#pragma unroll
+                for (int j = 0; j < d; ++j) tmp[j] = x[j];
+                mvn_layer_cold<T, DM>(true, tmp, &logdet, &g.layers[l], d, prow, a.sj);
+#pragma unroll
+                for (int j = 0; j < d; ++j) x[j] = tmp[j];
+            }
             else gf_layer_logpdf<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots);
         }
 #pragma unroll
@@ -60,7 +67,14 @@ __global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant_
         for (int j = 0; j < d; ++j) zsq = fma(x[j], x[j], zsq);
         int n_evals = 0, n_unconv = 0;
         for (int l = 0; l < a.n_layers; ++l) {
-            if (g.layers[l].kind == 1) mvn_layer_sample<T, DM>(x, logdet, g.layers[l], d, prow, a.sj);
+            if (g.layers[l].kind == 1) {
+                T tmp[DM];
+#pragma unroll
+                for (int j = 0; j < d; ++j) tmp[j] = x[j];
+                mvn_layer_cold<T, DM>(false, tmp, &logdet, &g.layers[l], d, prow, a.sj);
+#pragma unroll
+                for (int j = 0; j < d; ++j) x[j] = tmp[j];
+            }
             else gf_layer_sample<T, DM>(x, logdet, g.layers[l], d, g.layers[l].K, shared_params, tab, prow, a.sj, slots,
                                         n_evals, n_unconv);
         }

@@ -6,6 +6,12 @@ VARIANTS = {
     "unroll2": ["-DJF_K_UNROLL=2"],
     "estrin": ["-DJF_EXP_ESTRIN=1"],
     "unroll4": ["-DJF_K_UNROLL=4"],
+    "nopresolve": ["-DJF_PRESOLVE_F32=0"],
+    "quirk_inline": ["-DJF_QUIRK_OUTLINE=0"],
+    "pre_cvt": ["-DJF_PRE_CVT=1"],
+    "pre_it2": ["-DJF_PRE_ITERS=2"],
+    "pre_br32": ["-DJF_PRE_BRACKET32=1"],
+    "pre_br32_cvt": ["-DJF_PRE_BRACKET32=1", "-DJF_PRE_CVT=1"],
     "estrin_unroll4": ["-DJF_EXP_ESTRIN=1", "-DJF_K_UNROLL=4"],
 }
 d = os.path.join(B.PKG_DIR, "variants")
