@@ -276,17 +276,24 @@ class pdf(nn.Module):
     # The RNG call order is kept so that equal seeds give the reference's parameters.
     # ------------------------------------------------------------------------------------------------------------------
     def init_params(self, data=None, damping_factor=1000.0, mvn_min_max_sv_ratio=1e-4):
-        if data is not None:
-            raise NotImplementedError("data-driven initialisation (SURVEY.md section 8f rank 3) is not built yet")
+        from .init_fns import find_init_pars_of_chained_blocks
         with torch.no_grad():
+            if data is not None:
+                assert (data.shape[1] == self.total_target_dim), "Initialization with data must match the target dimension of the PDF!"
             params_list = []
+            this_dim_index = 0
             for subflow_index, subflow_description in enumerate(self.pdf_defs_list):
                 this_layer_list = self.layer_list[subflow_index]
+                this_dim = self.target_dims[subflow_index]
                 if "e" in subflow_description:
-                    # reference traverses the chain in reverse order (extra_functions.py:199)
-                    rev = [l.get_desired_init_parameters() for l in list(this_layer_list)[::-1]]
-                    params_list.append(torch.cat(rev[::-1]))
-                else:
+                    # Euclidean chains can be initialised from data (reference extra_functions.py:179-409)
+                    sub_data = data[:, this_dim_index:this_dim_index + this_dim] if data is not None else None
+                    params_list.append(find_init_pars_of_chained_blocks(this_layer_list, sub_data,
+                                                                        mvn_min_max_sv_ratio=mvn_min_max_sv_ratio))
+                    this_dim_index += this_dim
+                    continue
+                this_dim_index += this_dim
+                if True:
                     params_list.append(torch.cat([l.get_desired_init_parameters() for l in this_layer_list]))
             for ind, mlp_predictor in enumerate(self.mlp_predictors):
                 these_params = params_list[ind]

@@ -162,6 +162,9 @@ CASES = {
     # force_embedding_coordinates (what pdf.entropy uses by default): charts before / after the chain
     "emb_e2s2e2_cond": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=300, cond_dim=2, perturb=0.3, emb=True),
     "emb_s1s2i1": dict(pdf_defs="s1+s2+i1", flow_defs="m+v+r", n=300, perturb=0.0, emb=True),
+    # data-driven initialisation pdf.init_params(data=x) (extra_functions.py:179-409): state_dict AFTER the init
+    "init_e3_ggt_data": dict(pdf_defs="e3", flow_defs="ggt", n=400, data_init=True, opts={"t": {"cov_type": "full"}}),
+    "init_e2e2_cond_data": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=400, cond_dim=2, data_init=True),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
@@ -190,6 +193,13 @@ def build_case(jf, name, spec):
     if cond_dim is not None:
         cond = torch.randn(n, cond_dim, generator=gen, dtype=torch.float64).to(dtype)
     z = torch.randn(n, pdf.total_base_dim, generator=gen, dtype=torch.float64).to(dtype)
+    if spec.get("data_init", False):
+        torch.manual_seed(5)
+        np.random.seed(5)
+        # correlated, shifted data so that the PCA / percentile / covariance fits have something to find
+        mix = torch.randn(x.shape[1], x.shape[1], generator=gen, dtype=torch.float64)
+        x = (x @ mix + 0.7).to(dtype)
+        pdf.init_params(data=x)
     with torch.no_grad():
         logp, logp_base, base = pdf(x, conditional_input=cond)
         samp_x, _, samp_logp, samp_logp_base = pdf._obtain_sample(conditional_input=cond, predefined_target_input=z)
