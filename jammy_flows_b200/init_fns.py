@@ -110,7 +110,7 @@ def _push_through_g(layer, data, means, log_widths):
         pieces.append(torch.zeros(k * d, dtype=data.dtype))
     p = torch.cat([t.to(data.dtype).cpu() for t in pieces]).unsqueeze(0)
     dev = data.device if data.is_cuda else torch.device("cuda")
-    out, _ = tmp.inv_flow_mapping([data.to(dev).contiguous(), None], extra_inputs=p.to(dev))
+    out, _ = tmp.inv_flow_mapping([data.to(dev).contiguous(), 0.0], extra_inputs=p.to(dev))
     return out.to(data.device)
 
 

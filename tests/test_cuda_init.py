@@ -33,11 +33,11 @@ def test_data_init_matches_reference(name, lib_built):
                 h = lambda v: np.eye(len(v)) - 2 * np.outer(v, v) / (v @ v)
                 err = np.abs(h(v_got) - h(v_ref)).max()
                 worst = max(worst, err)
-                assert err < 1e-3, (k, err)
+                assert err < 1e-5, (k, err)
             continue
         err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
         worst = max(worst, err)
-        assert err < 1e-3, (k, err)
+        assert err < 1e-5, (k, err)
     print("\n%s: max parameter deviation from the reference init %.2e" % (name, worst))
     # the initialised flow describes the data: mean log-likelihood close to the reference's
     p = p.cuda()
