@@ -242,6 +242,15 @@ int jf_mlp_forward(const JfMlpDesc* desc, int dtype,
                    void* out, int64_t out_stride_param, int64_t out_stride_row,
                    int64_t B, void* stream);
 
+/* Same chain of Linear/tanh layers, optionally ACCUMULATING into `out` (out += result).  This is the building block of
+ * the reference's AmortizableMLP connectivity modes (amortizable_mlp.py:508-682: a sum of sub-MLP outputs and a linear
+ * highway, later sub-MLPs reading the running sum): the host composes the modes out of these calls. */
+int jf_mlp_forward_acc(const JfMlpDesc* desc, int dtype,
+                       const void* const* seg_ptrs, const int64_t* seg_ld,
+                       const void* const* weights, const void* const* biases,
+                       void* out, int64_t out_stride_param, int64_t out_stride_row,
+                       int64_t B, int accumulate, void* stream);
+
 /* Same, with caller-provided device workspace of jf_mlp_workspace_bytes(desc, dtype) bytes (0: none needed).  With a
  * workspace the fp64 one-hidden-layer (128) case runs on the tcgen05 tensor cores: the last-layer weights are split
  * once into int8 slices (kept in the workspace; `prepared` != 0 reuses the slices of the previous call, i.e. the same

@@ -91,6 +91,8 @@ SYMBOLS = {
     "jf_subpdf_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
     "jf_mlp_forward": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
                                  C.POINTER(_vp), _vp, _i64, _i64, _i64, _vp]),
+    "jf_mlp_forward_acc": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
+                                     C.POINTER(_vp), _vp, _i64, _i64, _i64, C.c_int, _vp]),
     "jf_mlp_workspace_bytes": (_i64, [C.POINTER(JfMlpDesc), C.c_int]),
     "jf_mlp_forward_ws": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
                                     C.POINTER(_vp), _vp, _i64, _i64, _i64, _vp, _i64, C.c_int, _vp]),

@@ -486,9 +486,11 @@ static int launch_mlp2_i8(const MlpArgs<float>& m, void* ws, int prepared, cudaS
 template <typename T>
 static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, const int64_t* seg_ld,
                          const void* const* weights, const void* const* biases, void* out, int64_t so_p, int64_t so_r,
-                         int64_t B, cudaStream_t st, void* ws = nullptr, int64_t ws_bytes = 0, int prepared = 0) {
+                         int64_t B, cudaStream_t st, void* ws = nullptr, int64_t ws_bytes = 0, int prepared = 0,
+                         int accumulate = 0) {
     MlpArgs<T> m;
     memset(&m, 0, sizeof(m));
+    m.acc = accumulate ? 1 : 0;
     m.n_linear = desc->n_linear;
     int maxd = 0, in_sum = 0;
     for (int l = 0; l <= desc->n_linear; ++l) {
@@ -512,10 +514,10 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
     }
     m.out = (T*)out; m.so_p = so_p; m.so_r = so_r; m.B = B;
     m.lda = maxd | 1;
-    if (ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
+    if (!accumulate && ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
         ws_bytes >= i8_ws_bytes(desc->dims[2], sizeof(T) == 8 ? JF_F64 : JF_F32))
         return launch_mlp2_i8(m, ws, prepared, st);
-    if (sizeof(T) == 8) {
+    if (sizeof(T) == 8 && !accumulate) {
         const int rc = try_mlp2_dmma(m, st);
         if (rc != JF_ERR_UNSUPPORTED) return rc;
     }
@@ -539,6 +541,24 @@ extern "C" int jf_mlp_forward(const JfMlpDesc* desc, int dtype, const void* cons
         return mlp_forward_t<double>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st);
     if (dtype == JF_F32)
         return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st);
+    return JF_ERR_BAD_ARG;
+}
+
+extern "C" int jf_mlp_forward_acc(const JfMlpDesc* desc, int dtype, const void* const* seg_ptrs, const int64_t* seg_ld,
+                                  const void* const* weights, const void* const* biases, void* out,
+                                  int64_t out_stride_param, int64_t out_stride_row, int64_t B, int accumulate,
+                                  void* stream) {
+    if (desc == nullptr || out == nullptr || seg_ptrs == nullptr || seg_ld == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_linear < 1 || desc->n_linear > JF_MAX_MLP_LINEAR) return JF_ERR_BAD_DESC;
+    if (desc->n_segments < 1 || desc->n_segments > JF_MAX_MLP_SEGMENTS) return JF_ERR_BAD_DESC;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return mlp_forward_t<double>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st,
+                                     nullptr, 0, 0, accumulate ? 1 : 0);
+    if (dtype == JF_F32)
+        return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st,
+                                    nullptr, 0, 0, accumulate ? 1 : 0);
     return JF_ERR_BAD_ARG;
 }
 

@@ -22,6 +22,7 @@ struct MlpArgs {
     T* out; int64_t so_p, so_r;       // out[j*so_p + row*so_r]
     int64_t B;
     int lda;                          // odd leading dimension of the activation tiles
+    int acc;                          // generic kernel only: out += result instead of out = result
 };
 
 constexpr int kMlpTN = 64;   // output columns per pass
@@ -104,7 +105,10 @@ __global__ void __launch_bounds__(256) mlp_kernel(const __grid_constant__ MlpArg
                     const int n = n0 + ty * 4 + c;
                     if (n >= N) continue;
                     if (last) {
-                        if (row < m.B) m.out[(int64_t)n * m.so_p + row * m.so_r] = acc[i][c];
+                        if (row < m.B) {
+                            T* o = m.out + (int64_t)n * m.so_p + row * m.so_r;
+                            *o = m.acc ? (*o + acc[i][c]) : acc[i][c];
+                        }
                     } else {
                         dst[(size_t)r * m.lda + n] = tanh(acc[i][c]);
                     }

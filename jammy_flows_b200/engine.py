@@ -156,7 +156,7 @@ def compile_pdf(pdf, dtype):
         d.emb_dim[k] = layers[-1]._embedding_conditional_return_num()
         mlp = pdf.mlp_predictors[k]
         d.has_mlp[k] = 0 if mlp is None else 1
-        if mlp is not None:
+        if mlp is not None and not hasattr(mlp, "u_v_b_pars"):      # AmortizableMLP: composed on the host (staged path)
             linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
             if len(linears) > _cabi.JF_MAX_MLP_LINEAR:
                 raise NotImplementedError("MLP deeper than %d Linear layers" % _cabi.JF_MAX_MLP_LINEAR)
@@ -183,6 +183,8 @@ class ParamPack:
                     _require_cuda(vec, "parameters of sub-pdf %d" % k)
                     self.keep.append(vec)
                     self.c.shared[k] = vec.data_ptr()
+            elif hasattr(mlp, "u_v_b_pars"):
+                continue
             else:
                 linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
                 for i, lin in enumerate(linears):
@@ -215,8 +217,121 @@ def _prep_inputs(pdf, t, cond, what):
     return t, cond
 
 
+def uses_custom_mlp(pdf):
+    return any(m is not None and hasattr(m, "u_v_b_pars") for m in pdf.mlp_predictors)
+
+
+def _run_chain(lib, dt, dev, layers_wb, segs, out, so_p, so_r, R, accumulate):
+    """one Linear/tanh chain with dense weights [(W, b)] on column blocks `segs` -> out (optionally +=)."""
+    md = _cabi.JfMlpDesc()
+    md.n_linear = len(layers_wb)
+    md.dims[0] = layers_wb[0][0].shape[1]
+    for i, (w, _) in enumerate(layers_wb):
+        md.dims[i + 1] = w.shape[0]
+    if md.n_linear > _cabi.JF_MAX_MLP_LINEAR or len(segs) > _cabi.JF_MAX_MLP_SEGMENTS:
+        raise NotImplementedError("MLP chain deeper than %d layers / more than %d input blocks"
+                                  % (_cabi.JF_MAX_MLP_LINEAR, _cabi.JF_MAX_MLP_SEGMENTS))
+    md.n_segments = len(segs)
+    for i, sg in enumerate(segs):
+        md.seg_cols[i] = sg.shape[1]
+    assert sum(sg.shape[1] for sg in segs) == md.dims[0], ([sg.shape for sg in segs], md.dims[0])
+    ptrs = (C.c_void_p * len(segs))(*[sg.data_ptr() for sg in segs])
+    lds = (C.c_int64 * len(segs))(*[sg.stride(0) for sg in segs])
+    ws = (C.c_void_p * len(layers_wb))(*[w.data_ptr() for w, _ in layers_wb])
+    bs = (C.c_void_p * len(layers_wb))(*[b.data_ptr() for _, b in layers_wb])
+    with torch.cuda.device(dev):
+        rc = lib.jf_mlp_forward_acc(C.byref(md), _DT[dt], ptrs, lds, ws, bs, _ptr(out), so_p, so_r, R,
+                                    1 if accumulate else 0, _stream_ptr(dev))
+    _cabi.check(rc, "jf_mlp_forward_acc")
+
+
+def custom_mlp_forward(mlp, segs, R):
+    """AmortizableMLP (permanent parameters) on the column blocks `segs` -> [R, output_dim] row-major.
+    The connectivity modes (reference amortizable_mlp.py:586-682) are composed from accumulating chain launches:
+    out = highway(x); out += chain_0(x); out += chain_i(x | out | [x, out]) for the later chains."""
+    lib = _cabi.load()
+    segs = [s if s.stride(1) == 1 else s.contiguous() for s in segs]
+    for s_ in segs:
+        _require_cuda(s_, "MLP input")
+    dt, dev = segs[0].dtype, segs[0].device
+    chains, hw = mlp.dense_weights(dt, dev)
+    P = mlp.output_dim
+    out = torch.empty(R, P, dtype=dt, device=dev)
+    started = False
+    if hw is not None:
+        _run_chain(lib, dt, dev, hw, segs, out, 1, P, R, False)
+        started = True
+    for ci, ch in enumerate(chains):
+        if ci == 0 or mlp.highway_mode <= 2:
+            inp = segs
+        elif mlp.highway_mode == 3:
+            inp = [out]
+        else:
+            inp = segs + [out]
+        # a CTA gathers the input rows it owns before it writes them, so reading `out` while accumulating into it is safe
+        _run_chain(lib, dt, dev, ch, inp, out, 1, P, R, started)
+        started = True
+    if not started:
+        out.zero_()
+    return out
+
+
+def _pdf_staged(pdf, src, cond, direction):
+    """Per-sub-pdf orchestration on the host: parameter generator (nn.Sequential or AmortizableMLP) -> layer chain, the
+    embedding of each sub-pdf's target feeding the later generators (reference main/default.py:931-1053 / :1413-1514).
+    Used when a generator is an AmortizableMLP, which the single-call C entries do not describe."""
+    lib = _cabi.load()
+    src, cond = _prep_inputs(pdf, src, cond, "input")
+    R = src.shape[0]
+    dt, dev = src.dtype, src.device
+    desc = pdf._desc(dt)
+    pack = ParamPack(pdf, dt, dev)
+    status = pdf._status(dev)
+    logpdf = direction == _cabi.JF_DIR_LOGPDF
+    dst = torch.empty(R, pdf.total_base_dim if logpdf else pdf.total_target_dim, dtype=dt, device=dev)
+    logdet = torch.empty(R, dtype=dt, device=dev)
+    logbase = torch.empty(R, dtype=dt, device=dev)
+    prev, keep = [], []
+    for k, layers in enumerate(pdf.layer_list):
+        mlp = pdf.mlp_predictors[k]
+        segs = ([cond] if cond is not None else []) + prev
+        n_par = desc.sub[k].n_params
+        if mlp is None:
+            params, sp, sr = C.c_void_p(pack.c.shared[k]), 1, 0
+        elif hasattr(mlp, "u_v_b_pars"):
+            buf = custom_mlp_forward(mlp, segs, R)
+            keep.append(buf)
+            params, sp, sr = _ptr(buf), 1, n_par
+        else:
+            linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
+            wb = [(pack_w, pack_b) for pack_w, pack_b in
+                  ((l.weight.detach().to(device=dev, dtype=dt).contiguous(), l.bias.detach().to(device=dev, dtype=dt).contiguous())
+                   for l in linears)]
+            buf = torch.empty(max(n_par, 1), R, dtype=dt, device=dev)
+            keep += [buf, wb]
+            _run_chain(lib, dt, dev, wb, segs, buf, R, 1, R, False)
+            params, sp, sr = _ptr(buf), R, 1
+        t0, t1 = pdf.target_dim_indices[k]
+        b0, b1 = pdf.base_dim_indices[k]
+        (i0, i1), (o0, o1) = ((t0, t1), (b0, b1)) if logpdf else ((b0, b1), (t0, t1))
+        v_in, v_out = src[:, i0:i1], dst[:, o0:o1]
+        emb = torch.empty(R, layers[-1]._embedding_conditional_return_num(), dtype=dt, device=dev)
+        first = k == 0
+        with torch.cuda.device(dev):
+            rc = lib.jf_subpdf_apply(C.byref(desc.sub[k]), _DT[dt], direction, _ptr(v_in), src.stride(0), params, sp, sr,
+                                     None if first else _ptr(logdet), _ptr(logdet), None if first else _ptr(logbase),
+                                     _ptr(logbase), _ptr(v_out), dst.stride(0), _ptr(emb), emb.shape[1], R,
+                                     _ptr(status), _stream_ptr(dev))
+        _cabi.check(rc, "jf_subpdf_apply")
+        prev.append(emb)
+    return dst, logdet, logbase
+
+
 def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True):
     """-> (log_pdf [B], log_pdf_base [B], base [B, D_base]) on x's device.  Reference: main/default.py:1059-1117."""
+    if uses_custom_mlp(pdf):
+        base, logdet, logbase = _pdf_staged(pdf, x, cond, _cabi.JF_DIR_LOGPDF)
+        return logdet + logbase, logbase, base
     lib = _cabi.load()
     x, cond = _prep_inputs(pdf, x, cond, "x")
     B = x.shape[0]
@@ -240,6 +355,9 @@ def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True):
 
 def pdf_sample(pdf, z, cond=None, chunk_rows=None):
     """z [B, D_base] -> (x [B, D], log_pdf [B], log_pdf_base [B]).  Reference: main/default.py:1373-1531, :1533-1707."""
+    if uses_custom_mlp(pdf):
+        xs, logdet, logbase = _pdf_staged(pdf, z, cond, _cabi.JF_DIR_SAMPLE)
+        return xs, logbase - logdet, logbase
     lib = _cabi.load()
     z, cond = _prep_inputs(pdf, z, cond, "base sample")
     B = z.shape[0]

@@ -50,8 +50,6 @@ class pdf(nn.Module):
         """Same parameters as the reference constructor (main/default.py:44-100)."""
         super().__init__()
         not_built = []
-        if amortization_mlp_use_custom_mode:
-            not_built.append("amortization_mlp_use_custom_mode (AmortizableMLP, SURVEY.md section 8f rank 4)")
         if amortize_everything:
             not_built.append("amortize_everything (fully amortized pdf, section 8f rank 4)")
         if predict_log_normalization:
@@ -150,6 +148,10 @@ class pdf(nn.Module):
             raise Exception("Hidden MLP dimensions must be defined either str or list, received ",
                             type(self.amortization_mlp_dims))
         self.amortization_mlp_ranks = amortization_mlp_ranks
+        if type(self.amortization_mlp_ranks) in (int, str):
+            self.amortization_mlp_ranks = [self.amortization_mlp_ranks] * len(self.pdf_defs_list)
+        elif type(self.amortization_mlp_ranks) != list:
+            raise Exception("Rank of MLP sub pdfs has to defined as an int or list type!")
         if len(self.amortization_mlp_dims) != len(self.pdf_defs_list):
             raise Exception("hidden mlp dimension definitions for sub pdfs is wrong length (%d) .. requires length (%d)"
                             % (len(self.amortization_mlp_dims), len(self.pdf_defs_list)))
@@ -260,6 +262,15 @@ class pdf(nn.Module):
             if self.conditional_input_dim is not None:
                 this_summary_dim += self.conditional_input_dim
             hidden = list_from_str(self.amortization_mlp_dims[pdf_index])
+            if self.amortization_mlp_use_custom_mode:
+                # reference main/default.py:643-651: AmortizableMLP with permanent parameters
+                from .amortizable_mlp import AmortizableMLP
+                self.mlp_predictors.append(AmortizableMLP(
+                    this_summary_dim, hidden, num_predicted_pars,
+                    low_rank_approximations=self.amortization_mlp_ranks[pdf_index], use_permanent_parameters=True,
+                    highway_mode=self.amortization_mlp_highway_mode, svd_mode="smart"))
+                prev_extra_input_num += emb_num
+                continue
             mlp_in_dims = [this_summary_dim] + hidden
             mlp_out_dims = hidden + [num_predicted_pars]
             nn_list = []
@@ -299,7 +310,10 @@ class pdf(nn.Module):
                 these_params = params_list[ind]
                 if len(these_params) == 0:
                     continue
-                if mlp_predictor is not None:
+                if mlp_predictor is not None and hasattr(mlp_predictor, "initialize_uvbs"):
+                    # custom low-rank MLPs initialise themselves (reference main/default.py:1896-1904)
+                    mlp_predictor.initialize_uvbs(fix_final_bias=these_params, prev_damping_factor=damping_factor)
+                elif mlp_predictor is not None:
                     for internal_layer in mlp_predictor:
                         if hasattr(internal_layer, "weight"):
                             nn.init.kaiming_uniform_(internal_layer.weight.data, a=numpy.sqrt(5))
@@ -600,7 +614,9 @@ class pdf(nn.Module):
             mlp = self.mlp_predictors[k]
             mlp_spec = None
             names = []
-            if mlp is not None:
+            if mlp is not None and hasattr(mlp, "u_v_b_pars"):
+                mlp_spec = mlp.structure()
+            elif mlp is not None:
                 mlp_spec = dict(linear_indices=[i for i, m in enumerate(mlp) if isinstance(m, nn.Linear)])
             else:
                 for li, l in enumerate(layers):

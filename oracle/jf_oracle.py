@@ -1158,6 +1158,8 @@ class OraclePdf:
     def _mlp(self, k, inp):
         """nn.Sequential(Linear, Tanh, ..., Linear).  Reference: main/default.py:654-670."""
         m = self.prog["subpdfs"][k]["mlp"]
+        if m.get("custom", False):
+            return self._custom_mlp(m, self.params["mlp_predictors.%d.u_v_b_pars" % k], inp)
         h = inp
         for li, idx in enumerate(m["linear_indices"]):
             w = self.params["mlp_predictors.%d.%d.weight" % (k, idx)]
@@ -1166,6 +1168,52 @@ class OraclePdf:
             if li < len(m["linear_indices"]) - 1:
                 h = torch.tanh(h)
         return h
+
+    @staticmethod
+    def _custom_mlp(m, flat, x):
+        """AmortizableMLP with permanent parameters.  Reference: amortizable_mlp.py:508-682 (U (V^T x) for factorised
+        layers, connectivity modes 0-4)."""
+        flat = flat.reshape(-1)
+
+        def chain(spec, pars, inp):
+            h, pos = inp, 0
+            n = len(spec["layers"])
+            for i, l in enumerate(spec["layers"]):
+                u = pars[pos:pos + l["n_u"]]
+                pos += l["n_u"]
+                v = pars[pos:pos + l["n_v"]]
+                pos += l["n_v"]
+                b = pars[pos:pos + l["n_b"]]
+                pos += l["n_b"]
+                if l["full"]:
+                    h = torch.einsum("ij,bj->bi", u.view(l["n_out"], l["n_in"]), h)
+                else:
+                    mid = torch.einsum("ij,bj->bi", v.view(l["rank"], l["n_in"]), h)
+                    h = torch.einsum("ij,bj->bi", u.view(l["n_out"], l["rank"]), mid)
+                if l["n_b"] > 0:
+                    h = h + b
+                if i < n - 1:
+                    h = torch.tanh(h)
+            return h
+
+        mode = m["highway_mode"]
+        prev = 0.0
+        if mode > 0:
+            hw = m["highway"]
+            prev = chain(hw, flat[-hw["num_params"]:], x)
+        pos = 0
+        nxt = x
+        for ci, ch in enumerate(m["chains"]):
+            nonlinear = chain(ch, flat[pos:pos + ch["num_params"]], x if ci == 0 else nxt)
+            pos += ch["num_params"]
+            if mode == 3:
+                nxt = prev + nonlinear
+            elif mode == 4:
+                nxt = torch.cat([x, prev + nonlinear], dim=1)
+            else:
+                nxt = x
+            prev = prev + nonlinear
+        return prev
 
     def _sub_params(self, k, cond, prev_emb, batch):
         sp = self.prog["subpdfs"][k]

@@ -165,6 +165,23 @@ CASES = {
     # data-driven initialisation pdf.init_params(data=x) (extra_functions.py:179-409): state_dict AFTER the init
     "init_e3_ggt_data": dict(pdf_defs="e3", flow_defs="ggt", n=400, data_init=True, opts={"t": {"cov_type": "full"}}),
     "init_e2e2_cond_data": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=400, cond_dim=2, data_init=True),
+    # AmortizableMLP parameter generators (amortization_mlp_use_custom_mode, amortizable_mlp.py): low-rank factors and
+    # the five connectivity modes; dims/ranks as in the reference's own sweep (tests/test_general.py:302-304)
+    "amlp_e2e2_cond_mode0": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=300, cond_dim=3, perturb=0.05,
+                                 pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
+                                             amortization_mlp_ranks="2-10-1000")),
+    "amlp_e2s2_mode1": dict(pdf_defs="e2+s2", flow_defs="gg+f", n=300, perturb=0.05,
+                            pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
+                                        amortization_mlp_ranks="2-10-1000-3", amortization_mlp_highway_mode=1)),
+    "amlp_e2e2_cond_mode2": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=300, cond_dim=3, perturb=0.05,
+                                 pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
+                                             amortization_mlp_ranks="2-10-5-0-4", amortization_mlp_highway_mode=2)),
+    "amlp_e2e2_cond_mode3": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=300, cond_dim=3, perturb=0.05,
+                                 pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
+                                             amortization_mlp_ranks="2-10-5-0-4", amortization_mlp_highway_mode=3)),
+    "amlp_e2e2_cond_mode4": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=300, cond_dim=3, perturb=0.05,
+                                 pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
+                                             amortization_mlp_ranks=0, amortization_mlp_highway_mode=4)),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
@@ -179,7 +196,8 @@ def build_case(jf, name, spec):
     dtype = getattr(torch, spec.get("dtype", "float64"))
     opts = spec.get("opts", {})
     cond_dim = spec.get("cond_dim", None)
-    pdf = jf.pdf(spec["pdf_defs"], spec["flow_defs"], options_overwrite=opts, conditional_input_dim=cond_dim)
+    pdf = jf.pdf(spec["pdf_defs"], spec["flow_defs"], options_overwrite=opts, conditional_input_dim=cond_dim,
+                 **spec.get("pdf_kw", {}))
     pdf = pdf.to(dtype)
     gen = torch.Generator().manual_seed(1234)
     if spec.get("perturb", 0.0) > 0:
@@ -209,6 +227,7 @@ def build_case(jf, name, spec):
         "meta": json.dumps(dict(name=name, pdf_defs=spec["pdf_defs"], flow_defs=spec["flow_defs"],
                                 options_overwrite={str(k): v for k, v in opts.items()},
                                 conditional_input_dim=cond_dim, dtype=spec.get("dtype", "float64"),
+                                pdf_kw=spec.get("pdf_kw", {}),
                                 perturb=spec.get("perturb", 0.0), seed=seed,
                                 reference="thoglu/jammy_flows v1.1.0 @ /root/reference, torch %s CPU" % torch.__version__)),
         "x": x.numpy(), "z": z.numpy(),

@@ -42,7 +42,7 @@ def build_pdf(meta, params=None, seed=None):
         torch.manual_seed(seed)
         np.random.seed(seed)
     p = jfb.pdf(meta["pdf_defs"], meta["flow_defs"], options_overwrite=_opts(meta),
-                conditional_input_dim=meta["conditional_input_dim"])
+                conditional_input_dim=meta["conditional_input_dim"], **meta.get("pdf_kw", {}))
     p = p.to(getattr(torch, meta["dtype"]))
     if params is not None:
         sd = {k: torch.from_numpy(np.asarray(v)) for k, v in params.items()}
