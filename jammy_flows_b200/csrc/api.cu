@@ -1,5 +1,8 @@
 // C-ABI entry points of libjammy_b200.so (see include/jammy_b200.h).  Host-side dispatch only; all math is in the
 // kernels.  Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+// exp() coefficients as immediates in this unit: measured, the tcgen05 MLP prologue (tanh) is faster that way, while the
+// "g" chain kernels (gf_inst_*.cu) gain 2-5 % from constant-bank operands (profiles/ncu_r01_final.md)
+#define JF_EXP_CONST 0
 #include <atomic>
 #include <cstdio>
 #include <cstring>

@@ -7,6 +7,7 @@ VARIANTS = {
     "estrin": ["-DJF_EXP_ESTRIN=1"],
     "unroll4": ["-DJF_K_UNROLL=4"],
     "nopresolve": ["-DJF_PRESOLVE_F32=0"],
+    "exp_imm": ["-DJF_EXP_CONST=0"],
     "quirk_inline": ["-DJF_QUIRK_OUTLINE=0"],
     "pre_cvt": ["-DJF_PRE_CVT=1"],
     "pre_it2": ["-DJF_PRE_ITERS=2"],
