@@ -404,6 +404,9 @@ JF_DEVINL float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" 
 #ifndef JF_PRE_ITERS
 #define JF_PRE_ITERS 3
 #endif
+#ifndef JF_PRE_STOP
+#define JF_PRE_STOP 4e-3
+#endif
 #ifndef JF_PRE_BRACKET32
 #define JF_PRE_BRACKET32 0
 #endif
@@ -420,9 +423,12 @@ JF_DEVINL float lds_as_f32(unsigned addr) {
 #endif
 }
 
-static __device__ __noinline__ double presolve_f32(const MixView<double>& mv, double t, double x0, double lo, double hi) {
+static __device__ __noinline__ double presolve_f32(const MixView<double>& mv, double t, double x0, double lo, double hi, double wmin) {
     const int K = mv.K;
     const float tf = (float)t, lof = (float)lo, hif = (float)hi;
+    // a third-order step of length dx leaves an error ~dx^3/w^2: below JF_PRE_STOP widths the next point is already at
+    // the single-precision floor and a confirming evaluation would be wasted
+    const float stop = (float)(JF_PRE_STOP * wmin);
     float x = (float)x0;
 #pragma unroll 1
     for (int it = 0; it < JF_PRE_ITERS; ++it) {
@@ -451,17 +457,17 @@ static __device__ __noinline__ double presolve_f32(const MixView<double>& mv, do
         const float xn = x - dx;
         if (!(xn > lof && xn < hif)) break;      // also catches NaN: keep the last good point
         x = xn;
-        if (fabsf(dx) <= 2e-6f * fabsf(x) + 1e-30f) break;
+        if (fabsf(dx) <= stop) break;
     }
     const double xr = (double)x;
     return (xr > lo && xr < hi) ? xr : x0;
 }
 
-template <typename T> JF_DEVINL T presolve(const MixView<T>&, T, T x0, T, T) { return x0; }
+template <typename T> JF_DEVINL T presolve(const MixView<T>&, T, T x0, T, T, T) { return x0; }
 #if JF_PRESOLVE_F32
-template <> JF_DEVINL double presolve<double>(const MixView<double>& mv, double t, double x0, double lo, double hi) {
+template <> JF_DEVINL double presolve<double>(const MixView<double>& mv, double t, double x0, double lo, double hi, double wmin) {
     // the fp32 stage has no rescaling exponent: only where exp(-|t|) and the tails stay inside the fp32 range
-    return (fabs(t) < 60.0) ? presolve_f32(mv, t, x0, lo, hi) : x0;
+    return (fabs(t) < 60.0) ? presolve_f32(mv, t, x0, lo, hi, wmin) : x0;
 }
 #endif
 
@@ -503,7 +509,7 @@ __device__ __noinline__ LogitRoot<T> solve_logit(const MixView<T>& mv, T t, bool
         hi = tmin(hi + pad, T(1e5));
         x = clampv(x, lo, hi);
     }
-    x = presolve<T>(mv, t, x, lo, hi);
+    x = presolve<T>(mv, t, x, lo, hi, wmin);
     const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
     // a third-order step of relative length s (in widths) lands within ~s^3 of the root, and log y' / log pdf carried to
     // first order are off by ~s^2: 2e-6 -> 1e-17 / 4e-12 (fp64).  The fp32 pre-solve typically leaves s ~ 1e-6.

@@ -7,6 +7,8 @@ VARIANTS = {
     "estrin": ["-DJF_EXP_ESTRIN=1"],
     "unroll4": ["-DJF_K_UNROLL=4"],
     "nopresolve": ["-DJF_PRESOLVE_F32=0"],
+    "stop0": ["-DJF_PRE_STOP=1e-6"],
+    "stop2e2": ["-DJF_PRE_STOP=2e-2"],
     "exp_imm": ["-DJF_EXP_CONST=0"],
     "quirk_inline": ["-DJF_QUIRK_OUTLINE=0"],
     "pre_cvt": ["-DJF_PRE_CVT=1"],
