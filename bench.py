@@ -25,6 +25,16 @@ sys.path.insert(0, ROOT)
 # to stdout as well, so it is silenced unless explicitly kept
 if os.environ.get("JF_KEEP_NCCL_DEBUG") is None:
     os.environ["NCCL_DEBUG"] = "WARN"
+# ... and because NCCL still prints its version line at WARN level (seen on the 2-GPU runs), everything that lands on
+# file descriptor 1 during the run is sent to stderr; the JSON line is written to the saved descriptor at the end
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -186,7 +196,7 @@ def run_reference_arm(args, rank, world):
                 logpdf_evals_per_s=cb["logpdf_evals_per_s"], samples_per_s=cb["samples_per_s"],
                 e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -443,7 +453,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     if cb is not None:
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "logpdf_evals_per_s",
                                                     "samples_per_s")}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
