@@ -805,6 +805,12 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
     cudaStream_t st[2];
     JF_CUDA_OK(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
     JF_CUDA_OK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+    // the two streams exist to overlap COPIES with kernels; the kernels of consecutive chunks are chained by events so
+    // that they never share the SMs (a persistent MLP CTA next to layer-kernel CTAs of the other chunk slows both)
+    static const bool chain_compute = [] { const char* e = getenv("JF_HOST_OVERLAP_COMPUTE"); return !(e && atoi(e) == 1); }();
+    cudaEvent_t done[2];
+    JF_CUDA_OK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    JF_CUDA_OK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     int64_t ci = 0;
     for (int64_t r0 = 0; r0 < B && rc == JF_OK; r0 += chunk, ++ci) {
         const int64_t n = (B - r0 < chunk) ? (B - r0) : chunk;
@@ -817,10 +823,16 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
             e = copy_rows(set + h.cond, d->cond_dim, (const char*)cond_h + r0 * ldc * es, ldc, d->cond_dim, n, es,
                           cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { rc = (int)e; break; }
+        if (chain_compute && ci > 0) {
+            e = cudaStreamWaitEvent(s, done[1 - b], 0);
+            if (e != cudaSuccess) { rc = (int)e; break; }
+        }
         rc = pdf_run(d, P, direction, set + h.src, src_cols, d->cond_dim > 0 ? set + h.cond : nullptr, d->cond_dim,
                      set + h.dst, dst_cols, set + h.logp, logp_base_h ? set + h.logp_base : nullptr, n, set + h.inner,
                      w.total, chunk, status, s);
         if (rc != JF_OK) break;
+        e = cudaEventRecord(done[b], s);
+        if (e != cudaSuccess) { rc = (int)e; break; }
         if (dst_h != nullptr)
             e = copy_rows((char*)dst_h + r0 * ld_dst * es, ld_dst, set + h.dst, dst_cols, dst_cols, n, es,
                           cudaMemcpyDeviceToHost, s);
@@ -834,6 +846,8 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
     cudaError_t e1 = cudaStreamSynchronize(st[1]);
     cudaStreamDestroy(st[0]);
     cudaStreamDestroy(st[1]);
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
     if (rc != JF_OK) return rc;
     if (e0 != cudaSuccess) return (int)e0;
     if (e1 != cudaSuccess) return (int)e1;

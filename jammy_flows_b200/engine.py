@@ -489,7 +489,7 @@ def _host_call(pdf, direction, src, cond, chunk_rows, device):
     dev = torch.device(device)
     B = src.shape[0]
     desc = pdf._desc(dt)
-    chunk = int(chunk_rows or min(max(B, 1), 1 << 18))
+    chunk = int(chunk_rows or min(max(B, 1), DEFAULT_CHUNK_ROWS))   # measured: 2^19 beats 2^18 by 5 % (tools/e2e_probe.py)
     nbytes = lib.jf_pdf_host_workspace_bytes(C.byref(desc), chunk)
     ws = _workspace(dev, nbytes)
     pack = ParamPack(pdf, dt, dev)
