@@ -505,8 +505,10 @@ __device__ __noinline__ LogitRoot<T> solve_logit(const MixView<T>& mv, T t, bool
     }
     {
         const T pad = T(1e-3) * wmax + bracket_eps * (fabs(lo) + fabs(hi));
-        lo = tmax(lo - pad, T(-1e5));   // keep inside the reference's search interval
-        hi = tmin(hi + pad, T(1e5));
+        // (not clipped to the reference's bisection interval [-1e5,1e5]: its Newton steps leave that interval
+        //  too, e.g. for logit targets ~1e3 behind a non-orthogonal triangular_combination "rotation")
+        lo -= pad;
+        hi += pad;
         x = clampv(x, lo, hi);
     }
     x = presolve<T>(mv, t, x, lo, hi, wmin);
@@ -584,8 +586,8 @@ __device__ __noinline__ T solve_general(const MixView<T>& mv, int type, T z, T& 
     }
     {
         const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
-        lo = tmax(lo - pad, T(-1e5));
-        hi = tmin(hi + pad, T(1e5));
+        lo -= pad;
+        hi += pad;
         x = clampv(x, lo, hi);
     }
     const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;

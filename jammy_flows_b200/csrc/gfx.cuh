@@ -272,7 +272,14 @@ JF_DEVINL void inv_stage_log(int type, T lc, T ls, T lp, T sfx, T& y, T& logd) {
 }
 
 // x with sigma(x) = exp(u), u < 0
-template <typename T> JF_DEVINL T logit_of_exp(T u) { return u - log(-expm1(u)); }
+// x with sigma(x)^e = P, given lprob = log P (<= 0) and log_neg_lprob = log(-log P) (needed when P is so close to 1
+// that -log P underflows next to 1: then 1 - e^u ~ -u and x = -log(-u))
+template <typename T>
+JF_DEVINL T quantile_logit(T lprob, T log_neg_lprob, T e) {
+    const T u = lprob / e;
+    if (-u < T(1e-8)) return -(log_neg_lprob - log(e));
+    return u - log(-expm1(u));
+}
 
 // Root of y(x) = z for a skewed mixture: analytic bracket from the per-kernel quantiles (the mixture cdf is a convex
 // combination of the kernel cdfs), then safeguarded Newton on y itself with bisection fall-back.
@@ -288,14 +295,18 @@ __device__ __noinline__ T skew_solve(const GfxView<T>& v, int type, T z, T& logd
     T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0;
     for (int pass = 0; pass < 2; ++pass) {
         const T t = pass == 0 ? t_lo : t_hi;
-        // log p = log sigma(t), log(1-p) = log sigma(-t)
-        const T lp_ = -(t > T(0) ? log1p(exp(-t)) : (log1p(exp(t)) - t));
-        const T lq_ = lp_ - t;
+        // log p = log sigma(t) = -softplus(-t) and log(1-p) = -softplus(t), each without cancellation, plus the logs of
+        // their magnitudes (|t| reaches 1e3 behind a non-orthogonal "rotation": 1-p or p is then ~e^-|t|)
+        const T at = fabs(t);
+        const T l1 = log1p(exp(-at));
+        const T tiny_l = (at > T(30)) ? -at : log(l1);          // log of softplus(-|t|)
+        const T lp_ = t > T(0) ? -l1 : (t - l1), llp = t > T(0) ? tiny_l : log(l1 - t);
+        const T lq_ = t > T(0) ? (-t - l1) : -l1, llq = t > T(0) ? log(t + l1) : tiny_l;
         for (int k = 0; k < K; ++k) {
             const T m = mv_m(v.mv, k), w = T(1) / mv_iw(v.mv, k);
             const T e = lds(v.s + k * v.mv.skb, T());
             const bool pos = k < K / 2;
-            const T a = pos ? logit_of_exp(tmin(lp_ / e, -Num<T>::eps)) : -logit_of_exp(tmin(lq_ / e, -Num<T>::eps));
+            const T a = pos ? quantile_logit(lp_, llp, e) : -quantile_logit(lq_, llq, e);
             const T c = fma(a, w, m);
             if (pass == 0) lo = tmin(lo, c); else hi = tmax(hi, c);
             x = fma(T(0.5) * exp(mv_n(v.mv, k)), c, x);
@@ -304,8 +315,8 @@ __device__ __noinline__ T skew_solve(const GfxView<T>& v, int type, T z, T& logd
     }
     {
         const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
-        lo = tmax(lo - pad, T(-1e5));
-        hi = tmin(hi + pad, T(1e5));
+        lo -= pad;
+        hi += pad;
         x = clampv(x, lo, hi);
     }
     const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
