@@ -458,8 +458,6 @@ class pdf(nn.Module):
                        only_last=False):
         if amortization_parameters is not None or only_last:
             raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
-        if failsafe_crosscheck_tolerance:
-            raise NotImplementedError("failsafe_crosscheck_tolerance (recheck_sampling) is not built yet")
         used_sample_size = samplesize
         if conditional_input is not None:
             used_sample_size = conditional_input.shape[0]
@@ -496,7 +494,36 @@ class pdf(nn.Module):
             # reference main/default.py:1522-1524: default -> embedding coordinates, log p = log N(z) - (logdet + chart)
             x, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)
             log_pdf = log_pdf - chart_log_det
+        if failsafe_crosscheck_tolerance:
+            assert (predefined_target_input is None), "Failsafe does not work with predefined input!"
+            x, std_normal_samples, log_pdf, log_gauss = self._recheck_sampling(
+                x, std_normal_samples, log_pdf, log_gauss, failsafe_crosscheck_tolerance, conditional_input,
+                force_embedding_coordinates, force_intrinsic_coordinates, data_type, used_device)
         return x, std_normal_samples, log_pdf, log_gauss
+
+    def _recheck_sampling(self, x, z, log_pdf, log_gauss, tol, conditional_input, force_emb, force_intr, dtype, device):
+        """Round-trip check of a sample and re-draw of the rows that fail it (reference extra_functions.py:413-533,
+        `recheck_sampling`, used for the iterative sphere flows): x -> base' -> x' must reproduce base, x and log p
+        within `tol`; deviating rows are sampled again (recursively, with the same check)."""
+        with torch.no_grad():
+            lp_new, _, base_new = self.forward(x, conditional_input=conditional_input,
+                                               force_embedding_coordinates=force_emb, force_intrinsic_coordinates=force_intr)
+            x_new = self._obtain_sample(conditional_input=conditional_input, predefined_target_input=base_new,
+                                        force_embedding_coordinates=force_emb, force_intrinsic_coordinates=force_intr,
+                                        dtype=dtype, device=device)[0]
+            dev = (torch.abs(lp_new - log_pdf) > tol) | (torch.abs(x_new - x) > tol).any(dim=1) \
+                | (torch.abs(base_new - z) > tol).any(dim=1)
+            n_dev = int(dev.sum())
+            if n_dev == 0:
+                return x, z, log_pdf, log_gauss
+            new_c = conditional_input[dev] if conditional_input is not None else None
+            rx, rz, rlp, rlg = self._obtain_sample(conditional_input=new_c, samplesize=n_dev,
+                                                   force_embedding_coordinates=force_emb,
+                                                   force_intrinsic_coordinates=force_intr,
+                                                   failsafe_crosscheck_tolerance=tol, dtype=dtype, device=device)
+            x, z, log_pdf, log_gauss = x.clone(), z.clone(), log_pdf.clone(), log_gauss.clone()
+            x[dev], z[dev], log_pdf[dev], log_gauss[dev] = rx, rz, rlp, rlg
+        return x, z, log_pdf, log_gauss
 
     def all_layer_forward(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
                           force_intrinsic_coordinates=False, only_last=False):
@@ -516,8 +543,6 @@ class pdf(nn.Module):
         """Monte-Carlo entropies (reference main/default.py:2263-2454): "total" = -mean log p over `samplesize` samples
         per conditional row; sub-manifold k: -mean_i log( mean_j p_k(x_k^i | x_<k^j) ), an S x S cross-evaluation of
         sub-pdf k (`engine.subpdf_logpdf`) reduced on the device (`jf_row_logmeanexp`)."""
-        if failsafe_crosscheck_tolerance:
-            raise NotImplementedError("failsafe_crosscheck_tolerance (recheck_sampling) is not built yet")
         for subdim in sub_manifolds:
             if subdim != -1:
                 assert (subdim >= 0 and subdim < len(self.layer_list))
@@ -548,7 +573,11 @@ class pdf(nn.Module):
                 assert z.shape == (n, self.total_base_dim)
             else:
                 z = torch.randn(n, self.total_base_dim, dtype=data_type, device=used_device)   # reference :2914 (device RNG)
-            x, log_pdf, _ = engine.pdf_sample(self, z, cond, chunk_rows=self.chunk_rows)
+            x, log_pdf, log_gauss = engine.pdf_sample(self, z, cond, chunk_rows=self.chunk_rows)
+            if failsafe_crosscheck_tolerance:
+                # reference main/default.py:2957-2976: the entropy samples go through the same round-trip check
+                x, z, log_pdf, log_gauss = self._recheck_sampling(x, z, log_pdf, log_gauss, failsafe_crosscheck_tolerance,
+                                                                  cond, False, False, data_type, used_device)
             emb = x
             if self._needs_transform():
                 emb, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)

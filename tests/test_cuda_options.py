@@ -197,3 +197,24 @@ def test_amortizable_mlp_module_matches_oracle(mode, lib_built):
     calm = z.abs().max(dim=1)[0] < 5.0
     assert float((rt_z - z).abs().max(dim=1)[0][calm].max()) < 1e-8
     assert float(((rt_lp - lp).abs() / lp.abs().clamp(min=1))[calm].max()) < 1e-8
+
+
+def test_failsafe_crosscheck_resamples_deviating_rows(lib_built):
+    """`failsafe_crosscheck_tolerance` (reference extra_functions.py:413-533): a generous tolerance changes nothing, a
+    tolerance inside the round-trip noise re-draws exactly the rows that exceed it"""
+    p = _perturbed("e2+s2", "gg+v", scale=0.0).cuda()
+    p.rng_mode = "device"
+    with torch.no_grad():
+        a = p.sample(samplesize=4000, seed=3)
+        b = p.sample(samplesize=4000, seed=3, failsafe_crosscheck_tolerance=1e-6)
+        for u, w in zip(a, b):
+            assert torch.equal(u, w)
+        tol = 2e-13
+        c = p.sample(samplesize=4000, seed=3, failsafe_crosscheck_tolerance=tol)
+        lp, _, base = p(c[0])
+        assert float((base - c[1]).abs().max()) <= 10 * tol and float((lp - c[2]).abs().max()) <= 10 * tol
+        changed = int((c[1] != a[1]).any(dim=1).sum())
+        print("\nfailsafe at %.0e: %d of 4000 rows re-drawn" % (tol, changed))
+        assert 0 < changed < 4000
+        ent = p.entropy(samplesize=500, failsafe_crosscheck_tolerance=1e-6)
+        assert torch.isfinite(ent["total"]).all()
