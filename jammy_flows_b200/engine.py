@@ -145,7 +145,7 @@ def compile_pdf(pdf, dtype):
     d.abi_version = _cabi.JF_ABI_VERSION
     d.dtype = _DT[dtype]
     d.n_sub = len(pdf.layer_list)
-    d.cond_dim = int(pdf.conditional_input_dim or 0)
+    d.cond_dim = int(pdf.conditional_input_dim or 0) if type(pdf.conditional_input_dim) != list else 0
     d.total_target_dim = pdf.total_target_dim
     d.total_base_dim = pdf.total_base_dim
     for k, layers in enumerate(pdf.layer_list):
@@ -207,9 +207,14 @@ def _prep_inputs(pdf, t, cond, what):
         raise ValueError("%s must be 2-dimensional (B, D)" % what)
     if t.stride(1) != 1:
         t = t.contiguous()
+    if isinstance(cond, (list, tuple)):
+        out = []
+        for ci in cond:
+            _require_cuda(ci, "conditional_input")
+            assert ci.dtype == t.dtype and ci.device == t.device
+            out.append(ci if ci.stride(1) == 1 else ci.contiguous())
+        return t, out
     if cond is not None:
-        if isinstance(cond, (list, tuple)):
-            raise NotImplementedError("per-sub-pdf conditional inputs (list) are not built yet")
         _require_cuda(cond, "conditional_input")
         assert cond.dtype == t.dtype and cond.device == t.device
         if cond.stride(1) != 1:
@@ -218,7 +223,10 @@ def _prep_inputs(pdf, t, cond, what):
 
 
 def uses_custom_mlp(pdf):
-    return any(m is not None and hasattr(m, "u_v_b_pars") for m in pdf.mlp_predictors)
+    """True when the per-sub-pdf orchestration on the host is needed: AmortizableMLP generators, or one conditional input
+    per sub-pdf (`conditional_input_dim` list), neither of which the single-call C entries describe."""
+    return type(pdf.conditional_input_dim) == list or \
+        any(m is not None and hasattr(m, "u_v_b_pars") for m in pdf.mlp_predictors)
 
 
 def _run_chain(lib, dt, dev, layers_wb, segs, out, so_p, so_r, R, accumulate):
@@ -294,7 +302,7 @@ def _pdf_staged(pdf, src, cond, direction):
     prev, keep = [], []
     for k, layers in enumerate(pdf.layer_list):
         mlp = pdf.mlp_predictors[k]
-        segs = ([cond] if cond is not None else []) + prev
+        segs = ([cond[k] if isinstance(cond, list) else cond] if cond is not None else []) + prev
         n_par = desc.sub[k].n_params
         if mlp is None:
             params, sp, sr = C.c_void_p(pack.c.shared[k]), 1, 0
@@ -592,7 +600,7 @@ def s2_embedding(x):
 def supports_backward(pdf):
     """True when every sub-pdf is Euclidean, made of "g" layers with a stage the backward kernel covers, and gets its
     parameters from an MLP (conditional pdf)."""
-    if pdf.conditional_input_dim is None:
+    if pdf.conditional_input_dim is None or uses_custom_mlp(pdf):
         return False
     for k, layers in enumerate(pdf.layer_list):
         if pdf.pdf_defs_list[k][0] != "e" or pdf.mlp_predictors[k] is None:

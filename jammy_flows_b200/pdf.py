@@ -58,8 +58,6 @@ class pdf(nn.Module):
             not_built.append("use_as_passthrough_instead_of_pdf")
         if skip_mlp_initialization:
             not_built.append("skip_mlp_initialization")
-        if type(conditional_input_dim) == list:
-            not_built.append("per-sub-pdf conditional_input_dim lists")
         if len(not_built) > 0:
             raise NotImplementedError("jammy_flows_b200.pdf: outside the hot path built so far: " + "; ".join(not_built))
 
@@ -260,7 +258,9 @@ class pdf(nn.Module):
                 continue
             this_summary_dim = prev_extra_input_num
             if self.conditional_input_dim is not None:
-                this_summary_dim += self.conditional_input_dim
+                # an int: one conditional input for all sub-pdfs; a list: one per sub-pdf (reference :637-641)
+                this_summary_dim += (self.conditional_input_dim if type(self.conditional_input_dim) == int
+                                     else self.conditional_input_dim[pdf_index])
             hidden = list_from_str(self.amortization_mlp_dims[pdf_index])
             if self.amortization_mlp_use_custom_mode:
                 # reference main/default.py:643-651: AmortizableMLP with permanent parameters
@@ -401,7 +401,13 @@ class pdf(nn.Module):
         assert (self.use_as_passthrough_instead_of_pdf == False)
         if amortization_parameters is not None or only_last:
             raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
-        if conditional_input is not None:
+        if type(conditional_input) == list:
+            # one conditional input per sub-pdf (reference main/default.py:1092-1103)
+            assert (type(self.conditional_input_dim) == list and len(self.conditional_input_dim) == len(conditional_input))
+            for ci_ind, ci in enumerate(conditional_input):
+                assert (self.conditional_input_dim[ci_ind] == ci.shape[1]), "Inputs of conditional input vector do not match with pre-defined input_dims!"
+                assert (x.shape[0] == ci.shape[0]), "Evaluating input x and condititional input shape must be similar!"
+        elif conditional_input is not None:
             assert (x.shape[0] == conditional_input.shape[0]), "Evaluating input x and condititional input shape must be similar!"
             assert (x.is_cuda == conditional_input.is_cuda), "input tensor *x* and *conditional_input* are on different devices"
             assert (self.conditional_input_dim == conditional_input.shape[1])
@@ -459,7 +465,13 @@ class pdf(nn.Module):
         if amortization_parameters is not None or only_last:
             raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
         used_sample_size = samplesize
-        if conditional_input is not None:
+        if type(conditional_input) == list:
+            assert (type(self.conditional_input_dim) == list and len(self.conditional_input_dim) == len(conditional_input))
+            for ci_ind, ci in enumerate(conditional_input):
+                assert (self.conditional_input_dim[ci_ind] == ci.shape[1]), "Inputs of conditional input vector do not match with pre-defined input_dims!"
+            used_sample_size = conditional_input[0].shape[0]
+            data_type, used_device = conditional_input[0].dtype, conditional_input[0].device
+        elif conditional_input is not None:
             used_sample_size = conditional_input.shape[0]
             data_type, used_device = conditional_input.dtype, conditional_input.device
         else:
@@ -473,7 +485,9 @@ class pdf(nn.Module):
         if predefined_target_input is not None:
             z = predefined_target_input
             assert (used_device == z.device)
-            if conditional_input is not None:
+            if type(conditional_input) == list:
+                assert (z.shape[0] == conditional_input[0].shape[0] and z.dtype == conditional_input[0].dtype)
+            elif conditional_input is not None:
                 assert (z.shape[0] == conditional_input.shape[0] and z.dtype == conditional_input.dtype)
         else:
             if self.rng_mode == "numpy":
@@ -555,7 +569,12 @@ class pdf(nn.Module):
         if dtype is not None:
             data_type = dtype
         S = samplesize
-        if conditional_input is not None:
+        if type(conditional_input) == list:
+            assert (type(self.conditional_input_dim) == list and len(self.conditional_input_dim) == len(conditional_input))
+            data_type, used_device = conditional_input[0].dtype, conditional_input[0].device
+            cond = [ci.repeat_interleave(S, dim=0) for ci in conditional_input]
+            batch = conditional_input[0].shape[0]
+        elif conditional_input is not None:
             assert (self.conditional_input_dim is not None)
             data_type, used_device = conditional_input.dtype, conditional_input.device
             cond = conditional_input.repeat_interleave(S, dim=0)
@@ -590,8 +609,9 @@ class pdf(nn.Module):
                 e0, e1 = self.target_dim_indices_embedded[sub_mf]
                 t0, t1 = self.target_dim_indices[sub_mf]
                 x_k = emb[:, e0:e1] if use_emb else x[:, t0:t1]
+                cond_k = cond[sub_mf] if type(cond) == list else cond
                 if sub_mf == 0:
-                    lp = engine.subpdf_logpdf(self, 0, x_k, [cond] if cond is not None else [], use_emb)
+                    lp = engine.subpdf_logpdf(self, 0, x_k, [cond_k] if cond_k is not None else [], use_emb)
                     out[0] = -lp.reshape(-1, S).mean(dim=1)
                     continue
                 prev = emb[:, :e0]
@@ -606,8 +626,8 @@ class pdf(nn.Module):
                     first = prev[rows].reshape(nb, S, e0).repeat(1, S, 1).reshape(-1, e0)
                     final = x_k[rows].reshape(nb, S, d_k).repeat_interleave(S, dim=1).reshape(-1, d_k)
                     segs = [first]
-                    if cond is not None:
-                        segs = [cond[rows].repeat_interleave(S, dim=0), first]
+                    if cond_k is not None:
+                        segs = [cond_k[rows].repeat_interleave(S, dim=0), first]
                     lp = engine.subpdf_logpdf(self, sub_mf, final, segs, use_emb)
                     vals.append(engine.row_logmeanexp(lp.reshape(-1, S)).reshape(nb, S).mean(dim=1))
                 out[sub_mf] = -torch.cat(vals)

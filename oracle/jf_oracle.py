@@ -1218,6 +1218,8 @@ class OraclePdf:
     def _sub_params(self, k, cond, prev_emb, batch):
         sp = self.prog["subpdfs"][k]
         if sp["mlp"] is not None:
+            if isinstance(cond, (list, tuple)):          # one conditional input per sub-pdf (main/default.py:944-949)
+                cond = cond[k]
             pieces = ([cond] if cond is not None else []) + prev_emb
             return self._mlp(k, torch.cat(pieces, dim=1))
         # permanent parameters: concatenate the layers' tensors in extra_inputs order, broadcast over the batch
@@ -1307,9 +1309,16 @@ class OraclePdf:
             out[sm] = -(torch.logsumexp(lp, dim=-1) - math.log(float(S))).mean(dim=1)
         return out
 
+    def _as_cond(self, cond):
+        if cond is None:
+            return None
+        if isinstance(cond, (list, tuple)):
+            return [torch.as_tensor(np.asarray(c)).to(self.dtype) for c in cond]
+        return torch.as_tensor(np.asarray(cond)).to(self.dtype)
+
     def log_pdf(self, x, cond=None):
         x = torch.as_tensor(np.asarray(x)).to(self.dtype)
-        cond = None if cond is None else torch.as_tensor(np.asarray(cond)).to(self.dtype)
+        cond = self._as_cond(cond)
         b = x.shape[0]
         log_det = torch.zeros(b, dtype=self.dtype)
         prev_emb, base = [], []
@@ -1329,7 +1338,7 @@ class OraclePdf:
 
     def sample(self, z, cond=None):
         z = torch.as_tensor(np.asarray(z)).to(self.dtype)
-        cond = None if cond is None else torch.as_tensor(np.asarray(cond)).to(self.dtype)
+        cond = self._as_cond(cond)
         b = z.shape[0]
         log_det = torch.zeros(b, dtype=self.dtype)
         prev_emb, out = [], []

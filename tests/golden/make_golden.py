@@ -182,6 +182,8 @@ CASES = {
     "amlp_e2e2_cond_mode4": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=300, cond_dim=3, perturb=0.05,
                                  pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
                                              amortization_mlp_ranks=0, amortization_mlp_highway_mode=4)),
+    # one conditional input per sub-pdf (conditional_input_dim as a list, main/default.py:286-296, :944-949)
+    "condlist_e2s2e1": dict(pdf_defs="e2+s2+e1", flow_defs="gg+f+g", n=300, cond_dim=[3, 2, 4], perturb=0.2),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
@@ -208,7 +210,9 @@ def build_case(jf, name, spec):
     n = spec["n"]
     x = make_inputs(spec["pdf_defs"], n, gen, tails=spec.get("tails", False)).to(dtype)
     cond = None
-    if cond_dim is not None:
+    if type(cond_dim) == list:
+        cond = [torch.randn(n, cd, generator=gen, dtype=torch.float64).to(dtype) for cd in cond_dim]
+    elif cond_dim is not None:
         cond = torch.randn(n, cond_dim, generator=gen, dtype=torch.float64).to(dtype)
     z = torch.randn(n, pdf.total_base_dim, generator=gen, dtype=torch.float64).to(dtype)
     if spec.get("data_init", False):
@@ -259,7 +263,10 @@ def build_case(jf, name, spec):
         out["ent_S"] = np.int64(S)
         out.update({"x_emb": x_emb.numpy(), "logp_emb": logp_e.numpy(), "base_emb": base_e.numpy(),
                     "samp_x_emb": sx_e.numpy(), "samp_logp_emb": slogp_e.numpy()})
-    if cond is not None:
+    if type(cond) == list:
+        for i_, c_ in enumerate(cond):
+            out["cond%d" % i_] = c_.numpy()
+    elif cond is not None:
         out["cond"] = cond.numpy()
     for k, v in pdf.state_dict().items():
         out["param/" + k] = v.numpy()

@@ -22,6 +22,8 @@ def load_golden(name):
     meta = json.loads(str(g["meta"]))
     params = {k[6:]: g[k] for k in g.files if k.startswith("param/")}
     data = {k: g[k] for k in g.files if not k.startswith("param/") and k != "meta"}   # includes "grad/<name>" entries
+    if "cond0" in data:     # one conditional input per sub-pdf
+        data["cond"] = [data["cond%d" % i] for i in range(len(meta["conditional_input_dim"]))]
     return meta, params, data
 
 

@@ -25,7 +25,9 @@ def _cuda_model(name):
     p = build_pdf(meta, params).cuda()
     dt = getattr(torch, meta["dtype"])
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
-    cond = t(data["cond"]) if "cond" in data else None
+    cond = None
+    if "cond" in data:
+        cond = [t(c) for c in data["cond"]] if isinstance(data["cond"], list) else t(data["cond"])
     return meta, data, p, t, cond
 
 
