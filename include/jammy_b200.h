@@ -109,6 +109,11 @@ extern "C" {
 #define JF_STRETCH_CLASSIC 0 /* logistic mixture CDF + inverse-CDF stage */
 #define JF_STRETCH_RQS 1     /* rational-quadratic spline with linear tails (spline_fns.py:188-358) */
 
+/* potential of "v" (exponential_map_s2.py:285-344), stored in JfLayerDesc.inv_type */
+#define JF_POT_EXPONENTIAL 0 /* grad = sum_k w_k mu_k exp(beta_k (x.mu_k - 1)); parameters [5, K] */
+#define JF_POT_LINEAR 1      /* grad = sum_k w_k mu_k;                         parameters [4, K] */
+#define JF_POT_QUADRATIC 2   /* grad = sum_k w_k mu_k (x.mu_k);                parameters [4, K] */
+
 /* status words */
 #define JF_STATUS_NONFINITE 0
 #define JF_STATUS_UNCONVERGED 1
@@ -149,7 +154,7 @@ typedef struct JfLayerDesc {
     int32_t param_offset; /* start of that slice (layers are stored in flow order, main/default.py:1488) */
     int32_t K;            /* g: num_kde */
     int32_t hh_iter;      /* number of Householder reflections (g: in R^d; f: in R^3); 0 = no rotation */
-    int32_t inv_type;     /* g: JF_INV_* ; t: JF_COV_* */
+    int32_t inv_type;     /* g: JF_INV_* ; t: JF_COV_* ; v: JF_POT_* */
     int32_t norm_mode;    /* g: JF_NORM_* */
     int32_t has_offset;   /* g: model_offset (euclidean_base.py:34-75); offset params come first in the slice */
     int32_t first;        /* s1/s2/interval: layer also applies the base chart of the sub-pdf (sphere_base.py:637-648,

@@ -31,6 +31,7 @@ JF_NORM_NONE, JF_NORM_RAW, JF_NORM_REGULATED = 0, 1, 2
 JF_ROT_HOUSEHOLDER, JF_ROT_NONE, JF_ROT_ANGLES, JF_ROT_CAYLEY, JF_ROT_TRIANGULAR = 0, 1, 2, 3, 4
 JF_WIDTH_SMOOTH, JF_WIDTH_EXP, JF_WIDTH_SOFTPLUS = 0, 1, 2
 JF_STRETCH_CLASSIC, JF_STRETCH_RQS = 0, 1
+JF_POT_EXPONENTIAL, JF_POT_LINEAR, JF_POT_QUADRATIC = 0, 1, 2
 JF_STATUS_NONFINITE, JF_STATUS_UNCONVERGED, JF_STATUS_OUT_OF_RANGE, JF_STATUS_ITERATIONS = 0, 1, 2, 3
 ERRORS = {-1: "JF_ERR_BAD_DESC (invalid descriptor)", -2: "JF_ERR_UNSUPPORTED (no kernel for this configuration)",
           -3: "JF_ERR_BAD_ARG (invalid argument)", -4: "JF_ERR_WORKSPACE (workspace missing or too small)"}

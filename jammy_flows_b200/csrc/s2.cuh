@@ -42,6 +42,7 @@ struct FvmLayerC {
     int kind, add_rotation, hh_iter, first, raw_off;
     int v_first, n_vertical, c_first, n_circular;   // f: nested spline sub-flows (indices into S2Args::splines)
     int K, natural_direction, max_iter;             // v: components / direction / iteration cap
+    int pot, pad_pot;                               // v: JF_POT_*
     double z_sign, min_kappa;
 };
 
@@ -197,13 +198,14 @@ constexpr int kMaxExpComp = 16;
 template <typename T>
 struct VRow {
     T mx[kMaxExpComp], my[kMaxExpComp], mz[kMaxExpComp], w[kMaxExpComp], beta[kMaxExpComp];
-    int K;
+    int K, pot;
 };
 
 // parameters [5, K] (index i*K + k): rows 0-2 mean direction (its length sets the weight bound), 3 log-weight, 4 log beta
 template <typename T>
-JF_DEVINL void v_setup(VRow<T>& r, int K, const T* p, int64_t sj) {
+JF_DEVINL void v_setup(VRow<T>& r, int K, int pot, const T* p, int64_t sj) {
     r.K = K;
+    r.pot = pot;
     T lmax = -Num<T>::big;
     for (int k = 0; k < K; ++k) lmax = tmax(lmax, p[(int64_t)(3 * K + k) * sj]);
     T lsum = 0;
@@ -215,7 +217,7 @@ JF_DEVINL void v_setup(VRow<T>& r, int K, const T* p, int64_t sj) {
         r.mx[k] = a / n; r.my[k] = b / n; r.mz[k] = c / n;
         const T fake = -log(T(1) + T(1.718281828459045) * exp(-n / T(10))) + T(1);          // :32-43, :262
         r.w[k] = exp(p[(int64_t)(3 * K + k) * sj] - lse + log(fake));                       // :288-289
-        r.beta[k] = exp(p[(int64_t)(4 * K + k) * sj]);                                      // :296
+        r.beta[k] = pot == JF_POT_EXPONENTIAL ? exp(p[(int64_t)(4 * K + k) * sj]) : T(0);   // :296
     }
 }
 
@@ -225,9 +227,12 @@ __device__ __noinline__ void v_eval(const VRow<T>& r, const T* x, T* y, T* J, T&
     T g0 = 0, g1 = 0, g2 = 0, G00 = 0, G01 = 0, G02 = 0, G11 = 0, G12 = 0, G22 = 0;
     for (int k = 0; k < r.K; ++k) {
         const T xm = x[0] * r.mx[k] + x[1] * r.my[k] + x[2] * r.mz[k];
-        const T c = r.w[k] * exp(r.beta[k] * (xm - T(1)));
+        // gradient of the potential and its Jacobian coefficient per component (exponential_map_s2.py:285-344)
+        T c, cb;
+        if (r.pot == JF_POT_EXPONENTIAL) { c = r.w[k] * exp(r.beta[k] * (xm - T(1))); cb = c * r.beta[k]; }
+        else if (r.pot == JF_POT_QUADRATIC) { c = r.w[k] * xm; cb = r.w[k]; }
+        else { c = r.w[k]; cb = T(0); }
         g0 = fma(c, r.mx[k], g0); g1 = fma(c, r.my[k], g1); g2 = fma(c, r.mz[k], g2);
-        const T cb = c * r.beta[k];
         G00 = fma(cb, r.mx[k] * r.mx[k], G00); G01 = fma(cb, r.mx[k] * r.my[k], G01); G02 = fma(cb, r.mx[k] * r.mz[k], G02);
         G11 = fma(cb, r.my[k] * r.my[k], G11); G12 = fma(cb, r.my[k] * r.mz[k], G12); G22 = fma(cb, r.mz[k] * r.mz[k], G22);
     }
@@ -389,7 +394,7 @@ JF_DEVINL void v_layer(bool logpdf, T& c0, T& c1, T& logdet, const FvmLayerC& c,
         s2_from_embedding(e, theta, phi, logdet);
     }
     VRow<T> row;
-    v_setup(row, c.K, pl + (int64_t)n_hh * sj, sj);
+    v_setup(row, c.K, c.pot, pl + (int64_t)n_hh * sj, sj);
     s2_to_embedding(theta, phi, e, logdet);
     T y[3], J[9], hld;
     const bool direct = logpdf ? (c.natural_direction == 0) : (c.natural_direction != 0);

@@ -109,6 +109,7 @@ def fill_layer_desc(ld, desc, param_offset):
         ld.natural_direction = desc["natural_direction"]
         ld.K = desc["K"]
         ld.max_iter = desc["max_iter"]
+        ld.inv_type = desc.get("potential", 0)
     else:
         raise NotImplementedError("no sm_100a kernel for layer code %r" % desc["code"])
 

@@ -337,6 +337,7 @@ class gf_block(layer_base):
 # =====================================================================================================================
 # Euclidean: affine layer "t"
 # =====================================================================================================================
+V_POTENTIALS = {"exponential": 0, "linear": 1, "quadratic": 2}     # JF_POT_* (exponential_map_s2.py:285-344)
 COV_TYPES = {"identity": 0, "diagonal_symmetric": 1, "diagonal": 2, "full": 3}
 
 
@@ -912,7 +913,8 @@ class exponential_map_s2(layer_base):
         if dimension != 2:
             raise Exception("The moebius flow should be used for dimension 2!")
         unsupported = []
-        if exp_map_type != "exponential":
+        if exp_map_type not in V_POTENTIALS:
+            # "splines" (integral of a spline) and "nn" have no kernel; anything else is unknown to the reference too
             unsupported.append("exp_map_type=%s" % exp_map_type)
         if mean_parametrization != "old":
             unsupported.append("mean_parametrization=%s" % mean_parametrization)
@@ -936,7 +938,8 @@ class exponential_map_s2(layer_base):
         self.exp_map_type = exp_map_type
         self.natural_direction = natural_direction
         self.max_num_newton_iter = max_num_newton_iter
-        self.num_potential_pars = 3 + 2
+        # mean direction (3) + log weight, + log beta for the exponential potential (exponential_map_s2.py:124-127)
+        self.num_potential_pars = 3 + (2 if exp_map_type == "exponential" else 1)
         if use_permanent_parameters:
             self.potential_pars = nn.Parameter(torch.randn(self.num_potential_pars, self.num_components).unsqueeze(0))
         self.total_param_num += self.num_potential_pars * self.num_components
@@ -961,7 +964,8 @@ class exponential_map_s2(layer_base):
     def descriptor(self):
         return dict(code="v", dim=2, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
                     first=int(self.euclidean_to_sphere_as_first), natural_direction=int(self.natural_direction),
-                    K=self.num_components, max_iter=int(self.max_num_newton_iter), n_params=self.total_param_num)
+                    K=self.num_components, max_iter=int(self.max_num_newton_iter), n_params=self.total_param_num,
+                    exp_map_type=self.exp_map_type, potential=V_POTENTIALS[self.exp_map_type])
 
     def _embedding_conditional_return(self, x):
         from . import engine

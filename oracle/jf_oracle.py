@@ -1020,7 +1020,8 @@ class VLayer:
     def _split(self, p):
         n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
         q = householder_matrix(p[:, :n_hh].reshape(-1, self.s["hh_iter"], 3)) if n_hh > 0 else None
-        return q, p[:, n_hh:].reshape(p.shape[0], 5, self.s["K"])
+        n_pot = 5 if self.s.get("exp_map_type", "exponential") == "exponential" else 4
+        return q, p[:, n_hh:].reshape(p.shape[0], n_pot, self.s["K"])
 
     @staticmethod
     def _log_map(base, g, jac_g):
@@ -1053,10 +1054,18 @@ class VLayer:
         lw = pars[:, 3:4, :] - torch.logsumexp(pars[:, 3:4, :], dim=2, keepdim=True) + fake.log()
         w = lw.exp()
         xm = (x[:, :, None] * mu).sum(dim=1, keepdim=True)
-        beta = pars[:, 4:5, :].exp()
-        e = torch.exp(beta * (xm - 1.0))
-        g = (w * mu * e).sum(dim=-1)
-        jac_g = torch.einsum("biu,bju->bij", beta * w * mu * e, mu)
+        kind = self.s.get("exp_map_type", "exponential")
+        if kind == "exponential":                                 # :285-314
+            beta = pars[:, 4:5, :].exp()
+            e = torch.exp(beta * (xm - 1.0))
+            g = (w * mu * e).sum(dim=-1)
+            jac_g = torch.einsum("biu,bju->bij", beta * w * mu * e, mu)
+        elif kind == "linear":                                    # :315-324 (no Jacobian of the gradient)
+            g = (w * mu).sum(dim=-1).expand(x.shape[0], -1)
+            jac_g = torch.zeros(x.shape[0], 3, 3, dtype=x.dtype)
+        else:                                                     # quadratic, :325-343
+            g = (w * mu * xm).sum(dim=-1)
+            jac_g = torch.einsum("biu,bju->bij", (w * mu).expand(x.shape[0], -1, -1), mu.expand(x.shape[0], -1, -1))
         th, proj, jt, jp = self._log_map(x, g, jac_g)
         y = x * torch.cos(proj) + th * torch.sin(proj)
         first = torch.diag_embed(torch.cos(proj).repeat(1, 3)) + (-x * torch.sin(proj)).unsqueeze(-1) @ jp

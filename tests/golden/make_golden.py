@@ -124,6 +124,11 @@ CASES = {
     "s2_vv_rot": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0, opts={"v": {"add_rotation": 1, "num_components": 4}}),
     "s2_v_natural": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"natural_direction": 1}}),
     "cfg4_e6s2_gv_small": dict(pdf_defs="e6+s2", flow_defs="gggggg+v", n=300, cond_dim=64, perturb=0.02),
+    "s2_v_linear": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"exp_map_type": "linear"}}),
+    "s2_v_quadratic_natural": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0,
+                                   opts={"v": {"exp_map_type": "quadratic", "natural_direction": 1}}),
+    "s2_v_quadratic_cond": dict(pdf_defs="e2+s2", flow_defs="gg+v", n=300, cond_dim=2, perturb=0.0,
+                                opts={"v": {"exp_map_type": "quadratic", "num_components": 6}}),
     # "t": affine layer (the docs' recommended Euclidean recipe is "g...gt" with cov_type="full", suggested_settings.rst:14-41)
     "t_e3_ggt_full": dict(pdf_defs="e3", flow_defs="ggt", n=500, tails=True, perturb=0.3, opts={"t": {"cov_type": "full"}}),
     "t_e4_gt_cond_diag": dict(pdf_defs="e4", flow_defs="gt", n=500, cond_dim=2, perturb=0.2),
