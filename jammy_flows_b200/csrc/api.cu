@@ -432,7 +432,10 @@ static int try_mlp2_dmma(const MlpArgs<T>&, cudaStream_t) { return JF_ERR_UNSUPP
 
 // fp64, hidden width 128, <= 16 inputs: the tcgen05 (int8-sliced, exact) kernel.  Needs the caller's workspace for the
 // pre-sliced last-layer weights; `prepared` skips the slicing pass (same weights as the previous call on this stream).
-constexpr int kI8NS = 7;      // fp64: 7 int8 slices (54 fractional bits)
+#ifndef JF_I8_NS
+#define JF_I8_NS 7
+#endif
+constexpr int kI8NS = JF_I8_NS;      // fp64: 7 int8 slices (54 fractional bits); 6 (46 bits) is an experiment variant
 constexpr int kI8NSF32 = 4;   // fp32: 4 int8 slices (30 fractional bits > the 24-bit significand)
 static int i8_tn() {       // output-tile width: 64 (default; N = 32 MMAs run at the same 32 cycles: A-read bound) or 32
     static const int tn = [] { const char* e = getenv("JF_I8_TN"); return (e != nullptr && atoi(e) == 32) ? 32 : 64; }();

@@ -599,12 +599,13 @@ def s2_embedding(x):
 # evaluated transposed ([P, B] = W2 h^T + b2), which IS the param-major layout the layer kernels read coalesced.
 # ---------------------------------------------------------------------------------------------------------------------
 def supports_backward(pdf):
-    """True when every sub-pdf is Euclidean, made of "g" layers with a stage the backward kernel covers, and gets its
-    parameters from an MLP (conditional pdf)."""
-    if pdf.conditional_input_dim is None or uses_custom_mlp(pdf):
+    """True when every sub-pdf is Euclidean and made of "g" layers (default options) with a stage the backward kernel
+    covers.  Parameters may come from an MLP (per-row) or be permanent: a permanent vector is expanded to per-row form
+    and autograd sums the per-row gradients back into it."""
+    if uses_custom_mlp(pdf):
         return False
     for k, layers in enumerate(pdf.layer_list):
-        if pdf.pdf_defs_list[k][0] != "e" or pdf.mlp_predictors[k] is None:
+        if pdf.pdf_defs_list[k][0] != "e":
             return False
         for l in layers:
             if getattr(l, "code", "") != "g" or l.inverse_function_type not in ("isigmoid", "inormal_partly_precise"):
@@ -663,13 +664,20 @@ def pdf_logpdf_trainable(pdf, x, cond):
         mlp = pdf.mlp_predictors[k]
         t0, t1 = pdf.target_dim_indices[k]
         x_k = x[:, t0:t1]
-        inp = torch.cat([cond] + prev, dim=1) if len(prev) > 0 else cond
-        h = inp
-        mods = list(mlp)
-        for m in mods[:-1]:
-            h = m(h)
-        last = mods[-1]
-        params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())        # [P, B], param-major
+        if mlp is None:
+            # permanent parameters (the reference's nn.Parameters broadcast over the batch): one vector in extra_inputs
+            # order, expanded to the per-row layout of the backward kernel; autograd reduces the row gradients
+            vec = torch.cat([l.packed_permanent_params() for l in layers]).to(device=dev, dtype=dt)
+            params_t = vec.unsqueeze(1).expand(vec.shape[0], x.shape[0]).contiguous()
+        else:
+            pieces = ([cond] if cond is not None else []) + prev
+            inp = torch.cat(pieces, dim=1) if len(pieces) > 1 else pieces[0]
+            h = inp
+            mods = list(mlp)
+            for m in mods[:-1]:
+                h = m(h)
+            last = mods[-1]
+            params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())        # [P, B], param-major
         lp_k, lb_k, base_k = _SubPdfLogPdf.apply(params_t, x_k, desc.sub[k], status)
         logp = lp_k if logp is None else logp + lp_k
         logp_base = lb_k if logp_base is None else logp_base + lb_k

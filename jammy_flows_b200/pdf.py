@@ -35,9 +35,9 @@ class _NoBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(
-            "jammy_flows_b200: backward kernels exist for conditional pdfs made of Euclidean 'g' sub-pdfs (isigmoid / "
-            "inormal_partly_precise stages, SURVEY.md K8 / cfg5); this pdf contains other layers or permanent "
-            "parameters, whose outputs are inference-only in this round.")
+            "jammy_flows_b200: backward kernels exist for pdfs made of Euclidean 'g' sub-pdfs with default options "
+            "(isigmoid / inormal_partly_precise stages; permanent or MLP-generated parameters; SURVEY.md K8 / cfg5); "
+            "this pdf contains other layers or options, whose outputs are inference-only in this round.")
 
 
 class pdf(nn.Module):

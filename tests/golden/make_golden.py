@@ -192,6 +192,8 @@ CASES = {
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
     "train_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=200, cond_dim=3, perturb=0.2, grads=True),
     "train_e10_gg_cond": dict(pdf_defs="e10", flow_defs="gg", n=100, cond_dim=4, perturb=0.05, grads=True),
+    "train_e2_gg_uncond": dict(pdf_defs="e2", flow_defs="gg", n=300, perturb=0.3, grads=True),
+    "train_e3e2_uncond": dict(pdf_defs="e3+e2", flow_defs="gg+gg", n=200, perturb=0.2, grads=True),
     "train_e2e2_cond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=200, cond_dim=2, perturb=0.2, grads=True),
 }
 

@@ -154,9 +154,10 @@ def test_edge_cases(lib_built):
         bad = torch.tensor([[float("nan"), 0.0]], dtype=torch.float64, device="cuda")
         p(bad)
         assert p.kernel_status()["nonfinite"] == 1
-    # backward is not silently wrong: it raises
+    # backward is not silently wrong: pdfs without a backward kernel raise (here: a non-default "g" option)
+    q = _perturbed("e2", "gg", options_overwrite={"g": {"rotation_mode": "angles"}}).cuda()
     x = torch.randn(4, 2, dtype=torch.float64, device="cuda")
-    lp, _, _ = p(x)
+    lp, _, _ = q(x)
     with pytest.raises(NotImplementedError):
         lp.sum().backward()
 

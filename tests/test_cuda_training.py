@@ -25,7 +25,7 @@ def test_gradients_match_reference_golden(name, lib_built):
     meta, params, data = load_golden(name)
     p = build_pdf(meta, params).cuda()
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    g, lp = cuda_grads(p, t(data["x"]), t(data["cond"]))
+    g, lp = cuda_grads(p, t(data["x"]), t(data["cond"]) if "cond" in data else None)
     assert np.abs(lp.cpu().numpy() - data["logp"]).max() < 1e-9
     for k in data:
         if k.startswith("grad/"):
@@ -88,7 +88,8 @@ def test_adam_steps_decrease_the_loss(lib_built):
 
 
 def test_backward_of_unsupported_pdfs_fails_loudly(lib_built):
-    p = jfb.pdf("e2", "gg").double().cuda()                  # permanent parameters: no backward kernel
-    lp, _, _ = p(torch.randn(8, 2, dtype=torch.float64, device="cuda"))
+    p = jfb.pdf("s2", "f").double().cuda()                   # manifold layers: no backward kernel
+    x = torch.tensor([[1.0, 2.0], [0.5, 4.0]], dtype=torch.float64, device="cuda")
+    lp, _, _ = p(x)
     with pytest.raises(NotImplementedError):
         lp.sum().backward()

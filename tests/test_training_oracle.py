@@ -31,7 +31,7 @@ def oracle_grads(pdf, params, x, cond):
 def test_oracle_autograd_reproduces_reference_gradients(name):
     meta, params, data = load_golden(name)
     pdf = build_pdf(meta)
-    g = oracle_grads(pdf, params, data["x"], data["cond"])
+    g = oracle_grads(pdf, params, data["x"], data.get("cond"))
     n = 0
     for k in data:
         if not k.startswith("grad/"):
@@ -40,7 +40,10 @@ def test_oracle_autograd_reproduces_reference_gradients(name):
         scale = max(np.abs(ref).max(), 1e-30)
         assert np.abs(g[k[5:]] - ref).max() / scale < 1e-9, k
         n += 1
-    assert n == 4 * len(meta["pdf_defs"].split("+"))       # weight + bias of both Linear layers of every MLP
+    if meta["conditional_input_dim"] is not None:
+        assert n == 4 * len(meta["pdf_defs"].split("+"))       # weight + bias of both Linear layers of every MLP
+    else:
+        assert n == len(params)                                 # every permanent tensor and every MLP tensor
 
 
 def _free_port():
