@@ -310,6 +310,7 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
     T merit = T(1) - (y[0] * tg[0] + y[1] * tg[1] + y[2] * tg[2]);
     const T tol = sizeof(T) == 8 ? T(1e-13) : T(1e-6);
     const int cap = max_iter < 200 ? max_iter : 200;
+    T prev_nrm = Num<T>::big;
 #pragma unroll 1
     for (int it = 0; it < cap; ++it) {
         // residual: logarithmic map of tg at y, expressed in a tangent basis at y
@@ -338,10 +339,15 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
         T nrm = sqrt(dl1 * dl1 + dl2 * dl2);
         if (!finite_(nrm)) break;
         if (nrm > T(1)) { dl1 /= nrm; dl2 /= nrm; nrm = T(1); }
-        if (nrm <= tol) {
+        // converged: the Newton step is below the tolerance, or it has stopped shrinking at a small length, i.e. it is
+        // rounding noise of the residual (quadratic convergence shrinks it by orders of magnitude per step otherwise).
+        // In fp32 the noise floor (~3e-6 for a Jacobian of condition ~10) sits ABOVE the fixed tolerance: without the
+        // second test most rows ran into the iteration cap (measured: 780 evaluations per row on cfg4).
+        if (nrm <= tol || (nrm < T(1e-3) && nrm >= T(0.5) * prev_nrm)) {
             converged = true;
             if (nrm == T(0)) break;
         }
+        prev_nrm = nrm;
         // step along the geodesic, halving while the merit does not decrease
         T xn[3], yn[3], Jn[9], hn, mn = merit;
         bool ok = false;
