@@ -651,6 +651,62 @@ class _SubPdfLogPdf(torch.autograd.Function):
         return grad, None, None, None
 
 
+class _MlpParamsTc(torch.autograd.Function):
+    """Per-row parameters [P, B] (param-major) of a Linear-tanh-Linear generator with 128 hidden units: forward on the
+    tcgen05 MLP kernel (`jf_mlp_forward_ws`, the same kernel as inference), backward with library GEMMs.  The hidden
+    activations are not kept: the backward recomputes them (a [B, in] x [in, 128] product, cheap next to the two
+    [P, B]-sized products of the last layer)."""
+
+    @staticmethod
+    def forward(ctx, inp, w1, b1, w2, b2):
+        lib = _cabi.load()
+        dt, dev = inp.dtype, inp.device
+        B, P = inp.shape[0], w2.shape[0]
+        md = _cabi.JfMlpDesc()
+        md.n_linear = 2
+        md.dims[0], md.dims[1], md.dims[2] = w1.shape[1], w1.shape[0], P
+        md.n_segments = 1
+        md.seg_cols[0] = inp.shape[1]
+        inp_c = inp if inp.stride(1) == 1 else inp.contiguous()
+        ws_ = [w1.detach().contiguous(), w2.detach().contiguous()]
+        bs_ = [b1.detach().contiguous(), b2.detach().contiguous()]
+        ptrs = (C.c_void_p * 1)(inp_c.data_ptr())
+        lds = (C.c_int64 * 1)(inp_c.stride(0))
+        wp = (C.c_void_p * 2)(*[t.data_ptr() for t in ws_])
+        bp = (C.c_void_p * 2)(*[t.data_ptr() for t in bs_])
+        out = torch.empty(P, B, dtype=dt, device=dev)
+        nws = lib.jf_mlp_workspace_bytes(C.byref(md), _DT[dt])
+        ws = _workspace(dev, max(int(nws), 16))
+        with torch.cuda.device(dev):
+            rc = lib.jf_mlp_forward_ws(C.byref(md), _DT[dt], ptrs, lds, wp, bp, _ptr(out), B, 1, B, _ptr(ws), nws, 0,
+                                       _stream_ptr(dev))
+        _cabi.check(rc, "jf_mlp_forward_ws")
+        ctx.save_for_backward(inp_c, w1, b1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):                                   # g: [P, B]
+        inp, w1, b1, w2 = ctx.saved_tensors
+        h = torch.tanh(torch.addmm(b1, inp, w1.t()))         # [B, 128]
+        g_w2 = torch.mm(g, h)                                # [P, 128]
+        g_b2 = g.sum(dim=1)
+        g_h = torch.mm(g.t(), w2)                            # [B, 128]
+        g_pre = g_h * (1.0 - h * h)
+        g_w1 = torch.mm(g_pre.t(), inp)                      # [128, in]
+        g_b1 = g_pre.sum(dim=0)
+        return None, g_w1, g_b1, g_w2, g_b2
+
+
+def _tc_mlp_eligible(mlp, dt):
+    """Linear-tanh-Linear with 128 hidden units and few enough inputs for the tcgen05 kernel (csrc/mlp_i8.cuh)."""
+    mods = list(mlp)
+    if len(mods) != 3 or not isinstance(mods[0], torch.nn.Linear) or not isinstance(mods[2], torch.nn.Linear):
+        return False
+    if mods[0].out_features != 128:
+        return False
+    return mods[0].in_features <= (16 if dt == torch.float64 else 96)
+
+
 def pdf_logpdf_trainable(pdf, x, cond):
     """-> (log_pdf [B] with autograd history, log_pdf_base [B], base [B, D]).  Reference: main/default.py:1059-1117 with
     `torch.is_grad_enabled()`; the conditioning on earlier sub-pdfs uses the data x (no gradient flows through it)."""
@@ -672,12 +728,15 @@ def pdf_logpdf_trainable(pdf, x, cond):
         else:
             pieces = ([cond] if cond is not None else []) + prev
             inp = torch.cat(pieces, dim=1) if len(pieces) > 1 else pieces[0]
-            h = inp
             mods = list(mlp)
-            for m in mods[:-1]:
-                h = m(h)
-            last = mods[-1]
-            params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())        # [P, B], param-major
+            if _tc_mlp_eligible(mlp, dt):
+                params_t = _MlpParamsTc.apply(inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias)
+            else:
+                h = inp
+                for m in mods[:-1]:
+                    h = m(h)
+                last = mods[-1]
+                params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())    # [P, B], param-major
         lp_k, lb_k, base_k = _SubPdfLogPdf.apply(params_t, x_k, desc.sub[k], status)
         logp = lp_k if logp is None else logp + lp_k
         logp_base = lb_k if logp_base is None else logp_base + lb_k
