@@ -316,6 +316,10 @@ def run_gpu_arm(args, rank, world, local_rank):
     pdf.rng_mode = "device"
     n = args.rows
     x, z = make_inputs(n, dev, 100 + rank)      # every rank owns its own shard of rows (no data-path collective)
+    # base normals of the sampling half: this rank's rows [rank*n, (rank+1)*n) of ONE global Philox stream
+    # (jf_normal_rows), so the union of the ranks' sample sets is the same set for any number of GPUs
+    from jammy_flows_b200 import engine as _engine
+    z = _engine.normal_rows(n, 10, 20261017, first_row=rank * n, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
     def step():

@@ -339,6 +339,12 @@ int jf_pdf_transform_target(const JfPdfDesc* desc, int to_embedding,
  * (pdf.entropy with sub_manifolds, main/default.py:2444-2448).  Device buffers. */
 int jf_row_logmeanexp(int dtype, const void* in, int64_t rows, int64_t cols, void* out, void* stream);
 
+/* Base-space standard normals on the device, out [B, ld_out] (first `dim` columns): Philox4x32-10 keyed by `seed`, row i
+ * is a function of (seed, first_row + i) only.  Replaces the reference's host numpy RNG + H2D copy in pdf.sample
+ * (main/default.py:1661-1668); ranks of a sharded job pass their first global row and draw slices of one stream. */
+int jf_normal_rows(int dtype, uint64_t seed, uint64_t first_row, int64_t B, int32_t dim, void* out, int64_t ld_out,
+                   void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 int jf_abi_version(void);
 /* FP64 DFMA / FP32 FFMA peak probe used as the roofline denominator of the compute-bound layer kernels:

@@ -11,6 +11,7 @@
 #include "gf_launch.cuh"
 #include "gfx.cuh"
 #include "chart.cuh"
+#include "rng.cuh"
 #include "mlp_kernels.cuh"
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
@@ -922,6 +923,19 @@ extern "C" int jf_row_logmeanexp(int dtype, const void* in, int64_t rows, int64_
     const int64_t blocks = (rows * 32 + 255) / 256;
     if (dtype == JF_F64) row_logmeanexp_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)in, rows, cols, (double*)out);
     else if (dtype == JF_F32) row_logmeanexp_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)in, rows, cols, (float*)out);
+    else return JF_ERR_BAD_ARG;
+    return check_launch();
+}
+
+extern "C" int jf_normal_rows(int dtype, uint64_t seed, uint64_t first_row, int64_t B, int32_t dim, void* out,
+                              int64_t ld_out, void* stream) {
+    if (B < 0 || dim < 1 || ld_out < dim || (B > 0 && out == nullptr)) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = B * ((dim + 1) / 2);
+    const int64_t blocks = (n + 255) / 256;
+    if (dtype == JF_F64) normal_rows_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(seed, first_row, B, dim, (double*)out, ld_out);
+    else if (dtype == JF_F32) normal_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(seed, first_row, B, dim, (float*)out, ld_out);
     else return JF_ERR_BAD_ARG;
     return check_launch();
 }

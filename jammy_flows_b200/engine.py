@@ -478,6 +478,21 @@ def subpdf_logpdf(pdf, k, x_k, cond_segments, embedding_coordinates=False):
     return logdet + logbase
 
 
+def normal_rows(n_rows, dim, seed, first_row=0, dtype=torch.float64, device="cuda"):
+    """[n_rows, dim] standard normals generated on the device by the counter-based generator (`jf_normal_rows`): row i
+    depends only on (seed, first_row + i), so shards of one global batch agree with the unsharded draw."""
+    lib = _cabi.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("jammy_flows_b200: the device RNG needs a CUDA device (there is no CPU fallback)")
+    out = torch.empty(n_rows, dim, dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_normal_rows(_DT[dtype], int(seed) & (2 ** 64 - 1), int(first_row), n_rows, dim, _ptr(out), dim,
+                                _stream_ptr(dev))
+    _cabi.check(rc, "jf_normal_rows")
+    return out
+
+
 def row_logmeanexp(t):
     """[R, S] -> [R]: log(mean(exp(row))) on the device (jf_row_logmeanexp)."""
     lib = _cabi.load()

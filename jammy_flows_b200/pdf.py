@@ -80,7 +80,10 @@ class pdf(nn.Module):
         self._status_cache = {}
         # RNG used by sample(): "numpy" reproduces the reference's host RNG bit for bit (main/default.py:1661-1668);
         # "device" draws the normals with torch's Philox generator on the GPU (no host round trip).
+        # base-space normals of sample(): "numpy" = the reference's host RNG (bit-identical draws for a seed), "device" =
+        # torch's CUDA generator, "philox" = the library's counter-based generator (row i = f(seed, rng_first_row + i))
         self.rng_mode = "numpy"
+        self.rng_first_row = 0
         self.chunk_rows = None
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -496,6 +499,12 @@ class pdf(nn.Module):
                     numpy.random.seed(seed)
                 std_normal = numpy.random.normal(size=(used_sample_size, self.total_base_dim))
                 z = torch.from_numpy(std_normal).type(data_type).to(used_device)
+            elif self.rng_mode == "philox":
+                # counter-based device generator: row i = f(seed, first_row + i); `first_row` lets the ranks of a sharded
+                # job draw slices of one global stream (jammy_flows_b200.sharding.shard_base_normals)
+                used_seed = seed if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+                z = engine.normal_rows(used_sample_size, self.total_base_dim, used_seed, first_row=self.rng_first_row,
+                                       dtype=data_type, device=used_device)
             else:
                 gen = None
                 if seed is not None:

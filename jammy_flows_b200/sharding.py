@@ -32,6 +32,16 @@ def sample_seed_offset(n_rows, rank, world):
     return shard_range(n_rows, rank, world)[0]
 
 
+def shard_base_normals(n_rows, dim, seed, rank=None, world=None, dtype=torch.float64, device="cuda"):
+    """This rank's rows [lo, hi) of the global [n_rows, dim] base-space normal draw for `seed` (device Philox,
+    `jf_normal_rows`): the union over the ranks equals the single-process draw bit for bit, for any number of ranks."""
+    from . import engine
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    lo, hi = shard_range(n_rows, rank, world)
+    return engine.normal_rows(hi - lo, dim, seed, first_row=lo, dtype=dtype, device=device)
+
+
 def gather_rows(local, n_rows, group=None):
     """All-gather ragged row blocks back into the global [B, ...] tensor on every rank (inverse of `shard_rows`)."""
     world = dist.get_world_size(group)
