@@ -14,6 +14,12 @@
 //       offset: minus the input gradient.
 // Supported stages: isigmoid and inormal_partly_precise (bulk and Pade tails); per-row parameters only.
 #pragma once
+#ifndef JF_BWD_K_UNROLL
+#define JF_BWD_K_UNROLL 1
+#endif
+#define JF_BWD_PRAGMA_(x) _Pragma(#x)
+#define JF_BWD_PRAGMA(x) JF_BWD_PRAGMA_(x)
+#define JF_BWD_UNROLL JF_BWD_PRAGMA(unroll JF_BWD_K_UNROLL)
 #include "gf.cuh"
 #include "subpdf_args.cuh"
 
@@ -40,8 +46,10 @@ __device__ __noinline__ T bwd_regulate(const GfLayerC<T>& c, int K, int j, const
     const int64_t step = (int64_t)d * sj;
     T nmax = -Num<T>::big;
     if (c.norm_mode == JF_NORM_RAW)
+        JF_BWD_UNROLL
         for (int k = 0; k < K; ++k) nmax = tmax(nmax, pn[k * step]);
     T G = 0;
+    JF_BWD_UNROLL
     for (int k = 0; k < K; ++k) {
         sm[(size_t)k * nt] = pm[k * step];
         si[(size_t)k * nt] = regulate_inv_width(pw[k * step], c.w_min, c.inv_w_max);
@@ -68,6 +76,7 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
     // ---- pass 1: common rescaling exponent (all kernels on one side of v) ----
     bool any_pos = false, any_neg = false;
     T delta = Num<T>::big;
+    JF_BWD_UNROLL
     for (int k = 0; k < K; ++k) {
         const T a = (v - sm[(size_t)k * nt]) * si[(size_t)k * nt];
         any_pos = any_pos || (a >= T(0));
@@ -79,6 +88,7 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
     const T E = exp(-delta);
     // ---- pass 2: the rescaled sums (csrc/gf.cuh mix_eval without the softplus-threshold bookkeeping) ----
     T Sc = 0, Ss = 0, Sp = 0, Sd = 0;
+    JF_BWD_UNROLL
     for (int k = 0; k < K; ++k) {
         const T iw = si[(size_t)k * nt], n = sn[(size_t)k * nt] * invG;
         const T a = (v - sm[(size_t)k * nt]) * iw;
@@ -146,6 +156,7 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
     T* gw = gp + (int64_t)(c.raw_w() + j) * sj;
     T* gn = gp + (int64_t)(c.raw_n() + j) * sj;
     const int64_t step = (int64_t)d * sj;
+    JF_BWD_UNROLL
     for (int k = 0; k < K; ++k) {
         const T m = sm[(size_t)k * nt], iw = si[(size_t)k * nt], g = sn[(size_t)k * nt], n = g * invG;
         const T a = (v - m) * iw;
@@ -168,6 +179,7 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
         if (c.norm_mode != JF_NORM_NONE) gn[k * step] = nbar;       // finished below (needs nbar_dot)
     }
     if (c.norm_mode != JF_NORM_NONE) {
+        JF_BWD_UNROLL
         for (int k = 0; k < K; ++k) {
             const T g = sn[(size_t)k * nt];
             const T gbar = (gn[k * step] - nbar_dot) * invG;        // n_k = g_k / G
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(128) gf_chain_backward_kernel(const __grid_con
             T vbar;
             if (!gf_elem_backward<T>(c, c.K, j, v[j], xb[j], gr, G, slots, grow, sj, vbar)) {
                 ++n_bad;
+                JF_BWD_UNROLL
                 for (int k = 0; k < c.K; ++k) {       // no stage gradient for rows in the Pade tails
                     grow[(int64_t)(c.raw_m() + k * d + j) * sj] = T(0);
                     grow[(int64_t)(c.raw_w() + k * d + j) * sj] = T(0);
