@@ -9,6 +9,7 @@ VARIANTS = {
     "nopresolve": ["-DJF_PRESOLVE_F32=0"],
     "stop0": ["-DJF_PRE_STOP=1e-6"],
     "stop2e2": ["-DJF_PRE_STOP=2e-2"],
+    "noprefetch": ["-DJF_PREFETCH_NEXT_DIM=0"],
     "exp_imm": ["-DJF_EXP_CONST=0"],
     "quirk_inline": ["-DJF_QUIRK_OUTLINE=0"],
     "pre_cvt": ["-DJF_PRE_CVT=1"],
