@@ -17,8 +17,11 @@ struct GfChainArgs {
 //   D_ > 0: compile-time dimension (row vector fully in registers); D_ == 0: run-time d <= JF_MAX_DIM.
 //   num_kde is a run-time value (rolled loops over K).
 // Dynamic shared memory: the processed table (shared parameters) or 3*Kmax*blockDim.x per-thread slots (per-row).
+#ifndef JF_GF_MIN_BLOCKS
+#define JF_GF_MIN_BLOCKS 3
+#endif
 template <typename T, int D_, int DIR>
-__global__ void __launch_bounds__(256, 3) gf_chain_kernel(const __grid_constant__ GfChainArgs<T> g) {
+__global__ void __launch_bounds__(256, JF_GF_MIN_BLOCKS) gf_chain_kernel(const __grid_constant__ GfChainArgs<T> g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tab = reinterpret_cast<T*>(smem_raw);
     T* slots = tab;

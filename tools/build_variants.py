@@ -10,6 +10,8 @@ VARIANTS = {
     "stop0": ["-DJF_PRE_STOP=1e-6"],
     "stop2e2": ["-DJF_PRE_STOP=2e-2"],
     "noprefetch": ["-DJF_PREFETCH_NEXT_DIM=0"],
+    "minblk4": ["-DJF_GF_MIN_BLOCKS=4"],
+    "minblk2": ["-DJF_GF_MIN_BLOCKS=2"],
     "exp_imm": ["-DJF_EXP_CONST=0"],
     "quirk_inline": ["-DJF_QUIRK_OUTLINE=0"],
     "pre_cvt": ["-DJF_PRE_CVT=1"],
