@@ -343,7 +343,7 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
         // rounding noise of the residual (quadratic convergence shrinks it by orders of magnitude per step otherwise).
         // In fp32 the noise floor (~3e-6 for a Jacobian of condition ~10) sits ABOVE the fixed tolerance: without the
         // second test most rows ran into the iteration cap (measured: 780 evaluations per row on cfg4).
-        if (nrm <= tol || (nrm < T(1e-3) && nrm >= T(0.5) * prev_nrm)) {
+        if (nrm <= tol || (nrm < (sizeof(T) == 8 ? T(1e-9) : T(1e-3)) && nrm >= T(0.5) * prev_nrm)) {
             converged = true;
             if (nrm == T(0)) break;
         }
