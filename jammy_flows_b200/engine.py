@@ -286,6 +286,21 @@ def custom_mlp_forward(mlp, segs, R):
 
 
 def _pdf_staged(pdf, src, cond, direction):
+    """Row-chunked wrapper of `_pdf_staged_chunk` (the per-row parameter buffers are [rows, P]: bounded by the chunk)."""
+    chunk = int(pdf.chunk_rows or DEFAULT_CHUNK_ROWS)
+    R = src.shape[0]
+    if R <= chunk:
+        return _pdf_staged_chunk(pdf, src, cond, direction)
+    parts = []
+    for r0 in range(0, R, chunk):
+        c = None
+        if cond is not None:
+            c = [ci[r0:r0 + chunk] for ci in cond] if isinstance(cond, (list, tuple)) else cond[r0:r0 + chunk]
+        parts.append(_pdf_staged_chunk(pdf, src[r0:r0 + chunk], c, direction))
+    return tuple(torch.cat([p[i] for p in parts], dim=0) for i in range(3))
+
+
+def _pdf_staged_chunk(pdf, src, cond, direction):
     """Per-sub-pdf orchestration on the host: parameter generator (nn.Sequential or AmortizableMLP) -> layer chain, the
     embedding of each sub-pdf's target feeding the later generators (reference main/default.py:931-1053 / :1413-1514).
     Used when a generator is an AmortizableMLP, which the single-call C entries do not describe."""

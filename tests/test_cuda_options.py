@@ -197,6 +197,11 @@ def test_amortizable_mlp_module_matches_oracle(mode, lib_built):
     calm = z.abs().max(dim=1)[0] < 5.0
     assert float((rt_z - z).abs().max(dim=1)[0][calm].max()) < 1e-8
     assert float(((rt_lp - lp).abs() / lp.abs().clamp(min=1))[calm].max()) < 1e-8
+    # the staged path is row-chunked: any chunk size gives bit-identical results
+    p.chunk_rows = 7001
+    with torch.no_grad():
+        xs2, _, lp2, _ = p._obtain_sample(conditional_input=c, predefined_target_input=z)
+    assert torch.equal(xs, xs2) and torch.equal(lp, lp2)
 
 
 def test_failsafe_crosscheck_resamples_deviating_rows(lib_built):
