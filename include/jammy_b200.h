@@ -345,6 +345,17 @@ int jf_row_logmeanexp(int dtype, const void* in, int64_t rows, int64_t cols, voi
 int jf_normal_rows(int dtype, uint64_t seed, uint64_t first_row, int64_t B, int32_t dim, void* out, int64_t ld_out,
                    void* stream);
 
+/* One Linear layer whose weights differ from row to row -- the "being amortised" mode of the reference's AmortizableMLP
+ * (amortizable_mlp.py:470-585: `_adaptive_matmul`, `_apply_amortized_mlp` with use_permanent_parameters=False), run for
+ * every sub-pdf by pdf(..., amortize_everything=True) / fully_amortized_pdf (main/fully_amortized.py:22-278):
+ *   out[r, o] (+)= act( sum_i W_r[o, i] * in[r, i] + b_r[o] )
+ *   W_r[o, i] = params[r*ld_params + off_w + o*n_in + i],   b_r[o] = params[r*ld_params + off_b + o]  (off_b < 0: no bias)
+ *   act: 0 = identity, 1 = tanh;  accumulate != 0: out += ...;  out element (o, r) at out[o*out_stride_param + r*out_stride_row].
+ * A rank-k factorised layer U (V^T x) is two calls (n_out = k, then n_in = k).  HBM-bound: every weight is read once. */
+int jf_rowwise_linear(int dtype, const void* params, int64_t ld_params, int64_t off_w, int64_t off_b,
+                      const void* in, int64_t ld_in, int32_t n_in, int32_t n_out, int act, int accumulate,
+                      void* out, int64_t out_stride_param, int64_t out_stride_row, int64_t B, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 int jf_abi_version(void);
 /* FP64 DFMA / FP32 FFMA peak probe used as the roofline denominator of the compute-bound layer kernels:

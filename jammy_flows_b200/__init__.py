@@ -9,5 +9,6 @@ Same constructor / forward / sample / entropy surface as `jammy_flows.pdf` (refe
 main/default.py:42-151); the layer math runs in hand-written CUDA kernels behind a C-ABI (include/jammy_b200.h).
 """
 from .pdf import pdf  # noqa: F401
+from .fully_amortized import fully_amortized_pdf  # noqa: F401
 
 __version__ = "0.1.0"

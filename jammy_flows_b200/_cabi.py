@@ -110,6 +110,8 @@ SYMBOLS = {
     "jf_pdf_transform_target": (C.c_int, [C.POINTER(JfPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp]),
     "jf_row_logmeanexp": (C.c_int, [C.c_int, _vp, _i64, _i64, _vp, _vp]),
     "jf_normal_rows": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _i64, C.c_int32, _vp, _i64, _vp]),
+    "jf_rowwise_linear": (C.c_int, [C.c_int, _vp, _i64, _i64, _i64, _vp, _i64, C.c_int32, C.c_int32, C.c_int, C.c_int,
+                                    _vp, _i64, _i64, _i64, _vp]),
     "jf_abi_version": (C.c_int, []),
     "jf_probe_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), _vp]),
     "jf_launch_count": (_i64, []),

@@ -14,9 +14,13 @@ interchangeable and equal seeds give equal parameters.
 
 How it runs here: every chain is a plain Linear/tanh chain for the sm_100a MLP kernel (`jf_mlp_forward_acc`); low-rank
 factors are multiplied out once per call (out x r times r x in, tiny) so the kernel sees dense weights, and the
-connectivity modes are composed on the host from accumulating kernel launches (jammy_flows_b200/engine.py).  The
-"being amortised" use (`use_permanent_parameters=False`, per-row weights) belongs to `amortize_everything` and is not
-built.
+connectivity modes are composed on the host from accumulating kernel launches (jammy_flows_b200/engine.py).
+
+"Being amortised" (`use_permanent_parameters=False`, reference amortizable_mlp.py:233-246, :586-611): the module owns no
+parameters; `forward(i, extra_inputs=[B, num_amortization_params])` applies a DIFFERENT network to every row, its flat
+vector being that row of `extra_inputs` (what `pdf(..., amortize_everything=True)` / `fully_amortized_pdf` do for every
+sub-pdf).  Every layer is one `jf_rowwise_linear` launch (two for a factorised layer: V^T x, then U (.)), composed by
+`engine.amortized_mlp_forward` in the same connectivity modes.
 """
 import math
 
@@ -88,9 +92,6 @@ class AmortizableMLP(nn.Module):
             raise NotImplementedError("AmortizableMLP: only the tanh nonlinearity has an sm_100a kernel")
         if len(precise_mlp_structure.keys()) > 0:
             raise NotImplementedError("AmortizableMLP: precise_mlp_structure is not supported")
-        if not use_permanent_parameters:
-            raise NotImplementedError("AmortizableMLP in amortised mode (per-row weights, `amortize_everything`; "
-                                      "SURVEY.md section 8f rank 4) is not built")
         assert 0 <= highway_mode <= 4
         self.input_dim, self.output_dim = input_dim, output_dim
         self.highway_mode = highway_mode
@@ -129,8 +130,11 @@ class AmortizableMLP(nn.Module):
                 self.chains.append(_Chain([first, h[ind]], [h[ind], output_dim], ranks[2 * ind:2 * ind + 2], False, svd_mode))
             self.highway = _Chain([input_dim], [output_dim], ranks[-1:], True, svd_mode)
         self.num_amortization_params = sum(c.num_params for c in self.chains) + (self.highway.num_params if self.highway else 0)
-        self.u_v_b_pars = nn.Parameter(torch.randn(self.num_amortization_params).type(torch.double).unsqueeze(0))
-        self.initialize_uvbs()
+        if use_permanent_parameters:
+            self.u_v_b_pars = nn.Parameter(torch.randn(self.num_amortization_params).type(torch.double).unsqueeze(0))
+            self.initialize_uvbs()
+        else:
+            self.u_v_b_pars = None      # the flat vector arrives per row through forward(extra_inputs=...)
 
     # ---- initialisation (reference amortizable_mlp.py:375-466) -----------------------------------------------------
     def obtain_default_init_tensor(self, fix_final_bias=None, prev_damping_factor=1000.0):
@@ -171,7 +175,7 @@ class AmortizableMLP(nn.Module):
     # ---- structure for the engine / the test oracle ----------------------------------------------------------------
     def structure(self):
         conv = lambda c: dict(layers=[dict(l) for l in c.layers], num_params=c.num_params)
-        return dict(custom=True, highway_mode=self.highway_mode, input_dim=self.input_dim, output_dim=self.output_dim,
+        return dict(custom=True, amortised=not self.use_permanent_parameters, highway_mode=self.highway_mode, input_dim=self.input_dim, output_dim=self.output_dim,
                     chains=[conv(c) for c in self.chains], highway=conv(self.highway) if self.highway else None)
 
     def dense_weights(self, dtype, device):
@@ -186,7 +190,13 @@ class AmortizableMLP(nn.Module):
 
     def forward(self, i, extra_inputs=None):
         """[B, input_dim] (CUDA) -> [B, output_dim].  Reference: amortizable_mlp.py:586-682."""
-        if extra_inputs is not None:
-            raise Exception("MLP uses permanent parameters but extra inputs are given in forward. This is not allowed!")
         from . import engine
+        if extra_inputs is not None:
+            if self.use_permanent_parameters:
+                raise Exception("MLP uses permanent parameters but extra inputs are given in forward. This is not allowed!")
+            assert (extra_inputs.shape[1] == self.num_amortization_params), \
+                ("Extra inputs dimension (%d) does not match number of amortization params of MLP (%d) "
+                 % (extra_inputs.shape[1], self.num_amortization_params))
+            return engine.amortized_mlp_forward(self, [i], extra_inputs, i.shape[0])
+        assert (self.use_permanent_parameters)
         return engine.custom_mlp_forward(self, [i], i.shape[0])

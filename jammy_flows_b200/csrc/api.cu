@@ -16,6 +16,7 @@
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
 #include "gf_bwd.cuh"
+#include "rowwise.cuh"
 #include <cstdlib>
 
 using namespace jf;
@@ -938,6 +939,43 @@ extern "C" int jf_normal_rows(int dtype, uint64_t seed, uint64_t first_row, int6
     else if (dtype == JF_F32) normal_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(seed, first_row, B, dim, (float*)out, ld_out);
     else return JF_ERR_BAD_ARG;
     return check_launch();
+}
+
+template <typename T>
+static int rowwise_linear_t(const void* params, int64_t ld_p, int64_t off_w, int64_t off_b, const void* in, int64_t ld_in,
+                            int n_in, int n_out, int act, int accumulate, void* out, int64_t so_p, int64_t so_r, int64_t B,
+                            cudaStream_t st) {
+    const int n_in_pad = (n_in + 1) & ~1;
+    const size_t smem = (size_t)ROWWISE_WARPS * (n_in_pad + (n_in >= 32 ? 0 : ROWWISE_TILE)) * sizeof(T);
+    if (smem > 200 * 1024) return JF_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        JF_CUDA_OK(cudaFuncSetAttribute(rowwise_linear_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    JF_CUDA_OK(cudaGetDevice(&dev));
+    JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t blocks = (B + ROWWISE_WARPS - 1) / ROWWISE_WARPS;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    rowwise_linear_kernel<T><<<(unsigned)blocks, ROWWISE_WARPS * 32, smem, st>>>(
+        (const T*)params, ld_p, off_w, off_b, (const T*)in, ld_in, n_in, n_in_pad, n_out, act, accumulate, (T*)out, so_p,
+        so_r, B);
+    return check_launch();
+}
+
+extern "C" int jf_rowwise_linear(int dtype, const void* params, int64_t ld_params, int64_t off_w, int64_t off_b,
+                                 const void* in, int64_t ld_in, int32_t n_in, int32_t n_out, int act, int accumulate,
+                                 void* out, int64_t out_stride_param, int64_t out_stride_row, int64_t B, void* stream) {
+    if (B < 0 || n_in < 1 || n_out < 1 || off_w < 0 || ld_in < n_in) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    if (params == nullptr || in == nullptr || out == nullptr) return JF_ERR_BAD_ARG;
+    if (off_w + (int64_t)n_in * n_out > ld_params || (off_b >= 0 && off_b + n_out > ld_params)) return JF_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return rowwise_linear_t<double>(params, ld_params, off_w, off_b, in, ld_in, n_in, n_out, act ? 1 : 0,
+                                        accumulate ? 1 : 0, out, out_stride_param, out_stride_row, B, st);
+    if (dtype == JF_F32)
+        return rowwise_linear_t<float>(params, ld_params, off_w, off_b, in, ld_in, n_in, n_out, act ? 1 : 0,
+                                       accumulate ? 1 : 0, out, out_stride_param, out_stride_row, B, st);
+    return JF_ERR_BAD_ARG;
 }
 
 extern "C" int jf_abi_version(void) { return JF_ABI_VERSION; }

@@ -176,6 +176,8 @@ class ParamPack:
         self.c = _cabi.JfPdfParams()
         for k, layers in enumerate(pdf.layer_list):
             mlp = pdf.mlp_predictors[k]
+            if mlp is None and pdf.amortize_everything:
+                continue            # the flow parameters arrive per row in `amortization_parameters`
             if mlp is None:
                 vecs = [l.packed_permanent_params() for l in layers]
                 vecs = [v for v in vecs if v is not None]
@@ -285,22 +287,110 @@ def custom_mlp_forward(mlp, segs, R):
     return out
 
 
-def _pdf_staged(pdf, src, cond, direction):
+def sequential_mlp_forward(mlp, x):
+    """nn.Sequential(Linear, Tanh, ..., Linear) on x [R, in] -> [R, out] row-major (jf_mlp_forward_acc)."""
+    lib = _cabi.load()
+    _require_cuda(x, "MLP input")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    dt, dev, R = x.dtype, x.device, x.shape[0]
+    wb = [(l.weight.detach().to(device=dev, dtype=dt).contiguous(), l.bias.detach().to(device=dev, dtype=dt).contiguous())
+          for l in mlp if isinstance(l, torch.nn.Linear)]
+    out = torch.empty(R, wb[-1][0].shape[0], dtype=dt, device=dev)
+    _run_chain(lib, dt, dev, wb, [x], out, 1, out.shape[1], R, False)
+    return out
+
+
+def _rowwise_linear(lib, dt, dev, extra, off_w, off_b, inp, n_in, n_out, act, accumulate, out, R):
+    with torch.cuda.device(dev):
+        rc = lib.jf_rowwise_linear(_DT[dt], _ptr(extra), extra.stride(0), off_w, off_b, _ptr(inp), inp.stride(0), n_in,
+                                   n_out, 1 if act else 0, 1 if accumulate else 0, _ptr(out), 1, out.stride(0), R,
+                                   _stream_ptr(dev))
+    _cabi.check(rc, "jf_rowwise_linear")
+
+
+def amortized_mlp_forward(mlp, segs, extra, R):
+    """AmortizableMLP "being amortised": row r runs the network whose flat parameter vector is extra[r]
+    (reference amortizable_mlp.py:508-682 with `extra_inputs`; used by pdf(amortize_everything=True) and
+    fully_amortized_pdf).  Every layer is one `jf_rowwise_linear` launch that reads its weights straight out of `extra`
+    (column offsets follow the reference's layout: per layer U, V, bias; chains in order; the linear map last);
+    factorised layers are V^T x then U (.), as the reference multiplies them.  -> [R, output_dim] row-major."""
+    lib = _cabi.load()
+    _require_cuda(extra, "amortization parameters")
+    if extra.stride(1) != 1:
+        extra = extra.contiguous()
+    segs = [s_ for s_ in segs]
+    for s_ in segs:
+        _require_cuda(s_, "MLP input")
+    x = segs[0] if len(segs) == 1 else torch.cat(segs, dim=1)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    dt, dev = x.dtype, x.device
+    assert extra.dtype == dt and extra.device == dev and extra.shape[0] == R and x.shape[0] == R
+    assert extra.shape[1] == mlp.num_amortization_params
+    P = mlp.output_dim
+    out = torch.empty(R, P, dtype=dt, device=dev)
+
+    def run_chain(chain, pos, inp, accumulate):
+        h = inp
+        n = len(chain.layers)
+        for i, l in enumerate(chain.layers):
+            last = i == n - 1
+            off_u, off_v, off_b = pos, pos + l["n_u"], pos + l["n_u"] + l["n_v"]
+            pos = off_b + l["n_b"]
+            if l["n_b"] == 0:
+                off_b = -1
+            dst = out if last else torch.empty(R, l["n_out"], dtype=dt, device=dev)
+            assert h.shape[1] == l["n_in"], (h.shape, l)
+            if l["full"]:
+                _rowwise_linear(lib, dt, dev, extra, off_u, off_b, h, l["n_in"], l["n_out"], not last,
+                                last and accumulate, dst, R)
+            else:
+                mid = torch.empty(R, l["rank"], dtype=dt, device=dev)
+                _rowwise_linear(lib, dt, dev, extra, off_v, -1, h, l["n_in"], l["rank"], False, False, mid, R)
+                _rowwise_linear(lib, dt, dev, extra, off_u, off_b, mid, l["rank"], l["n_out"], not last,
+                                last and accumulate, dst, R)
+            h = dst
+
+    started = False
+    if mlp.highway is not None:
+        run_chain(mlp.highway, mlp.num_amortization_params - mlp.highway.num_params, x, False)
+        started = True
+    pos = 0
+    for ci, ch in enumerate(mlp.chains):
+        if ci == 0 or mlp.highway_mode <= 2:
+            inp = x
+        elif mlp.highway_mode == 3:
+            inp = out       # read by the chain's first launch, accumulated into by its last
+        else:
+            inp = torch.cat([x, out], dim=1)
+        run_chain(ch, pos, inp, started)
+        pos += ch.num_params
+        started = True
+    if not started:
+        out.zero_()
+    return out
+
+
+def _pdf_staged(pdf, src, cond, direction, amort=None):
     """Row-chunked wrapper of `_pdf_staged_chunk` (the per-row parameter buffers are [rows, P]: bounded by the chunk)."""
     chunk = int(pdf.chunk_rows or DEFAULT_CHUNK_ROWS)
     R = src.shape[0]
+    if amort is not None:
+        assert amort.shape[0] == R, "batch size of amortization_parameters must agree with the batch size of the input"
     if R <= chunk:
-        return _pdf_staged_chunk(pdf, src, cond, direction)
+        return _pdf_staged_chunk(pdf, src, cond, direction, amort)
     parts = []
     for r0 in range(0, R, chunk):
         c = None
         if cond is not None:
             c = [ci[r0:r0 + chunk] for ci in cond] if isinstance(cond, (list, tuple)) else cond[r0:r0 + chunk]
-        parts.append(_pdf_staged_chunk(pdf, src[r0:r0 + chunk], c, direction))
+        parts.append(_pdf_staged_chunk(pdf, src[r0:r0 + chunk], c, direction,
+                                       None if amort is None else amort[r0:r0 + chunk]))
     return tuple(torch.cat([p[i] for p in parts], dim=0) for i in range(3))
 
 
-def _pdf_staged_chunk(pdf, src, cond, direction):
+def _pdf_staged_chunk(pdf, src, cond, direction, amort=None):
     """Per-sub-pdf orchestration on the host: parameter generator (nn.Sequential or AmortizableMLP) -> layer chain, the
     embedding of each sub-pdf's target feeding the later generators (reference main/default.py:931-1053 / :1413-1514).
     Used when a generator is an AmortizableMLP, which the single-call C entries do not describe."""
@@ -316,12 +406,31 @@ def _pdf_staged_chunk(pdf, src, cond, direction):
     logdet = torch.empty(R, dtype=dt, device=dev)
     logbase = torch.empty(R, dtype=dt, device=dev)
     prev, keep = [], []
+    amort_pos = 0
+    if amort is not None:
+        # reference main/default.py:925-927 / :1404-1407: the whole pdf (flow parameters of a first sub-pdf without
+        # generator, then every generator's flat vector, in sub-pdf order) comes per row from `amortization_parameters`
+        _require_cuda(amort, "amortization_parameters")
+        assert amort.dtype == dt and amort.device == dev
+        assert amort.shape[1] == pdf.total_number_amortizable_params, (amort.shape[1], pdf.total_number_amortizable_params)
+        if amort.stride(1) != 1:
+            amort = amort.contiguous()
     for k, layers in enumerate(pdf.layer_list):
         mlp = pdf.mlp_predictors[k]
         segs = ([cond[k] if isinstance(cond, list) else cond] if cond is not None else []) + prev
         n_par = desc.sub[k].n_params
-        if mlp is None:
+        if mlp is None and amort is not None and n_par > 0:
+            view = amort[:, amort_pos:amort_pos + n_par]
+            amort_pos += n_par
+            params, sp, sr = _ptr(view), 1, amort.stride(0)
+        elif mlp is None:
             params, sp, sr = C.c_void_p(pack.c.shared[k]), 1, 0
+        elif amort is not None:
+            n_am = mlp.num_amortization_params
+            buf = amortized_mlp_forward(mlp, segs, amort[:, amort_pos:amort_pos + n_am], R)
+            amort_pos += n_am
+            keep.append(buf)
+            params, sp, sr = _ptr(buf), 1, n_par
         elif hasattr(mlp, "u_v_b_pars"):
             buf = custom_mlp_forward(mlp, segs, R)
             keep.append(buf)
@@ -351,10 +460,12 @@ def _pdf_staged_chunk(pdf, src, cond, direction):
     return dst, logdet, logbase
 
 
-def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True):
+def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True, amort=None):
     """-> (log_pdf [B], log_pdf_base [B], base [B, D_base]) on x's device.  Reference: main/default.py:1059-1117."""
-    if uses_custom_mlp(pdf):
-        base, logdet, logbase = _pdf_staged(pdf, x, cond, _cabi.JF_DIR_LOGPDF)
+    if pdf.amortize_everything and amort is None:
+        raise AssertionError("a pdf built with amortize_everything needs amortization_parameters")
+    if uses_custom_mlp(pdf) or amort is not None:
+        base, logdet, logbase = _pdf_staged(pdf, x, cond, _cabi.JF_DIR_LOGPDF, amort)
         return logdet + logbase, logbase, base
     lib = _cabi.load()
     x, cond = _prep_inputs(pdf, x, cond, "x")
@@ -377,10 +488,12 @@ def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True):
     return logp, logp_base, base
 
 
-def pdf_sample(pdf, z, cond=None, chunk_rows=None):
+def pdf_sample(pdf, z, cond=None, chunk_rows=None, amort=None):
     """z [B, D_base] -> (x [B, D], log_pdf [B], log_pdf_base [B]).  Reference: main/default.py:1373-1531, :1533-1707."""
-    if uses_custom_mlp(pdf):
-        xs, logdet, logbase = _pdf_staged(pdf, z, cond, _cabi.JF_DIR_SAMPLE)
+    if pdf.amortize_everything and amort is None:
+        raise AssertionError("a pdf built with amortize_everything needs amortization_parameters")
+    if uses_custom_mlp(pdf) or amort is not None:
+        xs, logdet, logbase = _pdf_staged(pdf, z, cond, _cabi.JF_DIR_SAMPLE, amort)
         return xs, logbase - logdet, logbase
     lib = _cabi.load()
     z, cond = _prep_inputs(pdf, z, cond, "base sample")

@@ -50,8 +50,6 @@ class pdf(nn.Module):
         """Same parameters as the reference constructor (main/default.py:44-100)."""
         super().__init__()
         not_built = []
-        if amortize_everything:
-            not_built.append("amortize_everything (fully amortized pdf, section 8f rank 4)")
         if predict_log_normalization:
             not_built.append("predict_log_normalization (Poisson log-lambda head)")
         if use_as_passthrough_instead_of_pdf:
@@ -69,6 +67,11 @@ class pdf(nn.Module):
         self.use_as_passthrough_instead_of_pdf = use_as_passthrough_instead_of_pdf
         self.skip_mlp_initialization = skip_mlp_initialization
         self.total_number_amortizable_params = None
+        if self.amortize_everything:
+            # reference main/default.py:109-120
+            assert (self.predict_log_normalization == False), "Log Poisson prediction works only without full amortization in the default PDF. It can be used in the *fully_amortized_pdf*!"
+            assert (self.amortization_mlp_use_custom_mode), "Amortizing all MLPs requires custom MLPs."
+            self.total_number_amortizable_params = 0
 
         self.read_model_definition(pdf_defs, flow_defs, options_overwrite, conditional_input_dim, amortization_mlp_dims,
                                    amortization_mlp_ranks, verbose=verbose)
@@ -159,7 +162,8 @@ class pdf(nn.Module):
         self.layer_list = nn.ModuleList()
         self.force_permanent_parameters_in_first_subpdf = 0
         if self.conditional_input_dim is None:
-            self.force_permanent_parameters_in_first_subpdf = 1
+            if self.amortize_everything == False:          # reference main/default.py:323-325
+                self.force_permanent_parameters_in_first_subpdf = 1
 
     # ------------------------------------------------------------------------------------------------------------------
     # layer graph (reference main/default.py:378-479)
@@ -253,6 +257,10 @@ class pdf(nn.Module):
             if pdf_index == 0 and self.conditional_input_dim is None:
                 self.mlp_predictors.append(None)
                 prev_extra_input_num += emb_num
+                if self.amortize_everything:
+                    # no generator in front of the first sub-pdf: its flow parameters are amortized directly
+                    # (reference main/default.py:595-598)
+                    self.total_number_amortizable_params += sum(self.num_parameter_list[0])
                 continue
             num_predicted_pars = sum(self.num_parameter_list[pdf_index])
             if num_predicted_pars == 0:
@@ -270,8 +278,11 @@ class pdf(nn.Module):
                 from .amortizable_mlp import AmortizableMLP
                 self.mlp_predictors.append(AmortizableMLP(
                     this_summary_dim, hidden, num_predicted_pars,
-                    low_rank_approximations=self.amortization_mlp_ranks[pdf_index], use_permanent_parameters=True,
+                    low_rank_approximations=self.amortization_mlp_ranks[pdf_index],
+                    use_permanent_parameters=self.amortize_everything == False,
                     highway_mode=self.amortization_mlp_highway_mode, svd_mode="smart"))
+                if self.amortize_everything:
+                    self.total_number_amortizable_params += self.mlp_predictors[-1].num_amortization_params
                 prev_extra_input_num += emb_num
                 continue
             mlp_in_dims = [this_summary_dim] + hidden
@@ -291,6 +302,11 @@ class pdf(nn.Module):
     # ------------------------------------------------------------------------------------------------------------------
     def init_params(self, data=None, damping_factor=1000.0, mvn_min_max_sv_ratio=1e-4):
         from .init_fns import find_init_pars_of_chained_blocks
+        # amortize_everything: nothing is stored here; the desired values of the whole per-row vector are returned
+        # (reference main/default.py:1828-1832, :1900-1904, :1944-1946) and end up in the last bias of the outer generator
+        global_amortization_init, global_amortization_index = None, 0
+        if self.amortize_everything:
+            global_amortization_init = torch.zeros(self.total_number_amortizable_params)
         with torch.no_grad():
             if data is not None:
                 assert (data.shape[1] == self.total_target_dim), "Initialization with data must match the target dimension of the PDF!"
@@ -313,7 +329,13 @@ class pdf(nn.Module):
                 these_params = params_list[ind]
                 if len(these_params) == 0:
                     continue
-                if mlp_predictor is not None and hasattr(mlp_predictor, "initialize_uvbs"):
+                if mlp_predictor is not None and hasattr(mlp_predictor, "initialize_uvbs") and self.amortize_everything:
+                    n_uvb = mlp_predictor.num_amortization_params
+                    global_amortization_init[global_amortization_index:global_amortization_index + n_uvb] = \
+                        mlp_predictor.obtain_default_init_tensor(fix_final_bias=these_params,
+                                                                 prev_damping_factor=damping_factor)
+                    global_amortization_index += n_uvb
+                elif mlp_predictor is not None and hasattr(mlp_predictor, "initialize_uvbs"):
                     # custom low-rank MLPs initialise themselves (reference main/default.py:1896-1904)
                     mlp_predictor.initialize_uvbs(fix_final_bias=these_params, prev_damping_factor=damping_factor)
                 elif mlp_predictor is not None:
@@ -330,10 +352,14 @@ class pdf(nn.Module):
                     tot_param_index = 0
                     for layer in self.layer_list[ind]:
                         n = layer.get_total_param_num()
-                        layer.init_params(these_params[tot_param_index:tot_param_index + n])
+                        if self.amortize_everything == False:
+                            layer.init_params(these_params[tot_param_index:tot_param_index + n])
                         tot_param_index += n
+                    if self.amortize_everything:
+                        global_amortization_init[global_amortization_index:global_amortization_index + tot_param_index] = these_params
+                        global_amortization_index += tot_param_index
         self._desc_cache = {}
-        return None
+        return global_amortization_init
 
     # reference main/default.py:724-830
     def count_parameters(self, verbose=False):
@@ -402,8 +428,9 @@ class pdf(nn.Module):
     def forward(self, x, conditional_input=None, amortization_parameters=None, force_embedding_coordinates=False,
                 force_intrinsic_coordinates=False, only_last=False):
         assert (self.use_as_passthrough_instead_of_pdf == False)
-        if amortization_parameters is not None or only_last:
-            raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
+        if only_last:
+            raise NotImplementedError("only_last is outside the hot path built so far")
+        self._check_amortization_parameters(amortization_parameters, x.shape[0])
         if type(conditional_input) == list:
             # one conditional input per sub-pdf (reference main/default.py:1092-1103)
             assert (type(self.conditional_input_dim) == list and len(self.conditional_input_dim) == len(conditional_input))
@@ -425,23 +452,41 @@ class pdf(nn.Module):
         elif force_intrinsic_coordinates:
             assert (x.shape[1] == self.total_target_dim_intrinsic)
         assert (x.shape[1] == self.total_target_dim), (x.shape[1], self.total_target_dim)
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_grad and engine.supports_backward(self):
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                                  (amortization_parameters is not None and amortization_parameters.requires_grad))
+        if needs_grad and amortization_parameters is None and engine.supports_backward(self):
             # training path: fused forward AND backward layer kernels, torch autograd only for the parameter generator
             return engine.pdf_logpdf_trainable(self, x, conditional_input)
-        log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows)
+        amort = amortization_parameters.detach() if amortization_parameters is not None else None
+        log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows,
+                                                            amort=amort)
         if chart_log_det is not None:
             log_pdf = log_pdf + chart_log_det
         if needs_grad:
-            log_pdf, log_pdf_base, base_pos = _NoBackward.apply(self._anchor(), log_pdf, log_pdf_base, base_pos)
+            anchor = amortization_parameters if (amortization_parameters is not None and
+                                                 amortization_parameters.requires_grad) else self._anchor()
+            log_pdf, log_pdf_base, base_pos = _NoBackward.apply(anchor, log_pdf, log_pdf_base, base_pos)
         return log_pdf, log_pdf_base, base_pos
+
+    def _check_amortization_parameters(self, amortization_parameters, batch):
+        """reference main/default.py:925-927, :1404-1409, :1591-1595"""
+        if amortization_parameters is None:
+            assert (self.amortize_everything == False), "a pdf built with amortize_everything needs amortization_parameters"
+            return
+        assert (self.amortize_everything), "amortization_parameters require a pdf built with amortize_everything=True"
+        assert (amortization_parameters.dim() == 2 and
+                amortization_parameters.shape[1] == self.total_number_amortizable_params), \
+            (amortization_parameters.shape, self.total_number_amortizable_params)
+        assert (amortization_parameters.shape[0] == batch), "batch size of amortization_parameters must agree with the batch size of the input"
 
     def all_layer_inverse(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
                           force_intrinsic_coordinates=False, only_last=False):
         """target -> base through every sub-pdf (reference main/default.py:879-1057)."""
+        self._check_amortization_parameters(amortization_parameters, x.shape[0])
         if force_embedding_coordinates and self._needs_transform():
             x, log_det = engine.pdf_transform_target(self, x, log_det, to_embedding=False)
-        logp, logp_base, base = engine.pdf_logpdf(self, x, data_summary, chunk_rows=self.chunk_rows)
+        logp, logp_base, base = engine.pdf_logpdf(self, x, data_summary, chunk_rows=self.chunk_rows,
+                                                  amort=amortization_parameters)
         return base, log_det + (logp - logp_base)
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -465,10 +510,23 @@ class pdf(nn.Module):
                        amortization_parameters=None, force_embedding_coordinates=False,
                        force_intrinsic_coordinates=False, failsafe_crosscheck_tolerance=None, dtype=None, device=None,
                        only_last=False):
-        if amortization_parameters is not None or only_last:
-            raise NotImplementedError("amortization_parameters / only_last are outside the hot path built so far")
+        if only_last:
+            raise NotImplementedError("only_last is outside the hot path built so far")
         used_sample_size = samplesize
-        if type(conditional_input) == list:
+        if self.amortize_everything:
+            # reference main/default.py:1591-1606: batch, dtype and device come from the amortization parameters
+            assert (amortization_parameters is not None)
+            self._check_amortization_parameters(amortization_parameters, amortization_parameters.shape[0])
+            amortization_parameters = amortization_parameters.detach()
+            used_sample_size = amortization_parameters.shape[0]
+            data_type, used_device = amortization_parameters.dtype, amortization_parameters.device
+            if conditional_input is not None:
+                c0 = conditional_input[0] if type(conditional_input) == list else conditional_input
+                assert (c0.shape[0] == used_sample_size and c0.device == used_device)
+                assert (c0.dtype == data_type), "Dtypes between conditional_input and amortization_paramters have to agree!"
+        elif amortization_parameters is not None:
+            self._check_amortization_parameters(amortization_parameters, 0)
+        elif type(conditional_input) == list:
             assert (type(self.conditional_input_dim) == list and len(self.conditional_input_dim) == len(conditional_input))
             for ci_ind, ci in enumerate(conditional_input):
                 assert (self.conditional_input_dim[ci_ind] == ci.shape[1]), "Inputs of conditional input vector do not match with pre-defined input_dims!"
@@ -493,36 +551,43 @@ class pdf(nn.Module):
             elif conditional_input is not None:
                 assert (z.shape[0] == conditional_input.shape[0] and z.dtype == conditional_input.dtype)
         else:
-            if self.rng_mode == "numpy":
-                # reference: host numpy RNG then H2D copy (main/default.py:1661-1668)
-                if seed is not None:
-                    numpy.random.seed(seed)
-                std_normal = numpy.random.normal(size=(used_sample_size, self.total_base_dim))
-                z = torch.from_numpy(std_normal).type(data_type).to(used_device)
-            elif self.rng_mode == "philox":
-                # counter-based device generator: row i = f(seed, first_row + i); `first_row` lets the ranks of a sharded
-                # job draw slices of one global stream (jammy_flows_b200.sharding.shard_base_normals)
-                used_seed = seed if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
-                z = engine.normal_rows(used_sample_size, self.total_base_dim, used_seed, first_row=self.rng_first_row,
-                                       dtype=data_type, device=used_device)
-            else:
-                gen = None
-                if seed is not None:
-                    gen = torch.Generator(device=used_device)
-                    gen.manual_seed(seed)
-                z = torch.randn(used_sample_size, self.total_base_dim, dtype=data_type, device=used_device, generator=gen)
+            z = self._draw_base_normals(used_sample_size, seed, data_type, used_device)
             std_normal_samples = z
-        x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows)
+        x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows,
+                                                  amort=amortization_parameters)
         if force_embedding_coordinates and self._needs_transform():
             # reference main/default.py:1522-1524: default -> embedding coordinates, log p = log N(z) - (logdet + chart)
             x, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)
             log_pdf = log_pdf - chart_log_det
         if failsafe_crosscheck_tolerance:
             assert (predefined_target_input is None), "Failsafe does not work with predefined input!"
+            if amortization_parameters is not None:
+                raise NotImplementedError("failsafe_crosscheck_tolerance together with amortization_parameters")
             x, std_normal_samples, log_pdf, log_gauss = self._recheck_sampling(
                 x, std_normal_samples, log_pdf, log_gauss, failsafe_crosscheck_tolerance, conditional_input,
                 force_embedding_coordinates, force_intrinsic_coordinates, data_type, used_device)
         return x, std_normal_samples, log_pdf, log_gauss
+
+    def _draw_base_normals(self, n, seed, data_type, device):
+        """[n, total_base_dim] standard normals according to `rng_mode`."""
+        if self.rng_mode == "numpy":
+            # reference: host numpy RNG then H2D copy (main/default.py:1661-1668)
+            if seed is not None:
+                numpy.random.seed(seed)
+            std_normal = numpy.random.normal(size=(n, self.total_base_dim))
+            return torch.from_numpy(std_normal).type(data_type).to(device)
+        elif self.rng_mode == "philox":
+            # counter-based device generator: row i = f(seed, first_row + i); `first_row` lets the ranks of a sharded
+            # job draw slices of one global stream (jammy_flows_b200.sharding.shard_base_normals)
+            used_seed = seed if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+            return engine.normal_rows(n, self.total_base_dim, used_seed, first_row=self.rng_first_row,
+                                      dtype=data_type, device=device)
+        else:
+            gen = None
+            if seed is not None:
+                gen = torch.Generator(device=device)
+                gen.manual_seed(seed)
+            return torch.randn(n, self.total_base_dim, dtype=data_type, device=device, generator=gen)
 
     def _recheck_sampling(self, x, z, log_pdf, log_gauss, tol, conditional_input, force_emb, force_intr, dtype, device):
         """Round-trip check of a sample and re-draw of the rows that fail it (reference extra_functions.py:413-533,
@@ -551,7 +616,9 @@ class pdf(nn.Module):
     def all_layer_forward(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
                           force_intrinsic_coordinates=False, only_last=False):
         """base -> target through every sub-pdf (reference main/default.py:1373-1531)."""
-        xs, logp, logp_base = engine.pdf_sample(self, x, data_summary, chunk_rows=self.chunk_rows)
+        self._check_amortization_parameters(amortization_parameters, x.shape[0])
+        xs, logp, logp_base = engine.pdf_sample(self, x, data_summary, chunk_rows=self.chunk_rows,
+                                                amort=amortization_parameters)
         log_det = log_det + (logp_base - logp)
         if force_embedding_coordinates and self._needs_transform():
             xs, log_det = engine.pdf_transform_target(self, xs, log_det, to_embedding=True)

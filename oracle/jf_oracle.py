@@ -1182,6 +1182,8 @@ class OraclePdf:
     def _custom_mlp(m, flat, x):
         """AmortizableMLP with permanent parameters.  Reference: amortizable_mlp.py:508-682 (U (V^T x) for factorised
         layers, connectivity modes 0-4)."""
+        if flat.dim() == 2 and m.get("amortised", False):
+            return OraclePdf._custom_mlp_rows(m, flat, x)
         flat = flat.reshape(-1)
 
         def chain(spec, pars, inp):
@@ -1224,8 +1226,78 @@ class OraclePdf:
             prev = prev + nonlinear
         return prev
 
+    @staticmethod
+    def _custom_mlp_rows(m, rows, x):
+        """AmortizableMLP "being amortised": row b applies the network encoded by rows[b] (per-row weights).
+        Reference: amortizable_mlp.py:470-585 (`_adaptive_matmul`: bmm of the [B, out, in] view with the input) and
+        :586-682; same layout and connectivity as the permanent-parameter case above."""
+        def chain(spec, pars, inp):
+            h, pos = inp, 0
+            n = len(spec["layers"])
+            for i, l in enumerate(spec["layers"]):
+                u = pars[:, pos:pos + l["n_u"]]
+                pos += l["n_u"]
+                v = pars[:, pos:pos + l["n_v"]]
+                pos += l["n_v"]
+                b = pars[:, pos:pos + l["n_b"]]
+                pos += l["n_b"]
+                if l["full"]:
+                    h = torch.einsum("bij,bj->bi", u.reshape(-1, l["n_out"], l["n_in"]), h)
+                else:
+                    mid = torch.einsum("bij,bj->bi", v.reshape(-1, l["rank"], l["n_in"]), h)
+                    h = torch.einsum("bij,bj->bi", u.reshape(-1, l["n_out"], l["rank"]), mid)
+                if l["n_b"] > 0:
+                    h = h + b
+                if i < n - 1:
+                    h = torch.tanh(h)
+            return h
+
+        mode = m["highway_mode"]
+        prev = 0.0
+        if mode > 0:
+            hw = m["highway"]
+            prev = chain(hw, rows[:, -hw["num_params"]:], x)
+        pos = 0
+        nxt = x
+        for ci, ch in enumerate(m["chains"]):
+            nonlinear = chain(ch, rows[:, pos:pos + ch["num_params"]], x if ci == 0 else nxt)
+            pos += ch["num_params"]
+            if mode == 3:
+                nxt = prev + nonlinear
+            elif mode == 4:
+                nxt = torch.cat([x, prev + nonlinear], dim=1)
+            else:
+                nxt = x
+            prev = prev + nonlinear
+        return prev
+
+    def _split_amortization(self, amort):
+        """amortization_parameters [B, T] -> per sub-pdf column block (flow parameters of a first sub-pdf without
+        generator, else the flat vector of its generator), in sub-pdf order.  Reference: main/default.py:925-991."""
+        self._amort = None
+        if amort is None:
+            return
+        amort = torch.as_tensor(np.asarray(amort)).to(self.dtype)
+        out, pos = [], 0
+        for sp in self.prog["subpdfs"]:
+            m = sp["mlp"]
+            if m is not None:
+                n = sum(c["num_params"] for c in m["chains"]) + (m["highway"]["num_params"] if m["highway"] else 0)
+            else:
+                n = sp["layer_param_ranges"][-1][1] if len(sp["layer_param_ranges"]) else 0
+            out.append(amort[:, pos:pos + n])
+            pos += n
+        assert pos == amort.shape[1], (pos, amort.shape)
+        self._amort = out
+
     def _sub_params(self, k, cond, prev_emb, batch):
         sp = self.prog["subpdfs"][k]
+        am = getattr(self, "_amort", None)
+        if am is not None:
+            if sp["mlp"] is None:
+                return am[k]
+            pieces = ([cond] if cond is not None else []) + prev_emb
+            return self._custom_mlp(sp["mlp"], am[k], torch.cat(pieces, dim=1))
         if sp["mlp"] is not None:
             if isinstance(cond, (list, tuple)):          # one conditional input per sub-pdf (main/default.py:944-949)
                 cond = cond[k]
@@ -1325,9 +1397,11 @@ class OraclePdf:
             return [torch.as_tensor(np.asarray(c)).to(self.dtype) for c in cond]
         return torch.as_tensor(np.asarray(cond)).to(self.dtype)
 
-    def log_pdf(self, x, cond=None):
+    def log_pdf(self, x, cond=None, amort=None):
+        """amort: amortization_parameters [B, T] of a pdf built with amortize_everything (main/default.py:1062-1076)."""
         x = torch.as_tensor(np.asarray(x)).to(self.dtype)
         cond = self._as_cond(cond)
+        self._split_amortization(amort)
         b = x.shape[0]
         log_det = torch.zeros(b, dtype=self.dtype)
         prev_emb, base = [], []
@@ -1342,12 +1416,14 @@ class OraclePdf:
             base.append(cur)
             prev_emb.append(layers[-1].embedding(x[:, t0:t1]))
         base = torch.cat(base, dim=1)
+        self._amort = None
         logp_base = (-0.5 * base ** 2 - LOG_SQRT_2PI).sum(dim=-1)
         return logp_base + log_det, logp_base, base
 
-    def sample(self, z, cond=None):
+    def sample(self, z, cond=None, amort=None):
         z = torch.as_tensor(np.asarray(z)).to(self.dtype)
         cond = self._as_cond(cond)
+        self._split_amortization(amort)
         b = z.shape[0]
         log_det = torch.zeros(b, dtype=self.dtype)
         prev_emb, out = [], []
@@ -1362,5 +1438,27 @@ class OraclePdf:
             out.append(cur)
             prev_emb.append(layers[-1].embedding(cur))
         x = torch.cat(out, dim=1)
+        self._amort = None
         logp_base = (-0.5 * z ** 2 - LOG_SQRT_2PI).sum(dim=-1)
         return x, logp_base - log_det, logp_base
+
+
+def fully_amortized_parameters(outer_spec, params, cond, dtype=torch.float64):
+    """Outer generator of `fully_amortized_pdf`: conditional input [B, C] -> amortization parameters [B, T], which
+    OraclePdf.log_pdf / sample take as `amort`.  Reference: main/fully_amortized.py:96-131 (construction), :175 / :218
+    (`all_flow_params=self.amortization_mlp(conditional_input)`).
+    outer_spec: AmortizableMLP structure dict (custom mode, parameters `amortization_mlp.u_v_b_pars`) or
+    dict(linear_indices=[...]) for the plain nn.Sequential(Linear, Tanh, ..., Linear)."""
+    cond = torch.as_tensor(np.asarray(cond)).to(dtype)
+    if outer_spec.get("custom", False):
+        flat = torch.as_tensor(np.asarray(params["amortization_mlp.u_v_b_pars"])).to(dtype)
+        return OraclePdf._custom_mlp(dict(outer_spec, amortised=False), flat, cond)
+    h = cond
+    idx = outer_spec["linear_indices"]
+    for li, i in enumerate(idx):
+        w = torch.as_tensor(np.asarray(params["amortization_mlp.%d.weight" % i])).to(dtype)
+        b = torch.as_tensor(np.asarray(params["amortization_mlp.%d.bias" % i])).to(dtype)
+        h = F.linear(h, w, b)
+        if li < len(idx) - 1:
+            h = torch.tanh(h)
+    return h

@@ -287,11 +287,78 @@ def build_case(jf, name, spec):
     return out
 
 
+# fully_amortized_pdf (main/fully_amortized.py:22-278): one outer generator predicts, per row, the flow parameters AND the
+# weights of every inner AmortizableMLP (pdf(..., amortize_everything=True); amortizable_mlp.py:586-611 with
+# extra_inputs).  Inner connectivity modes 0-4, dense and factorised per-row layers, inner widths below and above 32.
+FA_CASES = {
+    "fa_e2s2e2_lowrank_mode1": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=120, perturb=0.05,
+                                    fa_kw=dict(conditional_input_dim=3, inner_mlp_dims_sub_pdfs="16", inner_mlp_ranks=3,
+                                               inner_mlp_highway_mode=1, amortization_mlp_dims="32",
+                                               amortization_mlp_ranks=5, amortization_mlp_highway_mode=0)),
+    "fa_e2e1_dense_mode4_seq": dict(pdf_defs="e2+e1", flow_defs="gg+g", n=120, perturb=0.05,
+                                    fa_kw=dict(conditional_input_dim=2, inner_mlp_dims_sub_pdfs="8-6", inner_mlp_ranks=0,
+                                               inner_mlp_highway_mode=4, amortization_mlp_dims="16",
+                                               amortization_mlp_use_custom_mode=False)),
+    "fa_e3i1_wide_mode0": dict(pdf_defs="e3+i1", flow_defs="gg+r", n=60, perturb=0.05,
+                               fa_kw=dict(conditional_input_dim=4, inner_mlp_dims_sub_pdfs="40", inner_mlp_ranks="3-0",
+                                          inner_mlp_highway_mode=0, amortization_mlp_dims="24",
+                                          amortization_mlp_ranks=4, amortization_mlp_highway_mode=1)),
+    "fa_e1e2_mode3": dict(pdf_defs="e1+e2", flow_defs="g+gg", n=60, perturb=0.05,
+                          fa_kw=dict(conditional_input_dim=2, inner_mlp_dims_sub_pdfs="34-5", inner_mlp_ranks=0,
+                                     inner_mlp_highway_mode=3, amortization_mlp_dims="16", amortization_mlp_ranks=3,
+                                     amortization_mlp_highway_mode=2)),
+    "fa_e1s1_lowrank_mode2": dict(pdf_defs="e1+s1", flow_defs="gg+m", n=120, perturb=0.05,
+                                  fa_kw=dict(conditional_input_dim=2, inner_mlp_dims_sub_pdfs="12-7",
+                                             inner_mlp_ranks="2-3-2-2-1", inner_mlp_highway_mode=2,
+                                             amortization_mlp_dims="16", amortization_mlp_ranks=3)),
+}
+
+
+def build_fa_case(jf, name, spec):
+    seed = 1
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    fa = jf.fully_amortized_pdf(spec["pdf_defs"], spec["flow_defs"], **spec["fa_kw"])
+    # with a plain nn.Sequential outer generator the reference's init leaves the last bias in float32
+    # (main/fully_amortized.py:253 assigns the float32 init vector): cast back as a user has to
+    fa = fa.double()
+    gen = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        for _, p in fa.named_parameters():
+            p.add_(spec["perturb"] * torch.randn(p.shape, generator=gen, dtype=torch.float64).to(p.dtype))
+    n = spec["n"]
+    x = make_inputs(spec["pdf_defs"], n, gen)
+    cond = torch.randn(n, spec["fa_kw"]["conditional_input_dim"], generator=gen, dtype=torch.float64)
+    inner = fa.pdf_to_amortize
+    z = torch.randn(n, inner.total_base_dim, generator=gen, dtype=torch.float64)
+    with torch.no_grad():
+        amort = fa.amortization_mlp(cond)
+        logp, logp_base, base = fa(x, conditional_input=cond)
+        samp_x, _, samp_logp, samp_logp_base = inner._obtain_sample(amortization_parameters=amort,
+                                                                    predefined_target_input=z)
+        rt_logp, _, rt_base = fa(samp_x, conditional_input=cond)
+    out = {
+        "meta": json.dumps(dict(name=name, pdf_defs=spec["pdf_defs"], flow_defs=spec["flow_defs"], fa_kw=spec["fa_kw"],
+                                dtype="float64", perturb=spec["perturb"], seed=seed,
+                                total_number_amortizable_params=int(inner.total_number_amortizable_params),
+                                total_param_num=int(fa.total_param_num),
+                                reference="thoglu/jammy_flows v1.1.0 @ /root/reference, torch %s CPU" % torch.__version__)),
+        "x": x.numpy(), "z": z.numpy(), "cond": cond.numpy(), "amort_head": amort[:8].numpy(),
+        "logp": logp.numpy(), "logp_base": logp_base.numpy(), "base": base.numpy(),
+        "samp_x": samp_x.numpy(), "samp_logp": samp_logp.numpy(), "samp_logp_base": samp_logp_base.numpy(),
+        "ref_roundtrip_base_err": np.nanmax(np.abs((rt_base - z).numpy())),
+        "ref_roundtrip_logp_err": np.nanmax(np.abs((rt_logp - samp_logp).numpy())),
+    }
+    for k, v in fa.state_dict().items():
+        out["param/" + k] = v.numpy()
+    return out
+
+
 def main():
     jf = import_reference()
-    names = sys.argv[1:] or list(CASES.keys())
+    names = sys.argv[1:] or (list(CASES.keys()) + list(FA_CASES.keys()))
     for name in names:
-        out = build_case(jf, name, CASES[name])
+        out = build_fa_case(jf, name, FA_CASES[name]) if name in FA_CASES else build_case(jf, name, CASES[name])
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
         print("%-32s logp[0:2]=%s rt_base_err=%.2e rt_logp_err=%.2e  %.1f KB" % (

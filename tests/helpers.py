@@ -14,7 +14,25 @@ EPS = {"float64": 2.220446049250313e-16, "float32": 1.1920929e-07}
 
 
 def golden_names():
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """goldens of `pdf` (the `fa_*` files hold `fully_amortized_pdf` cases: fa_golden_names)"""
+    return sorted(n for n in (os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("fa_"))
+
+
+def fa_golden_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "fa_*.npz")))
+
+
+def build_fa(meta, params=None, seed=None):
+    """Construct jammy_flows_b200.fully_amortized_pdf as the golden's reference model was constructed."""
+    import jammy_flows_b200 as jfb
+    if seed is not None:
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+    fa = jfb.fully_amortized_pdf(meta["pdf_defs"], meta["flow_defs"], **meta["fa_kw"])
+    if params is not None:
+        fa.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in params.items()})
+    return fa
 
 
 def load_golden(name):
@@ -90,3 +108,10 @@ def base_tolerance(p, dtype, base_ref):
             b0, b1 = p.base_dim_indices[k]
             extra = np.maximum(extra, icdf_conditioning(base_ref[:, b0:b1], dtype).max(axis=1))
     return tol + extra
+
+
+def fa_outer_spec(fa):
+    """plain-dict description of the outer generator of a fully_amortized_pdf for the oracle"""
+    if fa.use_amortizable_mlp:
+        return fa.amortization_mlp.structure()
+    return dict(linear_indices=[i for i, m in enumerate(fa.amortization_mlp) if isinstance(m, torch.nn.Linear)])

@@ -63,10 +63,11 @@ def test_conditional_wiring_dims():
 
 
 def test_unsupported_fails_loudly():
-    for kw in (dict(amortize_everything=True, amortization_mlp_use_custom_mode=True),
-               dict(predict_log_normalization=True)):
+    for kw in (dict(skip_mlp_initialization=True), dict(predict_log_normalization=True)):
         with pytest.raises(NotImplementedError):
             jfb.pdf("e2", "gg", **kw)
+    with pytest.raises(AssertionError):      # reference main/default.py:118-119: amortizing everything needs custom MLPs
+        jfb.pdf("e2", "gg", amortize_everything=True)
     with pytest.raises(NotImplementedError):
         jfb.pdf("e2", "gc")          # out of scope layer code
     with pytest.raises(NotImplementedError):
@@ -83,3 +84,19 @@ def test_cpu_tensors_are_rejected_no_fallback():
         p(torch.zeros(4, 2, dtype=torch.float64))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         p.sample(samplesize=3)
+
+
+def test_amortize_everything_structure():
+    """pdf(..., amortize_everything=True) owns no parameters; the amortizable count is the first sub-pdf's flow
+    parameters plus every inner generator's flat vector (reference main/default.py:595-651)."""
+    p = jfb.pdf("e2+s2", "gg+f", amortization_mlp_use_custom_mode=True, amortization_mlp_dims="16",
+                amortization_mlp_ranks=3, amortization_mlp_highway_mode=1, amortize_everything=True)
+    assert len(list(p.parameters())) == 0
+    assert p.mlp_predictors[0] is None and p.mlp_predictors[1].use_permanent_parameters is False
+    n_first = sum(p.num_parameter_list[0])
+    assert p.total_number_amortizable_params == n_first + p.mlp_predictors[1].num_amortization_params
+    init = p.init_params()
+    assert init.shape == (p.total_number_amortizable_params,)
+    with pytest.raises(Exception):           # CPU tensors are rejected: there is no fallback
+        import torch
+        p(torch.zeros(4, 4, dtype=torch.float64), amortization_parameters=init.double().unsqueeze(0).repeat(4, 1))

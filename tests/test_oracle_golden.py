@@ -3,8 +3,8 @@ This is what pins the oracle (the reference has no stored 
 import numpy as np
 import pytest
 
-from helpers import build_pdf, golden_names, load_golden, rel_err
-from oracle.jf_oracle import OraclePdf
+from helpers import build_fa, build_pdf, fa_golden_names, fa_outer_spec, golden_names, load_golden, rel_err
+from oracle.jf_oracle import OraclePdf, fully_amortized_parameters
 
 # the oracle uses the reference's own arithmetic (same torch ops), so it reproduces the goldens to rounding
 TOL = {"float64": 1e-12, "float32": 2e-6}
@@ -61,3 +61,43 @@ def test_oracle_embedding_coordinates(name):
         for k_, v_ in ent.items():
             ref = data["ent_%s_%s" % (tag, k_)]
             assert rel_err(v_.numpy(), ref).max() < max(1e-10, 10 * float(data["ref_roundtrip_base_err"])), (tag, k_)
+
+
+@pytest.mark.parametrize("name", fa_golden_names())
+def test_oracle_fully_amortized(name):
+    """fully_amortized_pdf (main/fully_amortized.py): outer generator -> per-row flow parameters and per-row inner MLP
+    weights (pdf(amortize_everything=True)); also pins the parameter counts and the bit-identical seeded init."""
+    meta, params, data = load_golden(name)
+    fa = build_fa(meta, seed=meta["seed"])
+    assert fa.pdf_to_amortize.total_number_amortizable_params == meta["total_number_amortizable_params"]
+    assert fa.count_parameters() == meta["total_param_num"]
+    assert sorted(fa.state_dict().keys()) == sorted(params.keys())
+    inner = fa.pdf_to_amortize
+    assert len(list(inner.parameters())) == 0          # everything is amortized: the inner pdf owns nothing
+    am = fully_amortized_parameters(fa_outer_spec(fa), params, data["cond"])
+    assert am.shape[1] == meta["total_number_amortizable_params"]
+    assert rel_err(am[:8].numpy(), data["amort_head"]).max() < 1e-12
+    o = OraclePdf(inner.export_program("float64"), {})
+    logp, logp_base, base = o.log_pdf(data["x"], None, amort=am)
+    assert rel_err(logp.numpy(), data["logp"]).max() < 1e-11
+    assert rel_err(logp_base.numpy(), data["logp_base"]).max() < 1e-11
+    assert rel_err(base.numpy(), data["base"]).max() < 1e-11
+    xs, slogp, slogp_base = o.sample(data["z"], None, amort=am)
+    stol = max(1e-9, 10 * float(data["ref_roundtrip_base_err"]))
+    assert rel_err(xs.numpy(), data["samp_x"]).max() < stol
+    assert rel_err(slogp.numpy(), data["samp_logp"]).max() < stol
+    assert rel_err(slogp_base.numpy(), data["samp_logp_base"]).max() < 1e-12
+
+
+def test_fully_amortized_seeded_init_matches_reference_layout():
+    """the init puts the desired flow / inner-generator values into the LAST bias of the outer generator
+    (main/fully_amortized.py:224-253, main/default.py:1828-1946): the tail of u_v_b_pars is the inner init vector"""
+    import torch
+    meta, params, _ = load_golden("fa_e2s2e2_lowrank_mode1")
+    fa = build_fa(meta, seed=3)
+    t = fa.pdf_to_amortize.total_number_amortizable_params
+    torch.manual_seed(5)
+    init = fa.pdf_to_amortize.init_params()
+    assert init.shape == (t,)
+    fa.amortization_mlp.initialize_uvbs(fix_final_bias=init)
+    assert torch.equal(fa.amortization_mlp.u_v_b_pars.data[0, -t:], init.double())
