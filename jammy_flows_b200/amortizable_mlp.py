@@ -63,6 +63,35 @@ class _Chain:
                                     n_b=n_out if (not last or final_bias) else 0))
         self.num_params = sum(l["n_u"] + l["n_v"] + l["n_b"] for l in self.layers)
 
+    def segments(self, flat):
+        """flat [num_params] -> list of Linear/tanh chains [[(W, b), ...], ...] to be run one after the other (no
+        activation between two chains).  A factorised layer whose factors are at least 4x smaller than the dense
+        matrix is applied as the reference does, U (V^T x): the chain is cut after V^T (a `rank`-wide intermediate).
+        With an output as wide as the parameter vector of a fully amortized pdf that is the difference between
+        rank*(in+out) and in*out multiply-adds per row; smaller layers are multiplied out (one launch)."""
+        segs, cur, pos = [], [], 0
+        for l in self.layers:
+            u = flat[pos:pos + l["n_u"]]
+            pos += l["n_u"]
+            v = flat[pos:pos + l["n_v"]]
+            pos += l["n_v"]
+            b = flat[pos:pos + l["n_b"]]
+            pos += l["n_b"]
+            if l["n_b"] == 0:
+                b = torch.zeros(l["n_out"], dtype=flat.dtype, device=flat.device)
+            if l["full"]:
+                cur.append((u.reshape(l["n_out"], l["n_in"]).contiguous(), b.contiguous()))
+            elif 4 * l["rank"] * (l["n_in"] + l["n_out"]) <= l["n_in"] * l["n_out"]:
+                cur.append((v.reshape(l["rank"], l["n_in"]).contiguous(),
+                            torch.zeros(l["rank"], dtype=flat.dtype, device=flat.device)))
+                segs.append(cur)
+                cur = [(u.reshape(l["n_out"], l["rank"]).contiguous(), b.contiguous())]
+            else:
+                w = torch.matmul(u.reshape(l["n_out"], l["rank"]), v.reshape(l["rank"], l["n_in"]))
+                cur.append((w.contiguous(), b.contiguous()))
+        segs.append(cur)
+        return segs
+
     def dense(self, flat):
         """flat [num_params] -> [(W [out,in], b [out])] with low-rank factors multiplied out."""
         out, pos = [], 0
@@ -186,6 +215,16 @@ class AmortizableMLP(nn.Module):
             chains.append(c.dense(flat[pos:pos + c.num_params]))
             pos += c.num_params
         hw = self.highway.dense(flat[pos:pos + self.highway.num_params]) if self.highway is not None else None
+        return chains, hw
+
+    def chain_segments(self, dtype, device):
+        """like dense_weights, every chain as a list of consecutive Linear/tanh chains (`_Chain.segments`)"""
+        flat = self.u_v_b_pars.detach().to(device=device, dtype=dtype).reshape(-1)
+        pos, chains = 0, []
+        for c in self.chains:
+            chains.append(c.segments(flat[pos:pos + c.num_params]))
+            pos += c.num_params
+        hw = self.highway.segments(flat[pos:pos + self.highway.num_params]) if self.highway is not None else None
         return chains, hw
 
     def forward(self, i, extra_inputs=None):

@@ -4,6 +4,7 @@
 // "g" chain kernels (gf_inst_*.cu) gain 2-5 % from constant-bank operands (profiles/ncu_r01_final.md)
 #define JF_EXP_CONST 0
 #include <atomic>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -425,6 +426,9 @@ static int try_mlp2_dmma(const MlpArgs<double>& m, cudaStream_t st) {
     if (m.n_linear != 2) return JF_ERR_UNSUPPORTED;
     const int Kin = m.dims[0], H = m.dims[1];
     if (H > 128 || (H & 1) || Kin > 256) return JF_ERR_UNSUPPORTED;
+    // the W2 / b2 tiles are streamed with 16-byte cp.async: sub-views of a flat parameter vector may start at an odd
+    // element, those take the generic kernel
+    if ((((uintptr_t)m.wt[1]) | ((uintptr_t)m.bias[1])) & 15) return JF_ERR_UNSUPPORTED;
     if (H <= 32) return launch_mlp2_dmma<32>(m, st);
     if (H <= 64) return launch_mlp2_dmma<64>(m, st);
     return launch_mlp2_dmma<128>(m, st);
@@ -524,6 +528,13 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
     }
     m.out = (T*)out; m.so_p = so_p; m.so_r = so_r; m.B = B;
     m.lda = maxd | 1;
+    if (m.n_linear == 1 && m.dims[0] <= kExpandK && m.dims[1] >= 256 && so_p == 1) {
+        // narrow input, wide row-major output (the U half of a factorised layer): write-bound expand kernel
+        dim3 grid((unsigned)((m.dims[1] + 255) / 256), (unsigned)((B + kExpandRows - 1) / kExpandRows));
+        if (grid.y > 65535u) return JF_ERR_UNSUPPORTED;
+        mlp_expand_kernel<T><<<grid, 256, 0, st>>>(m);
+        return check_launch();
+    }
     if (!accumulate && ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
         ws_bytes >= i8_ws_bytes(desc->dims[2], sizeof(T) == 8 ? JF_F64 : JF_F32))
         return launch_mlp2_i8(m, ws, prepared, st);

@@ -120,4 +120,45 @@ __global__ void __launch_bounds__(256) mlp_kernel(const __grid_constant__ MlpArg
     }
 }
 
+
+// One Linear layer with a narrow input (K <= 16) and a wide output: the U (.) half of a factorised layer of the outer
+// generator of a fully amortized pdf (rank -> thousands of amortization parameters per row).  Write-bound: 8 N bytes per
+// row against K N multiply-adds.  One thread per output column keeps its weight row in registers, the CTA's input rows
+// sit in shared memory (broadcast reads), stores are coalesced along the row-major output.
+constexpr int kExpandK = 16;
+constexpr int kExpandRows = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) mlp_expand_kernel(const __grid_constant__ MlpArgs<T> m) {
+    __shared__ T s_in[kExpandRows][kExpandK];
+    const int K = m.dims[0], N = m.dims[1];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * kExpandRows;
+    const int nr = (int)min((int64_t)kExpandRows, m.B - r0);
+    for (int idx = threadIdx.x; idx < nr * K; idx += 256) {
+        const int r = idx / K;
+        int k = idx - r * K, s = 0;
+        while (k >= m.seg_cols[s]) { k -= m.seg_cols[s]; ++s; }
+        s_in[r][idx - r * K] = m.seg_ptr[s][(r0 + r) * m.seg_ld[s] + k];
+    }
+    __syncthreads();
+    if (c >= N) return;
+    T w[kExpandK];
+#pragma unroll
+    for (int k = 0; k < kExpandK; ++k) w[k] = k < K ? m.wt[0][(int64_t)c * K + k] : T(0);
+    const T b = m.bias[0][c];
+    T* o = m.out + (int64_t)c * m.so_p + r0 * m.so_r;
+    for (int r = 0; r < nr; ++r) {
+        T a0 = b, a1 = T(0);
+#pragma unroll
+        for (int k = 0; k < kExpandK; k += 2) {
+            if (k < K) a0 = fma(w[k], s_in[r][k], a0);
+            if (k + 1 < K) a1 = fma(w[k + 1], s_in[r][k + 1], a1);
+        }
+        T v = a0 + a1;
+        if (m.acc) v += o[r * m.so_r];
+        o[r * m.so_r] = v;
+    }
+}
+
 }  // namespace jf

@@ -234,6 +234,10 @@ def uses_custom_mlp(pdf):
 
 def _run_chain(lib, dt, dev, layers_wb, segs, out, so_p, so_r, R, accumulate):
     """one Linear/tanh chain with dense weights [(W, b)] on column blocks `segs` -> out (optionally +=)."""
+    # slices of a flat parameter vector may start at an odd element: the tensor-pipe kernels stream weights in 16-byte
+    # pieces (the library falls back to its generic kernel for unaligned pointers; aligned copies keep the fast one)
+    layers_wb = [(w if w.data_ptr() % 16 == 0 else w.clone(), b if b.data_ptr() % 16 == 0 else b.clone())
+                 for w, b in layers_wb]
     md = _cabi.JfMlpDesc()
     md.n_linear = len(layers_wb)
     md.dims[0] = layers_wb[0][0].shape[1]
@@ -265,12 +269,22 @@ def custom_mlp_forward(mlp, segs, R):
     for s_ in segs:
         _require_cuda(s_, "MLP input")
     dt, dev = segs[0].dtype, segs[0].device
-    chains, hw = mlp.dense_weights(dt, dev)
+    chains, hw = mlp.chain_segments(dt, dev)
     P = mlp.output_dim
     out = torch.empty(R, P, dtype=dt, device=dev)
+
+    def run_pieces(pieces, inp, accumulate):
+        # consecutive Linear/tanh chains (cut behind the V^T of a factorised layer): narrow row-major intermediates
+        for piece in pieces[:-1]:
+            width = piece[-1][0].shape[0]
+            tmp = torch.empty(R, width, dtype=dt, device=dev)
+            _run_chain(lib, dt, dev, piece, inp, tmp, 1, width, R, False)
+            inp = [tmp]
+        _run_chain(lib, dt, dev, pieces[-1], inp, out, 1, P, R, accumulate)
+
     started = False
     if hw is not None:
-        _run_chain(lib, dt, dev, hw, segs, out, 1, P, R, False)
+        run_pieces(hw, segs, False)
         started = True
     for ci, ch in enumerate(chains):
         if ci == 0 or mlp.highway_mode <= 2:
@@ -280,7 +294,7 @@ def custom_mlp_forward(mlp, segs, R):
         else:
             inp = segs + [out]
         # a CTA gathers the input rows it owns before it writes them, so reading `out` while accumulating into it is safe
-        _run_chain(lib, dt, dev, ch, inp, out, 1, P, R, started)
+        run_pieces(ch, inp, started)
         started = True
     if not started:
         out.zero_()

@@ -33,7 +33,8 @@ def main():
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     hbm = float(peak.get("hbm_gbs", peak.get("hbm_GBps", 6458.1))) if isinstance(peak, dict) else 6458.1
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for dtype, code, es in ((torch.float64, _cabi.JF_F64, 8), (torch.float32, _cabi.JF_F32, 4)):
+    micro = "fa_only" not in sys.argv
+    for dtype, code, es in ((torch.float64, _cabi.JF_F64, 8), (torch.float32, _cabi.JF_F32, 4)) if micro else ():
         for n_in, n_out in ((7, 128), (128, 64), (3, 128), (128, 3), (16, 130)):
             R = rows
             ld = n_in * n_out + n_out
