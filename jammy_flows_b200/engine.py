@@ -434,21 +434,24 @@ def _pdf_staged_chunk(pdf, src, cond, direction, amort=None):
         segs = ([cond[k] if isinstance(cond, list) else cond] if cond is not None else []) + prev
         n_par = desc.sub[k].n_params
         if mlp is None and amort is not None and n_par > 0:
-            view = amort[:, amort_pos:amort_pos + n_par]
+            # param-major copy [n_par, R]: the thread-per-row layer kernels read it coalesced (a strided view of the
+            # [R, T] block costs them 4x; the transposing copy moves 2 x n_par x 8 B per row once)
+            buf = amort[:, amort_pos:amort_pos + n_par].t().contiguous()
             amort_pos += n_par
-            params, sp, sr = _ptr(view), 1, amort.stride(0)
+            keep.append(buf)
+            params, sp, sr = _ptr(buf), R, 1
         elif mlp is None:
             params, sp, sr = C.c_void_p(pack.c.shared[k]), 1, 0
         elif amort is not None:
             n_am = mlp.num_amortization_params
-            buf = amortized_mlp_forward(mlp, segs, amort[:, amort_pos:amort_pos + n_am], R)
+            buf = amortized_mlp_forward(mlp, segs, amort[:, amort_pos:amort_pos + n_am], R).t().contiguous()
             amort_pos += n_am
             keep.append(buf)
-            params, sp, sr = _ptr(buf), 1, n_par
+            params, sp, sr = _ptr(buf), R, 1
         elif hasattr(mlp, "u_v_b_pars"):
-            buf = custom_mlp_forward(mlp, segs, R)
+            buf = custom_mlp_forward(mlp, segs, R).t().contiguous()     # param-major for the layer kernels, as above
             keep.append(buf)
-            params, sp, sr = _ptr(buf), 1, n_par
+            params, sp, sr = _ptr(buf), R, 1
         else:
             linears = [m for m in mlp if isinstance(m, torch.nn.Linear)]
             wb = [(pack_w, pack_b) for pack_w, pack_b in

@@ -72,12 +72,22 @@ class fully_amortized_pdf(nn.Module):
     def chunk_rows(self, v):
         self.pdf_to_amortize.chunk_rows = v
 
+    @property
+    def rng_mode(self):
+        """base normals of sample(): "numpy" (the reference's host RNG, default), "device", "philox" -- see pdf.rng_mode"""
+        return self.pdf_to_amortize.rng_mode
+
+    @rng_mode.setter
+    def rng_mode(self, v):
+        self.pdf_to_amortize.rng_mode = v
+
     def _chunk(self):
-        """rows per pass: the [rows, T] block of amortization parameters stays below ~2 GiB unless chunk_rows is set"""
+        """rows per pass: the [rows, T] block of amortization parameters stays below ~16 GiB (of 180 GB HBM) unless
+        chunk_rows is set; the thread-per-row layer kernels want >= 3e5 rows in flight to fill 148 SMs"""
         if self.chunk_rows:
             return int(self.chunk_rows)
         t = max(1, self.pdf_to_amortize.total_number_amortizable_params)
-        return int(max(1024, min(engine.DEFAULT_CHUNK_ROWS, (1 << 31) // (8 * t))))
+        return int(max(1024, min(engine.DEFAULT_CHUNK_ROWS, (1 << 34) // (8 * t))))
 
     def kernel_status(self, reset=True):
         return self.pdf_to_amortize.kernel_status(reset=reset)
