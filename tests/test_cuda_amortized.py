@@ -148,3 +148,32 @@ def test_rowwise_linear_matches_torch(n_in, n_out, dtype, lib_built):
     assert lib.jf_rowwise_linear(code, C.c_void_p(params.data_ptr()), n_in * n_out - 1, 0, -1, C.c_void_p(inp.data_ptr()),
                                  inp.stride(0), n_in, n_out, 0, 0, C.c_void_p(out.data_ptr()), 1, n_out, R, st) < 0
     assert lib.jf_rowwise_linear(code, None, ld, off_w, -1, None, n_in, n_in, n_out, 0, 0, None, 1, n_out, 0, st) == 0
+
+
+def test_fully_amortized_embedding_coordinates_and_fp32(lib_built):
+    """force_embedding_coordinates through the amortized path (charts before / after the chain, main/default.py:906-909,
+    :1522-1524) and the same pdf evaluated in float32 (dtype follows the inputs: the inner pdf owns no parameters)."""
+    meta, params, data = load_golden("fa_e2s2e2_lowrank_mode1")
+    fa = build_fa(meta, params).cuda()
+    inner = fa.pdf_to_amortize
+    x, cond, z = (torch.from_numpy(data[k]).cuda() for k in ("x", "cond", "z"))
+    with torch.no_grad():
+        lp, _, base = fa(x, conditional_input=cond)
+        x_emb, ld = inner.transform_target_space(x, 0.0, transform_from="default", transform_to="embedding")
+        lp_e, _, base_e = fa(x_emb, conditional_input=cond, force_embedding_coordinates=True)
+        am = fa.amortization_parameters(cond)
+        xs_e, _, slp_e, _ = inner._obtain_sample(amortization_parameters=am, predefined_target_input=z,
+                                                 force_embedding_coordinates=True)
+        xs, _, slp, _ = inner._obtain_sample(amortization_parameters=am, predefined_target_input=z)
+        back, ld_s = inner.transform_target_space(xs, 0.0, transform_from="default", transform_to="embedding")
+    assert x_emb.shape[1] == 7 and xs_e.shape[1] == 7
+    assert (lp_e - (lp - ld)).abs().max() < 1e-9          # the round trip through acos near the poles costs ~1e-10
+    assert (base_e - base).abs().max() < 1e-7
+    assert torch.equal(xs_e, back) and (slp_e - (slp - ld_s)).abs().max() < 1e-12
+    assert ((xs_e[:, 2:5] ** 2).sum(dim=1) - 1).abs().max() < 1e-14
+    # float32: amortization parameters, inputs and outputs in single precision against the fp64 result
+    with torch.no_grad():
+        lp32, _, base32 = inner(x.float(), amortization_parameters=am.float())
+    assert lp32.dtype == torch.float32
+    err = (lp32.double() - lp).abs() / lp.abs().clamp(min=1)
+    assert err.median() < 1e-5 and err.max() < 1e-3       # rows in the far tails amplify the fp32 rounding of the weights
