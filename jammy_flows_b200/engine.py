@@ -386,25 +386,38 @@ def amortized_mlp_forward(mlp, segs, extra, R):
     return out
 
 
-def _pdf_staged(pdf, src, cond, direction, amort=None):
+def _pdf_staged(pdf, src, cond, direction, amort=None, only_last=False):
     """Row-chunked wrapper of `_pdf_staged_chunk` (the per-row parameter buffers are [rows, P]: bounded by the chunk)."""
     chunk = int(pdf.chunk_rows or DEFAULT_CHUNK_ROWS)
     R = src.shape[0]
     if amort is not None:
         assert amort.shape[0] == R, "batch size of amortization_parameters must agree with the batch size of the input"
     if R <= chunk:
-        return _pdf_staged_chunk(pdf, src, cond, direction, amort)
+        return _pdf_staged_chunk(pdf, src, cond, direction, amort, only_last)
     parts = []
     for r0 in range(0, R, chunk):
         c = None
         if cond is not None:
             c = [ci[r0:r0 + chunk] for ci in cond] if isinstance(cond, (list, tuple)) else cond[r0:r0 + chunk]
         parts.append(_pdf_staged_chunk(pdf, src[r0:r0 + chunk], c, direction,
-                                       None if amort is None else amort[r0:r0 + chunk]))
+                                       None if amort is None else amort[r0:r0 + chunk], only_last))
     return tuple(torch.cat([p[i] for p in parts], dim=0) for i in range(3))
 
 
-def _pdf_staged_chunk(pdf, src, cond, direction, amort=None):
+def _last_layer_desc(pdf, k, dt):
+    """`only_last` (reference main/default.py:1015-1024, :1490-1502): a one-layer program made of the LAST layer of
+    sub-pdf k, sphere layers with the base chart forced on (fix_euclidean_to_sphere_first=True); -> (desc, offset of
+    that layer's parameters inside the sub-pdf's parameter vector)."""
+    layers = pdf.layer_list[k]
+    d = dict(layers[-1].descriptor())
+    if pdf.pdf_defs_list[k][0] == "s":
+        d["first"] = 1
+    sd = _cabi.JfSubPdfDesc()
+    fill_subpdf_desc(sd, pdf.pdf_defs_list[k][0], layers[0].dimension, [d])
+    return sd, sum(l.total_param_num for l in layers[:-1])
+
+
+def _pdf_staged_chunk(pdf, src, cond, direction, amort=None, only_last=False):
     """Per-sub-pdf orchestration on the host: parameter generator (nn.Sequential or AmortizableMLP) -> layer chain, the
     embedding of each sub-pdf's target feeding the later generators (reference main/default.py:931-1053 / :1413-1514).
     Used when a generator is an AmortizableMLP, which the single-call C entries do not describe."""
@@ -467,8 +480,16 @@ def _pdf_staged_chunk(pdf, src, cond, direction, amort=None):
         v_in, v_out = src[:, i0:i1], dst[:, o0:o1]
         emb = torch.empty(R, layers[-1]._embedding_conditional_return_num(), dtype=dt, device=dev)
         first = k == 0
+        sub_desc = desc.sub[k]
+        if only_last:
+            if not logpdf and pdf.pdf_defs_list[k][0] not in ("s", "e"):
+                raise Exception("Flow type ", pdf.pdf_defs_list[k][0], " does not supported *only_last*!")
+            sub_desc, p_off = _last_layer_desc(pdf, k, dt)
+            keep.append(sub_desc)
+            if params.value is not None:
+                params = C.c_void_p(params.value + p_off * sp * (8 if dt == torch.float64 else 4))
         with torch.cuda.device(dev):
-            rc = lib.jf_subpdf_apply(C.byref(desc.sub[k]), _DT[dt], direction, _ptr(v_in), src.stride(0), params, sp, sr,
+            rc = lib.jf_subpdf_apply(C.byref(sub_desc), _DT[dt], direction, _ptr(v_in), src.stride(0), params, sp, sr,
                                      None if first else _ptr(logdet), _ptr(logdet), None if first else _ptr(logbase),
                                      _ptr(logbase), _ptr(v_out), dst.stride(0), _ptr(emb), emb.shape[1], R,
                                      _ptr(status), _stream_ptr(dev))
@@ -477,12 +498,12 @@ def _pdf_staged_chunk(pdf, src, cond, direction, amort=None):
     return dst, logdet, logbase
 
 
-def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True, amort=None):
+def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True, amort=None, only_last=False):
     """-> (log_pdf [B], log_pdf_base [B], base [B, D_base]) on x's device.  Reference: main/default.py:1059-1117."""
     if pdf.amortize_everything and amort is None:
         raise AssertionError("a pdf built with amortize_everything needs amortization_parameters")
-    if uses_custom_mlp(pdf) or amort is not None:
-        base, logdet, logbase = _pdf_staged(pdf, x, cond, _cabi.JF_DIR_LOGPDF, amort)
+    if uses_custom_mlp(pdf) or amort is not None or only_last:
+        base, logdet, logbase = _pdf_staged(pdf, x, cond, _cabi.JF_DIR_LOGPDF, amort, only_last)
         return logdet + logbase, logbase, base
     lib = _cabi.load()
     x, cond = _prep_inputs(pdf, x, cond, "x")
@@ -505,12 +526,12 @@ def pdf_logpdf(pdf, x, cond=None, chunk_rows=None, want_base=True, amort=None):
     return logp, logp_base, base
 
 
-def pdf_sample(pdf, z, cond=None, chunk_rows=None, amort=None):
+def pdf_sample(pdf, z, cond=None, chunk_rows=None, amort=None, only_last=False):
     """z [B, D_base] -> (x [B, D], log_pdf [B], log_pdf_base [B]).  Reference: main/default.py:1373-1531, :1533-1707."""
     if pdf.amortize_everything and amort is None:
         raise AssertionError("a pdf built with amortize_everything needs amortization_parameters")
-    if uses_custom_mlp(pdf) or amort is not None:
-        xs, logdet, logbase = _pdf_staged(pdf, z, cond, _cabi.JF_DIR_SAMPLE, amort)
+    if uses_custom_mlp(pdf) or amort is not None or only_last:
+        xs, logdet, logbase = _pdf_staged(pdf, z, cond, _cabi.JF_DIR_SAMPLE, amort, only_last)
         return xs, logbase - logdet, logbase
     lib = _cabi.load()
     z, cond = _prep_inputs(pdf, z, cond, "base sample")

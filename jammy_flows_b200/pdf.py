@@ -428,8 +428,6 @@ class pdf(nn.Module):
     def forward(self, x, conditional_input=None, amortization_parameters=None, force_embedding_coordinates=False,
                 force_intrinsic_coordinates=False, only_last=False):
         assert (self.use_as_passthrough_instead_of_pdf == False)
-        if only_last:
-            raise NotImplementedError("only_last is outside the hot path built so far")
         self._check_amortization_parameters(amortization_parameters, x.shape[0])
         if type(conditional_input) == list:
             # one conditional input per sub-pdf (reference main/default.py:1092-1103)
@@ -454,12 +452,12 @@ class pdf(nn.Module):
         assert (x.shape[1] == self.total_target_dim), (x.shape[1], self.total_target_dim)
         needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
                                                   (amortization_parameters is not None and amortization_parameters.requires_grad))
-        if needs_grad and amortization_parameters is None and engine.supports_backward(self):
+        if needs_grad and amortization_parameters is None and not only_last and engine.supports_backward(self):
             # training path: fused forward AND backward layer kernels, torch autograd only for the parameter generator
             return engine.pdf_logpdf_trainable(self, x, conditional_input)
         amort = amortization_parameters.detach() if amortization_parameters is not None else None
         log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows,
-                                                            amort=amort)
+                                                            amort=amort, only_last=only_last)
         if chart_log_det is not None:
             log_pdf = log_pdf + chart_log_det
         if needs_grad:
@@ -486,7 +484,7 @@ class pdf(nn.Module):
         if force_embedding_coordinates and self._needs_transform():
             x, log_det = engine.pdf_transform_target(self, x, log_det, to_embedding=False)
         logp, logp_base, base = engine.pdf_logpdf(self, x, data_summary, chunk_rows=self.chunk_rows,
-                                                  amort=amortization_parameters)
+                                                  amort=amortization_parameters, only_last=only_last)
         return base, log_det + (logp - logp_base)
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -510,8 +508,6 @@ class pdf(nn.Module):
                        amortization_parameters=None, force_embedding_coordinates=False,
                        force_intrinsic_coordinates=False, failsafe_crosscheck_tolerance=None, dtype=None, device=None,
                        only_last=False):
-        if only_last:
-            raise NotImplementedError("only_last is outside the hot path built so far")
         used_sample_size = samplesize
         if self.amortize_everything:
             # reference main/default.py:1591-1606: batch, dtype and device come from the amortization parameters
@@ -554,15 +550,15 @@ class pdf(nn.Module):
             z = self._draw_base_normals(used_sample_size, seed, data_type, used_device)
             std_normal_samples = z
         x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows,
-                                                  amort=amortization_parameters)
+                                                  amort=amortization_parameters, only_last=only_last)
         if force_embedding_coordinates and self._needs_transform():
             # reference main/default.py:1522-1524: default -> embedding coordinates, log p = log N(z) - (logdet + chart)
             x, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)
             log_pdf = log_pdf - chart_log_det
         if failsafe_crosscheck_tolerance:
             assert (predefined_target_input is None), "Failsafe does not work with predefined input!"
-            if amortization_parameters is not None:
-                raise NotImplementedError("failsafe_crosscheck_tolerance together with amortization_parameters")
+            if amortization_parameters is not None or only_last:
+                raise NotImplementedError("failsafe_crosscheck_tolerance together with amortization_parameters / only_last")
             x, std_normal_samples, log_pdf, log_gauss = self._recheck_sampling(
                 x, std_normal_samples, log_pdf, log_gauss, failsafe_crosscheck_tolerance, conditional_input,
                 force_embedding_coordinates, force_intrinsic_coordinates, data_type, used_device)
@@ -618,7 +614,7 @@ class pdf(nn.Module):
         """base -> target through every sub-pdf (reference main/default.py:1373-1531)."""
         self._check_amortization_parameters(amortization_parameters, x.shape[0])
         xs, logp, logp_base = engine.pdf_sample(self, x, data_summary, chunk_rows=self.chunk_rows,
-                                                amort=amortization_parameters)
+                                                amort=amortization_parameters, only_last=only_last)
         log_det = log_det + (logp_base - logp)
         if force_embedding_coordinates and self._needs_transform():
             xs, log_det = engine.pdf_transform_target(self, xs, log_det, to_embedding=True)

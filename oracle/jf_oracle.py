@@ -1397,8 +1397,18 @@ class OraclePdf:
             return [torch.as_tensor(np.asarray(c)).to(self.dtype) for c in cond]
         return torch.as_tensor(np.asarray(cond)).to(self.dtype)
 
-    def log_pdf(self, x, cond=None, amort=None):
-        """amort: amortization_parameters [B, T] of a pdf built with amortize_everything (main/default.py:1062-1076)."""
+    def _last_layer(self, k):
+        """the layer `only_last` applies for sub-pdf k: the last one, sphere layers with the base chart forced on
+        (`fix_euclidean_to_sphere_first=True`, main/default.py:1018-1021, :1497-1498)"""
+        sp = self.prog["subpdfs"][k]
+        ls = dict(sp["layers"][-1])
+        if sp["manifold"] == "s":
+            ls["first"] = 1
+        return LAYER_TYPES[ls["code"]](ls)
+
+    def log_pdf(self, x, cond=None, amort=None, only_last=False):
+        """amort: amortization_parameters [B, T] of a pdf built with amortize_everything (main/default.py:1062-1076).
+        only_last: apply only the last layer of every sub-pdf (main/default.py:1015-1024)."""
         x = torch.as_tensor(np.asarray(x)).to(self.dtype)
         cond = self._as_cond(cond)
         self._split_amortization(amort)
@@ -1410,9 +1420,13 @@ class OraclePdf:
             p = self._sub_params(k, cond, prev_emb, b)
             t0, t1 = sp["target_cols"]
             cur = x[:, t0:t1]
-            for li in reversed(range(len(layers))):
-                o0, o1 = sp["layer_param_ranges"][li]
-                cur, log_det = layers[li].inverse(cur, log_det, p[:, o0:o1])
+            if only_last:
+                o0, o1 = sp["layer_param_ranges"][-1]
+                cur, log_det = self._last_layer(k).inverse(cur, log_det, p[:, o0:o1])
+            else:
+                for li in reversed(range(len(layers))):
+                    o0, o1 = sp["layer_param_ranges"][li]
+                    cur, log_det = layers[li].inverse(cur, log_det, p[:, o0:o1])
             base.append(cur)
             prev_emb.append(layers[-1].embedding(x[:, t0:t1]))
         base = torch.cat(base, dim=1)
@@ -1420,7 +1434,7 @@ class OraclePdf:
         logp_base = (-0.5 * base ** 2 - LOG_SQRT_2PI).sum(dim=-1)
         return logp_base + log_det, logp_base, base
 
-    def sample(self, z, cond=None, amort=None):
+    def sample(self, z, cond=None, amort=None, only_last=False):
         z = torch.as_tensor(np.asarray(z)).to(self.dtype)
         cond = self._as_cond(cond)
         self._split_amortization(amort)
@@ -1432,9 +1446,15 @@ class OraclePdf:
             p = self._sub_params(k, cond, prev_emb, b)
             b0, b1 = sp["base_cols"]
             cur = z[:, b0:b1]
-            for li in range(len(layers)):
-                o0, o1 = sp["layer_param_ranges"][li]
-                cur, log_det = layers[li].forward(cur, log_det, p[:, o0:o1])
+            if only_last:
+                if sp["manifold"] not in ("s", "e"):
+                    raise Exception("Flow type ", sp["manifold"], " does not supported *only_last*!")   # :1499-1502
+                o0, o1 = sp["layer_param_ranges"][-1]
+                cur, log_det = self._last_layer(k).forward(cur, log_det, p[:, o0:o1])
+            else:
+                for li in range(len(layers)):
+                    o0, o1 = sp["layer_param_ranges"][li]
+                    cur, log_det = layers[li].forward(cur, log_det, p[:, o0:o1])
             out.append(cur)
             prev_emb.append(layers[-1].embedding(cur))
         x = torch.cat(out, dim=1)

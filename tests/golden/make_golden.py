@@ -187,6 +187,10 @@ CASES = {
     "amlp_e2e2_cond_mode4": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=300, cond_dim=3, perturb=0.05,
                                  pdf_kw=dict(amortization_mlp_use_custom_mode=True, amortization_mlp_dims="64-30",
                                              amortization_mlp_ranks=0, amortization_mlp_highway_mode=4)),
+    # only_last=True (main/default.py:1018-1024, :1490-1502): only the LAST layer of every sub-pdf is applied, sphere
+    # layers with their base chart forced on (fix_euclidean_to_sphere_first)
+    "last_e3s2e2": dict(pdf_defs="e3+s2+e2", flow_defs="ggg+vf+gg", n=300, perturb=0.3, only_last=True),
+    "last_e2s1s2_cond": dict(pdf_defs="e2+s1+s2", flow_defs="gg+mo+fv", n=300, cond_dim=3, perturb=0.2, only_last=True),
     # one conditional input per sub-pdf (conditional_input_dim as a list, main/default.py:286-296, :944-949)
     "condlist_e2s2e1": dict(pdf_defs="e2+s2+e1", flow_defs="gg+f+g", n=300, cond_dim=[3, 2, 4], perturb=0.2),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
@@ -247,6 +251,12 @@ def build_case(jf, name, spec):
         "ref_roundtrip_base_err": np.nanmax(np.abs((rt_base - z).numpy())),
         "ref_roundtrip_logp_err": np.nanmax(np.abs((rt_logp - samp_logp).numpy())),
     }
+    if spec.get("only_last", False):
+        with torch.no_grad():
+            l_logp, l_logp_base, l_base = pdf(x, conditional_input=cond, only_last=True)
+            l_sx, _, l_slogp, _ = pdf._obtain_sample(conditional_input=cond, predefined_target_input=z, only_last=True)
+        out.update({"last_logp": l_logp.numpy(), "last_logp_base": l_logp_base.numpy(), "last_base": l_base.numpy(),
+                    "last_samp_x": l_sx.numpy(), "last_samp_logp": l_slogp.numpy()})
     if spec.get("emb", False):
         with torch.no_grad():
             x_emb, _ = pdf.transform_target_space(x, 0.0, transform_from="default", transform_to="embedding")

@@ -249,3 +249,29 @@ def test_device_rng_matches_oracle_and_is_shard_invariant(lib_built):
         p.rng_first_row = 3000
         c = p.sample(samplesize=2000, seed=11)
     assert torch.equal(a[0], b[0]) and torch.equal(a[0][3000:], c[0]) and torch.equal(a[2][3000:], c[2])
+
+
+@pytest.mark.parametrize("name", ["last_e3s2e2", "last_e2s1s2_cond"])
+def test_only_last_matches_reference(name, lib_built):
+    """forward(..., only_last=True) / _obtain_sample(..., only_last=True) (main/default.py:1015-1024, :1490-1502): a
+    one-layer program per sub-pdf (its last layer, sphere layers with the base chart forced on) on the same kernels."""
+    from helpers import build_pdf, load_golden
+    meta, params, data = load_golden(name)
+    p = build_pdf(meta, params).cuda()
+    t = lambda a: torch.from_numpy(a).cuda()
+    cond = t(data["cond"]) if "cond" in data else None
+    with torch.no_grad():
+        lp, lb, base = p(t(data["x"]), conditional_input=cond, only_last=True)
+        xs, _, slp, _ = p._obtain_sample(conditional_input=cond, predefined_target_input=t(data["z"]), only_last=True)
+        rt_lp, _, rt_base = p(xs, conditional_input=cond, only_last=True)
+        full_lp, _, _ = p(t(data["x"]), conditional_input=cond)
+    assert rel_err(lp.cpu().numpy(), data["last_logp"]).max() < 1e-10
+    assert rel_err(lb.cpu().numpy(), data["last_logp_base"]).max() < 1e-10
+    assert rel_err(base.cpu().numpy(), data["last_base"]).max() < 1e-10
+    stol = max(1e-9, 10 * float(data["ref_roundtrip_base_err"]))
+    assert rel_err(xs.cpu().numpy(), data["last_samp_x"]).max() < stol
+    assert rel_err(slp.cpu().numpy(), data["last_samp_logp"]).max() < stol
+    assert (rt_base - t(data["z"])).abs().max() < 1e-8 and (rt_lp - slp).abs().max() < 1e-8
+    assert (full_lp - lp).abs().max() > 1e-3          # it really is a different (shorter) flow
+    st = p.kernel_status()
+    assert st["nonfinite"] == 0 and st["unconverged"] == 0

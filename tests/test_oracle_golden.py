@@ -101,3 +101,21 @@ def test_fully_amortized_seeded_init_matches_reference_layout():
     assert init.shape == (t,)
     fa.amortization_mlp.initialize_uvbs(fix_final_bias=init)
     assert torch.equal(fa.amortization_mlp.u_v_b_pars.data[0, -t:], init.double())
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("last_")])
+def test_oracle_only_last(name):
+    """forward(..., only_last=True) / _obtain_sample(..., only_last=True): main/default.py:1015-1024, :1490-1502"""
+    meta, params, data = load_golden(name)
+    pdf = build_pdf(meta)
+    o = OraclePdf(pdf.export_program(meta["dtype"]), params)
+    cond = data.get("cond")
+    logp, logp_base, base = o.log_pdf(data["x"], cond, only_last=True)
+    assert rel_err(logp.numpy(), data["last_logp"]).max() < 1e-12
+    assert rel_err(logp_base.numpy(), data["last_logp_base"]).max() < 1e-12
+    assert rel_err(base.numpy(), data["last_base"]).max() < 1e-12
+    xs, slogp, _ = o.sample(data["z"], cond, only_last=True)
+    # the "v" layer's sampling direction is an iterative inverse: agreement to the reference's own round-trip error
+    stol = max(1e-9, 10 * float(data["ref_roundtrip_base_err"]))
+    assert rel_err(xs.numpy(), data["last_samp_x"]).max() < stol
+    assert rel_err(slogp.numpy(), data["last_samp_logp"]).max() < stol
