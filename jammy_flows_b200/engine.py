@@ -229,6 +229,7 @@ def uses_custom_mlp(pdf):
     """True when the per-sub-pdf orchestration on the host is needed: AmortizableMLP generators, or one conditional input
     per sub-pdf (`conditional_input_dim` list), neither of which the single-call C entries describe."""
     return type(pdf.conditional_input_dim) == list or \
+        (pdf.predict_log_normalization and pdf.join_poisson_and_pdf_description) or \
         any(m is not None and hasattr(m, "u_v_b_pars") for m in pdf.mlp_predictors)
 
 
@@ -470,7 +471,9 @@ def _pdf_staged_chunk(pdf, src, cond, direction, amort=None, only_last=False):
             wb = [(pack_w, pack_b) for pack_w, pack_b in
                   ((l.weight.detach().to(device=dev, dtype=dt).contiguous(), l.bias.detach().to(device=dev, dtype=dt).contiguous())
                    for l in linears)]
-            buf = torch.empty(max(n_par, 1), R, dtype=dt, device=dev)
+            # a generator may predict more than the flow parameters (the Poisson log-lambda as its last output,
+            # predict_log_normalization + join_poisson_and_pdf_description): the layer kernels read the first n_par
+            buf = torch.empty(max(n_par, wb[-1][0].shape[0], 1), R, dtype=dt, device=dev)
             keep += [buf, wb]
             _run_chain(lib, dt, dev, wb, segs, buf, R, 1, R, False)
             params, sp, sr = _ptr(buf), R, 1
@@ -624,7 +627,8 @@ def subpdf_logpdf(pdf, k, x_k, cond_segments, embedding_coordinates=False):
             md.seg_cols[i] = sg.shape[1]
         ptrs = (C.c_void_p * len(segs))(*[sg.data_ptr() for sg in segs])
         lds = (C.c_int64 * len(segs))(*[sg.stride(0) for sg in segs])
-        keep = torch.empty(max(n_par, 1), R, dtype=dt, device=dev)          # param-major [P, R]
+        # param-major [P, R]; the generator may predict one more value than the layers use (joint log-lambda)
+        keep = torch.empty(max(n_par, int(md.dims[md.n_linear]), 1), R, dtype=dt, device=dev)
         nws = lib.jf_mlp_workspace_bytes(C.byref(md), _DT[dt])
         ws = torch.zeros(max(int(nws), 16), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
@@ -675,6 +679,10 @@ def _host_call(pdf, direction, src, cond, chunk_rows, device):
     """HOST tensors in, HOST tensors out (pinned): the end-to-end path with copies inside the library call."""
     lib = _cabi.load()
     assert not src.is_cuda
+    if uses_custom_mlp(pdf) or pdf.amortize_everything:
+        raise NotImplementedError("the host-buffer entries describe nn.Sequential generators only; AmortizableMLP / "
+                                  "per-sub-pdf conditional inputs / joint log-lambda prediction run through the "
+                                  "device-tensor API (pdf.forward / pdf.sample)")
     dt = src.dtype
     dev = torch.device(device)
     B = src.shape[0]

@@ -50,8 +50,13 @@ class pdf(nn.Module):
         """Same parameters as the reference constructor (main/default.py:44-100)."""
         super().__init__()
         not_built = []
-        if predict_log_normalization:
-            not_built.append("predict_log_normalization (Poisson log-lambda head)")
+        if predict_log_normalization and join_poisson_and_pdf_description and amortization_mlp_use_custom_mode:
+            # the reference's own init fails for this combination (main/default.py:1897 indexes the AmortizableMLP)
+            not_built.append("joint log-lambda prediction with an AmortizableMLP generator")
+        if predict_log_normalization and conditional_input_dim is not None and not join_poisson_and_pdf_description:
+            # the reference builds a separate log-lambda MLP here but its log_mean_poisson() raises "outdated"
+            # (main/default.py:876-877)
+            not_built.append("predict_log_normalization with a separate log-lambda MLP (join_poisson_and_pdf_description=False)")
         if use_as_passthrough_instead_of_pdf:
             not_built.append("use_as_passthrough_instead_of_pdf")
         if skip_mlp_initialization:
@@ -211,7 +216,15 @@ class pdf(nn.Module):
                 dim = int(subflow_description.split("_")[0][1:])
                 self.layer_list[subflow_index].append(flow_info[layer_type]["module"](dim, **this_kwargs))
                 self.num_parameter_list[subflow_index].append(self.layer_list[subflow_index][-1].get_total_param_num())
+        # Poisson log-mean prediction (reference main/default.py:466-477): a free parameter for an unconditional pdf; for a
+        # conditional one the first generator predicts it as one extra (last) output
         self.log_normalization = None
+        if self.predict_log_normalization:
+            assert (len(self.pdf_defs_list) == 1), "You chose to predict log-lambda, which is only allowed with a single sub-pdf (no autoregressive structure). For autoregressive PDFs with log-lambda prediction, use fully amortized PDFs."
+            if self.force_permanent_parameters_in_first_subpdf:
+                self.log_normalization = nn.Parameter(torch.randn(1).unsqueeze(0))
+            else:
+                self.log_normalization = torch.zeros(1).unsqueeze(0)
         self.update_embedding_structure()
 
     # reference main/default.py:481-567
@@ -252,6 +265,12 @@ class pdf(nn.Module):
         self.mlp_predictors = nn.ModuleList()
         self.log_normalization_mlp = None
         prev_extra_input_num = 0
+        if self.join_poisson_and_pdf_description:
+            # reference main/default.py:580-584
+            if len(self.pdf_defs_list) > 1:
+                raise Exception("A common poisson log-lambda and flow parameter prediction is currently only supported for a PDF that has a single flow (no autoregressive structure) for simplicity! .. number of autoregressive parts here: ", len(self.pdf_defs_list))
+            if self.conditional_input_dim is None:
+                raise Exception("Flow does not depend on conditional input .. please set 'join_poisson_and_pdf_description' to False, currently True")
         for pdf_index, _ in enumerate(self.pdf_defs_list):
             emb_num = self.layer_list[pdf_index][-1]._embedding_conditional_return_num()
             if pdf_index == 0 and self.conditional_input_dim is None:
@@ -263,6 +282,8 @@ class pdf(nn.Module):
                     self.total_number_amortizable_params += sum(self.num_parameter_list[0])
                 continue
             num_predicted_pars = sum(self.num_parameter_list[pdf_index])
+            if self.predict_log_normalization and pdf_index == 0 and self.join_poisson_and_pdf_description:
+                num_predicted_pars += 1             # log-lambda is the LAST output of the first generator (:624-626)
             if num_predicted_pars == 0:
                 self.mlp_predictors.append(None)
                 prev_extra_input_num += emb_num
@@ -329,6 +350,10 @@ class pdf(nn.Module):
                 these_params = params_list[ind]
                 if len(these_params) == 0:
                     continue
+                if mlp_predictor is not None and self.predict_log_normalization and \
+                        self.join_poisson_and_pdf_description and ind == 0:
+                    # desired initial log-lambda 0.1 behind the flow parameters (reference main/default.py:1893-1897)
+                    these_params = torch.cat([these_params, torch.Tensor([0.1]).type(these_params.dtype)])
                 if mlp_predictor is not None and hasattr(mlp_predictor, "initialize_uvbs") and self.amortize_everything:
                     n_uvb = mlp_predictor.num_amortization_params
                     global_amortization_init[global_amortization_index:global_amortization_index + n_uvb] = \
@@ -476,6 +501,22 @@ class pdf(nn.Module):
                 amortization_parameters.shape[1] == self.total_number_amortizable_params), \
             (amortization_parameters.shape, self.total_number_amortizable_params)
         assert (amortization_parameters.shape[0] == batch), "batch size of amortization_parameters must agree with the batch size of the input"
+
+    def log_mean_poisson(self, conditional_input=None, amortization_parameters=None):
+        """log-lambda of the Poisson prediction, (B,1) (or the (1,1) parameter of an unconditional pdf).
+        Reference main/default.py:832-877."""
+        if self.log_normalization is None:
+            raise Exception("This PDF does not predict the log-mean of a Poisson distriution. Initialize with 'predict_log_normalization'=True for this possibility.")
+        if amortization_parameters is not None:
+            raise Exception("Currently there is no support for the prediction of log-lambda and simultanesouly passing amortization_parameters .. there is some thinking involved in what to do in this situation so it is not supported at the moment.")
+        if conditional_input is None:
+            return self.log_normalization
+        assert (self.join_poisson_and_pdf_description)
+        mlp = self.mlp_predictors[0]
+        with torch.no_grad():
+            if hasattr(mlp, "u_v_b_pars"):
+                return mlp(conditional_input)[:, -1:]
+            return engine.sequential_mlp_forward(mlp, conditional_input)[:, -1:]
 
     def all_layer_inverse(self, x, log_det, data_summary, amortization_parameters=None, force_embedding_coordinates=False,
                           force_intrinsic_coordinates=False, only_last=False):

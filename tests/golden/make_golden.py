@@ -191,6 +191,14 @@ CASES = {
     # layers with their base chart forced on (fix_euclidean_to_sphere_first)
     "last_e3s2e2": dict(pdf_defs="e3+s2+e2", flow_defs="ggg+vf+gg", n=300, perturb=0.3, only_last=True),
     "last_e2s1s2_cond": dict(pdf_defs="e2+s1+s2", flow_defs="gg+mo+fv", n=300, cond_dim=3, perturb=0.2, only_last=True),
+    # Poisson log-mean prediction (main/default.py:466-477, :624-626, :832-877): joint with the flow parameters (last
+    # output of the generator) for a conditional pdf, a free parameter for an unconditional one
+    "poisson_e2_joint_cond": dict(pdf_defs="e2", flow_defs="gg", n=300, cond_dim=3, perturb=0.2, poisson=True,
+                                  pdf_kw=dict(predict_log_normalization=True, join_poisson_and_pdf_description=True)),
+    "poisson_s2_joint_cond": dict(pdf_defs="s2", flow_defs="f", n=300, cond_dim=2, perturb=0.2, poisson=True,
+                                  pdf_kw=dict(predict_log_normalization=True, join_poisson_and_pdf_description=True)),
+    "poisson_e2_uncond": dict(pdf_defs="e2", flow_defs="gg", n=300, perturb=0.2, poisson=True,
+                              pdf_kw=dict(predict_log_normalization=True)),
     # one conditional input per sub-pdf (conditional_input_dim as a list, main/default.py:286-296, :944-949)
     "condlist_e2s2e1": dict(pdf_defs="e2+s2+e1", flow_defs="gg+f+g", n=300, cond_dim=[3, 2, 4], perturb=0.2),
     # training (BASELINE.json configs[4] structure at fixture size): gradients of mean(log_pdf) w.r.t. every MLP tensor
@@ -251,6 +259,9 @@ def build_case(jf, name, spec):
         "ref_roundtrip_base_err": np.nanmax(np.abs((rt_base - z).numpy())),
         "ref_roundtrip_logp_err": np.nanmax(np.abs((rt_logp - samp_logp).numpy())),
     }
+    if spec.get("poisson", False):
+        with torch.no_grad():
+            out["log_lambda"] = pdf.log_mean_poisson(conditional_input=cond).numpy()
     if spec.get("only_last", False):
         with torch.no_grad():
             l_logp, l_logp_base, l_base = pdf(x, conditional_input=cond, only_last=True)

@@ -275,3 +275,19 @@ def test_only_last_matches_reference(name, lib_built):
     assert (full_lp - lp).abs().max() > 1e-3          # it really is a different (shorter) flow
     st = p.kernel_status()
     assert st["nonfinite"] == 0 and st["unconverged"] == 0
+
+
+@pytest.mark.parametrize("name", ["poisson_e2_joint_cond", "poisson_s2_joint_cond", "poisson_e2_uncond"])
+def test_poisson_log_lambda_matches_reference(name, lib_built):
+    """pdf.log_mean_poisson (main/default.py:832-877): the last output of the first generator (joint prediction) or
+    the free parameter; the flow evaluated next to it is covered by the golden parity tests on the same files."""
+    from helpers import build_pdf, load_golden
+    meta, params, data = load_golden(name)
+    p = build_pdf(meta, params).cuda()
+    cond = torch.from_numpy(data["cond"]).cuda() if "cond" in data else None
+    ll = p.log_mean_poisson(conditional_input=cond)
+    assert tuple(ll.shape) == data["log_lambda"].shape
+    assert rel_err(ll.detach().cpu().numpy(), data["log_lambda"]).max() < 1e-12
+    with torch.no_grad():
+        lp, _, _ = p(torch.from_numpy(data["x"]).cuda(), conditional_input=cond)
+    assert rel_err(lp.cpu().numpy(), data["logp"]).max() < 1e-10

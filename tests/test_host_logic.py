@@ -63,9 +63,18 @@ def test_conditional_wiring_dims():
 
 
 def test_unsupported_fails_loudly():
-    for kw in (dict(skip_mlp_initialization=True), dict(predict_log_normalization=True)):
+    for kw in (dict(skip_mlp_initialization=True),
+               # a separate log-lambda MLP: the reference's own log_mean_poisson() calls it outdated and raises
+               dict(predict_log_normalization=True, conditional_input_dim=2),
+               # the reference's init fails for a joint prediction through an AmortizableMLP
+               dict(predict_log_normalization=True, join_poisson_and_pdf_description=True, conditional_input_dim=2,
+                    amortization_mlp_use_custom_mode=True)):
         with pytest.raises(NotImplementedError):
             jfb.pdf("e2", "gg", **kw)
+    with pytest.raises(AssertionError):      # log-lambda prediction needs a single sub-pdf (main/default.py:471-472)
+        jfb.pdf("e2+e1", "gg+g", predict_log_normalization=True)
+    with pytest.raises(Exception):           # joint prediction needs a conditional input (main/default.py:583-584)
+        jfb.pdf("e2", "gg", predict_log_normalization=True, join_poisson_and_pdf_description=True)
     with pytest.raises(AssertionError):      # reference main/default.py:118-119: amortizing everything needs custom MLPs
         jfb.pdf("e2", "gg", amortize_everything=True)
     with pytest.raises(NotImplementedError):

@@ -119,3 +119,26 @@ def test_oracle_only_last(name):
     stol = max(1e-9, 10 * float(data["ref_roundtrip_base_err"]))
     assert rel_err(xs.numpy(), data["last_samp_x"]).max() < stol
     assert rel_err(slogp.numpy(), data["last_samp_logp"]).max() < stol
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("poisson_")])
+def test_poisson_log_normalization_structure(name):
+    """predict_log_normalization (main/default.py:466-477, :624-626, :1893-1897): the generator predicts one extra
+    (last) output, initialised to 0.1; an unconditional pdf owns a (1,1) parameter.  The flow itself is unchanged, which
+    test_oracle_reproduces_reference checks on the same files (the oracle reads the first n_par generator outputs)."""
+    import torch
+    meta, params, data = load_golden(name)
+    pdf = build_pdf(meta, seed=meta["seed"])
+    assert sorted(pdf.state_dict().keys()) == sorted(params.keys())
+    for k, v in pdf.state_dict().items():
+        assert tuple(v.shape) == params[k].shape, k
+    n_par = sum(pdf.num_parameter_list[0])
+    if meta["conditional_input_dim"] is None:
+        assert pdf.log_normalization.shape == (1, 1) and data["log_lambda"].shape == (1, 1)
+        pdf.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+        assert np.array_equal(pdf.log_mean_poisson().detach().numpy(), data["log_lambda"])
+    else:
+        last = pdf.mlp_predictors[0][-1]
+        assert last.out_features == n_par + 1
+        assert abs(float(last.bias.data[-1]) - 0.1) < 1e-7
+        assert data["log_lambda"].shape == (data["x"].shape[0], 1)
