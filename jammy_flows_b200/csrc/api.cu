@@ -530,9 +530,17 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
     m.lda = maxd | 1;
     if (m.n_linear == 1 && m.dims[0] <= kExpandK && m.dims[1] >= 256 && so_p == 1) {
         // narrow input, wide row-major output (the U half of a factorised layer): write-bound expand kernel
-        dim3 grid((unsigned)((m.dims[1] + 255) / 256), (unsigned)((B + kExpandRows - 1) / kExpandRows));
-        if (grid.y > 65535u) return JF_ERR_UNSUPPORTED;
-        mlp_expand_kernel<T><<<grid, 256, 0, st>>>(m);
+        int dev = 0, sms = 148;
+        JF_CUDA_OK(cudaGetDevice(&dev));
+        JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t col_tiles = (m.dims[1] + 511) / 512, row_tiles = (B + kExpandRows - 1) / kExpandRows;
+        int64_t gy = ((int64_t)sms * 6 + col_tiles - 1) / col_tiles;      // ~6 CTAs per SM in total, each walks row tiles
+        if (gy > row_tiles) gy = row_tiles;
+        if (gy > 65535) gy = 65535;
+        dim3 grid((unsigned)col_tiles, (unsigned)gy);
+        if (m.dims[0] <= 4) mlp_expand_kernel<T, 4><<<grid, 256, 0, st>>>(m);
+        else if (m.dims[0] <= 8) mlp_expand_kernel<T, 8><<<grid, 256, 0, st>>>(m);
+        else mlp_expand_kernel<T, 16><<<grid, 256, 0, st>>>(m);
         return check_launch();
     }
     if (!accumulate && ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
