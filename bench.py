@@ -21,12 +21,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints exactly ONE line on stdout (the JSON); NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) goes
-# to stdout as well, so it is silenced unless explicitly kept
-if os.environ.get("JF_KEEP_NCCL_DEBUG") is None:
-    os.environ["NCCL_DEBUG"] = "WARN"
-# ... and because NCCL still prints its version line at WARN level (seen on the 2-GPU runs), everything that lands on
-# file descriptor 1 during the run is sent to stderr; the JSON line is written to the saved descriptor at the end
+# rank 0 prints exactly ONE line on stdout (the JSON).  NCCL's banner / NCCL_DEBUG=INFO lines go to stdout as well; they
+# are NOT suppressed (the driver reads the communicator's rank count out of them): everything that lands on file
+# descriptor 1 during the run is sent to stderr instead, and the JSON line is written to the saved descriptor at the end
 _JSON_OUT = os.fdopen(os.dup(1), "w")
 os.dup2(2, 1)
 

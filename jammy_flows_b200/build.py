@@ -55,10 +55,10 @@ def build(force=False, verbose=True, extra_flags=(), out=None, tag=""):
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
-        out, _ = p.communicate()
-        log.append(out)
+        text, _ = p.communicate()
+        log.append(text)
         if p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(text)
             raise RuntimeError("nvcc failed on %s" % src)
     cmd = [_nvcc(), "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

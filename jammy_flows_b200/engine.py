@@ -886,23 +886,42 @@ class _MlpParamsTc(torch.autograd.Function):
         g_pre = g_h * (1.0 - h * h)
         g_w1 = torch.mm(g_pre.t(), inp)                      # [128, in]
         g_b1 = g_pre.sum(dim=0)
-        return None, g_w1, g_b1, g_w2, g_b2
+        # the generator's input may itself carry history (a conditional_input produced by an upstream encoder)
+        g_inp = torch.mm(g_pre, w1) if ctx.needs_input_grad[0] else None
+        return g_inp, g_w1, g_b1, g_w2, g_b2
 
 
-def _tc_mlp_eligible(mlp, dt):
-    """Linear-tanh-Linear with 128 hidden units and few enough inputs for the tcgen05 kernel (csrc/mlp_i8.cuh)."""
+def _tc_mlp_eligible(mlp, dt, dev):
+    """Linear-tanh-Linear with 128 hidden units and few enough inputs for the tcgen05 kernel (csrc/mlp_i8.cuh).  The
+    kernel reads the weights through raw pointers with the element type of the input: weights of another dtype / on
+    another device take the torch path, which raises the same dtype error as the reference."""
     mods = list(mlp)
     if len(mods) != 3 or not isinstance(mods[0], torch.nn.Linear) or not isinstance(mods[2], torch.nn.Linear):
         return False
     if mods[0].out_features != 128:
         return False
+    if any(q.dtype != dt or q.device != dev for q in mlp.parameters()):
+        return False
     return mods[0].in_features <= (16 if dt == torch.float64 else 96)
+
+
+def sequential_mlp_forward_trainable(mlp, x):
+    """nn.Sequential generator on x [R, in] -> [R, out] WITH autograd history (the tcgen05 forward + GEMM backward of
+    `_MlpParamsTc` when the shape fits, the torch module otherwise)."""
+    _require_cuda(x, "MLP input")
+    if _tc_mlp_eligible(mlp, x.dtype, x.device):
+        mods = list(mlp)
+        return _MlpParamsTc.apply(x, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias).t()
+    return mlp(x)
 
 
 def pdf_logpdf_trainable(pdf, x, cond):
     """-> (log_pdf [B] with autograd history, log_pdf_base [B], base [B, D]).  Reference: main/default.py:1059-1117 with
     `torch.is_grad_enabled()`; the conditioning on earlier sub-pdfs uses the data x (no gradient flows through it)."""
     x, cond = _prep_inputs(pdf, x, cond, "x")
+    if x.requires_grad:
+        raise NotImplementedError("gradients with respect to the evaluation points x are not provided by the backward "
+                                  "kernels (parameters and conditional_input are); detach x")
     dt, dev = x.dtype, x.device
     desc = pdf._desc(dt)
     status = pdf._status(dev)
@@ -921,7 +940,7 @@ def pdf_logpdf_trainable(pdf, x, cond):
             pieces = ([cond] if cond is not None else []) + prev
             inp = torch.cat(pieces, dim=1) if len(pieces) > 1 else pieces[0]
             mods = list(mlp)
-            if _tc_mlp_eligible(mlp, dt):
+            if _tc_mlp_eligible(mlp, dt, dev):
                 params_t = _MlpParamsTc.apply(inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias)
             else:
                 h = inp

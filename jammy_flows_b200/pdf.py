@@ -513,6 +513,15 @@ class pdf(nn.Module):
             return self.log_normalization
         assert (self.join_poisson_and_pdf_description)
         mlp = self.mlp_predictors[0]
+        needs_grad = torch.is_grad_enabled() and (conditional_input.requires_grad or
+                                                  any(q.requires_grad for q in mlp.parameters()))
+        if needs_grad:
+            # the Poisson term of the loss back-propagates through log-lambda (reference main/default.py:873 returns it
+            # with autograd history)
+            if hasattr(mlp, "u_v_b_pars"):
+                raise NotImplementedError("log_mean_poisson with gradients through an AmortizableMLP generator is not "
+                                          "built; evaluate under torch.no_grad() or use an nn.Sequential generator")
+            return engine.sequential_mlp_forward_trainable(mlp, conditional_input)[:, -1:]
         with torch.no_grad():
             if hasattr(mlp, "u_v_b_pars"):
                 return mlp(conditional_input)[:, -1:]
