@@ -267,6 +267,22 @@ int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype,
                       void* out, int64_t out_stride_param, int64_t out_stride_row,
                       int64_t B, void* workspace, int64_t workspace_bytes, int prepared, void* stream);
 
+/* Parameter generator + layer chain of ONE conditional Euclidean sub-pdf in a single kernel (csrc/gf_fused.cuh): replaces
+ * the hand-off main/default.py:956 (MLP call) -> :998-1029 (layer loop over `extra_inputs` slices), and for sampling
+ * :1438 -> :1482-1506, without the [rows, n_params] block ever existing in HBM.  Eligible: fp64, manifold 'e' with
+ * dim <= 4, default-option "g" layers with K = 10, generator Linear(<=16) -> tanh(128) -> Linear;
+ * jf_subpdf_generated_workspace_bytes returns -1 otherwise (and jf_subpdf_apply_generated JF_ERR_UNSUPPORTED): callers
+ * then chain jf_mlp_forward_ws and jf_subpdf_apply.  `prepared` != 0 reuses the weight slices a previous call with the
+ * same weights and direction left in the workspace.  seg_ptrs / weights / biases as in jf_mlp_forward, the remaining
+ * arguments as in jf_subpdf_apply. */
+int64_t jf_subpdf_generated_workspace_bytes(const JfSubPdfDesc* desc, const JfMlpDesc* mlp, int dtype);
+int jf_subpdf_apply_generated(const JfSubPdfDesc* desc, const JfMlpDesc* mlp, int dtype, int direction,
+                              const void* const* seg_ptrs, const int64_t* seg_ld,
+                              const void* const* weights, const void* const* biases,
+                              const void* in, int64_t ld_in, const void* logdet_in, void* logdet_out,
+                              const void* logbase_in, void* logbase_out, void* out, int64_t ld_out, int64_t B,
+                              void* workspace, int64_t workspace_bytes, int prepared, int64_t* status, void* stream);
+
 /* ---- whole-pdf entries -------------------------------------------------------------------------------------------- */
 typedef struct JfPdfDesc {
     int32_t abi_version; /* JF_ABI_VERSION */

@@ -18,6 +18,7 @@
 #include "mlp_i8.cuh"
 #include "gf_bwd.cuh"
 #include "rowwise.cuh"
+#include "gf_fused_launch.cuh"
 #include <cstdlib>
 
 using namespace jf;
@@ -615,6 +616,94 @@ extern "C" int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype, const void* c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// jf_subpdf_apply_generated: parameter generator + layer chain of one conditional Euclidean sub-pdf in ONE kernel
+// (csrc/gf_fused.cuh): the per-row parameters never exist in HBM
+// ---------------------------------------------------------------------------------------------------------------------
+static bool fused_eligible(const JfSubPdfDesc* sp, const JfMlpDesc* md, int dtype) {
+    static const bool off = [] { const char* e = getenv("JF_FUSED"); return e != nullptr && atoi(e) == 0; }();
+    if (off || dtype != JF_F64 || sp == nullptr || md == nullptr) return false;
+    if (sp->manifold != 'e' || sp->dim < 1 || sp->dim > kFuMaxD) return false;
+    if (sp->n_layers < 1 || sp->n_layers > JF_MAX_LAYERS) return false;
+    if (md->n_linear != 2 || md->dims[1] != kI8H || md->dims[0] < 1 || md->dims[0] > kI8MaxKin) return false;
+    if (md->dims[2] < sp->n_params) return false;
+    int off_p = 0;
+    for (int l = 0; l < sp->n_layers; ++l) {
+        const JfLayerDesc& L = sp->layers[l];
+        if (L.kind != JF_LAYER_GF || !gf_layer_is_default(L) || L.dim != sp->dim) return false;
+        if (L.K != kFuK || L.norm_mode != JF_NORM_REGULATED) return false;
+        if (L.hh_iter < 0 || L.hh_iter > kFuMaxHH) return false;
+        if (L.inv_type < 0 || L.inv_type > 3) return false;
+        if (!(L.w_min > 0) || !(L.w_max > 0)) return false;
+        if (L.param_offset != off_p) return false;
+        if ((L.has_offset ? sp->dim : 0) + L.hh_iter * sp->dim + 3 * L.K * sp->dim != L.n_params) return false;
+        off_p += L.n_params;
+    }
+    return off_p == sp->n_params;
+}
+
+extern "C" int64_t jf_subpdf_generated_workspace_bytes(const JfSubPdfDesc* desc, const JfMlpDesc* mlp, int dtype) {
+    if (!fused_eligible(desc, mlp, dtype)) return -1;
+    return fused_prep_bytes(desc->n_layers);
+}
+
+extern "C" int jf_subpdf_apply_generated(const JfSubPdfDesc* desc, const JfMlpDesc* mlp, int dtype, int direction,
+                                         const void* const* seg_ptrs, const int64_t* seg_ld,
+                                         const void* const* weights, const void* const* biases, const void* in,
+                                         int64_t ld_in, const void* logdet_in, void* logdet_out, const void* logbase_in,
+                                         void* logbase_out, void* out, int64_t ld_out, int64_t B, void* workspace,
+                                         int64_t workspace_bytes, int prepared, int64_t* status, void* stream) {
+    if (desc == nullptr || mlp == nullptr || in == nullptr || out == nullptr || seg_ptrs == nullptr || seg_ld == nullptr ||
+        weights == nullptr || biases == nullptr)
+        return JF_ERR_BAD_ARG;
+    if (direction != JF_DIR_LOGPDF && direction != JF_DIR_SAMPLE) return JF_ERR_BAD_ARG;
+    if (!fused_eligible(desc, mlp, dtype)) return JF_ERR_UNSUPPORTED;
+    if (mlp->n_segments < 1 || mlp->n_segments > JF_MAX_MLP_SEGMENTS) return JF_ERR_BAD_DESC;
+    if (workspace == nullptr || workspace_bytes < fused_prep_bytes(desc->n_layers)) return JF_ERR_WORKSPACE;
+    if (B < 0) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    FuArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m.n_linear = 2;
+    int in_sum = 0;
+    for (int l = 0; l <= 2; ++l) a.m.dims[l] = mlp->dims[l];
+    a.m.n_segments = mlp->n_segments;
+    for (int s = 0; s < mlp->n_segments; ++s) {
+        if (seg_ptrs[s] == nullptr || mlp->seg_cols[s] < 1) return JF_ERR_BAD_ARG;
+        a.m.seg_cols[s] = mlp->seg_cols[s];
+        a.m.seg_ptr[s] = (const double*)seg_ptrs[s];
+        a.m.seg_ld[s] = seg_ld[s];
+        in_sum += mlp->seg_cols[s];
+    }
+    if (in_sum != mlp->dims[0]) return JF_ERR_BAD_DESC;
+    for (int l = 0; l < 2; ++l) {
+        a.m.wt[l] = (const double*)weights[l];
+        a.m.bias[l] = (const double*)biases[l];
+        if (a.m.wt[l] == nullptr || a.m.bias[l] == nullptr) return JF_ERR_BAD_ARG;
+    }
+    a.m.B = B;
+    a.n_layers = desc->n_layers;
+    a.d = desc->dim;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const JfLayerDesc& L = desc->layers[l];
+        FuLayerC& c = a.layers[l];
+        c.inv_type = L.inv_type; c.has_offset = L.has_offset; c.hh_iter = L.hh_iter; c.raw_off = L.param_offset;
+        c.w_min = L.w_min; c.inv_w_max = 1.0 / L.w_max; c.n_min = L.n_min; c.n_max = L.n_max;
+    }
+    a.in = (const double*)in; a.ld_in = ld_in;
+    a.out = (double*)out; a.ld_out = ld_out;
+    a.logdet_in = (const double*)logdet_in; a.logdet_out = (double*)logdet_out;
+    a.logbase_in = (const double*)logbase_in; a.logbase_out = (double*)logbase_out;
+    a.status = status;
+    int rc = launch_fused_prep(a, a.m.wt[1], a.m.bias[1], direction, workspace, !prepared, st);
+    if (rc != JF_OK) return rc;
+    if (!prepared) { rc = check_launch(); if (rc != JF_OK) return rc; }
+    rc = launch_fused(a, direction, st);
+    if (rc != JF_OK) return rc;
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // whole-pdf orchestration (chunked; every launch on the caller's stream)
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -648,7 +737,9 @@ static int ws_layout(const JfPdfDesc* d, int64_t chunk, WsLayout& w) {
         w.mlp_bytes[k] = 0;
         if (d->has_mlp[k]) {
             JfMlpDesc md = d->mlp[k];           // jf_mlp_workspace_bytes only looks at n_linear / dims
-            const int64_t nb = jf_mlp_workspace_bytes(&md, d->dtype);
+            int64_t nb = jf_mlp_workspace_bytes(&md, d->dtype);
+            const int64_t nf = jf_subpdf_generated_workspace_bytes(&d->sub[k], &md, d->dtype);
+            if (nf > nb) nb = nf;
             if (nb > 0) { w.mlp_bytes[k] = nb; off = align_up(off + nb, 256); }
         }
     }
@@ -720,6 +811,17 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
                     ++ns;
                 }
                 md.n_segments = ns;
+                if (w.mlp_bytes[k] > 0 && fused_eligible(sp, &md, d->dtype)) {
+                    // generator + layer chain in one kernel: the parameter block never touches HBM
+                    const int in_col_f = logpdf ? d->target_col[k] : d->base_col[k];
+                    const int out_col_f = logpdf ? d->base_col[k] : d->target_col[k];
+                    rc = jf_subpdf_apply_generated(sp, &md, d->dtype, direction, seg_ptr, seg_ld, P->weights[k], P->biases[k],
+                                                   src_c + (int64_t)in_col_f * es, ld_src, k == 0 ? nullptr : logdet, logdet,
+                                                   k == 0 ? nullptr : logbase, logbase, dst_c + (int64_t)out_col_f * es,
+                                                   ld_dst_c, n, ws + w.mlp[k], w.mlp_bytes[k], r0 > 0 ? 1 : 0, status, st);
+                    if (rc != JF_OK) return rc;
+                    continue;
+                }
                 // the sliced last-layer weights are prepared by the first chunk and reused by the later ones
                 rc = jf_mlp_forward_ws(&md, d->dtype, seg_ptr, seg_ld, P->weights[k], P->biases[k], ws + w.params, chunk,
                                        1, n, w.mlp_bytes[k] > 0 ? ws + w.mlp[k] : nullptr, w.mlp_bytes[k], r0 > 0 ? 1 : 0,

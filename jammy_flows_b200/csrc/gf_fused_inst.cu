@@ -1,0 +1,47 @@
+// instantiation + launcher of the fused generator + "g"-chain kernel (csrc/gf_fused.cuh); its own translation unit so
+// that the library builds in parallel
+#include "gf_fused_launch.cuh"
+#include "gf_fused.cuh"
+
+namespace jf {
+
+template <int NS, int DIR, int KR>
+static int launch_fused_one(const FuArgs& a, int smem_max, int sms, cudaStream_t st) {
+    const int Kin = a.m.dims[0];
+    int n_slots = 8;
+    while (n_slots > 3 && fu_smem_bytes(NS, Kin, n_slots) > smem_max) --n_slots;
+    const int smem = fu_smem_bytes(NS, Kin, n_slots);
+    if (smem > smem_max) return JF_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(gf_fused_kernel<NS, DIR, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t blocks = (a.m.B + kI8Rows - 1) / kI8Rows;
+    const unsigned grid = (unsigned)(blocks < sms ? blocks : sms);
+    gf_fused_kernel<NS, DIR, KR><<<grid, kFuThreads, smem, st>>>(a, n_slots);
+    return JF_OK;
+}
+
+int64_t fused_prep_bytes(int n_layers) { return fu_prep_bytes<kFuNS>(n_layers); }
+
+int launch_fused_prep(FuArgs& a, const double* W2, const double* b2, int direction, void* ws, bool run, cudaStream_t st) {
+    const int n_tiles = 3 * a.n_layers;
+    a.wsB = (const unsigned char*)ws;
+    a.consts = reinterpret_cast<const double2*>((const unsigned char*)ws + (size_t)n_tiles * kFuNS * kFuTN * kI8H);
+    if (run) fu_prep_kernel<kFuNS><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
+    return JF_OK;
+}
+
+int launch_fused(const FuArgs& a, int direction, cudaStream_t st) {
+    int dev = 0, sms = 0, smem_max = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return (int)e;
+    const bool k8 = a.m.dims[0] <= 8;
+    if (direction == JF_DIR_LOGPDF)
+        return k8 ? launch_fused_one<kFuNS, JF_DIR_LOGPDF, 8>(a, smem_max, sms, st)
+                  : launch_fused_one<kFuNS, JF_DIR_LOGPDF, 16>(a, smem_max, sms, st);
+    return k8 ? launch_fused_one<kFuNS, JF_DIR_SAMPLE, 8>(a, smem_max, sms, st)
+              : launch_fused_one<kFuNS, JF_DIR_SAMPLE, 16>(a, smem_max, sms, st);
+}
+
+}  // namespace jf
