@@ -5,17 +5,23 @@
 //   reference hand-off: main/default.py:956 (MLP call) -> :998-1029 (layer loop, `extra_inputs` slices), sampling
 //   :1438 -> :1482-1506; layer math gaussianization_flow.py:389-1114 (same arithmetic as csrc/gf.cuh, register-resident).
 //
-// Structure (one persistent CTA per SM, 128 rows per block, 18 warps):
-//   warps 0-15  workers.  Prologue: layer 1 + tanh + int8 digits of the hidden activations -> A slices in shared memory
-//               (identical to mlp2_i8_kernel).  Then worker (row, j) = (TMEM lane, column group) owns DIMENSION j of its
-//               row: per layer it drains ITS 36 parameter columns (3 MMA tiles x 12 columns: the K log-widths, K log-norms,
-//               its component of every Householder vector, K means, its offset) straight from the TMEM accumulators into
-//               registers, regulates them and evaluates the mixture (log_pdf) or finds the root (sampling).  The four
-//               workers of a row meet once per layer through a 6-field shared-memory exchange for the rotation.
+// Structure (one persistent CTA per SM, 128 rows per block, 20 warps):
+//   warps 0-15  workers (112 registers each, setmaxnreg).  Prologue: layer 1 + tanh + int8 digits of the hidden
+//               activations -> A slices in shared memory (identical to mlp2_i8_kernel).  Then worker (row, j) = (TMEM
+//               lane, column group) owns DIMENSION j of its row: per layer it drains ITS 36 parameter columns (3 MMA tiles
+//               x 12 columns) straight from the TMEM accumulators into registers -- the level accumulators are combined
+//               in 64-bit INTEGER arithmetic (the ALU pipe idles, the FP64 pipe is the bound) -- and consumes them:
+//                 log_pdf   STREAMING: a tile carries (mean, log-width, log-norm) TRIPLES, each kernel is regulated and
+//                           added to the mixture sums as it arrives, nothing but the sums stays live (tile 0 opens with the
+//                           Householder components and the offset, so the rotated coordinate is known before the first
+//                           kernel); an online rescaling exponent keeps the sums exact however far out x is;
+//                 sampling  the K regulated kernels stay in registers for the root finder (csrc/gf.cuh's, register twin).
+//               The four workers of a row meet once per layer through a 6-field shared-memory exchange for the rotation.
 //   warp 16     one elected thread issues tcgen05.mma (kind::i8, M = 128, N = 48, K = 32) for tile t+1 as soon as the
 //               workers have drained tile t; the MMAs of a tile overlap the workers' regulation / evaluation of what they
 //               already hold -- the tensor pipe and the FP64 pipe run side by side.
 //   warp 17     one thread streams the pre-sliced W2 tiles (L2 resident) with cp.async.bulk into a small ring.
+//   warps 18-19 idle (they complete the service warpgroup: setmaxnreg is a warpgroup-wide instruction).
 // W2's rows are permuted by the prep kernel into CONSUMPTION order (per direction): tile (c, part) holds, for the layer
 // consumed c-th, the 12 columns of `part` for each of the 4 dimensions.
 #pragma once
@@ -29,11 +35,16 @@ constexpr int kFuTN = 48;           // output columns per MMA tile = 4 column gr
 constexpr int kFuCG = 12;           // columns per (tile, dimension)
 constexpr int kFuLvlStride = 64;    // TMEM columns between level accumulators
 constexpr int kFuWorkers = 512;     // 16 warps
-constexpr int kFuThreads = 576;     // + MMA warp + producer warp
+constexpr int kFuThreads = 640;     // + service warpgroup: MMA warp, producer warp, two idle warps
+constexpr int kFuRegsWorker = 112;  // setmaxnreg moves registers inside the CTA's own allocation (640 x 96): 512 x 16 taken = 128 x 64 released
+constexpr int kFuRegsService = 32;
 constexpr int kFuExFields = 6;      // exchange: x, 4 Householder components, log-derivative
 constexpr int kFuExBytes = 2 * kFuMaxD * kFuExFields * kI8Rows * 8;   // double buffered
 constexpr int kFuPrivFields = 3;    // per-worker scratch in shared memory: offset, running logdet, sum of squares
 constexpr int kFuPrivBytes = kFuMaxD * kFuPrivFields * kI8Rows * 8;
+// the level accumulators of one output are combined as ONE 64-bit integer: sum_{l < 6} v_l 256^(5-l) < 2^62
+// (|v_l| <= (l+1) 2^21); a 7th level is added in floating point
+template <int NS> struct FuLv { static constexpr int kInt = NS < 6 ? NS : 6; };
 
 template <int NS>
 __host__ __device__ inline int64_t fu_prep_bytes(int n_layers) {
@@ -47,13 +58,27 @@ __host__ __device__ inline int fu_smem_bytes(int ns, int kin, int n_slots) {
 
 // source row of W2 / b2 (index into the sub-pdf's raw parameter vector) of fused column (tile, jj); -1: zero column.
 // Slots of (layer, dimension j), 12 per part:
-//   part 0: log_w[0..9], offset_j, log_n[0]      part 1: log_n[1..8], v_0[j] .. v_3[j]      part 2: mean[0..9], log_n[9], pad
-__host__ __device__ inline int fu_source_param(const FuLayerC& c, int d, int part, int jj) {
+//   sampling  part 0: log_w[0..9], offset_j, log_n[0]      part 1: log_n[1..8], v_0[j] .. v_3[j]      part 2: mean[0..9], log_n[9], pad
+//   log_pdf   part 0: v_0[j] .. v_3[j], offset_j, (mean, log_w, log_n)[0], [1], pad      part 1: triples 2..5      part 2: triples 6..9
+__host__ __device__ inline int fu_source_param(const FuLayerC& c, int d, int direction, int part, int jj) {
     const int cg = jj / kFuCG, s = jj - cg * kFuCG;
     if (cg >= d) return -1;
     const int K = kFuK;
     const int off_hh = c.raw_off + (c.has_offset ? d : 0);
     const int off_m = off_hh + c.hh_iter * d, off_w = off_m + K * d, off_n = off_w + K * d;
+    if (direction == JF_DIR_LOGPDF) {
+        int t = s;                       // index into the triple stream of this part
+        int k0 = 2 + 4 * (part - 1);
+        if (part == 0) {
+            if (s < 4) return s < c.hh_iter ? off_hh + s * d + cg : -1;
+            if (s == 4) return c.has_offset ? c.raw_off + cg : -1;
+            if (s == 11) return -1;
+            t = s - 5;
+            k0 = 0;
+        }
+        const int k = k0 + t / 3, f = t - 3 * (t / 3);
+        return (f == 0 ? off_m : (f == 1 ? off_w : off_n)) + k * d + cg;
+    }
     if (part == 0) {
         if (s < 10) return off_w + s * d + cg;
         if (s == 10) return c.has_offset ? c.raw_off + cg : -1;
@@ -80,7 +105,7 @@ __global__ void __launch_bounds__(128) fu_prep_kernel(const __grid_constant__ Fu
     __shared__ double s_inv[kFuTN];
     __shared__ int s_src[kFuTN];
     for (int jj = threadIdx.x; jj < kFuTN; jj += blockDim.x) {
-        const int src = fu_source_param(a.layers[l], a.d, part, jj);
+        const int src = fu_source_param(a.layers[l], a.d, direction, part, jj);
         double mx = 0.0;
         if (src >= 0)
             for (int k = 0; k < kI8H; ++k) mx = fmax(mx, fabs(W2[(size_t)src * kI8H + k]));
@@ -88,7 +113,7 @@ __global__ void __launch_bounds__(128) fu_prep_kernel(const __grid_constant__ Fu
         if (mx > 0.0) { frexp(mx, &e); }
         s_inv[jj] = ldexp(1.0, -e);
         s_src[jj] = src;
-        cst[tile * kFuTN + jj] = src >= 0 ? make_double2(ldexp(1.0, e - 12), b2[src]) : make_double2(0.0, 0.0);
+        cst[tile * kFuTN + jj] = src >= 0 ? make_double2(ldexp(1.0, e - 12 - 8 * (FuLv<NS>::kInt - 1)), b2[src]) : make_double2(0.0, 0.0);
     }
     __syncthreads();
     unsigned char* base = ws + (size_t)tile * NS * kFuTN * kI8H;
@@ -109,10 +134,11 @@ JF_DEVINL void tmem_ld4(uint32_t taddr, int* v) {
 }
 JF_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// 12 parameter values of this worker from the NS level accumulators (same Horner / scale / bias arithmetic as the
-// epilogue of mlp2_i8_kernel, so the raw parameters are bit-identical to the unfused path)
+// 12 parameter values of this worker from the NS level accumulators: exact integer combine of the levels (ALU pipe),
+// one conversion, one FMA with (scale, b2)
 template <int NS>
 JF_DEVINL void fu_drain(uint32_t tbase, const double2* __restrict__ cst, double* v) {
+    constexpr int LI = FuLv<NS>::kInt;
 #pragma unroll
     for (int c4 = 0; c4 < 3; ++c4) {
         int r[NS][4];
@@ -121,14 +147,82 @@ JF_DEVINL void fu_drain(uint32_t tbase, const double2* __restrict__ cst, double*
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double sacc = __hiloint2double(0x43300000, r[NS - 1][j] ^ 0x80000000) - 4503601774854144.0;
+            long long acc = r[0][j];
 #pragma unroll
-            for (int l = NS - 2; l >= 0; --l)
-                sacc = fma(sacc, 0.00390625, __hiloint2double(0x43300000, r[l][j] ^ 0x80000000) - 4503601774854144.0);
+            for (int l = 1; l < LI; ++l) acc = acc * 256 + (long long)r[l][j];
+            double sacc = __ll2double_rn(acc);
+#pragma unroll
+            for (int l = LI; l < NS; ++l) sacc = fma((double)r[l][j], 1.0 / (double)(1ull << (8 * (l - LI + 1))), sacc);
             const double2 sb = __ldg(cst + c4 * 4 + j);
             v[c4 * 4 + j] = fma(sacc, sb.x, sb.y);
         }
     }
+}
+
+// ---- log_pdf: streaming mixture sums (same quantities as mix_eval of csrc/gf.cuh, accumulated kernel by kernel) ------
+// The rescaling exponent D plays the role of mix_eval's delta, but is found ONLINE: it is 0 unless the kernels seen so
+// far are all more than 512 widths away from x, and whenever a nearer kernel arrives the scaled sums are brought to the
+// new exponent (a rare, divergent branch).  With D = 0 -- every row that is not an extreme outlier -- the arithmetic is
+// that of mix_eval with delta = 0; the norms are used unnormalised and the sums divided by their total at the end.
+struct FuSums {
+    double D, E;                                  // rescaling exponent of the "small" sums and of Sp; E = exp(-D)
+    double big_p, small_p, big_n, small_n, Sp, ex, qc, nsum;
+    int n_pos;                                    // kernels with a >= 0
+};
+
+template <bool FIRST>
+JF_DEVINL void fu_stream(FuSums& A, const FuLayerC& lc, double x, double m, double w_raw, double n_raw) {
+    const double iw = regulate_inv_width(w_raw, lc.w_min, lc.inv_w_max);
+    const double n = regulate_norm(n_raw, lc.n_min, lc.n_max);
+    const double a = (x - m) * iw, sa = fabs(a);
+    if (FIRST) {
+        A.D = sa > 512.0 ? sa : 0.0;
+        A.E = 1.0;
+        if (A.D > 0.0) A.E = exp_neg(-A.D);
+        A.big_p = A.small_p = A.big_n = A.small_n = A.Sp = A.ex = A.qc = 0.0;
+        A.nsum = n;
+        A.n_pos = 0;
+    } else {
+        A.nsum += n;
+        if (A.D > 0.0 && sa < A.D) {
+            const double nd = sa > 512.0 ? sa : 0.0;
+            const double f = exp_neg(nd - A.D);
+            A.small_p *= f; A.small_n *= f; A.Sp *= f; A.qc *= f;
+            A.D = nd;
+            A.E = nd > 0.0 ? exp_neg(-nd) : 1.0;
+        }
+    }
+    const double u = exp_neg(A.D - sa);
+    const double e = u * A.E;
+    const double rx = rcp_1to2(1.0 + e);
+    const double nr = n * rx, nur = nr * u;
+    const double pt = nur * iw * rx;
+    if (a >= 0.0) { A.big_p += nr; A.small_p += nur; ++A.n_pos; }
+    else          { A.big_n += nr; A.small_n += nur; }
+    A.Sp += pt;
+    if (a < -20.0) {                               // softplus-threshold quirk of the reference, see mix_eval
+        const double nq = n * e * rx;
+        A.ex += nq;
+        A.qc = fma(nq, u, A.qc);
+        A.Sp = fma(nq * u * iw, 1.0 + rx, A.Sp);
+    }
+}
+
+JF_DEVINL MixVal<double> fu_stream_finish(FuSums& A) {
+    const bool all_neg = A.n_pos == 0, all_pos = A.n_pos == kFuK;
+    if (A.D > 0.0 && !(all_neg || all_pos)) { A.small_n *= A.E; A.qc *= A.E; A.small_p *= A.E; }
+    const double inv = rcp_pos_(A.nsum);
+    MixVal<double> v;
+    v.Sc = (A.big_p + A.small_n + A.qc) * inv;
+    v.Ss = (A.small_p + A.big_n) * inv;
+    v.Sp = A.Sp * inv;
+    v.ex = A.ex * inv;
+    v.Sd = 0.0;
+    v.E = A.E;
+    v.dc = all_neg ? A.D : 0.0;
+    v.ds = all_pos ? A.D : 0.0;
+    v.dp = A.D;
+    return v;
 }
 
 // ---- register-resident twins of mix_eval / presolve_f32 / solve_logit / solve_general (csrc/gf.cuh); same arithmetic ----
@@ -362,6 +456,9 @@ JF_DEVINL double fu_solve(const FuMix& p, int type, double z, double& logd_out, 
 }
 
 // ---- main kernel ------------------------------------------------------------------------------------------------------
+template <int REGS> JF_DEVINL void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> JF_DEVINL void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
 template <int NS, int DIR, int KR>
 __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_constant__ FuArgs a, int n_slots) {
     using Cfg = I8Cfg<NS, kFuTN>;
@@ -410,54 +507,58 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kFuTN >> 3) << 17) | ((uint32_t)(kI8Rows >> 4) << 24);
 
-    if (warp == 17) {
-        // ---- producer: stream every W2 slice of every block through the ring ----
-        if (lane == 0) {
-            const int loads_per_block = n_tiles * NS;
-            const int64_t total = (int64_t)my_blocks * loads_per_block;
-            int slot = 0, idx = 0;
-            uint32_t wrap_par = 1;                      // parity to wait for on empty[slot]: first round passes
-            for (int64_t i = 0; i < total; ++i) {
-                mbar_wait(bar_empty(slot), wrap_par);
-                mbar_expect_tx(bar_full(slot), Cfg::kSliceBytesB);
-                bulk_g2s(sbase + offB + slot * Cfg::kSliceBytesB, a.wsB + (size_t)idx * Cfg::kSliceBytesB, Cfg::kSliceBytesB,
-                         bar_full(slot));
-                if (++slot == n_slots) { slot = 0; wrap_par ^= 1u; }
-                if (++idx == loads_per_block) idx = 0;
+    if (warp >= 16) {
+        reg_dec<kFuRegsService>();
+        if (warp == 17) {
+            // ---- producer: stream every W2 slice of every block through the ring ----
+            if (lane == 0) {
+                const int loads_per_block = n_tiles * NS;
+                const int64_t total = (int64_t)my_blocks * loads_per_block;
+                int slot = 0, idx = 0;
+                uint32_t wrap_par = 1;                      // parity to wait for on empty[slot]: first round passes
+                for (int64_t i = 0; i < total; ++i) {
+                    mbar_wait(bar_empty(slot), wrap_par);
+                    mbar_expect_tx(bar_full(slot), Cfg::kSliceBytesB);
+                    bulk_g2s(sbase + offB + slot * Cfg::kSliceBytesB, a.wsB + (size_t)idx * Cfg::kSliceBytesB, Cfg::kSliceBytesB,
+                             bar_full(slot));
+                    if (++slot == n_slots) { slot = 0; wrap_par ^= 1u; }
+                    if (++idx == loads_per_block) idx = 0;
+                }
             }
-        }
-    } else if (warp == 16) {
-        // ---- MMA issuer ----
-        if (elect_one()) {
-            const uint32_t desc_hi = (Cfg::kSbo >> 4) | (1u << 14);
-            const uint32_t a_lo0 = (((sbase + Cfg::offA) & 0x3FFFF) >> 4) | ((uint32_t)(Cfg::kLboA >> 4) << 16);
-            const uint32_t b_lo0 = (((sbase + offB) & 0x3FFFF) >> 4) | ((uint32_t)(Cfg::kLboB >> 4) << 16);
-            int slot = 0;
-            uint32_t full_par = 0, tile_par = 0;
-            for (int jb = 0; jb < my_blocks; ++jb) {
-                mbar_wait(bar_a_full, (uint32_t)(jb & 1));        // the workers have written this block's A slices
-                tc_fence_after();
-                for (int t = 0; t < n_tiles; ++t, tile_par ^= 1u) {
-                    mbar_wait(bar_acc_empty, tile_par ^ 1u);      // the workers have drained the previous tile
+        } else if (warp == 16) {
+            // ---- MMA issuer ----
+            if (elect_one()) {
+                const uint32_t desc_hi = (Cfg::kSbo >> 4) | (1u << 14);
+                const uint32_t a_lo0 = (((sbase + Cfg::offA) & 0x3FFFF) >> 4) | ((uint32_t)(Cfg::kLboA >> 4) << 16);
+                const uint32_t b_lo0 = (((sbase + offB) & 0x3FFFF) >> 4) | ((uint32_t)(Cfg::kLboB >> 4) << 16);
+                int slot = 0;
+                uint32_t full_par = 0, tile_par = 0;
+                for (int jb = 0; jb < my_blocks; ++jb) {
+                    mbar_wait(bar_a_full, (uint32_t)(jb & 1));        // the workers have written this block's A slices
                     tc_fence_after();
-#pragma unroll
-                    for (int q = 0; q < NS; ++q) {
-                        mbar_wait(bar_full(slot), full_par);
+                    for (int t = 0; t < n_tiles; ++t, tile_par ^= 1u) {
+                        mbar_wait(bar_acc_empty, tile_par ^ 1u);      // the workers have drained the previous tile
                         tc_fence_after();
-                        const uint32_t b_lo = b_lo0 + slot * (Cfg::kSliceBytesB >> 4);
 #pragma unroll
-                        for (int p = 0; p + q < NS; ++p)
-                            tc_mma_i8_x4(tmem + (p + q) * kFuLvlStride, a_lo0 + p * (Cfg::kSliceBytesA >> 4), b_lo, desc_hi,
-                                         desc_hi, idesc, q > 0 ? 1u : 0u, (2 * Cfg::kLboA) >> 4, (2 * Cfg::kLboB) >> 4);
-                        tc_commit(bar_empty(slot));
-                        if (++slot == n_slots) { slot = 0; full_par ^= 1u; }
+                        for (int q = 0; q < NS; ++q) {
+                            mbar_wait(bar_full(slot), full_par);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + slot * (Cfg::kSliceBytesB >> 4);
+#pragma unroll
+                            for (int p = 0; p + q < NS; ++p)
+                                tc_mma_i8_x4(tmem + (p + q) * kFuLvlStride, a_lo0 + p * (Cfg::kSliceBytesA >> 4), b_lo, desc_hi,
+                                             desc_hi, idesc, q > 0 ? 1u : 0u, (2 * Cfg::kLboA) >> 4, (2 * Cfg::kLboB) >> 4);
+                            tc_commit(bar_empty(slot));
+                            if (++slot == n_slots) { slot = 0; full_par ^= 1u; }
+                        }
+                        tc_commit(bar_acc_full);
                     }
-                    tc_commit(bar_acc_full);
                 }
             }
         }
     } else {
         // ---- workers ----
+        reg_inc<kFuRegsWorker>();
         const int lq = warp & 3, cg = warp >> 2;
         const int r = lq * 32 + lane;
         const bool active = cg < d;
@@ -466,6 +567,15 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
         int ex_buf = 0;
         int n_evals = 0, n_unconv = 0, n_bad = 0;
         double* exr = sEx + r;                          // element (buf, j, f) at exr[((buf*4 + j)*6 + f)*128]
+        // wait for the next tile, drain this worker's 12 columns, hand the accumulators back
+        auto next_tile = [&](const double2* cst, double* v) {
+            mbar_wait(bar_acc_full, tile_par); tile_par ^= 1u;
+            tc_fence_after();
+            fu_drain<NS>(tbase, cst, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty);
+        };
 #pragma unroll 1
         for (int jb = 0; jb < my_blocks; ++jb) {
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)jb * gridDim.x) * kI8Rows;
@@ -557,9 +667,8 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                 double* exw = exr + (size_t)((ex_buf * 4 + cg) * kFuExFields) * kI8Rows;
                 const double* exb = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows;
                 // the four workers of a row meet here: sum of the log-derivatives, rotation of the row vector
-                auto meet = [&](double xin, double logd_in) -> double {
-                    exw[0] = xin;
-                    exw[5 * kI8Rows] = logd_in;
+                // (x, the Householder components and the log-derivative are in the exchange already)
+                auto meet = [&]() -> double {
                     bar_sync_named(2 + lq, 128);
                     double X[kFuMaxD], ld = 0.0;
 #pragma unroll
@@ -590,69 +699,71 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     }
                     return mine;
                 };
-                FuMix p;
                 double v[12];
-                // part 0: K log-widths, offset, first log-norm
-                mbar_wait(bar_acc_full, tile_par); tile_par ^= 1u;
-                tc_fence_after();
-                fu_drain<NS>(tbase, cst, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty);
-                if (DIR == JF_DIR_LOGPDF) { if (lc.has_offset) xj -= v[10]; }
-                else priv[0] = v[10];
+                if (DIR == JF_DIR_LOGPDF) {
+                    // tile 0: Householder components, offset, kernels 0-1
+                    next_tile(cst, v);
+                    if (lc.has_offset) xj -= v[4];
+                    exw[0] = xj;
 #pragma unroll
-                for (int k = 0; k < kFuK; ++k) p.iw[k] = regulate_inv_width(v[k], lc.w_min, lc.inv_w_max);
-                p.n[0] = regulate_norm(v[11], lc.n_min, lc.n_max);
-                // part 1: 8 log-norms, this dimension's component of the Householder vectors
-                mbar_wait(bar_acc_full, tile_par); tile_par ^= 1u;
-                tc_fence_after();
-                fu_drain<NS>(tbase, cst + kFuTN, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty);
+                    for (int i = 0; i < 4; ++i) exw[(1 + i) * kI8Rows] = v[i];
+                    exw[5 * kI8Rows] = logd_prev;
+                    xj = meet();
+                    FuSums S;
+                    fu_stream<true>(S, lc, xj, v[5], v[6], v[7]);
+                    fu_stream<false>(S, lc, xj, v[8], v[9], v[10]);
+                    // tiles 1, 2: four kernels each
+#pragma unroll 1
+                    for (int part = 1; part < 3; ++part) {
+                        next_tile(cst + part * kFuTN, v);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) exw[(1 + i) * kI8Rows] = v[8 + i];
+                        for (int k = 0; k < 4; ++k) fu_stream<false>(S, lc, xj, v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+                    }
+                    double y = xj, logd = 0.0;
+                    if (active && live) {
+                        const MixVal<double> mv = fu_stream_finish(S);
+                        inv_stage(lc.inv_type, mv, y, logd);
+                    }
+                    xj = y;
+                    logd_prev = logd;
+                } else {
+                    FuMix p;
+                    // part 0: K log-widths, offset, first log-norm
+                    next_tile(cst, v);
+                    priv[0] = v[10];
 #pragma unroll
-                for (int k = 1; k < 9; ++k) p.n[k] = regulate_norm(v[k - 1], lc.n_min, lc.n_max);
-                if (DIR == JF_DIR_LOGPDF) xj = meet(xj, logd_prev);      // (the MMAs of part 2 run meanwhile)
-                // part 2: K means, last log-norm
-                mbar_wait(bar_acc_full, tile_par); tile_par ^= 1u;
-                tc_fence_after();
-                fu_drain<NS>(tbase, cst + 2 * kFuTN, v);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty);
-                p.n[9] = regulate_norm(v[10], lc.n_min, lc.n_max);
-                {
-                    double nsum = 0;
+                    for (int k = 0; k < kFuK; ++k) p.iw[k] = regulate_inv_width(v[k], lc.w_min, lc.inv_w_max);
+                    p.n[0] = regulate_norm(v[11], lc.n_min, lc.n_max);
+                    // part 1: 8 log-norms, this dimension's component of the Householder vectors
+                    next_tile(cst + kFuTN, v);
 #pragma unroll
-                    for (int k = 0; k < kFuK; ++k) nsum += p.n[k];
-                    const double inv = 1.0 / nsum;
+                    for (int i = 0; i < 4; ++i) exw[(1 + i) * kI8Rows] = v[8 + i];
 #pragma unroll
-                    for (int k = 0; k < kFuK; ++k) p.n[k] *= inv;
-                }
-                p.mmin = Num<double>::big; p.mmax = -Num<double>::big;
+                    for (int k = 1; k < 9; ++k) p.n[k] = regulate_norm(v[k - 1], lc.n_min, lc.n_max);
+                    // part 2: K means, last log-norm
+                    next_tile(cst + 2 * kFuTN, v);
+                    p.n[9] = regulate_norm(v[10], lc.n_min, lc.n_max);
+                    {
+                        double nsum = 0;
 #pragma unroll
-                for (int k = 0; k < kFuK; ++k) { p.m[k] = v[k]; p.mmin = tmin(p.mmin, v[k]); p.mmax = tmax(p.mmax, v[k]); }
-
-                double logd = 0.0;
-                if (DIR == JF_DIR_SAMPLE) {
+                        for (int k = 0; k < kFuK; ++k) nsum += p.n[k];
+                        const double inv = 1.0 / nsum;
+#pragma unroll
+                        for (int k = 0; k < kFuK; ++k) p.n[k] *= inv;
+                    }
+                    p.mmin = Num<double>::big; p.mmax = -Num<double>::big;
+#pragma unroll
+                    for (int k = 0; k < kFuK; ++k) { p.m[k] = v[k]; p.mmin = tmin(p.mmin, v[k]); p.mmax = tmax(p.mmax, v[k]); }
+                    double logd = 0.0;
                     int ev = 0;
                     bool conv = true;
                     if (active && live) xj = fu_solve(p, lc.inv_type, xj, logd, ev, conv);
                     n_evals += ev;
                     n_unconv += conv ? 0 : 1;
-                    xj = meet(xj, logd);
+                    exw[0] = xj;
+                    exw[5 * kI8Rows] = logd;
+                    xj = meet();
                     if (lc.has_offset) xj += priv[0];
-                } else {
-                    double y = xj;
-                    if (active && live) {
-                        const MixVal<double> mv = fu_mix_eval<false>(p, xj);
-                        inv_stage(lc.inv_type, mv, y, logd);
-                    }
-                    xj = y;
-                    logd_prev = logd;
                 }
                 ex_buf ^= 1;
             }

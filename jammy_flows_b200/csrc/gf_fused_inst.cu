@@ -20,13 +20,20 @@ static int launch_fused_one(const FuArgs& a, int smem_max, int sms, cudaStream_t
     return JF_OK;
 }
 
-int64_t fused_prep_bytes(int n_layers) { return fu_prep_bytes<kFuNS>(n_layers); }
+int64_t fused_prep_bytes(int n_layers) {
+    const int64_t a = fu_prep_bytes<kFuNSLogpdf>(n_layers), b = fu_prep_bytes<kFuNSSample>(n_layers);
+    return a > b ? a : b;
+}
 
 int launch_fused_prep(FuArgs& a, const double* W2, const double* b2, int direction, void* ws, bool run, cudaStream_t st) {
     const int n_tiles = 3 * a.n_layers;
+    const int ns = direction == JF_DIR_LOGPDF ? kFuNSLogpdf : kFuNSSample;
     a.wsB = (const unsigned char*)ws;
-    a.consts = reinterpret_cast<const double2*>((const unsigned char*)ws + (size_t)n_tiles * kFuNS * kFuTN * kI8H);
-    if (run) fu_prep_kernel<kFuNS><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
+    a.consts = reinterpret_cast<const double2*>((const unsigned char*)ws + (size_t)n_tiles * ns * kFuTN * kI8H);
+    if (run) {
+        if (direction == JF_DIR_LOGPDF) fu_prep_kernel<kFuNSLogpdf><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
+        else fu_prep_kernel<kFuNSSample><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
+    }
     return JF_OK;
 }
 
@@ -38,10 +45,10 @@ int launch_fused(const FuArgs& a, int direction, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     const bool k8 = a.m.dims[0] <= 8;
     if (direction == JF_DIR_LOGPDF)
-        return k8 ? launch_fused_one<kFuNS, JF_DIR_LOGPDF, 8>(a, smem_max, sms, st)
-                  : launch_fused_one<kFuNS, JF_DIR_LOGPDF, 16>(a, smem_max, sms, st);
-    return k8 ? launch_fused_one<kFuNS, JF_DIR_SAMPLE, 8>(a, smem_max, sms, st)
-              : launch_fused_one<kFuNS, JF_DIR_SAMPLE, 16>(a, smem_max, sms, st);
+        return k8 ? launch_fused_one<kFuNSLogpdf, JF_DIR_LOGPDF, 8>(a, smem_max, sms, st)
+                  : launch_fused_one<kFuNSLogpdf, JF_DIR_LOGPDF, 16>(a, smem_max, sms, st);
+    return k8 ? launch_fused_one<kFuNSSample, JF_DIR_SAMPLE, 8>(a, smem_max, sms, st)
+              : launch_fused_one<kFuNSSample, JF_DIR_SAMPLE, 16>(a, smem_max, sms, st);
 }
 
 }  // namespace jf

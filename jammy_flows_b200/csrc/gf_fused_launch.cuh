@@ -5,10 +5,18 @@
 
 namespace jf {
 
-#ifndef JF_FUSED_NS
-#define JF_FUSED_NS 7
+// int8 slices of the fused kernel's contraction (csrc/mlp_i8.cuh; error of the generated parameters relative to the
+// scale of their W2 row: 7 slices 6e-15, 6 slices 3e-13, tools/ozaki_probe.py).  log_pdf: 6 -- the parameter error enters
+// log p with O(1..30) sensitivity, 1e-11 against the 1e-10 contract, and the tensor pipe is co-critical with the FP64
+// pipe there.  Sampling: 7 -- the root x(z) amplifies a parameter error by 1/pdf (2.6e-10 measured with 6 slices on the
+// golden emb_e2s2e2_cond), and its tensor work hides behind the root finder anyway.
+#ifndef JF_FUSED_NS_LOGPDF
+#define JF_FUSED_NS_LOGPDF 6
 #endif
-constexpr int kFuNS = JF_FUSED_NS;     // int8 slices of the fused kernel's contraction (see csrc/mlp_i8.cuh)
+#ifndef JF_FUSED_NS_SAMPLE
+#define JF_FUSED_NS_SAMPLE 7
+#endif
+constexpr int kFuNSLogpdf = JF_FUSED_NS_LOGPDF, kFuNSSample = JF_FUSED_NS_SAMPLE;
 constexpr int kFuK = 10;               // num_kde the column layout is built for: 3 K = 30 of the 36 slots of a (layer, dimension)
 constexpr int kFuMaxD = 4;             // dimensions = worker column groups
 constexpr int kFuMaxHH = 4;            // Householder reflections per layer

@@ -1,6 +1,11 @@
 """Summarise an `ncu --page source --csv` dump: samples per opcode class and the hottest instructions."""
 import csv, sys, collections, re
 rows = list(csv.reader(open(sys.argv[1])))
+# a dump of several launches repeats the ("Kernel Name", ...) + header lines: keep section `sys.argv[3]` (default 0)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+sec = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+rows = rows[starts[sec]:starts[sec + 1]]
+print(rows[0][1])
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 tot = 0
