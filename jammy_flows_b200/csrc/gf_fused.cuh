@@ -5,25 +5,28 @@
 //   reference hand-off: main/default.py:956 (MLP call) -> :998-1029 (layer loop, `extra_inputs` slices), sampling
 //   :1438 -> :1482-1506; layer math gaussianization_flow.py:389-1114 (same arithmetic as csrc/gf.cuh, register-resident).
 //
-// Structure (one persistent CTA per SM, 128 rows per block, 20 warps):
-//   warps 0-15  workers (112 registers each, setmaxnreg).  Prologue: layer 1 + tanh + int8 digits of the hidden
-//               activations -> A slices in shared memory (identical to mlp2_i8_kernel).  Then worker (row, j) = (TMEM
-//               lane, column group) owns DIMENSION j of its row: per layer it drains ITS 36 parameter columns (3 MMA tiles
-//               x 12 columns) straight from the TMEM accumulators into registers -- the level accumulators are combined
-//               in 64-bit INTEGER arithmetic (the ALU pipe idles, the FP64 pipe is the bound) -- and consumes them:
+// Structure (one persistent CTA per SM, 128 rows per block, 20 warps in 5 warpgroups):
+//   warps 0-15  workers (104 registers each, setmaxnreg).  Prologue: layer 1 + tanh + int8 digits of the hidden
+//               activations, written with tcgen05.st into TENSOR MEMORY: the A operand of the MMAs lives in TMEM (32
+//               columns per int8 slice), which takes the A read off the shared-memory port (an SS-mode M = 128 MMA costs
+//               33 cycles whatever N is; A-in-TMEM N = 48 costs 24) and frees 96 KB of shared memory for the staging
+//               below.  Then worker (row, j) owns DIMENSION j of its row: per layer it takes ITS parameter columns of
+//               each tile from the staging buffer into registers and consumes them:
 //                 log_pdf   STREAMING: a tile carries (mean, log-width, log-norm) TRIPLES, each kernel is regulated and
 //                           added to the mixture sums as it arrives, nothing but the sums stays live (tile 0 opens with the
 //                           Householder components and the offset, so the rotated coordinate is known before the first
 //                           kernel); an online rescaling exponent keeps the sums exact however far out x is;
 //                 sampling  the K regulated kernels stay in registers for the root finder (csrc/gf.cuh's, register twin).
 //               The four workers of a row meet once per layer through a 6-field shared-memory exchange for the rotation.
-//   warp 16     one elected thread issues tcgen05.mma (kind::i8, M = 128, N = 48, K = 32) for tile t+1 as soon as the
-//               workers have drained tile t; the MMAs of a tile overlap the workers' regulation / evaluation of what they
-//               already hold -- the tensor pipe and the FP64 pipe run side by side.
-//   warp 17     one thread streams the pre-sliced W2 tiles (L2 resident) with cp.async.bulk into a small ring.
-//   warps 18-19 idle (they complete the service warpgroup: setmaxnreg is a warpgroup-wide instruction).
+//   warps 16-19 the tensor warpgroup.  One elected thread streams the pre-sliced W2 tiles (L2 resident) with
+//               cp.async.bulk into a two-tile ring and issues the tcgen05.mma (kind::i8, M = 128, K = 32, A from TMEM) of a
+//               tile; then all four warps -- one per TMEM lane quarter -- drain the level accumulators: tcgen05.ld, exact
+//               64-bit INTEGER combine of the levels (ALU pipe), one conversion, scale and bias, and the fp64 parameters
+//               go to the staging buffer in shared memory.  MMA and TMEM reads serialise on tensor memory anyway (measured,
+//               profiles/), so one warpgroup doing both loses nothing, and it runs a tile or two AHEAD of the workers:
+//               the FP64 pipe (the bound of this kernel) never waits for a TMEM read (64 B/clk per SM: 1.2 us per tile).
 // W2's rows are permuted by the prep kernel into CONSUMPTION order (per direction): tile (c, part) holds, for the layer
-// consumed c-th, the 12 columns of `part` for each of the 4 dimensions.
+// consumed c-th, the SPT = TN/4 columns of `part` for each of the 4 dimensions.
 #pragma once
 #include "mlp_i8.cuh"
 #include "gf.cuh"
@@ -31,13 +34,15 @@
 
 namespace jf {
 
-constexpr int kFuTN = 48;           // output columns per MMA tile = 4 column groups (dimensions) x 12
-constexpr int kFuCG = 12;           // columns per (tile, dimension)
-constexpr int kFuLvlStride = 64;    // TMEM columns between level accumulators
 constexpr int kFuWorkers = 512;     // 16 warps
-constexpr int kFuThreads = 640;     // + service warpgroup: MMA warp, producer warp, two idle warps
-constexpr int kFuRegsWorker = 112;  // setmaxnreg moves registers inside the CTA's own allocation (640 x 96): 512 x 16 taken = 128 x 64 released
-constexpr int kFuRegsService = 32;
+constexpr int kFuThreads = 640;     // + the tensor warpgroup
+// registers: the CTA is launched with 640 x 96; setmaxnreg moves registers between the warpgroups inside that allocation
+// (sampling: the workers hold the K kernels of a dimension in registers: 512 x 8 taken = 128 x 32 released; log_pdf streams
+// and leaves the tensor warpgroup its 96 for an 8-column-wide drain)
+template <int DIR> struct FuRegs {
+    static constexpr int kWorker = DIR == JF_DIR_SAMPLE ? 104 : 96;
+    static constexpr int kTensor = DIR == JF_DIR_SAMPLE ? 64 : 96;
+};
 constexpr int kFuExFields = 6;      // exchange: x, 4 Householder components, log-derivative
 constexpr int kFuExBytes = 2 * kFuMaxD * kFuExFields * kI8Rows * 8;   // double buffered
 constexpr int kFuPrivFields = 3;    // per-worker scratch in shared memory: offset, running logdet, sum of squares
@@ -45,67 +50,80 @@ constexpr int kFuPrivBytes = kFuMaxD * kFuPrivFields * kI8Rows * 8;
 // the level accumulators of one output are combined as ONE 64-bit integer: sum_{l < 6} v_l 256^(5-l) < 2^62
 // (|v_l| <= (l+1) 2^21); a 7th level is added in floating point
 template <int NS> struct FuLv { static constexpr int kInt = NS < 6 ? NS : 6; };
+// timing experiments only (tools/fused_variants.py builds variant libraries; results are garbage with any bit set):
+// 1 no MMAs, 2 no layer arithmetic in the workers, 4 no layer-1 / tanh arithmetic, 8 no TMEM reads.  Product build: 0.
+#ifndef JF_FU_DBG
+#define JF_FU_DBG 0
+#endif
 
-template <int NS>
+// geometry of a (slices, tile width) configuration
+template <int NS, int TN>
+struct FuCfg {
+    static constexpr int kSPT = TN / kFuMaxD;                 // parameter slots per (tile, dimension)
+    static constexpr int kTPL = (36 + kSPT - 1) / kSPT;       // tiles per layer: 36 slots per (layer, dimension) for K = 10
+    static constexpr int kAccCol = 0;                         // TMEM: NS level accumulators of TN columns ...
+    static constexpr int kACol = NS * TN;                     // ... then the NS A slices of 32 columns (128 int8 per row)
+    static_assert(kACol + NS * 32 <= 512, "tensor memory: 512 columns");
+    static_assert(TN % 16 == 0 && TN % kFuMaxD == 0, "UMMA N for M = 128; equal share per dimension");
+    static constexpr int kSliceBytesB = TN * kI8H;
+    static constexpr int kLboB = (TN / 8) * 128, kSbo = 128;
+    static constexpr int kRing = NS;                          // W2 slices of one tile (refilled slice by slice as the MMAs retire)
+    static constexpr int kStageBytes = TN * kI8Rows * 8;      // fp64 parameters of one tile, [column][row]
+    static constexpr int offB = 0;
+    static constexpr int offStage = offB + kRing * kSliceBytesB;
+    static constexpr int kConstBytes = 2 * TN * 16;           // (scale, b2) of the tile being drained and of the next one
+    __host__ __device__ static constexpr int off_bar(int n_stages) { return offStage + n_stages * kStageBytes; }
+    __host__ __device__ static constexpr int smem_bytes(int kin, int n_stages) {
+        return off_bar(n_stages) + 512 + kConstBytes + kFuExBytes + kFuPrivBytes + (kin + 1) * kI8H * 8 + kI8Rows * (kin | 1) * 8;
+    }
+};
+
+template <int NS, int TN>
 __host__ __device__ inline int64_t fu_prep_bytes(int n_layers) {
-    const int64_t n_tiles = 3 * (int64_t)n_layers;
-    return n_tiles * NS * kFuTN * kI8H + n_tiles * kFuTN * 16;
+    const int64_t n_tiles = (int64_t)FuCfg<NS, TN>::kTPL * n_layers;
+    return n_tiles * NS * TN * kI8H + n_tiles * TN * 16;
 }
 
-__host__ __device__ inline int fu_smem_bytes(int ns, int kin, int n_slots) {
-    return ns * kI8Rows * kI8H + n_slots * kFuTN * kI8H + 512 + kFuExBytes + kFuPrivBytes + (kin + 1) * kI8H * 8 + kI8Rows * (kin | 1) * 8;
-}
-
-// source row of W2 / b2 (index into the sub-pdf's raw parameter vector) of fused column (tile, jj); -1: zero column.
-// Slots of (layer, dimension j), 12 per part:
-//   sampling  part 0: log_w[0..9], offset_j, log_n[0]      part 1: log_n[1..8], v_0[j] .. v_3[j]      part 2: mean[0..9], log_n[9], pad
-//   log_pdf   part 0: v_0[j] .. v_3[j], offset_j, (mean, log_w, log_n)[0], [1], pad      part 1: triples 2..5      part 2: triples 6..9
-__host__ __device__ inline int fu_source_param(const FuLayerC& c, int d, int direction, int part, int jj) {
-    const int cg = jj / kFuCG, s = jj - cg * kFuCG;
+// source row of W2 / b2 (index into the sub-pdf's raw parameter vector) of slot s of (layer, dimension cg); -1: zero column.
+//   sampling  w[0..9], n[0..9], v_0[j] .. v_3[j], mean[0..9], offset_j, padding   (widths and norms first: their regulators
+//             run while the tensor pipe produces the rest)
+//   log_pdf   v_0[j] .. v_3[j], offset_j, (mean, log_w, log_n)[0], [1], one pad, then the triples 2..9 (12 slots per tile:
+//             no triple straddles a tile)
+__host__ __device__ inline int fu_source_param(const FuLayerC& c, int d, int direction, int cg, int s) {
     if (cg >= d) return -1;
     const int K = kFuK;
     const int off_hh = c.raw_off + (c.has_offset ? d : 0);
     const int off_m = off_hh + c.hh_iter * d, off_w = off_m + K * d, off_n = off_w + K * d;
     if (direction == JF_DIR_LOGPDF) {
-        int t = s;                       // index into the triple stream of this part
-        int k0 = 2 + 4 * (part - 1);
-        if (part == 0) {
-            if (s < 4) return s < c.hh_iter ? off_hh + s * d + cg : -1;
-            if (s == 4) return c.has_offset ? c.raw_off + cg : -1;
-            if (s == 11) return -1;
-            t = s - 5;
-            k0 = 0;
-        }
-        const int k = k0 + t / 3, f = t - 3 * (t / 3);
+        if (s < 4) return s < c.hh_iter ? off_hh + s * d + cg : -1;
+        if (s == 4) return c.has_offset ? c.raw_off + cg : -1;
+        if (s == 11 || s >= 36) return -1;
+        const int t = s < 11 ? s - 5 : s - 6;          // index into the stream of triples
+        const int k = t / 3, f = t - 3 * k;
         return (f == 0 ? off_m : (f == 1 ? off_w : off_n)) + k * d + cg;
     }
-    if (part == 0) {
-        if (s < 10) return off_w + s * d + cg;
-        if (s == 10) return c.has_offset ? c.raw_off + cg : -1;
-        return off_n + cg;
-    }
-    if (part == 1) {
-        if (s < 8) return off_n + (s + 1) * d + cg;
-        const int i = s - 8;
-        return i < c.hh_iter ? off_hh + i * d + cg : -1;
-    }
-    if (s < 10) return off_m + s * d + cg;
-    if (s == 10) return off_n + 9 * d + cg;
+    if (s < 10) return off_w + s * d + cg;
+    if (s < 20) return off_n + (s - 10) * d + cg;
+    if (s < 24) return (s - 20) < c.hh_iter ? off_hh + (s - 20) * d + cg : -1;
+    if (s < 34) return off_m + (s - 24) * d + cg;
+    if (s == 34) return c.has_offset ? c.raw_off + cg : -1;
     return -1;
 }
 
 // W2 [P,128] fp64 -> int8 slices of the fused tiles (UMMA K-major no-swizzle layout) + (scale, b2) per fused column
-template <int NS>
+template <int NS, int TN>
 __global__ void __launch_bounds__(128) fu_prep_kernel(const __grid_constant__ FuArgs a, const double* __restrict__ W2,
                                                       const double* __restrict__ b2, int direction, unsigned char* ws) {
+    using G = FuCfg<NS, TN>;
     const int tile = blockIdx.x, n_tiles = gridDim.x;
-    const int c = tile / 3, part = tile - 3 * c;
+    const int c = tile / G::kTPL, part = tile - G::kTPL * c;
     const int l = direction == JF_DIR_LOGPDF ? a.n_layers - 1 - c : c;
-    double2* cst = reinterpret_cast<double2*>(ws + (size_t)n_tiles * NS * kFuTN * kI8H);
-    __shared__ double s_inv[kFuTN];
-    __shared__ int s_src[kFuTN];
-    for (int jj = threadIdx.x; jj < kFuTN; jj += blockDim.x) {
-        const int src = fu_source_param(a.layers[l], a.d, direction, part, jj);
+    double2* cst = reinterpret_cast<double2*>(ws + (size_t)n_tiles * NS * TN * kI8H);
+    __shared__ double s_inv[TN];
+    __shared__ int s_src[TN];
+    for (int jj = threadIdx.x; jj < TN; jj += blockDim.x) {
+        const int cg = jj / G::kSPT, s = part * G::kSPT + (jj - cg * G::kSPT);
+        const int src = fu_source_param(a.layers[l], a.d, direction, cg, s);
         double mx = 0.0;
         if (src >= 0)
             for (int k = 0; k < kI8H; ++k) mx = fmax(mx, fabs(W2[(size_t)src * kI8H + k]));
@@ -113,18 +131,18 @@ __global__ void __launch_bounds__(128) fu_prep_kernel(const __grid_constant__ Fu
         if (mx > 0.0) { frexp(mx, &e); }
         s_inv[jj] = ldexp(1.0, -e);
         s_src[jj] = src;
-        cst[tile * kFuTN + jj] = src >= 0 ? make_double2(ldexp(1.0, e - 12 - 8 * (FuLv<NS>::kInt - 1)), b2[src]) : make_double2(0.0, 0.0);
+        cst[tile * TN + jj] = src >= 0 ? make_double2(ldexp(1.0, e - 12 - 8 * (FuLv<NS>::kInt - 1)), b2[src]) : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    unsigned char* base = ws + (size_t)tile * NS * kFuTN * kI8H;
-    for (int idx = threadIdx.x; idx < kFuTN * kI8H; idx += blockDim.x) {
+    unsigned char* base = ws + (size_t)tile * NS * TN * kI8H;
+    for (int idx = threadIdx.x; idx < TN * kI8H; idx += blockDim.x) {
         const int jj = idx / kI8H, k = idx - jj * kI8H;
         const int src = s_src[jj];
         const double w = src >= 0 ? W2[(size_t)src * kI8H + k] * s_inv[jj] : 0.0;
         const unsigned long long dg = to_digits<NS>(w);
-        const int off = (k >> 4) * (kFuTN / 8) * 128 + (jj >> 3) * 128 + (jj & 7) * 16 + (k & 15);
+        const int off = (k >> 4) * (TN / 8) * 128 + (jj >> 3) * 128 + (jj & 7) * 16 + (k & 15);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) base[(size_t)(NS - 1 - s) * kFuTN * kI8H + off] = (unsigned char)(dg >> (8 * s));
+        for (int s = 0; s < NS; ++s) base[(size_t)(NS - 1 - s) * TN * kI8H + off] = (unsigned char)(dg >> (8 * s));
     }
 }
 
@@ -132,31 +150,48 @@ JF_DEVINL void tmem_ld4(uint32_t taddr, int* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
 }
-JF_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-// 12 parameter values of this worker from the NS level accumulators: exact integer combine of the levels (ALU pipe),
-// one conversion, one FMA with (scale, b2)
-template <int NS>
-JF_DEVINL void fu_drain(uint32_t tbase, const double2* __restrict__ cst, double* v) {
-    constexpr int LI = FuLv<NS>::kInt;
-#pragma unroll
-    for (int c4 = 0; c4 < 3; ++c4) {
-        int r[NS][4];
-#pragma unroll
-        for (int l = 0; l < NS; ++l) tmem_ld4(tbase + l * kFuLvlStride + c4 * 4, r[l]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            long long acc = r[0][j];
-#pragma unroll
-            for (int l = 1; l < LI; ++l) acc = acc * 256 + (long long)r[l][j];
-            double sacc = __ll2double_rn(acc);
-#pragma unroll
-            for (int l = LI; l < NS; ++l) sacc = fma((double)r[l][j], 1.0 / (double)(1ull << (8 * (l - LI + 1))), sacc);
-            const double2 sb = __ldg(cst + c4 * 4 + j);
-            v[c4 * 4 + j] = fma(sacc, sb.x, sb.y);
-        }
+JF_DEVINL void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// sum_{l < LI} v_l 256^(LI-1-l) as one 64-bit integer: the three lowest levels above the last go in with one
+// mad.wide.s32 each (32 x 32 + 64 -> 64), the rest are additions to the high word
+JF_DEVINL long long mad_wide(int a, int b, long long c) {
+    long long d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+template <int LI, int NSL, int CW>
+JF_DEVINL long long fu_combine(const int (&lv)[NSL][CW], int j) {
+    long long acc = (long long)lv[LI - 1][j];
+    if (LI >= 2) acc = mad_wide(lv[LI - 2][j], 1 << 8, acc);
+    if (LI >= 3) acc = mad_wide(lv[LI - 3][j], 1 << 16, acc);
+    if (LI >= 4) acc = mad_wide(lv[LI - 4][j], 1 << 24, acc);
+    if (LI >= 5) {
+        int hi = (int)(acc >> 32) + lv[LI - 5][j];
+        if (LI >= 6) hi += lv[LI - 6][j] << 8;
+        acc = (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)acc);
     }
+    return acc;
+}
+JF_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+JF_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T, int8 x int8 -> int32, M = 128: the four K = 32 steps of one (slice p, slice q) pair; A
+// advances 8 columns (32 int8 per row) per step, the B descriptor by adding to its low word
+JF_DEVINL void tc_mma_i8_ts_x4(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi_b, uint32_t idesc,
+                               uint32_t acc_first, uint32_t b_step) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 db;\n.reg .b32 bl, al;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "add.u32 al, %1, 8;\nadd.u32 bl, %2, %6;\nmov.b64 db, {bl, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [al], db, %4, p;\n"
+        "add.u32 al, al, 8;\nadd.u32 bl, bl, %6;\nmov.b64 db, {bl, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [al], db, %4, p;\n"
+        "add.u32 al, al, 8;\nadd.u32 bl, bl, %6;\nmov.b64 db, {bl, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [al], db, %4, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi_b), "r"(idesc), "r"(acc_first), "r"(b_step) : "memory");
 }
 
 // ---- log_pdf: streaming mixture sums (same quantities as mix_eval of csrc/gf.cuh, accumulated kernel by kernel) ------
@@ -170,41 +205,68 @@ struct FuSums {
     int n_pos;                                    // kernels with a >= 0
 };
 
-template <bool FIRST>
-JF_DEVINL void fu_stream(FuSums& A, const FuLayerC& lc, double x, double m, double w_raw, double n_raw) {
-    const double iw = regulate_inv_width(w_raw, lc.w_min, lc.inv_w_max);
-    const double n = regulate_norm(n_raw, lc.n_min, lc.n_max);
-    const double a = (x - m) * iw, sa = fabs(a);
+// N kernels at once, branch-free in the common case so that the N (x 2: width and norm regulators) exp / reciprocal
+// chains interleave: with four warps per scheduler the FP64 pipe is latency bound on a single chain (ncu: "wait").
+// t: N triples (mean, raw log-width, raw log-norm).
+template <int N, bool FIRST>
+JF_DEVINL void fu_stream(FuSums& A, const FuLayerC& lc, double x, const double* t) {
+    double iw[N], n[N], a[N], sa[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        iw[i] = regulate_inv_width(t[3 * i + 1], lc.w_min, lc.inv_w_max);
+        n[i] = regulate_norm(t[3 * i + 2], lc.n_min, lc.n_max);
+    }
+    double smin = Num<double>::big, amin = 0.0, nsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        a[i] = (x - t[3 * i]) * iw[i];
+        sa[i] = fabs(a[i]);
+        smin = tmin(smin, sa[i]);
+        amin = tmin(amin, a[i]);
+        nsum += n[i];
+    }
     if (FIRST) {
-        A.D = sa > 512.0 ? sa : 0.0;
+        A.D = smin > 512.0 ? smin : 0.0;
         A.E = 1.0;
         if (A.D > 0.0) A.E = exp_neg(-A.D);
         A.big_p = A.small_p = A.big_n = A.small_n = A.Sp = A.ex = A.qc = 0.0;
-        A.nsum = n;
+        A.nsum = nsum;
         A.n_pos = 0;
     } else {
-        A.nsum += n;
-        if (A.D > 0.0 && sa < A.D) {
-            const double nd = sa > 512.0 ? sa : 0.0;
+        A.nsum += nsum;
+        if (A.D > 0.0 && smin < A.D) {              // a nearer kernel than any before (extreme outliers only)
+            const double nd = smin > 512.0 ? smin : 0.0;
             const double f = exp_neg(nd - A.D);
             A.small_p *= f; A.small_n *= f; A.Sp *= f; A.qc *= f;
             A.D = nd;
             A.E = nd > 0.0 ? exp_neg(-nd) : 1.0;
         }
     }
-    const double u = exp_neg(A.D - sa);
-    const double e = u * A.E;
-    const double rx = rcp_1to2(1.0 + e);
-    const double nr = n * rx, nur = nr * u;
-    const double pt = nur * iw * rx;
-    if (a >= 0.0) { A.big_p += nr; A.small_p += nur; ++A.n_pos; }
-    else          { A.big_n += nr; A.small_n += nur; }
-    A.Sp += pt;
-    if (a < -20.0) {                               // softplus-threshold quirk of the reference, see mix_eval
-        const double nq = n * e * rx;
-        A.ex += nq;
-        A.qc = fma(nq, u, A.qc);
-        A.Sp = fma(nq * u * iw, 1.0 + rx, A.Sp);
+    double u[N], rx[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) u[i] = exp_neg(A.D - sa[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) rx[i] = rcp_1to2(fma(u[i], A.E, 1.0));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double nr = n[i] * rx[i], nur = nr * u[i];
+        const bool pos = a[i] >= 0.0;
+        A.big_p += pos ? nr : 0.0;
+        A.small_p += pos ? nur : 0.0;
+        A.big_n += pos ? 0.0 : nr;
+        A.small_n += pos ? 0.0 : nur;
+        A.n_pos += pos ? 1 : 0;
+        A.Sp = fma(nur * iw[i], rx[i], A.Sp);
+    }
+    if (amin < -20.0) {                             // softplus-threshold quirk of the reference, see mix_eval (rare)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (a[i] < -20.0) {
+                const double nq = n[i] * (u[i] * A.E) * rx[i];
+                A.ex += nq;
+                A.qc = fma(nq, u[i], A.qc);
+                A.Sp = fma(nq * u[i] * iw[i], 1.0 + rx[i], A.Sp);
+            }
     }
 }
 
@@ -459,25 +521,30 @@ JF_DEVINL double fu_solve(const FuMix& p, int type, double z, double& logd_out, 
 template <int REGS> JF_DEVINL void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> JF_DEVINL void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-template <int NS, int DIR, int KR>
-__global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_constant__ FuArgs a, int n_slots) {
-    using Cfg = I8Cfg<NS, kFuTN>;
+template <int NS, int TN, int DIR, int KR>
+__global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_constant__ FuArgs a, int n_stages) {
+    using G = FuCfg<NS, TN>;
+    constexpr int SPT = G::kSPT, TPL = G::kTPL;
     extern __shared__ __align__(1024) unsigned char smem[];
     const MlpArgs<double>& m = a.m;
     const int Kin = m.dims[0];
-    const int L = a.n_layers, n_tiles = 3 * L, d = a.d;
+    const int L = a.n_layers, n_tiles = TPL * L, d = a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_blocks = (m.B + kI8Rows - 1) / kI8Rows;
     const int my_blocks = (int)((n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t offB = Cfg::offB, offBar = offB + n_slots * Cfg::kSliceBytesB;
+    const uint32_t offBar = G::off_bar(n_stages);
     const uint32_t bar0 = sbase + offBar;
-    // barriers (8 B each): full[16] | empty[16] | acc_full | acc_empty | a_full ; tmem pointer at +448
-    auto bar_full = [&](int sl) { return bar0 + 8 * sl; };
-    auto bar_empty = [&](int sl) { return bar0 + 8 * (16 + sl); };
-    const uint32_t bar_acc_full = bar0 + 8 * 32, bar_acc_empty = bar0 + 8 * 33, bar_a_full = bar0 + 8 * 34;
+    // barriers (8 B each): slice_full[8] | slice_empty[8] | mma_done | a_full | stage_full[4] | stage_empty[4] ; tmem pointer at +448
+    auto bar_slice = [&](int sl) { return bar0 + 8 * sl; };
+    auto bar_slice_empty = [&](int sl) { return bar0 + 8 * (8 + sl); };
+    const uint32_t bar_mma_done = bar0 + 8 * 16, bar_a_full = bar0 + 8 * 17;
+    auto bar_stage_full = [&](int s) { return bar0 + 8 * (18 + s); };
+    auto bar_stage_empty = [&](int s) { return bar0 + 8 * (22 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 448);
-    double* sEx = reinterpret_cast<double*>(smem + offBar + 512);          // [2][4][6][128]
+    double* sStage = reinterpret_cast<double*>(smem + G::offStage);        // [n_stages][TN][128]
+    double2* sConst = reinterpret_cast<double2*>(smem + offBar + 512);     // [2][TN]
+    double* sEx = reinterpret_cast<double*>(smem + offBar + 512 + G::kConstBytes);   // [2][4][6][128]
     double* sPriv = sEx + kFuExBytes / 8;                                  // [4][3][128]
     double* sW1 = sPriv + kFuPrivBytes / 8;                                // [Kin][128]
     double* sB1 = sW1 + (size_t)Kin * kI8H;
@@ -485,10 +552,10 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
     const int ldin = Kin | 1;
 
     if (warp == 17 && lane == 0) {
-        for (int sl = 0; sl < n_slots; ++sl) { mbar_init(bar_full(sl), 1); mbar_init(bar_empty(sl), 1); }
-        mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 16);
+        for (int sl = 0; sl < G::kRing; ++sl) { mbar_init(bar_slice(sl), 1); mbar_init(bar_slice_empty(sl), 1); }
+        mbar_init(bar_mma_done, 1);
         mbar_init(bar_a_full, 16);
+        for (int s = 0; s < n_stages; ++s) { mbar_init(bar_stage_full(s), 4); mbar_init(bar_stage_empty(s), 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) {
@@ -505,76 +572,126 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kFuTN >> 3) << 17) | ((uint32_t)(kI8Rows >> 4) << 24);
+    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kI8Rows >> 4) << 24);
 
     if (warp >= 16) {
-        reg_dec<kFuRegsService>();
-        if (warp == 17) {
-            // ---- producer: stream every W2 slice of every block through the ring ----
-            if (lane == 0) {
-                const int loads_per_block = n_tiles * NS;
-                const int64_t total = (int64_t)my_blocks * loads_per_block;
-                int slot = 0, idx = 0;
-                uint32_t wrap_par = 1;                      // parity to wait for on empty[slot]: first round passes
-                for (int64_t i = 0; i < total; ++i) {
-                    mbar_wait(bar_empty(slot), wrap_par);
-                    mbar_expect_tx(bar_full(slot), Cfg::kSliceBytesB);
-                    bulk_g2s(sbase + offB + slot * Cfg::kSliceBytesB, a.wsB + (size_t)idx * Cfg::kSliceBytesB, Cfg::kSliceBytesB,
-                             bar_full(slot));
-                    if (++slot == n_slots) { slot = 0; wrap_par ^= 1u; }
-                    if (++idx == loads_per_block) idx = 0;
-                }
-            }
-        } else if (warp == 16) {
-            // ---- MMA issuer ----
+        // ---- tensor warpgroup: W2 ring, MMA issue, TMEM drain -> staging ----
+        if (FuRegs<DIR>::kTensor < 96) reg_dec<FuRegs<DIR>::kTensor>();
+        const int dq = warp - 16;
+        const int r = dq * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(dq * 32) << 16);
+        const int64_t total_tiles = (int64_t)my_blocks * n_tiles;
+        auto issue_load = [&](int t, int q) {                 // slice q of tile t into ring slot q
+            mbar_expect_tx(bar_slice(q), G::kSliceBytesB);
+            bulk_g2s(sbase + G::offB + q * G::kSliceBytesB, a.wsB + ((size_t)t * NS + q) * G::kSliceBytesB, G::kSliceBytesB,
+                     bar_slice(q));
+        };
+        if (warp == 16 && total_tiles > 0) {
             if (elect_one()) {
-                const uint32_t desc_hi = (Cfg::kSbo >> 4) | (1u << 14);
-                const uint32_t a_lo0 = (((sbase + Cfg::offA) & 0x3FFFF) >> 4) | ((uint32_t)(Cfg::kLboA >> 4) << 16);
-                const uint32_t b_lo0 = (((sbase + offB) & 0x3FFFF) >> 4) | ((uint32_t)(Cfg::kLboB >> 4) << 16);
-                int slot = 0;
-                uint32_t full_par = 0, tile_par = 0;
-                for (int jb = 0; jb < my_blocks; ++jb) {
-                    mbar_wait(bar_a_full, (uint32_t)(jb & 1));        // the workers have written this block's A slices
+#pragma unroll
+                for (int q = 0; q < NS; ++q) issue_load(0, q);
+            }
+        }
+        const int tw = tid - 16 * 32;                                        // 0..127 inside the warpgroup
+        if (tw < TN && total_tiles > 0) sConst[tw] = a.consts[tw];           // constants of tile 0
+        bar_sync_named(7, 128);
+        int t = 0, jb = 0, stage = 0;
+        uint32_t mma_par = 0, stage_wrap = 0;
+#pragma unroll 1
+        for (int64_t gt = 0; gt < total_tiles; ++gt) {
+            // one elected thread of warp 16 (a warp-uniform branch + elect.sync: UTCIMMA takes uniform-register operands, and
+            // under a divergent `lane == 0` the compiler wraps every single MMA in an election loop -- 51 cycles per MMA)
+            if (warp == 16 && elect_one()) {
+                if (t == 0) mbar_wait(bar_a_full, (uint32_t)(jb & 1));        // the workers have written this block's A slices
+                tc_fence_after();
+                const uint32_t desc_hi = (G::kSbo >> 4) | (1u << 14);
+                const uint32_t b_lo0 = (((sbase + G::offB) & 0x3FFFF) >> 4) | ((uint32_t)(G::kLboB >> 4) << 16);
+                const uint32_t ring_par = (uint32_t)(gt & 1);
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    mbar_wait(bar_slice(q), ring_par);
                     tc_fence_after();
-                    for (int t = 0; t < n_tiles; ++t, tile_par ^= 1u) {
-                        mbar_wait(bar_acc_empty, tile_par ^ 1u);      // the workers have drained the previous tile
-                        tc_fence_after();
+                    const uint32_t b_lo = b_lo0 + q * (G::kSliceBytesB >> 4);
 #pragma unroll
-                        for (int q = 0; q < NS; ++q) {
-                            mbar_wait(bar_full(slot), full_par);
-                            tc_fence_after();
-                            const uint32_t b_lo = b_lo0 + slot * (Cfg::kSliceBytesB >> 4);
+                    for (int p = 0; p + q < NS && !(JF_FU_DBG & 1); ++p)
+                        tc_mma_i8_ts_x4(tmem + G::kAccCol + (p + q) * TN, tmem + G::kACol + p * 32, b_lo, desc_hi, idesc,
+                                        q > 0 ? 1u : 0u, (2 * G::kLboB) >> 4);
+                    tc_commit(bar_slice_empty(q));               // slot q is free once these MMAs have read it
+                }
+                tc_commit(bar_mma_done);
+                // refill the ring with the next tile slice by slice as the MMAs retire (the last slot frees when the tile
+                // is complete, which is when the drain below can start anyway)
+                if (gt + 1 < total_tiles) {
+                    const int tn = t + 1 == n_tiles ? 0 : t + 1;
 #pragma unroll
-                            for (int p = 0; p + q < NS; ++p)
-                                tc_mma_i8_x4(tmem + (p + q) * kFuLvlStride, a_lo0 + p * (Cfg::kSliceBytesA >> 4), b_lo, desc_hi,
-                                             desc_hi, idesc, q > 0 ? 1u : 0u, (2 * Cfg::kLboA) >> 4, (2 * Cfg::kLboB) >> 4);
-                            tc_commit(bar_empty(slot));
-                            if (++slot == n_slots) { slot = 0; full_par ^= 1u; }
-                        }
-                        tc_commit(bar_acc_full);
+                    for (int q = 0; q < NS; ++q) {
+                        mbar_wait(bar_slice_empty(q), ring_par);
+                        issue_load(tn, q);
                     }
                 }
             }
+            __syncwarp();                                                    // (the issuer's 31 siblings wait here, not in a spin loop)
+            mbar_wait(bar_mma_done, mma_par); mma_par ^= 1u;
+            tc_fence_after();
+            mbar_wait(bar_stage_empty(stage), stage_wrap ^ 1u);              // the workers have taken the previous content
+            {
+                constexpr int LI = FuLv<NS>::kInt;
+                constexpr int CW = FuRegs<DIR>::kTensor >= 96 ? 8 : 4;       // columns per step
+                double* st = sStage + (size_t)stage * (TN * kI8Rows) + r;
+                const double2* cst = sConst + (gt & 1) * TN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += CW) {
+                    int lv[NS][CW];
+#pragma unroll
+                    for (int l = 0; l < NS; ++l) {
+                        if (JF_FU_DBG & 8) {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j) lv[l][j] = l + c0 + j;
+                        } else if (CW == 8) tmem_ld8(tlane + G::kAccCol + l * TN + c0, lv[l]);
+                        else tmem_ld4(tlane + G::kAccCol + l * TN + c0, lv[l]);
+                    }
+                    if (!(JF_FU_DBG & 8)) tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        double sacc = __ll2double_rn(fu_combine<LI>(lv, j));
+#pragma unroll
+                        for (int l = LI; l < NS; ++l) sacc = fma((double)lv[l][j], 1.0 / (double)(1ull << (8 * (l - LI + 1))), sacc);
+                        const double2 sb = cst[c0 + j];
+                        st[(size_t)(c0 + j) * kI8Rows] = fma(sacc, sb.x, sb.y);
+                    }
+                }
+                // constants of the next tile (read after the barrier below)
+                if (tw < TN && gt + 1 < total_tiles)
+                    sConst[((gt + 1) & 1) * TN + tw] = a.consts[(size_t)(t + 1 == n_tiles ? 0 : t + 1) * TN + tw];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_stage_full(stage));
+            bar_sync_named(7, 128);                                          // TMEM is free: the next tile's MMAs may start
+            if (++stage == n_stages) { stage = 0; stage_wrap ^= 1u; }
+            if (++t == n_tiles) { t = 0; ++jb; }
         }
     } else {
         // ---- workers ----
-        reg_inc<kFuRegsWorker>();
+        if (FuRegs<DIR>::kWorker > 96) reg_inc<FuRegs<DIR>::kWorker>();
         const int lq = warp & 3, cg = warp >> 2;
         const int r = lq * 32 + lane;
         const bool active = cg < d;
-        const uint32_t tbase = tmem + ((uint32_t)(lq * 32) << 16) + cg * kFuCG;
-        uint32_t tile_par = 0;
+        const uint32_t tlane = tmem + ((uint32_t)(lq * 32) << 16);
+        int wstage = 0;
+        uint32_t wwrap = 0;
         int ex_buf = 0;
         int n_evals = 0, n_unconv = 0, n_bad = 0;
         double* exr = sEx + r;                          // element (buf, j, f) at exr[((buf*4 + j)*6 + f)*128]
-        // wait for the next tile, drain this worker's 12 columns, hand the accumulators back
-        auto next_tile = [&](const double2* cst, double* v) {
-            mbar_wait(bar_acc_full, tile_par); tile_par ^= 1u;
-            tc_fence_after();
-            fu_drain<NS>(tbase, cst, v);
-            tc_fence_before();
+        // this worker's SPT values of the next tile: staging -> registers, then the stage goes back to the tensor warpgroup
+        auto next_tile = [&](double* v) {
+            mbar_wait(bar_stage_full(wstage), wwrap);
+            const double* st = sStage + (size_t)wstage * (TN * kI8Rows) + (size_t)(cg * SPT) * kI8Rows + r;
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) v[i] = st[(size_t)i * kI8Rows];
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty);
+            if (lane == 0) mbar_arrive(bar_stage_empty(wstage));
+            if (++wstage == n_stages) { wstage = 0; wwrap ^= 1u; }
         };
 #pragma unroll 1
         for (int jb = 0; jb < my_blocks; ++jb) {
@@ -595,13 +712,13 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                 sIn[rr * ldin + (e - rr * Kin)] = v;
             }
             bar_sync_named(1, kFuWorkers);
-            // ---- prologue: layer 1 + tanh + digits -> A slices (thread = (row, quarter of the hidden units)) ----
+            // ---- prologue: layer 1 + tanh + digits -> A slices in tensor memory (thread = (row, quarter of the hidden
+            //      units); a 32-bit TMEM column holds 4 consecutive int8 of the row, slice p occupies columns 32 p .. 32 p + 31) ----
             {
                 const int quarter = cg;
                 double in[KR];
 #pragma unroll
                 for (int i = 0; i < KR; ++i) in[i] = (i < Kin) ? sIn[r * ldin + i] : 0.0;
-                const uint32_t a_row = sbase + Cfg::offA + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll 1
                 for (int ch = 0; ch < 2; ++ch) {
                     const int chunk = quarter * 2 + ch;
@@ -616,7 +733,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
 #pragma unroll
                             for (int i = 0; i < KR; ++i)
                                 if (i < Kin) z = fma(in[i], sW1[i * kI8H + u], z);
-                            dg[uu] = to_digits<NS>(tanh_abs(z));
+                            dg[uu] = (JF_FU_DBG & 4) ? (unsigned long long)(u + r) : to_digits<NS>(tanh_abs(z));
                         }
                         {
                             const uint32_t a0 = (uint32_t)dg[0], a1 = (uint32_t)dg[1], a2 = (uint32_t)dg[2], a3 = (uint32_t)dg[3];
@@ -635,16 +752,15 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                         }
                     }
 #pragma unroll
-                    for (int sd = 0; sd < NS; ++sd) {
-                        const uint32_t addr = a_row + (NS - 1 - sd) * Cfg::kSliceBytesA + chunk * Cfg::kLboA;
-                        uint32_t w0, w1, w2, w3;
-                        if (sd < 4) { w0 = lo[0][sd]; w1 = lo[1][sd]; w2 = lo[2][sd]; w3 = lo[3][sd]; }
-                        else { w0 = hi[0][sd & 3]; w1 = hi[1][sd & 3]; w2 = hi[2][sd & 3]; w3 = hi[3][sd & 3]; }
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                    for (int sd = 0; sd < NS; ++sd) {                       // digit sd -> slice p = NS-1-sd
+                        const uint32_t taddr = tlane + G::kACol + (NS - 1 - sd) * 32 + chunk * 4;
+                        if (sd < 4) tmem_st4(taddr, lo[0][sd], lo[1][sd], lo[2][sd], lo[3][sd]);
+                        else tmem_st4(taddr, hi[0][sd & 3], hi[1][sd & 3], hi[2][sd & 3], hi[3][sd & 3]);
                     }
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a_full);
 
@@ -663,7 +779,6 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
             for (int c = 0; c < L; ++c) {
                 const int l = DIR == JF_DIR_LOGPDF ? L - 1 - c : c;
                 const FuLayerC& lc = a.layers[l];
-                const double2* cst = a.consts + (size_t)(3 * c) * kFuTN + cg * kFuCG;
                 double* exw = exr + (size_t)((ex_buf * 4 + cg) * kFuExFields) * kI8Rows;
                 const double* exb = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows;
                 // the four workers of a row meet here: sum of the log-derivatives, rotation of the row vector
@@ -699,10 +814,11 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     }
                     return mine;
                 };
-                double v[12];
+                double v[SPT];
                 if (DIR == JF_DIR_LOGPDF) {
+                    static_assert(DIR != JF_DIR_LOGPDF || SPT == 12, "log_pdf layout: 12 slots per (tile, dimension)");
                     // tile 0: Householder components, offset, kernels 0-1
-                    next_tile(cst, v);
+                    next_tile(v);
                     if (lc.has_offset) xj -= v[4];
                     exw[0] = xj;
 #pragma unroll
@@ -710,14 +826,14 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     exw[5 * kI8Rows] = logd_prev;
                     xj = meet();
                     FuSums S;
-                    fu_stream<true>(S, lc, xj, v[5], v[6], v[7]);
-                    fu_stream<false>(S, lc, xj, v[8], v[9], v[10]);
+                    if (JF_FU_DBG & 2) { S.D = 0; S.E = 1; S.big_p = S.small_p = S.big_n = S.small_n = S.Sp = v[5]; S.ex = S.qc = 0; S.nsum = 1; S.n_pos = 1; }
+                    else fu_stream<2, true>(S, lc, xj, v + 5);
                     // tiles 1, 2: four kernels each
 #pragma unroll 1
                     for (int part = 1; part < 3; ++part) {
-                        next_tile(cst + part * kFuTN, v);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) fu_stream<false>(S, lc, xj, v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+                        next_tile(v);
+                        if (JF_FU_DBG & 2) S.Sp += v[0] + v[3] + v[7] + v[11];
+                        else fu_stream<4, false>(S, lc, xj, v);
                     }
                     double y = xj, logd = 0.0;
                     if (active && live) {
@@ -727,22 +843,26 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     xj = y;
                     logd_prev = logd;
                 } else {
+                    // slots of the sampling layout: w[0..9] | n[0..9] | v_0..3 | mean[0..9] | offset | padding
                     FuMix p;
-                    // part 0: K log-widths, offset, first log-norm
-                    next_tile(cst, v);
-                    priv[0] = v[10];
+                    if (JF_FU_DBG & 2) {
 #pragma unroll
-                    for (int k = 0; k < kFuK; ++k) p.iw[k] = regulate_inv_width(v[k], lc.w_min, lc.inv_w_max);
-                    p.n[0] = regulate_norm(v[11], lc.n_min, lc.n_max);
-                    // part 1: 8 log-norms, this dimension's component of the Householder vectors
-                    next_tile(cst + kFuTN, v);
+                        for (int k = 0; k < kFuK; ++k) { p.m[k] = 0.1 * k; p.iw[k] = 1.0; p.n[k] = 0.1; }
+                    }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) exw[(1 + i) * kI8Rows] = v[8 + i];
+                    for (int part = 0; part < TPL; ++part) {
+                        next_tile(v);
 #pragma unroll
-                    for (int k = 1; k < 9; ++k) p.n[k] = regulate_norm(v[k - 1], lc.n_min, lc.n_max);
-                    // part 2: K means, last log-norm
-                    next_tile(cst + 2 * kFuTN, v);
-                    p.n[9] = regulate_norm(v[10], lc.n_min, lc.n_max);
+                        for (int i = 0; i < SPT; ++i) {
+                            const int s = part * SPT + i;
+                            if (JF_FU_DBG & 2) { p.m[0] += v[i]; continue; }
+                            if (s < 10) p.iw[s < 10 ? s : 0] = regulate_inv_width(v[i], lc.w_min, lc.inv_w_max);
+                            else if (s < 20) p.n[s < 20 ? s - 10 : 0] = regulate_norm(v[i], lc.n_min, lc.n_max);
+                            else if (s < 24) exw[(1 + (s - 20)) * kI8Rows] = v[i];
+                            else if (s < 34) p.m[s < 34 ? s - 24 : 0] = v[i];
+                            else if (s == 34) priv[0] = v[i];
+                        }
+                    }
                     {
                         double nsum = 0;
 #pragma unroll
@@ -753,11 +873,12 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     }
                     p.mmin = Num<double>::big; p.mmax = -Num<double>::big;
 #pragma unroll
-                    for (int k = 0; k < kFuK; ++k) { p.m[k] = v[k]; p.mmin = tmin(p.mmin, v[k]); p.mmax = tmax(p.mmax, v[k]); }
+                    for (int k = 0; k < kFuK; ++k) { p.mmin = tmin(p.mmin, p.m[k]); p.mmax = tmax(p.mmax, p.m[k]); }
                     double logd = 0.0;
                     int ev = 0;
                     bool conv = true;
-                    if (active && live) xj = fu_solve(p, lc.inv_type, xj, logd, ev, conv);
+                    if (JF_FU_DBG & 2) xj += p.m[0];
+                    else if (active && live) xj = fu_solve(p, lc.inv_type, xj, logd, ev, conv);
                     n_evals += ev;
                     n_unconv += conv ? 0 : 1;
                     exw[0] = xj;

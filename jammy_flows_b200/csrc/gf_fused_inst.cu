@@ -5,34 +5,36 @@
 
 namespace jf {
 
-template <int NS, int DIR, int KR>
+template <int NS, int TN, int DIR, int KR>
 static int launch_fused_one(const FuArgs& a, int smem_max, int sms, cudaStream_t st) {
+    using G = FuCfg<NS, TN>;
     const int Kin = a.m.dims[0];
-    int n_slots = 8;
-    while (n_slots > 3 && fu_smem_bytes(NS, Kin, n_slots) > smem_max) --n_slots;
-    const int smem = fu_smem_bytes(NS, Kin, n_slots);
+    int n_stages = 3;
+    while (n_stages > 1 && G::smem_bytes(Kin, n_stages) > smem_max) --n_stages;
+    const int smem = G::smem_bytes(Kin, n_stages);
     if (smem > smem_max) return JF_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(gf_fused_kernel<NS, DIR, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gf_fused_kernel<NS, TN, DIR, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t blocks = (a.m.B + kI8Rows - 1) / kI8Rows;
     const unsigned grid = (unsigned)(blocks < sms ? blocks : sms);
-    gf_fused_kernel<NS, DIR, KR><<<grid, kFuThreads, smem, st>>>(a, n_slots);
+    gf_fused_kernel<NS, TN, DIR, KR><<<grid, kFuThreads, smem, st>>>(a, n_stages);
     return JF_OK;
 }
 
 int64_t fused_prep_bytes(int n_layers) {
-    const int64_t a = fu_prep_bytes<kFuNSLogpdf>(n_layers), b = fu_prep_bytes<kFuNSSample>(n_layers);
+    const int64_t a = fu_prep_bytes<kFuNSLogpdf, kFuTNLogpdf>(n_layers), b = fu_prep_bytes<kFuNSSample, kFuTNSample>(n_layers);
     return a > b ? a : b;
 }
 
 int launch_fused_prep(FuArgs& a, const double* W2, const double* b2, int direction, void* ws, bool run, cudaStream_t st) {
-    const int n_tiles = 3 * a.n_layers;
-    const int ns = direction == JF_DIR_LOGPDF ? kFuNSLogpdf : kFuNSSample;
+    const bool lp = direction == JF_DIR_LOGPDF;
+    const int n_tiles = (lp ? FuCfg<kFuNSLogpdf, kFuTNLogpdf>::kTPL : FuCfg<kFuNSSample, kFuTNSample>::kTPL) * a.n_layers;
+    const int ns = lp ? kFuNSLogpdf : kFuNSSample, tn = lp ? kFuTNLogpdf : kFuTNSample;
     a.wsB = (const unsigned char*)ws;
-    a.consts = reinterpret_cast<const double2*>((const unsigned char*)ws + (size_t)n_tiles * ns * kFuTN * kI8H);
+    a.consts = reinterpret_cast<const double2*>((const unsigned char*)ws + (size_t)n_tiles * ns * tn * kI8H);
     if (run) {
-        if (direction == JF_DIR_LOGPDF) fu_prep_kernel<kFuNSLogpdf><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
-        else fu_prep_kernel<kFuNSSample><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
+        if (lp) fu_prep_kernel<kFuNSLogpdf, kFuTNLogpdf><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
+        else fu_prep_kernel<kFuNSSample, kFuTNSample><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
     }
     return JF_OK;
 }
@@ -45,10 +47,10 @@ int launch_fused(const FuArgs& a, int direction, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     const bool k8 = a.m.dims[0] <= 8;
     if (direction == JF_DIR_LOGPDF)
-        return k8 ? launch_fused_one<kFuNSLogpdf, JF_DIR_LOGPDF, 8>(a, smem_max, sms, st)
-                  : launch_fused_one<kFuNSLogpdf, JF_DIR_LOGPDF, 16>(a, smem_max, sms, st);
-    return k8 ? launch_fused_one<kFuNSSample, JF_DIR_SAMPLE, 8>(a, smem_max, sms, st)
-              : launch_fused_one<kFuNSSample, JF_DIR_SAMPLE, 16>(a, smem_max, sms, st);
+        return k8 ? launch_fused_one<kFuNSLogpdf, kFuTNLogpdf, JF_DIR_LOGPDF, 8>(a, smem_max, sms, st)
+                  : launch_fused_one<kFuNSLogpdf, kFuTNLogpdf, JF_DIR_LOGPDF, 16>(a, smem_max, sms, st);
+    return k8 ? launch_fused_one<kFuNSSample, kFuTNSample, JF_DIR_SAMPLE, 8>(a, smem_max, sms, st)
+              : launch_fused_one<kFuNSSample, kFuTNSample, JF_DIR_SAMPLE, 16>(a, smem_max, sms, st);
 }
 
 }  // namespace jf

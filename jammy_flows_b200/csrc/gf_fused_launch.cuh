@@ -17,6 +17,14 @@ namespace jf {
 #define JF_FUSED_NS_SAMPLE 7
 #endif
 constexpr int kFuNSLogpdf = JF_FUSED_NS_LOGPDF, kFuNSSample = JF_FUSED_NS_SAMPLE;
+// MMA tile width (N): tensor memory holds NS accumulators of TN columns plus the NS A slices of 32 columns (<= 512)
+#ifndef JF_FUSED_TN_LOGPDF
+#define JF_FUSED_TN_LOGPDF 48
+#endif
+#ifndef JF_FUSED_TN_SAMPLE
+#define JF_FUSED_TN_SAMPLE 32
+#endif
+constexpr int kFuTNLogpdf = JF_FUSED_TN_LOGPDF, kFuTNSample = JF_FUSED_TN_SAMPLE;
 constexpr int kFuK = 10;               // num_kde the column layout is built for: 3 K = 30 of the 36 slots of a (layer, dimension)
 constexpr int kFuMaxD = 4;             // dimensions = worker column groups
 constexpr int kFuMaxHH = 4;            // Householder reflections per layer
@@ -35,8 +43,8 @@ struct FuArgs {
     const double* logdet_in;  double* logdet_out;
     const double* logbase_in; double* logbase_out;
     int64_t* status;
-    const unsigned char* wsB;       // [3 L tiles][NS slices][48 x 128 B] in consumption order
-    const double2* consts;          // [3 L * 48] (scale, b2) per fused column
+    const unsigned char* wsB;       // [tiles][NS slices][TN x 128 B] in consumption order
+    const double2* consts;          // [tiles * TN] (scale, b2) per fused column
 };
 
 int64_t fused_prep_bytes(int n_layers);

@@ -1,7 +1,7 @@
 """Fused generator + "g"-chain kernel (jf_subpdf_apply_generated) of the README flow's last sub-pdf, timed alone on N rows
 (CUDA events on the launching stream) -- optimisation loop helper and ncu target.
 
-    python tools/fused_bench.py [rows] [reps]
+    python tools/fused_bench.py [rows] [reps] [logpdf|sample|both]
 """
 import ctypes as C
 import os
@@ -13,6 +13,7 @@ from jammy_flows_b200 import _cabi, engine
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+which = sys.argv[3] if len(sys.argv) > 3 else "both"
 lib = _cabi.load()
 pdf = bench.make_model().cuda()
 dev = torch.device("cuda")
@@ -48,6 +49,8 @@ def run(direction, src, prepared):
 
 
 for direction, src, name in ((0, x, "logpdf"), (1, z, "sample")):
+    if which not in ("both", name):
+        continue
     assert run(direction, src, 0) == 0
     torch.cuda.synchronize()
     ts = []
