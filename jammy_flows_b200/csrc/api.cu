@@ -641,6 +641,19 @@ static bool fused_eligible(const JfSubPdfDesc* sp, const JfMlpDesc* md, int dtyp
     return off_p == sp->n_params;
 }
 
+// eligible AND the kernel of this direction fits into the device's shared memory (sampling keeps the kernels of every
+// (row, dimension) in shared-memory slots, which limits the generator's input width)
+static bool fused_usable(const JfSubPdfDesc* sp, const JfMlpDesc* md, int dtype, int direction) {
+    if (!fused_eligible(sp, md, dtype)) return false;
+    static const int smem_max = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+        return v;
+    }();
+    return fused_fits(direction, md->dims[0], smem_max);
+}
+
 extern "C" int64_t jf_subpdf_generated_workspace_bytes(const JfSubPdfDesc* desc, const JfMlpDesc* mlp, int dtype) {
     if (!fused_eligible(desc, mlp, dtype)) return -1;
     return fused_prep_bytes(desc->n_layers);
@@ -656,7 +669,7 @@ extern "C" int jf_subpdf_apply_generated(const JfSubPdfDesc* desc, const JfMlpDe
         weights == nullptr || biases == nullptr)
         return JF_ERR_BAD_ARG;
     if (direction != JF_DIR_LOGPDF && direction != JF_DIR_SAMPLE) return JF_ERR_BAD_ARG;
-    if (!fused_eligible(desc, mlp, dtype)) return JF_ERR_UNSUPPORTED;
+    if (!fused_usable(desc, mlp, dtype, direction)) return JF_ERR_UNSUPPORTED;
     if (mlp->n_segments < 1 || mlp->n_segments > JF_MAX_MLP_SEGMENTS) return JF_ERR_BAD_DESC;
     if (workspace == nullptr || workspace_bytes < fused_prep_bytes(desc->n_layers)) return JF_ERR_WORKSPACE;
     if (B < 0) return JF_ERR_BAD_ARG;
@@ -811,7 +824,7 @@ static int pdf_run(const JfPdfDesc* d, const JfPdfParams* P, int direction, cons
                     ++ns;
                 }
                 md.n_segments = ns;
-                if (w.mlp_bytes[k] > 0 && fused_eligible(sp, &md, d->dtype)) {
+                if (w.mlp_bytes[k] > 0 && fused_usable(sp, &md, d->dtype, direction)) {
                     // generator + layer chain in one kernel: the parameter block never touches HBM
                     const int in_col_f = logpdf ? d->target_col[k] : d->base_col[k];
                     const int out_col_f = logpdf ? d->base_col[k] : d->target_col[k];

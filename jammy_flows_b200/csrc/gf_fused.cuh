@@ -6,7 +6,7 @@
 //   :1438 -> :1482-1506; layer math gaussianization_flow.py:389-1114 (same arithmetic as csrc/gf.cuh, register-resident).
 //
 // Structure (one persistent CTA per SM, 128 rows per block, 20 warps in 5 warpgroups):
-//   warps 0-15  workers (104 registers each, setmaxnreg).  Prologue: layer 1 + tanh + int8 digits of the hidden
+//   warps 0-15  workers.  Prologue: layer 1 + tanh + int8 digits of the hidden
 //               activations, written with tcgen05.st into TENSOR MEMORY: the A operand of the MMAs lives in TMEM (32
 //               columns per int8 slice), which takes the A read off the shared-memory port (an SS-mode M = 128 MMA costs
 //               33 cycles whatever N is; A-in-TMEM N = 48 costs 24) and frees 96 KB of shared memory for the staging
@@ -16,7 +16,8 @@
 //                           added to the mixture sums as it arrives, nothing but the sums stays live (tile 0 opens with the
 //                           Householder components and the offset, so the rotated coordinate is known before the first
 //                           kernel); an online rescaling exponent keeps the sums exact however far out x is;
-//                 sampling  the K regulated kernels stay in registers for the root finder (csrc/gf.cuh's, register twin).
+//                 sampling  the K regulated kernels of the dimension go to the worker's shared-memory slots (the 96 KB that
+//                           the A operand left free), where the root finder of csrc/gf.cuh reads them.
 //               The four workers of a row meet once per layer through a 6-field shared-memory exchange for the rotation.
 //   warps 16-19 the tensor warpgroup.  One elected thread streams the pre-sliced W2 tiles (L2 resident) with
 //               cp.async.bulk into a two-tile ring and issues the tcgen05.mma (kind::i8, M = 128, K = 32, A from TMEM) of a
@@ -28,6 +29,7 @@
 // W2's rows are permuted by the prep kernel into CONSUMPTION order (per direction): tile (c, part) holds, for the layer
 // consumed c-th, the SPT = TN/4 columns of `part` for each of the 4 dimensions.
 #pragma once
+#include <cstdio>
 #include "mlp_i8.cuh"
 #include "gf.cuh"
 #include "gf_fused_launch.cuh"
@@ -36,17 +38,8 @@ namespace jf {
 
 constexpr int kFuWorkers = 512;     // 16 warps
 constexpr int kFuThreads = 640;     // + the tensor warpgroup
-// registers: the CTA is launched with 640 x 96; setmaxnreg moves registers between the warpgroups inside that allocation
-// (sampling: the workers hold the K kernels of a dimension in registers: 512 x 8 taken = 128 x 32 released; log_pdf streams
-// and leaves the tensor warpgroup its 96 for an 8-column-wide drain)
-template <int DIR> struct FuRegs {
-    static constexpr int kWorker = DIR == JF_DIR_SAMPLE ? 104 : 96;
-    static constexpr int kTensor = DIR == JF_DIR_SAMPLE ? 64 : 96;
-};
 constexpr int kFuExFields = 6;      // exchange: x, 4 Householder components, log-derivative
-constexpr int kFuExBytes = 2 * kFuMaxD * kFuExFields * kI8Rows * 8;   // double buffered
-constexpr int kFuPrivFields = 3;    // per-worker scratch in shared memory: offset, running logdet, sum of squares
-constexpr int kFuPrivBytes = kFuMaxD * kFuPrivFields * kI8Rows * 8;
+constexpr int kFuExBufBytes = kFuMaxD * kFuExFields * kI8Rows * 8;
 // the level accumulators of one output are combined as ONE 64-bit integer: sum_{l < 6} v_l 256^(5-l) < 2^62
 // (|v_l| <= (l+1) 2^21); a 7th level is added in floating point
 template <int NS> struct FuLv { static constexpr int kInt = NS < 6 ? NS : 6; };
@@ -55,9 +48,18 @@ template <int NS> struct FuLv { static constexpr int kInt = NS < 6 ? NS : 6; };
 #ifndef JF_FU_DBG
 #define JF_FU_DBG 0
 #endif
+// JF_FU_PROF=1 (variant builds only): lane 0 of every tensor warp of CTA 0 accumulates clock64() per phase and prints them
+#ifndef JF_FU_PROF
+#define JF_FU_PROF 0
+#endif
+#if JF_FU_PROF
+#define FU_T(i) do { const long long now_ = clock64(); prof_[i] += now_ - last_; last_ = now_; } while (0)
+#else
+#define FU_T(i) do { } while (0)
+#endif
 
-// geometry of a (slices, tile width) configuration
-template <int NS, int TN>
+// geometry of a (slices, tile width, direction) configuration
+template <int NS, int TN, int DIR = JF_DIR_LOGPDF>
 struct FuCfg {
     static constexpr int kSPT = TN / kFuMaxD;                 // parameter slots per (tile, dimension)
     static constexpr int kTPL = (36 + kSPT - 1) / kSPT;       // tiles per layer: 36 slots per (layer, dimension) for K = 10
@@ -69,12 +71,27 @@ struct FuCfg {
     static constexpr int kLboB = (TN / 8) * 128, kSbo = 128;
     static constexpr int kRing = NS;                          // W2 slices of one tile (refilled slice by slice as the MMAs retire)
     static constexpr int kStageBytes = TN * kI8Rows * 8;      // fp64 parameters of one tile, [column][row]
+    static constexpr int kConstBytes = 3 * TN * 16;           // (scale, b2) of the tile being drained, the next one, and one in between
+                                                              // (a warp may still store the last columns of the previous tile)
+    // sampling keeps the regulated kernels of every (row, dimension) in shared-memory slots for the root finder
+    // ([field m / 1/w / n][k][worker]: 120 KB); to make room its exchange is single buffered (two barriers per meeting)
+    // and W1 / the gathered inputs -- prologue only -- live inside staging buffer 0
+    static constexpr bool kSample = DIR == JF_DIR_SAMPLE;
+    static constexpr int kExBufs = kSample ? 1 : 2;
+    static constexpr int kSlotBytes = kSample ? 3 * kFuK * kFuWorkers * 8 : 0;
     static constexpr int offB = 0;
     static constexpr int offStage = offB + kRing * kSliceBytesB;
-    static constexpr int kConstBytes = 2 * TN * 16;           // (scale, b2) of the tile being drained and of the next one
+    __host__ __device__ static constexpr int pro_bytes(int kin) { return (kin + 1) * kI8H * 8 + kI8Rows * (kin | 1) * 8; }   // W1^T, b1, inputs
     __host__ __device__ static constexpr int off_bar(int n_stages) { return offStage + n_stages * kStageBytes; }
+    __host__ __device__ static constexpr int off_ex(int n_stages) { return off_bar(n_stages) + 512 + kConstBytes; }
+    __host__ __device__ static constexpr int off_slots(int n_stages) { return off_ex(n_stages) + kExBufs * kFuExBufBytes; }
+    __host__ __device__ static constexpr int off_pro(int n_stages) { return kSample ? offStage : off_slots(n_stages) + kSlotBytes; }
     __host__ __device__ static constexpr int smem_bytes(int kin, int n_stages) {
-        return off_bar(n_stages) + 512 + kConstBytes + kFuExBytes + kFuPrivBytes + (kin + 1) * kI8H * 8 + kI8Rows * (kin | 1) * 8;
+        return kSample ? off_slots(n_stages) + kSlotBytes : off_pro(n_stages) + pro_bytes(kin);
+    }
+    // (sampling: W1 and the inputs must fit into one staging buffer)
+    __host__ __device__ static constexpr bool fits(int kin, int n_stages, int smem_max) {
+        return smem_bytes(kin, n_stages) <= smem_max && (!kSample || pro_bytes(kin) <= kStageBytes);
     }
 };
 
@@ -287,243 +304,10 @@ JF_DEVINL MixVal<double> fu_stream_finish(FuSums& A) {
     return v;
 }
 
-// ---- register-resident twins of mix_eval / presolve_f32 / solve_logit / solve_general (csrc/gf.cuh); same arithmetic ----
-struct FuMix {
-    double m[kFuK], iw[kFuK], n[kFuK];
-    double mmin, mmax;
-};
-
-template <bool NEED_D>
-JF_DEVINL MixVal<double> fu_mix_eval(const FuMix& p, double x) {
-    const bool all_neg = x < p.mmin, all_pos = x > p.mmax;
-    double delta = 0;
-    if (all_neg || all_pos) {
-        delta = Num<double>::big;
-#pragma unroll
-        for (int k = 0; k < kFuK; ++k) delta = tmin(delta, fabs((x - p.m[k]) * p.iw[k]));
-    }
-    const double E = (delta > 0.0) ? exp_neg(-delta) : 1.0;
-    double big_p = 0, small_p = 0, big_n = 0, small_n = 0, Sp = 0, ex = 0, qc = 0, Sd = 0;
-#pragma unroll
-    for (int k = 0; k < kFuK; ++k) {
-        const double iw = p.iw[k], n = p.n[k];
-        const double a = (x - p.m[k]) * iw;
-        const double u = exp_neg(delta - fabs(a));
-        const double e = u * E;
-        const double rx = rcp_1to2(1.0 + e);
-        const double nr = n * rx, nur = nr * u;
-        const double pt = nur * iw * rx;
-        if (a >= 0.0) { big_p += nr; small_p += nur; }
-        else          { big_n += nr; small_n += nur; }
-        if (NEED_D) {
-            const double dt = pt * iw * (rx - e * rx);
-            Sd += (a >= 0.0) ? -dt : dt;
-        }
-        Sp += pt;
-        if (a < -20.0) {
-            const double nq = n * e * rx;
-            ex += nq;
-            qc = fma(nq, u, qc);
-            Sp = fma(nq * u * iw, 1.0 + rx, Sp);
-        }
-    }
-    MixVal<double> v;
-    v.Sc = big_p + small_n + qc; v.Ss = small_p + big_n; v.Sp = Sp; v.ex = ex; v.Sd = Sd; v.E = E;
-    v.dc = all_neg ? delta : 0.0;
-    v.ds = all_pos ? delta : 0.0;
-    v.dp = delta;
-    return v;
-}
-
-JF_DEVINL double fu_presolve_f32(const FuMix& p, double t, double x0, double lo, double hi, double wmin) {
-    const float tf = (float)t, lof = (float)lo, hif = (float)hi;
-    const float stop = (float)(JF_PRE_STOP * wmin);
-    float x = (float)x0;
-#pragma unroll 1
-    for (int it = 0; it < JF_PRE_ITERS; ++it) {
-        float Sc = 0.f, Ss = 0.f, Sp = 0.f, Sd = 0.f;
-#pragma unroll
-        for (int k = 0; k < kFuK; ++k) {
-            const float iw = (float)p.iw[k], n = (float)p.n[k];
-            const float a = (x - (float)p.m[k]) * iw;
-            const float e = ex2_approx(-fabsf(a) * 1.4426950408889634f);
-            const float r = rcp_approx(1.f + e);
-            const float nr = n * r, ner = nr * e;
-            const bool pos = a >= 0.f;
-            Sc += pos ? nr : ner;
-            Ss += pos ? ner : nr;
-            const float pt = ner * r * iw;
-            Sp += pt;
-            const float dt = pt * iw * (r - e * r);
-            Sd += pos ? -dt : dt;
-        }
-        const float ics = rcp_approx(Sc * Ss);
-        const float dy = Sp * ics;
-        const float f = (lg2_approx(Sc) - lg2_approx(Ss)) * 0.6931471805599453f - tf;
-        const float d2 = Sd * ics - dy * dy * (Ss - Sc);
-        const float den = 2.f * dy * dy - f * d2;
-        const float dx = (den > dy * dy) ? (2.f * f * dy * rcp_approx(den)) : (f * rcp_approx(dy));
-        const float xn = x - dx;
-        if (!(xn > lof && xn < hif)) break;
-        x = xn;
-        if (fabsf(dx) <= stop) break;
-    }
-    const double xr = (double)x;
-    return (xr > lo && xr < hi) ? xr : x0;
-}
-
-JF_DEVINL LogitRoot<double> fu_solve_logit(const FuMix& p, double t, bool use_ex) {
-    using T = double;
-    T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0, wmin = Num<T>::big;
-#pragma unroll
-    for (int k = 0; k < kFuK; ++k) {
-        const T m = p.m[k], w = rcp_pos(p.iw[k]);
-        const T c = fma(t, w, m);
-        lo = tmin(lo, c);
-        hi = tmax(hi, c);
-        x = fma(p.n[k], c, x);
-        wmax = tmax(wmax, w);
-        wmin = tmin(wmin, w);
-    }
-    {
-        const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
-        lo -= pad;
-        hi += pad;
-        x = clampv(x, lo, hi);
-    }
-    if (fabs(t) < 60.0) x = fu_presolve_f32(p, t, x, lo, hi, wmin);
-    const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
-    const T early = T(2e-6);
-    LogitRoot<T> out;
-    out.converged = false;
-    out.evals = 0;
-    out.x = x; out.logd = 0; out.lpdf = 0;
-    T fprev = Num<T>::big, f = 0;
-    const int kMaxIt = 64;
-#pragma unroll 1
-    for (int it = 0; it <= kMaxIt; ++it) {
-        const MixVal<T> v = fu_mix_eval<true>(p, x);
-        const T ssq = use_ex ? (v.Ss + v.ex) : v.Ss;
-        if (it == kMaxIt) {          // iteration budget exhausted (non-finite parameters): report the last point
-            out.x = x;
-            out.logd = log(v.Sp / (v.Sc * ssq)) + (use_ex ? v.ex : T(0));
-            out.lpdf = log(v.Sp) - v.dp;
-            out.converged = false;
-            return out;
-        }
-        ++out.evals;
-        const T ics = rcp_pos(v.Sc * ssq);
-        const T dy = v.Sp * ics;
-        f = log(v.Sc * v.Sc * ics) + (v.ds - v.dc) - t;
-        const T smc = (v.dc > T(0)) ? (ssq - v.Sc * v.E) : ((v.ds > T(0)) ? (ssq * v.E - v.Sc) : (ssq - v.Sc));
-        const T d2 = v.Sd * ics - dy * dy * smc;
-        const T den = T(2) * dy * dy - f * d2;
-        const T dx = (den > dy * dy) ? (T(2) * f * dy * rcp_pos(den)) : (f * rcp_pos(dy));
-        if (f < T(0)) lo = x; else hi = x;
-        const T xn = x - dx;
-        const bool inside = (xn > lo) && (xn < hi);
-        const T adx = fabs(dx);
-        const bool tiny = adx <= tol_abs + tol_rel * fabs(x);
-        const bool at_noise = fabs(f) <= T(32) * Num<T>::eps * (T(1) + fabs(t));
-        const bool small_step = inside && adx * dy <= early && adx <= early * wmin;
-        if (small_step || tiny || at_noise) {
-            const bool step = inside;
-            out.x = step ? xn : x;
-            const T sdx = step ? dx : T(0);
-            if (use_ex) { out.logd = log(dy) + v.ex - sdx * d2 * rcp_pos(dy); out.lpdf = T(0); }
-            else { out.lpdf = log(v.Sp) - v.dp - sdx * v.Sd * rcp_pos(v.Sp); out.logd = T(0); }
-            out.converged = true;
-            return out;
-        }
-        if (hi - lo <= tol_abs + tol_rel * fabs(x)) {
-            out.x = x;
-            if (use_ex) { out.logd = log(dy) + v.ex; out.lpdf = T(0); }
-            else { out.lpdf = log(v.Sp) - v.dp; out.logd = T(0); }
-            out.converged = fabs(f) <= Num<T>::target_prec;
-            return out;
-        }
-        const bool shrinking = fabs(f) < T(0.75) * fprev;
-        fprev = fabs(f);
-        x = (inside && shrinking && finite_(xn)) ? xn : T(0.5) * (lo + hi);
-    }
-    return out;
-}
-
-// Pade tails of the inverse-normal variants (|z| > 5.32, ~1e-7 of all normals) and "inormal_full_pade": safeguarded
-// Newton directly on y(x) = z, as solve_general in csrc/gf.cuh (cold)
-JF_DEVINL double fu_solve_general(const FuMix& p, int type, double z, double& logd_out, int& evals, bool& converged) {
-    using T = double;
-    const T marg = (type == JF_INV_PARTLY_CRUDE ? T(0.6) : T(0.05)) + T(0.02) * fabs(z);
-    const T t_lo = logit_phi<T>(z - marg), t_hi = logit_phi<T>(z + marg);
-    T lo = Num<T>::big, hi = -Num<T>::big, x = 0, wmax = 0;
-    const T t_mid = T(0.5) * (t_lo + t_hi);
-#pragma unroll
-    for (int k = 0; k < kFuK; ++k) {
-        const T m = p.m[k], w = T(1) / p.iw[k];
-        lo = tmin(lo, fma(t_lo, w, m));
-        hi = tmax(hi, fma(t_hi, w, m));
-        x = fma(p.n[k], fma(t_mid, w, m), x);
-        wmax = tmax(wmax, w);
-    }
-    {
-        const T pad = T(1e-3) * wmax + T(64) * Num<T>::eps * (fabs(lo) + fabs(hi));
-        lo -= pad;
-        hi += pad;
-        x = clampv(x, lo, hi);
-    }
-    const T tol_abs = Num<T>::newton_abs_tol, tol_rel = T(4) * Num<T>::eps;
-    T fprev = Num<T>::big, f = 0, logd = 0;
-    converged = false;
-    evals = 0;
-    const int kMaxIt = 64;
-#pragma unroll 1
-    for (int it = 0; it < kMaxIt; ++it) {
-        const MixVal<T> v = fu_mix_eval<true>(p, x);
-        ++evals;
-        T y;
-        inv_stage(type, v, y, logd);          // log y' of the last evaluated point is what is reported
-        f = y - z;
-        if (f < T(0)) lo = x; else hi = x;
-        const T dx = f / exp(logd);
-        const T xn = x - dx;
-        const bool inside = (xn > lo) && (xn < hi);
-        if (fabs(dx) <= tol_abs + tol_rel * fabs(x)) {
-            if (inside) x = xn;
-            converged = true;
-            break;
-        }
-        if (hi - lo <= tol_abs + tol_rel * fabs(x)) { converged = true; break; }
-        const bool shrinking = fabs(f) < T(0.75) * fprev;
-        fprev = fabs(f);
-        x = (inside && shrinking && finite_(xn)) ? xn : T(0.5) * (lo + hi);
-    }
-    logd_out = logd;
-    if (!(fabs(f) <= Num<T>::target_prec)) converged = false;
-    return x;
-}
-
-JF_DEVINL double fu_solve(const FuMix& p, int type, double z, double& logd_out, int& evals, bool& converged) {
-    if (type == JF_INV_ISIGMOID) {
-        const LogitRoot<double> r = fu_solve_logit(p, z, true);
-        logd_out = r.logd; evals = r.evals; converged = r.converged;
-        return r.x;
-    }
-    if (type != JF_INV_FULL_PADE && fabs(z) < 5.32) {
-        const LogitRoot<double> r = fu_solve_logit(p, logit_phi<double>(z), false);
-        logd_out = kLogSqrt2Pi + 0.5 * z * z + r.lpdf;
-        evals = r.evals; converged = r.converged;
-        return r.x;
-    }
-    return fu_solve_general(p, type, z, logd_out, evals, converged);
-}
-
 // ---- main kernel ------------------------------------------------------------------------------------------------------
-template <int REGS> JF_DEVINL void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
-template <int REGS> JF_DEVINL void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
-
 template <int NS, int TN, int DIR, int KR>
 __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_constant__ FuArgs a, int n_stages) {
-    using G = FuCfg<NS, TN>;
+    using G = FuCfg<NS, TN, DIR>;
     constexpr int SPT = G::kSPT, TPL = G::kTPL;
     extern __shared__ __align__(1024) unsigned char smem[];
     const MlpArgs<double>& m = a.m;
@@ -543,10 +327,10 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
     auto bar_stage_empty = [&](int s) { return bar0 + 8 * (22 + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 448);
     double* sStage = reinterpret_cast<double*>(smem + G::offStage);        // [n_stages][TN][128]
-    double2* sConst = reinterpret_cast<double2*>(smem + offBar + 512);     // [2][TN]
-    double* sEx = reinterpret_cast<double*>(smem + offBar + 512 + G::kConstBytes);   // [2][4][6][128]
-    double* sPriv = sEx + kFuExBytes / 8;                                  // [4][3][128]
-    double* sW1 = sPriv + kFuPrivBytes / 8;                                // [Kin][128]
+    double2* sConst = reinterpret_cast<double2*>(smem + offBar + 512);     // [3][TN]
+    double* sEx = reinterpret_cast<double*>(smem + G::off_ex(n_stages));   // [kExBufs][4][6][128]
+    double* sSlots = reinterpret_cast<double*>(smem + G::off_slots(n_stages));   // sampling: [3][K][512]
+    double* sW1 = reinterpret_cast<double*>(smem + G::off_pro(n_stages));  // [Kin][128]  (sampling: inside staging buffer 0)
     double* sB1 = sW1 + (size_t)Kin * kI8H;
     double* sIn = sB1 + kI8H;                                              // [128][Kin|1]
     const int ldin = Kin | 1;
@@ -563,11 +347,13 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                      ::"r"(bar0 + 448), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int e = tid; e < Kin * kI8H; e += kFuThreads) {
-        const int i = e / kI8H, u = e - i * kI8H;
-        sW1[e] = m.wt[0][(size_t)u * Kin + i];
+    if (!G::kSample) {
+        for (int e = tid; e < Kin * kI8H; e += kFuThreads) {
+            const int i = e / kI8H, u = e - i * kI8H;
+            sW1[e] = m.wt[0][(size_t)u * Kin + i];
+        }
+        if (tid < kI8H) sB1[tid] = m.bias[0][tid];
     }
-    if (tid < kI8H) sB1[tid] = m.bias[0][tid];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -576,7 +362,6 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
 
     if (warp >= 16) {
         // ---- tensor warpgroup: W2 ring, MMA issue, TMEM drain -> staging ----
-        if (FuRegs<DIR>::kTensor < 96) reg_dec<FuRegs<DIR>::kTensor>();
         const int dq = warp - 16;
         const int r = dq * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(dq * 32) << 16);
@@ -595,15 +380,20 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
         const int tw = tid - 16 * 32;                                        // 0..127 inside the warpgroup
         if (tw < TN && total_tiles > 0) sConst[tw] = a.consts[tw];           // constants of tile 0
         bar_sync_named(7, 128);
-        int t = 0, jb = 0, stage = 0;
+#if JF_FU_PROF
+        long long prof_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
+        int t = 0, jb = 0, stage = 0, cb = 0;                                // cb: constants buffer of the current tile (gt mod 3)
         uint32_t mma_par = 0, stage_wrap = 0;
 #pragma unroll 1
         for (int64_t gt = 0; gt < total_tiles; ++gt) {
             // one elected thread of warp 16 (a warp-uniform branch + elect.sync: UTCIMMA takes uniform-register operands, and
             // under a divergent `lane == 0` the compiler wraps every single MMA in an election loop -- 51 cycles per MMA)
+            FU_T(9);
             if (warp == 16 && elect_one()) {
                 if (t == 0) mbar_wait(bar_a_full, (uint32_t)(jb & 1));        // the workers have written this block's A slices
                 tc_fence_after();
+                FU_T(0);
                 const uint32_t desc_hi = (G::kSbo >> 4) | (1u << 14);
                 const uint32_t b_lo0 = (((sbase + G::offB) & 0x3FFFF) >> 4) | ((uint32_t)(G::kLboB >> 4) << 16);
                 const uint32_t ring_par = (uint32_t)(gt & 1);
@@ -619,6 +409,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     tc_commit(bar_slice_empty(q));               // slot q is free once these MMAs have read it
                 }
                 tc_commit(bar_mma_done);
+                FU_T(1);
                 // refill the ring with the next tile slice by slice as the MMAs retire (the last slot frees when the tile
                 // is complete, which is when the drain below can start anyway)
                 if (gt + 1 < total_tiles) {
@@ -630,50 +421,77 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     }
                 }
             }
+            FU_T(2);
             __syncwarp();                                                    // (the issuer's 31 siblings wait here, not in a spin loop)
+            FU_T(3);
             mbar_wait(bar_mma_done, mma_par); mma_par ^= 1u;
             tc_fence_after();
+            FU_T(4);
             mbar_wait(bar_stage_empty(stage), stage_wrap ^ 1u);              // the workers have taken the previous content
+            FU_T(5);
             {
+                // software-pipelined drain, 4 columns per step in two register buffers: the tcgen05.ld of the next step are in
+                // flight while the current step is combined and stored (TMEM reads are port bound: 64 B/clk per SM)
                 constexpr int LI = FuLv<NS>::kInt;
-                constexpr int CW = FuRegs<DIR>::kTensor >= 96 ? 8 : 4;       // columns per step
                 double* st = sStage + (size_t)stage * (TN * kI8Rows) + r;
-                const double2* cst = sConst + (gt & 1) * TN;
-#pragma unroll 1
-                for (int c0 = 0; c0 < TN; c0 += CW) {
-                    int lv[NS][CW];
+                const double2* cst = sConst + cb * TN;
+                int lvA[NS][4], lvB[NS][4];
+                auto issue = [&](int (&lv)[NS][4], int c0) {
 #pragma unroll
                     for (int l = 0; l < NS; ++l) {
-                        if (JF_FU_DBG & 8) {
-#pragma unroll
-                            for (int j = 0; j < CW; ++j) lv[l][j] = l + c0 + j;
-                        } else if (CW == 8) tmem_ld8(tlane + G::kAccCol + l * TN + c0, lv[l]);
+                        if (JF_FU_DBG & 8) { lv[l][0] = lv[l][1] = lv[l][2] = lv[l][3] = l + c0; }
                         else tmem_ld4(tlane + G::kAccCol + l * TN + c0, lv[l]);
                     }
-                    if (!(JF_FU_DBG & 8)) tmem_ld_wait();
+                };
+                auto process = [&](const int (&lv)[NS][4], int c0) {
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         double sacc = __ll2double_rn(fu_combine<LI>(lv, j));
 #pragma unroll
                         for (int l = LI; l < NS; ++l) sacc = fma((double)lv[l][j], 1.0 / (double)(1ull << (8 * (l - LI + 1))), sacc);
                         const double2 sb = cst[c0 + j];
                         st[(size_t)(c0 + j) * kI8Rows] = fma(sacc, sb.x, sb.y);
                     }
+                };
+                issue(lvA, 0);
+                if (!(JF_FU_DBG & 8)) tmem_ld_wait();
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN - 8; c0 += 8) {
+                    issue(lvB, c0 + 4);
+                    process(lvA, c0);
+                    if (!(JF_FU_DBG & 8)) tmem_ld_wait();
+                    issue(lvA, c0 + 8);
+                    process(lvB, c0 + 4);
+                    if (!(JF_FU_DBG & 8)) tmem_ld_wait();
                 }
+                issue(lvB, TN - 4);
+                process(lvA, TN - 8);
+                if (!(JF_FU_DBG & 8)) tmem_ld_wait();
                 // constants of the next tile (read after the barrier below)
                 if (tw < TN && gt + 1 < total_tiles)
-                    sConst[((gt + 1) & 1) * TN + tw] = a.consts[(size_t)(t + 1 == n_tiles ? 0 : t + 1) * TN + tw];
+                    sConst[(cb == 2 ? 0 : cb + 1) * TN + tw] = a.consts[(size_t)(t + 1 == n_tiles ? 0 : t + 1) * TN + tw];
+                tc_fence_before();
+                FU_T(6);
+                bar_sync_named(7, 128);                                      // TMEM is free: the next tile's MMAs may start
+                FU_T(7);
+                process(lvB, TN - 4);
             }
-            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_stage_full(stage));
-            bar_sync_named(7, 128);                                          // TMEM is free: the next tile's MMAs may start
+            FU_T(8);
             if (++stage == n_stages) { stage = 0; stage_wrap ^= 1u; }
             if (++t == n_tiles) { t = 0; ++jb; }
+            cb = cb == 2 ? 0 : cb + 1;
         }
+#if JF_FU_PROF
+        if (blockIdx.x == 0 && lane == 0)
+            printf("warp %d tiles %lld cycles/tile: a_full %lld | slices+mma issue %lld | refill(=mma run) %lld | syncwarp %lld | mma_done %lld | stage_empty %lld | drain %lld | bar7 %lld | tail %lld | loop %lld\n",
+                   warp, total_tiles, prof_[0] / total_tiles, prof_[1] / total_tiles, prof_[2] / total_tiles, prof_[3] / total_tiles,
+                   prof_[4] / total_tiles, prof_[5] / total_tiles, prof_[6] / total_tiles, prof_[7] / total_tiles, prof_[8] / total_tiles,
+                   prof_[9] / total_tiles);
+#endif
     } else {
         // ---- workers ----
-        if (FuRegs<DIR>::kWorker > 96) reg_inc<FuRegs<DIR>::kWorker>();
         const int lq = warp & 3, cg = warp >> 2;
         const int r = lq * 32 + lane;
         const bool active = cg < d;
@@ -683,9 +501,14 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
         int ex_buf = 0;
         int n_evals = 0, n_unconv = 0, n_bad = 0;
         double* exr = sEx + r;                          // element (buf, j, f) at exr[((buf*4 + j)*6 + f)*128]
+#if JF_FU_PROF
+        long long prof_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
         // this worker's SPT values of the next tile: staging -> registers, then the stage goes back to the tensor warpgroup
         auto next_tile = [&](double* v) {
+            FU_T(0);
             mbar_wait(bar_stage_full(wstage), wwrap);
+            FU_T(1);
             const double* st = sStage + (size_t)wstage * (TN * kI8Rows) + (size_t)(cg * SPT) * kI8Rows + r;
 #pragma unroll
             for (int i = 0; i < SPT; ++i) v[i] = st[(size_t)i * kI8Rows];
@@ -698,6 +521,16 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)jb * gridDim.x) * kI8Rows;
             const int64_t row = row0 + r;
             const bool live = row < m.B;
+            if (G::kSample) {
+                // W1 and the inputs live in staging buffer 0 (prologue only): every worker has taken the last tile of the
+                // previous block, and the tensor warpgroup cannot write the buffer again before this block's A is complete
+                bar_sync_named(1, kFuWorkers);
+                for (int e = tid; e < Kin * kI8H; e += kFuWorkers) {
+                    const int i = e / kI8H, u = e - i * kI8H;
+                    sW1[e] = m.wt[0][(size_t)u * Kin + i];
+                }
+                if (tid < kI8H) sB1[tid] = m.bias[0][tid];
+            }
             // ---- gather the generator's input rows ----
             for (int e = tid; e < kI8Rows * Kin; e += kFuWorkers) {
                 const int rr = e / Kin;
@@ -711,7 +544,9 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                 }
                 sIn[rr * ldin + (e - rr * Kin)] = v;
             }
+            FU_T(2);
             bar_sync_named(1, kFuWorkers);
+            FU_T(3);
             // ---- prologue: layer 1 + tanh + digits -> A slices in tensor memory (thread = (row, quarter of the hidden
             //      units); a 32-bit TMEM column holds 4 consecutive int8 of the row, slice p occupies columns 32 p .. 32 p + 31) ----
             {
@@ -763,16 +598,15 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a_full);
+            FU_T(4);
 
             // ---- the layer chain of this row, dimension cg ----
             double xj = (live && active) ? a.in[row * a.ld_in + cg] : 0.0;
-            double* priv = sPriv + (size_t)(cg * kFuPrivFields) * kI8Rows + r;   // [0] offset, [1] logdet, [2] zsq
+            double logdet_acc = 0.0, zsq = 0.0;         // (worker 0 of the row only)
             if (cg == 0) {
-                priv[kI8Rows] = (live && a.logdet_in) ? a.logdet_in[row] : 0.0;
-                double zsq = 0.0;
+                logdet_acc = (live && a.logdet_in) ? a.logdet_in[row] : 0.0;
                 if (DIR == JF_DIR_SAMPLE && live)
                     for (int j = 0; j < d; ++j) { const double zj = a.in[row * a.ld_in + j]; zsq = fma(zj, zj, zsq); }
-                priv[2 * kI8Rows] = zsq;
             }
             double logd_prev = 0.0;                     // log_pdf: log-derivative of the previous layer, not yet exchanged
 #pragma unroll 1
@@ -784,12 +618,14 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                 // the four workers of a row meet here: sum of the log-derivatives, rotation of the row vector
                 // (x, the Householder components and the log-derivative are in the exchange already)
                 auto meet = [&]() -> double {
+                    FU_T(0);
                     bar_sync_named(2 + lq, 128);
+                    FU_T(5);
                     double X[kFuMaxD], ld = 0.0;
 #pragma unroll
                     for (int j = 0; j < kFuMaxD; ++j)
                         if (j < d) { X[j] = exb[(j * kFuExFields) * kI8Rows]; ld += exb[(j * kFuExFields + 5) * kI8Rows]; }
-                    if (cg == 0) priv[kI8Rows] += DIR == JF_DIR_SAMPLE ? -ld : ld;
+                    if (cg == 0) logdet_acc += DIR == JF_DIR_SAMPLE ? -ld : ld;
 #pragma unroll 1
                     for (int ii = 0; ii < lc.hh_iter; ++ii) {
                         const int i = DIR == JF_DIR_LOGPDF ? ii : lc.hh_iter - 1 - ii;
@@ -812,6 +648,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                         mine = (j == cg) ? X[j] : mine;
                         if (DIR == JF_DIR_SAMPLE && cg == 0 && j < d && !finite_(X[j])) n_bad |= 1;
                     }
+                    if (G::kExBufs == 1) bar_sync_named(2 + lq, 128);       // single buffer: everybody has read before anybody writes again
                     return mine;
                 };
                 double v[SPT];
@@ -843,50 +680,56 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     xj = y;
                     logd_prev = logd;
                 } else {
-                    // slots of the sampling layout: w[0..9] | n[0..9] | v_0..3 | mean[0..9] | offset | padding
-                    FuMix p;
-                    if (JF_FU_DBG & 2) {
-#pragma unroll
-                        for (int k = 0; k < kFuK; ++k) { p.m[k] = 0.1 * k; p.iw[k] = 1.0; p.n[k] = 0.1; }
-                    }
+                    // slots of the sampling layout: w[0..9] | n[0..9] | v_0..3 | mean[0..9] | offset | padding.  The regulated
+                    // kernels go to this worker's shared-memory slots ([field][k][worker], conflict free), where the root
+                    // finder of csrc/gf.cuh (rolled loops over k, out of line) reads them.
+                    double* slot_m = sSlots + tid, * slot_iw = slot_m + kFuK * kFuWorkers, * slot_n = slot_iw + kFuK * kFuWorkers;
+                    double off = 0.0, nsum = 0.0, mmin = Num<double>::big, mmax = -Num<double>::big;
 #pragma unroll
                     for (int part = 0; part < TPL; ++part) {
                         next_tile(v);
 #pragma unroll
                         for (int i = 0; i < SPT; ++i) {
                             const int s = part * SPT + i;
-                            if (JF_FU_DBG & 2) { p.m[0] += v[i]; continue; }
-                            if (s < 10) p.iw[s < 10 ? s : 0] = regulate_inv_width(v[i], lc.w_min, lc.inv_w_max);
-                            else if (s < 20) p.n[s < 20 ? s - 10 : 0] = regulate_norm(v[i], lc.n_min, lc.n_max);
-                            else if (s < 24) exw[(1 + (s - 20)) * kI8Rows] = v[i];
-                            else if (s < 34) p.m[s < 34 ? s - 24 : 0] = v[i];
-                            else if (s == 34) priv[0] = v[i];
+                            if (JF_FU_DBG & 2) { off += v[i]; continue; }
+                            if (s < 10) slot_iw[s * kFuWorkers] = regulate_inv_width(v[i], lc.w_min, lc.inv_w_max);
+                            else if (s < 20) {
+                                const double g = regulate_norm(v[i], lc.n_min, lc.n_max);
+                                nsum += g;
+                                slot_n[(s - 10) * kFuWorkers] = g;
+                            } else if (s < 24) exw[(1 + (s - 20)) * kI8Rows] = v[i];
+                            else if (s < 34) {
+                                slot_m[(s - 24) * kFuWorkers] = v[i];
+                                mmin = tmin(mmin, v[i]);
+                                mmax = tmax(mmax, v[i]);
+                            } else if (s == 34) off = v[i];
                         }
                     }
-                    {
-                        double nsum = 0;
-#pragma unroll
-                        for (int k = 0; k < kFuK; ++k) nsum += p.n[k];
-                        const double inv = 1.0 / nsum;
-#pragma unroll
-                        for (int k = 0; k < kFuK; ++k) p.n[k] *= inv;
-                    }
-                    p.mmin = Num<double>::big; p.mmax = -Num<double>::big;
-#pragma unroll
-                    for (int k = 0; k < kFuK; ++k) { p.mmin = tmin(p.mmin, p.m[k]); p.mmax = tmax(p.mmax, p.m[k]); }
                     double logd = 0.0;
                     int ev = 0;
                     bool conv = true;
-                    if (JF_FU_DBG & 2) xj += p.m[0];
-                    else if (active && live) xj = fu_solve(p, lc.inv_type, xj, logd, ev, conv);
+                    FU_T(0);
+                    if (JF_FU_DBG & 2) xj += off;
+                    else {
+                        const double inv = 1.0 / nsum;
+#pragma unroll
+                        for (int k = 0; k < kFuK; ++k) slot_n[k * kFuWorkers] *= inv;
+                        if (active && live) {
+                            MixView<double> mv;
+                            mv.m = smem_addr(slot_m); mv.iw = smem_addr(slot_iw); mv.n = smem_addr(slot_n);
+                            mv.skb = (unsigned)(kFuWorkers * sizeof(double)); mv.K = kFuK; mv.mmin = mmin; mv.mmax = mmax;
+                            xj = gf_solve<double>(mv, lc.inv_type, xj, logd, ev, conv);
+                        }
+                    }
+                    FU_T(6);
                     n_evals += ev;
                     n_unconv += conv ? 0 : 1;
                     exw[0] = xj;
                     exw[5 * kI8Rows] = logd;
                     xj = meet();
-                    if (lc.has_offset) xj += priv[0];
+                    if (lc.has_offset) xj += off;
                 }
-                ex_buf ^= 1;
+                if (G::kExBufs == 2) ex_buf ^= 1;
             }
             // ---- outputs ----
             if (DIR == JF_DIR_LOGPDF) {
@@ -897,27 +740,27 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                 bar_sync_named(2 + lq, 128);
                 if (cg == 0) {
                     const double* exb = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows;
-                    double ld = 0.0, zsq = 0.0;
+                    double ld = 0.0, zsq_b = 0.0;
                     for (int j = 0; j < d; ++j) {
                         const double xb = exb[(j * kFuExFields) * kI8Rows];
                         ld += exb[(j * kFuExFields + 5) * kI8Rows];
-                        zsq = fma(xb, xb, zsq);
+                        zsq_b = fma(xb, xb, zsq_b);
                         if (!finite_(xb)) n_bad |= 1;
                     }
-                    priv[kI8Rows] += ld;
-                    priv[2 * kI8Rows] = zsq;
+                    logdet_acc += ld;
+                    zsq = zsq_b;
                 }
-                ex_buf ^= 1;
+                if (G::kExBufs == 2) ex_buf ^= 1;
             }
             if (live) {
                 if (active) a.out[row * a.ld_out + cg] = xj;
                 if (cg == 0) {
-                    const double logdet = priv[kI8Rows];
+                    const double logdet = logdet_acc;
                     if (!finite_(logdet)) n_bad |= 1;
                     if (a.logdet_out) a.logdet_out[row] = logdet;
                     if (a.logbase_out) {
                         const double prev = a.logbase_in ? a.logbase_in[row] : 0.0;
-                        a.logbase_out[row] = prev - 0.5 * priv[2 * kI8Rows] - (double)d * kLogSqrt2Pi;
+                        a.logbase_out[row] = prev - 0.5 * zsq - (double)d * kLogSqrt2Pi;
                     }
                 } else if (DIR == JF_DIR_SAMPLE && active && !finite_(xj)) {
                     n_bad |= 2;                     // (an offset made it non-finite: worker 0 saw a finite value)
@@ -926,6 +769,13 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
             if (!live) { n_bad = 0; }
             if (n_bad) { status_add(a.status, JF_STATUS_NONFINITE, 1); n_bad = 0; }
         }
+#if JF_FU_PROF
+        FU_T(0);
+        if (blockIdx.x == 0 && lane == 0 && lq == 0)
+            printf("worker warp %d blocks %d cycles/block: compute %lld | wait tile %lld | gather %lld | bar512 %lld | prologue %lld | meet barrier %lld | solve %lld\n",
+                   warp, my_blocks, prof_[0] / my_blocks, prof_[1] / my_blocks, prof_[2] / my_blocks, prof_[3] / my_blocks, prof_[4] / my_blocks,
+                   prof_[5] / my_blocks, prof_[6] / my_blocks);
+#endif
         if (DIR == JF_DIR_SAMPLE) {
             int tot = n_evals, unc = n_unconv;
             for (int o = 16; o > 0; o >>= 1) {

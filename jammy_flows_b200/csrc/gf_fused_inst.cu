@@ -7,12 +7,12 @@ namespace jf {
 
 template <int NS, int TN, int DIR, int KR>
 static int launch_fused_one(const FuArgs& a, int smem_max, int sms, cudaStream_t st) {
-    using G = FuCfg<NS, TN>;
+    using G = FuCfg<NS, TN, DIR>;
     const int Kin = a.m.dims[0];
     int n_stages = 3;
-    while (n_stages > 1 && G::smem_bytes(Kin, n_stages) > smem_max) --n_stages;
+    while (n_stages > 1 && !G::fits(Kin, n_stages, smem_max)) --n_stages;
+    if (!G::fits(Kin, n_stages, smem_max)) return JF_ERR_UNSUPPORTED;
     const int smem = G::smem_bytes(Kin, n_stages);
-    if (smem > smem_max) return JF_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(gf_fused_kernel<NS, TN, DIR, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const int64_t blocks = (a.m.B + kI8Rows - 1) / kI8Rows;
@@ -37,6 +37,11 @@ int launch_fused_prep(FuArgs& a, const double* W2, const double* b2, int directi
         else fu_prep_kernel<kFuNSSample, kFuTNSample><<<n_tiles, 128, 0, st>>>(a, W2, b2, direction, (unsigned char*)ws);
     }
     return JF_OK;
+}
+
+bool fused_fits(int direction, int kin, int smem_max) {
+    return direction == JF_DIR_LOGPDF ? FuCfg<kFuNSLogpdf, kFuTNLogpdf, JF_DIR_LOGPDF>::fits(kin, 1, smem_max)
+                                      : FuCfg<kFuNSSample, kFuTNSample, JF_DIR_SAMPLE>::fits(kin, 1, smem_max);
 }
 
 int launch_fused(const FuArgs& a, int direction, cudaStream_t st) {

@@ -51,5 +51,7 @@ int64_t fused_prep_bytes(int n_layers);
 // slices W2 / b2 into the workspace in the consumption order of `direction`, and points a.wsB / a.consts at it
 int launch_fused_prep(FuArgs& a, const double* W2, const double* b2, int direction, void* ws, bool run, cudaStream_t st);
 int launch_fused(const FuArgs& a, int direction, cudaStream_t st);
+// does the kernel of this direction fit into `smem_max` bytes of shared memory with `kin` generator inputs?
+bool fused_fits(int direction, int kin, int smem_max);
 
 }  // namespace jf

@@ -64,11 +64,17 @@ __host__ __device__ inline int64_t i8_prep_bytes(int N) {
 JF_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// The suspend-time hint keeps a waiting warp asleep inside the instruction (it wakes when the phase completes): without
+// it the try_wait / branch loops of the waiting warps were 30 % of all executed instructions of the fused kernel, and
+// these kernels are instruction-issue bound (ncu, profiles/).
+#ifndef JF_MBAR_SUSPEND_NS
+#define JF_MBAR_SUSPEND_NS 20000
+#endif
 JF_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)JF_MBAR_SUSPEND_NS) : "memory");
     } while (!ok);
 }
 JF_DEVINL void mbar_arrive(uint32_t bar) {
