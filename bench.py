@@ -94,6 +94,7 @@ ALG = {
     # flop-equivalents per row for each kernel of the step; sampling kernels are scaled by measured evals/element
     "mlp_s2": flops_mlp(4, 128, 10),
     "mlp_e4": flops_mlp(7, 128, 548),
+    "mlp_fp64_part": 2.0 * 7 * 128 + 128 * SPECIAL,          # layer 1 + tanh: what the generator leaves on the FP64 pipe
     "g_logpdf_shared": 4 * D * flops_g_eval(),
     "g_logpdf_perrow": 4 * D * flops_g_eval() + 4 * flops_g_regulate_layer(),
     "s2": 40 * SPECIAL,
@@ -282,6 +283,35 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         return lib.jf_mlp_forward_ws(C.byref(md), _cabi.JF_F64, ptrs, lds, pack.c.weights[k], pack.c.biases[k], vp(pbuf),
                                      chunk, 1, n, C.c_void_p(mlp_ws[k].data_ptr()), nws, prepared, st)
 
+    fused_ws = {}
+
+    def fused(k, direction, segs, src, col_in, col_out, n):
+        """generator + layer chain of sub-pdf k in ONE kernel (jf_subpdf_apply_generated): what the whole-pdf path runs"""
+        md = _cabi.JfMlpDesc()
+        C.memmove(C.byref(md), C.byref(desc.mlp[k]), C.sizeof(md))
+        md.n_segments = len(segs)
+        ptrs = (C.c_void_p * len(segs))(*[s_[0] for s_ in segs])
+        lds = (C.c_int64 * len(segs))(*[s_[1] for s_ in segs])
+        for i, s_ in enumerate(segs):
+            md.seg_cols[i] = s_[2]
+        nws = lib.jf_subpdf_generated_workspace_bytes(C.byref(desc.sub[k]), C.byref(md), _cabi.JF_F64)
+        key = (k, direction)
+        prepared = 1 if key in fused_ws else 0
+        if key not in fused_ws:
+            fused_ws[key] = torch.zeros(max(int(nws), 16), dtype=torch.uint8, device=dev)
+        return lib.jf_subpdf_apply_generated(C.byref(desc.sub[k]), C.byref(md), _cabi.JF_F64, direction, ptrs, lds,
+                                             pack.c.weights[k], pack.c.biases[k], vp(src, col_in), 10, vp(ld), vp(ld), vp(lb),
+                                             vp(lb), vp(out, col_out), 10, n, C.c_void_p(fused_ws[key].data_ptr()), nws,
+                                             prepared, vp(status), st)
+
+    def fused_ok(k, n_in):
+        md = _cabi.JfMlpDesc()
+        C.memmove(C.byref(md), C.byref(desc.mlp[k]), C.sizeof(md))
+        return lib.jf_subpdf_generated_workspace_bytes(C.byref(desc.sub[k]), C.byref(md), _cabi.JF_F64) > 0 \
+            and os.environ.get("JF_FUSED", "1") != "0"
+
+    use_fused = fused_ok(2, 7)
+
     def sub(k, direction, src, ld_src, col_in, col_out, shared, n, first):
         params = C.c_void_p(pack.c.shared[k]) if shared else vp(pbuf)
         return lib.jf_subpdf_apply(C.byref(desc.sub[k]), _cabi.JF_F64, direction, vp(src, col_in), ld_src, params,
@@ -296,14 +326,20 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         timed("g_chain_logpdf[e4 shared]", lambda: sub(0, 0, xc, 10, 0, 0, True, n, True))
         timed("mlp[4->128->10]", lambda: mlp(1, [(vp(xc), 10, 4)], n))
         timed("s2_chain_logpdf[f]", lambda: sub(1, 0, xc, 10, 4, 4, False, n, False))
-        timed("mlp[7->128->548]", lambda: mlp(2, [(vp(xc), 10, 4), (vp(emb), 3, 3)], n))
-        timed("g_chain_logpdf[e4 per-row]", lambda: sub(2, 0, xc, 10, 6, 6, False, n, False))
+        if use_fused:
+            timed("fused_generator+g_chain_logpdf[e4]", lambda: fused(2, 0, [(vp(xc), 10, 4), (vp(emb), 3, 3)], xc, 6, 6, n))
+        else:
+            timed("mlp[7->128->548]", lambda: mlp(2, [(vp(xc), 10, 4), (vp(emb), 3, 3)], n))
+            timed("g_chain_logpdf[e4 per-row]", lambda: sub(2, 0, xc, 10, 6, 6, False, n, False))
         # sampling direction
         timed("g_chain_sample[e4 shared]", lambda: sub(0, 1, zc, 10, 0, 0, True, n, True))
         timed("mlp[4->128->10]", lambda: mlp(1, [(vp(out), 10, 4)], n))
         timed("s2_chain_sample[f]", lambda: sub(1, 1, zc, 10, 4, 4, False, n, False))
-        timed("mlp[7->128->548]", lambda: mlp(2, [(vp(out), 10, 4), (vp(emb), 3, 3)], n))
-        timed("g_chain_sample[e4 per-row]", lambda: sub(2, 1, zc, 10, 6, 6, False, n, False))
+        if use_fused:
+            timed("fused_generator+g_chain_sample[e4]", lambda: fused(2, 1, [(vp(out), 10, 4), (vp(emb), 3, 3)], zc, 6, 6, n))
+        else:
+            timed("mlp[7->128->548]", lambda: mlp(2, [(vp(out), 10, 4), (vp(emb), 3, 3)], n))
+            timed("g_chain_sample[e4 per-row]", lambda: sub(2, 1, zc, 10, 6, 6, False, n, False))
     torch.cuda.synchronize()
     alg = {
         "g_chain_logpdf[e4 shared]": ALG["g_logpdf_shared"],
@@ -311,6 +347,11 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         "g_chain_sample[e4 shared]": 4 * D * flops_g_eval() * evals_per_elem,
         "g_chain_sample[e4 per-row]": 4 * D * flops_g_eval() * evals_per_elem + 4 * flops_g_regulate_layer(),
         "mlp[4->128->10]": ALG["mlp_s2"], "mlp[7->128->548]": ALG["mlp_e4"],
+        # fused kernel: FP64-pipe work only (layer 1 + tanh of the generator, regulators, mixture evaluations); the
+        # 128 x 548 contraction runs on the tensor cores and is reported separately as int8 op/s
+        "fused_generator+g_chain_logpdf[e4]": ALG["g_logpdf_perrow"] + ALG["mlp_fp64_part"],
+        "fused_generator+g_chain_sample[e4]": 4 * D * flops_g_eval() * evals_per_elem + 4 * flops_g_regulate_layer()
+                                              + ALG["mlp_fp64_part"],
         "s2_chain_logpdf[f]": ALG["s2"], "s2_chain_sample[f]": ALG["s2"],
     }
     rows = []
@@ -325,6 +366,15 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
         nrows = B * (2 if r["kernel"].startswith("mlp") else 1)
         r["achieved_tflops"] = r["flop_equiv_per_row"] * nrows / (r["ms"] * 1e-3) * 1e-12
         r["avg_launch_ms"] = r["ms"] / r["launches"]
+        if r["kernel"].startswith("fused"):
+            # tensor-core part of the fused kernel (csrc/gf_fused.cuh): log_pdf 6 int8 slices (21 pair GEMMs) of 12 tiles
+            # x 48 columns, sampling 7 slices (28 pairs) of 20 tiles x 32 columns, per 128 rows
+            lp = "logpdf" in r["kernel"]
+            pairs, cols = (21, 12 * 48) if lp else (28, 20 * 32)
+            r["path"] = ("one kernel: tcgen05 kind::i8 (A in TMEM, %d int8 slices) -> TMEM drain + integer combine -> "
+                         "staged fp64 parameters -> FP64 layer chain; the [P,rows] block never exists in HBM"
+                         % (6 if lp else 7))
+            r["int8_tops"] = pairs * 2.0 * 128 * cols * nrows / (r["ms"] * 1e-3) * 1e-12
         if r["kernel"].startswith("mlp"):
             # tcgen05 path: 28 int8 slice-pair GEMMs of 128 x N(padded to 64) x 128 per row block (csrc/mlp_i8.cuh)
             n_out = int(r["kernel"].split("->")[-1].rstrip("]"))
@@ -347,7 +397,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     pdf = make_model().to(dev)
     pdf.rng_mode = "device"
-    n = args.rows
+    strong = args.scaling == "strong"
+    n = args.rows // world if strong else args.rows     # strong: BASELINE config 2 as written (10 M rows sharded over N)
     x, z = make_inputs(n, dev, 100 + rank)      # every rank owns its own shard of rows (no data-path collective)
     # base normals of the sampling half: this rank's rows [rank*n, (rank+1)*n) of ONE global Philox stream
     # (jf_normal_rows), so the union of the ranks' sample sets is the same set for any number of GPUs
@@ -406,8 +457,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step():
-        engine.pdf_logpdf_host(pdf, xh, device=dev)       # x (H2D) -> logp, logp_base, base (D2H)
-        engine.pdf_sample_host(pdf, zh, device=dev)       # z (H2D) -> x, logp, logp_base (D2H)
+        engine.pdf_logpdf_host(pdf, xh, device=dev, reuse_outputs=True)     # x (H2D) -> logp, logp_base, base (D2H)
+        engine.pdf_sample_host(pdf, zh, device=dev, reuse_outputs=True)     # z (H2D) -> x, logp, logp_base (D2H)
 
     e2e_step()
     barrier()
@@ -423,6 +474,22 @@ def run_gpu_arm(args, rank, world, local_rank):
     h2d = 2 * n * 10 * 8
     d2h = n * (10 + 2) * 8 + n * (10 + 2) * 8
     del xh, zh
+
+    # ---- inverse round trip on this rank's first rows: z -> x = f(z) -> z' = f^-1(x)  (north_star: "round-trip error reported") ----
+    with torch.no_grad():
+        m_rt = min(n, 1 << 20)
+        xs_rt, _, _ = engine.pdf_sample(pdf, z[:m_rt])
+        _, _, z_rt = engine.pdf_logpdf(pdf, xs_rt, want_base=True)
+        err = (z_rt - z[:m_rt]).abs()
+        err_e = torch.cat([err[:, :4], err[:, 6:]], dim=1).amax(dim=1)      # Euclidean coordinates (the S2 pair is a chart)
+        fin = torch.isfinite(err_e)
+        q = torch.sort(err_e[fin]).values
+        roundtrip = dict(rows=int(m_rt), median=float(q[q.numel() // 2]), p9999=float(q[int(q.numel() * 0.9999)]),
+                         max=float(q[-1]), nonfinite_rows=int((~fin).sum()),
+                         note="|f^-1(f(z)) - z| over the 8 Euclidean base coordinates; the largest values are rows inside "
+                              "the reference's own gaps (bulk/Pade switch of the inverse-normal stage, S2 chart clamp), "
+                              "DESIGN.md section 2")
+        del xs_rt, z_rt, err, err_e
 
     if rank != 0:
         if dist is not None:
@@ -445,20 +512,21 @@ def run_gpu_arm(args, rank, world, local_rank):
     kernels = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rows]
     hbm = dict(achieved_gbs=(ALG["bytes_logpdf"] + ALG["bytes_sample"]) * n / (ms_per_step * 1e-3) * 1e-9,
                peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback")
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    int8_peak = 2.0 * bf16
+    int8_src = ("int8 dense = 2 x bf16_tflops of MEASURED_PEAKS.json" if "bf16_tflops" in peaks
+                else "int8 dense = 2 x fallback bf16 1.59 PFLOP/s")
     if top["kernel"].startswith("mlp"):
         # dominant kernel = the tcgen05 MLP: tensor-pipe roofline.  Work = the int8 operations the kernel issues (28 slice
         # pair GEMMs of 128 x N_pad x 128 per 128 rows); peak = int8 dense, taken as 2x the MEASURED
         # bf16 cuBLAS throughput (the nominal ratio 4.5 / 2.25 PFLOP/s) -- burst figure: the kernel is timed alone.
-        bf16 = peaks.get("bf16_tflops", 1590.0)
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_i8_traffic_r01.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
-        roofline = dict(bound="tensor", kernel=top["kernel"], achieved=top["int8_tops"], peak=2.0 * bf16, unit="TFLOP/s",
-                        frac=top["int8_tops"] / (2.0 * bf16), traffic=traffic,
-                        peak_source="int8 dense = 2 x bf16_tflops of MEASURED_PEAKS.json" if "bf16_tflops" in peaks
-                        else "int8 dense = 2 x fallback bf16 1.59 PFLOP/s",
+        roofline = dict(bound="tensor", kernel=top["kernel"], achieved=top["int8_tops"], peak=int8_peak, unit="TFLOP/s",
+                        frac=top["int8_tops"] / int8_peak, traffic=traffic, peak_source=int8_src,
                         note="unit is int8 TOP/s; the same kernel delivers %.1f fp64 TFLOP-equivalents/s = %.2f x the measured "
                              "DFMA peak (%.1f TFLOP/s) that bounded the DMMA kernel it replaces"
                              % (top["achieved_tflops"], top["achieved_tflops"] / fp64_peak if fp64_peak else 0.0, fp64_peak or 0.0),
@@ -466,15 +534,29 @@ def run_gpu_arm(args, rank, world, local_rank):
                         flop_equiv_per_row=top["flop_equiv_per_row"], share_of_step=top["share"],
                         avg_launch_ms=top["avg_launch_ms"], hbm=hbm, kernels=kernels)
     else:
+        traffic, note = None, None
+        if top["kernel"].startswith("fused"):
+            # the fused generator + layer-chain kernel: FP64 pipe is its bound (ncu: tensor pipe idle most of the time);
+            # achieved = FP64-pipe flop-equivalents only, the tensor-core contraction is listed next to it
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_fused_traffic_r02.json")))
+                traffic = tr["logpdf" if "logpdf" in top["kernel"] else "sample"]["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            note = ("FP64-pipe work only (layer 1 + tanh, regulators, mixture evaluations / root finder); the 128 x 548 "
+                    "contraction of the same kernel runs on the tensor cores at %.0f int8 TOP/s = %.2f of %s"
+                    % (top["int8_tops"], top["int8_tops"] / int8_peak, int8_src))
         roofline = dict(bound="fp64", kernel=top["kernel"], achieved=top["achieved_tflops"], peak=fp64_peak, unit="TFLOP/s",
-                        frac=top["achieved_tflops"] / fp64_peak if fp64_peak else None, traffic=None,
+                        frac=top["achieved_tflops"] / fp64_peak if fp64_peak else None, traffic=traffic,
                         peak_source="DFMA probe kernel timed live (jf_probe_fma_peak); MEASURED_PEAKS.json has no fp64 entry",
                         flop_equiv_per_row=top["flop_equiv_per_row"], share_of_step=top["share"],
                         avg_launch_ms=top["avg_launch_ms"], hbm=hbm, kernels=kernels)
+        if note:
+            roofline["note"] = note
     cb = cpu_arm(3, 1) if world == 1 else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic",
+                ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
                 config=dict(workload="README 10-d e4+s2+e4 'gggg+n+gggg' ('n' = alias of 'f', SURVEY F2), fp64, "
                                      "log_pdf + sample of %d rows per GPU per step" % n,
                             rows_per_gpu=n, params=pdf.count_parameters(), parallelism="rows sharded, dp%d, no collective" % world,
@@ -485,11 +567,210 @@ def run_gpu_arm(args, rank, world, local_rank):
                 newton_evals_per_element=evals_per_elem,
                 kernel_status=status, gpu_launches=int(launches), clocks=clock_info,
                 e2e=dict(value=world * n / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=e2e_ms),
+                         ms_per_step=e2e_ms, pcie_gbs_per_rank=(h2d + d2h) / (e2e_ms * 1e-3) * 1e-9,
+                         api="engine.pdf_logpdf_host / pdf_sample_host (jf_pdf_*_host): pinned host buffers in and out"),
+                roundtrip=roundtrip,
                 roofline=roofline)
     if cb is not None:
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "logpdf_evals_per_s",
                                                     "samples_per_s")}
+    emit(line)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training arm (BASELINE.json configs[4]): conditional e10 "gggggggg", 64 conditional inputs, 1 M rows per GPU, fp32
+# ---------------------------------------------------------------------------------------------------------------------
+TRAIN_METRIC = "training rows/s (fwd + bwd + gradient all-reduce + Adam), conditional e10 'gggggggg' flow, cond dim 64, fp32"
+
+
+def make_train_model(dtype=torch.float32):
+    import jammy_flows_b200 as jfb
+    torch.manual_seed(1)
+    np.random.seed(1)
+    return jfb.pdf("e10", "gggggggg", conditional_input_dim=64).to(dtype)
+
+
+def make_train_data(n, device, seed, dtype=torch.float32):
+    g = torch.Generator(device=device).manual_seed(seed)
+    cond = torch.randn(n, 64, generator=g, dtype=dtype, device=device)
+    y = 0.5 * cond[:, :10] + 0.8 * torch.randn(n, 10, generator=g, dtype=dtype, device=device)
+    return y, cond
+
+
+def train_cpu_arm(steps, n=4096):
+    """CPU arm of the training step on a bounded batch: the unmodified reference (oracle/_ref) when staged, else the torch
+    autograd of the oracle port is not available for training -> reported as unavailable."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    pdf = make_train_model()
+    y, cond = make_train_data(n, "cpu", 100)
+    try:
+        from oracle import stage_ref
+        jf = stage_ref.import_staged()
+        torch.manual_seed(1)
+        np.random.seed(1)
+        ref = jf.pdf("e10", "gggggggg", conditional_input_dim=64)
+        ref.load_state_dict({k: v.detach().cpu() for k, v in pdf.state_dict().items()})
+        opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+        ts = []
+        for it in range(steps + 1):
+            t0 = time.perf_counter()
+            opt.zero_grad(set_to_none=True)
+            lp, _, _ = ref(y, conditional_input=cond)
+            (-lp.mean()).backward()
+            opt.step()
+            if it > 0:
+                ts.append(time.perf_counter() - t0)
+        v = n / float(np.median(ts))
+        return dict(value=v, unit=UNIT, cores=threads, kind="reference",
+                    sample="fwd + bwd + Adam on %d rows per step (median of %d), the unmodified reference (oracle/_ref), "
+                           "torch CPU fp32" % (n, steps))
+    except Exception as exc:
+        return dict(value=None, unit=UNIT, cores=threads, kind="unavailable", sample="%s: %s" % (type(exc).__name__, exc))
+
+
+def run_train_arm(args, rank, world, local_rank):
+    """One step = forward + backward over `rows` rows per GPU in chunks (gradient accumulation: the per-row parameter
+    block is 12.8 KB/row), ONE flat NCCL all-reduce of the 422 410 gradients, Adam."""
+    from jammy_flows_b200 import _cabi, sharding
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _cabi.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n, chunk = args.train_rows, args.train_chunk
+    pdf = make_train_model().to(dev)
+    y, cond = make_train_data(n, dev, 100 + rank)      # (every rank builds the same seeded model: no broadcast needed)
+    opt = torch.optim.Adam(pdf.parameters(), lr=1e-3)
+    ar_ms = []
+
+    def step(time_ar=False):
+        opt.zero_grad(set_to_none=True)
+        tot = torch.zeros((), dtype=torch.float64, device=dev)
+        for r0 in range(0, n, chunk):
+            lp, _, _ = pdf(y[r0:r0 + chunk], conditional_input=cond[r0:r0 + chunk])
+            loss = -lp.sum() / n
+            loss.backward()
+            tot += loss.detach().double()
+        if dist is not None:
+            if time_ar:
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+            sharding.allreduce_gradients(pdf)
+            if time_ar:
+                a1.record()
+                ar_ms.append((a0, a1))
+        opt.step()
+        return tot
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(args.warmup):
+        losses.append(float(step()))
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.jf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    loss_t = []
+    for _ in range(args.steps):
+        loss_t.append(step(time_ar=True))
+    e1.record()
+    barrier()
+    launches = lib.jf_launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    losses += [float(t) for t in loss_t]
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    ar = float(np.mean([a.elapsed_time(b) for a, b in ar_ms])) if ar_ms else 0.0
+
+    # ---- end to end: this step's rows come from pinned host memory, the loss goes back to the host ----
+    yh, ch = y.cpu().pin_memory(), cond.cpu().pin_memory()
+    yd, cd = torch.empty_like(y), torch.empty_like(cond)
+
+    def e2e_step():
+        yd.copy_(yh, non_blocking=True)
+        cd.copy_(ch, non_blocking=True)
+        opt.zero_grad(set_to_none=True)
+        tot = torch.zeros((), dtype=torch.float64, device=dev)
+        for r0 in range(0, n, chunk):
+            lp, _, _ = pdf(yd[r0:r0 + chunk], conditional_input=cd[r0:r0 + chunk])
+            loss = -lp.sum() / n
+            loss.backward()
+            tot += loss.detach().double()
+        if dist is not None:
+            sharding.allreduce_gradients(pdf)
+        opt.step()
+        return float(tot.cpu())                         # D2H read of the loss
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    k_e2e = max(1, min(args.steps, 3))
+    for _ in range(k_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    status = pdf.kernel_status()
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    n_par = pdf.count_parameters()
+    # algorithmic work per row (DESIGN.md section 6): generator 64->128->3210 forward (2*(64*128 + 128*3210)) and its
+    # backward (2x), layer chain forward + backward (8 layers x 10 dims x (25 + ~60) specials)
+    P = 3210
+    flops_row = 3 * 2.0 * (64 * 128 + 128 * P) + 8 * 10 * (85 * SPECIAL + 600)
+    achieved = flops_row * n * world / (ms_per_step * 1e-3) * 1e-12
+    tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+    roofline = dict(bound="tensor", kernel="training step (generator GEMMs + fused layer forward/backward)", achieved=achieved,
+                    peak=tf32_peak, unit="TFLOP/s", frac=achieved / tf32_peak, traffic=None,
+                    peak_source="tf32 dense = bf16_tflops / 2 of MEASURED_PEAKS.json (nominal ratio)",
+                    flop_equiv_per_row=flops_row,
+                    note="whole-step figure: the step is a chain of kernels (tcgen05 forward MLP, layer forward, layer "
+                         "backward, backward GEMMs, optimizer); per-kernel shares in profiles/")
+    cb = train_cpu_arm(2) if world == 1 else None
+    line = dict(metric=TRAIN_METRIC, value=world * n / (ms_per_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload="BASELINE configs[4]: training step on conditional e10 'gggggggg' (cond dim 64), "
+                                     "%d rows per GPU per step in chunks of %d" % (n, chunk),
+                            rows_per_gpu=n, chunk_rows=chunk, params=n_par,
+                            parallelism="data parallel dp%d: rows sharded, ONE flat NCCL all-reduce of %d fp32 gradients "
+                                        "per step" % (world, n_par),
+                            l2="inputs (%.0f MB per rank) exceed the 126 MB L2" % (n * 74 * 4 / 1e6)),
+                allreduce_ms=ar, allreduce_bytes=4 * n_par if world > 1 else 0, losses=losses, kernel_status=status,
+                gpu_launches=int(launches), clocks=clock_info,
+                e2e=dict(value=world * n / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=n * 74 * 4, d2h_bytes_per_step=8,
+                         ms_per_step=e2e_ms, api="pdf(y, conditional_input=c) + backward + Adam; rows from pinned host memory"),
+                roofline=roofline)
+    if cb is not None:
+        line["cpu_baseline"] = cb
     emit(line)
     if dist is not None:
         dist.barrier()
@@ -503,6 +784,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rows", type=int, default=10_000_000, help="rows per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE configs[1] (headline); train: configs[4], the training step with NCCL gradient all-reduce")
+    ap.add_argument("--train-rows", type=int, default=1_000_000, help="--config train: rows per GPU per step")
+    ap.add_argument("--train-chunk", type=int, default=65536, help="--config train: rows per forward/backward chunk")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows per GPU; strong: --rows in total, sharded over the GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -516,7 +803,10 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
-    run_gpu_arm(args, rank, world, local_rank)
+    if args.config == "train":
+        run_train_arm(args, rank, world, local_rank)
+    else:
+        run_gpu_arm(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

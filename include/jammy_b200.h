@@ -19,9 +19,10 @@
  *
  * Ownership: the caller allocates every buffer (inputs, outputs, workspace) and passes raw device pointers
  * (host pointers only for the *_host entries); the library never allocates or frees device memory.
- * Threading: re-entrant, no global mutable state; all work is enqueued on the caller's `stream` (a cudaStream_t
- * passed as void*).  No entry point synchronises the device except the *_host entries, which synchronise their
- * internal streams before returning.
+ * Threading: re-entrant; all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*).  No entry
+ * point synchronises the device except the *_host entries: they run on two internal NON-BLOCKING streams (created once
+ * per host thread and device, then kept) and synchronise those before returning; whatever the caller prepared on other
+ * streams (parameters, workspace, status words) must be complete when a *_host entry is called.
  * ABI history: v2 added JfSplineDesc and the spline / S1 / "v" / "t" layer kinds; v3 added the non-default "g" options
  * (rotation_mode, width_mode, width_clamp, skew, center_mean, stretch, clamp_lo/hi in JfLayerDesc).
  * Errors: return value 0 = ok, <0 = invalid/unsupported descriptor (JF_ERR_*), >0 = CUDA runtime error code.

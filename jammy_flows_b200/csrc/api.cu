@@ -943,15 +943,27 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
     const bool logpdf = direction == JF_DIR_LOGPDF;
     const int src_cols = logpdf ? d->total_target_dim : d->total_base_dim;
     const int dst_cols = logpdf ? d->total_base_dim : d->total_target_dim;
-    cudaStream_t st[2];
-    JF_CUDA_OK(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
-    JF_CUDA_OK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+    // two copy/compute streams + two events per (host thread, device), created on first use and kept (creating and
+    // destroying them cost ~50 us per call).  They are non-blocking streams: the CALLER must have finished preparing the
+    // parameter vector / workspace / status words (jammy_flows_b200.engine synchronises torch's current stream first).
+    struct HostStreams { cudaStream_t st[2]; cudaEvent_t done[2]; bool ready; };
+    static thread_local HostStreams cache[64] = {};
+    int dev = 0;
+    JF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return JF_ERR_BAD_ARG;
+    HostStreams& hs = cache[dev];
+    if (!hs.ready) {
+        JF_CUDA_OK(cudaStreamCreateWithFlags(&hs.st[0], cudaStreamNonBlocking));
+        JF_CUDA_OK(cudaStreamCreateWithFlags(&hs.st[1], cudaStreamNonBlocking));
+        JF_CUDA_OK(cudaEventCreateWithFlags(&hs.done[0], cudaEventDisableTiming));
+        JF_CUDA_OK(cudaEventCreateWithFlags(&hs.done[1], cudaEventDisableTiming));
+        hs.ready = true;
+    }
+    cudaStream_t* st = hs.st;
+    cudaEvent_t* done = hs.done;
     // the two streams exist to overlap COPIES with kernels; the kernels of consecutive chunks are chained by events so
     // that they never share the SMs (a persistent MLP CTA next to layer-kernel CTAs of the other chunk slows both)
     static const bool chain_compute = [] { const char* e = getenv("JF_HOST_OVERLAP_COMPUTE"); return !(e && atoi(e) == 1); }();
-    cudaEvent_t done[2];
-    JF_CUDA_OK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
-    JF_CUDA_OK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     int64_t ci = 0;
     for (int64_t r0 = 0; r0 < B && rc == JF_OK; r0 += chunk, ++ci) {
         const int64_t n = (B - r0 < chunk) ? (B - r0) : chunk;
@@ -985,10 +997,6 @@ static int pdf_run_host(const JfPdfDesc* d, const JfPdfParams* P, int direction,
     }
     cudaError_t e0 = cudaStreamSynchronize(st[0]);
     cudaError_t e1 = cudaStreamSynchronize(st[1]);
-    cudaStreamDestroy(st[0]);
-    cudaStreamDestroy(st[1]);
-    cudaEventDestroy(done[0]);
-    cudaEventDestroy(done[1]);
     if (rc != JF_OK) return rc;
     if (e0 != cudaSuccess) return (int)e0;
     if (e1 != cudaSuccess) return (int)e1;

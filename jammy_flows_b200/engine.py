@@ -678,8 +678,27 @@ def row_logmeanexp(t):
     return out
 
 
-def _host_call(pdf, direction, src, cond, chunk_rows, device):
-    """HOST tensors in, HOST tensors out (pinned): the end-to-end path with copies inside the library call."""
+_PINNED_OUT = {}
+
+
+def _pinned_out(tag, shape, dtype, reuse):
+    """Pinned host output buffer; with `reuse` the buffer of the previous call with the same shape is handed out again
+    (page-locking 2 GB of fresh host memory per call costs more than the copies it receives)."""
+    if not reuse:
+        return torch.empty(*shape, dtype=dtype, pin_memory=True)
+    key = (tag, tuple(shape), dtype)
+    buf = _PINNED_OUT.get(key)
+    if buf is None:
+        for k in [k for k in _PINNED_OUT if k[0] == tag]:
+            del _PINNED_OUT[k]                              # one live buffer per role
+        buf = _PINNED_OUT[key] = torch.empty(*shape, dtype=dtype, pin_memory=True)
+    return buf
+
+
+def _host_call(pdf, direction, src, cond, chunk_rows, device, reuse_outputs=False):
+    """HOST tensors in, HOST tensors out (pinned): the end-to-end path with copies inside the library call.
+    reuse_outputs=True returns the SAME pinned output tensors on every call of that shape (they are overwritten by the
+    next call): what a serving loop wants."""
     lib = _cabi.load()
     assert not src.is_cuda
     if uses_custom_mlp(pdf) or pdf.amortize_everything:
@@ -695,19 +714,22 @@ def _host_call(pdf, direction, src, cond, chunk_rows, device):
     ws = _workspace(dev, nbytes)
     pack = ParamPack(pdf, dt, dev)
     status = pdf._status(dev)
-    pin = dict(dtype=dt, pin_memory=True)
-    logp = torch.empty(B, **pin)
-    logp_base = torch.empty(B, **pin)
+    tag = "lp" if direction == _cabi.JF_DIR_LOGPDF else "s"
+    logp = _pinned_out(tag + "_logp", (B,), dt, reuse_outputs)
+    logp_base = _pinned_out(tag + "_logp_base", (B,), dt, reuse_outputs)
     src = src.contiguous()
     cond = cond.contiguous() if cond is not None else None
     with torch.cuda.device(dev):
+        # the library's copy/compute streams are non-blocking streams: the parameter vector (torch.cat / casts), the
+        # zeroed status words and the workspace were prepared on torch's current stream and must be complete first
+        torch.cuda.current_stream(dev).synchronize()
         if direction == _cabi.JF_DIR_LOGPDF:
-            out = torch.empty(B, pdf.total_base_dim, **pin)
+            out = _pinned_out(tag + "_out", (B, pdf.total_base_dim), dt, reuse_outputs)
             rc = lib.jf_pdf_logpdf_host(C.byref(desc), C.byref(pack.c), _ptr(src), src.stride(0), _ptr(cond),
                                         cond.stride(0) if cond is not None else 0, _ptr(logp), _ptr(logp_base), _ptr(out),
                                         pdf.total_base_dim, B, _ptr(ws), ws.numel(), chunk, _ptr(status))
         else:
-            out = torch.empty(B, pdf.total_target_dim, **pin)
+            out = _pinned_out(tag + "_out", (B, pdf.total_target_dim), dt, reuse_outputs)
             rc = lib.jf_pdf_sample_host(C.byref(desc), C.byref(pack.c), _ptr(src), src.stride(0), _ptr(cond),
                                         cond.stride(0) if cond is not None else 0, _ptr(out), pdf.total_target_dim,
                                         _ptr(logp), _ptr(logp_base), B, _ptr(ws), ws.numel(), chunk, _ptr(status))
@@ -715,13 +737,13 @@ def _host_call(pdf, direction, src, cond, chunk_rows, device):
     return out, logp, logp_base
 
 
-def pdf_logpdf_host(pdf, x_host, cond_host=None, chunk_rows=None, device="cuda"):
-    base, logp, logp_base = _host_call(pdf, _cabi.JF_DIR_LOGPDF, x_host, cond_host, chunk_rows, device)
+def pdf_logpdf_host(pdf, x_host, cond_host=None, chunk_rows=None, device="cuda", reuse_outputs=False):
+    base, logp, logp_base = _host_call(pdf, _cabi.JF_DIR_LOGPDF, x_host, cond_host, chunk_rows, device, reuse_outputs)
     return logp, logp_base, base
 
 
-def pdf_sample_host(pdf, z_host, cond_host=None, chunk_rows=None, device="cuda"):
-    return _host_call(pdf, _cabi.JF_DIR_SAMPLE, z_host, cond_host, chunk_rows, device)
+def pdf_sample_host(pdf, z_host, cond_host=None, chunk_rows=None, device="cuda", reuse_outputs=False):
+    return _host_call(pdf, _cabi.JF_DIR_SAMPLE, z_host, cond_host, chunk_rows, device, reuse_outputs)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
