@@ -268,6 +268,25 @@ int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype,
                       void* out, int64_t out_stride_param, int64_t out_stride_row,
                       int64_t B, void* workspace, int64_t workspace_bytes, int prepared, void* stream);
 
+/* Training: gradient of the parameter generator  params = W2 tanh(W1 inp + b1) + b2  (what the reference gets from
+ * autograd through nn.Sequential(Linear, Tanh, Linear), main/default.py:654-670, called at :956) given the gradient with
+ * respect to its PARAM-MAJOR output, i.e. what jf_subpdf_backward writes.  Eligible: fp32, one hidden layer of 128, at
+ * most 96 inputs (jf_mlp_backward_workspace_bytes returns -1 otherwise, jf_mlp_backward JF_ERR_UNSUPPORTED).  The two
+ * large products run as tcgen05 kind::tf32 MMAs (10-bit operand mantissas, fp32 accumulation: relative error of the
+ * weight gradients ~1e-3 / sqrt(rows)); csrc/mlp_bwd.cuh.
+ *   inp          [B, dims[0]] (ld_inp)         weights / biases as in jf_mlp_forward (biases[1] is not read)
+ *   grad_out     element (j,row) at grad_out[j*go_stride_param + row]; go_stride_row must be 1, 16-byte aligned rows
+ *   grad_w1/b1/w2/b2   outputs in torch layout, ZEROED BY THE CALLER (partial sums are added with red.global)
+ *   grad_inp     [B, dims[0]] (ld_ginp) or NULL
+ *   workspace    jf_mlp_backward_workspace_bytes(desc, dtype, B) bytes, 256-byte aligned */
+int64_t jf_mlp_backward_workspace_bytes(const JfMlpDesc* desc, int dtype, int64_t B);
+int jf_mlp_backward(const JfMlpDesc* desc, int dtype, const void* inp, int64_t ld_inp,
+                    const void* const* weights, const void* const* biases,
+                    const void* grad_out, int64_t go_stride_param, int64_t go_stride_row,
+                    void* grad_w1, void* grad_b1, void* grad_w2, void* grad_b2,
+                    void* grad_inp, int64_t ld_ginp, int64_t B,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Parameter generator + layer chain of ONE conditional Euclidean sub-pdf in a single kernel (csrc/gf_fused.cuh): replaces
  * the hand-off main/default.py:956 (MLP call) -> :998-1029 (layer loop over `extra_inputs` slices), and for sampling
  * :1438 -> :1482-1506, without the [rows, n_params] block ever existing in HBM.  Eligible: fp64, manifold 'e' with

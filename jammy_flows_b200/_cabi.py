@@ -97,6 +97,9 @@ SYMBOLS = {
     "jf_mlp_workspace_bytes": (_i64, [C.POINTER(JfMlpDesc), C.c_int]),
     "jf_mlp_forward_ws": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
                                     C.POINTER(_vp), _vp, _i64, _i64, _i64, _vp, _i64, C.c_int, _vp]),
+    "jf_mlp_backward_workspace_bytes": (_i64, [C.POINTER(JfMlpDesc), C.c_int, _i64]),
+    "jf_mlp_backward": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _i64,
+                                  _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "jf_subpdf_generated_workspace_bytes": (_i64, [C.POINTER(JfSubPdfDesc), C.POINTER(JfMlpDesc), C.c_int]),
     "jf_subpdf_apply_generated": (C.c_int, [C.POINTER(JfSubPdfDesc), C.POINTER(JfMlpDesc), C.c_int, C.c_int,
                                             C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_vp), _vp, _i64,

@@ -19,6 +19,7 @@
 #include "gf_bwd.cuh"
 #include "rowwise.cuh"
 #include "gf_fused_launch.cuh"
+#include "mlp_bwd_launch.cuh"
 #include <cstdlib>
 
 using namespace jf;
@@ -613,6 +614,49 @@ extern "C" int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype, const void* c
         return mlp_forward_t<float>(desc, seg_ptrs, seg_ld, weights, biases, out, out_stride_param, out_stride_row, B, st,
                                     workspace, workspace_bytes, prepared);
     return JF_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// jf_mlp_backward: gradient of the parameter generator on the tensor cores (csrc/mlp_bwd.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+static bool mlp_bwd_eligible(const JfMlpDesc* md, int dtype) {
+    return md != nullptr && dtype == JF_F32 && md->n_linear == 2 && md->dims[1] == 128 && md->dims[0] >= 1 &&
+           md->dims[0] <= 96 && md->dims[2] >= 1;
+}
+
+extern "C" int64_t jf_mlp_backward_workspace_bytes(const JfMlpDesc* desc, int dtype, int64_t B) {
+    if (!mlp_bwd_eligible(desc, dtype) || B < 0) return -1;
+    return mlp_bwd_workspace_bytes(desc->dims[2], B);
+}
+
+extern "C" int jf_mlp_backward(const JfMlpDesc* desc, int dtype, const void* inp, int64_t ld_inp,
+                               const void* const* weights, const void* const* biases, const void* grad_out,
+                               int64_t go_stride_param, int64_t go_stride_row, void* grad_w1, void* grad_b1, void* grad_w2,
+                               void* grad_b2, void* grad_inp, int64_t ld_ginp, int64_t B, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+    if (desc == nullptr || inp == nullptr || weights == nullptr || biases == nullptr || grad_out == nullptr ||
+        grad_w1 == nullptr || grad_b1 == nullptr || grad_w2 == nullptr || grad_b2 == nullptr)
+        return JF_ERR_BAD_ARG;
+    if (!mlp_bwd_eligible(desc, dtype)) return JF_ERR_UNSUPPORTED;
+    if (go_stride_row != 1 || (go_stride_param & 3) != 0 || go_stride_param < B) return JF_ERR_BAD_ARG;   // param-major, 16-byte rows
+    if ((reinterpret_cast<uintptr_t>(grad_out) & 15) != 0) return JF_ERR_BAD_ARG;
+    if (B < 0) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    if (workspace == nullptr || workspace_bytes < mlp_bwd_workspace_bytes(desc->dims[2], B)) return JF_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return JF_ERR_WORKSPACE;
+    BwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.G = (const float*)grad_out; a.ldg = go_stride_param;
+    a.P = desc->dims[2]; a.B = B;
+    a.x = (const float*)inp; a.ldx = ld_inp; a.in = desc->dims[0];
+    a.W1 = (const float*)weights[0]; a.b1 = (const float*)biases[0]; a.W2 = (const float*)weights[1];
+    if (a.W1 == nullptr || a.b1 == nullptr || a.W2 == nullptr) return JF_ERR_BAD_ARG;
+    a.dW1 = (float*)grad_w1; a.db1 = (float*)grad_b1; a.dW2 = (float*)grad_w2; a.db2 = (float*)grad_b2;
+    a.dx = (float*)grad_inp; a.lddx = ld_ginp;
+    int rc = launch_mlp_bwd(a, workspace, (cudaStream_t)stream);
+    g_launches.fetch_add(kMlpBwdLaunches - 1, std::memory_order_relaxed);
+    if (rc != JF_OK) return rc;
+    return check_launch();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

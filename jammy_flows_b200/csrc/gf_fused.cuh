@@ -191,7 +191,6 @@ JF_DEVINL long long fu_combine(const int (&lv)[NSL][CW], int j) {
     return acc;
 }
 JF_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-JF_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]^T, int8 x int8 -> int32, M = 128: the four K = 32 steps of one (slice p, slice q) pair; A
 // advances 8 columns (32 int8 per row) per step, the B descriptor by adding to its low word
 JF_DEVINL void tc_mma_i8_ts_x4(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi_b, uint32_t idesc,

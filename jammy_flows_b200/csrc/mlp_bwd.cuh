@@ -1,0 +1,428 @@
+// Backward of the parameter generator  params[P, B] = W2 tanh(W1 x + b1) + b2  (fp32, hidden 128) on the tensor cores.
+//
+//   reference: autograd through nn.Sequential(Linear, Tanh, Linear), main/default.py:654-670, called at :956; here the
+//   upstream gradient G = d loss / d params arrives PARAM-MAJOR ([P, B], what csrc/gf_bwd.cuh writes).
+//
+// The two products that carry 99 % of the flops (2 x 2 P 128 B) run as tcgen05.mma kind::tf32 with fp32 accumulators in
+// tensor memory -- tf32 keeps 10 mantissa bits of each operand: the gradients of the generator weights carry a relative
+// error of ~1e-3 / sqrt(terms) (stated tolerance, tests/test_cuda_training.py: 2e-3 of the tensor maximum against fp64):
+//   bw_dh_kernel    dh[B,128]   = G^T W2            M = 128 rows, N = 128, K = P   (one CTA per 128 rows)
+//                   epilogue: dpre = dh (1 - h^2) -> [B,128] row major
+//   bw_dw2_kernel   [dW2 | db2] = G [h | 1]         M = 128 parameters, N = 144, K = rows (CTA = parameter tile x row range,
+//                   partial sums added with red.global)
+// Operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices; the same
+// layout as csrc/mlp_i8.cuh): G is read ONCE per kernel straight from HBM (cp.async; bw_dh transposes its chunk through
+// shared memory, for bw_dw2 the param-major rows already are K-major), W2 and h come pre-tiled from small prep kernels
+// (bw_w2_tiles_kernel once per call, bw_h_tiles_kernel: h = tanh(W1 x + b1) recomputed in fp32) so that one 1-D
+// cp.async.bulk per chunk is enough.  Both kernels are HBM bound by design: 2 x P B 4 bytes of G per call.
+// The three small products (dW1 = dpre^T x, db1, dx = dpre W1: 1 % of the flops) are a plain FFMA kernel (bw_small_kernel).
+#pragma once
+#include "mlp_i8.cuh"
+#include "mlp_bwd_launch.cuh"
+
+namespace jf {
+
+constexpr int kBwH = 128;          // hidden width
+constexpr int kBwKC = 32;          // K elements per pipeline chunk (4 MMAs of K = 8)
+constexpr int kBwNExt = 144;       // [h | 1 | padding]: N of the dW2 product
+constexpr int kBwProducers = 256;  // 8 warps stage operands, warp 8 issues the MMAs
+constexpr int kBwThreads = 288;
+
+
+// byte offset of element (r, k) of a [R rows][KC k] fp32 operand tile in the K-major no-swizzle UMMA layout
+__host__ __device__ constexpr int bw_tile_off(int R, int r, int k) { return (k >> 2) * (R / 8) * 128 + (r >> 3) * 128 + (r & 7) * 16 + (k & 3) * 4; }
+
+JF_DEVINL float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+JF_DEVINL void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor of kind::tf32: D = f32, A = B = tf32, both K-major
+__host__ __device__ constexpr uint32_t bw_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+JF_DEVINL void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+JF_DEVINL void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+// ---- prep: W2 [P,128] -> tiles of 32 parameters: B operand (n = hidden, k = parameter) of the dh product ------------------
+__global__ void __launch_bounds__(256) bw_w2_tiles_kernel(const float* __restrict__ W2, int P, float* __restrict__ tiles) {
+    const int c = blockIdx.x;
+    char* t = reinterpret_cast<char*>(tiles) + (size_t)c * (kBwH * kBwKC * 4);
+    for (int e = threadIdx.x; e < kBwH * kBwKC; e += blockDim.x) {
+        const int k = e >> 7, n = e & 127;                  // consecutive threads: consecutive n of one parameter (coalesced)
+        const int p = c * kBwKC + k;
+        const float v = p < P ? W2[(size_t)p * kBwH + n] : 0.f;
+        *reinterpret_cast<float*>(t + bw_tile_off(kBwH, n, k)) = to_tf32(v);
+    }
+}
+
+// ---- prep: h = tanh(W1 x + b1) -> tiles of 32 rows: B operand (n = hidden | 1, k = row) of the dW2 product ---------------
+// one block = one tile (32 rows); thread (row = tid & 31, group of 16 hidden units = tid >> 5)
+__global__ void __launch_bounds__(256) bw_h_tiles_kernel(const BwArgs a) {
+    extern __shared__ float sm_h[];
+    float* sW = sm_h;                                       // [in][128]  (W1 transposed)
+    float* sX = sW + (size_t)a.in * kBwH;                   // [32][in + 1]
+    const int ldxs = a.in | 1;
+    const int64_t row0 = (int64_t)blockIdx.x * kBwKC;
+    for (int e = threadIdx.x; e < a.in * kBwH; e += blockDim.x) {
+        const int u = e / a.in, i = e - u * a.in;
+        sW[i * kBwH + u] = a.W1[e];
+    }
+    for (int e = threadIdx.x; e < kBwKC * a.in; e += blockDim.x) {
+        const int r = e / a.in, i = e - r * a.in;
+        sX[r * ldxs + i] = (row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 31, ug = threadIdx.x >> 5;
+    const bool live = row0 + r < a.B;
+    char* t = reinterpret_cast<char*>(a.h_tiles) + (size_t)blockIdx.x * (kBwNExt * kBwKC * 4);
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = a.b1[ug * 16 + j];
+    for (int i = 0; i < a.in; ++i) {
+        const float xi = sX[r * ldxs + i];
+        const float* w = sW + i * kBwH + ug * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = fmaf(xi, w[j], z[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, ug * 16 + j, r)) = live ? to_tf32(tanhf(z[j])) : 0.f;
+    // column 128 = 1 (its product with G is db2), the padding columns are zero
+    if (ug < 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = kBwH + ug * 8 + j;
+            *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, n, r)) = (n == kBwH && live) ? 1.f : 0.f;
+        }
+    }
+}
+
+// ---- dh = G^T W2, dpre = dh (1 - h^2) ---------------------------------------------------------------------------------------
+// shared memory: raw G chunks [3][32 p][128 rows] | A stages [2][128 rows x 32 k] | B stages [2][128 n x 32 k] | barriers
+constexpr int kDhRaw = 3, kDhStages = 2;
+constexpr int kDhTile = kBwH * kBwKC * 4;                   // 16 KB
+constexpr int kDhSmem = (kDhRaw + 2 * kDhStages) * kDhTile + 256;
+
+__global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t offA = kDhRaw * kDhTile, offB = offA + kDhStages * kDhTile, offBar = offB + kDhStages * kDhTile;
+    const uint32_t bar0 = sbase + offBar;
+    auto bar_fullA = [&](int s) { return bar0 + 8 * s; };
+    auto bar_fullB = [&](int s) { return bar0 + 8 * (2 + s); };
+    auto bar_empty = [&](int s) { return bar0 + 8 * (4 + s); };
+    const uint32_t bar_done = bar0 + 8 * 6;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 128);
+    const int64_t row0 = (int64_t)blockIdx.x * 128;
+    const int n_chunks = (a.P + kBwKC - 1) / kBwKC;
+
+    if (tid == 0) {
+        for (int s = 0; s < kDhStages; ++s) { mbar_init(bar_fullA(s), 8); mbar_init(bar_fullB(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + 128), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ---- producers ----
+        // raw chunk c: 32 parameters x 128 rows; 16-byte unit u = tid + 256 j: parameter u >> 5, rows 4 (u & 31) ..
+        auto prefetch = [&](int c) {
+            const uint32_t dst0 = sbase + (c % kDhRaw) * kDhTile;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int u = tid + 256 * j;
+                const int k = u >> 5, rq = u & 31;
+                const int p = c * kBwKC + k;
+                const int64_t row = row0 + 4 * rq;
+                int bytes = 0;
+                if (p < a.P && row < a.B) { const int64_t left = a.B - row; bytes = left >= 4 ? 16 : (int)left * 4; }
+                const float* src = a.G + (size_t)(p < a.P ? p : 0) * a.ldg + (row < a.B ? row : 0);
+                cp_async16(dst0 + (k * 128 + 4 * rq) * 4, src, bytes);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        prefetch(0);
+        if (n_chunks > 1) prefetch(1); else asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c & 1;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");               // chunk c has landed (this thread's pieces)
+            bar_sync_named(1, kBwProducers);                                   // ... everybody's
+            if (c >= kDhStages) mbar_wait(bar_empty(s), (uint32_t)(((c >> 1) - 1) & 1));   // the MMAs of chunk c-2 have read the stage
+            // transpose raw [k][row] -> A stage [row][k] (K-major core matrices), rounded to tf32:
+            // thread -> (row = tid & 127, two k-quads): 4 conflict-free LDS.32, one STS.128
+            {
+                const float* raw = reinterpret_cast<const float*>(smem + (c % kDhRaw) * kDhTile);
+                const int r = tid & 127;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kq = (tid >> 7) + 2 * j;
+                    const float v0 = to_tf32(raw[(4 * kq + 0) * 128 + r]), v1 = to_tf32(raw[(4 * kq + 1) * 128 + r]);
+                    const float v2 = to_tf32(raw[(4 * kq + 2) * 128 + r]), v3 = to_tf32(raw[(4 * kq + 3) * 128 + r]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + offA + s * kDhTile + bw_tile_off(128, r, 4 * kq)),
+                                 "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+                }
+            }
+            if (tid == 0) {                                                    // W2 tile c -> B stage
+                mbar_expect_tx(bar_fullB(s), kDhTile);
+                bulk_g2s(sbase + offB + s * kDhTile, a.w2_tiles + (size_t)c * (kDhTile / 4), kDhTile, bar_fullB(s));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_fullA(s));
+            bar_sync_named(1, kBwProducers);                                   // the raw buffer of chunk c is free
+            if (c + 2 < n_chunks) prefetch(c + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    } else {
+        // ---- MMA issuer ----
+        if (elect_one()) {
+            constexpr uint32_t idesc = bw_idesc(128, 128);
+            constexpr uint32_t lbo = (128 / 8) * 128;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c & 1;
+                const uint32_t par = (uint32_t)((c >> 1) & 1);
+                mbar_wait(bar_fullA(s), par);
+                mbar_wait(bar_fullB(s), par);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = umma_desc(sbase + offA + s * kDhTile + ks * 2 * lbo, lbo, 128);
+                    const uint64_t bd = umma_desc(sbase + offB + s * kDhTile + ks * 2 * lbo, lbo, 128);
+                    tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                }
+                tc_commit(bar_empty(s));
+            }
+            tc_commit(bar_done);
+        }
+    }
+    // ---- epilogue: warps 0-3, thread = row ----
+    if (warp < 4) {
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        const int r = warp * 32 + lane;
+        const int64_t row = row0 + r;
+        const char* ht = reinterpret_cast<const char*>(a.h_tiles) + (size_t)(row / kBwKC) * (kBwNExt * kBwKC * 4);
+        const int kr = (int)(row % kBwKC);
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int n0 = 0; n0 < kBwH; n0 += 8) {
+            int v[8];
+            tmem_ld8(tl + n0, v);
+            tmem_ld_wait();
+            if (row < a.B) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = *reinterpret_cast<const float*>(ht + bw_tile_off(kBwNExt, n0 + j, kr));
+                    o[j] = __int_as_float(v[j]) * (1.f - h * h);
+                }
+                float4* dst = reinterpret_cast<float4*>(a.dpre + row * kBwH + n0);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128) : "memory");
+}
+
+// ---- [dW2 | db2] = G [h | 1] ------------------------------------------------------------------------------------------------
+// CTA = (parameter tile of 128, row range); 4 stages of (A: 128 p x 32 rows, 16 KB; B: 144 x 32, 18 KB)
+constexpr int kW2Stages = 4;
+constexpr int kW2TileA = 128 * kBwKC * 4, kW2TileB = kBwNExt * kBwKC * 4;
+constexpr int kW2Smem = kW2Stages * (kW2TileA + kW2TileB) + 256;
+
+__global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t offB = kW2Stages * kW2TileA, offBar = offB + kW2Stages * kW2TileB;
+    const uint32_t bar0 = sbase + offBar;
+    auto bar_full = [&](int s) { return bar0 + 8 * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8 * (4 + s); };
+    const uint32_t bar_done = bar0 + 8 * 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 128);
+    const int p0 = blockIdx.x * 128;
+    // this CTA's row range, in chunks of 32 rows
+    const int64_t total_chunks = (a.B + kBwKC - 1) / kBwKC;
+    const int64_t per = (total_chunks + a.n_splits - 1) / a.n_splits;
+    const int64_t c_begin = (int64_t)blockIdx.y * per;
+    const int64_t c_end = c_begin + per < total_chunks ? c_begin + per : total_chunks;
+    const int n_chunks = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kW2Stages; ++s) { mbar_init(bar_full(s), 9); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + 128), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (n_chunks > 0) {
+        if (warp < 8) {
+            // ---- producers: cp.async 16-byte units (4 rows of one parameter) straight into the K-major A stage ----
+            // unit idx = tid + 256 j: w = idx >> 5, l = idx & 31 -> parameter (w >> 1) 8 + (l & 7), k-quad (w & 1) 4 + (l >> 3):
+            // a warp reads 64 contiguous bytes of 8 parameter rows and writes 512 contiguous bytes of shared memory
+            auto issue = [&](int c) {
+                const int s = c % kW2Stages;
+                const int64_t rbase = (c_begin + c) * kBwKC;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = tid + 256 * j;
+                    const int w = idx >> 5, l = idx & 31;
+                    const int pl = (w >> 1) * 8 + (l & 7), kq = (w & 1) * 4 + (l >> 3);
+                    const int p = p0 + pl;
+                    const int64_t row = rbase + 4 * kq;
+                    int bytes = 0;
+                    if (p < a.P && row < a.B) { const int64_t left = a.B - row; bytes = left >= 4 ? 16 : (int)left * 4; }
+                    const float* src = a.G + (size_t)(p < a.P ? p : 0) * a.ldg + (row < a.B ? row : 0);
+                    cp_async16(sbase + s * kW2TileA + bw_tile_off(128, pl, 4 * kq), src, bytes);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (tid == 0) {
+                    mbar_expect_tx(bar_full(s), kW2TileB);
+                    bulk_g2s(sbase + offB + s * kW2TileB, a.h_tiles + (size_t)(c_begin + c) * (kW2TileB / 4), kW2TileB, bar_full(s));
+                }
+            };
+            for (int c = 0; c < kW2Stages - 1; ++c) {
+                if (c < n_chunks) issue(c); else asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            for (int c = 0; c < n_chunks; ++c) {
+                const int cn = c + kW2Stages - 1;
+                if (cn < n_chunks) {
+                    if (cn >= kW2Stages) mbar_wait(bar_empty(cn % kW2Stages), (uint32_t)(((cn / kW2Stages) - 1) & 1));
+                    issue(cn);
+                } else {
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                asm volatile("cp.async.wait_group %0;" ::"n"(kW2Stages - 1) : "memory");   // chunk c has landed
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full(c % kW2Stages));
+            }
+        } else {
+            if (elect_one()) {
+                constexpr uint32_t idesc = bw_idesc(128, kBwNExt);
+                constexpr uint32_t lboA = (128 / 8) * 128, lboB = (kBwNExt / 8) * 128;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int s = c % kW2Stages;
+                    mbar_wait(bar_full(s), (uint32_t)((c / kW2Stages) & 1));
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t ad = umma_desc(sbase + s * kW2TileA + ks * 2 * lboA, lboA, 128);
+                        const uint64_t bd = umma_desc(sbase + offB + s * kW2TileB + ks * 2 * lboB, lboB, 128);
+                        tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(bar_empty(s));
+                }
+                tc_commit(bar_done);
+            }
+        }
+        // ---- epilogue: warps 0-3, thread = parameter row: partial sums -> red.global ----
+        if (warp < 4) {
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+            const int p = p0 + warp * 32 + lane;
+            const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int n0 = 0; n0 < kBwNExt - 8; n0 += 8) {                       // columns 0..135 (128 = db2, the rest is padding)
+                int v[8];
+                tmem_ld8(tl + n0, v);
+                tmem_ld_wait();
+                if (p < a.P) {
+                    if (n0 < kBwH) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) red_add(a.dW2 + (size_t)p * kBwH + n0 + j, __int_as_float(v[j]));
+                    } else {
+                        red_add(a.db2 + p, __int_as_float(v[0]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+}
+
+// ---- dW1 = dpre^T x, db1 = sum dpre, dx = dpre W1 (1 % of the flops: FFMA) -------------------------------------------------
+// one block = 64 rows; thread t: hidden unit u = t & 127, half = t >> 7
+constexpr int kSmRows = 64;
+__global__ void __launch_bounds__(256) bw_small_kernel(const BwArgs a) {
+    extern __shared__ float sm_s[];
+    float* sD = sm_s;                                   // [64][129] dpre
+    float* sX = sD + kSmRows * 129;                     // [64][in + 1]
+    float* sW = sX + kSmRows * (a.in | 1);              // [128][in + 1]  W1
+    const int ldxs = a.in | 1;
+    const int64_t row0 = (int64_t)blockIdx.x * kSmRows;
+    for (int e = threadIdx.x; e < kSmRows * kBwH; e += blockDim.x) {
+        const int r = e >> 7, n = e & 127;
+        sD[r * 129 + n] = (row0 + r < a.B) ? a.dpre[(row0 + r) * kBwH + n] : 0.f;
+    }
+    for (int e = threadIdx.x; e < kSmRows * a.in; e += blockDim.x) {
+        const int r = e / a.in, i = e - r * a.in;
+        sX[r * ldxs + i] = (row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
+    }
+    if (a.dx != nullptr)
+        for (int e = threadIdx.x; e < kBwH * a.in; e += blockDim.x) {
+            const int u = e / a.in, i = e - u * a.in;
+            sW[u * ldxs + i] = a.W1[e];
+        }
+    __syncthreads();
+    const int u = threadIdx.x & 127, half = threadIdx.x >> 7;
+    // dW1[u][i] for the inputs i of this half; db1[u]
+    {
+        const int i0 = half * ((a.in + 1) / 2), i1 = half == 0 ? (a.in + 1) / 2 : a.in;
+        float bsum = 0.f;
+        if (half == 0)
+            for (int r = 0; r < kSmRows; ++r) bsum += sD[r * 129 + u];
+        for (int i = i0; i < i1; i += 8) {
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int r = 0; r < kSmRows; ++r) {
+                const float dv = sD[r * 129 + u];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (i + j < i1) acc[j] = fmaf(dv, sX[r * ldxs + i + j], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i + j < i1) red_add(a.dW1 + (size_t)u * a.in + i + j, acc[j]);
+        }
+        if (half == 0) red_add(a.db1 + u, bsum);
+    }
+    // dx[row][i] = sum_u dpre[row][u] W1[u][i]: thread -> (row = t & 63, inputs i = (t >> 6) + 4 j)
+    if (a.dx != nullptr) {
+        const int r = threadIdx.x & 63;
+        if (row0 + r < a.B) {
+            for (int i = threadIdx.x >> 6; i < a.in; i += 4) {
+                float acc = 0.f;
+                for (int n = 0; n < kBwH; ++n) acc = fmaf(sD[r * 129 + n], sW[n * ldxs + i], acc);
+                a.dx[(row0 + r) * a.lddx + i] = acc;
+            }
+        }
+    }
+}
+
+}  // namespace jf

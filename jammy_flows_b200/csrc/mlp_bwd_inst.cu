@@ -1,0 +1,57 @@
+// launcher of the tensor-core backward of the parameter generator (csrc/mlp_bwd.cuh); its own translation unit so that
+// the library builds in parallel
+#include "mlp_bwd.cuh"
+
+namespace jf {
+
+static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+
+int64_t mlp_bwd_workspace_bytes(int P, int64_t B) {
+    const int64_t w2 = (int64_t)((P + kBwKC - 1) / kBwKC) * kDhTile;
+    const int64_t ht = ((B + kBwKC - 1) / kBwKC) * (int64_t)kW2TileB;
+    return align256(w2) + align256(ht) + align256(B * kBwH * 4);
+}
+
+int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    char* ws = (char*)workspace;
+    const int n_ptiles32 = (a.P + kBwKC - 1) / kBwKC;
+    const int64_t n_rtiles32 = (a.B + kBwKC - 1) / kBwKC;
+    a.w2_tiles = (float*)ws;
+    a.h_tiles = (float*)(ws + align256((int64_t)n_ptiles32 * kDhTile));
+    a.dpre = (float*)((char*)a.h_tiles + align256(n_rtiles32 * (int64_t)kW2TileB));
+    bw_w2_tiles_kernel<<<n_ptiles32, 256, 0, st>>>(a.W2, a.P, a.w2_tiles);
+    {
+        const int smem = (a.in * kBwH + kBwKC * (a.in | 1)) * 4;
+        e = cudaFuncSetAttribute(bw_h_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        bw_h_tiles_kernel<<<(unsigned)n_rtiles32, 256, smem, st>>>(a);
+    }
+    e = cudaFuncSetAttribute(bw_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDhSmem);
+    if (e != cudaSuccess) return (int)e;
+    bw_dh_kernel<<<(unsigned)((a.B + 127) / 128), kBwThreads, kDhSmem, st>>>(a);
+    {
+        // parameter tiles x row ranges: about three waves of CTAs, at least 8 chunks of rows each
+        const int n_pt = (a.P + 127) / 128;
+        int64_t splits = (3 * (int64_t)sms + n_pt - 1) / n_pt;
+        if (splits > (n_rtiles32 + 7) / 8) splits = (n_rtiles32 + 7) / 8;
+        if (splits < 1) splits = 1;
+        a.n_splits = (int)splits;
+        e = cudaFuncSetAttribute(bw_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem);
+        if (e != cudaSuccess) return (int)e;
+        bw_dw2_kernel<<<dim3((unsigned)n_pt, (unsigned)splits), kBwThreads, kW2Smem, st>>>(a);
+    }
+    {
+        const int ldxs = a.in | 1;
+        const int smem = (kSmRows * 129 + kSmRows * ldxs + kBwH * ldxs) * 4;
+        e = cudaFuncSetAttribute(bw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        bw_small_kernel<<<(unsigned)((a.B + kSmRows - 1) / kSmRows), 256, smem, st>>>(a);
+    }
+    return 0;
+}
+
+}  // namespace jf

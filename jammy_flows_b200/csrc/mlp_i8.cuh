@@ -133,6 +133,7 @@ JF_DEVINL void tmem_ld8(uint32_t taddr, int* v) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
+JF_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 JF_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // tanh with an ABSOLUTE error of ~2 ulp(1): (1-e)/(1+e), e = exp(-2|x|); what the fixed-point operand needs

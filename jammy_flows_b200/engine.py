@@ -901,6 +901,9 @@ class _MlpParamsTc(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):                                   # g: [P, B]
         inp, w1, b1, w2 = ctx.saved_tensors
+        if g.dtype == torch.float32:
+            return _mlp_backward_tc(inp, w1, b1, w2, g, ctx.needs_input_grad[0])
+        # fp64: library GEMMs (the tensor-core kernels are tf32: 1e-3, the fp64 training contract is 1e-8)
         h = torch.tanh(torch.addmm(b1, inp, w1.t()))         # [B, 128]
         g_w2 = torch.mm(g, h)                                # [P, 128]
         g_b2 = g.sum(dim=1)
@@ -911,6 +914,43 @@ class _MlpParamsTc(torch.autograd.Function):
         # the generator's input may itself carry history (a conditional_input produced by an upstream encoder)
         g_inp = torch.mm(g_pre, w1) if ctx.needs_input_grad[0] else None
         return g_inp, g_w1, g_b1, g_w2, g_b2
+
+
+def _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad):
+    """fp32 gradient of the generator on the tensor cores (`jf_mlp_backward`, csrc/mlp_bwd.cuh): h is recomputed, the two
+    [P, B]-sized products run as tcgen05 kind::tf32 MMAs, the small ones as FFMA; g is read twice from HBM and nothing of
+    its size is written."""
+    lib = _cabi.load()
+    dev = inp.device
+    B, P, n_in = inp.shape[0], w2.shape[0], inp.shape[1]
+    md = _cabi.JfMlpDesc()
+    md.n_linear = 2
+    md.dims[0], md.dims[1], md.dims[2] = n_in, w1.shape[0], P
+    md.n_segments = 1
+    md.seg_cols[0] = n_in
+    g = g if (g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0) else g.contiguous()
+    if g.stride(0) % 4 != 0:                                 # rows of a multiple of 4 floats (16-byte cp.async units)
+        gp = torch.zeros(P, (B + 3) // 4 * 4, dtype=g.dtype, device=dev)
+        gp[:, :B] = g
+        g = gp
+    inp_c = inp if inp.stride(1) == 1 else inp.contiguous()
+    ws_ = [w1.detach().contiguous(), w2.detach().contiguous()]
+    bs_ = [b1.detach().contiguous(), b1.detach().contiguous()]
+    wp = (C.c_void_p * 2)(*[t.data_ptr() for t in ws_])
+    bp = (C.c_void_p * 2)(*[t.data_ptr() for t in bs_])
+    g_w1, g_b1 = torch.zeros_like(ws_[0]), torch.zeros_like(bs_[0])
+    g_w2, g_b2 = torch.zeros_like(ws_[1]), torch.zeros(P, dtype=g.dtype, device=dev)
+    g_inp = torch.empty(B, n_in, dtype=g.dtype, device=dev) if want_inp_grad else None
+    nws = lib.jf_mlp_backward_workspace_bytes(C.byref(md), _cabi.JF_F32, B)
+    if nws < 0:
+        raise RuntimeError("jf_mlp_backward: shape not eligible (%d -> %d -> %d)" % (n_in, w1.shape[0], P))
+    ws = _workspace(dev, max(int(nws), 16))
+    with torch.cuda.device(dev):
+        rc = lib.jf_mlp_backward(C.byref(md), _cabi.JF_F32, _ptr(inp_c), inp_c.stride(0), wp, bp, _ptr(g), g.stride(0), 1,
+                                 _ptr(g_w1), _ptr(g_b1), _ptr(g_w2), _ptr(g_b2), _ptr(g_inp),
+                                 g_inp.stride(0) if g_inp is not None else 0, B, _ptr(ws), ws.numel(), _stream_ptr(dev))
+    _cabi.check(rc, "jf_mlp_backward")
+    return g_inp, g_w1, g_b1, g_w2, g_b2
 
 
 def _tc_mlp_eligible(mlp, dt, dev):

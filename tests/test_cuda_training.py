@@ -93,3 +93,26 @@ def test_backward_of_unsupported_pdfs_fails_loudly(lib_built):
     lp, _, _ = p(x)
     with pytest.raises(NotImplementedError):
         lp.sum().backward()
+
+
+def test_generator_backward_kernel_matches_fp64_reference(lib_built):
+    """jf_mlp_backward (tcgen05 kind::tf32 products, csrc/mlp_bwd.cuh) against a plain torch fp64 evaluation of the same
+    gradient.  Stated tolerance of the tf32 path: 2e-3 of each tensor's maximum (10-bit operand mantissas)."""
+    import torch
+    from jammy_flows_b200 import engine
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    for B, n_in, P in ((1000, 7, 300), (4099, 64, 3210), (130, 96, 129)):
+        inp = torch.randn(B, n_in, device=dev)
+        w1 = 0.3 * torch.randn(128, n_in, device=dev)
+        b1 = 0.1 * torch.randn(128, device=dev)
+        w2 = 0.2 * torch.randn(P, 128, device=dev)
+        g = torch.randn(P, B, device=dev) * torch.rand(P, 1, device=dev)
+        got = engine._mlp_backward_tc(inp, w1, b1, w2, g, True)
+        i64, w164, b164, w264, g64 = (t.double() for t in (inp, w1, b1, w2, g))
+        h = torch.tanh(torch.addmm(b164, i64, w164.t()))
+        g_pre = (g64.t() @ w264) * (1.0 - h * h)
+        ref = (g_pre @ w164, g_pre.t() @ i64, g_pre.sum(0), g64 @ h, g64.sum(1))
+        for name, a, r in zip(("inp", "w1", "b1", "w2", "b2"), got, ref):
+            err = float((a.double() - r).abs().max() / r.abs().max())
+            assert err < 2e-3, (B, n_in, P, name, err)
