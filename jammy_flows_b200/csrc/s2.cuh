@@ -241,7 +241,11 @@ __device__ __noinline__ void v_eval(const VRow<T>& r, const T* x, T* y, T* J, T&
     // unnormalised logarithmic map of g at x and its Jacobians (:153-214)
     const T tn = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
     const T nh[3] = {g0 / tn, g1 / tn, g2 / tn};
-    const T ca = nh[0] * x[0] + nh[1] * x[1] + nh[2] * x[2];
+    // (the dot product of two unit vectors can exceed 1 by a rounding error when the gradient is parallel to x: acos and
+    //  sqrt(1 - ca^2) then return NaN -- once per ~4 M rows in fp32, never observed in fp64; the reference asserts fp64
+    //  for this layer, exponential_map_s2.py:448.  Kept a few ulp inside (-1, 1): the map is the identity there.)
+    const T ca_lim = T(1) - T(4) * Num<T>::eps;
+    const T ca = clampv(nh[0] * x[0] + nh[1] * x[1] + nh[2] * x[2], -ca_lim, ca_lim);
     const T sa = sin(acos(ca));
     const T sq = sqrt(T(1) - ca * ca);
     T th[3], u[3];

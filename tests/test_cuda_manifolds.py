@@ -131,3 +131,48 @@ def test_cfg4_four_million_rows_conditional(lib_built):
     # oracle on the first rows: the reference's own inverse of "v" is only good to ~1e-7 (see test_cuda_parity)
     assert row_rel_err(x[:m].cpu().numpy(), xs_o.numpy()).max() < 5e-6
     assert rel_err(logp[:m].cpu().numpy(), slp_o.numpy()).max() < 5e-6
+
+
+def test_cfg4_four_million_rows_fp32(lib_built):
+    """BASELINE configs[3] as written: fp32.  The reference cannot run "v" in fp32 (it asserts fp64,
+    exponential_map_s2.py:448), so the fp32 kernels are held against the fp64 kernels (pinned to the reference by the test
+    above) on the same fp32-rounded inputs, and the status counters are accounted for:
+      * nonfinite: none (a unit-vector dot product that rounds above 1 used to give one NaN row per ~4 M);
+      * unconverged: the Newton iteration of the "v" inverse on the sphere stalls above the fp32 target (1e-4) where the
+        map is ill conditioned -- a few ten rows per million, bounded here, and every one of them converges in fp64."""
+    import copy
+    p64 = _model("e6+s2", "gggggg+v", 0.02, cond=64)
+    p32 = copy.deepcopy(p64).float().cuda()
+    p64 = p64.cuda()
+    n = 4_000_000
+    g = torch.Generator(device="cuda").manual_seed(31)
+    cond = torch.randn(n, 64, generator=g, dtype=torch.float64, device="cuda").float()
+    z = torch.randn(n, 8, generator=g, dtype=torch.float64, device="cuda").float()
+    for q in (p32, p64):
+        q.chunk_rows = 1 << 18
+    with torch.no_grad():
+        x, _, logp, _ = p32._obtain_sample(conditional_input=cond, predefined_target_input=z)
+        st = p32.kernel_status()
+        rt_logp, _, rt_z = p32(x, conditional_input=cond)
+        st_lp = p32.kernel_status()
+        x64, _, logp64, _ = p64._obtain_sample(conditional_input=cond.double(), predefined_target_input=z.double())
+        st64 = p64.kernel_status()
+    r_s2 = z[:, 6:].norm(dim=1)
+    calm = (z[:, :6].abs().max(dim=1)[0] < 5.2) & (r_s2 < 5.2) & (r_s2 > 2e-3)
+    finite = torch.isfinite(x).all(dim=1) & torch.isfinite(logp) & torch.isfinite(rt_z).all(dim=1) & torch.isfinite(rt_logp)
+    err = (rt_z - z).abs().max(dim=1)[0] / z.abs().max(dim=1)[0].clamp(min=1)
+    # the S2 angles wrap: compare samples in the embedding
+    def emb(a):
+        return torch.cat([a[:, :6], torch.stack([a[:, 6].sin() * a[:, 7].cos(), a[:, 6].sin() * a[:, 7].sin(), a[:, 6].cos()], 1)], 1)
+    e64 = (emb(x.double()) - emb(x64)).abs().max(dim=1)[0]
+    print("\ncfg4 fp32: status sample %s / log_pdf %s (fp64: %s); non-calm rows %d; round trip median %.1e p999 %.1e max %.1e; "
+          "vs fp64 samples median %.1e p999 %.1e" % (st, st_lp, st64, int((~calm).sum()), float(err[calm].median()),
+                                                     float(err[calm].quantile(0.999)), float(err[calm].max()),
+                                                     float(e64[calm].median()), float(e64[calm].quantile(0.999))))
+    assert st["nonfinite"] == 0 and st_lp["nonfinite"] == 0 and bool(finite[calm].all())
+    assert st64["unconverged"] <= int((~calm).sum()) + 4                  # every row converges in fp64
+    assert st["unconverged"] <= 50e-6 * n, st                             # fp32: a few ten per million (ill-conditioned "v" rows)
+    assert float(err[calm].median()) < 1e-5 and float(err[calm].quantile(0.999)) < 2e-4
+    assert float(e64[calm].median()) < 1e-5 and float(e64[calm].quantile(0.999)) < 2e-4
+    # the rows that round trip badly in fp32 are at most the unconverged ones plus fp32 noise at ill-conditioned points
+    assert int((err[calm] > 1e-2).sum()) <= st["unconverged"] + 4
