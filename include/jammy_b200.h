@@ -24,7 +24,9 @@
  * per host thread and device, then kept) and synchronise those before returning; whatever the caller prepared on other
  * streams (parameters, workspace, status words) must be complete when a *_host entry is called.
  * ABI history: v2 added JfSplineDesc and the spline / S1 / "v" / "t" layer kinds; v3 added the non-default "g" options
- * (rotation_mode, width_mode, width_clamp, skew, center_mean, stretch, clamp_lo/hi in JfLayerDesc).
+ * (rotation_mode, width_mode, width_clamp, skew, center_mean, stretch, clamp_lo/hi in JfLayerDesc).  v4 added
+ * jf_subpdf_apply_generated (fused generator + layer chain), jf_mlp_backward (tensor-core generator gradient) and the
+ * "f" rotation modes / kappa link functions (JF_ROT_XYZ, JF_ROT_QUATERNION, JF_KAPPA_* in rotation_mode / width_mode).
  * Errors: return value 0 = ok, <0 = invalid/unsupported descriptor (JF_ERR_*), >0 = CUDA runtime error code.
  * Numerical conditions (non-finite values, unconverged root finds, out-of-range inputs) are counted in the device
  * int64 array `status[JF_STATUS_WORDS]` and are read lazily by the caller (no implicit sync), mirroring the reference's
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define JF_ABI_VERSION 3
+#define JF_ABI_VERSION 4
 
 #define JF_MAX_LAYERS 16
 #define JF_MAX_SUBPDFS 8
@@ -100,6 +102,19 @@ extern "C" {
 #define JF_ROT_ANGLES 2      /* chain of d(d-1)/2 Givens rotations */
 #define JF_ROT_CAYLEY 3      /* d = 2, one parameter */
 #define JF_ROT_TRIANGULAR 4  /* triangular_combination: unit lower x zero-sum diagonal x unit upper, d(d-1)+d-1 parameters */
+/* rotation of "f" in the embedding space of S2 (layers/spheres/sphere_base.py:79-91, :112-216): JF_ROT_HOUSEHOLDER,
+ * JF_ROT_ANGLES (3 Givens angles), and */
+#define JF_ROT_XYZ 5         /* 3 parameters: the z axis is rotated onto the normalised vector */
+#define JF_ROT_QUATERNION 6  /* 4 parameters: rotation of the (unnormalised) quaternion */
+/* concentration of "f" (layers/spheres/fvm_2d.py:108-138, :289-330), stored in JfLayerDesc.width_mode; width_clamp =
+ * kappa_clamping (raw parameter clamped at -5 from below) */
+#define JF_KAPPA_DIRECT_LOG 0       /* exp(raw) + min_kappa (default) */
+#define JF_KAPPA_SOFTPLUS 1         /* softplus(raw) + min_kappa */
+#define JF_KAPPA_LOG_BOUNDED 2      /* exp(softplus(raw) + log min_kappa) */
+#define JF_KAPPA_MU 3               /* |rotation parameters| (rotation mode xyz); no kappa parameter */
+#define JF_KAPPA_MU_SQUARED 4
+#define JF_KAPPA_QUATVEC 5          /* |vector part of the quaternion| (rotation mode quaternion); no kappa parameter */
+#define JF_KAPPA_QUATVEC_SQUARED 6
 
 /* width regulator of "g" (gaussianization_flow.py:264-317) */
 #define JF_WIDTH_SMOOTH 0   /* w = w_min + 1/(1/w_max + exp(-raw))   (width_smooth_saturation=1, default) */
@@ -164,9 +179,9 @@ typedef struct JfLayerDesc {
     int32_t max_iter;     /* v: max_num_newton_iter */
     int32_t n_vertical;   /* f: number of nested "r" sub-flows, spline[0 .. n_vertical) */
     int32_t n_circular;   /* f: number of nested "o" sub-flows, spline[n_vertical .. n_vertical+n_circular) */
-    int32_t rotation_mode; /* g: JF_ROT_* (0 = Householder, the default) */
-    int32_t width_mode;    /* g: JF_WIDTH_* */
-    int32_t width_clamp;   /* g: clamp_widths: raw width parameter clamped into [clamp_lo, clamp_hi] first */
+    int32_t rotation_mode; /* g, f: JF_ROT_* (0 = Householder, the default) */
+    int32_t width_mode;    /* g: JF_WIDTH_* ; f: JF_KAPPA_* */
+    int32_t width_clamp;   /* g: clamp_widths: raw width parameter clamped into [clamp_lo, clamp_hi] first; f: kappa_clamping */
     int32_t skew;          /* g: add_skewness (one more K*d block of log skew exponents at the end of the slice) */
     int32_t center_mean;   /* g: only K-1 means per dimension are parameters (gaussianization_flow.py:841-848) */
     int32_t stretch;       /* g: JF_STRETCH_* */

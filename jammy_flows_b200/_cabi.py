@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JF_LIB_PATH") or os.path.join(PKG_DIR, "libjammy_b200.so")
 
 # ---- constants (keep in sync with include/jammy_b200.h; checked by tests/test_cabi_symbols.py) -----------------------
-JF_ABI_VERSION = 3
+JF_ABI_VERSION = 4
 JF_MAX_LAYERS = 16
 JF_MAX_SUBPDFS = 8
 JF_MAX_MLP_LINEAR = 6
@@ -29,6 +29,9 @@ JF_SPLINE_PLAIN, JF_SPLINE_SMOOTH, JF_SPLINE_CIRCULAR = 0, 1, 2
 JF_BD_PARAMS, JF_BD_FIXED, JF_BD_PERIODIC = 0, 1, 2
 JF_NORM_NONE, JF_NORM_RAW, JF_NORM_REGULATED = 0, 1, 2
 JF_ROT_HOUSEHOLDER, JF_ROT_NONE, JF_ROT_ANGLES, JF_ROT_CAYLEY, JF_ROT_TRIANGULAR = 0, 1, 2, 3, 4
+JF_ROT_XYZ, JF_ROT_QUATERNION = 5, 6
+(JF_KAPPA_DIRECT_LOG, JF_KAPPA_SOFTPLUS, JF_KAPPA_LOG_BOUNDED, JF_KAPPA_MU, JF_KAPPA_MU_SQUARED, JF_KAPPA_QUATVEC,
+ JF_KAPPA_QUATVEC_SQUARED) = 0, 1, 2, 3, 4, 5, 6
 JF_WIDTH_SMOOTH, JF_WIDTH_EXP, JF_WIDTH_SOFTPLUS = 0, 1, 2
 JF_STRETCH_CLASSIC, JF_STRETCH_RQS = 0, 1
 JF_POT_EXPONENTIAL, JF_POT_LINEAR, JF_POT_QUADRATIC = 0, 1, 2

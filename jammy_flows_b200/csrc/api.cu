@@ -229,8 +229,23 @@ static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaS
         memset(&c, 0, sizeof(c));
         c.kind = L.kind;
         c.add_rotation = L.hh_iter > 0; c.hh_iter = L.hh_iter; c.first = L.first; c.raw_off = L.param_offset;
-        const int n_hh = L.hh_iter > 0 ? L.hh_iter * 3 : 0;
+        int n_hh = L.hh_iter > 0 ? L.hh_iter * 3 : 0;
+        c.rot_mode = JF_ROT_HOUSEHOLDER; c.n_rot = n_hh; c.kappa_mode = JF_KAPPA_DIRECT_LOG; c.kappa_clamp = 0;
         if (L.kind == JF_LAYER_FVM) {
+            // rotation modes of sphere_base.py:79-91 and the kappa link functions of fvm_2d.py:108-138
+            if (L.rotation_mode == JF_ROT_ANGLES || L.rotation_mode == JF_ROT_XYZ || L.rotation_mode == JF_ROT_QUATERNION) {
+                c.add_rotation = 1; c.hh_iter = 0; c.rot_mode = L.rotation_mode;
+                n_hh = L.rotation_mode == JF_ROT_QUATERNION ? 4 : 3;
+                c.n_rot = n_hh;
+            } else if (L.rotation_mode != JF_ROT_HOUSEHOLDER) {
+                return JF_ERR_UNSUPPORTED;
+            }
+            if (L.width_mode < JF_KAPPA_DIRECT_LOG || L.width_mode > JF_KAPPA_QUATVEC_SQUARED) return JF_ERR_BAD_DESC;
+            c.kappa_mode = L.width_mode; c.kappa_clamp = L.width_clamp != 0;
+            if ((c.kappa_mode == JF_KAPPA_MU || c.kappa_mode == JF_KAPPA_MU_SQUARED) && c.rot_mode != JF_ROT_XYZ) return JF_ERR_BAD_DESC;
+            if ((c.kappa_mode == JF_KAPPA_QUATVEC || c.kappa_mode == JF_KAPPA_QUATVEC_SQUARED) && c.rot_mode != JF_ROT_QUATERNION)
+                return JF_ERR_BAD_DESC;
+            if (c.kappa_mode >= JF_KAPPA_MU) n_hh -= 1;      // no kappa parameter of its own: "expect = n_hh + 1" below
             c.z_sign = L.z_sign; c.min_kappa = L.min_kappa;
             if (L.n_vertical < 0 || L.n_circular < 0 || L.n_vertical + L.n_circular > JF_MAX_NESTED) return JF_ERR_BAD_DESC;
             if (n_sp + L.n_vertical + L.n_circular > kS2MaxSplines) return JF_ERR_UNSUPPORTED;

@@ -40,6 +40,8 @@ JF_DEVINL void s2_from_embedding(const T* e, T& theta, T& phi, T& logdet) {
 // one layer of an S2 sub-pdf: "f" (JF_LAYER_FVM) or "v" (JF_LAYER_EXPMAP)
 struct FvmLayerC {
     int kind, add_rotation, hh_iter, first, raw_off;
+    int rot_mode, n_rot;                            // f: JF_ROT_* of sphere_base.py:112-240 and its parameter count
+    int kappa_mode, kappa_clamp;                    // f: JF_KAPPA_* (fvm_2d.py:108-138, :289-330)
     int v_first, n_vertical, c_first, n_circular;   // f: nested spline sub-flows (indices into S2Args::splines)
     int K, natural_direction, max_iter;             // v: components / direction / iteration cap
     int pot, pad_pot;                               // v: JF_POT_*
@@ -101,20 +103,94 @@ JF_DEVINL void s2_rotate(T* e, int n_iter, bool transpose, const T* p, int64_t s
     }
 }
 
+// 3x3 rotation matrix of the non-Householder modes (reference sphere_base.py:127-216): "angles" = three Givens rotations
+// over the index pairs (0,1), (0,2), (1,2) multiplied from the left, "xyz" = the rotation that takes the z axis to the
+// normalised parameter vector, "quaternion" = the rotation of the (unnormalised) quaternion (a, i, j, k)
+template <typename T>
+JF_DEVINL void s2_rot_matrix(int mode, const T* p, int64_t sj, T (&M)[3][3]) {
+    if (mode == JF_ROT_ANGLES) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i][j] = i == j ? T(1) : T(0);
+        const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
+        for (int ind = 0; ind < 3; ++ind) {
+            T sn, cs;
+            sincos(p[(int64_t)ind * sj], &sn, &cs);
+            const int a = pa[ind], b = pb[ind];
+            for (int j = 0; j < 3; ++j) {                                // M <- G M: rows a and b mix
+                const T ra = M[a][j], rb = M[b][j];
+                M[a][j] = cs * ra + sn * rb;
+                M[b][j] = -sn * ra + cs * rb;
+            }
+        }
+    } else if (mode == JF_ROT_XYZ) {
+        T nx = p[0], ny = p[sj], nz = p[2 * sj];
+        const T inv = T(1) / sqrt(nx * nx + ny * ny + nz * nz);
+        nx *= inv; ny *= inv; nz *= inv;
+        const T q = T(1) + nz;
+        M[0][0] = T(1) - nx * nx / q; M[0][1] = -nx * ny / q;       M[0][2] = nx;
+        M[1][0] = -nx * ny / q;       M[1][1] = T(1) - ny * ny / q; M[1][2] = ny;
+        M[2][0] = -nx;                M[2][1] = -ny;                M[2][2] = nz;
+    } else {
+        const T a = p[0], i = p[sj], j = p[2 * sj], k = p[3 * sj];
+        const T n2 = a * a + i * i + j * j + k * k;
+        M[0][0] = T(1) - T(2) * (j * j + k * k) / n2; M[0][1] = T(2) * (i * j - a * k) / n2;       M[0][2] = T(2) * (i * k + j * a) / n2;
+        M[1][0] = T(2) * (i * j + a * k) / n2;       M[1][1] = T(1) - T(2) * (i * i + k * k) / n2; M[1][2] = T(2) * (j * k - i * a) / n2;
+        M[2][0] = T(2) * (i * k - j * a) / n2;       M[2][1] = T(2) * (j * k + i * a) / n2;       M[2][2] = T(1) - T(2) * (i * i + j * j) / n2;
+    }
+}
+
+// rotation of the "f" layer in embedding space: Householder reflections (default) or one of the matrix modes;
+// transpose = inverse rotation (log_pdf direction, sphere_base.py:621)
+template <typename T>
+JF_DEVINL void fvm_rotate(T* e, const FvmLayerC& c, bool transpose, const T* p, int64_t sj) {
+    if (c.rot_mode == JF_ROT_HOUSEHOLDER) { s2_rotate(e, c.hh_iter, transpose, p, sj); return; }
+    T M[3][3];
+    s2_rot_matrix(c.rot_mode, p, sj, M);
+    const T x0 = e[0], x1 = e[1], x2 = e[2];
+    if (transpose) {
+        e[0] = M[0][0] * x0 + M[1][0] * x1 + M[2][0] * x2;
+        e[1] = M[0][1] * x0 + M[1][1] * x1 + M[2][1] * x2;
+        e[2] = M[0][2] * x0 + M[1][2] * x1 + M[2][2] * x2;
+    } else {
+        e[0] = M[0][0] * x0 + M[0][1] * x1 + M[0][2] * x2;
+        e[1] = M[1][0] * x0 + M[1][1] * x1 + M[1][2] * x2;
+        e[2] = M[2][0] * x0 + M[2][1] * x1 + M[2][2] * x2;
+    }
+}
+
+// concentration of the "f" layer (reference fvm_2d.py:108-138 and :289-330): from its own raw parameter (three
+// link functions, optionally clamped from below at -5) or from the norm of the rotation parameters
+template <typename T>
+JF_DEVINL T fvm_kappa(const FvmLayerC& c, const T* pl, int64_t sj) {
+    if (c.kappa_mode >= JF_KAPPA_MU) {
+        const int i0 = (c.kappa_mode == JF_KAPPA_MU || c.kappa_mode == JF_KAPPA_MU_SQUARED) ? 0 : 1;
+        T s2 = 0;
+        for (int i = i0; i < i0 + 3; ++i) { const T v = pl[(int64_t)i * sj]; s2 = fma(v, v, s2); }
+        return (c.kappa_mode == JF_KAPPA_MU || c.kappa_mode == JF_KAPPA_QUATVEC) ? sqrt(s2) : s2;
+    }
+    T raw = pl[(int64_t)c.n_rot * sj];
+    if (c.kappa_mode == JF_KAPPA_LOG_BOUNDED) {
+        const T spl = raw > T(20) ? raw : log1p(exp(raw));               // F.softplus (threshold 20); clamping at -5 never binds
+        return exp(spl + log(T(c.min_kappa)));
+    }
+    if (c.kappa_clamp) raw = tmax(raw, T(-5));
+    if (c.kappa_mode == JF_KAPPA_SOFTPLUS) return (raw > T(20) ? raw : log1p(exp(raw))) + T(c.min_kappa);
+    return exp(raw) + T(c.min_kappa);
+}
+
 // log_pdf direction: reference sphere_base.py:601-650 + fvm_2d.py:273-500 (+ sphere_to_plane :496-513, :416-430)
 template <typename T>
 JF_DEVINL void fvm_logpdf(T& c0, T& c1, T& logdet, const FvmLayerC& c, const SplineC<T>* sp, const T* p, int64_t sj,
                           int& oor) {
     T theta = c0, phi = c1;
     const T* pl = p + (int64_t)c.raw_off * sj;
-    const int n_hh = c.add_rotation ? c.hh_iter * 3 : 0;
+    const int n_hh = c.n_rot + (c.kappa_mode >= JF_KAPPA_MU ? -1 : 0);   // (+1 below: the layer's own kappa parameter, if any)
     if (c.add_rotation) {
         T e[3];
         s2_to_embedding(theta, phi, e, logdet);
-        s2_rotate(e, c.hh_iter, true, pl, sj);
+        fvm_rotate(e, c, true, pl, sj);
         s2_from_embedding(e, theta, phi, logdet);
     }
-    const T kappa = exp(pl[(int64_t)n_hh * sj]) + T(c.min_kappa);
+    const T kappa = fvm_kappa(c, pl, sj);
     const T s = T(c.z_sign);
     const T ct = cos(theta);
     logdet += log(sin(safe_angle(theta)));
@@ -151,7 +227,7 @@ JF_DEVINL void fvm_sample(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
                           int& oor) {
     T theta, phi;
     const T* pl = p + (int64_t)c.raw_off * sj;
-    const int n_hh = c.add_rotation ? c.hh_iter * 3 : 0;
+    const int n_hh = c.n_rot + (c.kappa_mode >= JF_KAPPA_MU ? -1 : 0);
     if (c.first) {
         const T r = sqrt(c0 * c0 + c1 * c1);
         const T arg = (r == T(0)) ? T(1) : c0 / r;
@@ -163,7 +239,7 @@ JF_DEVINL void fvm_sample(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
         theta = c0;
         phi = c1;
     }
-    const T kappa = exp(pl[(int64_t)n_hh * sj]) + T(c.min_kappa);
+    const T kappa = fvm_kappa(c, pl, sj);
     const T s = T(c.z_sign);
     T ct = cos(theta);
     logdet += log(sin(safe_angle(theta)));
@@ -179,7 +255,7 @@ JF_DEVINL void fvm_sample(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
     if (c.add_rotation) {
         T e[3];
         s2_to_embedding(theta, phi, e, logdet);
-        s2_rotate(e, c.hh_iter, false, pl, sj);
+        fvm_rotate(e, c, false, pl, sj);
         s2_from_embedding(e, theta, phi, logdet);
     }
     c0 = theta;

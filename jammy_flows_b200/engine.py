@@ -75,6 +75,11 @@ def fill_layer_desc(ld, desc, param_offset):
     elif desc["code"] == "f":
         ld.kind = _cabi.JF_LAYER_FVM
         ld.hh_iter = desc["hh_iter"] if desc["add_rotation"] else 0
+        ld.rotation_mode = {"householder": _cabi.JF_ROT_HOUSEHOLDER, "angles": _cabi.JF_ROT_ANGLES, "xyz": _cabi.JF_ROT_XYZ,
+                            "quaternion": _cabi.JF_ROT_QUATERNION}[desc.get("rotation_mode", "householder")] \
+            if desc["add_rotation"] else _cabi.JF_ROT_HOUSEHOLDER
+        ld.width_mode = desc.get("kappa_mode", 0)
+        ld.width_clamp = desc.get("kappa_clamping", 0)
         ld.first = desc["first"]
         ld.z_sign = desc["z_sign"]
         ld.min_kappa = desc["min_kappa"]

@@ -442,6 +442,10 @@ class mvn_block(layer_base):
 # =====================================================================================================================
 # S2: Fisher-von-Mises layer "f" (reference defaults: Householder rotation + vMF z-scaling)
 # =====================================================================================================================
+KAPPA_MODES = {"direct_log_real_bounded": 0, "softplus_real_bounded": 1, "log_bounded": 2, "mu": 3, "mu_squared": 4,
+               "quatvec": 5, "quatvec_squared": 6}
+
+
 class fisher_von_mises_2d(layer_base):
     """Symbol "f" (and the "n" alias).
 
@@ -468,10 +472,17 @@ class fisher_von_mises_2d(layer_base):
         unsupported = []
         if add_correlated_rq_spline_flow:
             unsupported.append("correlated rq-spline sub-flow (needs the AmortizableMLP path, SURVEY.md section 8f rank 4)")
-        if kappa_prediction != "direct_log_real_bounded" or kappa_clamping:
-            unsupported.append("kappa_prediction=%s kappa_clamping=%d" % (kappa_prediction, kappa_clamping))
-        if add_rotation and rotation_mode != "householder":
-            unsupported.append("rotation_mode=%s" % rotation_mode)
+        if kappa_prediction not in KAPPA_MODES:
+            raise Exception("Unknown kappa_prediction: %s" % kappa_prediction)
+        if add_rotation and rotation_mode not in ("householder", "angles", "xyz", "quaternion"):
+            raise Exception("Unknown rotation mode for spheres: ", rotation_mode)
+        # reference fvm_2d.py:133-138
+        if kappa_prediction in ("mu", "mu_squared"):
+            assert (add_rotation)
+            assert (rotation_mode == "xyz")
+        if kappa_prediction in ("quatvec", "quatvec_squared"):
+            assert (add_rotation)
+            assert (rotation_mode == "quaternion"), ("ROTATION MODE?!", rotation_mode)
         if add_extra_rotation_inbetween:
             unsupported.append("add_extra_rotation_inbetween=1")
         if boundary_cos_theta_identity_region != 0.0:
@@ -492,16 +503,28 @@ class fisher_von_mises_2d(layer_base):
         self.min_kappa = min_kappa
         self.num_householder_params = 0
         self.num_householder_iter = 0
+        self.kappa_prediction, self.kappa_clamping = kappa_prediction, kappa_clamping
         if add_rotation:
-            self.num_householder_iter = dimension + 1 if num_householder_iter == -1 else num_householder_iter
-            self.num_householder_params = self.num_householder_iter * (dimension + 1)
-        # RNG order as in the reference: sphere_base (householder) first, then kappa
+            # reference sphere_base.py:79-105 ("householder params stands for any rotation params here")
+            if rotation_mode == "angles":
+                self.num_householder_params = int(((dimension + 1) * dimension) / 2)
+            elif rotation_mode == "xyz":
+                self.num_householder_params = 3
+            elif rotation_mode == "quaternion":
+                self.num_householder_params = 4
+            else:
+                self.num_householder_iter = dimension + 1 if num_householder_iter == -1 else num_householder_iter
+                self.num_householder_params = self.num_householder_iter * (dimension + 1)
+        # RNG order as in the reference: sphere_base (rotation) first, then kappa
         if use_permanent_parameters and self.num_householder_params > 0:
             self.householder_params = nn.Parameter(torch.randn((1, self.num_householder_params)))
         self.total_param_num += self.num_householder_params
-        if use_permanent_parameters:
-            self.loglike_kappa = nn.Parameter(torch.randn(1).unsqueeze(0))
-        self.total_param_num += 1
+        # reference fvm_2d.py:140-146: the norm-of-the-rotation-vector predictions have no kappa parameter of their own
+        self.num_loglike_kappa_params = 1 if KAPPA_MODES[kappa_prediction] <= 2 else 0
+        if self.num_loglike_kappa_params:
+            if use_permanent_parameters:
+                self.loglike_kappa = nn.Parameter(torch.randn(1).unsqueeze(0))
+            self.total_param_num += 1
 
         # nested pass-through sub-flows (reference fvm_2d.py:158-225: `pdf("i1_-1.00_1.00", vertical_flow_defs, ...)`
         # and `pdf("s1", circular_flow_defs, ...)` with amortize_everything / use_as_passthrough_instead_of_pdf).
@@ -551,7 +574,8 @@ class fisher_von_mises_2d(layer_base):
         par_list = []
         if self.num_householder_params > 0:
             par_list.append(torch.randn((self.num_householder_params)))
-        par_list.append(torch.randn((1)) - 3.0)
+        if self.num_loglike_kappa_params:
+            par_list.append(torch.randn((1)) - 3.0)
         par_list += [l.get_desired_init_parameters() for l in self.vertical_layers]
         par_list += [l.get_desired_init_parameters() for l in self.circular_layers]
         return torch.cat(par_list)
@@ -561,15 +585,18 @@ class fisher_von_mises_2d(layer_base):
         n = self.num_householder_params
         if self.add_rotation:
             self.householder_params.data = params[:n].reshape(1, n)
-        self.loglike_kappa.data = params[n:n + 1].reshape(1, 1)
+        k = self.num_loglike_kappa_params
+        if k:
+            self.loglike_kappa.data = params[n:n + 1].reshape(1, 1)
         nv, nc = self.total_num_vertical_params, self.total_num_circular_params
         if self.add_vertical_rq_spline_flow:
-            self.vertical_flow_params.data = params[n + 1:n + 1 + nv].reshape(1, nv)
+            self.vertical_flow_params.data = params[n + k:n + k + nv].reshape(1, nv)
         if self.add_circular_rq_spline_flow:
-            self.circular_flow_params.data = params[n + 1 + nv:n + 1 + nv + nc].reshape(1, nc)
+            self.circular_flow_params.data = params[n + k + nv:n + k + nv + nc].reshape(1, nc)
 
     def permanent_param_names(self):
-        names = (["householder_params"] if self.num_householder_params > 0 else []) + ["loglike_kappa"]
+        names = (["householder_params"] if self.num_householder_params > 0 else []) + \
+                (["loglike_kappa"] if self.num_loglike_kappa_params else [])
         if self.add_vertical_rq_spline_flow:
             names.append("vertical_flow_params")
         if self.add_circular_rq_spline_flow:
@@ -585,6 +612,8 @@ class fisher_von_mises_2d(layer_base):
             circular.append(dict(l.spline_spec(), param_offset=off))
             off += l.total_param_num
         return dict(code="f", dim=2, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
+                    rotation_mode=self.rotation_mode, n_rot=int(self.num_householder_params),
+                    kappa_mode=KAPPA_MODES[self.kappa_prediction], kappa_clamping=int(self.kappa_clamping),
                     z_sign=float(self.z_scaling_factor), min_kappa=float(self.min_kappa),
                     first=int(self.euclidean_to_sphere_as_first), vertical=vertical, circular=circular,
                     n_params=self.total_param_num)

@@ -49,6 +49,42 @@ def householder_matrix(vs):
     return q
 
 
+def s2_rotation_matrix(mode, p):
+    """Rotation matrix of the non-Householder modes of the sphere layers.  p: [B, n] rotation parameters.
+    Reference: layers/spheres/sphere_base.py:127-216 ("angles": Givens rotations over itertools.combinations(range(3), 2)
+    multiplied from the left; "xyz": z axis onto the normalised vector; "quaternion": unnormalised quaternion a,i,j,k)."""
+    b = p.shape[0]
+    if mode == "angles":
+        m = torch.eye(3, dtype=p.dtype).unsqueeze(0).repeat(b, 1, 1)
+        for ind, (a_, b_) in enumerate(((0, 1), (0, 2), (1, 2))):
+            g = torch.eye(3, dtype=p.dtype).unsqueeze(0).repeat(b, 1, 1)
+            g[:, a_, a_] = torch.cos(p[:, ind])
+            g[:, b_, b_] = g[:, a_, a_]
+            g[:, a_, b_] = torch.sin(p[:, ind])
+            g[:, b_, a_] = -g[:, a_, b_]
+            m = torch.bmm(g, m)
+        return m
+    if mode == "xyz":
+        n = p[:, :3] / (p[:, :3] ** 2).sum(dim=-1, keepdim=True).sqrt()
+        nx, ny, nz = n[:, 0], n[:, 1], n[:, 2]
+        m = torch.zeros(b, 3, 3, dtype=p.dtype)
+        m[:, 0, 0] = 1.0 - nx ** 2 / (1 + nz); m[:, 1, 1] = 1.0 - ny ** 2 / (1 + nz); m[:, 2, 2] = nz
+        m[:, 0, 1] = -nx * ny / (1 + nz); m[:, 1, 2] = ny
+        m[:, 1, 0] = -nx * ny / (1 + nz); m[:, 2, 1] = -ny
+        m[:, 0, 2] = nx; m[:, 2, 0] = -nx
+        return m
+    if mode == "quaternion":
+        n2 = (p[:, :4] ** 2).sum(dim=-1)
+        a, i, j, k = p[:, 0], p[:, 1], p[:, 2], p[:, 3]
+        m = torch.zeros(b, 3, 3, dtype=p.dtype)
+        m[:, 0, 0] = 1 - 2 * (j ** 2 + k ** 2) / n2; m[:, 1, 1] = 1 - 2 * (i ** 2 + k ** 2) / n2; m[:, 2, 2] = 1 - 2 * (i ** 2 + j ** 2) / n2
+        m[:, 0, 1] = 2 * (i * j - a * k) / n2; m[:, 1, 2] = 2 * (j * k - i * a) / n2
+        m[:, 1, 0] = 2 * (i * j + a * k) / n2; m[:, 2, 1] = 2 * (j * k + i * a) / n2
+        m[:, 0, 2] = 2 * (i * k + j * a) / n2; m[:, 2, 0] = 2 * (i * k - j * a) / n2
+        return m
+    raise ValueError(mode)
+
+
 def _safe_angle(x, margin=1e-7):
     """Reference: layers/spheres/sphere_base.py:8-19."""
     return torch.clamp(x, min=margin, max=math.pi - margin)
@@ -901,9 +937,15 @@ class FvmLayer:
         """Reference: fvm_2d.py:267-271."""
         return torch.where(c <= 0, 6 * c ** 5 + 15 * c ** 4 + 10 * c ** 3 + 1.0, -6 * c ** 5 + 15 * c ** 4 - 10 * c ** 3 + 1.0)
 
+    def _n_rot(self):
+        if not self.s["add_rotation"]:
+            return 0
+        mode = self.s.get("rotation_mode", "householder")
+        return {"householder": self.s["hh_iter"] * 3, "angles": 3, "xyz": 3, "quaternion": 4}[mode]
+
     def _sub_params(self, p):
-        n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
-        o = n_hh + 1
+        n_hh = self._n_rot()
+        o = n_hh + (1 if self.s.get("kappa_mode", 0) <= 2 else 0)
         nv = sum(v.s["n_w"] + v.s["n_h"] + v.s["n_d"] for v in self.vertical)
         nc = sum(v.s["n_w"] + v.s["n_h"] + v.s["n_d"] for v in self.circular)
         return p[:, o:o + nv], p[:, o + nv:o + nv + nc]
@@ -936,9 +978,30 @@ class FvmLayer:
         return x, log_det
 
     def _split(self, p):
-        n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
-        q = householder_matrix(p[:, :n_hh].reshape(-1, self.s["hh_iter"], 3)) if n_hh > 0 else None
-        kappa = torch.exp(p[:, n_hh:n_hh + 1]) + self.s["min_kappa"]          # fvm_2d.py:123
+        n_hh = self._n_rot()
+        mode = self.s.get("rotation_mode", "householder")
+        q = None
+        if n_hh > 0:
+            q = (householder_matrix(p[:, :n_hh].reshape(-1, self.s["hh_iter"], 3)) if mode == "householder"
+                 else s2_rotation_matrix(mode, p[:, :n_hh]))
+        # concentration: fvm_2d.py:108-138 (link functions) and :289-330 (norm of the rotation parameters)
+        km, clamp = self.s.get("kappa_mode", 0), self.s.get("kappa_clamping", 0)
+        raw = p[:, n_hh:n_hh + 1]
+        if km == 0:
+            kappa = torch.exp(torch.clamp(raw, min=-5.0) if clamp else raw) + self.s["min_kappa"]
+        elif km == 1:
+            kappa = F.softplus(torch.clamp(raw, min=-5.0) if clamp else raw) + self.s["min_kappa"]
+        elif km == 2:
+            sp = F.softplus(raw)
+            kappa = ((torch.clamp(sp, min=-5.0) if clamp else sp) + math.log(self.s["min_kappa"])).exp()
+        elif km == 3:
+            kappa = (p[:, :3] ** 2).sum(dim=-1, keepdim=True).sqrt()
+        elif km == 4:
+            kappa = (p[:, :3] ** 2).sum(dim=-1, keepdim=True)
+        elif km == 5:
+            kappa = (p[:, 1:4] ** 2).sum(dim=-1, keepdim=True).sqrt()
+        else:
+            kappa = (p[:, 1:4] ** 2).sum(dim=-1, keepdim=True)
         return q, kappa
 
     # log_pdf direction.  Reference: sphere_base.py:601-650 + fvm_2d.py:273-500

@@ -88,6 +88,23 @@ CASES = {
                         opts={"g": {"fit_normalization": 0}}),
     "g_e5_k7_cond_f32": dict(pdf_defs="e5", flow_defs="gg", n=500, cond_dim=2, perturb=0.03, dtype="float32",
                              opts={"g": {"num_kde": 7}}),
+    # "f": rotation modes of sphere_base.py:79-91 and the kappa predictions of fvm_2d.py:108-138 -- the reference's own
+    # sweep (tests/test_general.py:123-172) plus the two remaining link functions with kappa_clamping
+    "f_rot_angles": dict(pdf_defs="s2", flow_defs="f", n=500, perturb=0.5, opts={"f": {"rotation_mode": "angles"}}),
+    "f_rot_xyz_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3, opts={"f": {"rotation_mode": "xyz"}}),
+    "f_rot_xyz_mu": dict(pdf_defs="s2", flow_defs="f", n=500, perturb=0.5,
+                         opts={"f": {"rotation_mode": "xyz", "kappa_prediction": "mu"}}),
+    "f_rot_xyz_mu_squared_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3,
+                                      opts={"f": {"rotation_mode": "xyz", "kappa_prediction": "mu_squared"}}),
+    "f_rot_quat": dict(pdf_defs="s2", flow_defs="f", n=500, perturb=0.5, opts={"f": {"rotation_mode": "quaternion"}}),
+    "f_rot_quat_quatvec_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3,
+                                    opts={"f": {"rotation_mode": "quaternion", "kappa_prediction": "quatvec"}}),
+    "f_rot_quat_quatvec_squared": dict(pdf_defs="s2", flow_defs="f", n=500, perturb=0.5,
+                                       opts={"f": {"rotation_mode": "quaternion", "kappa_prediction": "quatvec_squared"}}),
+    "f_kappa_softplus_clamp": dict(pdf_defs="s2", flow_defs="f", n=500, perturb=0.5,
+                                   opts={"f": {"kappa_prediction": "softplus_real_bounded", "kappa_clamping": 1}}),
+    "f_kappa_log_bounded_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3,
+                                     opts={"f": {"kappa_prediction": "log_bounded", "min_kappa": 1e-3}}),
     "s2_f_uncond": dict(pdf_defs="s2", flow_defs="f", n=1000, perturb=0.5),
     "s2_f_cond": dict(pdf_defs="s2", flow_defs="f", n=1000, cond_dim=2, perturb=0.3),
     # BASELINE.json configs[2]: s2 "f" with smooth vMF-scaled spline sub-flows + i1 "r" (docs/suggested_settings.rst:52-73)
