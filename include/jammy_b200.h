@@ -182,7 +182,8 @@ typedef struct JfLayerDesc {
     int32_t rotation_mode; /* g, f: JF_ROT_* (0 = Householder, the default) */
     int32_t width_mode;    /* g: JF_WIDTH_* ; f: JF_KAPPA_* */
     int32_t width_clamp;   /* g: clamp_widths: raw width parameter clamped into [clamp_lo, clamp_hi] first; f: kappa_clamping */
-    int32_t skew;          /* g: add_skewness (one more K*d block of log skew exponents at the end of the slice) */
+    int32_t skew;          /* g: add_skewness (one more K*d block of log skew exponents at the end of the slice);
+                              f: add_extra_rotation_inbetween (fvm_2d.py:381-402) */
     int32_t center_mean;   /* g: only K-1 means per dimension are parameters (gaussianization_flow.py:841-848) */
     int32_t stretch;       /* g: JF_STRETCH_* */
     double w_min, w_max; /* g: width bounds (gaussianization_flow.py:300-317) */
@@ -190,7 +191,7 @@ typedef struct JfLayerDesc {
     double z_sign;       /* f: z_scaling_factor (+1/-1, fvm_2d.py:96-99) */
     double min_kappa;    /* f: kappa = exp(raw) + min_kappa (fvm_2d.py:123) */
     double lo, hi;       /* r: interval boundaries */
-    double clamp_lo, clamp_hi; /* g: see width_clamp (clamp_hi may be +inf) */
+    double clamp_lo, clamp_hi; /* g: see width_clamp (clamp_hi may be +inf); f: clamp_lo = boundary_cos_theta_identity_region */
     JfSplineDesc spline[JF_MAX_NESTED]; /* r, o: spline[0]; f: nested sub-flows */
 } JfLayerDesc;
 

@@ -242,6 +242,8 @@ static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaS
             }
             if (L.width_mode < JF_KAPPA_DIRECT_LOG || L.width_mode > JF_KAPPA_QUATVEC_SQUARED) return JF_ERR_BAD_DESC;
             c.kappa_mode = L.width_mode; c.kappa_clamp = L.width_clamp != 0;
+            c.extra_rot = L.skew != 0; c.identity_region = L.clamp_lo;
+            if (!(L.clamp_lo >= 0.0 && L.clamp_lo < 1.0)) return JF_ERR_BAD_DESC;
             if ((c.kappa_mode == JF_KAPPA_MU || c.kappa_mode == JF_KAPPA_MU_SQUARED) && c.rot_mode != JF_ROT_XYZ) return JF_ERR_BAD_DESC;
             if ((c.kappa_mode == JF_KAPPA_QUATVEC || c.kappa_mode == JF_KAPPA_QUATVEC_SQUARED) && c.rot_mode != JF_ROT_QUATERNION)
                 return JF_ERR_BAD_DESC;

@@ -42,6 +42,8 @@ struct FvmLayerC {
     int kind, add_rotation, hh_iter, first, raw_off;
     int rot_mode, n_rot;                            // f: JF_ROT_* of sphere_base.py:112-240 and its parameter count
     int kappa_mode, kappa_clamp;                    // f: JF_KAPPA_* (fvm_2d.py:108-138, :289-330)
+    int extra_rot;                                  // f: add_extra_rotation_inbetween (fvm_2d.py:381-402, :664-688)
+    double identity_region;                         // f: boundary_cos_theta_identity_region (fvm_2d.py:404-436, :573-612)
     int v_first, n_vertical, c_first, n_circular;   // f: nested spline sub-flows (indices into S2Args::splines)
     int K, natural_direction, max_iter;             // v: components / direction / iteration cap
     int pot, pad_pot;                               // v: JF_POT_*
@@ -177,6 +179,22 @@ JF_DEVINL T fvm_kappa(const FvmLayerC& c, const T* pl, int64_t sj) {
     return exp(raw) + T(c.min_kappa);
 }
 
+// the fixed rotation between the z-scaling and the spline sub-flows (add_extra_rotation_inbetween): cylinder -> angle ->
+// embedding -> M = [[0,0,1],[0,1,0],[-1,0,0]] (its transpose in the log_pdf direction) -> angle -> cylinder, with the
+// reference's chain of log-det updates (fvm_2d.py:381-402 / :664-688)
+template <typename T>
+JF_DEVINL void fvm_extra_rotation(T& ret, T& phi, T& logdet, bool transpose) {
+    T theta = acos(ret);
+    logdet -= log(sin(safe_angle(theta)));
+    T e[3];
+    s2_to_embedding(theta, phi, e, logdet);
+    const T x0 = e[0], x2 = e[2];
+    if (transpose) { e[0] = -x2; e[2] = x0; } else { e[0] = x2; e[2] = -x0; }
+    s2_from_embedding(e, theta, phi, logdet);
+    ret = cos(theta);
+    logdet += log(sin(safe_angle(theta)));
+}
+
 // log_pdf direction: reference sphere_base.py:601-650 + fvm_2d.py:273-500 (+ sphere_to_plane :496-513, :416-430)
 template <typename T>
 JF_DEVINL void fvm_logpdf(T& c0, T& c1, T& logdet, const FvmLayerC& c, const SplineC<T>* sp, const T* p, int64_t sj,
@@ -201,8 +219,14 @@ JF_DEVINL void fvm_logpdf(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
     if (kappa < Num<T>::kappa_identity) ret = ct;
     ret = safe_costheta(ret, Num<T>::safe_costheta);
     const T* psub = pl + (int64_t)(n_hh + 1) * sj;     // spline parameters follow kappa (fvm_2d.py:311-316)
-    if (c.n_circular > 0) phi = fvm_circular<T>(c, sp, true, phi, fvm_window(ret), logdet, psub, sj, oor);
-    if (c.n_vertical > 0) ret = safe_costheta(fvm_vertical<T>(c, sp, true, ret, logdet, psub, sj, oor), Num<T>::safe_costheta);
+    if (c.extra_rot) fvm_extra_rotation(ret, phi, logdet, true);
+    // sub-flows act only inside the identity region's complement (all rows when the region is 0)
+    const bool contained = c.identity_region == 0.0 || (ret > T(-1.0 + c.identity_region) && ret < T(1.0 - c.identity_region));
+    if (contained) {
+        if (c.n_circular > 0) phi = fvm_circular<T>(c, sp, true, phi, fvm_window(ret), logdet, psub, sj, oor);
+        if (c.n_vertical > 0) ret = fvm_vertical<T>(c, sp, true, ret, logdet, psub, sj, oor);
+    }
+    ret = safe_costheta(ret, Num<T>::safe_costheta);
     theta = acos(ret);
     logdet -= log(sin(safe_angle(theta)));
     if (c.first) {
@@ -244,8 +268,12 @@ JF_DEVINL void fvm_sample(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
     T ct = cos(theta);
     logdet += log(sin(safe_angle(theta)));
     const T* psub = pl + (int64_t)(n_hh + 1) * sj;
-    if (c.n_vertical > 0) ct = fvm_vertical<T>(c, sp, false, ct, logdet, psub, sj, oor);                       // fvm_2d.py:591
-    if (c.n_circular > 0) phi = fvm_circular<T>(c, sp, false, phi, fvm_window(ct), logdet, psub, sj, oor);     // :595-607
+    const bool contained = c.identity_region == 0.0 || (ct > T(-1.0 + c.identity_region) && ct < T(1.0 - c.identity_region));
+    if (contained) {
+        if (c.n_vertical > 0) ct = fvm_vertical<T>(c, sp, false, ct, logdet, psub, sj, oor);                       // fvm_2d.py:591
+        if (c.n_circular > 0) phi = fvm_circular<T>(c, sp, false, phi, fvm_window(ct), logdet, psub, sj, oor);     // :595-607
+    }
+    if (c.extra_rot) fvm_extra_rotation(ct, phi, logdet, false);
     logdet -= log(kappa * s * ct + kappa / tanh(kappa));
     T ret = s * (T(1) + (T(1) / kappa) * log(T(0.5) * (T(1) + s * ct) + (T(0.5) - T(0.5) * s * ct) * exp(T(-2) * kappa)));
     if (kappa < Num<T>::kappa_identity) ret = ct;

@@ -80,6 +80,8 @@ def fill_layer_desc(ld, desc, param_offset):
             if desc["add_rotation"] else _cabi.JF_ROT_HOUSEHOLDER
         ld.width_mode = desc.get("kappa_mode", 0)
         ld.width_clamp = desc.get("kappa_clamping", 0)
+        ld.skew = desc.get("extra_rotation", 0)
+        ld.clamp_lo = desc.get("identity_region", 0.0)
         ld.first = desc["first"]
         ld.z_sign = desc["z_sign"]
         ld.min_kappa = desc["min_kappa"]

@@ -483,10 +483,8 @@ class fisher_von_mises_2d(layer_base):
         if kappa_prediction in ("quatvec", "quatvec_squared"):
             assert (add_rotation)
             assert (rotation_mode == "quaternion"), ("ROTATION MODE?!", rotation_mode)
-        if add_extra_rotation_inbetween:
-            unsupported.append("add_extra_rotation_inbetween=1")
-        if boundary_cos_theta_identity_region != 0.0:
-            unsupported.append("boundary_cos_theta_identity_region")
+        if not (0.0 <= boundary_cos_theta_identity_region < 1.0):
+            raise Exception("boundary_cos_theta_identity_region must be in [0, 1)")
         if add_circular_rq_spline_flow and circular_add_rotation:
             # reference fvm_2d.py:207 asserts the same
             raise AssertionError("Currently not allowing additional S-1 rotations (circular_add_rotation must be 0)")
@@ -504,6 +502,8 @@ class fisher_von_mises_2d(layer_base):
         self.num_householder_params = 0
         self.num_householder_iter = 0
         self.kappa_prediction, self.kappa_clamping = kappa_prediction, kappa_clamping
+        self.add_extra_rotation_inbetween = add_extra_rotation_inbetween
+        self.boundary_cos_theta_identity_region = boundary_cos_theta_identity_region
         if add_rotation:
             # reference sphere_base.py:79-105 ("householder params stands for any rotation params here")
             if rotation_mode == "angles":
@@ -614,6 +614,8 @@ class fisher_von_mises_2d(layer_base):
         return dict(code="f", dim=2, add_rotation=int(self.add_rotation), hh_iter=self.num_householder_iter,
                     rotation_mode=self.rotation_mode, n_rot=int(self.num_householder_params),
                     kappa_mode=KAPPA_MODES[self.kappa_prediction], kappa_clamping=int(self.kappa_clamping),
+                    extra_rotation=int(self.add_extra_rotation_inbetween),
+                    identity_region=float(self.boundary_cos_theta_identity_region),
                     z_sign=float(self.z_scaling_factor), min_kappa=float(self.min_kappa),
                     first=int(self.euclidean_to_sphere_as_first), vertical=vertical, circular=circular,
                     n_params=self.total_param_num)

@@ -937,6 +937,18 @@ class FvmLayer:
         """Reference: fvm_2d.py:267-271."""
         return torch.where(c <= 0, 6 * c ** 5 + 15 * c ** 4 + 10 * c ** 3 + 1.0, -6 * c ** 5 + 15 * c ** 4 - 10 * c ** 3 + 1.0)
 
+    @staticmethod
+    def _extra_rotation(ret, angle, log_det, transpose):
+        """add_extra_rotation_inbetween: cylinder -> angles -> embedding -> fixed matrix -> angles -> cylinder."""
+        th = torch.acos(ret)
+        log_det = log_det - torch.log(torch.sin(_safe_angle(th[:, 0])))
+        e, log_det = s2_to_embedding(torch.cat([th, angle], dim=1), log_det)
+        m = torch.tensor([[0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [-1.0, 0.0, 0.0]], dtype=ret.dtype)
+        e = torch.einsum("ij,bj->bi", m.t() if transpose else m, e)
+        comb, log_det = s2_from_embedding(e, log_det)
+        log_det = log_det + torch.log(torch.sin(_safe_angle(comb[:, 0])))
+        return torch.cos(comb[:, :1]), comb[:, 1:], log_det
+
     def _n_rot(self):
         if not self.s["add_rotation"]:
             return 0
@@ -1021,12 +1033,22 @@ class FvmLayer:
         ret = torch.where(kappa < (1e-4 if x.dtype == torch.float32 else 1e-8), ct, ret)
         ret = _safe_costheta(ret)
         angle = x[:, 1:]
+        if self.s.get("extra_rotation", 0):                                     # fvm_2d.py:381-402
+            ret, angle, log_det = self._extra_rotation(ret, angle, log_det, True)
         pv, pc = self._sub_params(p)
-        if len(self.circular) > 0:                                              # fvm_2d.py:413-427
-            angle, log_det = self._chain(self.circular, angle, log_det, pc.expand(x.shape[0], -1) * self._window(ret),
-                                         True, True)
-        if len(self.vertical) > 0:                                              # fvm_2d.py:430-432
-            ret, log_det = self._chain(self.vertical, ret, log_det, pv, True, False)
+        region = self.s.get("identity_region", 0.0)
+        # fvm_2d.py:404-470: with an identity region only the rows inside (-1 + region, 1 - region) pass the sub-flows
+        mask = (torch.ones_like(ret[:, 0], dtype=torch.bool) if region == 0.0
+                else ((ret > -1.0 + region) & (ret < 1.0 - region))[:, 0])
+        if len(self.circular) > 0 and bool(mask.any()):                         # fvm_2d.py:413-427
+            a2, l2 = self._chain(self.circular, angle[mask], log_det[mask],
+                                 (pc.expand(x.shape[0], -1) * self._window(ret))[mask], True, True)
+            angle, log_det = angle.clone(), log_det.clone()
+            angle[mask], log_det[mask] = a2, l2
+        if len(self.vertical) > 0 and bool(mask.any()):                         # fvm_2d.py:430-432
+            r2, l2 = self._chain(self.vertical, ret[mask], log_det[mask], pv.expand(x.shape[0], -1)[mask], True, False)
+            ret, log_det = ret.clone(), log_det.clone()
+            ret[mask], log_det[mask] = r2, l2
         ret = _safe_costheta(ret)
         theta = torch.acos(ret)
         log_det = log_det - torch.log(torch.sin(_safe_angle(theta[:, 0])))
@@ -1045,11 +1067,20 @@ class FvmLayer:
         log_det = log_det + torch.log(torch.sin(_safe_angle(x[:, 0])))
         angle = x[:, 1:]
         pv, pc = self._sub_params(p)
-        if len(self.vertical) > 0:                                              # fvm_2d.py:591-592
-            ct, log_det = self._chain(self.vertical, ct, log_det, pv, False, False)
-        if len(self.circular) > 0:                                              # fvm_2d.py:595-607
-            angle, log_det = self._chain(self.circular, angle, log_det, pc.expand(x.shape[0], -1) * self._window(ct),
-                                         False, True)
+        region = self.s.get("identity_region", 0.0)
+        mask = (torch.ones_like(ct[:, 0], dtype=torch.bool) if region == 0.0
+                else ((ct > -1.0 + region) & (ct < 1.0 - region))[:, 0])               # fvm_2d.py:612 (before the vertical flow)
+        if len(self.vertical) > 0 and bool(mask.any()):                         # fvm_2d.py:591-592
+            c2, l2 = self._chain(self.vertical, ct[mask], log_det[mask], pv.expand(x.shape[0], -1)[mask], False, False)
+            ct, log_det = ct.clone(), log_det.clone()
+            ct[mask], log_det[mask] = c2, l2
+        if len(self.circular) > 0 and bool(mask.any()):                         # fvm_2d.py:595-607
+            a2, l2 = self._chain(self.circular, angle[mask], log_det[mask],
+                                 (pc.expand(x.shape[0], -1) * self._window(ct))[mask], False, True)
+            angle, log_det = angle.clone(), log_det.clone()
+            angle[mask], log_det[mask] = a2, l2
+        if self.s.get("extra_rotation", 0):                                     # fvm_2d.py:664-688
+            ct, angle, log_det = self._extra_rotation(ct, angle, log_det, False)
         kappa = kappa.expand(x.shape[0], -1)
         log_det = log_det - torch.log(kappa * s * ct + kappa / torch.tanh(kappa))[:, 0]
         ret = s * (1.0 + (1.0 / kappa) * torch.log(0.5 * (1.0 + s * ct) + (0.5 - 0.5 * s * ct) * torch.exp(-2.0 * kappa)))

@@ -105,6 +105,12 @@ CASES = {
                                    opts={"f": {"kappa_prediction": "softplus_real_bounded", "kappa_clamping": 1}}),
     "f_kappa_log_bounded_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3,
                                      opts={"f": {"kappa_prediction": "log_bounded", "min_kappa": 1e-3}}),
+    "f_extra_rotation": dict(pdf_defs="s2", flow_defs="f", n=500, perturb=0.3,
+                             opts={"f": {"add_extra_rotation_inbetween": 1, "add_vertical_rq_spline_flow": 1,
+                                         "add_circular_rq_spline_flow": 1, "circular_add_rotation": 0}}),
+    "f_identity_region_cond": dict(pdf_defs="s2", flow_defs="f", n=500, cond_dim=2, perturb=0.3,
+                                   opts={"f": {"boundary_cos_theta_identity_region": 0.1, "add_vertical_rq_spline_flow": 1,
+                                               "add_circular_rq_spline_flow": 1, "circular_add_rotation": 0}}),
     "s2_f_uncond": dict(pdf_defs="s2", flow_defs="f", n=1000, perturb=0.5),
     "s2_f_cond": dict(pdf_defs="s2", flow_defs="f", n=1000, cond_dim=2, perturb=0.3),
     # BASELINE.json configs[2]: s2 "f" with smooth vMF-scaled spline sub-flows + i1 "r" (docs/suggested_settings.rst:52-73)
