@@ -562,6 +562,30 @@ static int mlp_forward_t(const JfMlpDesc* desc, const void* const* seg_ptrs, con
         else mlp_expand_kernel<T, 16><<<grid, 256, 0, st>>>(m);
         return check_launch();
     }
+    if (m.n_linear == 2 && m.dims[0] <= kSmMaxIn && m.dims[1] <= 128 && m.dims[2] <= kSmMaxOut) {
+        // narrow generator (the README flow's S2 sub-pdf: 4 -> 128 -> 10): thread per row, see csrc/mlp_kernels.cuh
+        static const bool off = [] { const char* e = getenv("JF_MLP_SMALL"); return e != nullptr && atoi(e) == 0; }();
+        if (!off) {
+            int dev = 0, sms = 148;
+            JF_CUDA_OK(cudaGetDevice(&dev));
+            JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const int64_t want = (B + 127) / 128;
+            const unsigned grid = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+            auto go = [&](auto kern, int IN, int OUT) -> int {
+                const size_t smem = (size_t)m.dims[1] * (IN + OUT + 1) * sizeof(T);
+                JF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, 128, smem, st>>>(m);
+                return check_launch();
+            };
+            const int in = m.dims[0], out_n = m.dims[2];
+            if (in <= 4 && out_n <= 4) return go(mlp_small_kernel<T, 4, 4>, 4, 4);
+            if (in <= 4 && out_n <= 10) return go(mlp_small_kernel<T, 4, 10>, 4, 10);
+            if (in <= 8 && out_n <= 10) return go(mlp_small_kernel<T, 8, 10>, 8, 10);
+            if (in <= 8) return go(mlp_small_kernel<T, 8, 16>, 8, 16);
+            if (out_n <= 10) return go(mlp_small_kernel<T, 16, 10>, 16, 10);
+            return go(mlp_small_kernel<T, 16, 16>, 16, 16);
+        }
+    }
     if (!accumulate && ws != nullptr && i8_eligible(desc, sizeof(T) == 8 ? JF_F64 : JF_F32) &&
         ws_bytes >= i8_ws_bytes(desc->dims[2], sizeof(T) == 8 ? JF_F64 : JF_F32))
         return launch_mlp2_i8(m, ws, prepared, st);

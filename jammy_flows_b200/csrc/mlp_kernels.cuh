@@ -205,3 +205,83 @@ __global__ void __launch_bounds__(256) mlp_expand_kernel(const __grid_constant__
 }
 
 }  // namespace jf
+
+namespace jf {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Narrow generator: Linear(in <= 16) -> tanh(H <= 128) -> Linear(out <= 16), one THREAD per row.
+// (reference main/default.py:654-670; the README flow's S2 sub-pdf: 4 -> 128 -> 10.)  With ten outputs the tensor-core
+// kernel pays a 64-column MMA tile and a full TMEM drain for 10 numbers and is bound by its prologue (the 128 tanh per
+// row); here the whole row lives in registers, the weights are broadcast from shared memory with 16-byte loads, four
+// hidden units are in flight per thread, and two thirds of the executed instructions are FP64.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSmMaxIn = 16, kSmMaxOut = 16;
+
+JF_DEVINL double sm_tanh(double x) {
+    const double e = exp_neg(-2.0 * fabs(x));
+    const double t = (1.0 - e) * rcp_1to2(1.0 + e);
+    return x < 0.0 ? -t : t;
+}
+JF_DEVINL float sm_tanh(float x) { return tanhf(x); }
+
+template <typename T, int IN, int OUT>     // IN, OUT: padded to even compile-time sizes (4/8/16)
+__global__ void __launch_bounds__(128) mlp_small_kernel(const __grid_constant__ MlpArgs<T> m) {
+    extern __shared__ __align__(16) unsigned char smem_small[];
+    const int H = m.dims[1], Kin = m.dims[0], N = m.dims[2];
+    T* sW1 = reinterpret_cast<T*>(smem_small);          // [H][IN]   (rows of W1, zero padded)
+    T* sW2 = sW1 + (size_t)H * IN;                      // [H][OUT]  (W2 transposed, zero padded)
+    T* sB1 = sW2 + (size_t)H * OUT;                     // [H]
+    for (int e = threadIdx.x; e < H * IN; e += blockDim.x) {
+        const int u = e / IN, i = e - u * IN;
+        sW1[e] = i < Kin ? m.wt[0][(size_t)u * Kin + i] : T(0);
+    }
+    for (int e = threadIdx.x; e < H * OUT; e += blockDim.x) {
+        const int u = e / OUT, j = e - u * OUT;
+        sW2[e] = j < N ? m.wt[1][(size_t)j * H + u] : T(0);
+    }
+    for (int e = threadIdx.x; e < H; e += blockDim.x) sB1[e] = m.bias[0][e];
+    __syncthreads();
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < m.B; row += (int64_t)gridDim.x * blockDim.x) {
+        T x[IN], o[OUT];
+#pragma unroll
+        for (int c = 0; c < IN; ++c) {                   // (static c: the row stays in registers)
+            T v = T(0);
+            int off = 0;
+            for (int sg = 0; sg < m.n_segments; ++sg) {
+                const int cols = m.seg_cols[sg];
+                if (c >= off && c < off + cols) v = m.seg_ptr[sg][row * m.seg_ld[sg] + (c - off)];
+                off += cols;
+            }
+            x[c] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < OUT; ++j) o[j] = j < N ? m.bias[1][j] : T(0);
+#pragma unroll 1
+        for (int u0 = 0; u0 < H; u0 += 4) {
+            T h[4];
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const int u = u0 + uu;
+                T z = u < H ? sB1[u] : T(0);
+                const T* w = sW1 + (size_t)(u < H ? u : 0) * IN;
+#pragma unroll
+                for (int i = 0; i < IN; ++i) z = fma(x[i], w[i], z);
+                h[uu] = u < H ? sm_tanh(z) : T(0);
+            }
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const T* w = sW2 + (size_t)(u0 + uu < H ? u0 + uu : 0) * OUT;
+#pragma unroll
+                for (int j = 0; j < OUT; ++j) o[j] = fma(h[uu], w[j], o[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < OUT; ++j)
+            if (j < N) {
+                T* dst = m.out + (int64_t)j * m.so_p + row * m.so_r;
+                *dst = m.acc ? *dst + o[j] : o[j];
+            }
+    }
+}
+
+}  // namespace jf
