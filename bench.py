@@ -375,7 +375,9 @@ def kernel_breakdown(pdf, x, z, lib, evals_per_elem):
                          "staged fp64 parameters -> FP64 layer chain; the [P,rows] block never exists in HBM"
                          % (6 if lp else 7))
             r["int8_tops"] = pairs * 2.0 * 128 * cols * nrows / (r["ms"] * 1e-3) * 1e-12
-        if r["kernel"].startswith("mlp"):
+        if r["kernel"].startswith("mlp") and int(r["kernel"].split("->")[-1].rstrip("]")) <= 16:
+            r["path"] = "narrow generator: thread per row, weights broadcast from shared memory (mlp_small_kernel), FP64 pipe"
+        elif r["kernel"].startswith("mlp"):
             # tcgen05 path: 28 int8 slice-pair GEMMs of 128 x N(padded to 64) x 128 per row block (csrc/mlp_i8.cuh)
             n_out = int(r["kernel"].split("->")[-1].rstrip("]"))
             n_pad = (n_out + 63) // 64 * 64
