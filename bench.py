@@ -518,6 +518,14 @@ def run_gpu_arm(args, rank, world, local_rank):
     int8_peak = 2.0 * bf16
     int8_src = ("int8 dense = 2 x bf16_tflops of MEASURED_PEAKS.json" if "bf16_tflops" in peaks
                 else "int8 dense = 2 x fallback bf16 1.59 PFLOP/s")
+    try:
+        # measured on this pool's B200 (tools/int8_peak.cu: back-to-back tcgen05.mma kind::i8, M = 128, resident operands)
+        meas = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "int8_peak_r02.jsonl")) if l.startswith("{")]
+        int8_peak = max(m_["tops"] for m_ in meas)
+        int8_src = ("measured tcgen05 kind::i8 peak (tools/int8_peak.cu, profiles/int8_peak_r02.jsonl: N >= 128; an N = 64 / "
+                    "48 / 32 instruction runs at 62 / 46 / 31 %% of it)")
+    except Exception:
+        pass
     if top["kernel"].startswith("mlp"):
         # dominant kernel = the tcgen05 MLP: tensor-pipe roofline.  Work = the int8 operations the kernel issues (28 slice
         # pair GEMMs of 128 x N_pad x 128 per 128 rows); peak = int8 dense, taken as 2x the MEASURED
