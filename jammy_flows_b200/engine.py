@@ -836,91 +836,82 @@ def supports_backward(pdf):
     return True
 
 
-class _SubPdfLogPdf(torch.autograd.Function):
-    """log p_k(x_k | params) = log N(base) + logdet of one Euclidean sub-pdf; differentiable w.r.t. the per-row params."""
-
-    @staticmethod
-    def forward(ctx, params_t, x_k, sub_desc, status):
-        lib = _cabi.load()
-        B, d = x_k.shape
-        dt, dev = x_k.dtype, x_k.device
-        base = torch.empty(B, d, dtype=dt, device=dev)
-        logdet = torch.empty(B, dtype=dt, device=dev)
-        logbase = torch.empty(B, dtype=dt, device=dev)
-        with torch.cuda.device(dev):
-            rc = lib.jf_subpdf_apply(C.byref(sub_desc), _DT[dt], _cabi.JF_DIR_LOGPDF, _ptr(x_k), x_k.stride(0),
-                                     _ptr(params_t), params_t.stride(0), 1, None, _ptr(logdet), None, _ptr(logbase),
-                                     _ptr(base), d, None, 0, B, _ptr(status), _stream_ptr(dev))
-        _cabi.check(rc, "jf_subpdf_apply")
-        ctx.save_for_backward(params_t, x_k)
-        ctx.sub_desc, ctx.status = sub_desc, status
-        ctx.mark_non_differentiable(base, logbase)
-        return logdet + logbase, logbase, base
-
-    @staticmethod
-    def backward(ctx, g_logp, g_logbase, g_base):
-        lib = _cabi.load()
-        params_t, x_k = ctx.saved_tensors
-        B = x_k.shape[0]
-        dt, dev = x_k.dtype, x_k.device
-        grad = torch.empty_like(params_t)
-        g = g_logp.contiguous()
-        with torch.cuda.device(dev):
-            rc = lib.jf_subpdf_backward(C.byref(ctx.sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
-                                        params_t.stride(0), 1, _ptr(g), _ptr(grad), B, _ptr(ctx.status), _stream_ptr(dev))
-        _cabi.check(rc, "jf_subpdf_backward")
-        return grad, None, None, None
+def subpdf_logpdf_forward(pdf, k, params_t, x_k):
+    """log p_k(x_k | params) = log N(base) + logdet of Euclidean sub-pdf k with per-row (param-major) parameters
+    -> (log_pdf_k [B], log_base_k [B], base_k [B, d]).  Body of the op `jammy_b200::subpdf_logpdf` (ops.py)."""
+    lib = _cabi.load()
+    B, d = x_k.shape
+    dt, dev = x_k.dtype, x_k.device
+    sub_desc, status = pdf._desc(dt).sub[k], pdf._status(dev)
+    base = torch.empty(B, d, dtype=dt, device=dev)
+    logdet = torch.empty(B, dtype=dt, device=dev)
+    logbase = torch.empty(B, dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_apply(C.byref(sub_desc), _DT[dt], _cabi.JF_DIR_LOGPDF, _ptr(x_k), x_k.stride(0),
+                                 _ptr(params_t), params_t.stride(0), 1, None, _ptr(logdet), None, _ptr(logbase),
+                                 _ptr(base), d, None, 0, B, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_apply")
+    return logdet + logbase, logbase, base
 
 
-class _MlpParamsTc(torch.autograd.Function):
-    """Per-row parameters [P, B] (param-major) of a Linear-tanh-Linear generator with 128 hidden units: forward on the
-    tcgen05 MLP kernel (`jf_mlp_forward_ws`, the same kernel as inference), backward with library GEMMs.  The hidden
-    activations are not kept: the backward recomputes them (a [B, in] x [in, 128] product, cheap next to the two
-    [P, B]-sized products of the last layer)."""
+def subpdf_logpdf_backward(pdf, k, params_t, x_k, g_logp):
+    """Gradient of sum(g_logp * log p_k) with respect to the per-row parameters (`jf_subpdf_backward`, csrc/gf_bwd.cuh)."""
+    lib = _cabi.load()
+    B = x_k.shape[0]
+    dt, dev = x_k.dtype, x_k.device
+    sub_desc, status = pdf._desc(dt).sub[k], pdf._status(dev)
+    grad = torch.empty_like(params_t)
+    g = g_logp.contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_backward(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
+                                    params_t.stride(0), 1, _ptr(g), _ptr(grad), B, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_backward")
+    return grad
 
-    @staticmethod
-    def forward(ctx, inp, w1, b1, w2, b2):
-        lib = _cabi.load()
-        dt, dev = inp.dtype, inp.device
-        B, P = inp.shape[0], w2.shape[0]
-        md = _cabi.JfMlpDesc()
-        md.n_linear = 2
-        md.dims[0], md.dims[1], md.dims[2] = w1.shape[1], w1.shape[0], P
-        md.n_segments = 1
-        md.seg_cols[0] = inp.shape[1]
-        inp_c = inp if inp.stride(1) == 1 else inp.contiguous()
-        ws_ = [w1.detach().contiguous(), w2.detach().contiguous()]
-        bs_ = [b1.detach().contiguous(), b2.detach().contiguous()]
-        ptrs = (C.c_void_p * 1)(inp_c.data_ptr())
-        lds = (C.c_int64 * 1)(inp_c.stride(0))
-        wp = (C.c_void_p * 2)(*[t.data_ptr() for t in ws_])
-        bp = (C.c_void_p * 2)(*[t.data_ptr() for t in bs_])
-        out = torch.empty(P, B, dtype=dt, device=dev)
-        nws = lib.jf_mlp_workspace_bytes(C.byref(md), _DT[dt])
-        ws = _workspace(dev, max(int(nws), 16))
-        with torch.cuda.device(dev):
-            rc = lib.jf_mlp_forward_ws(C.byref(md), _DT[dt], ptrs, lds, wp, bp, _ptr(out), B, 1, B, _ptr(ws), nws, 0,
-                                       _stream_ptr(dev))
-        _cabi.check(rc, "jf_mlp_forward_ws")
-        ctx.save_for_backward(inp_c, w1, b1, w2)
-        return out
 
-    @staticmethod
-    def backward(ctx, g):                                   # g: [P, B]
-        inp, w1, b1, w2 = ctx.saved_tensors
-        if g.dtype == torch.float32:
-            return _mlp_backward_tc(inp, w1, b1, w2, g, ctx.needs_input_grad[0])
-        # fp64: library GEMMs (the tensor-core kernels are tf32: 1e-3, the fp64 training contract is 1e-8)
-        h = torch.tanh(torch.addmm(b1, inp, w1.t()))         # [B, 128]
-        g_w2 = torch.mm(g, h)                                # [P, 128]
-        g_b2 = g.sum(dim=1)
-        g_h = torch.mm(g.t(), w2)                            # [B, 128]
-        g_pre = g_h * (1.0 - h * h)
-        g_w1 = torch.mm(g_pre.t(), inp)                      # [128, in]
-        g_b1 = g_pre.sum(dim=0)
-        # the generator's input may itself carry history (a conditional_input produced by an upstream encoder)
-        g_inp = torch.mm(g_pre, w1) if ctx.needs_input_grad[0] else None
-        return g_inp, g_w1, g_b1, g_w2, g_b2
+def mlp_params_forward(inp, w1, b1, w2, b2):
+    """Per-row parameters [P, B] (param-major) of a Linear-tanh-Linear generator with 128 hidden units on the tcgen05
+    MLP kernel (`jf_mlp_forward_ws`, the same kernel as inference).  Body of the op `jammy_b200::mlp_params`."""
+    lib = _cabi.load()
+    dt, dev = inp.dtype, inp.device
+    B, P = inp.shape[0], w2.shape[0]
+    md = _cabi.JfMlpDesc()
+    md.n_linear = 2
+    md.dims[0], md.dims[1], md.dims[2] = w1.shape[1], w1.shape[0], P
+    md.n_segments = 1
+    md.seg_cols[0] = inp.shape[1]
+    inp_c = inp if inp.stride(1) == 1 else inp.contiguous()
+    ws_ = [w1.detach().contiguous(), w2.detach().contiguous()]
+    bs_ = [b1.detach().contiguous(), b2.detach().contiguous()]
+    ptrs = (C.c_void_p * 1)(inp_c.data_ptr())
+    lds = (C.c_int64 * 1)(inp_c.stride(0))
+    wp = (C.c_void_p * 2)(*[t.data_ptr() for t in ws_])
+    bp = (C.c_void_p * 2)(*[t.data_ptr() for t in bs_])
+    out = torch.empty(P, B, dtype=dt, device=dev)
+    nws = lib.jf_mlp_workspace_bytes(C.byref(md), _DT[dt])
+    ws = _workspace(dev, max(int(nws), 16))
+    with torch.cuda.device(dev):
+        rc = lib.jf_mlp_forward_ws(C.byref(md), _DT[dt], ptrs, lds, wp, bp, _ptr(out), B, 1, B, _ptr(ws), nws, 0,
+                                   _stream_ptr(dev))
+    _cabi.check(rc, "jf_mlp_forward_ws")
+    return out
+
+
+def mlp_params_backward(inp, w1, b1, w2, g, want_inp_grad):
+    """Gradient of the generator given g = d loss / d params [P, B].  fp32: `jf_mlp_backward` (tensor cores, tf32);
+    fp64: library GEMMs (the fp64 training contract is 1e-8).  The hidden activations are recomputed."""
+    if g.dtype == torch.float32:
+        return _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad)
+    h = torch.tanh(torch.addmm(b1, inp, w1.t()))         # [B, 128]
+    g_w2 = torch.mm(g, h)                                # [P, 128]
+    g_b2 = g.sum(dim=1)
+    g_h = torch.mm(g.t(), w2)                            # [B, 128]
+    g_pre = g_h * (1.0 - h * h)
+    g_w1 = torch.mm(g_pre.t(), inp)                      # [128, in]
+    g_b1 = g_pre.sum(dim=0)
+    # the generator's input may itself carry history (a conditional_input produced by an upstream encoder)
+    g_inp = torch.mm(g_pre, w1) if want_inp_grad else None
+    return g_inp, g_w1, g_b1, g_w2, g_b2
 
 
 def _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad):
@@ -976,11 +967,12 @@ def _tc_mlp_eligible(mlp, dt, dev):
 
 def sequential_mlp_forward_trainable(mlp, x):
     """nn.Sequential generator on x [R, in] -> [R, out] WITH autograd history (the tcgen05 forward + GEMM backward of
-    `_MlpParamsTc` when the shape fits, the torch module otherwise)."""
+    the op `jammy_b200::mlp_params` when the shape fits, the torch module otherwise)."""
     _require_cuda(x, "MLP input")
     if _tc_mlp_eligible(mlp, x.dtype, x.device):
+        from . import ops  # noqa: F401  (registers torch.ops.jammy_b200.*)
         mods = list(mlp)
-        return _MlpParamsTc.apply(x, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias).t()
+        return torch.ops.jammy_b200.mlp_params(x, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias).t()
     return mlp(x)
 
 
@@ -991,9 +983,9 @@ def pdf_logpdf_trainable(pdf, x, cond):
     if x.requires_grad:
         raise NotImplementedError("gradients with respect to the evaluation points x are not provided by the backward "
                                   "kernels (parameters and conditional_input are); detach x")
+    from . import ops
     dt, dev = x.dtype, x.device
-    desc = pdf._desc(dt)
-    status = pdf._status(dev)
+    handle = ops.handle_of(pdf)
     logp, logp_base, bases = None, None, []
     prev = []
     for k, layers in enumerate(pdf.layer_list):
@@ -1010,14 +1002,14 @@ def pdf_logpdf_trainable(pdf, x, cond):
             inp = torch.cat(pieces, dim=1) if len(pieces) > 1 else pieces[0]
             mods = list(mlp)
             if _tc_mlp_eligible(mlp, dt, dev):
-                params_t = _MlpParamsTc.apply(inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias)
+                params_t = torch.ops.jammy_b200.mlp_params(inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias)
             else:
                 h = inp
                 for m in mods[:-1]:
                     h = m(h)
                 last = mods[-1]
                 params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())    # [P, B], param-major
-        lp_k, lb_k, base_k = _SubPdfLogPdf.apply(params_t, x_k, desc.sub[k], status)
+        lp_k, lb_k, base_k = torch.ops.jammy_b200.subpdf_logpdf(params_t, x_k.contiguous(), handle, k)
         logp = lp_k if logp is None else logp + lp_k
         logp_base = lb_k if logp_base is None else logp_base + lb_k
         bases.append(base_k)

@@ -93,6 +93,14 @@ class pdf(nn.Module):
         self.rng_mode = "numpy"
         self.rng_first_row = 0
         self.chunk_rows = None
+        from . import ops
+        self._op_handle = ops.register(self)       # handle under which the torch.library ops (ops.py) find this module
+
+    def __setstate__(self, state):
+        # deepcopy / unpickle: the copy is a different module and needs a handle of its own
+        super().__setstate__(state)
+        from . import ops
+        self._op_handle = ops.register(self)
 
     # ------------------------------------------------------------------------------------------------------------------
     # model definition (reference main/default.py:153-325)
@@ -481,8 +489,15 @@ class pdf(nn.Module):
             # training path: fused forward AND backward layer kernels, torch autograd only for the parameter generator
             return engine.pdf_logpdf_trainable(self, x, conditional_input)
         amort = amortization_parameters.detach() if amortization_parameters is not None else None
-        log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows,
-                                                            amort=amort, only_last=only_last)
+        if (x.is_cuda and amort is None and not only_last and not engine.uses_custom_mlp(self)
+                and type(conditional_input) != list):      # (CPU tensors: engine raises, there is no CPU fallback)
+            # the whole-pdf entry as a torch.library op (ops.py): opaque to torch.compile, no graph break
+            from . import ops
+            log_pdf, log_pdf_base, base_pos = torch.ops.jammy_b200.pdf_logpdf(x, conditional_input, self._op_handle,
+                                                                              int(self.chunk_rows or 0))
+        else:
+            log_pdf, log_pdf_base, base_pos = engine.pdf_logpdf(self, x, conditional_input, chunk_rows=self.chunk_rows,
+                                                                amort=amort, only_last=only_last)
         if chart_log_det is not None:
             log_pdf = log_pdf + chart_log_det
         if needs_grad:
@@ -599,8 +614,14 @@ class pdf(nn.Module):
         else:
             z = self._draw_base_normals(used_sample_size, seed, data_type, used_device)
             std_normal_samples = z
-        x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows,
-                                                  amort=amortization_parameters, only_last=only_last)
+        if (z.is_cuda and amortization_parameters is None and not only_last and not engine.uses_custom_mlp(self)
+                and type(conditional_input) != list):
+            from . import ops       # the whole-pdf entry as a torch.library op (ops.py)
+            x, log_pdf, log_gauss = torch.ops.jammy_b200.pdf_sample(z, conditional_input, self._op_handle,
+                                                                    int(self.chunk_rows or 0))
+        else:
+            x, log_pdf, log_gauss = engine.pdf_sample(self, z, conditional_input, chunk_rows=self.chunk_rows,
+                                                      amort=amortization_parameters, only_last=only_last)
         if force_embedding_coordinates and self._needs_transform():
             # reference main/default.py:1522-1524: default -> embedding coordinates, log p = log N(z) - (logdet + chart)
             x, chart_log_det = engine.pdf_transform_target(self, x, None, to_embedding=True)

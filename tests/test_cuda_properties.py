@@ -232,3 +232,29 @@ def test_fp32_path_runs_and_matches_fp64(lib_built):
         lp32, _, _ = p32(x.float().cuda(), conditional_input=c.float().cuda())
     err = ((lp32.double() - lp64).abs() / lp64.abs().clamp(min=1)).cpu().numpy()
     assert np.quantile(err, 0.99) < 1e-4 and err.max() < 1e-2     # fp32 input rounding propagates through 6 layers
+
+
+def test_torch_library_ops_and_compile_without_graph_breaks(lib_built):
+    """The C-ABI entries are torch.library custom ops (jammy_flows_b200/ops.py): pdf.forward traces through Dynamo
+    without a graph break at the library boundary, the compiled module returns what eager returns, and opcheck accepts the
+    ops' schemas / fake implementations."""
+    import torch._dynamo
+    from jammy_flows_b200 import ops
+    p = jfb.pdf("e4+s2+e4", "gggg+n+gggg").double().cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = 1.5 * torch.randn(4096, 10, generator=g, dtype=torch.float64, device="cuda")
+    x[:, 4] = torch.acos(1 - 2 * torch.rand(4096, generator=g, dtype=torch.float64, device="cuda"))
+    x[:, 5] = 2 * np.pi * torch.rand(4096, generator=g, dtype=torch.float64, device="cuda")
+    with torch.no_grad():
+        ref = p(x)
+        torch._dynamo.reset()
+        ex = torch._dynamo.explain(p)(x)
+        assert ex.graph_break_count == 0, ex.break_reasons
+        assert any("pdf_logpdf" in str(n.target) for gm in ex.graphs for n in gm.graph.nodes)
+        out = torch.compile(p, backend="eager", fullgraph=True)(x)
+    for a, b in zip(ref, out):
+        assert torch.equal(a, b)
+    h = ops.handle_of(p)
+    torch.library.opcheck(torch.ops.jammy_b200.pdf_logpdf.default, (x[:64], None, h, 0), test_utils=("test_schema", "test_faketensor"))
+    z = torch.randn(64, 10, generator=g, dtype=torch.float64, device="cuda")
+    torch.library.opcheck(torch.ops.jammy_b200.pdf_sample.default, (z, None, h, 0), test_utils=("test_schema", "test_faketensor"))
