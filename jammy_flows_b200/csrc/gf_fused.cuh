@@ -74,10 +74,10 @@ struct FuCfg {
     static constexpr int kConstBytes = 3 * TN * 16;           // (scale, b2) of the tile being drained, the next one, and one in between
                                                               // (a warp may still store the last columns of the previous tile)
     // sampling keeps the regulated kernels of every (row, dimension) in shared-memory slots for the root finder
-    // ([field m / 1/w / n][k][worker]: 120 KB); to make room its exchange is single buffered (two barriers per meeting)
-    // and W1 / the gathered inputs -- prologue only -- live inside staging buffer 0
+    // ([field m / 1/w / n][k][worker]: 120 KB); to make room its exchange lives inside the slots (two barriers per
+    // meeting) and W1 / the gathered inputs -- prologue only -- live inside staging buffer 0
     static constexpr bool kSample = DIR == JF_DIR_SAMPLE;
-    static constexpr int kExBufs = kSample ? 1 : 2;
+    static constexpr int kExBufs = kSample ? 0 : 2;          // sampling: the exchange lives in the slots
     static constexpr int kSlotBytes = kSample ? 3 * kFuK * kFuWorkers * 8 : 0;
     static constexpr int offB = 0;
     static constexpr int offStage = offB + kRing * kSliceBytesB;
@@ -499,7 +499,12 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
         uint32_t wwrap = 0;
         int ex_buf = 0;
         int n_evals = 0, n_unconv = 0, n_bad = 0;
-        double* exr = sEx + r;                          // element (buf, j, f) at exr[((buf*4 + j)*6 + f)*128]
+        // exchange of the four workers of a row: field f of dimension j at exr[buf_off + j * exJ + f * exF].  log_pdf: its own
+        // double-buffered array; sampling: the workers' shared-memory slots (mean slots k = 0..5 of worker (row, j)), which
+        // are dead between a worker's solve and the arrival of the next layer's means -- that is what frees 24 KB for a
+        // second staging buffer
+        double* exr = (G::kSample ? sSlots : sEx) + r;
+        constexpr int exF = G::kSample ? kFuWorkers : kI8Rows, exJ = G::kSample ? kI8Rows : kFuExFields * kI8Rows;
 #if JF_FU_PROF
         long long prof_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
 #endif
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
             for (int c = 0; c < L; ++c) {
                 const int l = DIR == JF_DIR_LOGPDF ? L - 1 - c : c;
                 const FuLayerC& lc = a.layers[l];
-                double* exw = exr + (size_t)((ex_buf * 4 + cg) * kFuExFields) * kI8Rows;
+                double* exw = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows + cg * exJ;
                 const double* exb = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows;
                 // the four workers of a row meet here: sum of the log-derivatives, rotation of the row vector
                 // (x, the Householder components and the log-derivative are in the exchange already)
@@ -623,7 +628,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     double X[kFuMaxD], ld = 0.0;
 #pragma unroll
                     for (int j = 0; j < kFuMaxD; ++j)
-                        if (j < d) { X[j] = exb[(j * kFuExFields) * kI8Rows]; ld += exb[(j * kFuExFields + 5) * kI8Rows]; }
+                        if (j < d) { X[j] = exb[j * exJ]; ld += exb[j * exJ + 5 * exF]; }
                     if (cg == 0) logdet_acc += DIR == JF_DIR_SAMPLE ? -ld : ld;
 #pragma unroll 1
                     for (int ii = 0; ii < lc.hh_iter; ++ii) {
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < kFuMaxD; ++j)
                             if (j < d) {
-                                V[j] = exb[(j * kFuExFields + 1 + i) * kI8Rows];
+                                V[j] = exb[j * exJ + (1 + i) * exF];
                                 dot = fma(V[j], X[j], dot);
                                 nrm = fma(V[j], V[j], nrm);
                             }
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                         mine = (j == cg) ? X[j] : mine;
                         if (DIR == JF_DIR_SAMPLE && cg == 0 && j < d && !finite_(X[j])) n_bad |= 1;
                     }
-                    if (G::kExBufs == 1) bar_sync_named(2 + lq, 128);       // single buffer: everybody has read before anybody writes again
+                    if (G::kExBufs < 2) bar_sync_named(2 + lq, 128);        // single buffer: everybody has read before anybody writes again
                     return mine;
                 };
                 double v[SPT];
@@ -658,8 +663,8 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     if (lc.has_offset) xj -= v[4];
                     exw[0] = xj;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) exw[(1 + i) * kI8Rows] = v[i];
-                    exw[5 * kI8Rows] = logd_prev;
+                    for (int i = 0; i < 4; ++i) exw[(1 + i) * exF] = v[i];
+                    exw[5 * exF] = logd_prev;
                     xj = meet();
                     FuSums S;
                     if (JF_FU_DBG & 2) { S.D = 0; S.E = 1; S.big_p = S.small_p = S.big_n = S.small_n = S.Sp = v[5]; S.ex = S.qc = 0; S.nsum = 1; S.n_pos = 1; }
@@ -684,6 +689,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     // finder of csrc/gf.cuh (rolled loops over k, out of line) reads them.
                     double* slot_m = sSlots + tid, * slot_iw = slot_m + kFuK * kFuWorkers, * slot_n = slot_iw + kFuK * kFuWorkers;
                     double off = 0.0, nsum = 0.0, mmin = Num<double>::big, mmax = -Num<double>::big;
+                    double hh[4] = {0.0, 0.0, 0.0, 0.0};        // this dimension's Householder components: exchanged after the solve
 #pragma unroll
                     for (int part = 0; part < TPL; ++part) {
                         next_tile(v);
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                                 const double g = regulate_norm(v[i], lc.n_min, lc.n_max);
                                 nsum += g;
                                 slot_n[(s - 10) * kFuWorkers] = g;
-                            } else if (s < 24) exw[(1 + (s - 20)) * kI8Rows] = v[i];
+                            } else if (s < 24) hh[s < 24 ? s - 20 : 0] = v[i];
                             else if (s < 34) {
                                 slot_m[(s - 24) * kFuWorkers] = v[i];
                                 mmin = tmin(mmin, v[i]);
@@ -723,8 +729,10 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     FU_T(6);
                     n_evals += ev;
                     n_unconv += conv ? 0 : 1;
-                    exw[0] = xj;
-                    exw[5 * kI8Rows] = logd;
+                    exw[0] = xj;                                // (own mean slots: the solve is over)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) exw[(1 + i) * exF] = hh[i];
+                    exw[5 * exF] = logd;
                     xj = meet();
                     if (lc.has_offset) xj += off;
                 }
@@ -733,16 +741,16 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
             // ---- outputs ----
             if (DIR == JF_DIR_LOGPDF) {
                 // final exchange: base coordinates and the last layer's log-derivatives -> worker 0 of the row
-                double* exw = exr + (size_t)((ex_buf * 4 + cg) * kFuExFields) * kI8Rows;
+                double* exw = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows + cg * exJ;
                 exw[0] = xj;
-                exw[5 * kI8Rows] = logd_prev;
+                exw[5 * exF] = logd_prev;
                 bar_sync_named(2 + lq, 128);
                 if (cg == 0) {
                     const double* exb = exr + (size_t)(ex_buf * 4 * kFuExFields) * kI8Rows;
                     double ld = 0.0, zsq_b = 0.0;
                     for (int j = 0; j < d; ++j) {
-                        const double xb = exb[(j * kFuExFields) * kI8Rows];
-                        ld += exb[(j * kFuExFields + 5) * kI8Rows];
+                        const double xb = exb[j * exJ];
+                        ld += exb[j * exJ + 5 * exF];
                         zsq_b = fma(xb, xb, zsq_b);
                         if (!finite_(xb)) n_bad |= 1;
                     }
