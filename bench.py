@@ -797,7 +797,7 @@ def main():
     ap.add_argument("--config", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE configs[1] (headline); train: configs[4], the training step with NCCL gradient all-reduce")
     ap.add_argument("--train-rows", type=int, default=1_000_000, help="--config train: rows per GPU per step")
-    ap.add_argument("--train-chunk", type=int, default=65536, help="--config train: rows per forward/backward chunk")
+    ap.add_argument("--train-chunk", type=int, default=262144, help="--config train: rows per forward/backward chunk")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --rows per GPU; strong: --rows in total, sharded over the GPUs")
     args = ap.parse_args()

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define JF_ABI_VERSION 4
+#define JF_ABI_VERSION 5
 
 #define JF_MAX_LAYERS 16
 #define JF_MAX_SUBPDFS 8
@@ -252,6 +252,24 @@ int jf_subpdf_backward(const JfSubPdfDesc* desc, int dtype,
                        int64_t B, int64_t* status, void* stream);
 
 /*
+ * Training, one pass: the LOGPDF direction of jf_subpdf_apply (base point, logdet, log N(base)) AND the gradients of
+ * jf_subpdf_backward from ONE kernel (csrc/gf_fb.cuh, worker = (row, dimension)); the backward needs the recomputed
+ * forward anyway, so a training step that calls this instead of apply + backward saves the forward kernel.  With
+ * grad_logp = NULL the gradient buffers hold the per-row JACOBIAN d log_pdf[row] / d params[., row], which a caller can
+ * scale by the upstream gradient later (jf_mlp_backward's row_scale) -- that is how the autograd path of
+ * jammy_flows_b200.pdf.forward uses it.
+ *   grad_x       optional out [B, d] (ld_gx): d log_pdf / d x (the reference differentiates through the evaluation points too)
+ *   base_out     optional out [B, d] (ld_out); logdet_out, logbase_out: optional out [B]
+ * Other arguments and the status counters as in jf_subpdf_backward.
+ */
+int jf_subpdf_forward_backward(const JfSubPdfDesc* desc, int dtype,
+                               const void* x, int64_t ld_x,
+                               const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                               const void* grad_logp, void* grad_params, void* grad_x, int64_t ld_gx,
+                               void* base_out, int64_t ld_out, void* logdet_out, void* logbase_out,
+                               int64_t B, int64_t* status, void* stream);
+
+/*
  * params = W_L * tanh(... tanh(W_1 * concat(segments) + b_1) ...) + b_L for B rows.
  *   seg_ptrs[i]/seg_ld[i]  column block i: [B, seg_cols[i]] with leading dimension seg_ld[i].
  *   weights[l]             weight of Linear l in torch layout: [dims[l+1], dims[l]] row-major (= Linear.weight).
@@ -292,13 +310,16 @@ int jf_mlp_forward_ws(const JfMlpDesc* desc, int dtype,
  * weight gradients ~1e-3 / sqrt(rows)); csrc/mlp_bwd.cuh.
  *   inp          [B, dims[0]] (ld_inp)         weights / biases as in jf_mlp_forward (biases[1] is not read)
  *   grad_out     element (j,row) at grad_out[j*go_stride_param + row]; go_stride_row must be 1, 16-byte aligned rows
+ *   row_scale    [B] or NULL: the upstream gradient is grad_out[j, row] * row_scale[row] (grad_out = the per-row Jacobian of
+ *                jf_subpdf_forward_backward, row_scale = d loss / d log_pdf); applied on the small operands, grad_out is
+ *                read as it is
  *   grad_w1/b1/w2/b2   outputs in torch layout, ZEROED BY THE CALLER (partial sums are added with red.global)
  *   grad_inp     [B, dims[0]] (ld_ginp) or NULL
  *   workspace    jf_mlp_backward_workspace_bytes(desc, dtype, B) bytes, 256-byte aligned */
 int64_t jf_mlp_backward_workspace_bytes(const JfMlpDesc* desc, int dtype, int64_t B);
 int jf_mlp_backward(const JfMlpDesc* desc, int dtype, const void* inp, int64_t ld_inp,
                     const void* const* weights, const void* const* biases,
-                    const void* grad_out, int64_t go_stride_param, int64_t go_stride_row,
+                    const void* grad_out, int64_t go_stride_param, int64_t go_stride_row, const void* row_scale,
                     void* grad_w1, void* grad_b1, void* grad_w2, void* grad_b2,
                     void* grad_inp, int64_t ld_ginp, int64_t B,
                     void* workspace, int64_t workspace_bytes, void* stream);

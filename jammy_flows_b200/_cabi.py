@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JF_LIB_PATH") or os.path.join(PKG_DIR, "libjammy_b200.so")
 
 # ---- constants (keep in sync with include/jammy_b200.h; checked by tests/test_cabi_symbols.py) -----------------------
-JF_ABI_VERSION = 4
+JF_ABI_VERSION = 5
 JF_MAX_LAYERS = 16
 JF_MAX_SUBPDFS = 8
 JF_MAX_MLP_LINEAR = 6
@@ -93,6 +93,8 @@ SYMBOLS = {
     "jf_subpdf_apply": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp,
                                   _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
     "jf_subpdf_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "jf_subpdf_forward_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64,
+                                             _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "jf_mlp_forward": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
                                  C.POINTER(_vp), _vp, _i64, _i64, _i64, _vp]),
     "jf_mlp_forward_acc": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
@@ -102,7 +104,7 @@ SYMBOLS = {
                                     C.POINTER(_vp), _vp, _i64, _i64, _i64, _vp, _i64, C.c_int, _vp]),
     "jf_mlp_backward_workspace_bytes": (_i64, [C.POINTER(JfMlpDesc), C.c_int, _i64]),
     "jf_mlp_backward": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _i64,
-                                  _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "jf_subpdf_generated_workspace_bytes": (_i64, [C.POINTER(JfSubPdfDesc), C.POINTER(JfMlpDesc), C.c_int]),
     "jf_subpdf_apply_generated": (C.c_int, [C.POINTER(JfSubPdfDesc), C.POINTER(JfMlpDesc), C.c_int, C.c_int,
                                             C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_vp), _vp, _i64,

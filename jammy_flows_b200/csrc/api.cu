@@ -16,7 +16,7 @@
 #include "mlp_kernels.cuh"
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
-#include "gf_bwd.cuh"
+#include "gf_fb_launch.cuh"
 #include "rowwise.cuh"
 #include "gf_fused_launch.cuh"
 #include "mlp_bwd_launch.cuh"
@@ -366,19 +366,23 @@ extern "C" int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int directio
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// jf_subpdf_backward: per-row parameter gradients of the log_pdf of a Euclidean "g" sub-pdf
+// jf_subpdf_forward_backward / jf_subpdf_backward: log_pdf of a Euclidean "g" sub-pdf and its per-row parameter gradients
+// in one kernel (csrc/gf_fb.cuh)
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
-static int subpdf_backward_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, const void* params, int64_t sp,
-                             int64_t sr, const void* grad_logp, void* grad_params, int64_t B, int64_t* status,
-                             cudaStream_t st) {
-    GfBwdArgs<T> g;
-    fill_common<T>(g.a, desc, x, ld_x, params, sp, sr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, B, status);
+static int subpdf_fb_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, const void* params, int64_t sp,
+                       int64_t sr, const void* grad_logp, void* grad_params, void* grad_x, int64_t ld_gx, void* base_out,
+                       int64_t ld_out, void* logdet_out, void* logbase_out, int64_t B, int64_t* status, cudaStream_t st) {
+    GfFbArgs<T> g;
+    fill_common<T>(g.a, desc, x, ld_x, params, sp, sr, nullptr, logdet_out, nullptr, logbase_out, base_out, ld_out, nullptr, 0,
+                   B, status);
     g.grad_logp = (const T*)grad_logp;
     g.grad_params = (T*)grad_params;
+    g.grad_x = (T*)grad_x;
+    g.ld_gx = ld_gx;
     const int d = desc->dim;
-    if (d < 1 || d > kBwdMaxDim) return JF_ERR_UNSUPPORTED;
-    int kmax = 1;
+    if (d < 1 || d > JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
+    int kmax = 1, hh_max = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
         const JfLayerDesc& L = desc->layers[l];
         if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_UNSUPPORTED;
@@ -393,30 +397,47 @@ static int subpdf_backward_t(const JfSubPdfDesc* desc, const void* x, int64_t ld
         c.has_offset = L.has_offset; c.raw_off = L.param_offset; c.tab_off = 0;
         c.w_min = (T)L.w_min; c.inv_w_max = (T)(1.0 / L.w_max); c.n_min = (T)L.n_min; c.n_max = (T)L.n_max;
         kmax = L.K > kmax ? L.K : kmax;
+        hh_max = L.hh_iter > hh_max ? L.hh_iter : hh_max;
     }
-    const int threads = 128;
-    const size_t smem = (size_t)3 * kmax * threads * sizeof(T);
-    if (smem > 48 * 1024)
-        JF_CUDA_OK(cudaFuncSetAttribute(gf_chain_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = (B + threads - 1) / threads;
-    gf_chain_backward_kernel<T><<<(unsigned)blocks, threads, smem, st>>>(g);
+    g.kmax = kmax;
+    g.hh_max = hh_max;
+    const int rc = launch_gf_fb<T>(g, st);
+    if (rc != JF_OK) return rc;
     return check_launch();
+}
+
+static int subpdf_fb_checks(const JfSubPdfDesc* desc, const void* x, const void* params, const void* grad_params,
+                            int64_t p_stride_row, int64_t B) {
+    if (desc == nullptr || x == nullptr || params == nullptr || grad_params == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
+    if (desc->manifold != 'e') return JF_ERR_UNSUPPORTED;
+    if (p_stride_row == 0) return JF_ERR_UNSUPPORTED;      // shared (permanent) parameters: expand them to per-row form
+    if (B < 0) return JF_ERR_BAD_ARG;
+    return JF_OK;
 }
 
 extern "C" int jf_subpdf_backward(const JfSubPdfDesc* desc, int dtype, const void* x, int64_t ld_x, const void* params,
                                   int64_t p_stride_param, int64_t p_stride_row, const void* grad_logp, void* grad_params,
                                   int64_t B, int64_t* status, void* stream) {
-    if (desc == nullptr || x == nullptr || params == nullptr || grad_params == nullptr) return JF_ERR_BAD_ARG;
-    if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
-    if (desc->manifold != 'e') return JF_ERR_UNSUPPORTED;
-    if (p_stride_row == 0) return JF_ERR_UNSUPPORTED;      // shared (permanent) parameters: no backward kernel yet
-    if (B < 0) return JF_ERR_BAD_ARG;
+    return jf_subpdf_forward_backward(desc, dtype, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params,
+                                      nullptr, 0, nullptr, 0, nullptr, nullptr, B, status, stream);
+}
+
+extern "C" int jf_subpdf_forward_backward(const JfSubPdfDesc* desc, int dtype, const void* x, int64_t ld_x,
+                                          const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                                          const void* grad_logp, void* grad_params, void* grad_x, int64_t ld_gx,
+                                          void* base_out, int64_t ld_out, void* logdet_out, void* logbase_out, int64_t B,
+                                          int64_t* status, void* stream) {
+    const int rc = subpdf_fb_checks(desc, x, params, grad_params, p_stride_row, B);
+    if (rc != JF_OK) return rc;
     if (B == 0) return JF_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == JF_F64)
-        return subpdf_backward_t<double>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, B, status, st);
+        return subpdf_fb_t<double>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, grad_x, ld_gx,
+                                   base_out, ld_out, logdet_out, logbase_out, B, status, st);
     if (dtype == JF_F32)
-        return subpdf_backward_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, B, status, st);
+        return subpdf_fb_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, grad_x, ld_gx,
+                                  base_out, ld_out, logdet_out, logbase_out, B, status, st);
     return JF_ERR_BAD_ARG;
 }
 
@@ -672,7 +693,8 @@ extern "C" int64_t jf_mlp_backward_workspace_bytes(const JfMlpDesc* desc, int dt
 
 extern "C" int jf_mlp_backward(const JfMlpDesc* desc, int dtype, const void* inp, int64_t ld_inp,
                                const void* const* weights, const void* const* biases, const void* grad_out,
-                               int64_t go_stride_param, int64_t go_stride_row, void* grad_w1, void* grad_b1, void* grad_w2,
+                               int64_t go_stride_param, int64_t go_stride_row, const void* row_scale, void* grad_w1,
+                               void* grad_b1, void* grad_w2,
                                void* grad_b2, void* grad_inp, int64_t ld_ginp, int64_t B, void* workspace,
                                int64_t workspace_bytes, void* stream) {
     if (desc == nullptr || inp == nullptr || weights == nullptr || biases == nullptr || grad_out == nullptr ||
@@ -688,6 +710,7 @@ extern "C" int jf_mlp_backward(const JfMlpDesc* desc, int dtype, const void* inp
     BwArgs a;
     memset(&a, 0, sizeof(a));
     a.G = (const float*)grad_out; a.ldg = go_stride_param;
+    a.row_scale = (const float*)row_scale;
     a.P = desc->dims[2]; a.B = B;
     a.x = (const float*)inp; a.ldx = ld_inp; a.in = desc->dims[0];
     a.W1 = (const float*)weights[0]; a.b1 = (const float*)biases[0]; a.W2 = (const float*)weights[1];

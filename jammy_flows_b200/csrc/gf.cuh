@@ -111,7 +111,8 @@ JF_DEVINL unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to
 // NOTE: the asm loads above are not ordered against these C++ stores by the compiler; the slots are only read through
 // mix_eval/gf_solve, which are separate (noinline) functions called after this one returns.
 template <typename T>
-__device__ __noinline__ MixView<T> regulate_to_slots(const GfLayerC<T>& c, int K, int j, const T* p, int64_t sj, T* slots) {
+__device__ __noinline__ MixView<T> regulate_to_slots(const GfLayerC<T>& c, int K, int j, const T* p, int64_t sj, T* slots,
+                                                     bool prefetch_next_dim = true) {
     const int d = c.d, nt = blockDim.x;
     T* sm = slots + threadIdx.x;
     T* si = sm + (size_t)K * nt;
@@ -134,7 +135,7 @@ __device__ __noinline__ MixView<T> regulate_to_slots(const GfLayerC<T>& c, int K
     // (the [P, rows] buffer is 2.3 GB per chunk, read exactly once: every first touch is an HBM access otherwise).
     // Measured: log_pdf per-row -9.6 %, sampling per-row -4.2 %; also prefetching across the layer boundary (next
     // layer's Householder vectors and first dimension) cost more instructions than it saved (+3 %) and was dropped.
-    if (j + 1 < d) {
+    if (prefetch_next_dim && j + 1 < d) {
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + k * step + sj));

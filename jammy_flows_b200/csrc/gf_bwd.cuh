@@ -1,4 +1,5 @@
-// Backward of the Euclidean "g"-chain log_pdf (training, BASELINE configs[4]): per-row gradient of
+// Element-level pieces of the backward of the Euclidean "g"-chain log_pdf (training, BASELINE configs[4]; the kernel
+// that drives them is csrc/gf_fb.cuh): per-row gradient of
 //   log p(x) = sum_j log N(z_j) + sum_layers sum_j log y'(v_j)
 // with respect to the PER-ROW raw parameters the MLP emitted (the reference gets these from autograd through
 // gaussianization_flow.py:995-1057, :699-861, :389-454; here they are closed-form, one thread per row, nothing stored
@@ -24,14 +25,6 @@
 #include "subpdf_args.cuh"
 
 namespace jf {
-
-template <typename T>
-struct GfBwdArgs {
-    SubPdfArgs<T> a;           // in = targets x, params = raw per-row parameters; out / logdet / logbase unused
-    const T* grad_logp;        // [B] upstream gradient of log_pdf (NULL = 1)
-    T* grad_params;            // same indexing as params: element (i,row) at grad_params[i*sj + row*sr]
-    GfLayerC<T> layers[JF_MAX_LAYERS];
-};
 
 // regulated parameters of (layer, dimension j) into this thread's slots WITHOUT normalising the weights; returns their sum
 template <typename T>
@@ -190,87 +183,6 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
         }
     }
     return true;
-}
-
-constexpr int kBwdMaxDim = JF_MAX_DIM;
-
-template <typename T>
-__global__ void __launch_bounds__(128) gf_chain_backward_kernel(const __grid_constant__ GfBwdArgs<T> g) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* slots = reinterpret_cast<T*>(smem_raw);
-    const SubPdfArgs<T>& a = g.a;
-    const int d = a.d, L = a.n_layers;
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= a.B) return;
-    const T* prow = a.params + row * a.sr;
-    T* grow = g.grad_params + row * a.sr;
-    const int64_t sj = a.sj;
-    T x[kBwdMaxDim];
-    T vs[JF_MAX_LAYERS * kBwdMaxDim];                 // pre-stage vectors of every layer (local memory)
-    for (int j = 0; j < d; ++j) x[j] = a.in[row * a.ld_in + j];
-    // ---- forward, recomputed ----
-    for (int l = L - 1; l >= 0; --l) {
-        const GfLayerC<T>& c = g.layers[l];
-        if (c.has_offset)
-            for (int j = 0; j < d; ++j) x[j] -= prow[(int64_t)(c.raw_off + j) * sj];
-        if (c.hh_iter > 0)
-            householder_apply<T, kBwdMaxDim>(x, d, c.hh_iter, true, false, nullptr, prow + (int64_t)c.raw_hh() * sj, sj);
-        for (int j = 0; j < d; ++j) {
-            vs[l * kBwdMaxDim + j] = x[j];
-            const MixView<T> mv = regulate_to_slots<T>(c, c.K, j, prow, sj, slots);
-            T y, logd;
-            gf_eval_logpdf<T>(mv, c.inv_type, x[j], y, logd);
-            x[j] = y;
-        }
-    }
-    // ---- backward ----
-    const T gr = g.grad_logp ? g.grad_logp[row] : T(1);
-    T xb[kBwdMaxDim];
-    for (int j = 0; j < d; ++j) xb[j] = -x[j] * gr;   // d/dz of sum_j log N(z_j)
-    int n_bad = 0;
-    for (int l = 0; l < L; ++l) {
-        const GfLayerC<T>& c = g.layers[l];
-        T v[kBwdMaxDim];
-        for (int j = 0; j < d; ++j) {
-            v[j] = vs[l * kBwdMaxDim + j];
-            const T G = bwd_regulate<T>(c, c.K, j, prow, sj, slots);
-            T vbar;
-            if (!gf_elem_backward<T>(c, c.K, j, v[j], xb[j], gr, G, slots, grow, sj, vbar)) {
-                ++n_bad;
-                JF_BWD_UNROLL
-                for (int k = 0; k < c.K; ++k) {       // no stage gradient for rows in the Pade tails
-                    grow[(int64_t)(c.raw_m() + k * d + j) * sj] = T(0);
-                    grow[(int64_t)(c.raw_w() + k * d + j) * sj] = T(0);
-                    if (c.norm_mode != JF_NORM_NONE) grow[(int64_t)(c.raw_n() + k * d + j) * sj] = T(0);
-                }
-            }
-            xb[j] = vbar;
-        }
-        // rotation v = H_{n-1} ... H_0 u : go back reflection by reflection (each one is its own inverse)
-        for (int i = c.hh_iter - 1; i >= 0; --i) {
-            const T* pv = prow + (int64_t)(c.raw_hh() + i * d) * sj;
-            T* gv = grow + (int64_t)(c.raw_hh() + i * d) * sj;
-            T s = 0, aa = 0, bb = 0;
-            for (int j = 0; j < d; ++j) {
-                const T w = pv[(int64_t)j * sj];
-                s = fma(w, w, s);
-                aa = fma(w, v[j], aa);                // v . x_out  ( = -(v . x_in) )
-                bb = fma(w, xb[j], bb);
-            }
-            const T is = T(1) / s;
-            const T ain = -aa;                        // v . x_in, since x_in = x_out - 2 (v.x_out)/s v
-            for (int j = 0; j < d; ++j) {
-                const T w = pv[(int64_t)j * sj];
-                const T xin = v[j] - T(2) * aa * is * w;
-                gv[(int64_t)j * sj] = -T(2) * is * (bb * xin + ain * xb[j]) + T(4) * ain * bb * is * is * w;
-                xb[j] -= T(2) * bb * is * w;
-                v[j] = xin;
-            }
-        }
-        if (c.has_offset)
-            for (int j = 0; j < d; ++j) grow[(int64_t)(c.raw_off + j) * sj] = -xb[j];
-    }
-    if (n_bad) status_add(a.status, JF_STATUS_OUT_OF_RANGE, n_bad);
 }
 
 }  // namespace jf

@@ -7,7 +7,7 @@
 // tensor memory -- tf32 keeps 10 mantissa bits of each operand: the gradients of the generator weights carry a relative
 // error of ~1e-3 / sqrt(terms) (stated tolerance, tests/test_cuda_training.py: 2e-3 of the tensor maximum against fp64):
 //   bw_dh_kernel    dh[B,128]   = G^T W2            M = 128 rows, N = 128, K = P   (one CTA per 128 rows)
-//                   epilogue: dpre = dh (1 - h^2) -> [B,128] row major
+//                   epilogue: dpre = dh (1 - h^2) s -> [B,128] row major   (s: optional per-row scale of the upstream gradient)
 //   bw_dw2_kernel   [dW2 | db2] = G [h | 1]         M = 128 parameters, N = 144, K = rows (CTA = parameter tile x row range,
 //                   partial sums added with red.global)
 // Operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout (8 x 16 B core matrices; the same
@@ -92,15 +92,27 @@ __global__ void __launch_bounds__(256) bw_h_tiles_kernel(const BwArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[j] = fmaf(xi, w[j], z[j]);
     }
+    // the upstream gradient of row r is G[., r] * s_r (s = 1 without row_scale): the scale rides on the B operand of the
+    // dW2 product (h s | s) and on the factor (1 - h^2) s of the dh epilogue, G itself is never rescaled
+    const float sr = (live && a.row_scale != nullptr) ? a.row_scale[row0 + r] : 1.f;
+    float fc[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-        *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, ug * 16 + j, r)) = live ? to_tf32(tanhf(z[j])) : 0.f;
-    // column 128 = 1 (its product with G is db2), the padding columns are zero
+    for (int j = 0; j < 16; ++j) {
+        const float h = tanhf(z[j]);
+        *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, ug * 16 + j, r)) = live ? to_tf32(h * sr) : 0.f;
+        fc[j] = (1.f - h * h) * sr;
+    }
+    if (live) {
+        float4* dst = reinterpret_cast<float4*>(a.fac + (row0 + r) * kBwH + ug * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(fc[4 * q], fc[4 * q + 1], fc[4 * q + 2], fc[4 * q + 3]);
+    }
+    // column 128 = s (its product with G is db2), the padding columns are zero
     if (ug < 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = kBwH + ug * 8 + j;
-            *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, n, r)) = (n == kBwH && live) ? 1.f : 0.f;
+            *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, n, r)) = (n == kBwH && live) ? to_tf32(sr) : 0.f;
         }
     }
 }
@@ -216,8 +228,7 @@ __global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
         tc_fence_after();
         const int r = warp * 32 + lane;
         const int64_t row = row0 + r;
-        const char* ht = reinterpret_cast<const char*>(a.h_tiles) + (size_t)(row / kBwKC) * (kBwNExt * kBwKC * 4);
-        const int kr = (int)(row % kBwKC);
+        const float* fc = a.fac + row * kBwH;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int n0 = 0; n0 < kBwH; n0 += 8) {
@@ -225,12 +236,11 @@ __global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
             tmem_ld8(tl + n0, v);
             tmem_ld_wait();
             if (row < a.B) {
+                const float4 f0 = *reinterpret_cast<const float4*>(fc + n0), f1 = *reinterpret_cast<const float4*>(fc + n0 + 4);
+                const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float h = *reinterpret_cast<const float*>(ht + bw_tile_off(kBwNExt, n0 + j, kr));
-                    o[j] = __int_as_float(v[j]) * (1.f - h * h);
-                }
+                for (int j = 0; j < 8; ++j) o[j] = __int_as_float(v[j]) * f[j];
                 float4* dst = reinterpret_cast<float4*>(a.dpre + row * kBwH + n0);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_float4(o[4], o[5], o[6], o[7]);

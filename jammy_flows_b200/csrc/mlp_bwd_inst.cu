@@ -9,7 +9,7 @@ static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 int64_t mlp_bwd_workspace_bytes(int P, int64_t B) {
     const int64_t w2 = (int64_t)((P + kBwKC - 1) / kBwKC) * kDhTile;
     const int64_t ht = ((B + kBwKC - 1) / kBwKC) * (int64_t)kW2TileB;
-    return align256(w2) + align256(ht) + align256(B * kBwH * 4);
+    return align256(w2) + align256(ht) + 2 * align256(B * kBwH * 4);
 }
 
 int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
@@ -23,6 +23,7 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
     a.w2_tiles = (float*)ws;
     a.h_tiles = (float*)(ws + align256((int64_t)n_ptiles32 * kDhTile));
     a.dpre = (float*)((char*)a.h_tiles + align256(n_rtiles32 * (int64_t)kW2TileB));
+    a.fac = (float*)((char*)a.dpre + align256(a.B * kBwH * 4));
     bw_w2_tiles_kernel<<<n_ptiles32, 256, 0, st>>>(a.W2, a.P, a.w2_tiles);
     {
         const int smem = (a.in * kBwH + kBwKC * (a.in | 1)) * 4;

@@ -13,6 +13,8 @@ struct BwArgs {
     float* w2_tiles;                        // workspace: ceil(P/32) tiles [128 n][32 k]
     float* h_tiles;                         // workspace: ceil(B/32) tiles [144 n][32 k]
     float* dpre;                            // workspace: [B, 128]
+    const float* row_scale;                 // optional [B]: the upstream gradient is G[p, row] * row_scale[row]
+    float* fac;                             // workspace: [B, 128] (1 - h^2) * row_scale
     float* dW1; float* db1; float* dW2; float* db2;   // outputs (zeroed by the caller, accumulated)
     float* dx; int64_t lddx;                // optional [B, in]
     int n_splits;                           // bw_dw2: row ranges per parameter tile

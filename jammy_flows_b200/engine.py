@@ -854,8 +854,33 @@ def subpdf_logpdf_forward(pdf, k, params_t, x_k):
     return logdet + logbase, logbase, base
 
 
+def subpdf_logpdf_fb(pdf, k, params_t, x_k, g_logp=None):
+    """Forward AND backward of Euclidean sub-pdf k in one kernel (`jf_subpdf_forward_backward`, csrc/gf_fb.cuh)
+    -> (log_pdf_k [B], log_base_k [B], base_k [B, d], jac [P, B], jx [B, d]).  With g_logp = None, jac / jx are the
+    per-row Jacobians d log_pdf_k[row] / d params[:, row] and / d x_k[row]; the autograd formulas of ops.py scale them by
+    the upstream gradient (the tensor-core generator backward takes it as `row_scale`, so the [P, B] block is never
+    rescaled in HBM).  Body of the ops `jammy_b200::subpdf_logpdf` / `jammy_b200::generated_logpdf`."""
+    lib = _cabi.load()
+    B, d = x_k.shape
+    dt, dev = x_k.dtype, x_k.device
+    sub_desc, status = pdf._desc(dt).sub[k], pdf._status(dev)
+    base = torch.empty(B, d, dtype=dt, device=dev)
+    logdet = torch.empty(B, dtype=dt, device=dev)
+    logbase = torch.empty(B, dtype=dt, device=dev)
+    jac = torch.empty_like(params_t)
+    jx = torch.empty(B, d, dtype=dt, device=dev)
+    g = None if g_logp is None else g_logp.contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_forward_backward(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
+                                            params_t.stride(0), 1, _ptr(g), _ptr(jac), _ptr(jx), d, _ptr(base), d,
+                                            _ptr(logdet), _ptr(logbase), B, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_forward_backward")
+    return logdet + logbase, logbase, base, jac, jx
+
+
 def subpdf_logpdf_backward(pdf, k, params_t, x_k, g_logp):
-    """Gradient of sum(g_logp * log p_k) with respect to the per-row parameters (`jf_subpdf_backward`, csrc/gf_bwd.cuh)."""
+    """Gradient of sum(g_logp * log p_k) with respect to the per-row parameters (`jf_subpdf_backward`: the same kernel
+    with the forward outputs switched off)."""
     lib = _cabi.load()
     B = x_k.shape[0]
     dt, dev = x_k.dtype, x_k.device
@@ -897,11 +922,14 @@ def mlp_params_forward(inp, w1, b1, w2, b2):
     return out
 
 
-def mlp_params_backward(inp, w1, b1, w2, g, want_inp_grad):
-    """Gradient of the generator given g = d loss / d params [P, B].  fp32: `jf_mlp_backward` (tensor cores, tf32);
-    fp64: library GEMMs (the fp64 training contract is 1e-8).  The hidden activations are recomputed."""
+def mlp_params_backward(inp, w1, b1, w2, g, want_inp_grad, row_scale=None):
+    """Gradient of the generator given d loss / d params [P, B] = g (* row_scale[None, :] if given).  fp32:
+    `jf_mlp_backward` (tensor cores, tf32); fp64: library GEMMs (the fp64 training contract is 1e-8).  The hidden
+    activations are recomputed."""
     if g.dtype == torch.float32:
-        return _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad)
+        return _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad, row_scale)
+    if row_scale is not None:
+        g = g * row_scale.unsqueeze(0)
     h = torch.tanh(torch.addmm(b1, inp, w1.t()))         # [B, 128]
     g_w2 = torch.mm(g, h)                                # [P, 128]
     g_b2 = g.sum(dim=1)
@@ -914,7 +942,7 @@ def mlp_params_backward(inp, w1, b1, w2, g, want_inp_grad):
     return g_inp, g_w1, g_b1, g_w2, g_b2
 
 
-def _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad):
+def _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad, row_scale=None):
     """fp32 gradient of the generator on the tensor cores (`jf_mlp_backward`, csrc/mlp_bwd.cuh): h is recomputed, the two
     [P, B]-sized products run as tcgen05 kind::tf32 MMAs, the small ones as FFMA; g is read twice from HBM and nothing of
     its size is written."""
@@ -931,6 +959,7 @@ def _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad):
         gp = torch.zeros(P, (B + 3) // 4 * 4, dtype=g.dtype, device=dev)
         gp[:, :B] = g
         g = gp
+    rs = None if row_scale is None else row_scale.to(dtype=g.dtype).contiguous()
     inp_c = inp if inp.stride(1) == 1 else inp.contiguous()
     ws_ = [w1.detach().contiguous(), w2.detach().contiguous()]
     bs_ = [b1.detach().contiguous(), b1.detach().contiguous()]
@@ -945,7 +974,7 @@ def _mlp_backward_tc(inp, w1, b1, w2, g, want_inp_grad):
     ws = _workspace(dev, max(int(nws), 16))
     with torch.cuda.device(dev):
         rc = lib.jf_mlp_backward(C.byref(md), _cabi.JF_F32, _ptr(inp_c), inp_c.stride(0), wp, bp, _ptr(g), g.stride(0), 1,
-                                 _ptr(g_w1), _ptr(g_b1), _ptr(g_w2), _ptr(g_b2), _ptr(g_inp),
+                                 _ptr(rs), _ptr(g_w1), _ptr(g_b1), _ptr(g_w2), _ptr(g_b2), _ptr(g_inp),
                                  g_inp.stride(0) if g_inp is not None else 0, B, _ptr(ws), ws.numel(), _stream_ptr(dev))
     _cabi.check(rc, "jf_mlp_backward")
     return g_inp, g_w1, g_b1, g_w2, g_b2
@@ -980,9 +1009,6 @@ def pdf_logpdf_trainable(pdf, x, cond):
     """-> (log_pdf [B] with autograd history, log_pdf_base [B], base [B, D]).  Reference: main/default.py:1059-1117 with
     `torch.is_grad_enabled()`; the conditioning on earlier sub-pdfs uses the data x (no gradient flows through it)."""
     x, cond = _prep_inputs(pdf, x, cond, "x")
-    if x.requires_grad:
-        raise NotImplementedError("gradients with respect to the evaluation points x are not provided by the backward "
-                                  "kernels (parameters and conditional_input are); detach x")
     from . import ops
     dt, dev = x.dtype, x.device
     handle = ops.handle_of(pdf)
@@ -1002,14 +1028,22 @@ def pdf_logpdf_trainable(pdf, x, cond):
             inp = torch.cat(pieces, dim=1) if len(pieces) > 1 else pieces[0]
             mods = list(mlp)
             if _tc_mlp_eligible(mlp, dt, dev):
-                params_t = torch.ops.jammy_b200.mlp_params(inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias)
+                # generator + layer chain as ONE autograd node: the forward keeps the per-row Jacobian instead of the
+                # parameter block, the backward is the tensor-core generator gradient with the upstream gradient as row scale
+                lp_k, lb_k, base_k, _, _ = torch.ops.jammy_b200.generated_logpdf(
+                    inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias, x_k.contiguous(), handle, k)
+                logp = lp_k if logp is None else logp + lp_k
+                logp_base = lb_k if logp_base is None else logp_base + lb_k
+                bases.append(base_k)
+                prev.append(x_k)
+                continue
             else:
                 h = inp
                 for m in mods[:-1]:
                     h = m(h)
                 last = mods[-1]
                 params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())    # [P, B], param-major
-        lp_k, lb_k, base_k = torch.ops.jammy_b200.subpdf_logpdf(params_t, x_k.contiguous(), handle, k)
+        lp_k, lb_k, base_k, _, _ = torch.ops.jammy_b200.subpdf_logpdf(params_t, x_k.contiguous(), handle, k)
         logp = lp_k if logp is None else logp + lp_k
         logp_base = lb_k if logp_base is None else logp_base + lb_k
         bases.append(base_k)

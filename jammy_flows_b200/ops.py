@@ -77,16 +77,20 @@ def _(z, cond, handle, chunk_rows):
 # ---------------------------------------------------------------------------------------------------------------------
 # training ops
 # ---------------------------------------------------------------------------------------------------------------------
+_Out5 = Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]
+
+
 @torch.library.custom_op("jammy_b200::subpdf_logpdf", mutates_args=(), device_types="cuda")
-def subpdf_logpdf(params_t: torch.Tensor, x_k: torch.Tensor, handle: int, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def subpdf_logpdf(params_t: torch.Tensor, x_k: torch.Tensor, handle: int, k: int) -> _Out5:
+    """-> (log_pdf, log_base, base, jac, jx): forward and per-row Jacobians from one kernel (jf_subpdf_forward_backward)"""
     p = _pdf(handle)
-    return engine.subpdf_logpdf_forward(p, k, params_t, x_k)
+    return engine.subpdf_logpdf_fb(p, k, params_t, x_k)
 
 
 @subpdf_logpdf.register_fake
 def _(params_t, x_k, handle, k):
     B = x_k.shape[0]
-    return x_k.new_empty(B), x_k.new_empty(B), x_k.new_empty(B, x_k.shape[1])
+    return x_k.new_empty(B), x_k.new_empty(B), x_k.new_empty(B, x_k.shape[1]), torch.empty_like(params_t), torch.empty_like(x_k)
 
 
 @torch.library.custom_op("jammy_b200::subpdf_logpdf_backward", mutates_args=(), device_types="cuda")
@@ -101,18 +105,65 @@ def _(params_t, x_k, g_logp, handle, k):
 
 
 def _subpdf_setup(ctx, inputs, output):
-    params_t, x_k, handle, k = inputs
-    ctx.save_for_backward(params_t, x_k)
-    ctx.handle, ctx.k = handle, k
+    ctx.save_for_backward(output[3], output[4])          # the Jacobians; the parameter block itself is not kept
 
 
-def _subpdf_bwd(ctx, g_logp, g_logbase, g_base):
-    params_t, x_k = ctx.saved_tensors
-    grad = torch.ops.jammy_b200.subpdf_logpdf_backward(params_t, x_k, g_logp.contiguous(), ctx.handle, ctx.k)
-    return grad, None, None, None
+def _subpdf_bwd(ctx, g_logp, g_logbase, g_base, g_jac, g_jx):
+    jac, jx = ctx.saved_tensors
+    g_params = jac * g_logp.unsqueeze(0) if ctx.needs_input_grad[0] else None
+    g_x = jx * g_logp.unsqueeze(1) if ctx.needs_input_grad[1] else None
+    return g_params, g_x, None, None
 
 
 subpdf_logpdf.register_autograd(_subpdf_bwd, setup_context=_subpdf_setup)
+
+
+@torch.library.custom_op("jammy_b200::generated_logpdf", mutates_args=(), device_types="cuda")
+def generated_logpdf(inp: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                     x_k: torch.Tensor, handle: int, k: int) -> _Out5:
+    """Generator (tcgen05 MLP kernel) + layer chain forward/backward kernel of sub-pdf k; the [P, B] parameter block is a
+    temporary of this call, what stays for the backward is the Jacobian block."""
+    p = _pdf(handle)
+    params_t = engine.mlp_params_forward(inp, w1, b1, w2, b2)
+    return engine.subpdf_logpdf_fb(p, k, params_t, x_k)
+
+
+@generated_logpdf.register_fake
+def _(inp, w1, b1, w2, b2, x_k, handle, k):
+    B = x_k.shape[0]
+    return (x_k.new_empty(B), x_k.new_empty(B), x_k.new_empty(B, x_k.shape[1]), inp.new_empty(w2.shape[0], B),
+            torch.empty_like(x_k))
+
+
+def _generated_setup(ctx, inputs, output):
+    inp, w1, b1, w2, b2, x_k, handle, k = inputs
+    ctx.save_for_backward(inp, w1, b1, w2, output[3], output[4])
+
+
+def _generated_bwd(ctx, g_logp, g_logbase, g_base, g_jac, g_jx):
+    inp, w1, b1, w2, jac, jx = ctx.saved_tensors
+    want = ctx.needs_input_grad[0]
+    g_inp, g_w1, g_b1, g_w2, g_b2 = torch.ops.jammy_b200.mlp_params_backward_scaled(inp, w1, b1, w2, jac, g_logp.contiguous(), want)
+    g_x = jx * g_logp.unsqueeze(1) if ctx.needs_input_grad[5] else None
+    return (g_inp if want else None), g_w1, g_b1, g_w2, g_b2, g_x, None, None
+
+
+generated_logpdf.register_autograd(_generated_bwd, setup_context=_generated_setup)
+
+
+@torch.library.custom_op("jammy_b200::mlp_params_backward_scaled", mutates_args=(), device_types="cuda")
+def mlp_params_backward_scaled(inp: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, jac: torch.Tensor,
+                               row_scale: torch.Tensor, want_inp_grad: bool) -> _Out5:
+    g_inp, g_w1, g_b1, g_w2, g_b2 = engine.mlp_params_backward(inp, w1, b1, w2, jac, want_inp_grad, row_scale)
+    if g_inp is None:
+        g_inp = inp.new_zeros(0)
+    return g_inp, g_w1, g_b1, g_w2, g_b2
+
+
+@mlp_params_backward_scaled.register_fake
+def _(inp, w1, b1, w2, jac, row_scale, want_inp_grad):
+    return (torch.empty_like(inp) if want_inp_grad else inp.new_empty(0), torch.empty_like(w1), torch.empty_like(b1),
+            torch.empty_like(w2), w2.new_empty(w2.shape[0]))
 
 
 @torch.library.custom_op("jammy_b200::mlp_params", mutates_args=(), device_types="cuda")

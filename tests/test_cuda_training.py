@@ -67,6 +67,68 @@ def test_fp32_gradients_close_to_fp64(lib_built):
         assert err < 2e-3, (k, err)
 
 
+def test_weighted_loss_gradients_match_oracle_autograd(lib_built):
+    """a per-row upstream gradient (loss = sum_r w_r log p_r): the forward pass keeps the per-row Jacobian and the backward
+    scales it by w_r (elementwise in fp64, as `row_scale` of the tensor-core generator backward in fp32)"""
+    from oracle.jf_oracle import OraclePdf
+    p, y, c = _cfg5(64)
+    w = torch.linspace(-0.5, 2.0, 64, dtype=torch.float64)
+    o = OraclePdf(p.export_program("float64"), {k: v.numpy() for k, v in p.state_dict().items()})
+    for t in o.params.values():
+        t.requires_grad_(True)
+    lp, _, _ = o.log_pdf(y.numpy(), c.numpy())
+    (lp * w).sum().backward()
+    ref = {k: t.grad.detach().numpy() for k, t in o.params.items() if t.grad is not None}
+    pc = p.cuda()
+    pc.zero_grad()
+    lpc, _, _ = pc(y.cuda(), conditional_input=c.cuda())
+    (lpc * w.cuda()).sum().backward()
+    for k, r in ref.items():
+        g = dict(pc.named_parameters())[k].grad.cpu().numpy()
+        err = np.abs(g - r).max() / max(np.abs(r).max(), 1e-30)
+        assert err < 1e-8, (k, err)
+    # fp32: the same loss through jf_mlp_backward's row_scale (tf32 products: 2e-3 of the tensor maximum)
+    p32 = p.float().cuda()
+    p32.zero_grad()
+    lp32, _, _ = p32(y.float().cuda(), conditional_input=c.float().cuda())
+    (lp32 * w.float().cuda()).sum().backward()
+    for k, r in ref.items():
+        g = dict(p32.named_parameters())[k].grad.double().cpu().numpy()
+        err = np.abs(g - r).max() / max(np.abs(r).max(), 1e-30)
+        assert err < 2e-3, (k, err)
+
+
+def test_gradients_wrt_x_and_conditional_input_by_finite_differences(lib_built):
+    """the reference differentiates log_pdf through the evaluation points and the conditional input as well
+    (autograd); here d log_pdf / d x comes out of the forward + backward kernel (grad_x) and flows on through the
+    generators of the later sub-pdfs, d / d cond through jf_mlp_backward / the fp64 GEMMs"""
+    torch.manual_seed(2)
+    np.random.seed(2)
+    p = jfb.pdf("e3+e2", "ggg+gg", conditional_input_dim=5).double()
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for q in p.parameters():
+            q.add_(0.05 * torch.randn(q.shape, generator=g, dtype=torch.float64))
+    p = p.cuda()
+    n = 16
+    x = torch.randn(n, 5, generator=g, dtype=torch.float64).cuda().requires_grad_(True)
+    c = torch.randn(n, 5, generator=g, dtype=torch.float64).cuda().requires_grad_(True)
+    w = torch.linspace(0.5, 1.5, n, dtype=torch.float64).cuda()
+    lp, _, _ = p(x, conditional_input=c)
+    (lp * w).sum().backward()
+    h = 1e-6
+    with torch.no_grad():
+        for t, gt in ((x, x.grad), (c, c.grad)):
+            for col in range(t.shape[1]):
+                e = torch.zeros_like(t)
+                e[:, col] = h
+                args = lambda s: (x + s * e, c) if t is x else (x, c + s * e)
+                xa, ca = args(1.0)
+                xb, cb = args(-1.0)
+                fd = (p(xa, conditional_input=ca)[0] - p(xb, conditional_input=cb)[0]) / (2 * h) * w
+                assert (fd - gt[:, col]).abs().max() < 1e-6 * max(1.0, float(gt.abs().max())), (t is x, col)
+
+
 def test_adam_steps_decrease_the_loss(lib_built):
     """a few optimiser steps on synthetic conditional data: the negative log-likelihood goes down, nothing goes non-finite"""
     p, _, c = _cfg5(8192, scale=0.0)
