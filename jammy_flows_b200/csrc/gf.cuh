@@ -30,7 +30,7 @@ namespace jf {
 
 // 1/x for a positive normal x (hardware seed + two Newton steps; no special-case handling)
 JF_DEVINL double rcp_pos_(double x) { return rcp_1to2(x); }
-JF_DEVINL float rcp_pos_(float x) { return 1.0f / x; }
+JF_DEVINL float rcp_pos_(float x) { return rcp_1to2(x); }   // rcp.approx.ftz: 1 ulp, no slow path
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Layer constants (host fills from JfLayerDesc)

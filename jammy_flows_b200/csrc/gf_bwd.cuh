@@ -37,18 +37,26 @@ __device__ __noinline__ T bwd_regulate(const GfLayerC<T>& c, int K, int j, const
     const T* pw = p + (int64_t)(c.raw_w() + j) * sj;
     const T* pn = p + (int64_t)(c.raw_n() + j) * sj;
     const int64_t step = (int64_t)d * sj;
+    // phase 1: raw values -> slots (a pure copy loop keeps 3 x 8 independent loads in flight: the latency of the parameter
+    // stream is paid once per (layer, dimension), not once per kernel)
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+        sm[(size_t)k * nt] = pm[k * step];
+        si[(size_t)k * nt] = pw[k * step];
+        sn[(size_t)k * nt] = (c.norm_mode != JF_NORM_NONE) ? pn[k * step] : T(0);
+    }
+    // phase 2: regulate in place
     T nmax = -Num<T>::big;
     if (c.norm_mode == JF_NORM_RAW)
         JF_BWD_UNROLL
-        for (int k = 0; k < K; ++k) nmax = tmax(nmax, pn[k * step]);
+        for (int k = 0; k < K; ++k) nmax = tmax(nmax, sn[(size_t)k * nt]);
     T G = 0;
     JF_BWD_UNROLL
     for (int k = 0; k < K; ++k) {
-        sm[(size_t)k * nt] = pm[k * step];
-        si[(size_t)k * nt] = regulate_inv_width(pw[k * step], c.w_min, c.inv_w_max);
+        si[(size_t)k * nt] = regulate_inv_width(si[(size_t)k * nt], c.w_min, c.inv_w_max);
         T g;
-        if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(pn[k * step], c.n_min, c.n_max);
-        else if (c.norm_mode == JF_NORM_RAW) g = exp(pn[k * step] - nmax);
+        if (c.norm_mode == JF_NORM_REGULATED) g = regulate_norm(sn[(size_t)k * nt], c.n_min, c.n_max);
+        else if (c.norm_mode == JF_NORM_RAW) g = exp(sn[(size_t)k * nt] - nmax);
         else g = T(1);
         sn[(size_t)k * nt] = g;
         G += g;
@@ -65,7 +73,7 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
     const T* sm = slots + threadIdx.x;
     const T* si = sm + (size_t)K * nt;
     const T* sn = si + (size_t)K * nt;
-    const T invG = T(1) / G;
+    const T invG = rcp_pos_(G);
     // ---- pass 1: common rescaling exponent (all kernels on one side of v) ----
     bool any_pos = false, any_neg = false;
     T delta = Num<T>::big;
@@ -85,8 +93,8 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
     for (int k = 0; k < K; ++k) {
         const T iw = si[(size_t)k * nt], n = sn[(size_t)k * nt] * invG;
         const T a = (v - sm[(size_t)k * nt]) * iw;
-        const T u = exp(delta - fabs(a)), e = u * E;
-        const T rx = T(1) / (T(1) + e);
+        const T u = exp_neg(delta - fabs(a)), e = u * E;
+        const T rx = rcp_1to2(T(1) + e);
         const T big = n * rx, small = big * u;
         if (a >= T(0)) { Sc += big; Ss += small; } else { Sc += small; Ss += big; }
         const T pt = small * iw * rx;                 // n sigma (1-sigma) / w, rescaled by 1/E
@@ -153,8 +161,8 @@ __device__ __noinline__ bool gf_elem_backward(const GfLayerC<T>& c, int K, int j
     for (int k = 0; k < K; ++k) {
         const T m = sm[(size_t)k * nt], iw = si[(size_t)k * nt], g = sn[(size_t)k * nt], n = g * invG;
         const T a = (v - m) * iw;
-        const T u = exp(delta - fabs(a)), e = u * E;
-        const T rx = T(1) / (T(1) + e);
+        const T u = exp_neg(delta - fabs(a)), e = u * E;
+        const T rx = rcp_1to2(T(1) + e);
         const T t = u * rx * rx;                                    // sigma (1-sigma) / E
         const T om2s = (a >= T(0) ? -(T(1) - e) : (T(1) - e)) * rx; // 1 - 2 sigma
         const T mbar = n * (-cCS * t * iw - glp * t * om2s * iw * iw);

@@ -23,6 +23,252 @@
 
 namespace jf {
 
+// ask L2 for the parameters this worker reads in ANOTHER layer (its own column: offset, reflection components, the K
+// triples) while the current layer is being computed: the [P, rows] block is streamed from HBM exactly once per
+// direction, and with ~30 warps per SM a first touch that goes to HBM is not hidden (ncu: long_scoreboard 45 % of the samples)
+template <typename T>
+JF_DEVINL void fb_prefetch_layer(const GfLayerC<T>& c, int D, int j, const T* prow, int64_t sj) {
+    if (c.has_offset) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(c.raw_off + j) * sj));
+#pragma unroll 1
+    for (int i = 0; i < c.hh_iter; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(c.raw_hh() + i * D + j) * sj));
+    const T* pm = prow + (int64_t)(c.raw_m() + j) * sj;
+    const int64_t step = (int64_t)D * sj;
+    const int nf = c.norm_mode != JF_NORM_NONE ? 3 * c.K : 2 * c.K;       // m, w, n blocks are contiguous: K*D rows each
+#pragma unroll 1
+    for (int k = 0; k < nf; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + k * step));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Register-resident mixture of one (layer, dimension) for a compile-time K: the K raw triples are loaded back to back
+// (3 K independent loads in flight), regulated into registers and consumed there -- no shared-memory slots, no address
+// arithmetic in the loops, every loop unrolled.  The first version drove csrc/gf.cuh's slot-based helpers (rolled loops,
+// 64-bit slot indices): ncu counted 8 600 instructions per (row, layer, dimension) forward + backward, 760 per mixture
+// kernel, against ~200 of arithmetic.  Same formulas as mix_eval / gf_elem_backward (which stay the path for other K).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kFbFastK = 10;   // the default num_kde of the reference (flow_options.py): register-resident path
+
+template <typename T, int K>
+struct FbMix {
+    T m[K], iw[K], g[K];   // means, regulated 1/width, unnormalised regulated weights
+    T G;                   // sum of the weights
+};
+
+// pm: address of (raw_m + j) of this row; the m / w / n blocks follow each other, K * d parameters each (step = d * sj)
+template <typename T, int K>
+JF_DEVINL void fb_load(const GfLayerC<T>& c, const T* pm, int64_t step, FbMix<T, K>& M) {
+    T rw[K], rn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        M.m[k] = pm[k * step];
+        rw[k] = pm[(K + k) * step];
+    }
+    if (c.norm_mode != JF_NORM_NONE) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rn[k] = pm[(2 * K + k) * step];
+    }
+    T G = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) M.iw[k] = regulate_inv_width(rw[k], c.w_min, c.inv_w_max);
+    if (c.norm_mode == JF_NORM_REGULATED) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { M.g[k] = regulate_norm(rn[k], c.n_min, c.n_max); G += M.g[k]; }
+    } else if (c.norm_mode == JF_NORM_RAW) {
+        T nmax = -Num<T>::big;
+#pragma unroll
+        for (int k = 0; k < K; ++k) nmax = tmax(nmax, rn[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { M.g[k] = exp(rn[k] - nmax); G += M.g[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) M.g[k] = T(1);
+        G = T(K);
+    }
+    M.G = G;
+}
+
+// rescaling exponent (see mix_eval): 0 unless every kernel lies on one side of x
+template <typename T, int K>
+JF_DEVINL T fb_delta(const FbMix<T, K>& M, T x, bool& all_neg, bool& all_pos) {
+    bool any_pos = false, any_neg = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const bool pos = x >= M.m[k];                  // 1/w > 0: sign(a_k) = sign(x - m_k)
+        any_pos = any_pos || pos;
+        any_neg = any_neg || !pos;
+    }
+    all_neg = !any_pos;
+    all_pos = !any_neg;
+    T delta = 0;
+    if (all_neg || all_pos) {
+        delta = Num<T>::big;
+#pragma unroll
+        for (int k = 0; k < K; ++k) delta = tmin(delta, fabs((x - M.m[k]) * M.iw[k]));
+    }
+    return delta;
+}
+
+// forward of one element: load + regulate + mixture + inverse-CDF stage
+template <typename T, int K>
+__device__ __noinline__ void fb_fwd_elem(const GfLayerC<T>& c, const T* pm, int64_t step, T x, T& y, T& logd) {
+    FbMix<T, K> M;
+    fb_load<T, K>(c, pm, step, M);
+    bool all_neg, all_pos;
+    const T delta = fb_delta<T, K>(M, x, all_neg, all_pos);
+    const T E = (delta > T(0)) ? exp_neg(-delta) : T(1);
+    T big_p = 0, small_p = 0, big_n = 0, small_n = 0, Sp = 0, amin = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const T iw = M.iw[k];
+        const T a = (x - M.m[k]) * iw;
+        const T u = exp_neg(delta - fabs(a));
+        const T rx = rcp_1to2(fma(u, E, T(1)));        // exact sigma(|a|)
+        const T nr = M.g[k] * rx, nur = nr * u;
+        const bool pos = a >= T(0);
+        big_p += pos ? nr : T(0);
+        small_p += pos ? nur : T(0);
+        big_n += pos ? T(0) : nr;
+        small_n += pos ? T(0) : nur;
+        Sp = fma(nur * iw, rx, Sp);
+        amin = tmin(amin, a);
+    }
+    T ex = 0, qc = 0;
+    if (amin < T(-20)) {                               // softplus-threshold quirk of the reference, see mix_eval (rare)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const T iw = M.iw[k];
+            const T a = (x - M.m[k]) * iw;
+            if (a < T(-20)) {
+                const T u = exp_neg(delta - fabs(a));
+                const T e = u * E;
+                const T rx = rcp_1to2(T(1) + e);
+                const T nq = M.g[k] * e * rx;
+                ex += nq;
+                qc = fma(nq, u, qc);
+                Sp = fma(nq * u * iw, T(1) + rx, Sp);
+            }
+        }
+    }
+    const T invG = rcp_pos_(M.G);
+    MixVal<T> v;
+    v.Sc = (big_p + small_n + qc) * invG;
+    v.Ss = (small_p + big_n) * invG;
+    v.Sp = Sp * invG;
+    v.ex = ex * invG;
+    v.Sd = 0;
+    v.E = E;
+    v.dc = all_neg ? delta : T(0);
+    v.ds = all_pos ? delta : T(0);
+    v.dp = delta;
+    inv_stage(c.inv_type, v, y, logd);
+}
+
+// backward of one element (v -> (y, l); gy, gl upstream): writes the raw-parameter gradients of this (layer, dimension)
+// through gm (address of (raw_m + j) in the gradient block), returns d/dv in vbar; false for rows outside the supported
+// stages.  Formulas: csrc/gf_bwd.cuh gf_elem_backward.
+template <typename T, int K>
+__device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* gm, int64_t step, T v, T gy, T gl, T& vbar) {
+    FbMix<T, K> M;
+    fb_load<T, K>(c, pm, step, M);
+    const T invG = rcp_pos_(M.G);
+    bool all_neg, all_pos;
+    const T delta = fb_delta<T, K>(M, v, all_neg, all_pos);
+    const T E = (delta > T(0)) ? exp_neg(-delta) : T(1);
+    T Sc = 0, Ss = 0, Sp = 0, Sd = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const T iw = M.iw[k], n = M.g[k] * invG;
+        const T a = (v - M.m[k]) * iw;
+        const T u = exp_neg(delta - fabs(a)), e = u * E;
+        const T rx = rcp_1to2(T(1) + e);
+        const T big = n * rx, small = big * u;
+        const bool pos = a >= T(0);
+        Sc += pos ? big : small;
+        Ss += pos ? small : big;
+        const T pt = small * iw * rx;                  // n sigma (1-sigma) / w, rescaled by 1/E
+        Sp += pt;
+        const T dd = pt * iw * (T(1) - e) * rx;
+        Sd += pos ? -dd : dd;
+    }
+    const T fC = all_neg ? T(1) : E, fS = all_pos ? T(1) : E;
+    T y_coefC, y_coefS, nC, nS, nC_true = 0;
+    if (c.inv_type == JF_INV_ISIGMOID) {
+        y_coefC = (gy - gl) * fC / Sc;
+        y_coefS = -(gy + gl) * fS / Ss;
+        nC = (gy - gl) / Sc;
+        nS = -(gy + gl) / Ss;
+    } else {
+        const T Ct = Sc * (all_neg ? E : T(1)), St = Ss * (all_pos ? E : T(1));
+        const T eps = T(0.5e-7);
+        if (c.inv_type != JF_INV_PARTLY_PRECISE) { vbar = T(0); return false; }
+        const bool upper = !(St > eps), lower = !(Ct > eps);
+        if (!upper && !lower) {
+            const T er = (Ct <= T(0.5)) ? -erfcinv(T(2) * Ct) : erfcinv(T(2) * St);
+            const T y = T(1.4142135623730951) * er;
+            const T Dn = T(2.5066282746310002) * exp(er * er);      // 1/phi(y)
+            nC_true = (gy + gl * y) * Dn;
+            y_coefC = nC_true * E;
+            y_coefS = T(0);
+            nC = T(0);
+            nS = T(0);
+        } else {
+            const T pa = T(0.147), pc = T(2.0 / (kPi * 0.147));
+            const T Lf = (log(Sc) - (all_neg ? delta : T(0))) + (log(Ss) - (all_pos ? delta : T(0))) + T(1.3862943611198906);
+            const T F = pc + Lf * T(0.5);
+            const T F2 = sqrt(F * F - Lf / pa);
+            const T dF2 = (F - T(1) / pa) / (T(2) * F2);
+            const T diff = F2 - F;
+            const T yv = (upper ? T(1) : T(-1)) * sqrt(tmax(T(0), T(2) * diff));
+            const T dy = (dF2 - T(0.5)) / yv;
+            const T dl = (dF2 - T(0.5)) / (diff + T(1) / pa) - T(0.5) * (dF2 - T(0.5)) / diff - dF2 / F2;
+            const T gL = gy * dy + gl * dl;
+            nC_true = -T(2) * gl / (T(1) - T(2) * Ct);
+            y_coefC = (gL - gl) * fC / Sc + nC_true * E;
+            y_coefS = (gL - gl) * fS / Ss;
+            nC = (gL - gl) / Sc;
+            nS = (gL - gl) / Ss;
+        }
+    }
+    const T cCS = y_coefC - y_coefS;
+    const T glp = gl / Sp;
+    vbar = cCS * Sp + glp * Sd;
+    T nb[K];
+    T nbar_dot = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const T m = M.m[k], iw = M.iw[k], n = M.g[k] * invG;
+        const T a = (v - m) * iw;
+        const T u = exp_neg(delta - fabs(a)), e = u * E;
+        const T rx = rcp_1to2(T(1) + e);
+        const T t = u * rx * rx;                                    // sigma (1-sigma) / E
+        const bool pos = a >= T(0);
+        const T om2s = (pos ? -(T(1) - e) : (T(1) - e)) * rx;       // 1 - 2 sigma
+        const T mbar = n * (-cCS * t * iw - glp * t * om2s * iw * iw);
+        const T iwbar = n * (cCS * t * (v - m) + glp * t * (T(1) + om2s * a));
+        const T ur = u * rx;
+        const T sigC = pos ? rx : ur, sigS = pos ? ur : rx;
+        const T sig_t = pos ? rx : ur * E;
+        nb[k] = nC * sigC + nS * sigS + nC_true * sig_t + glp * t * iw;
+        nbar_dot = fma(nb[k], n, nbar_dot);
+        gm[k * step] = mbar;
+        // 1/w = q/(w_min q + 1), q = 1/w_max + exp(-raw): d(1/w)/d raw = -(q - 1/w_max) (1 - w_min/w)^2
+        const T om = T(1) - c.w_min * iw;
+        const T q = iw * rcp_pos_(om);
+        gm[(K + k) * step] = -iwbar * (q - c.inv_w_max) * om * om;
+    }
+    if (c.norm_mode != JF_NORM_NONE) {
+        const T inv_nmax = c.norm_mode == JF_NORM_REGULATED ? T(1) / c.n_max : T(0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const T g = M.g[k];
+            const T gbar = (nb[k] - nbar_dot) * invG;               // n_k = g_k / G
+            T dg = g;
+            if (c.norm_mode == JF_NORM_REGULATED) { const T s = (g - c.n_min) * inv_nmax; dg = c.n_max * s * (T(1) - s); }
+            gm[(2 * K + k) * step] = gbar * dg;
+        }
+    }
+    return true;
+}
+
 JF_DEVINL void fb_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <typename T, int D>
@@ -52,9 +298,11 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
 #pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
         const GfLayerC<T>& c = g.layers[l];
+        if (l > 0) fb_prefetch_layer<T>(g.layers[l - 1], D, j, prow, sj);
         if (c.has_offset) xj -= prow[(int64_t)(c.raw_off + j) * sj];
         if (c.hh_iter > 0) {
             ex[(fX + j) * 32] = xj;
+#pragma unroll 4
             for (int i = 0; i < c.hh_iter; ++i) ex[(fH + i * D + j) * 32] = prow[(int64_t)(c.raw_hh() + i * D + j) * sj];
             fb_bar(bar_id, 32 * D);
             T X[D];
@@ -69,7 +317,7 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
                     dot = fma(w[jj], X[jj], dot);
                     nrm = fma(w[jj], w[jj], nrm);
                 }
-                const T cc = T(2) * dot / nrm;
+                const T cc = T(2) * dot * rcp_pos_(nrm);
 #pragma unroll
                 for (int jj = 0; jj < D; ++jj) X[jj] = fma(-cc, w[jj], X[jj]);
             }
@@ -79,9 +327,13 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
         }
         vsave[l] = xj;
         if (live) {
-            const MixView<T> mv = regulate_to_slots<T>(c, c.K, j, prow, sj, slots, false);
             T y, logd;
-            gf_eval_logpdf<T>(mv, c.inv_type, xj, y, logd);
+            if (c.K == kFbFastK) {
+                fb_fwd_elem<T, kFbFastK>(c, prow + (int64_t)(c.raw_m() + j) * sj, (int64_t)D * sj, xj, y, logd);
+            } else {
+                const MixView<T> mv = regulate_to_slots<T>(c, c.K, j, prow, sj, slots, false);
+                gf_eval_logpdf<T>(mv, c.inv_type, xj, y, logd);
+            }
             xj = y;
             ld_acc += logd;
         }
@@ -110,10 +362,18 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
     for (int l = 0; l < L; ++l) {
         const GfLayerC<T>& c = g.layers[l];
         const T v = vsave[l];
+        if (l + 1 < L) fb_prefetch_layer<T>(g.layers[l + 1], D, j, prow, sj);
         if (live) {
-            const T Gs = bwd_regulate<T>(c, c.K, j, prow, sj, slots);
             T vbar;
-            if (!gf_elem_backward<T>(c, c.K, j, v, xb, gr, Gs, slots, grow, sj, vbar)) {
+            bool ok;
+            if (c.K == kFbFastK) {
+                ok = fb_bwd_elem<T, kFbFastK>(c, prow + (int64_t)(c.raw_m() + j) * sj, grow + (int64_t)(c.raw_m() + j) * sj,
+                                              (int64_t)D * sj, v, xb, gr, vbar);
+            } else {
+                const T Gs = bwd_regulate<T>(c, c.K, j, prow, sj, slots);
+                ok = gf_elem_backward<T>(c, c.K, j, v, xb, gr, Gs, slots, grow, sj, vbar);
+            }
+            if (!ok) {
                 ++n_bad;
 #pragma unroll 1
                 for (int k = 0; k < c.K; ++k) {        // no stage gradient for rows in the Pade tails
@@ -128,6 +388,7 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
             // v = H_{n-1} ... H_0 u: undo reflection by reflection (each one is its own inverse)
             ex[(fX + j) * 32] = v;
             ex[(fXB + j) * 32] = xb;
+#pragma unroll 4
             for (int i = 0; i < c.hh_iter; ++i) ex[(fH + i * D + j) * 32] = prow[(int64_t)(c.raw_hh() + i * D + j) * sj];
             fb_bar(bar_id, 32 * D);
             T V[D], XB[D];
@@ -144,7 +405,7 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
                     aa = fma(w[jj], V[jj], aa);        // w . x_out ( = -(w . x_in) )
                     bb = fma(w[jj], XB[jj], bb);
                 }
-                const T is = T(1) / s;
+                const T is = rcp_pos_(s);
                 const T ain = -aa;
                 const T w_own = ex[(fH + i * D + j) * 32];
                 const T ca = T(2) * aa * is, cb = T(2) * bb * is;
