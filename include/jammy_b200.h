@@ -270,6 +270,24 @@ int jf_subpdf_forward_backward(const JfSubPdfDesc* desc, int dtype,
                                int64_t B, int64_t* status, void* stream);
 
 /*
+ * Training, non-Euclidean sub-pdfs (S2 "f" / "v", S1 "o" / "m", interval "r"): per-row JACOBIAN of
+ * log_pdf = log N(base) + logdet with respect to the raw parameters and the coordinates -- what the reference obtains
+ * from autograd through layers/spheres/fvm_2d.py, exponential_map_s2.py, splines_1d.py, moebius_1d.py,
+ * layers/intervals/rational_quadratic_spline.py and layers/spline_fns.py.  Forward-mode sweep of the value-path device
+ * code over dual numbers (csrc/jac_sweep.cuh): one pass per parameter / coordinate, every option of the value path covered
+ * by construction.  The values themselves come from jf_subpdf_apply.
+ *   params       element (j,row) at params[j*p_stride_param + row*p_stride_row]; p_stride_row == 0: shared parameters
+ *   jac_params   out, element (j,row) at jac_params[j*jac_stride_param + row]   (at most 160 parameters per sub-pdf)
+ *   jac_x        out, optional [B, dim] (ld_jx): d log_pdf / d x
+ * "v" layers are differentiated in their closed-form direction only (natural_direction = 0), JF_ERR_UNSUPPORTED otherwise.
+ */
+int jf_subpdf_jacobian(const JfSubPdfDesc* desc, int dtype,
+                       const void* x, int64_t ld_x,
+                       const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                       void* jac_params, int64_t jac_stride_param, void* jac_x, int64_t ld_jx,
+                       int64_t B, int64_t* status, void* stream);
+
+/*
  * params = W_L * tanh(... tanh(W_1 * concat(segments) + b_1) ...) + b_L for B rows.
  *   seg_ptrs[i]/seg_ld[i]  column block i: [B, seg_cols[i]] with leading dimension seg_ld[i].
  *   weights[l]             weight of Linear l in torch layout: [dims[l+1], dims[l]] row-major (= Linear.weight).

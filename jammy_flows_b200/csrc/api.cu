@@ -17,6 +17,7 @@
 #include "mlp_dmma.cuh"
 #include "mlp_i8.cuh"
 #include "gf_fb_launch.cuh"
+#include "jac_sweep.cuh"
 #include "rowwise.cuh"
 #include "gf_fused_launch.cuh"
 #include "mlp_bwd_launch.cuh"
@@ -218,7 +219,7 @@ static int fill_spline(SplineC<T>& c, const JfSplineDesc& d, int rel_off) {
 }
 
 template <typename T>
-static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaStream_t st) {
+static int fill_s2(const JfSubPdfDesc* desc, S2Args<T>& g) {
     if (desc->dim != 2) return JF_ERR_UNSUPPORTED;
     int n_sp = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
@@ -271,6 +272,13 @@ static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaS
             c.K = L.K; c.natural_direction = L.natural_direction; c.max_iter = L.max_iter > 0 ? L.max_iter : 1000;
         }
     }
+    return JF_OK;
+}
+
+template <typename T>
+static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaStream_t st) {
+    const int rc = fill_s2<T>(desc, g);
+    if (rc != JF_OK) return rc;
     const int threads = 128;
     const int64_t blocks = (g.a.B + threads - 1) / threads;
     if (direction == JF_DIR_LOGPDF) s2_chain_kernel<T, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, 0, st>>>(g);
@@ -280,7 +288,7 @@ static int apply_s2(const JfSubPdfDesc* desc, int direction, S2Args<T>& g, cudaS
 
 // one-dimensional sub-pdfs: interval ("r") and circle ("o", "m")
 template <typename T>
-static int apply_chain1(const JfSubPdfDesc* desc, int direction, Chain1Args<T>& g, cudaStream_t st) {
+static int fill_chain1(const JfSubPdfDesc* desc, Chain1Args<T>& g) {
     if (desc->dim != 1) return JF_ERR_UNSUPPORTED;
     g.manifold = desc->manifold;
     for (int l = 0; l < desc->n_layers; ++l) {
@@ -312,6 +320,13 @@ static int apply_chain1(const JfSubPdfDesc* desc, int direction, Chain1Args<T>& 
             }
         }
     }
+    return JF_OK;
+}
+
+template <typename T>
+static int apply_chain1(const JfSubPdfDesc* desc, int direction, Chain1Args<T>& g, cudaStream_t st) {
+    const int rc = fill_chain1<T>(desc, g);
+    if (rc != JF_OK) return rc;
     const int threads = 128;
     const int64_t blocks = (g.a.B + threads - 1) / threads;
     if (direction == JF_DIR_LOGPDF) chain1_kernel<T, JF_DIR_LOGPDF><<<(unsigned)blocks, threads, 0, st>>>(g);
@@ -438,6 +453,65 @@ extern "C" int jf_subpdf_forward_backward(const JfSubPdfDesc* desc, int dtype, c
     if (dtype == JF_F32)
         return subpdf_fb_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, grad_x, ld_gx,
                                   base_out, ld_out, logdet_out, logbase_out, B, status, st);
+    return JF_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// jf_subpdf_jacobian: per-row Jacobian of the log_pdf of a non-Euclidean sub-pdf (forward-mode sweep, csrc/jac_sweep.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename F>
+static int subpdf_jacobian_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, const void* params, int64_t sp, int64_t sr,
+                             void* jac, int64_t jac_sj, void* jx, int64_t ld_jx, int64_t B, cudaStream_t st) {
+    JacIO<F> io;
+    io.n_params = desc->n_params; io.d = desc->dim; io.B = B;
+    io.in = (const F*)x; io.ld_in = ld_x;
+    io.params = (const F*)params; io.sj = sp; io.sr = sr;
+    io.jac = (F*)jac; io.jac_sj = jac_sj;
+    io.jx = (F*)jx; io.ld_jx = ld_jx;
+    const int threads = 128;
+    const dim3 grid((unsigned)((B + threads - 1) / threads), (unsigned)(desc->n_params + (jx != nullptr ? desc->dim : 0)));
+    if (grid.y == 0) return JF_OK;
+    if (desc->manifold == 's' && desc->dim == 2) {
+        S2Args<Dual> g;
+        memset(&g.a, 0, sizeof(g.a));
+        g.a.n_layers = desc->n_layers; g.a.d = desc->dim; g.a.B = B;
+        const int rc = fill_s2<Dual>(desc, g);
+        if (rc != JF_OK) return rc;
+        for (int l = 0; l < desc->n_layers; ++l)      // the inverse of "v" in its non-natural direction is an iteration
+            if (g.layers[l].kind == JF_LAYER_EXPMAP && g.layers[l].natural_direction != 0) return JF_ERR_UNSUPPORTED;
+        s2_jac_kernel<F><<<grid, threads, 0, st>>>(io, g);
+        return check_launch();
+    }
+    if ((desc->manifold == 's' && desc->dim == 1) || desc->manifold == 'i') {
+        Chain1Args<Dual> g;
+        memset(&g.a, 0, sizeof(g.a));
+        g.a.n_layers = desc->n_layers; g.a.d = desc->dim; g.a.B = B;
+        const int rc = fill_chain1<Dual>(desc, g);
+        if (rc != JF_OK) return rc;
+        chain1_jac_kernel<F><<<grid, threads, 0, st>>>(io, g);
+        return check_launch();
+    }
+    return JF_ERR_UNSUPPORTED;
+}
+
+extern "C" int jf_subpdf_jacobian(const JfSubPdfDesc* desc, int dtype, const void* x, int64_t ld_x, const void* params,
+                                  int64_t p_stride_param, int64_t p_stride_row, void* jac_params, int64_t jac_stride_param,
+                                  void* jac_x, int64_t ld_jx, int64_t B, int64_t* status, void* stream) {
+    (void)status;
+    if (desc == nullptr || x == nullptr) return JF_ERR_BAD_ARG;
+    if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
+    if (desc->manifold == 'e') return JF_ERR_UNSUPPORTED;      // Euclidean chains: jf_subpdf_forward_backward
+    if (desc->n_params < 0 || desc->n_params > kJacMaxParams) return JF_ERR_UNSUPPORTED;
+    if (desc->n_params > 0 && (params == nullptr || jac_params == nullptr)) return JF_ERR_BAD_ARG;
+    if (B < 0) return JF_ERR_BAD_ARG;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return subpdf_jacobian_t<double>(desc, x, ld_x, params, p_stride_param, p_stride_row, jac_params, jac_stride_param,
+                                         jac_x, ld_jx, B, st);
+    if (dtype == JF_F32)
+        return subpdf_jacobian_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, jac_params, jac_stride_param,
+                                        jac_x, ld_jx, B, st);
     return JF_ERR_BAD_ARG;
 }
 

@@ -56,7 +56,7 @@ template <typename T>
 JF_DEVINL T s1_to_line(T x, T& logdet) {
     const bool neg = x > T(kPi);
     T y = neg ? T(2 * kPi) - x : x;
-    const T eps = sizeof(T) == 8 ? T(1e-8) : T(1e-5);
+    const T eps = Prec<T>::f64 ? T(1e-8) : T(1e-5);
     if (y <= T(0)) y = eps;
     if (y >= T(2 * kPi)) y = T(2 * kPi) - eps;
     const T z = T(1.4142135623730951) * erfcinv(y / T(kPi));

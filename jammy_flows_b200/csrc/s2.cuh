@@ -217,7 +217,7 @@ JF_DEVINL void fvm_logpdf(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
     const T em2k = exp(T(-2) * kappa);
     T ret = s * ((T(1) + em2k - T(2) * exp(kappa * (s * ct - T(1)))) / (T(-1) + em2k));
     if (kappa < Num<T>::kappa_identity) ret = ct;
-    ret = safe_costheta(ret, Num<T>::safe_costheta);
+    ret = safe_costheta(ret, T(Num<T>::safe_costheta));
     const T* psub = pl + (int64_t)(n_hh + 1) * sj;     // spline parameters follow kappa (fvm_2d.py:311-316)
     if (c.extra_rot) fvm_extra_rotation(ret, phi, logdet, true);
     // sub-flows act only inside the identity region's complement (all rows when the region is 0)
@@ -226,7 +226,7 @@ JF_DEVINL void fvm_logpdf(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
         if (c.n_circular > 0) phi = fvm_circular<T>(c, sp, true, phi, fvm_window(ret), logdet, psub, sj, oor);
         if (c.n_vertical > 0) ret = fvm_vertical<T>(c, sp, true, ret, logdet, psub, sj, oor);
     }
-    ret = safe_costheta(ret, Num<T>::safe_costheta);
+    ret = safe_costheta(ret, T(Num<T>::safe_costheta));
     theta = acos(ret);
     logdet -= log(sin(safe_angle(theta)));
     if (c.first) {
@@ -277,7 +277,7 @@ JF_DEVINL void fvm_sample(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
     logdet -= log(kappa * s * ct + kappa / tanh(kappa));
     T ret = s * (T(1) + (T(1) / kappa) * log(T(0.5) * (T(1) + s * ct) + (T(0.5) - T(0.5) * s * ct) * exp(T(-2) * kappa)));
     if (kappa < Num<T>::kappa_identity) ret = ct;
-    ret = safe_costheta(ret, Num<T>::safe_costheta);
+    ret = safe_costheta(ret, T(Num<T>::safe_costheta));
     theta = acos(ret);
     logdet -= log(sin(safe_angle(theta)));
     if (c.add_rotation) {
@@ -416,7 +416,7 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
     evals = 1;
     converged = false;
     T merit = T(1) - (y[0] * tg[0] + y[1] * tg[1] + y[2] * tg[2]);
-    const T tol = sizeof(T) == 8 ? T(1e-13) : T(1e-6);
+    const T tol = Prec<T>::f64 ? T(1e-13) : T(1e-6);
     const int cap = max_iter < 200 ? max_iter : 200;
     T prev_nrm = Num<T>::big;
 #pragma unroll 1
@@ -451,7 +451,7 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
         // rounding noise of the residual (quadratic convergence shrinks it by orders of magnitude per step otherwise).
         // In fp32 the noise floor (~3e-6 for a Jacobian of condition ~10) sits ABOVE the fixed tolerance: without the
         // second test most rows ran into the iteration cap (measured: 780 evaluations per row on cfg4).
-        if (nrm <= tol || (nrm < (sizeof(T) == 8 ? T(1e-9) : T(1e-3)) && nrm >= T(0.5) * prev_nrm)) {
+        if (nrm <= tol || (nrm < (Prec<T>::f64 ? T(1e-9) : T(1e-3)) && nrm >= T(0.5) * prev_nrm)) {
             converged = true;
             if (nrm == T(0)) break;
         }
@@ -481,7 +481,7 @@ __device__ __noinline__ void v_solve(const VRow<T>& r, const T* tg, int max_iter
         merit = mn;
         if (converged) break;
     }
-    if (!(merit <= (sizeof(T) == 8 ? T(1e-10) : T(1e-5)))) converged = false;
+    if (!(merit <= (Prec<T>::f64 ? T(1e-10) : T(1e-5)))) converged = false;
 }
 
 // reference exponential_map_s2.py:446-528 wrapped by sphere_base.py:601-695

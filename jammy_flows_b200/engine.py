@@ -5,6 +5,7 @@ only.  Every number comes out of libjammy_b200.so; nothing here computes layer m
 eager PyTorch or the CPU.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -819,21 +820,47 @@ def s2_embedding(x):
 # generator stays a torch module so that its backward is torch's own (plain library GEMMs, cuBLAS).  Its last Linear is
 # evaluated transposed ([P, B] = W2 h^T + b2), which IS the param-major layout the layer kernels read coalesced.
 # ---------------------------------------------------------------------------------------------------------------------
+_JAC_CODES = ("f", "v", "r", "o", "m")       # non-Euclidean layers: Jacobian by the forward-mode sweep (csrc/jac_sweep.cuh)
+_JAC_MAX_PARAMS = 160
+
+
 def supports_backward(pdf):
-    """True when every sub-pdf is Euclidean and made of "g" layers (default options) with a stage the backward kernel
-    covers.  Parameters may come from an MLP (per-row) or be permanent: a permanent vector is expanded to per-row form
-    and autograd sums the per-row gradients back into it."""
+    """True when every sub-pdf has a backward path: Euclidean sub-pdfs made of "g" layers with default options and a stage
+    the closed-form reverse pass covers (`jf_subpdf_forward_backward`), non-Euclidean sub-pdfs ("f", "v", "r", "o", "m",
+    any option; "v" / "m" in their closed-form direction) through the dual-number sweep `jf_subpdf_jacobian`.  Parameters
+    may come from an MLP (per-row) or be permanent: a permanent vector is expanded to per-row form and autograd sums the
+    per-row gradients back into it."""
     if uses_custom_mlp(pdf):
         return False
     for k, layers in enumerate(pdf.layer_list):
         if pdf.pdf_defs_list[k][0] != "e":
-            return False
+            for l in layers:
+                if getattr(l, "code", "") not in _JAC_CODES:
+                    return False
+                if l.code in ("v", "m") and int(getattr(l, "natural_direction", 0)) != 0:
+                    return False
+            if sum(int(l.get_total_param_num()) for l in layers) > _JAC_MAX_PARAMS:
+                return False
+            continue
         for l in layers:
             if getattr(l, "code", "") != "g" or l.inverse_function_type not in ("isigmoid", "inormal_partly_precise"):
                 return False
             if not l.is_default_kernel_config:
                 return False
     return True
+
+
+def _embedding_torch(pdf, k, x_k):
+    """embedding coordinates of the targets of sub-pdf k with torch ops (differentiable: the conditioning input of the
+    later generators, reference sphere_base.py:779-794 / main/default.py:1050-1053)"""
+    name = pdf.pdf_defs_list[k]
+    if name[0] == "s" and x_k.shape[1] == 2:
+        th = x_k[:, 0:1].clamp(1e-7, math.pi - 1e-7)
+        ph = x_k[:, 1:2]
+        return torch.cat([torch.sin(th) * torch.cos(ph), torch.sin(th) * torch.sin(ph), torch.cos(th)], dim=1)
+    if name[0] == "s":
+        return torch.cat([torch.cos(x_k), torch.sin(x_k)], dim=1)
+    return x_k
 
 
 def subpdf_logpdf_forward(pdf, k, params_t, x_k):
@@ -869,6 +896,22 @@ def subpdf_logpdf_fb(pdf, k, params_t, x_k, g_logp=None):
     logbase = torch.empty(B, dtype=dt, device=dev)
     jac = torch.empty_like(params_t)
     jx = torch.empty(B, d, dtype=dt, device=dev)
+    if pdf.pdf_defs_list[k][0] != "e":
+        # non-Euclidean sub-pdf: values from the layer kernel, Jacobians from the dual-number sweep over the same device code
+        assert g_logp is None
+        with torch.cuda.device(dev):
+            rc = lib.jf_subpdf_apply(C.byref(sub_desc), _DT[dt], _cabi.JF_DIR_LOGPDF, _ptr(x_k), x_k.stride(0),
+                                     _ptr(params_t), params_t.stride(0), 1, None, _ptr(logdet), None, _ptr(logbase),
+                                     _ptr(base), d, None, 0, B, _ptr(status), _stream_ptr(dev))
+            _cabi.check(rc, "jf_subpdf_apply")
+            rc = lib.jf_subpdf_jacobian(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
+                                        params_t.stride(0), 1, _ptr(jac), jac.stride(0), _ptr(jx), d, B, _ptr(status),
+                                        _stream_ptr(dev))
+        if rc == -2:                      # JF_ERR_UNSUPPORTED
+            raise NotImplementedError("jf_subpdf_jacobian: no backward for this sub-pdf (more than %d parameters, or an "
+                                      "iterative direction)" % _JAC_MAX_PARAMS)
+        _cabi.check(rc, "jf_subpdf_jacobian")
+        return logdet + logbase, logbase, base, jac, jx
     g = None if g_logp is None else g_logp.contiguous()
     with torch.cuda.device(dev):
         rc = lib.jf_subpdf_forward_backward(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
@@ -1021,7 +1064,8 @@ def pdf_logpdf_trainable(pdf, x, cond):
         if mlp is None:
             # permanent parameters (the reference's nn.Parameters broadcast over the batch): one vector in extra_inputs
             # order, expanded to the per-row layout of the backward kernel; autograd reduces the row gradients
-            vec = torch.cat([l.packed_permanent_params() for l in layers]).to(device=dev, dtype=dt)
+            vecs = [v for v in (l.packed_permanent_params() for l in layers) if v is not None]
+            vec = torch.cat(vecs).to(device=dev, dtype=dt) if len(vecs) > 0 else torch.zeros(0, dtype=dt, device=dev)
             params_t = vec.unsqueeze(1).expand(vec.shape[0], x.shape[0]).contiguous()
         else:
             pieces = ([cond] if cond is not None else []) + prev
@@ -1035,7 +1079,7 @@ def pdf_logpdf_trainable(pdf, x, cond):
                 logp = lp_k if logp is None else logp + lp_k
                 logp_base = lb_k if logp_base is None else logp_base + lb_k
                 bases.append(base_k)
-                prev.append(x_k)
+                prev.append(_embedding_torch(pdf, k, x_k))
                 continue
             else:
                 h = inp
@@ -1047,5 +1091,5 @@ def pdf_logpdf_trainable(pdf, x, cond):
         logp = lp_k if logp is None else logp + lp_k
         logp_base = lb_k if logp_base is None else logp_base + lb_k
         bases.append(base_k)
-        prev.append(x_k)
+        prev.append(_embedding_torch(pdf, k, x_k))
     return logp, logp_base, torch.cat(bases, dim=1)

@@ -230,6 +230,13 @@ CASES = {
     "train_e2_gg_uncond": dict(pdf_defs="e2", flow_defs="gg", n=300, perturb=0.3, grads=True),
     "train_e3e2_uncond": dict(pdf_defs="e3+e2", flow_defs="gg+gg", n=200, perturb=0.2, grads=True),
     "train_e2e2_cond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=200, cond_dim=2, perturb=0.2, grads=True),
+    # non-Euclidean sub-pdfs in the training path (README-style mixed flow, every manifold layer kind)
+    "train_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=120, perturb=0.1, grads=True),
+    "train_s2_f_splines_cond": dict(pdf_defs="s2", flow_defs="f", n=120, cond_dim=2, perturb=0.1, grads=True,
+                                    opts={"f": CFG3_F}),
+    "train_s2_v_cond": dict(pdf_defs="s2", flow_defs="v", n=120, cond_dim=2, perturb=0.1, grads=True),
+    "train_s1i1_or_cond": dict(pdf_defs="s1+i1_-0.5_0.8", flow_defs="o+r", n=120, cond_dim=2, perturb=0.1, grads=True),
+    "train_s1_m_uncond": dict(pdf_defs="s1", flow_defs="m", n=120, perturb=0.1, grads=True),
 }
 
 

@@ -150,7 +150,7 @@ def test_adam_steps_decrease_the_loss(lib_built):
 
 
 def test_backward_of_unsupported_pdfs_fails_loudly(lib_built):
-    p = jfb.pdf("s2", "f").double().cuda()                   # manifold layers: no backward kernel
+    p = jfb.pdf("e2", "gt").double().cuda()                  # "t" layers / non-default "g" options: no backward kernel
     x = torch.tensor([[1.0, 2.0], [0.5, 4.0]], dtype=torch.float64, device="cuda")
     lp, _, _ = p(x)
     with pytest.raises(NotImplementedError):
