@@ -270,6 +270,24 @@ int jf_subpdf_forward_backward(const JfSubPdfDesc* desc, int dtype,
                                int64_t B, int64_t* status, void* stream);
 
 /*
+ * Training through SAMPLES (reference: pdf.sample(allow_gradients=True), main/default.py:1342, which differentiates through
+ * the bisection / Newton iterations of layers/bisection_n_newton.py): backward of the sampling direction of a Euclidean
+ * "g" sub-pdf at the sample x = T(z; params) that jf_subpdf_apply(JF_DIR_SAMPLE) returned.  The layer inputs are
+ * recovered by running the closed-form log_pdf direction from x (no root finder), then every element is differentiated
+ * in implicit-function form (csrc/gf_fb.cuh, MODE 1).
+ *   x            [B, d] the samples (ld_x)              params  as in jf_subpdf_backward
+ *   grad_x       [B, d] (ld_gx) cotangent of x, or NULL (= 0);   grad_logp  [B] cotangent of log_pdf(x), or NULL (= 0)
+ *   grad_params  out, indexed like params
+ *   grad_z       optional out [B, d] (ld_gz): cotangent of the base point z
+ */
+int jf_subpdf_sample_backward(const JfSubPdfDesc* desc, int dtype,
+                              const void* x, int64_t ld_x,
+                              const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                              const void* grad_x, int64_t ld_gx, const void* grad_logp,
+                              void* grad_params, void* grad_z, int64_t ld_gz,
+                              int64_t B, int64_t* status, void* stream);
+
+/*
  * Training, non-Euclidean sub-pdfs (S2 "f" / "v", S1 "o" / "m", interval "r"): per-row JACOBIAN of
  * log_pdf = log N(base) + logdet with respect to the raw parameters and the coordinates -- what the reference obtains
  * from autograd through layers/spheres/fvm_2d.py, exponential_map_s2.py, splines_1d.py, moebius_1d.py,

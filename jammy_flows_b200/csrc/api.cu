@@ -387,7 +387,8 @@ extern "C" int jf_subpdf_apply(const JfSubPdfDesc* desc, int dtype, int directio
 template <typename T>
 static int subpdf_fb_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, const void* params, int64_t sp,
                        int64_t sr, const void* grad_logp, void* grad_params, void* grad_x, int64_t ld_gx, void* base_out,
-                       int64_t ld_out, void* logdet_out, void* logbase_out, int64_t B, int64_t* status, cudaStream_t st) {
+                       int64_t ld_out, void* logdet_out, void* logbase_out, int64_t B, int64_t* status, cudaStream_t st,
+                       const void* grad_out_x = nullptr, int64_t ld_go = 0, int mode = 0) {
     GfFbArgs<T> g;
     fill_common<T>(g.a, desc, x, ld_x, params, sp, sr, nullptr, logdet_out, nullptr, logbase_out, base_out, ld_out, nullptr, 0,
                    B, status);
@@ -395,6 +396,8 @@ static int subpdf_fb_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, co
     g.grad_params = (T*)grad_params;
     g.grad_x = (T*)grad_x;
     g.ld_gx = ld_gx;
+    g.grad_out_x = (const T*)grad_out_x;
+    g.ld_go = ld_go;
     const int d = desc->dim;
     if (d < 1 || d > JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
     int kmax = 1, hh_max = 0;
@@ -416,7 +419,7 @@ static int subpdf_fb_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, co
     }
     g.kmax = kmax;
     g.hh_max = hh_max;
-    const int rc = launch_gf_fb<T>(g, st);
+    const int rc = mode == 0 ? launch_gf_fb<T>(g, st) : launch_gf_sbwd<T>(g, st);
     if (rc != JF_OK) return rc;
     return check_launch();
 }
@@ -453,6 +456,23 @@ extern "C" int jf_subpdf_forward_backward(const JfSubPdfDesc* desc, int dtype, c
     if (dtype == JF_F32)
         return subpdf_fb_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, grad_x, ld_gx,
                                   base_out, ld_out, logdet_out, logbase_out, B, status, st);
+    return JF_ERR_BAD_ARG;
+}
+
+extern "C" int jf_subpdf_sample_backward(const JfSubPdfDesc* desc, int dtype, const void* x, int64_t ld_x,
+                                         const void* params, int64_t p_stride_param, int64_t p_stride_row,
+                                         const void* grad_x, int64_t ld_gx, const void* grad_logp, void* grad_params,
+                                         void* grad_z, int64_t ld_gz, int64_t B, int64_t* status, void* stream) {
+    const int rc = subpdf_fb_checks(desc, x, params, grad_params, p_stride_row, B);
+    if (rc != JF_OK) return rc;
+    if (B == 0) return JF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == JF_F64)
+        return subpdf_fb_t<double>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, grad_z, ld_gz,
+                                   nullptr, 0, nullptr, nullptr, B, status, st, grad_x, ld_gx, 1);
+    if (dtype == JF_F32)
+        return subpdf_fb_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, grad_logp, grad_params, grad_z, ld_gz,
+                                  nullptr, 0, nullptr, nullptr, B, status, st, grad_x, ld_gx, 1);
     return JF_ERR_BAD_ARG;
 }
 

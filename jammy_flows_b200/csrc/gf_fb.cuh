@@ -162,10 +162,67 @@ __device__ __noinline__ void fb_fwd_elem(const GfLayerC<T>& c, const T* pm, int6
     inv_stage(c.inv_type, v, y, logd);
 }
 
+// coefficients of the inverse-CDF stage's reverse pass (linear in the upstream gradients gy of y and gl of l = log y'):
+// see csrc/gf_bwd.cuh gf_elem_backward for the derivation
+template <typename T>
+struct FbCoef {
+    T y_coefC, y_coefS;     // coefficients of (dC/dtheta)/E and (dS/dtheta)/E
+    T nC, nS;               // coefficients of sigma_k and (1 - sigma_k) in their side-dependent rescaled form
+    T nC_true;              // coefficient of the TRUE sigma_k
+    bool ok;
+};
+template <typename T>
+JF_DEVINL FbCoef<T> fb_coef(const GfLayerC<T>& c, T Sc, T Ss, T E, T delta, bool all_neg, bool all_pos, T gy, T gl) {
+    FbCoef<T> r;
+    r.ok = true;
+    r.nC_true = 0;
+    const T fC = all_neg ? T(1) : E, fS = all_pos ? T(1) : E;
+    if (c.inv_type == JF_INV_ISIGMOID) {
+        r.y_coefC = (gy - gl) * fC / Sc;
+        r.y_coefS = -(gy + gl) * fS / Ss;
+        r.nC = (gy - gl) / Sc;
+        r.nS = -(gy + gl) / Ss;
+        return r;
+    }
+    const T Ct = Sc * (all_neg ? E : T(1)), St = Ss * (all_pos ? E : T(1));
+    const T eps = T(0.5e-7);
+    if (c.inv_type != JF_INV_PARTLY_PRECISE) { r.ok = false; r.y_coefC = r.y_coefS = r.nC = r.nS = 0; return r; }
+    const bool upper = !(St > eps), lower = !(Ct > eps);
+    if (!upper && !lower) {
+        const T er = (Ct <= T(0.5)) ? -erfcinv(T(2) * Ct) : erfcinv(T(2) * St);
+        const T y = T(1.4142135623730951) * er;
+        const T Dn = T(2.5066282746310002) * exp(er * er);      // 1/phi(y)
+        r.nC_true = (gy + gl * y) * Dn;
+        r.y_coefC = r.nC_true * E;
+        r.y_coefS = T(0);
+        r.nC = T(0);
+        r.nS = T(0);
+    } else {
+        const T pa = T(0.147), pc = T(2.0 / (kPi * 0.147));
+        const T Lf = (log(Sc) - (all_neg ? delta : T(0))) + (log(Ss) - (all_pos ? delta : T(0))) + T(1.3862943611198906);
+        const T F = pc + Lf * T(0.5);
+        const T F2 = sqrt(F * F - Lf / pa);
+        const T dF2 = (F - T(1) / pa) / (T(2) * F2);
+        const T diff = F2 - F;
+        const T yv = (upper ? T(1) : T(-1)) * sqrt(tmax(T(0), T(2) * diff));
+        const T dy = (dF2 - T(0.5)) / yv;
+        const T dl = (dF2 - T(0.5)) / (diff + T(1) / pa) - T(0.5) * (dF2 - T(0.5)) / diff - dF2 / F2;
+        const T gL = gy * dy + gl * dl;
+        r.nC_true = -T(2) * gl / (T(1) - T(2) * Ct);
+        r.y_coefC = (gL - gl) * fC / Sc + r.nC_true * E;
+        r.y_coefS = (gL - gl) * fS / Ss;
+        r.nC = (gL - gl) / Sc;
+        r.nS = (gL - gl) / Ss;
+    }
+    return r;
+}
+
 // backward of one element (v -> (y, l); gy, gl upstream): writes the raw-parameter gradients of this (layer, dimension)
 // through gm (address of (raw_m + j) in the gradient block), returns d/dv in vbar; false for rows outside the supported
 // stages.  Formulas: csrc/gf_bwd.cuh gf_elem_backward.
-template <typename T, int K>
+// SDIR: the element is traversed in the SAMPLING direction (y -> v): gy is then the cotangent of v, gl that of log_pdf, and
+// vbar returns the cotangent of y.
+template <typename T, int K, bool SDIR = false>
 __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* gm, int64_t step, T v, T gy, T gl, T& vbar) {
     FbMix<T, K> M;
     fb_load<T, K>(c, pm, step, M);
@@ -189,48 +246,27 @@ __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* g
         const T dd = pt * iw * (T(1) - e) * rx;
         Sd += pos ? -dd : dd;
     }
-    const T fC = all_neg ? T(1) : E, fS = all_pos ? T(1) : E;
-    T y_coefC, y_coefS, nC, nS, nC_true = 0;
-    if (c.inv_type == JF_INV_ISIGMOID) {
-        y_coefC = (gy - gl) * fC / Sc;
-        y_coefS = -(gy + gl) * fS / Ss;
-        nC = (gy - gl) / Sc;
-        nS = -(gy + gl) / Ss;
+    FbCoef<T> cf;
+    if (SDIR) {
+        // sampling direction: y -> v = f^-1(y), log_pdf gains l(v).  With A = f'(v) and l_v (the coefficients are linear in
+        // (gy, gl)): cotangent of y is w = (vbar_in + gl l_v) / A, the parameter gradients are those of the log_pdf
+        // direction for (gy, gl) = (-w, gl)
+        const FbCoef<T> ca = fb_coef<T>(c, Sc, Ss, E, delta, all_neg, all_pos, T(1), T(0));
+        const FbCoef<T> cb = fb_coef<T>(c, Sc, Ss, E, delta, all_neg, all_pos, T(0), T(1));
+        if (!ca.ok) { vbar = T(0); return false; }
+        const T A = (ca.y_coefC - ca.y_coefS) * Sp;
+        const T Bv = (cb.y_coefC - cb.y_coefS) * Sp + Sd / Sp;
+        const T w = (gy + gl * Bv) / A;
+        cf = fb_coef<T>(c, Sc, Ss, E, delta, all_neg, all_pos, -w, gl);
+        vbar = w;
     } else {
-        const T Ct = Sc * (all_neg ? E : T(1)), St = Ss * (all_pos ? E : T(1));
-        const T eps = T(0.5e-7);
-        if (c.inv_type != JF_INV_PARTLY_PRECISE) { vbar = T(0); return false; }
-        const bool upper = !(St > eps), lower = !(Ct > eps);
-        if (!upper && !lower) {
-            const T er = (Ct <= T(0.5)) ? -erfcinv(T(2) * Ct) : erfcinv(T(2) * St);
-            const T y = T(1.4142135623730951) * er;
-            const T Dn = T(2.5066282746310002) * exp(er * er);      // 1/phi(y)
-            nC_true = (gy + gl * y) * Dn;
-            y_coefC = nC_true * E;
-            y_coefS = T(0);
-            nC = T(0);
-            nS = T(0);
-        } else {
-            const T pa = T(0.147), pc = T(2.0 / (kPi * 0.147));
-            const T Lf = (log(Sc) - (all_neg ? delta : T(0))) + (log(Ss) - (all_pos ? delta : T(0))) + T(1.3862943611198906);
-            const T F = pc + Lf * T(0.5);
-            const T F2 = sqrt(F * F - Lf / pa);
-            const T dF2 = (F - T(1) / pa) / (T(2) * F2);
-            const T diff = F2 - F;
-            const T yv = (upper ? T(1) : T(-1)) * sqrt(tmax(T(0), T(2) * diff));
-            const T dy = (dF2 - T(0.5)) / yv;
-            const T dl = (dF2 - T(0.5)) / (diff + T(1) / pa) - T(0.5) * (dF2 - T(0.5)) / diff - dF2 / F2;
-            const T gL = gy * dy + gl * dl;
-            nC_true = -T(2) * gl / (T(1) - T(2) * Ct);
-            y_coefC = (gL - gl) * fC / Sc + nC_true * E;
-            y_coefS = (gL - gl) * fS / Ss;
-            nC = (gL - gl) / Sc;
-            nS = (gL - gl) / Ss;
-        }
+        cf = fb_coef<T>(c, Sc, Ss, E, delta, all_neg, all_pos, gy, gl);
+        if (!cf.ok) { vbar = T(0); return false; }
     }
-    const T cCS = y_coefC - y_coefS;
+    const T nC = cf.nC, nS = cf.nS, nC_true = cf.nC_true;
+    const T cCS = cf.y_coefC - cf.y_coefS;
     const T glp = gl / Sp;
-    vbar = cCS * Sp + glp * Sd;
+    if (!SDIR) vbar = cCS * Sp + glp * Sd;
     T nb[K];
     T nbar_dot = 0;
 #pragma unroll
@@ -271,7 +307,11 @@ __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* g
 
 JF_DEVINL void fb_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <typename T, int D>
+// MODE 0: log_pdf forward + backward.  MODE 1: backward of the SAMPLING direction at the sample x = T(z; theta) (a.in): the
+// layers' inputs are recovered by running the closed-form log_pdf direction from x (no root finder), then the chain is
+// walked from the x side to the z side with the implicit-function form of every element (fb_bwd_elem<SDIR>): cotangents
+// grad_out_x of x and grad_logp of log_pdf(x) in, parameter gradients and (optionally, grad_x) the cotangent of z out.
+template <typename T, int D, int MODE>
 __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf_chain_fb_kernel(const __grid_constant__ GfFbArgs<T> g) {
     constexpr int NG = fb_groups(D);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -338,6 +378,7 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
             ld_acc += logd;
         }
     }
+    if (MODE == 0) {
     // ---- forward outputs: base point, logdet, log N(z) ----
     if (live && a.out != nullptr) a.out[row * a.ld_out + j] = xj;
     if (a.logdet_out != nullptr || a.logbase_out != nullptr) {
@@ -353,6 +394,103 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
             if (a.logbase_out != nullptr) a.logbase_out[row] = -T(0.5) * zsq - T(D) * T(kLogSqrt2Pi);
         }
         fb_bar(bar_id, 32 * D);
+    }
+    }
+    if (MODE == 1) {
+        // ---- backward of the sampling direction: x side first ----
+        T xb = g.grad_out_x ? g.grad_out_x[row * g.ld_go + j] : T(0);
+        const T gl = g.grad_logp ? g.grad_logp[row] : T(0);
+        int n_bad = 0;
+#pragma unroll 1
+        for (int l = L - 1; l >= 0; --l) {
+            const GfLayerC<T>& c = g.layers[l];
+            const T v = vsave[l];
+            if (l > 0) fb_prefetch_layer<T>(g.layers[l - 1], D, j, prow, sj);
+            if (c.has_offset && live) grow[(int64_t)(c.raw_off + j) * sj] = xb;      // x = Q v + offset
+            if (c.hh_iter > 0) {
+                ex[(fX + j) * 32] = v;
+                ex[(fXB + j) * 32] = xb;
+#pragma unroll 4
+                for (int i = 0; i < c.hh_iter; ++i) ex[(fH + i * D + j) * 32] = prow[(int64_t)(c.raw_hh() + i * D + j) * sj];
+                fb_bar(bar_id, 32 * D);
+                T V[D], XB[D];
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) { V[jj] = ex[(fX + jj) * 32]; XB[jj] = ex[(fXB + jj) * 32]; }
+                // t_0 = H_0 ... H_{n-1} v  (the rotated vector, = x - offset)
+#pragma unroll 1
+                for (int i = c.hh_iter - 1; i >= 0; --i) {
+                    T w[D], dot = 0, nrm = 0;
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) {
+                        w[jj] = ex[(fH + i * D + jj) * 32];
+                        dot = fma(w[jj], V[jj], dot);
+                        nrm = fma(w[jj], w[jj], nrm);
+                    }
+                    const T cc = T(2) * dot * rcp_pos_(nrm);
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) V[jj] = fma(-cc, w[jj], V[jj]);
+                }
+                T t_own = v, xb_own = xb;
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) t_own = (jj == j) ? V[jj] : t_own;
+                // undo the reflections from the output side: t_i = H_i t_{i+1}, cotangent of t_i known
+#pragma unroll 1
+                for (int i = 0; i < c.hh_iter; ++i) {
+                    T w[D], s_ = 0, aa = 0, bb = 0;
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) {
+                        w[jj] = ex[(fH + i * D + jj) * 32];
+                        s_ = fma(w[jj], w[jj], s_);
+                        aa = fma(w[jj], V[jj], aa);         // w . t_i ( = -(w . t_{i+1}) )
+                        bb = fma(w[jj], XB[jj], bb);
+                    }
+                    const T is = rcp_pos_(s_);
+                    const T ain = -aa;
+                    const T w_own = ex[(fH + i * D + j) * 32];
+                    const T ca = T(2) * aa * is, cb = T(2) * bb * is;
+                    const T tin = fma(-ca, w_own, t_own);
+                    if (live)
+                        grow[(int64_t)(c.raw_hh() + i * D + j) * sj] = -T(2) * is * (bb * tin + ain * xb_own) + T(4) * ain * bb * is * is * w_own;
+                    xb_own = fma(-cb, w_own, xb_own);
+                    t_own = tin;
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) { V[jj] = fma(-ca, w[jj], V[jj]); XB[jj] = fma(-cb, w[jj], XB[jj]); }
+                }
+                xb = xb_own;                                  // cotangent of v
+                fb_bar(bar_id, 32 * D);
+            }
+            if (live) {
+                T ybar;
+                bool ok;
+                if (c.K == kFbFastK) {
+                    ok = fb_bwd_elem<T, kFbFastK, true>(c, prow + (int64_t)(c.raw_m() + j) * sj, grow + (int64_t)(c.raw_m() + j) * sj,
+                                                        (int64_t)D * sj, v, xb, gl, ybar);
+                } else {
+                    const T Gs = bwd_regulate<T>(c, c.K, j, prow, sj, slots);
+                    T A_, Bv_, dummy;
+                    ok = gf_elem_backward<T>(c, c.K, j, v, T(1), T(0), Gs, slots, grow, sj, A_);
+                    if (ok) {
+                        gf_elem_backward<T>(c, c.K, j, v, T(0), T(1), Gs, slots, grow, sj, Bv_);
+                        ybar = (xb + gl * Bv_) / A_;
+                        gf_elem_backward<T>(c, c.K, j, v, -ybar, gl, Gs, slots, grow, sj, dummy);
+                    }
+                }
+                if (!ok) {
+                    ++n_bad;
+                    ybar = T(0);
+#pragma unroll 1
+                    for (int k = 0; k < c.K; ++k) {
+                        grow[(int64_t)(c.raw_m() + k * D + j) * sj] = T(0);
+                        grow[(int64_t)(c.raw_w() + k * D + j) * sj] = T(0);
+                        if (c.norm_mode != JF_NORM_NONE) grow[(int64_t)(c.raw_n() + k * D + j) * sj] = T(0);
+                    }
+                }
+                xb = ybar;
+            }
+        }
+        if (g.grad_x != nullptr && live) g.grad_x[row * g.ld_gx + j] = xb;
+        if (n_bad) status_add(a.status, JF_STATUS_OUT_OF_RANGE, n_bad);
+        return;
     }
     // ---- backward ----
     const T gr = g.grad_logp ? g.grad_logp[row] : T(1);

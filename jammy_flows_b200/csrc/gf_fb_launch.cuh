@@ -10,7 +10,8 @@ struct GfFbArgs {
     SubPdfArgs<T> a;           // in = x, params = raw per-row parameters, out = base z (may be NULL), logdet_out / logbase_out (may be NULL)
     const T* grad_logp;        // [B] upstream gradient of log_pdf (NULL = 1)
     T* grad_params;            // indexed like params
-    T* grad_x; int64_t ld_gx;  // optional [B, d]: d log_pdf / d x (times grad_logp)
+    T* grad_x; int64_t ld_gx;  // optional [B, d]: d log_pdf / d x (times grad_logp); sampling backward: cotangent of the base z
+    const T* grad_out_x; int64_t ld_go;   // sampling backward only: cotangent of the sample x [B, d] (NULL = 0)
     int kmax, hh_max;          // slot / exchange geometry
     GfLayerC<T> layers[JF_MAX_LAYERS];
 };
@@ -25,7 +26,9 @@ __host__ __device__ constexpr size_t fb_smem_bytes(int D, int kmax, int hh_max) 
     return ((size_t)3 * kmax * fb_threads(D) + (size_t)fb_groups(D) * (hh_max * D + 2 * D) * 32) * sizeof(T);
 }
 
-// launches gf_chain_fb_kernel<T, d>; returns a JF_ERR_* / cudaError code
+// launches gf_chain_fb_kernel<T, d, 0> (log_pdf forward + backward) / <T, d, 1> (backward of the sampling direction);
+// return a JF_ERR_* / cudaError code
 template <typename T> int launch_gf_fb(const GfFbArgs<T>& g, cudaStream_t st);
+template <typename T> int launch_gf_sbwd(const GfFbArgs<T>& g, cudaStream_t st);
 
 }  // namespace jf

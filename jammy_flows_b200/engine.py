@@ -937,6 +937,43 @@ def subpdf_logpdf_backward(pdf, k, params_t, x_k, g_logp):
     return grad
 
 
+def subpdf_sample_forward(pdf, k, params_t, z_k):
+    """x_k = T_k(z_k; params) of Euclidean sub-pdf k with per-row (param-major) parameters (`jf_subpdf_apply`, sampling
+    direction) -> (x_k [B, d], log_pdf_k [B], log_base_k [B]).  Body of the op `jammy_b200::subpdf_sample`."""
+    lib = _cabi.load()
+    B, d = z_k.shape
+    dt, dev = z_k.dtype, z_k.device
+    sub_desc, status = pdf._desc(dt).sub[k], pdf._status(dev)
+    x = torch.empty(B, d, dtype=dt, device=dev)
+    logdet = torch.empty(B, dtype=dt, device=dev)
+    logbase = torch.empty(B, dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_apply(C.byref(sub_desc), _DT[dt], _cabi.JF_DIR_SAMPLE, _ptr(z_k), z_k.stride(0),
+                                 _ptr(params_t), params_t.stride(0), 1, None, _ptr(logdet), None, _ptr(logbase),
+                                 _ptr(x), d, None, 0, B, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_apply")
+    return x, logbase - logdet, logbase
+
+
+def subpdf_sample_backward(pdf, k, params_t, x_k, g_x, g_logp):
+    """(gradient with respect to the per-row parameters [P, B], cotangent of z_k [B, d]) of a sample x_k given the
+    cotangents of x_k and of log_pdf_k (`jf_subpdf_sample_backward`: implicit differentiation, no root finder)."""
+    lib = _cabi.load()
+    B, d = x_k.shape
+    dt, dev = x_k.dtype, x_k.device
+    sub_desc, status = pdf._desc(dt).sub[k], pdf._status(dev)
+    grad = torch.empty_like(params_t)
+    g_z = torch.empty(B, d, dtype=dt, device=dev)
+    gx = g_x.contiguous()
+    gl = g_logp.contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.jf_subpdf_sample_backward(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
+                                           params_t.stride(0), 1, _ptr(gx), gx.stride(0), _ptr(gl), _ptr(grad), _ptr(g_z), d,
+                                           B, _ptr(status), _stream_ptr(dev))
+    _cabi.check(rc, "jf_subpdf_sample_backward")
+    return grad, g_z
+
+
 def mlp_params_forward(inp, w1, b1, w2, b2):
     """Per-row parameters [P, B] (param-major) of a Linear-tanh-Linear generator with 128 hidden units on the tcgen05
     MLP kernel (`jf_mlp_forward_ws`, the same kernel as inference).  Body of the op `jammy_b200::mlp_params`."""
@@ -1093,3 +1130,45 @@ def pdf_logpdf_trainable(pdf, x, cond):
         bases.append(base_k)
         prev.append(_embedding_torch(pdf, k, x_k))
     return logp, logp_base, torch.cat(bases, dim=1)
+
+
+def supports_sample_backward(pdf):
+    """differentiable sampling: Euclidean sub-pdfs made of default "g" layers (implicit-function reverse pass)"""
+    return supports_backward(pdf) and all(d[0] == "e" for d in pdf.pdf_defs_list)
+
+
+def pdf_sample_trainable(pdf, z, cond):
+    """-> (x [B, D], log_pdf [B], log_pdf_base [B]) WITH autograd history: the reference's `sample(allow_gradients=True)`
+    (main/default.py:1342), which differentiates through its bisection / Newton iterations; here the samples come from
+    the same kernels as without gradients and the backward is the implicit-function pass `jf_subpdf_sample_backward`."""
+    z, cond = _prep_inputs(pdf, z, cond, "z")
+    from . import ops
+    dt, dev = z.dtype, z.device
+    handle = ops.handle_of(pdf)
+    logp, logp_base, xs, prev = None, None, [], []
+    for k, layers in enumerate(pdf.layer_list):
+        mlp = pdf.mlp_predictors[k]
+        b0, b1 = pdf.base_dim_indices[k]
+        z_k = z[:, b0:b1].contiguous()
+        if mlp is None:
+            vecs = [v for v in (l.packed_permanent_params() for l in layers) if v is not None]
+            vec = torch.cat(vecs).to(device=dev, dtype=dt)
+            params_t = vec.unsqueeze(1).expand(vec.shape[0], z.shape[0]).contiguous()
+        else:
+            pieces = ([cond] if cond is not None else []) + prev
+            inp = torch.cat(pieces, dim=1) if len(pieces) > 1 else pieces[0]
+            mods = list(mlp)
+            if _tc_mlp_eligible(mlp, dt, dev):
+                params_t = torch.ops.jammy_b200.mlp_params(inp, mods[0].weight, mods[0].bias, mods[2].weight, mods[2].bias)
+            else:
+                h = inp
+                for m in mods[:-1]:
+                    h = m(h)
+                last = mods[-1]
+                params_t = torch.addmm(last.bias.unsqueeze(1), last.weight, h.t())
+        x_k, lp_k, lb_k = torch.ops.jammy_b200.subpdf_sample(params_t, z_k, handle, k)
+        logp = lp_k if logp is None else logp + lp_k
+        logp_base = lb_k if logp_base is None else logp_base + lb_k
+        xs.append(x_k)
+        prev.append(_embedding_torch(pdf, k, x_k))
+    return torch.cat(xs, dim=1), logp, logp_base

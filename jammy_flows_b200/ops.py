@@ -166,6 +166,48 @@ def _(inp, w1, b1, w2, jac, row_scale, want_inp_grad):
             torch.empty_like(w2), w2.new_empty(w2.shape[0]))
 
 
+@torch.library.custom_op("jammy_b200::subpdf_sample", mutates_args=(), device_types="cuda")
+def subpdf_sample(params_t: torch.Tensor, z_k: torch.Tensor, handle: int, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (x_k, log_pdf_k, log_base_k) of Euclidean sub-pdf k in the sampling direction (jf_subpdf_apply)"""
+    return engine.subpdf_sample_forward(_pdf(handle), k, params_t, z_k)
+
+
+@subpdf_sample.register_fake
+def _(params_t, z_k, handle, k):
+    B = z_k.shape[0]
+    return torch.empty_like(z_k), z_k.new_empty(B), z_k.new_empty(B)
+
+
+@torch.library.custom_op("jammy_b200::subpdf_sample_backward", mutates_args=(), device_types="cuda")
+def subpdf_sample_backward(params_t: torch.Tensor, x_k: torch.Tensor, g_x: torch.Tensor, g_logp: torch.Tensor, handle: int,
+                           k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    return engine.subpdf_sample_backward(_pdf(handle), k, params_t, x_k, g_x, g_logp)
+
+
+@subpdf_sample_backward.register_fake
+def _(params_t, x_k, g_x, g_logp, handle, k):
+    return torch.empty_like(params_t), torch.empty_like(x_k)
+
+
+def _sample_setup(ctx, inputs, output):
+    params_t, z_k, handle, k = inputs
+    ctx.save_for_backward(params_t, output[0], z_k)
+    ctx.handle, ctx.k = handle, k
+
+
+def _sample_bwd(ctx, g_x, g_logp, g_logbase):
+    params_t, x_k, z_k = ctx.saved_tensors
+    g_params, g_z = torch.ops.jammy_b200.subpdf_sample_backward(params_t, x_k, g_x.contiguous(), g_logp.contiguous(),
+                                                               ctx.handle, ctx.k)
+    if ctx.needs_input_grad[1]:
+        # log_pdf = log N(z) + sum of the layers' log-derivatives: the base density adds -z per unit of log_pdf / log_base
+        g_z = g_z - z_k * (g_logp + g_logbase).unsqueeze(1)
+    return g_params, (g_z if ctx.needs_input_grad[1] else None), None, None
+
+
+subpdf_sample.register_autograd(_sample_bwd, setup_context=_sample_setup)
+
+
 @torch.library.custom_op("jammy_b200::mlp_params", mutates_args=(), device_types="cuda")
 def mlp_params(inp: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     return engine.mlp_params_forward(inp, w1, b1, w2, b2)

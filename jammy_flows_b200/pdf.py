@@ -560,7 +560,15 @@ class pdf(nn.Module):
                failsafe_crosscheck_tolerance=None, dtype=None, device=None, only_last=False):
         assert (self.use_as_passthrough_instead_of_pdf == False)
         if allow_gradients:
-            raise NotImplementedError("differentiable sampling needs the backward kernels (K8), not built yet")
+            # reference main/default.py:1342-1355: the same call without torch.no_grad()
+            if (amortization_parameters is not None or only_last or failsafe_crosscheck_tolerance
+                    or not engine.supports_sample_backward(self)):
+                raise NotImplementedError("sample(allow_gradients=True) is built for pdfs made of Euclidean sub-pdfs with "
+                                          "default \"g\" layers (jf_subpdf_sample_backward)")
+            return self._obtain_sample(conditional_input=conditional_input, seed=seed, samplesize=samplesize,
+                                       force_embedding_coordinates=force_embedding_coordinates,
+                                       force_intrinsic_coordinates=force_intrinsic_coordinates, device=device, dtype=dtype,
+                                       _trainable=True)
         with torch.no_grad():
             return self._obtain_sample(conditional_input=conditional_input, seed=seed, samplesize=samplesize,
                                        amortization_parameters=amortization_parameters,
@@ -572,7 +580,7 @@ class pdf(nn.Module):
     def _obtain_sample(self, conditional_input=None, predefined_target_input=None, samplesize=1, seed=None,
                        amortization_parameters=None, force_embedding_coordinates=False,
                        force_intrinsic_coordinates=False, failsafe_crosscheck_tolerance=None, dtype=None, device=None,
-                       only_last=False):
+                       only_last=False, _trainable=False):
         used_sample_size = samplesize
         if self.amortize_everything:
             # reference main/default.py:1591-1606: batch, dtype and device come from the amortization parameters
@@ -614,7 +622,9 @@ class pdf(nn.Module):
         else:
             z = self._draw_base_normals(used_sample_size, seed, data_type, used_device)
             std_normal_samples = z
-        if (z.is_cuda and amortization_parameters is None and not only_last and not engine.uses_custom_mlp(self)
+        if _trainable and torch.is_grad_enabled():
+            x, log_pdf, log_gauss = engine.pdf_sample_trainable(self, z, conditional_input)
+        elif (z.is_cuda and amortization_parameters is None and not only_last and not engine.uses_custom_mlp(self)
                 and type(conditional_input) != list):
             from . import ops       # the whole-pdf entry as a torch.library op (ops.py)
             x, log_pdf, log_gauss = torch.ops.jammy_b200.pdf_sample(z, conditional_input, self._op_handle,

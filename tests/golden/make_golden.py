@@ -230,6 +230,9 @@ CASES = {
     "train_e2_gg_uncond": dict(pdf_defs="e2", flow_defs="gg", n=300, perturb=0.3, grads=True),
     "train_e3e2_uncond": dict(pdf_defs="e3+e2", flow_defs="gg+gg", n=200, perturb=0.2, grads=True),
     "train_e2e2_cond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=200, cond_dim=2, perturb=0.2, grads=True),
+    # gradients through SAMPLES (sample(allow_gradients=True), main/default.py:1342): loss = sum(x * w) + 0.3 sum(log_pdf)
+    "strain_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=100, cond_dim=3, perturb=0.2, sgrads=True),
+    "strain_e2e2_uncond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=100, perturb=0.2, sgrads=True),
     # non-Euclidean sub-pdfs in the training path (README-style mixed flow, every manifold layer kind)
     "train_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=120, perturb=0.1, grads=True),
     "train_s2_f_splines_cond": dict(pdf_defs="s2", flow_defs="f", n=120, cond_dim=2, perturb=0.1, grads=True,
@@ -328,6 +331,16 @@ def build_case(jf, name, spec):
         out["cond"] = cond.numpy()
     for k, v in pdf.state_dict().items():
         out["param/" + k] = v.numpy()
+    if spec.get("sgrads", False):
+        # reference autograd through the sampling direction (bisection + Newton iterations unrolled by autograd)
+        pdf.zero_grad()
+        w = torch.linspace(-1.0, 1.5, x.shape[1], dtype=dtype).unsqueeze(0) * torch.linspace(0.5, 1.5, n, dtype=dtype).unsqueeze(1)
+        sx, _, slp, _ = pdf._obtain_sample(conditional_input=cond, predefined_target_input=z)
+        ((sx * w).sum() + 0.3 * slp.sum()).backward()
+        out["sgrad_w"] = w.numpy()
+        for k, p_ in pdf.named_parameters():
+            if p_.grad is not None:
+                out["sgrad/" + k] = p_.grad.detach().numpy()
     if spec.get("grads", False):
         # reference autograd: d mean(log_pdf) / d (every parameter)
         pdf.zero_grad()

@@ -149,6 +149,76 @@ def test_adam_steps_decrease_the_loss(lib_built):
     assert p.kernel_status()["nonfinite"] == 0
 
 
+STRAIN = [n for n in golden_names() if n.startswith("strain_")]
+
+
+@pytest.mark.parametrize("name", STRAIN)
+def test_sample_gradients_match_reference_golden(name, lib_built):
+    """gradients through samples: the reference differentiates through its bisection / Newton iterations
+    (sample(allow_gradients=True), main/default.py:1342); here the implicit-function reverse pass
+    jf_subpdf_sample_backward.  Stated tolerance 1e-6 of each tensor's maximum (the reference's own iteration stops at
+    1e-7 of the target)."""
+    meta, params, data = load_golden(name)
+    p = build_pdf(meta, params).cuda()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    cond = t(data["cond"]) if "cond" in data else None
+    p.zero_grad()
+    x, _, lp, _ = p._obtain_sample(conditional_input=cond, predefined_target_input=t(data["z"]), _trainable=True)
+    assert np.abs(x.detach().cpu().numpy() - data["samp_x"]).max() < 1e-9
+    ((x * t(data["sgrad_w"])).sum() + 0.3 * lp.sum()).backward()
+    g = {k: q.grad.detach().cpu().numpy() for k, q in p.named_parameters() if q.grad is not None}
+    n = 0
+    for k in data:
+        if k.startswith("sgrad/"):
+            ref = data[k]
+            err = np.abs(g[k[6:]] - ref).max() / max(np.abs(ref).max(), 1e-30)
+            assert err < 1e-6, (k, err)
+            n += 1
+    assert n == len(g) and n > 0
+    assert p.kernel_status()["out_of_range"] == 0
+
+
+def test_sample_allow_gradients_api(lib_built):
+    """pdf.sample(allow_gradients=True): reparametrised samples carry gradients to the parameters and the conditional input"""
+    p = jfb.pdf("e3", "gg", conditional_input_dim=2).double().cuda()
+    c = torch.randn(64, 2, dtype=torch.float64, device="cuda", requires_grad=True)
+    x, z, lp, lb = p.sample(conditional_input=c, seed=3, allow_gradients=True)
+    (x.pow(2).sum() - lp.sum()).backward()
+    assert c.grad is not None and torch.isfinite(c.grad).all() and float(c.grad.abs().max()) > 0
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in p.parameters())
+    x2, _, lp2, _ = p.sample(conditional_input=c.detach(), seed=3)
+    assert torch.equal(x.detach(), x2) and torch.allclose(lp.detach(), lp2, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        jfb.pdf("s2", "f").double().cuda().sample(samplesize=4, allow_gradients=True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_readme_flow_trains(lib_built, dtype):
+    """the README flow (Euclidean + S2 + Euclidean, autoregressively conditioned) through pdf.forward + autograd: closed-form
+    reverse pass for the "g" chains, dual-number sweep for the "f" layer, generator gradients on the MLP kernels"""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    p = jfb.pdf("e4+s2+e4", "gggg+f+gggg").to(dtype).cuda()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = 4096
+    a = 0.7 * torch.randn(n, 4, generator=g, device="cuda", dtype=torch.float64) + 0.3
+    th = torch.acos(1 - 2 * torch.rand(n, generator=g, device="cuda", dtype=torch.float64)).clamp(0.05, 3.0)
+    ph = (2 * np.pi * torch.rand(n, generator=g, device="cuda", dtype=torch.float64) + 0.5 * a[:, 0]) % (2 * np.pi)
+    b = 0.5 * a + 0.5 * torch.randn(n, 4, generator=g, device="cuda", dtype=torch.float64)
+    x = torch.cat([a, th[:, None], ph[:, None], b], dim=1).to(dtype)
+    opt = torch.optim.Adam(p.parameters(), lr=5e-3)
+    losses = []
+    for _ in range(15):
+        opt.zero_grad()
+        lp, _, _ = p(x)
+        loss = -lp.mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 0.1, losses
+    assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in p.parameters())
+
+
 def test_backward_of_unsupported_pdfs_fails_loudly(lib_built):
     p = jfb.pdf("e2", "gt").double().cuda()                  # "t" layers / non-default "g" options: no backward kernel
     x = torch.tensor([[1.0, 2.0], [0.5, 4.0]], dtype=torch.float64, device="cuda")
