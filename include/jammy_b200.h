@@ -297,12 +297,15 @@ int jf_subpdf_sample_backward(const JfSubPdfDesc* desc, int dtype,
  *   params       element (j,row) at params[j*p_stride_param + row*p_stride_row]; p_stride_row == 0: shared parameters
  *   jac_params   out, element (j,row) at jac_params[j*jac_stride_param + row]   (at most 160 parameters per sub-pdf)
  *   jac_x        out, optional [B, dim] (ld_jx): d log_pdf / d x
+ *   jac_base     out, optional [n_params + dim][B][dim] (needs jac_x): derivative of the BASE point with respect to every
+ *                parameter, then every coordinate -- with it the caller differentiates the SAMPLING direction implicitly
+ *                (x = T(z): dx/dtheta = -(dbase/dx)^-1 dbase/dtheta), the reference's sample(allow_gradients=True)
  * "v" layers are differentiated in their closed-form direction only (natural_direction = 0), JF_ERR_UNSUPPORTED otherwise.
  */
 int jf_subpdf_jacobian(const JfSubPdfDesc* desc, int dtype,
                        const void* x, int64_t ld_x,
                        const void* params, int64_t p_stride_param, int64_t p_stride_row,
-                       void* jac_params, int64_t jac_stride_param, void* jac_x, int64_t ld_jx,
+                       void* jac_params, int64_t jac_stride_param, void* jac_x, int64_t ld_jx, void* jac_base,
                        int64_t B, int64_t* status, void* stream);
 
 /*

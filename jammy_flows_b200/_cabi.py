@@ -95,8 +95,8 @@ SYMBOLS = {
     "jf_subpdf_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
     "jf_subpdf_sample_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp,
                                             _vp, _i64, _i64, _vp, _vp]),
-    "jf_subpdf_jacobian": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64,
-                                     _vp, _vp]),
+    "jf_subpdf_jacobian": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp,
+                                     _i64, _vp, _vp]),
     "jf_subpdf_forward_backward": (C.c_int, [C.POINTER(JfSubPdfDesc), C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64,
                                              _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "jf_mlp_forward": (C.c_int, [C.POINTER(JfMlpDesc), C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),

@@ -481,13 +481,14 @@ extern "C" int jf_subpdf_sample_backward(const JfSubPdfDesc* desc, int dtype, co
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename F>
 static int subpdf_jacobian_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, const void* params, int64_t sp, int64_t sr,
-                             void* jac, int64_t jac_sj, void* jx, int64_t ld_jx, int64_t B, cudaStream_t st) {
+                             void* jac, int64_t jac_sj, void* jx, int64_t ld_jx, void* jbase, int64_t B, cudaStream_t st) {
     JacIO<F> io;
     io.n_params = desc->n_params; io.d = desc->dim; io.B = B;
     io.in = (const F*)x; io.ld_in = ld_x;
     io.params = (const F*)params; io.sj = sp; io.sr = sr;
     io.jac = (F*)jac; io.jac_sj = jac_sj;
     io.jx = (F*)jx; io.ld_jx = ld_jx;
+    io.jbase = (F*)jbase;
     const int threads = 128;
     const dim3 grid((unsigned)((B + threads - 1) / threads), (unsigned)(desc->n_params + (jx != nullptr ? desc->dim : 0)));
     if (grid.y == 0) return JF_OK;
@@ -516,8 +517,9 @@ static int subpdf_jacobian_t(const JfSubPdfDesc* desc, const void* x, int64_t ld
 
 extern "C" int jf_subpdf_jacobian(const JfSubPdfDesc* desc, int dtype, const void* x, int64_t ld_x, const void* params,
                                   int64_t p_stride_param, int64_t p_stride_row, void* jac_params, int64_t jac_stride_param,
-                                  void* jac_x, int64_t ld_jx, int64_t B, int64_t* status, void* stream) {
+                                  void* jac_x, int64_t ld_jx, void* jac_base, int64_t B, int64_t* status, void* stream) {
     (void)status;
+    if (jac_base != nullptr && jac_x == nullptr) return JF_ERR_BAD_ARG;
     if (desc == nullptr || x == nullptr) return JF_ERR_BAD_ARG;
     if (desc->n_layers < 1 || desc->n_layers > JF_MAX_LAYERS) return JF_ERR_BAD_DESC;
     if (desc->manifold == 'e') return JF_ERR_UNSUPPORTED;      // Euclidean chains: jf_subpdf_forward_backward
@@ -528,10 +530,10 @@ extern "C" int jf_subpdf_jacobian(const JfSubPdfDesc* desc, int dtype, const voi
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == JF_F64)
         return subpdf_jacobian_t<double>(desc, x, ld_x, params, p_stride_param, p_stride_row, jac_params, jac_stride_param,
-                                         jac_x, ld_jx, B, st);
+                                         jac_x, ld_jx, jac_base, B, st);
     if (dtype == JF_F32)
         return subpdf_jacobian_t<float>(desc, x, ld_x, params, p_stride_param, p_stride_row, jac_params, jac_stride_param,
-                                        jac_x, ld_jx, B, st);
+                                        jac_x, ld_jx, jac_base, B, st);
     return JF_ERR_BAD_ARG;
 }
 

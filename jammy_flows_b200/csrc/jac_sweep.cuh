@@ -23,6 +23,7 @@ struct JacIO {
     const F* params; int64_t sj, sr;    // element (i,row) at params[i*sj + row*sr]; sr == 0: shared
     F* jac; int64_t jac_sj;             // out: element (i,row) at jac[i*jac_sj + row]
     F* jx; int64_t ld_jx;               // out, optional: [B, d]
+    F* jbase;                           // out, optional: [n_params + d][B][d] derivative of the BASE point per seed
 };
 
 template <typename F>
@@ -34,6 +35,10 @@ template <typename F>
 JF_DEVINL void jac_store(const JacIO<F>& io, int64_t row, int seed, double v) {
     if (seed < io.n_params) io.jac[(int64_t)seed * io.jac_sj + row] = (F)v;
     else io.jx[row * io.ld_jx + (seed - io.n_params)] = (F)v;
+}
+template <typename F>
+JF_DEVINL void jac_store_base(const JacIO<F>& io, int64_t row, int seed, int i, double v) {
+    if (io.jbase != nullptr) io.jbase[((int64_t)seed * io.B + row) * io.d + i] = (F)v;
 }
 
 template <typename F>
@@ -53,6 +58,8 @@ __global__ void __launch_bounds__(128) s2_jac_kernel(const __grid_constant__ Jac
     }
     const Dual total = logdet - Dual(0.5) * (c0 * c0 + c1 * c1);
     jac_store(io, row, seed, total.d);
+    jac_store_base(io, row, seed, 0, c0.d);
+    jac_store_base(io, row, seed, 1, c1.d);
 }
 
 template <typename F>
@@ -69,6 +76,7 @@ __global__ void __launch_bounds__(128) chain1_jac_kernel(const __grid_constant__
         x = layer1_logpdf<Dual>(g.layers[l], g.manifold, x, logdet, p, 1, oor, evals, unconv);
     const Dual total = logdet - Dual(0.5) * x * x;
     jac_store(io, row, seed, total.d);
+    jac_store_base(io, row, seed, 0, x.d);
 }
 
 }  // namespace jf

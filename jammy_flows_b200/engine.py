@@ -905,7 +905,7 @@ def subpdf_logpdf_fb(pdf, k, params_t, x_k, g_logp=None):
                                      _ptr(base), d, None, 0, B, _ptr(status), _stream_ptr(dev))
             _cabi.check(rc, "jf_subpdf_apply")
             rc = lib.jf_subpdf_jacobian(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
-                                        params_t.stride(0), 1, _ptr(jac), jac.stride(0), _ptr(jx), d, B, _ptr(status),
+                                        params_t.stride(0), 1, _ptr(jac), jac.stride(0), _ptr(jx), d, None, B, _ptr(status),
                                         _stream_ptr(dev))
         if rc == -2:                      # JF_ERR_UNSUPPORTED
             raise NotImplementedError("jf_subpdf_jacobian: no backward for this sub-pdf (more than %d parameters, or an "
@@ -955,9 +955,12 @@ def subpdf_sample_forward(pdf, k, params_t, z_k):
     return x, logbase - logdet, logbase
 
 
-def subpdf_sample_backward(pdf, k, params_t, x_k, g_x, g_logp):
+def subpdf_sample_backward(pdf, k, params_t, x_k, z_k, g_x, g_logp):
     """(gradient with respect to the per-row parameters [P, B], cotangent of z_k [B, d]) of a sample x_k given the
-    cotangents of x_k and of log_pdf_k (`jf_subpdf_sample_backward`: implicit differentiation, no root finder)."""
+    cotangents of x_k and of log_pdf_k.  Euclidean "g" chains: `jf_subpdf_sample_backward` (implicit differentiation
+    layer by layer, no root finder).  Non-Euclidean sub-pdfs: the Jacobian blocks of the log_pdf direction at x_k from
+    the dual-number sweep (`jf_subpdf_jacobian` with jac_base), then dx/dtheta = -(dbase/dx)^-1 dbase/dtheta on the
+    d x d blocks (d <= 2)."""
     lib = _cabi.load()
     B, d = x_k.shape
     dt, dev = x_k.dtype, x_k.device
@@ -966,6 +969,25 @@ def subpdf_sample_backward(pdf, k, params_t, x_k, g_x, g_logp):
     g_z = torch.empty(B, d, dtype=dt, device=dev)
     gx = g_x.contiguous()
     gl = g_logp.contiguous()
+    if pdf.pdf_defs_list[k][0] != "e":
+        P = params_t.shape[0]
+        jx = torch.empty(B, d, dtype=dt, device=dev)
+        jb = torch.empty(P + d, B, d, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.jf_subpdf_jacobian(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
+                                        params_t.stride(0), 1, _ptr(grad), grad.stride(0), _ptr(jx), d, _ptr(jb), B,
+                                        _ptr(status), _stream_ptr(dev))
+        if rc == -2:
+            raise NotImplementedError("jf_subpdf_jacobian: no backward for this sub-pdf")
+        _cabi.check(rc, "jf_subpdf_jacobian")
+        # the sweep differentiates log N(base) + logdet: add base . dbase back to get the logdet part alone
+        dld_dp = grad + torch.einsum("pbd,bd->pb", jb[:P], z_k)
+        dld_dx = jx + torch.einsum("sbd,bd->bs", jb[P:], z_k)
+        Jx = jb[P:].permute(1, 2, 0)                                   # [B, d_out, d_seed] = dbase/dx
+        u = gx + gl.unsqueeze(1) * dld_dx
+        lam = torch.linalg.solve(Jx.transpose(1, 2), u.unsqueeze(2)).squeeze(2)
+        g_params = gl.unsqueeze(0) * dld_dp - torch.einsum("pbd,bd->pb", jb[:P], lam)
+        return g_params, lam
     with torch.cuda.device(dev):
         rc = lib.jf_subpdf_sample_backward(C.byref(sub_desc), _DT[dt], _ptr(x_k), x_k.stride(0), _ptr(params_t),
                                            params_t.stride(0), 1, _ptr(gx), gx.stride(0), _ptr(gl), _ptr(grad), _ptr(g_z), d,
@@ -1133,8 +1155,9 @@ def pdf_logpdf_trainable(pdf, x, cond):
 
 
 def supports_sample_backward(pdf):
-    """differentiable sampling: Euclidean sub-pdfs made of default "g" layers (implicit-function reverse pass)"""
-    return supports_backward(pdf) and all(d[0] == "e" for d in pdf.pdf_defs_list)
+    """differentiable sampling: every pdf whose log_pdf has a backward path (Euclidean "g" chains: implicit-function
+    reverse pass; non-Euclidean sub-pdfs: Jacobian blocks of the log_pdf direction at the sample)"""
+    return supports_backward(pdf)
 
 
 def pdf_sample_trainable(pdf, z, cond):
@@ -1152,7 +1175,7 @@ def pdf_sample_trainable(pdf, z, cond):
         z_k = z[:, b0:b1].contiguous()
         if mlp is None:
             vecs = [v for v in (l.packed_permanent_params() for l in layers) if v is not None]
-            vec = torch.cat(vecs).to(device=dev, dtype=dt)
+            vec = torch.cat(vecs).to(device=dev, dtype=dt) if len(vecs) > 0 else torch.zeros(0, dtype=dt, device=dev)
             params_t = vec.unsqueeze(1).expand(vec.shape[0], z.shape[0]).contiguous()
         else:
             pieces = ([cond] if cond is not None else []) + prev

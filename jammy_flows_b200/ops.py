@@ -179,13 +179,13 @@ def _(params_t, z_k, handle, k):
 
 
 @torch.library.custom_op("jammy_b200::subpdf_sample_backward", mutates_args=(), device_types="cuda")
-def subpdf_sample_backward(params_t: torch.Tensor, x_k: torch.Tensor, g_x: torch.Tensor, g_logp: torch.Tensor, handle: int,
-                           k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    return engine.subpdf_sample_backward(_pdf(handle), k, params_t, x_k, g_x, g_logp)
+def subpdf_sample_backward(params_t: torch.Tensor, x_k: torch.Tensor, z_k: torch.Tensor, g_x: torch.Tensor,
+                           g_logp: torch.Tensor, handle: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    return engine.subpdf_sample_backward(_pdf(handle), k, params_t, x_k, z_k, g_x, g_logp)
 
 
 @subpdf_sample_backward.register_fake
-def _(params_t, x_k, g_x, g_logp, handle, k):
+def _(params_t, x_k, z_k, g_x, g_logp, handle, k):
     return torch.empty_like(params_t), torch.empty_like(x_k)
 
 
@@ -197,7 +197,7 @@ def _sample_setup(ctx, inputs, output):
 
 def _sample_bwd(ctx, g_x, g_logp, g_logbase):
     params_t, x_k, z_k = ctx.saved_tensors
-    g_params, g_z = torch.ops.jammy_b200.subpdf_sample_backward(params_t, x_k, g_x.contiguous(), g_logp.contiguous(),
+    g_params, g_z = torch.ops.jammy_b200.subpdf_sample_backward(params_t, x_k, z_k, g_x.contiguous(), g_logp.contiguous(),
                                                                ctx.handle, ctx.k)
     if ctx.needs_input_grad[1]:
         # log_pdf = log N(z) + sum of the layers' log-derivatives: the base density adds -z per unit of log_pdf / log_base

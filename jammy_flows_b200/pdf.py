@@ -563,8 +563,8 @@ class pdf(nn.Module):
             # reference main/default.py:1342-1355: the same call without torch.no_grad()
             if (amortization_parameters is not None or only_last or failsafe_crosscheck_tolerance
                     or not engine.supports_sample_backward(self)):
-                raise NotImplementedError("sample(allow_gradients=True) is built for pdfs made of Euclidean sub-pdfs with "
-                                          "default \"g\" layers (jf_subpdf_sample_backward)")
+                raise NotImplementedError("sample(allow_gradients=True): this pdf has no backward path (default \"g\" layers "
+                                          "and the non-Euclidean layers f / v / r / o / m have one)")
             return self._obtain_sample(conditional_input=conditional_input, seed=seed, samplesize=samplesize,
                                        force_embedding_coordinates=force_embedding_coordinates,
                                        force_intrinsic_coordinates=force_intrinsic_coordinates, device=device, dtype=dtype,

@@ -233,6 +233,8 @@ CASES = {
     # gradients through SAMPLES (sample(allow_gradients=True), main/default.py:1342): loss = sum(x * w) + 0.3 sum(log_pdf)
     "strain_e3_ggg_cond": dict(pdf_defs="e3", flow_defs="ggg", n=100, cond_dim=3, perturb=0.2, sgrads=True),
     "strain_e2e2_uncond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=100, perturb=0.2, sgrads=True),
+    "strain_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=100, perturb=0.1, sgrads=True),
+    "strain_s1i1_or_cond": dict(pdf_defs="s1+i1_-0.5_0.8", flow_defs="o+r", n=100, cond_dim=2, perturb=0.1, sgrads=True),
     # non-Euclidean sub-pdfs in the training path (README-style mixed flow, every manifold layer kind)
     "train_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=120, perturb=0.1, grads=True),
     "train_s2_f_splines_cond": dict(pdf_defs="s2", flow_defs="f", n=120, cond_dim=2, perturb=0.1, grads=True,

@@ -189,7 +189,7 @@ def test_sample_allow_gradients_api(lib_built):
     x2, _, lp2, _ = p.sample(conditional_input=c.detach(), seed=3)
     assert torch.equal(x.detach(), x2) and torch.allclose(lp.detach(), lp2, atol=1e-12)
     with pytest.raises(NotImplementedError):
-        jfb.pdf("s2", "f").double().cuda().sample(samplesize=4, allow_gradients=True)
+        jfb.pdf("e2", "gt").double().cuda().sample(samplesize=4, allow_gradients=True)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
