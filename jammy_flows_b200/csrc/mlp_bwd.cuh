@@ -253,24 +253,28 @@ __global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
 }
 
 // ---- [dW2 | db2] = G [h | 1] ------------------------------------------------------------------------------------------------
-// CTA = (parameter tile of 128, row range); 4 stages of (A: 128 p x 32 rows, 16 KB; B: 144 x 32, 18 KB)
-constexpr int kW2Stages = 4;
-constexpr int kW2TileA = 128 * kBwKC * 4, kW2TileB = kBwNExt * kBwKC * 4;
-constexpr int kW2Smem = kW2Stages * (kW2TileA + kW2TileB) + 256;
+// CTA = (parameter tile of 128, row range); 3 stages of (A: 128 p x 64 rows, 32 KB; B: two h tiles of 144 x 32, 36 KB).
+// 64 rows per chunk = 256 contiguous bytes of every parameter row: with 32 rows (128 B pieces 4 B * ld apart, every one in
+// another DRAM page) the kernel ran at 1.8 TB/s, long_scoreboard 11 per issue (ncu, profiles/), against 4.3 TB/s for
+// bw_dh's 512-byte pieces.
+constexpr int kW2Stages = 3;
+constexpr int kW2KC = 64;                                    // rows per chunk (8 MMAs of K = 8)
+constexpr int kW2TileA = 128 * kW2KC * 4, kW2TileB = kBwNExt * kBwKC * 4;     // B stage = 2 h tiles
+constexpr int kW2Smem = kW2Stages * (kW2TileA + 2 * kW2TileB) + 256;
 
 __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t offB = kW2Stages * kW2TileA, offBar = offB + kW2Stages * kW2TileB;
+    const uint32_t offB = kW2Stages * kW2TileA, offBar = offB + kW2Stages * 2 * kW2TileB;
     const uint32_t bar0 = sbase + offBar;
     auto bar_full = [&](int s) { return bar0 + 8 * s; };
     auto bar_empty = [&](int s) { return bar0 + 8 * (4 + s); };
     const uint32_t bar_done = bar0 + 8 * 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 128);
     const int p0 = blockIdx.x * 128;
-    // this CTA's row range, in chunks of 32 rows
-    const int64_t total_chunks = (a.B + kBwKC - 1) / kBwKC;
+    // this CTA's row range, in chunks of 64 rows
+    const int64_t total_chunks = (a.B + kW2KC - 1) / kW2KC;
     const int64_t per = (total_chunks + a.n_splits - 1) / a.n_splits;
     const int64_t c_begin = (int64_t)blockIdx.y * per;
     const int64_t c_end = c_begin + per < total_chunks ? c_begin + per : total_chunks;
@@ -292,16 +296,16 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
     if (n_chunks > 0) {
         if (warp < 8) {
             // ---- producers: cp.async 16-byte units (4 rows of one parameter) straight into the K-major A stage ----
-            // unit idx = tid + 256 j: w = idx >> 5, l = idx & 31 -> parameter (w >> 1) 8 + (l & 7), k-quad (w & 1) 4 + (l >> 3):
-            // a warp reads 64 contiguous bytes of 8 parameter rows and writes 512 contiguous bytes of shared memory
+            // unit idx = tid + 256 j (2048 per chunk): w = idx >> 5, l = idx & 31 -> parameter (w >> 2) 8 + (l & 7), k-quad
+            // (w & 3) 4 + (l >> 3): a warp reads 64 contiguous bytes of 8 parameter rows, writes 512 contiguous bytes
             auto issue = [&](int c) {
                 const int s = c % kW2Stages;
-                const int64_t rbase = (c_begin + c) * kBwKC;
+                const int64_t rbase = (c_begin + c) * kW2KC;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const int idx = tid + 256 * j;
                     const int w = idx >> 5, l = idx & 31;
-                    const int pl = (w >> 1) * 8 + (l & 7), kq = (w & 1) * 4 + (l >> 3);
+                    const int pl = (w >> 2) * 8 + (l & 7), kq = (w & 3) * 4 + (l >> 3);
                     const int p = p0 + pl;
                     const int64_t row = rbase + 4 * kq;
                     int bytes = 0;
@@ -310,9 +314,10 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
                     cp_async16(sbase + s * kW2TileA + bw_tile_off(128, pl, 4 * kq), src, bytes);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                if (tid == 0) {
-                    mbar_expect_tx(bar_full(s), kW2TileB);
-                    bulk_g2s(sbase + offB + s * kW2TileB, a.h_tiles + (size_t)(c_begin + c) * (kW2TileB / 4), kW2TileB, bar_full(s));
+                if (tid == 0) {                                     // the two 32-row h tiles of this chunk (contiguous)
+                    mbar_expect_tx(bar_full(s), 2 * kW2TileB);
+                    bulk_g2s(sbase + offB + s * 2 * kW2TileB, a.h_tiles + (size_t)(c_begin + c) * (2 * kW2TileB / 4), 2 * kW2TileB,
+                             bar_full(s));
                 }
             };
             for (int c = 0; c < kW2Stages - 1; ++c) {
@@ -340,9 +345,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
                     mbar_wait(bar_full(s), (uint32_t)((c / kW2Stages) & 1));
                     tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
+                    for (int ks = 0; ks < kW2KC / 8; ++ks) {
                         const uint64_t ad = umma_desc(sbase + s * kW2TileA + ks * 2 * lboA, lboA, 128);
-                        const uint64_t bd = umma_desc(sbase + offB + s * kW2TileB + ks * 2 * lboB, lboB, 128);
+                        const uint64_t bd = umma_desc(sbase + offB + s * 2 * kW2TileB + (ks >> 2) * kW2TileB + (ks & 3) * 2 * lboB, lboB, 128);
                         tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     }
                     tc_commit(bar_empty(s));

@@ -8,7 +8,7 @@ static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
 int64_t mlp_bwd_workspace_bytes(int P, int64_t B) {
     const int64_t w2 = (int64_t)((P + kBwKC - 1) / kBwKC) * kDhTile;
-    const int64_t ht = ((B + kBwKC - 1) / kBwKC) * (int64_t)kW2TileB;
+    const int64_t ht = ((B + kW2KC - 1) / kW2KC) * 2 * (int64_t)kW2TileB;      // an even number of 32-row h tiles
     return align256(w2) + align256(ht) + 2 * align256(B * kBwH * 4);
 }
 
@@ -19,7 +19,7 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     char* ws = (char*)workspace;
     const int n_ptiles32 = (a.P + kBwKC - 1) / kBwKC;
-    const int64_t n_rtiles32 = (a.B + kBwKC - 1) / kBwKC;
+    const int64_t n_rtiles32 = (a.B + kW2KC - 1) / kW2KC * 2;     // even: bw_dw2 reads the h tiles in pairs (a tile past B is zero)
     a.w2_tiles = (float*)ws;
     a.h_tiles = (float*)(ws + align256((int64_t)n_ptiles32 * kDhTile));
     a.dpre = (float*)((char*)a.h_tiles + align256(n_rtiles32 * (int64_t)kW2TileB));
@@ -35,10 +35,11 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     bw_dh_kernel<<<(unsigned)((a.B + 127) / 128), kBwThreads, kDhSmem, st>>>(a);
     {
-        // parameter tiles x row ranges: about three waves of CTAs, at least 8 chunks of rows each
+        // parameter tiles x row ranges: three waves of CTAs, at least 8 chunks of rows each
         const int n_pt = (a.P + 127) / 128;
-        int64_t splits = (3 * (int64_t)sms + n_pt - 1) / n_pt;
-        if (splits > (n_rtiles32 + 7) / 8) splits = (n_rtiles32 + 7) / 8;
+        const int64_t n_chunks64 = n_rtiles32 / 2;
+        int64_t splits = (3 * (int64_t)sms) / n_pt;                 // at most three full waves of CTAs (one CTA per SM)
+        if (splits > (n_chunks64 + 7) / 8) splits = (n_chunks64 + 7) / 8;
         if (splits < 1) splits = 1;
         a.n_splits = (int)splits;
         e = cudaFuncSetAttribute(bw_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem);
