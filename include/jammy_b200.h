@@ -129,6 +129,7 @@ extern "C" {
 #define JF_POT_EXPONENTIAL 0 /* grad = sum_k w_k mu_k exp(beta_k (x.mu_k - 1)); parameters [5, K] */
 #define JF_POT_LINEAR 1      /* grad = sum_k w_k mu_k;                         parameters [4, K] */
 #define JF_POT_QUADRATIC 2   /* grad = sum_k w_k mu_k (x.mu_k);                parameters [4, K] */
+#define JF_POT_SPLINES 3   /* v: integral-of-a-spline potential, 10-bin rational-quadratic spline per component (exponential_map_s2.py:346-388) */
 
 /* status words */
 #define JF_STATUS_NONFINITE 0

@@ -266,8 +266,9 @@ static int fill_s2(const JfSubPdfDesc* desc, S2Args<T>& g) {
             if (expect != L.n_params) return JF_ERR_BAD_DESC;
         } else {
             if (L.K < 1 || L.K > kMaxExpComp) return JF_ERR_UNSUPPORTED;
-            if (L.inv_type < JF_POT_EXPONENTIAL || L.inv_type > JF_POT_QUADRATIC) return JF_ERR_BAD_DESC;
-            if (n_hh + (L.inv_type == JF_POT_EXPONENTIAL ? 5 : 4) * L.K != L.n_params) return JF_ERR_BAD_DESC;
+            if (L.inv_type < JF_POT_EXPONENTIAL || L.inv_type > JF_POT_SPLINES) return JF_ERR_BAD_DESC;
+            const int n_pot = L.inv_type == JF_POT_EXPONENTIAL ? 5 : (L.inv_type == JF_POT_SPLINES ? 4 + 3 * kVSplineBins + 1 : 4);
+            if (n_hh + n_pot * L.K != L.n_params) return JF_ERR_BAD_DESC;
             c.pot = L.inv_type;
             c.K = L.K; c.natural_direction = L.natural_direction; c.max_iter = L.max_iter > 0 ? L.max_iter : 1000;
         }

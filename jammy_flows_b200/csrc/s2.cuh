@@ -298,11 +298,15 @@ JF_DEVINL void fvm_sample(T& c0, T& c1, T& logdet, const FvmLayerC& c, const Spl
 // log-det = 1/2 log det( (J B)^T (J B) ), J the 3x3 Jacobian of y in embedding space, B = [t, x cross t].
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxExpComp = 16;
+constexpr int kVSplineBins = 10;        // exp_map_type "splines": num_spline_basis_functions (exponential_map_s2.py:111)
 
 template <typename T>
 struct VRow {
     T mx[kMaxExpComp], my[kMaxExpComp], mz[kMaxExpComp], w[kMaxExpComp], beta[kMaxExpComp];
     int K, pot;
+    const T* sp_p;      // "splines" potential: raw spline parameters of component 0 (rows 4 .. 4 + 3 n + 1 of the [n_pot, K] block)
+    int64_t sp_sj;      // stride between consecutive spline parameters of one component (K * sj)
+    int64_t sp_ck;      // stride between components (sj)
 };
 
 // parameters [5, K] (index i*K + k): rows 0-2 mean direction (its length sets the weight bound), 3 log-weight, 4 log beta
@@ -310,6 +314,9 @@ template <typename T>
 JF_DEVINL void v_setup(VRow<T>& r, int K, int pot, const T* p, int64_t sj) {
     r.K = K;
     r.pot = pot;
+    r.sp_p = p + (int64_t)(4 * K) * sj;
+    r.sp_sj = (int64_t)K * sj;
+    r.sp_ck = sj;
     T lmax = -Num<T>::big;
     for (int k = 0; k < K; ++k) lmax = tmax(lmax, p[(int64_t)(3 * K + k) * sj]);
     T lsum = 0;
@@ -329,12 +336,28 @@ JF_DEVINL void v_setup(VRow<T>& r, int K, int pot, const T* p, int64_t sj) {
 template <typename T>
 __device__ __noinline__ void v_eval(const VRow<T>& r, const T* x, T* y, T* J, T& hld) {
     T g0 = 0, g1 = 0, g2 = 0, G00 = 0, G01 = 0, G02 = 0, G11 = 0, G12 = 0, G22 = 0;
+    SplineC<T> sc;
+    if (r.pot == JF_POT_SPLINES) {
+        // plain 10-bin spline on [-1,1] -> [-1,1] with (n, n, n+1) raw parameters, exponential_map_s2.py:358-366
+        sc.kind = JF_SPLINE_PLAIN; sc.n_bins = kVSplineBins; sc.n_w = kVSplineBins; sc.n_h = kVSplineBins; sc.n_d = kVSplineBins + 1;
+        sc.fix_first = 0; sc.fix_second = 0; sc.indep = 0; sc.bd_mode = JF_BD_PARAMS; sc.natural_direction = 0; sc.raw_off = 0;
+        sc.pad_ = 0;
+        sc.lo = T(-1); sc.hi = T(1); sc.min_w = T(1e-3); sc.min_h = T(1e-3); sc.min_d = T(1e-3); sc.bd_fixed = T(0);
+        sc.ln_max_ratio = T(-1);
+    }
     for (int k = 0; k < r.K; ++k) {
         const T xm = x[0] * r.mx[k] + x[1] * r.my[k] + x[2] * r.mz[k];
         // gradient of the potential and its Jacobian coefficient per component (exponential_map_s2.py:285-344)
         T c, cb;
         if (r.pot == JF_POT_EXPONENTIAL) { c = r.w[k] * exp(r.beta[k] * (xm - T(1))); cb = c * r.beta[k]; }
         else if (r.pot == JF_POT_QUADRATIC) { c = r.w[k] * xm; cb = r.w[k]; }
+        else if (r.pot == JF_POT_SPLINES) {
+            // the potential is the integral of the spline: its gradient is w mu s(x.mu), the Jacobian w mu mu^T s'(x.mu)
+            T sv, lad;
+            spline_apply<T>(sc, r.sp_p + (int64_t)k * r.sp_ck, r.sp_sj, T(1), false, xm, sv, lad);
+            c = r.w[k] * sv;
+            cb = r.w[k] * exp(lad);
+        }
         else { c = r.w[k]; cb = T(0); }
         g0 = fma(c, r.mx[k], g0); g1 = fma(c, r.my[k], g1); g2 = fma(c, r.mz[k], g2);
         G00 = fma(cb, r.mx[k] * r.mx[k], G00); G01 = fma(cb, r.mx[k] * r.my[k], G01); G02 = fma(cb, r.mx[k] * r.mz[k], G02);

@@ -337,7 +337,7 @@ class gf_block(layer_base):
 # =====================================================================================================================
 # Euclidean: affine layer "t"
 # =====================================================================================================================
-V_POTENTIALS = {"exponential": 0, "linear": 1, "quadratic": 2}     # JF_POT_* (exponential_map_s2.py:285-344)
+V_POTENTIALS = {"exponential": 0, "linear": 1, "quadratic": 2, "splines": 3}     # JF_POT_* (exponential_map_s2.py:285-344)
 COV_TYPES = {"identity": 0, "diagonal_symmetric": 1, "diagonal": 2, "full": 3}
 
 
@@ -945,9 +945,11 @@ class exponential_map_s2(layer_base):
             raise Exception("The moebius flow should be used for dimension 2!")
         unsupported = []
         if exp_map_type not in V_POTENTIALS:
-            # "splines" (integral of a spline) and "nn" have no kernel; anything else is unknown to the reference too
+            # "nn" raises in the reference itself ("only used for testing"); anything else is unknown to the reference too
             unsupported.append("exp_map_type=%s" % exp_map_type)
         if mean_parametrization != "old":
+            # (the reference's own evaluation of "householder" raises a TypeError: exponential_map_s2.py:270 calls
+            #  compute_householder_matrix without its hh_iter argument)
             unsupported.append("mean_parametrization=%s" % mean_parametrization)
         if num_components > 16:
             unsupported.append("num_components > 16")
@@ -970,7 +972,10 @@ class exponential_map_s2(layer_base):
         self.natural_direction = natural_direction
         self.max_num_newton_iter = max_num_newton_iter
         # mean direction (3) + log weight, + log beta for the exponential potential (exponential_map_s2.py:124-127)
-        self.num_potential_pars = 3 + (2 if exp_map_type == "exponential" else 1)
+        # "splines": + 10 widths, 10 heights, 11 derivatives of the spline whose integral is the potential (:129-131)
+        self.num_spline_basis_functions = 10
+        self.num_potential_pars = 3 + (2 if exp_map_type == "exponential" else
+                                       (1 + 3 * self.num_spline_basis_functions + 1 if exp_map_type == "splines" else 1))
         if use_permanent_parameters:
             self.potential_pars = nn.Parameter(torch.randn(self.num_potential_pars, self.num_components).unsqueeze(0))
         self.total_param_num += self.num_potential_pars * self.num_components

@@ -1114,7 +1114,8 @@ class VLayer:
     def _split(self, p):
         n_hh = self.s["hh_iter"] * 3 if self.s["add_rotation"] else 0
         q = householder_matrix(p[:, :n_hh].reshape(-1, self.s["hh_iter"], 3)) if n_hh > 0 else None
-        n_pot = 5 if self.s.get("exp_map_type", "exponential") == "exponential" else 4
+        kind = self.s.get("exp_map_type", "exponential")
+        n_pot = 5 if kind == "exponential" else (35 if kind == "splines" else 4)
         return q, p[:, n_hh:].reshape(p.shape[0], n_pot, self.s["K"])
 
     @staticmethod
@@ -1154,6 +1155,20 @@ class VLayer:
             e = torch.exp(beta * (xm - 1.0))
             g = (w * mu * e).sum(dim=-1)
             jac_g = torch.einsum("biu,bju->bij", beta * w * mu * e, mu)
+        elif kind == "splines":                                   # :346-388: the potential is the integral of a spline
+            nb, K = 10, self.s["K"]
+            b = max(x.shape[0], pars.shape[0])
+            sp = Spline(dict(kind="plain", n_bins=nb, n_w=nb, n_h=nb, n_d=nb + 1, fix_first=0, fix_second=0, indep=0,
+                             bd_mode=0, bd_fixed=0.0, lo=-1.0, hi=1.0, min_w=1e-3, min_h=1e-3, min_d=1e-3, max_ratio=-1.0))
+            res, der = [], []
+            for k in range(K):
+                pk = pars[:, 4:4 + 3 * nb + 1, k].expand(b, -1)
+                r_k, lad_k = sp.apply(xm[:, 0, k:k + 1].expand(b, -1), pk, False)
+                res.append(r_k)
+                der.append(lad_k.exp())
+            res, der = torch.stack(res, dim=2), torch.stack(der, dim=2)          # [B, 1, K]
+            g = (w * mu * res).sum(dim=-1)
+            jac_g = torch.einsum("biu,bju->bij", w * mu * der, mu.expand(b, -1, -1))
         elif kind == "linear":                                    # :315-324 (no Jacobian of the gradient)
             g = (w * mu).sum(dim=-1).expand(x.shape[0], -1)
             jac_g = torch.zeros(x.shape[0], 3, 3, dtype=x.dtype)

@@ -147,6 +147,9 @@ CASES = {
     "s2_vv_rot": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0, opts={"v": {"add_rotation": 1, "num_components": 4}}),
     "s2_v_natural": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"natural_direction": 1}}),
     "cfg4_e6s2_gv_small": dict(pdf_defs="e6+s2", flow_defs="gggggg+v", n=300, cond_dim=64, perturb=0.02),
+    "s2_v_splines": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.3, opts={"v": {"exp_map_type": "splines"}}),
+    "s2_v_splines_natural_cond": dict(pdf_defs="e2+s2", flow_defs="gg+v", n=200, cond_dim=2, perturb=0.1,
+                              opts={"v": {"exp_map_type": "splines", "natural_direction": 1, "num_components": 4}}),
     "s2_v_linear": dict(pdf_defs="s2", flow_defs="v", n=300, perturb=0.0, opts={"v": {"exp_map_type": "linear"}}),
     "s2_v_quadratic_natural": dict(pdf_defs="s2", flow_defs="vv", n=300, perturb=0.0,
                                    opts={"v": {"exp_map_type": "quadratic", "natural_direction": 1}}),

@@ -82,7 +82,7 @@ def test_unsupported_fails_loudly():
     with pytest.raises(NotImplementedError):
         jfb.pdf("e2", "gx")          # not built yet: must not fall back to anything
     with pytest.raises(NotImplementedError):
-        jfb.pdf("s2", "v", options_overwrite={"v": {"exp_map_type": "splines"}})
+        jfb.pdf("s2", "v", options_overwrite={"v": {"mean_parametrization": "householder"}})   # (fails in the reference too)
     with pytest.raises(Exception):
         jfb.pdf("e2", "f")           # layer/manifold mismatch (main/default.py:397-398)
 
