@@ -501,7 +501,9 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
     ms_probe, fma = C.c_float(0), C.c_double(0)
-    rc = lib.jf_probe_fma_peak(_cabi.JF_F64, 4096, C.byref(ms_probe), C.byref(fma), engine._stream_ptr(dev))
+    scratch = torch.zeros(64, dtype=torch.float64, device=dev)
+    rc = lib.jf_probe_fma_peak(_cabi.JF_F64, 4096, C.byref(ms_probe), C.byref(fma), C.c_void_p(scratch.data_ptr()),
+                               engine._stream_ptr(dev))
     fp64_peak = 2.0 * fma.value / (ms_probe.value * 1e-3) * 1e-12 if rc == 0 else None
     rows, total_kernel_ms = kernel_breakdown(pdf, x, z, lib, evals_per_elem)
     top = rows[0]

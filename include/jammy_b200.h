@@ -474,7 +474,7 @@ int jf_abi_version(void);
 /* FP64 DFMA / FP32 FFMA peak probe used as the roofline denominator of the compute-bound layer kernels:
  * runs `iters` dependent FMA chains on every SM and returns the elapsed milliseconds (CUDA events) in *ms and the
  * FMA count in *fma_count. */
-int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* stream);
+int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* scratch /* >= 256 bytes, device */, void* stream);
 /* number of kernel launches issued by this library since process start (for bench.py's gpu_launches) */
 int64_t jf_launch_count(void);
 /* sizeof() of the ABI structs as compiled into the library (0: JfLayerDesc, 1: JfSubPdfDesc, 2: JfMlpDesc,

@@ -129,7 +129,7 @@ SYMBOLS = {
     "jf_rowwise_linear": (C.c_int, [C.c_int, _vp, _i64, _i64, _i64, _vp, _i64, C.c_int32, C.c_int32, C.c_int, C.c_int,
                                     _vp, _i64, _i64, _i64, _vp]),
     "jf_abi_version": (C.c_int, []),
-    "jf_probe_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), _vp]),
+    "jf_probe_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), _vp, _vp]),
     "jf_launch_count": (_i64, []),
     "jf_struct_size": (_i64, [C.c_int]),
 }

@@ -619,8 +619,7 @@ static int launch_mlp2_i8_tn(const MlpArgs<T>& m, void* ws, int prepared, cudaSt
     JF_CUDA_OK(cudaFuncSetAttribute(mlp2_i8_kernel<T, NS, TN, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t blocks = (m.B + kI8Rows - 1) / kI8Rows;
     const unsigned grid = (unsigned)(blocks < sms ? blocks : sms);     // persistent: one CTA per SM
-    static const int dbg = [] { const char* e = getenv("JF_I8_DBG"); return e ? atoi(e) : 0; }();   // timing experiments only
-    mlp2_i8_kernel<T, NS, TN, KR><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots, dbg);
+    mlp2_i8_kernel<T, NS, TN, KR><<<grid, kI8Threads, smem, st>>>(m, (const unsigned char*)ws, n_slots);
     return check_launch();
 }
 static int launch_mlp2_i8(const MlpArgs<double>& m, void* ws, int prepared, cudaStream_t st) {
@@ -1354,14 +1353,13 @@ __global__ void fma_probe_kernel(T* out, int iters, T a, T b) {
     if (s == T(12345.678)) out[0] = s;
 }
 
-extern "C" int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* stream) {
-    if (ms == nullptr || fma_count == nullptr || iters < 1) return JF_ERR_BAD_ARG;
+extern "C" int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_count, void* scratch, void* stream) {
+    if (ms == nullptr || fma_count == nullptr || scratch == nullptr || iters < 1) return JF_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     JF_CUDA_OK(cudaGetDevice(&dev));
     JF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    void* buf = nullptr;
-    JF_CUDA_OK(cudaMalloc(&buf, 256));   // diagnostics only; the compute entry points never allocate
+    void* buf = scratch;                  // 256 bytes of device memory from the caller: the library never allocates
     const int threads = 512, grid = sms * 4;
     cudaEvent_t e0, e1;
     JF_CUDA_OK(cudaEventCreate(&e0));
@@ -1378,6 +1376,5 @@ extern "C" int jf_probe_fma_peak(int dtype, int iters, float* ms, double* fma_co
     *fma_count = (double)grid * threads * (double)iters * 8.0;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(buf);
     return JF_OK;
 }

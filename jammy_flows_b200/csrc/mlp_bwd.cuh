@@ -383,61 +383,78 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
 }
 
 // ---- dW1 = dpre^T x, db1 = sum dpre, dx = dpre W1 (1 % of the flops: FFMA) -------------------------------------------------
-// one block = 64 rows; thread t: hidden unit u = t & 127, half = t >> 7
+// persistent blocks over tiles of 64 rows; thread t: hidden unit u = t & 127, half = t >> 7 of the inputs.  The partial sums
+// of dW1 / db1 stay in registers over all tiles of a block and go out with ONE red.global pass per block (the first version
+// issued 128 x in atomics per 64 rows: 134 M per 1 M rows).
 constexpr int kSmRows = 64;
+constexpr int kSmMaxHalf = 48;                          // inputs per half: (96 + 1) / 2
 __global__ void __launch_bounds__(256) bw_small_kernel(const BwArgs a) {
     extern __shared__ float sm_s[];
     float* sD = sm_s;                                   // [64][129] dpre
     float* sX = sD + kSmRows * 129;                     // [64][in + 1]
     float* sW = sX + kSmRows * (a.in | 1);              // [128][in + 1]  W1
     const int ldxs = a.in | 1;
-    const int64_t row0 = (int64_t)blockIdx.x * kSmRows;
-    for (int e = threadIdx.x; e < kSmRows * kBwH; e += blockDim.x) {
-        const int r = e >> 7, n = e & 127;
-        sD[r * 129 + n] = (row0 + r < a.B) ? a.dpre[(row0 + r) * kBwH + n] : 0.f;
-    }
-    for (int e = threadIdx.x; e < kSmRows * a.in; e += blockDim.x) {
-        const int r = e / a.in, i = e - r * a.in;
-        sX[r * ldxs + i] = (row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
-    }
     if (a.dx != nullptr)
         for (int e = threadIdx.x; e < kBwH * a.in; e += blockDim.x) {
             const int u = e / a.in, i = e - u * a.in;
             sW[u * ldxs + i] = a.W1[e];
         }
-    __syncthreads();
     const int u = threadIdx.x & 127, half = threadIdx.x >> 7;
-    // dW1[u][i] for the inputs i of this half; db1[u]
-    {
-        const int i0 = half * ((a.in + 1) / 2), i1 = half == 0 ? (a.in + 1) / 2 : a.in;
-        float bsum = 0.f;
+    const int i0 = half * ((a.in + 1) / 2), i1 = half == 0 ? (a.in + 1) / 2 : a.in;
+    float acc[kSmMaxHalf / 8][8];
+#pragma unroll
+    for (int g = 0; g < kSmMaxHalf / 8; ++g)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[g][j] = 0.f;
+    float bsum = 0.f;
+    const int64_t n_tiles = (a.B + kSmRows - 1) / kSmRows;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kSmRows;
+        __syncthreads();                                // the previous tile has been consumed
+        for (int e = threadIdx.x; e < kSmRows * kBwH; e += blockDim.x) {
+            const int r = e >> 7, n = e & 127;
+            sD[r * 129 + n] = (row0 + r < a.B) ? a.dpre[(row0 + r) * kBwH + n] : 0.f;
+        }
+        for (int e = threadIdx.x; e < kSmRows * a.in; e += blockDim.x) {
+            const int r = e / a.in, i = e - r * a.in;
+            sX[r * ldxs + i] = (row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
+        }
+        __syncthreads();
+        // dW1[u][i] for the inputs i of this half; db1[u]
         if (half == 0)
             for (int r = 0; r < kSmRows; ++r) bsum += sD[r * 129 + u];
-        for (int i = i0; i < i1; i += 8) {
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int r = 0; r < kSmRows; ++r) {
-                const float dv = sD[r * 129 + u];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (i + j < i1) acc[j] = fmaf(dv, sX[r * ldxs + i + j], acc[j]);
-            }
+        for (int g = 0; g < kSmMaxHalf / 8; ++g) {
+            const int i = i0 + 8 * g;
+            if (i < i1) {
+                for (int r = 0; r < kSmRows; ++r) {
+                    const float dv = sD[r * 129 + u];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (i + j < i1) red_add(a.dW1 + (size_t)u * a.in + i + j, acc[j]);
-        }
-        if (half == 0) red_add(a.db1 + u, bsum);
-    }
-    // dx[row][i] = sum_u dpre[row][u] W1[u][i]: thread -> (row = t & 63, inputs i = (t >> 6) + 4 j)
-    if (a.dx != nullptr) {
-        const int r = threadIdx.x & 63;
-        if (row0 + r < a.B) {
-            for (int i = threadIdx.x >> 6; i < a.in; i += 4) {
-                float acc = 0.f;
-                for (int n = 0; n < kBwH; ++n) acc = fmaf(sD[r * 129 + n], sW[n * ldxs + i], acc);
-                a.dx[(row0 + r) * a.lddx + i] = acc;
+                    for (int j = 0; j < 8; ++j)
+                        if (i + j < i1) acc[g][j] = fmaf(dv, sX[r * ldxs + i + j], acc[g][j]);
+                }
             }
         }
+        // dx[row][i] = sum_u dpre[row][u] W1[u][i]: thread -> (row = t & 63, inputs i = (t >> 6) + 4 j)
+        if (a.dx != nullptr) {
+            const int r = threadIdx.x & 63;
+            if (row0 + r < a.B) {
+                for (int i = threadIdx.x >> 6; i < a.in; i += 4) {
+                    float s_ = 0.f;
+                    for (int n = 0; n < kBwH; ++n) s_ = fmaf(sD[r * 129 + n], sW[n * ldxs + i], s_);
+                    a.dx[(row0 + r) * a.lddx + i] = s_;
+                }
+            }
+        }
     }
+#pragma unroll
+    for (int g = 0; g < kSmMaxHalf / 8; ++g)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + 8 * g + j;
+            if (i < i1) red_add(a.dW1 + (size_t)u * a.in + i, acc[g][j]);
+        }
+    if (half == 0) red_add(a.db1 + u, bsum);
 }
 
 }  // namespace jf

@@ -51,7 +51,9 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
         const int smem = (kSmRows * 129 + kSmRows * ldxs + kBwH * ldxs) * 4;
         e = cudaFuncSetAttribute(bw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        bw_small_kernel<<<(unsigned)((a.B + kSmRows - 1) / kSmRows), 256, smem, st>>>(a);
+        const int64_t n_tiles = (a.B + kSmRows - 1) / kSmRows;
+        const int64_t grid = n_tiles < 2 * (int64_t)sms ? n_tiles : 2 * (int64_t)sms;      // persistent: two blocks per SM
+        bw_small_kernel<<<(unsigned)grid, 256, smem, st>>>(a);
     }
     return 0;
 }

@@ -202,10 +202,15 @@ __global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const T* __restrict__ 
 // (free-running MMA 0.53 ms + free-running LDTM 0.40 ms = 0.98 ms together, profiles/), so a double-buffered or
 // level-major accumulator scheme only adds hand-shakes.  What does overlap with the next tile's MMAs is the fp64
 // scale/bias and the global stores, which run after TMEM has been handed back.
+#ifndef JF_I8_DBG
+#define JF_I8_DBG 0
+#endif
 template <typename T, int NS, int TN, int KR>
 __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_constant__ MlpArgs<T> m,
-                                                                 const unsigned char* __restrict__ wsB, int n_slots,
-                                                                 int dbg) {
+                                                                 const unsigned char* __restrict__ wsB, int n_slots) {
+    // timing experiments only (variant builds with -DJF_I8_DBG=<bits>, never the product): 1 no MMAs, 2 loader free-runs,
+    // 4 no global stores, 8 no TMEM reads
+    constexpr int dbg = JF_I8_DBG;
     using Cfg = I8Cfg<NS, TN>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int Kin = m.dims[0], N = m.dims[2];

@@ -106,10 +106,13 @@ def _(params_t, x_k, g_logp, handle, k):
 
 def _subpdf_setup(ctx, inputs, output):
     ctx.save_for_backward(output[3], output[4])          # the Jacobians; the parameter block itself is not kept
+    ctx.set_materialize_grads(False)                     # (no [P, B] block of zeros for the unused Jacobian outputs)
 
 
 def _subpdf_bwd(ctx, g_logp, g_logbase, g_base, g_jac, g_jx):
     jac, jx = ctx.saved_tensors
+    if g_logp is None:                                    # log_pdf unused downstream (only log_base / base, which carry no history)
+        return None, None, None, None
     g_params = jac * g_logp.unsqueeze(0) if ctx.needs_input_grad[0] else None
     g_x = jx * g_logp.unsqueeze(1) if ctx.needs_input_grad[1] else None
     return g_params, g_x, None, None
@@ -138,10 +141,13 @@ def _(inp, w1, b1, w2, b2, x_k, handle, k):
 def _generated_setup(ctx, inputs, output):
     inp, w1, b1, w2, b2, x_k, handle, k = inputs
     ctx.save_for_backward(inp, w1, b1, w2, output[3], output[4])
+    ctx.set_materialize_grads(False)
 
 
 def _generated_bwd(ctx, g_logp, g_logbase, g_base, g_jac, g_jx):
     inp, w1, b1, w2, jac, jx = ctx.saved_tensors
+    if g_logp is None:
+        return None, None, None, None, None, None, None, None
     want = ctx.needs_input_grad[0]
     g_inp, g_w1, g_b1, g_w2, g_b2 = torch.ops.jammy_b200.mlp_params_backward_scaled(inp, w1, b1, w2, jac, g_logp.contiguous(), want)
     g_x = jx * g_logp.unsqueeze(1) if ctx.needs_input_grad[5] else None
@@ -193,10 +199,16 @@ def _sample_setup(ctx, inputs, output):
     params_t, z_k, handle, k = inputs
     ctx.save_for_backward(params_t, output[0], z_k)
     ctx.handle, ctx.k = handle, k
+    ctx.set_materialize_grads(False)
 
 
 def _sample_bwd(ctx, g_x, g_logp, g_logbase):
     params_t, x_k, z_k = ctx.saved_tensors
+    if g_x is None and g_logp is None and g_logbase is None:
+        return None, None, None, None
+    g_x = torch.zeros_like(x_k) if g_x is None else g_x
+    g_logp = x_k.new_zeros(x_k.shape[0]) if g_logp is None else g_logp
+    g_logbase = x_k.new_zeros(x_k.shape[0]) if g_logbase is None else g_logbase
     g_params, g_z = torch.ops.jammy_b200.subpdf_sample_backward(params_t, x_k, z_k, g_x.contiguous(), g_logp.contiguous(),
                                                                ctx.handle, ctx.k)
     if ctx.needs_input_grad[1]:
