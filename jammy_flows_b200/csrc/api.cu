@@ -404,6 +404,11 @@ static int subpdf_fb_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, co
     int kmax = 1, hh_max = 0;
     for (int l = 0; l < desc->n_layers; ++l) {
         const JfLayerDesc& L = desc->layers[l];
+        if (L.kind == JF_LAYER_MVN && L.dim == d) {               // "t": affine layer, reverse pass in fb_mvn_backward
+            const int rc = fill_mvn<T>(g.layers[l], L, d, 0);
+            if (rc != JF_OK) return rc;
+            continue;
+        }
         if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_UNSUPPORTED;
         if (!gf_layer_is_default(L)) return JF_ERR_UNSUPPORTED;   // the closed-form backward covers the default options
         if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;

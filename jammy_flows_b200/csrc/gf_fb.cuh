@@ -305,6 +305,82 @@ __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* g
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "t" (affine) layers inside the chain: x = L z + mu with a lower-triangular L (csrc/gf.cuh mvn_layer_*; reference
+// layers/euclidean/multivariate_normal.py:228-272).  A "t" layer costs ~d^2 operations per row against ~2500 x d for a "g"
+// layer, so ONE worker of the row (dimension 0) does the whole vector: the others hand their component over through the
+// exchange and wait.
+//   log_pdf direction: y = x - mu, L z = y, logdet -= sum log w_i.  Reverse pass for cotangents zb of z and gl of logdet:
+//   yb = L^-T zb, Lbar_ij = -yb_i z_j, wbar_i = -yb_i z_i - gl / w_i, mubar = -yb, xbar = yb.
+//   sampling direction (MODE 1): x = L z + mu: zb = L^T xb, Lbar_ij = xb_i z_j, wbar_i = xb_i z_i - gl / w_i, mubar = xb.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T> JF_DEVINL T fb_dw_draw(T w, T w_min, T inv_w_max) {
+    // w = w_min + 1/q, q = 1/w_max + exp(-raw):  dw/draw = (q - 1/w_max) / q^2
+    const T r = w - w_min;                              // 1/q
+    return (T(1) / r - inv_w_max) * r * r;
+}
+
+template <typename T, int D, bool SDIR>
+__device__ __noinline__ void fb_mvn_backward(const GfLayerC<T>& c, const T* prow, T* grow, int64_t sj, const T* z, T* zb, T gl) {
+    const int cov = c.inv_type;
+    const T* q = prow + (int64_t)(c.raw_off + (c.has_offset ? D : 0)) * sj;
+    T* gq = grow + (int64_t)(c.raw_off + (c.has_offset ? D : 0)) * sj;
+    if (SDIR && c.has_offset) {
+        for (int i = 0; i < D; ++i) grow[(int64_t)(c.raw_off + i) * sj] = zb[i];
+    }
+    if (cov == 1) {
+        T w, iw;
+        regulate_width(q[0], c.w_min, c.inv_w_max, w, iw);
+        T s = 0;
+        for (int i = 0; i < D; ++i) s = fma(zb[i], z[i], s);
+        // log_pdf: z = y / w (dz/dw = -z/w);  sampling: x = w z (dx/dw = z)
+        const T wbar = (SDIR ? s : -s * iw) - gl * T(D) * iw;
+        gq[0] = wbar * fb_dw_draw(w, c.w_min, c.inv_w_max);
+        for (int i = 0; i < D; ++i) zb[i] *= SDIR ? w : iw;
+    } else if (cov >= 2) {
+        T w[D], iw[D], out[D];
+        for (int i = 0; i < D; ++i) regulate_width(q[(int64_t)i * sj], c.w_min, c.inv_w_max, w[i], iw[i]);
+        if (SDIR) {
+            for (int i = 0; i < D; ++i) {                   // zb_out = L^T xb
+                T acc = w[i] * zb[i];
+                if (cov == 3)
+                    for (int k = i + 1; k < D; ++k) acc = fma(q[(int64_t)(D + mvn_lower_index(D, k, i)) * sj], zb[k], acc);
+                out[i] = acc;
+            }
+            for (int i = 0; i < D; ++i) {
+                gq[(int64_t)i * sj] = (zb[i] * z[i] - gl * iw[i]) * fb_dw_draw(w[i], c.w_min, c.inv_w_max);
+                if (cov == 3)
+                    for (int jj = 0; jj < i; ++jj) gq[(int64_t)(D + mvn_lower_index(D, i, jj)) * sj] = zb[i] * z[jj];
+            }
+        } else {
+            for (int ii = 0; ii < D; ++ii) {                // yb = L^-T zb (back substitution)
+                const int i = D - 1 - ii;
+                T acc = zb[i];
+                if (cov == 3)
+                    for (int k = i + 1; k < D; ++k) acc = fma(-q[(int64_t)(D + mvn_lower_index(D, k, i)) * sj], out[k], acc);
+                out[i] = acc * iw[i];
+            }
+            for (int i = 0; i < D; ++i) {
+                gq[(int64_t)i * sj] = (-out[i] * z[i] - gl * iw[i]) * fb_dw_draw(w[i], c.w_min, c.inv_w_max);
+                if (cov == 3)
+                    for (int jj = 0; jj < i; ++jj) gq[(int64_t)(D + mvn_lower_index(D, i, jj)) * sj] = -out[i] * z[jj];
+            }
+        }
+        for (int i = 0; i < D; ++i) zb[i] = out[i];
+    }
+    if (!SDIR && c.has_offset) {
+        for (int i = 0; i < D; ++i) grow[(int64_t)(c.raw_off + i) * sj] = -zb[i];
+    }
+}
+
+template <typename T, int D>
+__device__ __noinline__ void fb_mvn_forward(const GfLayerC<T>& c, const T* prow, int64_t sj, T* x, T& ld) {
+    T v[D];
+    for (int i = 0; i < D; ++i) v[i] = x[i];
+    mvn_layer_logpdf<T, D>(v, ld, c, D, prow, sj);
+    for (int i = 0; i < D; ++i) x[i] = v[i];
+}
+
 JF_DEVINL void fb_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // MODE 0: log_pdf forward + backward.  MODE 1: backward of the SAMPLING direction at the sample x = T(z; theta) (a.in): the
@@ -338,7 +414,26 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
 #pragma unroll 1
     for (int l = L - 1; l >= 0; --l) {
         const GfLayerC<T>& c = g.layers[l];
-        if (l > 0) fb_prefetch_layer<T>(g.layers[l - 1], D, j, prow, sj);
+        if (c.kind == 1) {
+            // "t" layer: worker 0 of the row maps the whole vector (see fb_mvn_backward); vsave keeps the layer's OUTPUT
+            ex[(fX + j) * 32] = xj;
+            fb_bar(bar_id, 32 * D);
+            if (j == 0 && live) {
+                T X[D], ldt = 0;
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) X[jj] = ex[(fX + jj) * 32];
+                fb_mvn_forward<T, D>(c, prow, sj, X, ldt);
+                ld_acc += ldt;
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) ex[(fXB + jj) * 32] = X[jj];
+            }
+            fb_bar(bar_id, 32 * D);
+            xj = ex[(fXB + j) * 32];
+            vsave[l] = xj;
+            fb_bar(bar_id, 32 * D);
+            continue;
+        }
+        if (l > 0 && g.layers[l - 1].kind == 0) fb_prefetch_layer<T>(g.layers[l - 1], D, j, prow, sj);
         if (c.has_offset) xj -= prow[(int64_t)(c.raw_off + j) * sj];
         if (c.hh_iter > 0) {
             ex[(fX + j) * 32] = xj;
@@ -405,7 +500,24 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
         for (int l = L - 1; l >= 0; --l) {
             const GfLayerC<T>& c = g.layers[l];
             const T v = vsave[l];
-            if (l > 0) fb_prefetch_layer<T>(g.layers[l - 1], D, j, prow, sj);
+            if (c.kind == 1) {
+                ex[(fX + j) * 32] = v;
+                ex[(fXB + j) * 32] = xb;
+                fb_bar(bar_id, 32 * D);
+                if (j == 0 && live) {
+                    T Z[D], ZB[D];
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) { Z[jj] = ex[(fX + jj) * 32]; ZB[jj] = ex[(fXB + jj) * 32]; }
+                    fb_mvn_backward<T, D, true>(c, prow, grow, sj, Z, ZB, gl);
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) ex[(fX + jj) * 32] = ZB[jj];
+                }
+                fb_bar(bar_id, 32 * D);
+                xb = ex[(fX + j) * 32];
+                fb_bar(bar_id, 32 * D);
+                continue;
+            }
+            if (l > 0 && g.layers[l - 1].kind == 0) fb_prefetch_layer<T>(g.layers[l - 1], D, j, prow, sj);
             if (c.has_offset && live) grow[(int64_t)(c.raw_off + j) * sj] = xb;      // x = Q v + offset
             if (c.hh_iter > 0) {
                 ex[(fX + j) * 32] = v;
@@ -500,7 +612,24 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
     for (int l = 0; l < L; ++l) {
         const GfLayerC<T>& c = g.layers[l];
         const T v = vsave[l];
-        if (l + 1 < L) fb_prefetch_layer<T>(g.layers[l + 1], D, j, prow, sj);
+        if (c.kind == 1) {
+            ex[(fX + j) * 32] = v;
+            ex[(fXB + j) * 32] = xb;
+            fb_bar(bar_id, 32 * D);
+            if (j == 0 && live) {
+                T Z[D], ZB[D];
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) { Z[jj] = ex[(fX + jj) * 32]; ZB[jj] = ex[(fXB + jj) * 32]; }
+                fb_mvn_backward<T, D, false>(c, prow, grow, sj, Z, ZB, gr);
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) ex[(fX + jj) * 32] = ZB[jj];
+            }
+            fb_bar(bar_id, 32 * D);
+            xb = ex[(fX + j) * 32];
+            fb_bar(bar_id, 32 * D);
+            continue;
+        }
+        if (l + 1 < L && g.layers[l + 1].kind == 0) fb_prefetch_layer<T>(g.layers[l + 1], D, j, prow, sj);
         if (live) {
             T vbar;
             bool ok;

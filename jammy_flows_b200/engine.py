@@ -826,7 +826,7 @@ _JAC_MAX_PARAMS = 160
 
 def supports_backward(pdf):
     """True when every sub-pdf has a backward path: Euclidean sub-pdfs made of "g" layers with default options and a stage
-    the closed-form reverse pass covers (`jf_subpdf_forward_backward`), non-Euclidean sub-pdfs ("f", "v", "r", "o", "m",
+    the closed-form reverse pass covers and / or "t" layers (`jf_subpdf_forward_backward`), non-Euclidean sub-pdfs ("f", "v", "r", "o", "m",
     any option; "v" / "m" in their closed-form direction) through the dual-number sweep `jf_subpdf_jacobian`.  Parameters
     may come from an MLP (per-row) or be permanent: a permanent vector is expanded to per-row form and autograd sums the
     per-row gradients back into it."""
@@ -843,6 +843,8 @@ def supports_backward(pdf):
                 return False
             continue
         for l in layers:
+            if getattr(l, "code", "") == "t":          # affine layer: reverse pass inside the chain kernel (fb_mvn_backward)
+                continue
             if getattr(l, "code", "") != "g" or l.inverse_function_type not in ("isigmoid", "inormal_partly_precise"):
                 return False
             if not l.is_default_kernel_config:

@@ -238,6 +238,15 @@ CASES = {
     "strain_e2e2_uncond": dict(pdf_defs="e2+e2", flow_defs="gg+gg", n=100, perturb=0.2, sgrads=True),
     "strain_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=100, perturb=0.1, sgrads=True),
     "strain_s1i1_or_cond": dict(pdf_defs="s1+i1_-0.5_0.8", flow_defs="o+r", n=100, cond_dim=2, perturb=0.1, sgrads=True),
+    "strain_e3_ggt_cond": dict(pdf_defs="e3", flow_defs="ggt", n=100, cond_dim=2, perturb=0.2, sgrads=True,
+                               opts={"t": {"cov_type": "full"}}),
+    # the docs' recommended Euclidean recipe "g...gt" (suggested_settings.rst:14-41) in the training path
+    "train_e3_ggt_full_cond": dict(pdf_defs="e3", flow_defs="ggt", n=150, cond_dim=2, perturb=0.2, grads=True,
+                                   opts={"t": {"cov_type": "full"}}),
+    "train_e2e3_t_variants": dict(pdf_defs="e2+e3", flow_defs="tg+gt", n=150, perturb=0.2, grads=True,
+                                  opts={"t": {"cov_type": "diagonal"}}),
+    "train_e2_gt_symmetric": dict(pdf_defs="e2", flow_defs="gt", n=150, cond_dim=2, perturb=0.2, grads=True,
+                                  opts={"t": {"cov_type": "diagonal_symmetric"}}),
     # non-Euclidean sub-pdfs in the training path (README-style mixed flow, every manifold layer kind)
     "train_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=120, perturb=0.1, grads=True),
     "train_s2_f_splines_cond": dict(pdf_defs="s2", flow_defs="f", n=120, cond_dim=2, perturb=0.1, grads=True,

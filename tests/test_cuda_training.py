@@ -189,7 +189,7 @@ def test_sample_allow_gradients_api(lib_built):
     x2, _, lp2, _ = p.sample(conditional_input=c.detach(), seed=3)
     assert torch.equal(x.detach(), x2) and torch.allclose(lp.detach(), lp2, atol=1e-12)
     with pytest.raises(NotImplementedError):
-        jfb.pdf("e2", "gt").double().cuda().sample(samplesize=4, allow_gradients=True)
+        jfb.pdf("e2", "gg", options_overwrite={"g": {"rotation_mode": "angles"}}).double().cuda().sample(samplesize=4, allow_gradients=True)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -220,7 +220,7 @@ def test_readme_flow_trains(lib_built, dtype):
 
 
 def test_backward_of_unsupported_pdfs_fails_loudly(lib_built):
-    p = jfb.pdf("e2", "gt").double().cuda()                  # "t" layers / non-default "g" options: no backward kernel
+    p = jfb.pdf("e2", "gg", options_overwrite={"g": {"rotation_mode": "angles"}}).double().cuda()   # non-default "g" options: no backward kernel
     x = torch.tensor([[1.0, 2.0], [0.5, 4.0]], dtype=torch.float64, device="cuda")
     lp, _, _ = p(x)
     with pytest.raises(NotImplementedError):
