@@ -759,13 +759,52 @@ def run_train_arm(args, rank, world, local_rank):
     P = 3210
     flops_row = 3 * 2.0 * (64 * 128 + 128 * P) + 8 * 10 * (85 * SPECIAL + 600)
     achieved = flops_row * n * world / (ms_per_step * 1e-3) * 1e-12
-    tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
-    roofline = dict(bound="tensor", kernel="training step (generator GEMMs + fused layer forward/backward)", achieved=achieved,
-                    peak=tf32_peak, unit="TFLOP/s", frac=achieved / tf32_peak, traffic=None,
-                    peak_source="tf32 dense = bf16_tflops / 2 of MEASURED_PEAKS.json (nominal ratio)",
-                    flop_equiv_per_row=flops_row,
-                    note="whole-step figure: the step is a chain of kernels (tcgen05 forward MLP, layer forward, layer "
-                         "backward, backward GEMMs, optimizer); per-kernel shares in profiles/")
+    # ---- the dominant kernel, timed live with CUDA events on the launching stream: the three stages of one chunk driven
+    #      through the same entries the autograd path calls (generator forward, chain forward + backward, generator backward)
+    from jammy_flows_b200 import engine
+    mods = list(pdf.mlp_predictors[0])
+    w1, b1, w2, b2 = mods[0].weight.detach(), mods[0].bias.detach(), mods[2].weight.detach(), mods[2].bias.detach()
+    stage_ms = [0.0, 0.0, 0.0]
+    g_row = torch.full((min(chunk, n),), -1.0 / n, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        for rep in range(2):                                    # first pass warms up
+            stage_ms = [0.0, 0.0, 0.0]
+            for r0 in range(0, n, chunk):
+                yc, cc = y[r0:r0 + chunk].contiguous(), cond[r0:r0 + chunk]
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
+                params_t = engine.mlp_params_forward(cc, w1, b1, w2, b2)
+                ev[1].record()
+                _, _, _, jac, _ = engine.subpdf_logpdf_fb(pdf, 0, params_t, yc)
+                ev[2].record()
+                engine.mlp_params_backward(cc, w1, b1, w2, jac, False, g_row[:yc.shape[0]])
+                ev[3].record()
+                torch.cuda.synchronize()
+                for i in range(3):
+                    stage_ms[i] += ev[i].elapsed_time(ev[i + 1])
+                del params_t, jac
+    n_chunks = (n + chunk - 1) // chunk
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # the chain kernel streams the [P, rows] fp32 parameter block twice (forward, backward) and writes the Jacobian block once
+    fb_bytes = 3.0 * P * 4 * n
+    achieved_gbs = fb_bytes / (stage_ms[1] * 1e-3) * 1e-9
+    kernels = [dict(kernel="gf_chain_fb_kernel<float,10,0> (chain forward + backward)", ms=stage_ms[1], share=stage_ms[1] / ms_per_step,
+                    launches=n_chunks, avg_launch_ms=stage_ms[1] / n_chunks),
+               dict(kernel="generator forward (mlp2_i8_kernel<float,4,64>, tcgen05 kind::i8)", ms=stage_ms[0],
+                    share=stage_ms[0] / ms_per_step, launches=2 * n_chunks),
+               dict(kernel="generator backward (bw_w2_tiles, bw_h_tiles, bw_dh, bw_dw2 [tcgen05 kind::tf32], bw_small)", ms=stage_ms[2],
+                    share=stage_ms[2] / ms_per_step, launches=5 * n_chunks)]
+    roofline = dict(bound="hbm", kernel=kernels[0]["kernel"], achieved=achieved_gbs, peak=hbm_peak, unit="GB/s",
+                    frac=achieved_gbs / hbm_peak, traffic=10.1e9 * (min(chunk, n) / 262144.0),
+                    peak_source="MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
+                    algorithmic_bytes_per_row=3 * P * 4, share_of_step=kernels[0]["share"], avg_launch_ms=kernels[0]["avg_launch_ms"],
+                    kernels=kernels,
+                    note="the kernel is instruction-issue bound (ncu: issue slots 64 %% busy at 20 warps per SM, DRAM 24 %%, "
+                         "profiles/ncu_r02_train.md); HBM is the roofline that would bound it, its algorithmic bytes are those "
+                         "of this unfused design (parameter block read twice + Jacobian block written: 38.5 KB per row; a "
+                         "generator-fused design needs 296 B per row, SURVEY 8d).  traffic: ncu dram bytes per 262 144-row "
+                         "launch (6.3 GB read + 3.9 GB written), scaled to the chunk.  Whole step: %.1f TFLOP-eq/s of generator "
+                         "GEMM + layer work" % achieved)
     cb = train_cpu_arm(2) if world == 1 else None
     line = dict(metric=TRAIN_METRIC, value=world * n / (ms_per_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
