@@ -70,11 +70,17 @@ JF_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
 #ifndef JF_MBAR_SUSPEND_NS
 #define JF_MBAR_SUSPEND_NS 20000
 #endif
+// JF_MBAR_SLEEP_NS > 0: back off with nanosleep after a failed try (a spinning warp otherwise issues try_wait / branch /
+// yield continuously: a third of the executed instructions of the fused sampling kernel, ncu source page)
+#ifndef JF_MBAR_SLEEP_NS
+#define JF_MBAR_SLEEP_NS 0
+#endif
 JF_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)JF_MBAR_SUSPEND_NS) : "memory");
+        if (JF_MBAR_SLEEP_NS > 0 && !ok) asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)JF_MBAR_SLEEP_NS));
     } while (!ok);
 }
 JF_DEVINL void mbar_arrive(uint32_t bar) {
