@@ -29,13 +29,14 @@ namespace jf {
 template <typename T>
 JF_DEVINL void fb_prefetch_layer(const GfLayerC<T>& c, int D, int j, const T* prow, int64_t sj) {
     if (c.has_offset) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(c.raw_off + j) * sj));
-#pragma unroll 1
-    for (int i = 0; i < c.hh_iter; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (int64_t)(c.raw_hh() + i * D + j) * sj));
-    const T* pm = prow + (int64_t)(c.raw_m() + j) * sj;
+    // the reflection components and the m / w / n blocks follow each other, every D-th parameter is this worker's
+    const T* q = prow + (int64_t)(c.raw_hh() + j) * sj;
     const int64_t step = (int64_t)D * sj;
-    const int nf = c.norm_mode != JF_NORM_NONE ? 3 * c.K : 2 * c.K;       // m, w, n blocks are contiguous: K*D rows each
+    const int nq = c.hh_iter + (c.norm_mode != JF_NORM_NONE ? 3 * c.K : 2 * c.K);
+    // the 32 rows of a warp share one 128-byte line per parameter (fp32): LANE k asks for parameter k, so that one
+    // instruction per warp covers 32 parameters (40 per-thread prefetches per layer were 12 % of the executed instructions)
 #pragma unroll 1
-    for (int k = 0; k < nf; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + k * step));
+    for (int k = (int)(threadIdx.x & 31); k < nq; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (int64_t)k * step));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -57,14 +58,14 @@ struct FbMix {
 template <typename T, int K>
 JF_DEVINL void fb_load(const GfLayerC<T>& c, const T* pm, int64_t step, FbMix<T, K>& M) {
     T rw[K], rn[K];
+    const T* q = pm;                       // (a walking pointer: k * step as a 64-bit product costs 5 instructions per load)
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        M.m[k] = pm[k * step];
-        rw[k] = pm[(K + k) * step];
-    }
+    for (int k = 0; k < K; ++k) { M.m[k] = *q; q += step; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { rw[k] = *q; q += step; }
     if (c.norm_mode != JF_NORM_NONE) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) rn[k] = pm[(2 * K + k) * step];
+        for (int k = 0; k < K; ++k) { rn[k] = *q; q += step; }
     }
     T G = 0;
 #pragma unroll
@@ -269,6 +270,9 @@ __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* g
     if (!SDIR) vbar = cCS * Sp + glp * Sd;
     T nb[K];
     T nbar_dot = 0;
+    T* gq_m = gm;
+    T* gq_w = gm + (int64_t)K * step;
+    T* gq_n = gq_w + (int64_t)K * step;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const T m = M.m[k], iw = M.iw[k], n = M.g[k] * invG;
@@ -285,11 +289,13 @@ __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* g
         const T sig_t = pos ? rx : ur * E;
         nb[k] = nC * sigC + nS * sigS + nC_true * sig_t + glp * t * iw;
         nbar_dot = fma(nb[k], n, nbar_dot);
-        gm[k * step] = mbar;
+        *gq_m = mbar;
+        gq_m += step;
         // 1/w = q/(w_min q + 1), q = 1/w_max + exp(-raw): d(1/w)/d raw = -(q - 1/w_max) (1 - w_min/w)^2
         const T om = T(1) - c.w_min * iw;
         const T q = iw * rcp_pos_(om);
-        gm[(K + k) * step] = -iwbar * (q - c.inv_w_max) * om * om;
+        *gq_w = -iwbar * (q - c.inv_w_max) * om * om;
+        gq_w += step;
     }
     if (c.norm_mode != JF_NORM_NONE) {
         const T inv_nmax = c.norm_mode == JF_NORM_REGULATED ? T(1) / c.n_max : T(0);
@@ -299,7 +305,8 @@ __device__ __noinline__ bool fb_bwd_elem(const GfLayerC<T>& c, const T* pm, T* g
             const T gbar = (nb[k] - nbar_dot) * invG;               // n_k = g_k / G
             T dg = g;
             if (c.norm_mode == JF_NORM_REGULATED) { const T s = (g - c.n_min) * inv_nmax; dg = c.n_max * s * (T(1) - s); }
-            gm[(2 * K + k) * step] = gbar * dg;
+            *gq_n = gbar * dg;
+            gq_n += step;
         }
     }
     return true;
@@ -437,8 +444,12 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
         if (c.has_offset) xj -= prow[(int64_t)(c.raw_off + j) * sj];
         if (c.hh_iter > 0) {
             ex[(fX + j) * 32] = xj;
-#pragma unroll 4
-            for (int i = 0; i < c.hh_iter; ++i) ex[(fH + i * D + j) * 32] = prow[(int64_t)(c.raw_hh() + i * D + j) * sj];
+            {
+                const T* ph = prow + (int64_t)(c.raw_hh() + j) * sj;
+                T* eh = ex + (fH + j) * 32;
+#pragma unroll 5
+                for (int i = 0; i < c.hh_iter; ++i) { *eh = *ph; ph += (int64_t)D * sj; eh += D * 32; }
+            }
             fb_bar(bar_id, 32 * D);
             T X[D];
 #pragma unroll
@@ -522,8 +533,12 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
             if (c.hh_iter > 0) {
                 ex[(fX + j) * 32] = v;
                 ex[(fXB + j) * 32] = xb;
-#pragma unroll 4
-                for (int i = 0; i < c.hh_iter; ++i) ex[(fH + i * D + j) * 32] = prow[(int64_t)(c.raw_hh() + i * D + j) * sj];
+                {
+                    const T* ph = prow + (int64_t)(c.raw_hh() + j) * sj;
+                    T* eh = ex + (fH + j) * 32;
+#pragma unroll 5
+                    for (int i = 0; i < c.hh_iter; ++i) { *eh = *ph; ph += (int64_t)D * sj; eh += D * 32; }
+                }
                 fb_bar(bar_id, 32 * D);
                 T V[D], XB[D];
 #pragma unroll
@@ -546,6 +561,8 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
 #pragma unroll
                 for (int jj = 0; jj < D; ++jj) t_own = (jj == j) ? V[jj] : t_own;
                 // undo the reflections from the output side: t_i = H_i t_{i+1}, cotangent of t_i known
+                const int64_t hstep = (int64_t)D * sj;
+                T* gh = grow + (int64_t)(c.raw_hh() + j) * sj;
 #pragma unroll 1
                 for (int i = 0; i < c.hh_iter; ++i) {
                     T w[D], s_ = 0, aa = 0, bb = 0;
@@ -561,8 +578,8 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
                     const T w_own = ex[(fH + i * D + j) * 32];
                     const T ca = T(2) * aa * is, cb = T(2) * bb * is;
                     const T tin = fma(-ca, w_own, t_own);
-                    if (live)
-                        grow[(int64_t)(c.raw_hh() + i * D + j) * sj] = -T(2) * is * (bb * tin + ain * xb_own) + T(4) * ain * bb * is * is * w_own;
+                    if (live) *gh = -T(2) * is * (bb * tin + ain * xb_own) + T(4) * ain * bb * is * is * w_own;
+                    gh += hstep;
                     xb_own = fma(-cb, w_own, xb_own);
                     t_own = tin;
 #pragma unroll
@@ -655,13 +672,19 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
             // v = H_{n-1} ... H_0 u: undo reflection by reflection (each one is its own inverse)
             ex[(fX + j) * 32] = v;
             ex[(fXB + j) * 32] = xb;
-#pragma unroll 4
-            for (int i = 0; i < c.hh_iter; ++i) ex[(fH + i * D + j) * 32] = prow[(int64_t)(c.raw_hh() + i * D + j) * sj];
+            {
+                const T* ph = prow + (int64_t)(c.raw_hh() + j) * sj;
+                T* eh = ex + (fH + j) * 32;
+#pragma unroll 5
+                for (int i = 0; i < c.hh_iter; ++i) { *eh = *ph; ph += (int64_t)D * sj; eh += D * 32; }
+            }
             fb_bar(bar_id, 32 * D);
             T V[D], XB[D];
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) { V[jj] = ex[(fX + jj) * 32]; XB[jj] = ex[(fXB + jj) * 32]; }
             T v_own = v, xb_own = xb;
+            const int64_t hstep = (int64_t)D * sj;
+            T* gh = grow + (int64_t)(c.raw_hh() + j) * sj + (int64_t)(c.hh_iter - 1) * hstep;
 #pragma unroll 1
             for (int i = c.hh_iter - 1; i >= 0; --i) {
                 T w[D], s = 0, aa = 0, bb = 0;
@@ -677,8 +700,8 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
                 const T w_own = ex[(fH + i * D + j) * 32];
                 const T ca = T(2) * aa * is, cb = T(2) * bb * is;
                 const T xin = fma(-ca, w_own, v_own);
-                if (live)
-                    grow[(int64_t)(c.raw_hh() + i * D + j) * sj] = -T(2) * is * (bb * xin + ain * xb_own) + T(4) * ain * bb * is * is * w_own;
+                if (live) *gh = -T(2) * is * (bb * xin + ain * xb_own) + T(4) * ain * bb * is * is * w_own;
+                gh -= hstep;
                 xb_own = fma(-cb, w_own, xb_own);
                 v_own = xin;
 #pragma unroll
