@@ -64,55 +64,62 @@ __global__ void __launch_bounds__(256) bw_w2_tiles_kernel(const float* __restric
 }
 
 // ---- prep: h = tanh(W1 x + b1) -> tiles of 32 rows: B operand (n = hidden | 1, k = row) of the dW2 product ---------------
-// one block = one tile (32 rows); thread (row = tid & 31, group of 16 hidden units = tid >> 5)
-__global__ void __launch_bounds__(256) bw_h_tiles_kernel(const BwArgs a) {
+// persistent blocks over tiles (W1 is staged in shared memory once per block, not once per 32 rows); thread (row = tid & 31,
+// group of 16 hidden units = tid >> 5)
+__global__ void __launch_bounds__(256) bw_h_tiles_kernel(const BwArgs a, int64_t n_tiles) {
     extern __shared__ float sm_h[];
     float* sW = sm_h;                                       // [in][128]  (W1 transposed)
     float* sX = sW + (size_t)a.in * kBwH;                   // [32][in + 1]
     const int ldxs = a.in | 1;
-    const int64_t row0 = (int64_t)blockIdx.x * kBwKC;
     for (int e = threadIdx.x; e < a.in * kBwH; e += blockDim.x) {
         const int u = e / a.in, i = e - u * a.in;
         sW[i * kBwH + u] = a.W1[e];
     }
-    for (int e = threadIdx.x; e < kBwKC * a.in; e += blockDim.x) {
-        const int r = e / a.in, i = e - r * a.in;
-        sX[r * ldxs + i] = (row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
-    }
-    __syncthreads();
     const int r = threadIdx.x & 31, ug = threadIdx.x >> 5;
-    const bool live = row0 + r < a.B;
-    char* t = reinterpret_cast<char*>(a.h_tiles) + (size_t)blockIdx.x * (kBwNExt * kBwKC * 4);
-    float z[16];
+    float bias[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) z[j] = a.b1[ug * 16 + j];
-    for (int i = 0; i < a.in; ++i) {
-        const float xi = sX[r * ldxs + i];
-        const float* w = sW + i * kBwH + ug * 16;
+    for (int j = 0; j < 16; ++j) bias[j] = a.b1[ug * 16 + j];
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kBwKC;
+        __syncthreads();                                    // (first pass: W1 is in place; later: the previous tile's inputs are consumed)
+        for (int e = threadIdx.x; e < kBwKC * a.in; e += blockDim.x) {
+            const int rr = e / a.in, i = e - rr * a.in;
+            sX[rr * ldxs + i] = (row0 + rr < a.B) ? a.x[(row0 + rr) * a.ldx + i] : 0.f;
+        }
+        __syncthreads();
+        const bool live = row0 + r < a.B;
+        char* t = reinterpret_cast<char*>(a.h_tiles) + (size_t)tile * (kBwNExt * kBwKC * 4);
+        float z[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) z[j] = fmaf(xi, w[j], z[j]);
-    }
-    // the upstream gradient of row r is G[., r] * s_r (s = 1 without row_scale): the scale rides on the B operand of the
-    // dW2 product (h s | s) and on the factor (1 - h^2) s of the dh epilogue, G itself is never rescaled
-    const float sr = (live && a.row_scale != nullptr) ? a.row_scale[row0 + r] : 1.f;
-    float fc[16];
+        for (int j = 0; j < 16; ++j) z[j] = bias[j];
+        for (int i = 0; i < a.in; ++i) {
+            const float xi = sX[r * ldxs + i];
+            const float* w = sW + i * kBwH + ug * 16;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float h = tanhf(z[j]);
-        *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, ug * 16 + j, r)) = live ? to_tf32(h * sr) : 0.f;
-        fc[j] = (1.f - h * h) * sr;
-    }
-    if (live) {
-        float4* dst = reinterpret_cast<float4*>(a.fac + (row0 + r) * kBwH + ug * 16);
+            for (int j = 0; j < 16; ++j) z[j] = fmaf(xi, w[j], z[j]);
+        }
+        // the upstream gradient of row r is G[., r] * s_r (s = 1 without row_scale): the scale rides on the B operand of the
+        // dW2 product (h s | s) and on the factor (1 - h^2) s of the dh epilogue, G itself is never rescaled
+        const float sr = (live && a.row_scale != nullptr) ? a.row_scale[row0 + r] : 1.f;
+        float fc[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(fc[4 * q], fc[4 * q + 1], fc[4 * q + 2], fc[4 * q + 3]);
-    }
-    // column 128 = s (its product with G is db2), the padding columns are zero
-    if (ug < 2) {
+        for (int j = 0; j < 16; ++j) {
+            const float h = tanhf(z[j]);
+            *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, ug * 16 + j, r)) = live ? to_tf32(h * sr) : 0.f;
+            fc[j] = (1.f - h * h) * sr;
+        }
+        if (live) {
+            float4* dst = reinterpret_cast<float4*>(a.fac + (row0 + r) * kBwH + ug * 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = kBwH + ug * 8 + j;
-            *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, n, r)) = (n == kBwH && live) ? to_tf32(sr) : 0.f;
+            for (int q = 0; q < 4; ++q) dst[q] = make_float4(fc[4 * q], fc[4 * q + 1], fc[4 * q + 2], fc[4 * q + 3]);
+        }
+        // column 128 = s (its product with G is db2), the padding columns are zero
+        if (ug < 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = kBwH + ug * 8 + j;
+                *reinterpret_cast<float*>(t + bw_tile_off(kBwNExt, n, r)) = (n == kBwH && live) ? to_tf32(sr) : 0.f;
+            }
         }
     }
 }

@@ -29,7 +29,8 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
         const int smem = (a.in * kBwH + kBwKC * (a.in | 1)) * 4;
         e = cudaFuncSetAttribute(bw_h_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        bw_h_tiles_kernel<<<(unsigned)n_rtiles32, 256, smem, st>>>(a);
+        const int64_t grid = n_rtiles32 < 4 * (int64_t)sms ? n_rtiles32 : 4 * (int64_t)sms;       // persistent over the tiles
+        bw_h_tiles_kernel<<<(unsigned)grid, 256, smem, st>>>(a, n_rtiles32);
     }
     e = cudaFuncSetAttribute(bw_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDhSmem);
     if (e != cudaSuccess) return (int)e;
