@@ -17,6 +17,7 @@
 // cp.async.bulk per chunk is enough.  Both kernels are HBM bound by design: 2 x P B 4 bytes of G per call.
 // The three small products (dW1 = dpre^T x, db1, dx = dpre W1: 1 % of the flops) are a plain FFMA kernel (bw_small_kernel).
 #pragma once
+#include <cuda.h>
 #include "mlp_i8.cuh"
 #include "mlp_bwd_launch.cuh"
 
@@ -260,19 +261,34 @@ __global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
 }
 
 // ---- [dW2 | db2] = G [h | 1] ------------------------------------------------------------------------------------------------
-// CTA = (parameter tile of 128, row range); 3 stages of (A: 128 p x 64 rows, 32 KB; B: two h tiles of 144 x 32, 36 KB).
-// 64 rows per chunk = 256 contiguous bytes of every parameter row: with 32 rows (128 B pieces 4 B * ld apart, every one in
-// another DRAM page) the kernel ran at 1.8 TB/s, long_scoreboard 11 per issue (ncu, profiles/), against 4.3 TB/s for
-// bw_dh's 512-byte pieces.
+// CTA = (parameter tile of 128, row range); 3 stages of (A: 128 p x 64 rows of G, 32 KB; B: two h tiles of 144 x 32, 36 KB).
+// The A operand is loaded by TMA (cp.async.bulk.tensor.2d, two boxes of 32 rows x 128 parameters per chunk) straight into
+// the 128-byte-swizzled K-major layout that tcgen05.mma reads: one elected thread issues the copies, there are no producer
+// warps and no per-thread cp.async (the 16-byte cp.async version kept the l1tex pipe 59 % busy at 28 % of the DRAM rate,
+// long_scoreboard 11.7 per issue -- ncu, profiles/ncu_r02_train.md); rows >= B and parameters >= P are zero-filled by the
+// tensor map.  64 rows per chunk = 256 contiguous bytes of every parameter row.
 constexpr int kW2Stages = 3;
 constexpr int kW2KC = 64;                                    // rows per chunk (8 MMAs of K = 8)
-constexpr int kW2TileA = 128 * kW2KC * 4, kW2TileB = kBwNExt * kBwKC * 4;     // B stage = 2 h tiles
-constexpr int kW2Smem = kW2Stages * (kW2TileA + 2 * kW2TileB) + 256;
+constexpr int kW2BoxA = 128 * 32 * 4;                        // one TMA box: 128 parameters x 32 rows (128 bytes per row: the swizzle atom)
+constexpr int kW2TileA = 2 * kW2BoxA, kW2TileB = kBwNExt * kBwKC * 4;     // B stage = 2 h tiles
+constexpr int kW2Smem = kW2Stages * (kW2TileA + 2 * kW2TileB) + 256 + 1024;   // (+ alignment of the swizzled stages to 1024 bytes)
 
-__global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+// K-major operand in the 128-byte swizzle: rows of 128 bytes (32 fp32 of K), 8-row groups 1024 bytes apart
+JF_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+JF_DEVINL void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a, const __grid_constant__ CUtensorMap tmapG) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t sraw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t sbase = (sraw + 1023u) & ~1023u;                                    // swizzle atoms are 1024-byte aligned
+    unsigned char* smem = smem_raw + (sbase - sraw);
     const uint32_t offB = kW2Stages * kW2TileA, offBar = offB + kW2Stages * 2 * kW2TileB;
     const uint32_t bar0 = sbase + offBar;
     auto bar_full = [&](int s) { return bar0 + 8 * s; };
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
     const int n_chunks = c_end > c_begin ? (int)(c_end - c_begin) : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < kW2Stages; ++s) { mbar_init(bar_full(s), 9); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < kW2Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -301,59 +317,32 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (n_chunks > 0) {
-        if (warp < 8) {
-            // ---- producers: cp.async 16-byte units (4 rows of one parameter) straight into the K-major A stage ----
-            // unit idx = tid + 256 j (2048 per chunk): w = idx >> 5, l = idx & 31 -> parameter (w >> 2) 8 + (l & 7), k-quad
-            // (w & 3) 4 + (l >> 3): a warp reads 64 contiguous bytes of 8 parameter rows, writes 512 contiguous bytes
-            auto issue = [&](int c) {
-                const int s = c % kW2Stages;
-                const int64_t rbase = (c_begin + c) * kW2KC;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int idx = tid + 256 * j;
-                    const int w = idx >> 5, l = idx & 31;
-                    const int pl = (w >> 2) * 8 + (l & 7), kq = (w & 3) * 4 + (l >> 3);
-                    const int p = p0 + pl;
-                    const int64_t row = rbase + 4 * kq;
-                    int bytes = 0;
-                    if (p < a.P && row < a.B) { const int64_t left = a.B - row; bytes = left >= 4 ? 16 : (int)left * 4; }
-                    const float* src = a.G + (size_t)(p < a.P ? p : 0) * a.ldg + (row < a.B ? row : 0);
-                    cp_async16(sbase + s * kW2TileA + bw_tile_off(128, pl, 4 * kq), src, bytes);
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (tid == 0) {                                     // the two 32-row h tiles of this chunk (contiguous)
-                    mbar_expect_tx(bar_full(s), 2 * kW2TileB);
+        if (warp == 0) {
+            // ---- producer: one thread, TMA for G and a bulk copy for the two h tiles of every chunk ----
+            if (elect_one()) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int s = c % kW2Stages;
+                    if (c >= kW2Stages) mbar_wait(bar_empty(s), (uint32_t)(((c / kW2Stages) - 1) & 1));
+                    const int64_t row0 = (c_begin + c) * kW2KC;
+                    mbar_expect_tx(bar_full(s), kW2TileA + 2 * kW2TileB);
+                    tma_load_2d(sbase + s * kW2TileA, &tmapG, (int)row0, p0, bar_full(s));
+                    tma_load_2d(sbase + s * kW2TileA + kW2BoxA, &tmapG, (int)row0 + 32, p0, bar_full(s));
                     bulk_g2s(sbase + offB + s * 2 * kW2TileB, a.h_tiles + (size_t)(c_begin + c) * (2 * kW2TileB / 4), 2 * kW2TileB,
                              bar_full(s));
                 }
-            };
-            for (int c = 0; c < kW2Stages - 1; ++c) {
-                if (c < n_chunks) issue(c); else asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            for (int c = 0; c < n_chunks; ++c) {
-                const int cn = c + kW2Stages - 1;
-                if (cn < n_chunks) {
-                    if (cn >= kW2Stages) mbar_wait(bar_empty(cn % kW2Stages), (uint32_t)(((cn / kW2Stages) - 1) & 1));
-                    issue(cn);
-                } else {
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                }
-                asm volatile("cp.async.wait_group %0;" ::"n"(kW2Stages - 1) : "memory");   // chunk c has landed
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full(c % kW2Stages));
-            }
-        } else {
+        } else if (warp == 8) {
             if (elect_one()) {
                 constexpr uint32_t idesc = bw_idesc(128, kBwNExt);
-                constexpr uint32_t lboA = (128 / 8) * 128, lboB = (kBwNExt / 8) * 128;
+                constexpr uint32_t lboB = (kBwNExt / 8) * 128;
                 for (int c = 0; c < n_chunks; ++c) {
                     const int s = c % kW2Stages;
                     mbar_wait(bar_full(s), (uint32_t)((c / kW2Stages) & 1));
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < kW2KC / 8; ++ks) {
-                        const uint64_t ad = umma_desc(sbase + s * kW2TileA + ks * 2 * lboA, lboA, 128);
+                        // A: box (ks >> 2), 32 bytes (8 fp32 of K) further inside the swizzle atom per step
+                        const uint64_t ad = umma_desc_sw128(sbase + s * kW2TileA + (ks >> 2) * kW2BoxA + (ks & 3) * 32);
                         const uint64_t bd = umma_desc(sbase + offB + s * 2 * kW2TileB + (ks >> 2) * kW2TileB + (ks & 3) * 2 * lboB, lboB, 128);
                         tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     }
@@ -364,6 +353,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a) {
         }
         // ---- epilogue: warps 0-3, thread = parameter row: partial sums -> red.global ----
         if (warp < 4) {
+            __syncwarp();
             mbar_wait(bar_done, 0);
             tc_fence_after();
             const int p = p0 + warp * 32 + lane;

@@ -1,6 +1,8 @@
 // launcher of the tensor-core backward of the parameter generator (csrc/mlp_bwd.cuh); its own translation unit so that
 // the library builds in parallel
+#include <cudaTypedefs.h>
 #include "mlp_bwd.cuh"
+#include "../../include/jammy_b200.h"
 
 namespace jf {
 
@@ -45,7 +47,28 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
         a.n_splits = (int)splits;
         e = cudaFuncSetAttribute(bw_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem);
         if (e != cudaSuccess) return (int)e;
-        bw_dw2_kernel<<<dim3((unsigned)n_pt, (unsigned)splits), kBwThreads, kW2Smem, st>>>(a);
+        // tensor map of G [P rows][B columns] fp32, boxes of 32 columns x 128 rows in the 128-byte swizzle, zero fill outside
+        CUtensorMap tmapG;
+        {
+            static PFN_cuTensorMapEncodeTiled encode = [] {
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                    q != cudaDriverEntryPointSuccess)
+                    fn = nullptr;
+                return (PFN_cuTensorMapEncodeTiled)fn;
+            }();
+            if (encode == nullptr) return JF_ERR_UNSUPPORTED;
+            const cuuint64_t gdim[2] = {(cuuint64_t)a.B, (cuuint64_t)a.P};
+            const cuuint64_t gstride[1] = {(cuuint64_t)a.ldg * 4};
+            const cuuint32_t box[2] = {32, 128};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = encode(&tmapG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.G, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return JF_ERR_BAD_ARG;
+        }
+        bw_dw2_kernel<<<dim3((unsigned)n_pt, (unsigned)splits), kBwThreads, kW2Smem, st>>>(a, tmapG);
     }
     {
         const int ldxs = a.in | 1;
