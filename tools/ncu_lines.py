@@ -33,10 +33,16 @@ for l in dis[start:]:
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+.*;", l):
-        ins.append(cur)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", l)
+    if m:
+        ins.append((cur, m.group(1).strip()))
 ins = ins[:len(data)]
 assert len(ins) == len(data), (len(ins), len(data))
+opc = lambda t: [w for w in t.replace("{", " ").split() if not w.startswith("@")][0].split(".")[0]
+bad = sum(1 for (_, a), (_, _, b) in zip(ins, data) if opc(a) != opc(b))
+if bad:
+    print("WARNING: %d of %d instructions do not match the object (another build?): the attribution below is unreliable" % (bad, len(data)))
+ins = [c for c, _ in ins]
 by, bs = collections.Counter(), collections.Counter()
 for line, (n, s, _) in zip(ins, data):
     by[line] += n
