@@ -410,7 +410,10 @@ static int subpdf_fb_t(const JfSubPdfDesc* desc, const void* x, int64_t ld_x, co
             continue;
         }
         if (L.kind != JF_LAYER_GF || L.dim != d) return JF_ERR_UNSUPPORTED;
-        if (!gf_layer_is_default(L)) return JF_ERR_UNSUPPORTED;   // the closed-form backward covers the default options
+        // the closed-form backward covers the default options and rotation_mode "none" (no reflections at all)
+        JfLayerDesc Lr = L;
+        if (Lr.rotation_mode == JF_ROT_NONE && Lr.hh_iter == 0) Lr.rotation_mode = JF_ROT_HOUSEHOLDER;
+        if (!gf_layer_is_default(Lr)) return JF_ERR_UNSUPPORTED;
         if (L.K < 1 || L.K > JF_MAX_KDE || L.hh_iter < 0 || L.hh_iter > 4 * JF_MAX_DIM) return JF_ERR_UNSUPPORTED;
         if (L.inv_type == JF_INV_FULL_PADE || L.inv_type == JF_INV_PARTLY_CRUDE) return JF_ERR_UNSUPPORTED;
         const int expect = (L.has_offset ? d : 0) + L.hh_iter * d + (L.norm_mode != JF_NORM_NONE ? 3 : 2) * L.K * d;

@@ -847,9 +847,15 @@ def supports_backward(pdf):
                 continue
             if getattr(l, "code", "") != "g" or l.inverse_function_type not in ("isigmoid", "inormal_partly_precise"):
                 return False
-            if not l.is_default_kernel_config:
+            if not (l.is_default_kernel_config or _default_without_rotation(l)):
                 return False
     return True
+
+
+def _default_without_rotation(l):
+    """default "g" options except rotation_mode="none": the chain kernel's reverse pass simply has no reflections to undo"""
+    return (l.nonlinear_stretch_type == "classic" and l.rotation_mode == "none" and not l.add_skewness
+            and not l.center_mean and l.width_mode == "smooth" and l.width_clamp is None)
 
 
 def _embedding_torch(pdf, k, x_k):

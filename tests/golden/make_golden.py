@@ -247,6 +247,11 @@ CASES = {
                                   opts={"t": {"cov_type": "diagonal"}}),
     "train_e2_gt_symmetric": dict(pdf_defs="e2", flow_defs="gt", n=150, cond_dim=2, perturb=0.2, grads=True,
                                   opts={"t": {"cov_type": "diagonal_symmetric"}}),
+    "train_e3_gg_variants_cond": dict(pdf_defs="e3+e2", flow_defs="gg+gg", n=150, cond_dim=2, perturb=0.2, grads=True,
+                                      opts={"g": {"rotation_mode": "none", "fit_normalization": 0, "num_kde": 6,
+                                                  "inverse_function_type": "isigmoid"}}),
+    "train_e2_gg_rawnorm": dict(pdf_defs="e2", flow_defs="gg", n=150, perturb=0.2, grads=True,
+                                opts={"g": {"regulate_normalization": 0}}),
     # non-Euclidean sub-pdfs in the training path (README-style mixed flow, every manifold layer kind)
     "train_e2s2e2_f": dict(pdf_defs="e2+s2+e2", flow_defs="gg+f+gg", n=120, perturb=0.1, grads=True),
     "train_s2_f_splines_cond": dict(pdf_defs="s2", flow_defs="f", n=120, cond_dim=2, perturb=0.1, grads=True,
