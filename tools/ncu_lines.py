@@ -2,7 +2,7 @@
 instruction) with `nvdisasm -g` line markers of the object the kernel was built from (both list the instructions of the
 kernel and of its out-of-line callees in the same order).
 
-    python tools/ncu_lines.py <report.ncu-rep> <object.o> <mangled-name substring> [top N] [warps for the per-warp column]
+    python tools/ncu_lines.py <report.ncu-rep> <object.o> <mangled-name substring> [top N] [warps for the per-warp column] [launch index]
 """
 import collections, csv, os, re, subprocess, sys, tempfile
 rep, obj, name = sys.argv[1], sys.argv[2], sys.argv[3]
@@ -11,7 +11,8 @@ nw = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
-rows = rows[starts[0]:starts[1]]
+sec = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+rows = rows[starts[sec]:starts[sec + 1]]
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 data = [(int(r[ix["Instructions Executed"]] or 0), int(r[ix["# Samples"]] or 0), r[ix["Source"]].strip())
