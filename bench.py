@@ -218,6 +218,22 @@ def cpu_arm(steps, warmup, n_lp=20000, n_s=4000):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
+    if args.config == "train":
+        # the reference's own forward + backward + Adam on the host cores, on a bounded batch of the same workload
+        cb = train_cpu_arm(max(args.steps, 1))
+        if cb.get("value") is None:
+            emit(dict(impl="reference", unavailable=cb.get("sample", "reference not staged")))
+            return
+        n_ref = 4096
+        line = dict(impl="reference", metric=TRAIN_METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                    warmup=1, ms_per_step=1e3 * n_ref / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload="BASELINE configs[4]: training step on conditional e10 'gggggggg' (cond dim 64); CPU arm: "
+                                         "the unmodified reference on a bounded batch", rows_per_step=n_ref),
+                    cpu_baseline=dict(kind=cb["kind"], cores=cb["cores"], sample=cb["sample"], value=cb["value"], unit=UNIT),
+                    e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        emit(line)
+        return
     cb = cpu_arm(args.steps, min(args.warmup, 1))
     ms = 1e3 * (1.0 / cb["logpdf_evals_per_s"] * 20000 + 1.0 / cb["samples_per_s"] * 4000)
     line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
