@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(128) mlp_i8_prep_kernel(const T* __restrict__ 
         int e = 0;
         if (mx > 0.0) { frexp(mx, &e); }                 // mx = f * 2^e, f in [0.5,1)  =>  |W/2^e| < 1
         s_inv[jj] = ldexp(1.0, -e);
-        scl[tile * TN + jj] = (j < N) ? ldexp(1.0, e - 12) : 0.0;
+        // fp32 callers read the (exact, power-of-two) scale as a float from the low half of the 8-byte cell: no per-element
+        // double -> float conversion in the epilogue
+        if (sizeof(T) == 8) scl[tile * TN + jj] = (j < N) ? ldexp(1.0, e - 12) : 0.0;
+        else { float* sf = reinterpret_cast<float*>(scl + tile * TN + jj); sf[0] = (j < N) ? ldexpf(1.0f, e - 12) : 0.0f; sf[1] = 0.0f; }
     }
     __syncthreads();
     unsigned char* base = ws + (size_t)tile * NS * TN * kI8H;
@@ -488,13 +491,19 @@ __global__ void __launch_bounds__(kI8Threads, 1) mlp2_i8_kernel(const __grid_con
                 for (int i = 0; i < kMine; ++i) {
                     const int c = grp + i * kGroups;
                     if (c < kChunks && !(dbg & 4)) {
+                        // one 64-bit address per chunk of 8 columns, then a walking pointer: the first version computed
+                        // n * so_p + row * so_r per element -- 36 % of the kernel's executed instructions (ncu source page)
+                        const int nb = n0 + c * 8;
+                        T* op = m.out + (int64_t)nb * m.so_p + row * m.so_r;
+                        const int nvalid = (row < m.B) ? (N - nb) : 0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const int n = n0 + c * 8 + j;
                             T o;
                             if (sizeof(T) == 8) o = (T)fma((double)acc_d[i][j], sc[c * 8 + j], sc[TN + c * 8 + j]);
-                            else o = (T)fmaf((float)acc_d[i][j], (float)sc[c * 8 + j], reinterpret_cast<const float*>(sc + TN + c * 8 + j)[0]);
-                            if (n < N && row < m.B) m.out[(int64_t)n * m.so_p + row * m.so_r] = o;
+                            else o = (T)fmaf((float)acc_d[i][j], reinterpret_cast<const float*>(sc + c * 8 + j)[0],
+                                             reinterpret_cast<const float*>(sc + TN + c * 8 + j)[0]);
+                            if (j < nvalid) *op = o;
+                            op += m.so_p;
                         }
                     }
                 }
