@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libjammy_b200.so")
-SOURCES = ["api.cu", "gf_inst_f64_logpdf.cu", "gf_inst_f64_sample.cu", "gf_inst_f32_logpdf.cu", "gf_inst_f32_sample.cu", "gfx_inst.cu", "gf_fused_inst.cu", "mlp_bwd_inst.cu", "gf_fb_inst.cu", "gf_sbwd_inst.cu"]
+SOURCES = ["api.cu", "gf_inst_f64_logpdf.cu", "gf_inst_f64_sample.cu", "gf_inst_f32_logpdf.cu", "gf_inst_f32_sample.cu", "gfx_inst.cu", "gf_fused_inst.cu", "mlp_bwd_inst.cu", "gf_fb_inst.cu", "gf_sbwd_inst.cu", "gf_fwd_inst.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

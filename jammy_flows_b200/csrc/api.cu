@@ -177,6 +177,24 @@ static int apply_gf(const JfSubPdfDesc* desc, int direction, GfChainArgs<T>& g, 
         kmax = L.K > kmax ? L.K : kmax;
     }
     g.a.tab_total = tab;
+    // per-row parameters, log_pdf direction: the (row, dimension)-worker kernel of csrc/gf_fb.cuh in its forward-only mode
+    // (coalesced param-major loads, register-resident unrolled mixture).  JF_ROWDIM_FWD=0 keeps the thread-per-row kernel.
+    static const bool rowdim = [] { const char* e = getenv("JF_ROWDIM_FWD"); return e == nullptr || atoi(e) != 0; }();
+    if (rowdim && direction == JF_DIR_LOGPDF && g.a.sr != 0) {
+        GfFbArgs<T> f;
+        memset(&f, 0, sizeof(f));
+        f.a = g.a;
+        int hh_max = 0;
+        for (int l = 0; l < desc->n_layers; ++l) {
+            f.layers[l] = g.layers[l];
+            hh_max = g.layers[l].hh_iter > hh_max ? g.layers[l].hh_iter : hh_max;
+        }
+        f.kmax = kmax;
+        f.hh_max = hh_max;
+        const int rc = launch_gf_fwd<T>(f, st);
+        if (rc == JF_OK) return check_launch();
+        if (rc != JF_ERR_UNSUPPORTED) return rc;          // (too much shared memory for this shape: the thread-per-row kernel)
+    }
     const size_t smem = (g.a.sr == 0) ? (size_t)tab * sizeof(T) : 0;
     if (smem > 200 * 1024) return JF_ERR_UNSUPPORTED;
     const int rc = (direction == JF_DIR_LOGPDF) ? launch_gf_dir<T, JF_DIR_LOGPDF>(g, d, kmax, smem, st)

@@ -390,7 +390,8 @@ __device__ __noinline__ void fb_mvn_forward(const GfLayerC<T>& c, const T* prow,
 
 JF_DEVINL void fb_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// MODE 0: log_pdf forward + backward.  MODE 1: backward of the SAMPLING direction at the sample x = T(z; theta) (a.in): the
+// MODE 2: log_pdf forward only (what jf_subpdf_apply runs for per-row parameters: same workers, same register-resident
+// mixture, no reverse pass).  MODE 0: log_pdf forward + backward.  MODE 1: backward of the SAMPLING direction at the sample x = T(z; theta) (a.in): the
 // layers' inputs are recovered by running the closed-form log_pdf direction from x (no root finder), then the chain is
 // walked from the x side to the z side with the implicit-function form of every element (fb_bwd_elem<SDIR>): cotangents
 // grad_out_x of x and grad_logp of log_pdf(x) in, parameter gradients and (optionally, grad_x) the cotangent of z out.
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
     const int64_t sj = a.sj;
 
     T xj = a.in[row * a.ld_in + j];
+    if (MODE == 2 && a.emb_out != nullptr && live) a.emb_out[row * a.ld_emb + j] = xj;      // Euclidean: the target itself
     T ld_acc = 0;
     T vsave[JF_MAX_LAYERS];                            // pre-stage value of this dimension in every layer
     // ---- forward ----
@@ -484,23 +486,26 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
             ld_acc += logd;
         }
     }
-    if (MODE == 0) {
-    // ---- forward outputs: base point, logdet, log N(z) ----
-    if (live && a.out != nullptr) a.out[row * a.ld_out + j] = xj;
-    if (a.logdet_out != nullptr || a.logbase_out != nullptr) {
-        ex[(fX + j) * 32] = ld_acc;
-        ex[(fXB + j) * 32] = xj * xj;
-        fb_bar(bar_id, 32 * D);
-        if (j == 0 && live) {
-            T ld = 0, zsq = 0;
+    if (MODE == 0 || MODE == 2) {
+        // ---- forward outputs: base point, logdet, log N(z) ----
+        if (live && a.out != nullptr) a.out[row * a.ld_out + j] = xj;
+        if (MODE == 2 || a.logdet_out != nullptr || a.logbase_out != nullptr) {
+            ex[(fX + j) * 32] = ld_acc;
+            ex[(fXB + j) * 32] = xj * xj;
+            fb_bar(bar_id, 32 * D);
+            if (j == 0 && live) {
+                T ld = a.logdet_in != nullptr ? a.logdet_in[row] : T(0), zsq = 0;
 #pragma unroll
-            for (int jj = 0; jj < D; ++jj) { ld += ex[(fX + jj) * 32]; zsq += ex[(fXB + jj) * 32]; }
-            if (!finite_(ld)) status_add(a.status, JF_STATUS_NONFINITE, 1);
-            if (a.logdet_out != nullptr) a.logdet_out[row] = ld;
-            if (a.logbase_out != nullptr) a.logbase_out[row] = -T(0.5) * zsq - T(D) * T(kLogSqrt2Pi);
+                for (int jj = 0; jj < D; ++jj) { ld += ex[(fX + jj) * 32]; zsq += ex[(fXB + jj) * 32]; }
+                // (a non-finite base coordinate makes zsq non-finite: one count per row)
+                if (!finite_(ld) || (MODE == 2 && !finite_(zsq))) status_add(a.status, JF_STATUS_NONFINITE, 1);
+                if (a.logdet_out != nullptr) a.logdet_out[row] = ld;
+                if (a.logbase_out != nullptr)
+                    a.logbase_out[row] = (a.logbase_in != nullptr ? a.logbase_in[row] : T(0)) - T(0.5) * zsq - T(D) * T(kLogSqrt2Pi);
+            }
+            fb_bar(bar_id, 32 * D);
         }
-        fb_bar(bar_id, 32 * D);
-    }
+        if (MODE == 2) return;                         // forward only: the (row, dimension) log_pdf kernel of jf_subpdf_apply
     }
     if (MODE == 1) {
         // ---- backward of the sampling direction: x side first ----

@@ -24,8 +24,10 @@ static int launch_fb_d(const GfFbArgs<T>& g, cudaStream_t st) {
 
 #if JF_FB_MODE == 0
 #define JF_FB_LAUNCH launch_gf_fb
-#else
+#elif JF_FB_MODE == 1
 #define JF_FB_LAUNCH launch_gf_sbwd
+#else
+#define JF_FB_LAUNCH launch_gf_fwd
 #endif
 template <typename T>
 int JF_FB_LAUNCH(const GfFbArgs<T>& g, cudaStream_t st) {

@@ -30,5 +30,6 @@ __host__ __device__ constexpr size_t fb_smem_bytes(int D, int kmax, int hh_max) 
 // return a JF_ERR_* / cudaError code
 template <typename T> int launch_gf_fb(const GfFbArgs<T>& g, cudaStream_t st);
 template <typename T> int launch_gf_sbwd(const GfFbArgs<T>& g, cudaStream_t st);
+template <typename T> int launch_gf_fwd(const GfFbArgs<T>& g, cudaStream_t st);      // <T, d, 2>: log_pdf forward only
 
 }  // namespace jf
