@@ -126,27 +126,46 @@ __global__ void __launch_bounds__(256) bw_h_tiles_kernel(const BwArgs a, int64_t
 }
 
 // ---- dh = G^T W2, dpre = dh (1 - h^2) ---------------------------------------------------------------------------------------
-// shared memory: raw G chunks [3][32 p][128 rows] | A stages [2][128 rows x 32 k] | B stages [2][128 n x 32 k] | barriers
-constexpr int kDhRaw = 3, kDhStages = 2;
-constexpr int kDhTile = kBwH * kBwKC * 4;                   // 16 KB
-constexpr int kDhSmem = (kDhRaw + 2 * kDhStages) * kDhTile + 256;
+// A = G^T: M = 128 rows, K = parameters.  G is param-major (rows contiguous), i.e. the A operand is MN-MAJOR: TMA boxes of
+// 32 rows x 32 parameters in the 128-byte swizzle with 32-byte atoms ARE the canonical MN-major tf32 UMMA layout (32 fp32 of M
+// per 128-byte line, one line per K index, 4-line groups 512 bytes apart = SBO, the four row boxes of a chunk 4096 bytes
+// apart = LBO), so the
+// gradient block goes from HBM to the tensor core without passing through registers (the first version transposed every
+// chunk through shared memory with 8 producer warps).  3 stages of (A 16 KB, W2 tile 16 KB); 2 CTAs per SM.
+constexpr int kDhStages = 3;
+constexpr int kDhTile = kBwH * kBwKC * 4;                   // 16 KB: A chunk (4 boxes of 4 KB) and W2 tile alike
+constexpr int kDhBox = 32 * 32 * 4;
+constexpr int kDhSmem = 2 * kDhStages * kDhTile + 256 + 1024;
 
-__global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+// MN-major tf32 operands have exactly one shared-memory layout: the 128-byte swizzle with a 32-byte base (layout type 1,
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32 fp32 of M per 128-byte line, one line per K index, the 32-byte pieces of a
+// line permuted by (line & 3); lbo = distance between 32-element chunks of M, sbo = between groups of 4 lines (4 K)
+JF_DEVINL uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)1 << 61);
+}
+JF_DEVINL void tma_load_2d_(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a, const __grid_constant__ CUtensorMap tmapG) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t offA = kDhRaw * kDhTile, offB = offA + kDhStages * kDhTile, offBar = offB + kDhStages * kDhTile;
+    const uint32_t sraw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t sbase = (sraw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (sbase - sraw);
+    const uint32_t offB = kDhStages * kDhTile, offBar = 2 * kDhStages * kDhTile;
     const uint32_t bar0 = sbase + offBar;
-    auto bar_fullA = [&](int s) { return bar0 + 8 * s; };
-    auto bar_fullB = [&](int s) { return bar0 + 8 * (2 + s); };
+    auto bar_full = [&](int s) { return bar0 + 8 * s; };
     auto bar_empty = [&](int s) { return bar0 + 8 * (4 + s); };
-    const uint32_t bar_done = bar0 + 8 * 6;
+    const uint32_t bar_done = bar0 + 8 * 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + offBar + 128);
     const int64_t row0 = (int64_t)blockIdx.x * 128;
     const int n_chunks = (a.P + kBwKC - 1) / kBwKC;
 
     if (tid == 0) {
-        for (int s = 0; s < kDhStages; ++s) { mbar_init(bar_fullA(s), 8); mbar_init(bar_fullB(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < kDhStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -159,70 +178,32 @@ __global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
-        // ---- producers ----
-        // raw chunk c: 32 parameters x 128 rows; 16-byte unit u = tid + 256 j: parameter u >> 5, rows 4 (u & 31) ..
-        auto prefetch = [&](int c) {
-            const uint32_t dst0 = sbase + (c % kDhRaw) * kDhTile;
+    if (warp == 0) {
+        // ---- producer: one thread; per chunk of 32 parameters four TMA boxes (32 rows each) of G and the W2 tile ----
+        if (elect_one()) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % kDhStages;
+                if (c >= kDhStages) mbar_wait(bar_empty(s), (uint32_t)(((c / kDhStages) - 1) & 1));
+                mbar_expect_tx(bar_full(s), 2 * kDhTile);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int u = tid + 256 * j;
-                const int k = u >> 5, rq = u & 31;
-                const int p = c * kBwKC + k;
-                const int64_t row = row0 + 4 * rq;
-                int bytes = 0;
-                if (p < a.P && row < a.B) { const int64_t left = a.B - row; bytes = left >= 4 ? 16 : (int)left * 4; }
-                const float* src = a.G + (size_t)(p < a.P ? p : 0) * a.ldg + (row < a.B ? row : 0);
-                cp_async16(dst0 + (k * 128 + 4 * rq) * 4, src, bytes);
+                for (int b = 0; b < 4; ++b)
+                    tma_load_2d_(sbase + s * kDhTile + b * kDhBox, &tmapG, (int)row0 + 32 * b, c * kBwKC, bar_full(s));
+                bulk_g2s(sbase + offB + s * kDhTile, a.w2_tiles + (size_t)c * (kDhTile / 4), kDhTile, bar_full(s));
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        prefetch(0);
-        if (n_chunks > 1) prefetch(1); else asm volatile("cp.async.commit_group;" ::: "memory");
-        for (int c = 0; c < n_chunks; ++c) {
-            const int s = c & 1;
-            asm volatile("cp.async.wait_group 1;" ::: "memory");               // chunk c has landed (this thread's pieces)
-            bar_sync_named(1, kBwProducers);                                   // ... everybody's
-            if (c >= kDhStages) mbar_wait(bar_empty(s), (uint32_t)(((c >> 1) - 1) & 1));   // the MMAs of chunk c-2 have read the stage
-            // transpose raw [k][row] -> A stage [row][k] (K-major core matrices), rounded to tf32:
-            // thread -> (row = tid & 127, two k-quads): 4 conflict-free LDS.32, one STS.128
-            {
-                const float* raw = reinterpret_cast<const float*>(smem + (c % kDhRaw) * kDhTile);
-                const int r = tid & 127;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int kq = (tid >> 7) + 2 * j;
-                    const float v0 = to_tf32(raw[(4 * kq + 0) * 128 + r]), v1 = to_tf32(raw[(4 * kq + 1) * 128 + r]);
-                    const float v2 = to_tf32(raw[(4 * kq + 2) * 128 + r]), v3 = to_tf32(raw[(4 * kq + 3) * 128 + r]);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + offA + s * kDhTile + bw_tile_off(128, r, 4 * kq)),
-                                 "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
-                }
-            }
-            if (tid == 0) {                                                    // W2 tile c -> B stage
-                mbar_expect_tx(bar_fullB(s), kDhTile);
-                bulk_g2s(sbase + offB + s * kDhTile, a.w2_tiles + (size_t)c * (kDhTile / 4), kDhTile, bar_fullB(s));
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_fullA(s));
-            bar_sync_named(1, kBwProducers);                                   // the raw buffer of chunk c is free
-            if (c + 2 < n_chunks) prefetch(c + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
         }
-    } else {
+    } else if (warp == 8) {
         // ---- MMA issuer ----
         if (elect_one()) {
-            constexpr uint32_t idesc = bw_idesc(128, 128);
-            constexpr uint32_t lbo = (128 / 8) * 128;
+            constexpr uint32_t idesc = bw_idesc(128, 128) | (1u << 15);              // A is MN-major
+            constexpr uint32_t lboB = (128 / 8) * 128;
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c & 1;
-                const uint32_t par = (uint32_t)((c >> 1) & 1);
-                mbar_wait(bar_fullA(s), par);
-                mbar_wait(bar_fullB(s), par);
+                const int s = c % kDhStages;
+                mbar_wait(bar_full(s), (uint32_t)((c / kDhStages) & 1));
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = umma_desc(sbase + offA + s * kDhTile + ks * 2 * lbo, lbo, 128);
-                    const uint64_t bd = umma_desc(sbase + offB + s * kDhTile + ks * 2 * lbo, lbo, 128);
+                    const uint64_t ad = umma_desc_mn_sw128(sbase + s * kDhTile + ks * 1024, kDhBox, 512);
+                    const uint64_t bd = umma_desc(sbase + offB + s * kDhTile + ks * 2 * lboB, lboB, 128);
                     tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                 }
                 tc_commit(bar_empty(s));
@@ -232,6 +213,7 @@ __global__ void __launch_bounds__(kBwThreads, 2) bw_dh_kernel(const BwArgs a) {
     }
     // ---- epilogue: warps 0-3, thread = row ----
     if (warp < 4) {
+        __syncwarp();
         mbar_wait(bar_done, 0);
         tc_fence_after();
         const int r = warp * 32 + lane;

@@ -34,9 +34,35 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
         const int64_t grid = n_rtiles32 < 4 * (int64_t)sms ? n_rtiles32 : 4 * (int64_t)sms;       // persistent over the tiles
         bw_h_tiles_kernel<<<(unsigned)grid, 256, smem, st>>>(a, n_rtiles32);
     }
+    // tensor maps of G [P rows][B columns] fp32 in the 128-byte swizzle, zero fill outside: boxes of 32 columns x 32 rows
+    // (bw_dh: MN-major A operand) and 32 columns x 128 rows (bw_dw2: K-major A operand)
+    CUtensorMap tmapG32, tmapG128;
+    {
+        static PFN_cuTensorMapEncodeTiled encode = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess)
+                fn = nullptr;
+            return (PFN_cuTensorMapEncodeTiled)fn;
+        }();
+        if (encode == nullptr) return JF_ERR_UNSUPPORTED;
+        const cuuint64_t gdim[2] = {(cuuint64_t)a.B, (cuuint64_t)a.P};
+        const cuuint64_t gstride[1] = {(cuuint64_t)a.ldg * 4};
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint32_t box32[2] = {32, 32}, box128[2] = {32, 128};
+        CUresult r = encode(&tmapG32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.G, gdim, gstride, box32, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return JF_ERR_BAD_ARG;
+        r = encode(&tmapG128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.G, gdim, gstride, box128, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return JF_ERR_BAD_ARG;
+    }
     e = cudaFuncSetAttribute(bw_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDhSmem);
     if (e != cudaSuccess) return (int)e;
-    bw_dh_kernel<<<(unsigned)((a.B + 127) / 128), kBwThreads, kDhSmem, st>>>(a);
+    bw_dh_kernel<<<(unsigned)((a.B + 127) / 128), kBwThreads, kDhSmem, st>>>(a, tmapG32);
     {
         // parameter tiles x row ranges: three waves of CTAs, at least 8 chunks of rows each
         const int n_pt = (a.P + 127) / 128;
@@ -47,28 +73,7 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
         a.n_splits = (int)splits;
         e = cudaFuncSetAttribute(bw_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem);
         if (e != cudaSuccess) return (int)e;
-        // tensor map of G [P rows][B columns] fp32, boxes of 32 columns x 128 rows in the 128-byte swizzle, zero fill outside
-        CUtensorMap tmapG;
-        {
-            static PFN_cuTensorMapEncodeTiled encode = [] {
-                void* fn = nullptr;
-                cudaDriverEntryPointQueryResult q;
-                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-                    q != cudaDriverEntryPointSuccess)
-                    fn = nullptr;
-                return (PFN_cuTensorMapEncodeTiled)fn;
-            }();
-            if (encode == nullptr) return JF_ERR_UNSUPPORTED;
-            const cuuint64_t gdim[2] = {(cuuint64_t)a.B, (cuuint64_t)a.P};
-            const cuuint64_t gstride[1] = {(cuuint64_t)a.ldg * 4};
-            const cuuint32_t box[2] = {32, 128};
-            const cuuint32_t estr[2] = {1, 1};
-            const CUresult r = encode(&tmapG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.G, gdim, gstride, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return JF_ERR_BAD_ARG;
-        }
-        bw_dw2_kernel<<<dim3((unsigned)n_pt, (unsigned)splits), kBwThreads, kW2Smem, st>>>(a, tmapG);
+        bw_dw2_kernel<<<dim3((unsigned)n_pt, (unsigned)splits), kBwThreads, kW2Smem, st>>>(a, tmapG128);
     }
     {
         const int ldxs = a.in | 1;
