@@ -46,6 +46,9 @@ JF_DEVINL void fb_prefetch_layer(const GfLayerC<T>& c, int D, int j, const T* pr
 // 64-bit slot indices): ncu counted 8 600 instructions per (row, layer, dimension) forward + backward, 760 per mixture
 // kernel, against ~200 of arithmetic.  Same formulas as mix_eval / gf_elem_backward (which stay the path for other K).
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef JF_FB_ROT1
+#define JF_FB_ROT1 1      // 1: one worker of the row applies the reflections (0: every worker redundantly, +8 % time)
+#endif
 constexpr int kFbFastK = 10;   // the default num_kde of the reference (flow_options.py): register-resident path
 
 template <typename T, int K>
@@ -453,6 +456,34 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
                 for (int i = 0; i < c.hh_iter; ++i) { *eh = *ph; ph += (int64_t)D * sj; eh += D * 32; }
             }
             fb_bar(bar_id, 32 * D);
+#if JF_FB_ROT1
+            if (MODE != 1) {
+                // experiment: ONE worker of the row applies the reflections (no redundant work), the others wait
+                if (j == 0) {
+                    T X[D];
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) X[jj] = ex[(fX + jj) * 32];
+#pragma unroll 1
+                    for (int i = 0; i < c.hh_iter; ++i) {
+                        T w[D], dot = 0, nrm = 0;
+#pragma unroll
+                        for (int jj = 0; jj < D; ++jj) {
+                            w[jj] = ex[(fH + i * D + jj) * 32];
+                            dot = fma(w[jj], X[jj], dot);
+                            nrm = fma(w[jj], w[jj], nrm);
+                        }
+                        const T cc = T(2) * dot * rcp_pos_(nrm);
+#pragma unroll
+                        for (int jj = 0; jj < D; ++jj) X[jj] = fma(-cc, w[jj], X[jj]);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) ex[(fXB + jj) * 32] = X[jj];
+                }
+                fb_bar(bar_id, 32 * D);
+                xj = ex[(fXB + j) * 32];
+            } else
+#endif
+            {
             T X[D];
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) X[jj] = ex[(fX + jj) * 32];
@@ -472,6 +503,7 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) xj = (jj == j) ? X[jj] : xj;
             fb_bar(bar_id, 32 * D);            // everybody has read the exchange
+            }
         }
         vsave[l] = xj;
         if (live) {
@@ -684,6 +716,41 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
                 for (int i = 0; i < c.hh_iter; ++i) { *eh = *ph; ph += (int64_t)D * sj; eh += D * 32; }
             }
             fb_bar(bar_id, 32 * D);
+#if JF_FB_ROT1
+            if (j == 0) {
+                T V[D], XB[D];
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) { V[jj] = ex[(fX + jj) * 32]; XB[jj] = ex[(fXB + jj) * 32]; }
+                const int64_t hstep1 = (int64_t)D * sj;
+                T* gh1 = grow + (int64_t)c.raw_hh() * sj + (int64_t)(c.hh_iter - 1) * hstep1;
+#pragma unroll 1
+                for (int i = c.hh_iter - 1; i >= 0; --i) {
+                    T w[D], s_ = 0, aa = 0, bb = 0;
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) {
+                        w[jj] = ex[(fH + i * D + jj) * 32];
+                        s_ = fma(w[jj], w[jj], s_);
+                        aa = fma(w[jj], V[jj], aa);
+                        bb = fma(w[jj], XB[jj], bb);
+                    }
+                    const T is = rcp_pos_(s_);
+                    const T ain = -aa;
+                    const T ca = T(2) * aa * is, cb = T(2) * bb * is, c4 = T(4) * ain * bb * is * is, m2 = -T(2) * is;
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) {
+                        const T xin = fma(-ca, w[jj], V[jj]);
+                        if (live) gh1[(int64_t)jj * sj] = fma(m2, bb * xin + ain * XB[jj], c4 * w[jj]);
+                        XB[jj] = fma(-cb, w[jj], XB[jj]);
+                        V[jj] = xin;
+                    }
+                    gh1 -= hstep1;
+                }
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) ex[(fXB + jj) * 32] = XB[jj];
+            }
+            fb_bar(bar_id, 32 * D);
+            const T xb_own = ex[(fXB + j) * 32];
+#else
             T V[D], XB[D];
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) { V[jj] = ex[(fX + jj) * 32]; XB[jj] = ex[(fXB + jj) * 32]; }
@@ -712,8 +779,11 @@ __global__ void __launch_bounds__(fb_threads(D), fb_min_blocks(D, sizeof(T))) gf
 #pragma unroll
                 for (int jj = 0; jj < D; ++jj) { V[jj] = fma(-ca, w[jj], V[jj]); XB[jj] = fma(-cb, w[jj], XB[jj]); }
             }
+#endif
             xb = xb_own;
+#if !JF_FB_ROT1
             fb_bar(bar_id, 32 * D);
+#endif
         }
         if (c.has_offset && live) grow[(int64_t)(c.raw_off + j) * sj] = -xb;
     }

@@ -19,8 +19,11 @@ struct GfFbArgs {
 // row groups (of 32 rows) per block: about 256-320 threads
 __host__ __device__ constexpr int fb_groups(int D) { return D >= 8 ? 1 : (D >= 4 ? 2 : (D >= 2 ? 4 : 8)); }
 __host__ __device__ constexpr int fb_threads(int D) { return 32 * D * fb_groups(D); }
+#ifndef JF_FB_REGS32
+#define JF_FB_REGS32 96
+#endif
 // resident blocks per SM the register allocation aims at: 96 registers per thread in fp32, 128 in fp64 (the unrolled register-resident mixture)
-__host__ __device__ constexpr int fb_min_blocks(int D, size_t elem) { return (int)(65536 / ((elem == 4 ? 96 : 128) * fb_threads(D))); }
+__host__ __device__ constexpr int fb_min_blocks(int D, size_t elem) { return (int)(65536 / ((elem == 4 ? JF_FB_REGS32 : 128) * fb_threads(D))); }
 template <typename T>
 __host__ __device__ constexpr size_t fb_smem_bytes(int D, int kmax, int hh_max) {
     return ((size_t)3 * kmax * fb_threads(D) + (size_t)fb_groups(D) * (hh_max * D + 2 * D) * 32) * sizeof(T);
