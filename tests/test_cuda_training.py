@@ -129,6 +129,19 @@ def test_gradients_wrt_x_and_conditional_input_by_finite_differences(lib_built):
                 assert (fd - gt[:, col]).abs().max() < 1e-6 * max(1.0, float(gt.abs().max())), (t is x, col)
 
 
+@pytest.mark.parametrize("n", [1, 3, 31, 33, 130])
+def test_fp32_tiny_and_ragged_batches(lib_built, n):
+    """row counts below / across the 32- and 64-row tiles of the tensor-core generator backward (TMA boxes reach past the
+    tensor: zero fill) and of the chain kernel's 32-row warps"""
+    p, y, c = _cfg5(max(n, 4))
+    y, c = y[:n], c[:n]
+    g64, _ = cuda_grads(p.cuda(), y.cuda(), c.cuda())
+    g32, _ = cuda_grads(p.float().cuda(), y.float().cuda(), c.float().cuda())
+    for k in g64:
+        err = np.abs(g32[k] - g64[k]).max() / max(np.abs(g64[k]).max(), 1e-30)
+        assert err < 3e-3, (n, k, err)
+
+
 def test_adam_steps_decrease_the_loss(lib_built):
     """a few optimiser steps on synthetic conditional data: the negative log-likelihood goes down, nothing goes non-finite"""
     p, _, c = _cfg5(8192, scale=0.0)
