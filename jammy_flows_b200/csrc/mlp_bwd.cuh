@@ -362,55 +362,59 @@ __global__ void __launch_bounds__(kBwThreads, 1) bw_dw2_kernel(const BwArgs a, c
 }
 
 // ---- dW1 = dpre^T x, db1 = sum dpre, dx = dpre W1 (1 % of the flops: FFMA) -------------------------------------------------
-// persistent blocks over tiles of 64 rows; thread t: hidden unit u = t & 127, half = t >> 7 of the inputs.  The partial sums
-// of dW1 / db1 stay in registers over all tiles of a block and go out with ONE red.global pass per block (the first version
-// issued 128 x in atomics per 64 rows: 134 M per 1 M rows).
+// persistent blocks over tiles of 64 rows.  dW1: thread -> (pair of hidden units 2 hp, 2 hp + 1; quarter q of the inputs):
+// per row one 8-byte load of the two dpre values and 16-byte broadcast loads of the inputs feed 2 x kSmPer multiply-adds
+// (the first version issued 9 shared-memory loads per 8 multiply-adds).  The partial sums stay in registers over all
+// tiles of a block and go out with ONE red.global pass per block.
 constexpr int kSmRows = 64;
-constexpr int kSmMaxHalf = 48;                          // inputs per half: (96 + 1) / 2
+constexpr int kSmPer = 24;                              // inputs per thread: ceil(96 / 4)
+constexpr int kSmLdD = 130;                             // dpre row stride in shared memory (even: 8-byte loads, conflict free)
 __global__ void __launch_bounds__(256) bw_small_kernel(const BwArgs a) {
-    extern __shared__ float sm_s[];
-    float* sD = sm_s;                                   // [64][129] dpre
-    float* sX = sD + kSmRows * 129;                     // [64][in + 1]
-    float* sW = sX + kSmRows * (a.in | 1);              // [128][in + 1]  W1
-    const int ldxs = a.in | 1;
+    extern __shared__ __align__(16) float sm_s[];
+    const int ldxs = ((a.in + 3) / 4) * 4 + 4 * ((kSmPer + 3) / 4);   // inputs padded so that every thread may read kSmPer values
+    float* sD = sm_s;                                   // [64][130] dpre
+    float* sX = sD + kSmRows * kSmLdD;                  // [64][ldxs] inputs (zero padded)
+    float* sW = sX + kSmRows * ldxs;                    // [128][in | 1]  W1 (dx only)
+    const int ldw = a.in | 1;
     if (a.dx != nullptr)
         for (int e = threadIdx.x; e < kBwH * a.in; e += blockDim.x) {
             const int u = e / a.in, i = e - u * a.in;
-            sW[u * ldxs + i] = a.W1[e];
+            sW[u * ldw + i] = a.W1[e];
         }
-    const int u = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int i0 = half * ((a.in + 1) / 2), i1 = half == 0 ? (a.in + 1) / 2 : a.in;
-    float acc[kSmMaxHalf / 8][8];
+    const int hp = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int per = ((a.in + 3) / 4 + 3) / 4 * 4;      // inputs per quarter, a multiple of 4 (<= kSmPer)
+    const int i0 = q * per;
+    float acc0[kSmPer], acc1[kSmPer];
 #pragma unroll
-    for (int g = 0; g < kSmMaxHalf / 8; ++g)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[g][j] = 0.f;
-    float bsum = 0.f;
+    for (int j = 0; j < kSmPer; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    float bsum0 = 0.f, bsum1 = 0.f;
     const int64_t n_tiles = (a.B + kSmRows - 1) / kSmRows;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kSmRows;
         __syncthreads();                                // the previous tile has been consumed
         for (int e = threadIdx.x; e < kSmRows * kBwH; e += blockDim.x) {
             const int r = e >> 7, n = e & 127;
-            sD[r * 129 + n] = (row0 + r < a.B) ? a.dpre[(row0 + r) * kBwH + n] : 0.f;
+            sD[r * kSmLdD + n] = (row0 + r < a.B) ? a.dpre[(row0 + r) * kBwH + n] : 0.f;
         }
-        for (int e = threadIdx.x; e < kSmRows * a.in; e += blockDim.x) {
-            const int r = e / a.in, i = e - r * a.in;
-            sX[r * ldxs + i] = (row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
+        for (int e = threadIdx.x; e < kSmRows * ldxs; e += blockDim.x) {
+            const int r = e / ldxs, i = e - r * ldxs;
+            sX[e] = (i < a.in && row0 + r < a.B) ? a.x[(row0 + r) * a.ldx + i] : 0.f;
         }
         __syncthreads();
-        // dW1[u][i] for the inputs i of this half; db1[u]
-        if (half == 0)
-            for (int r = 0; r < kSmRows; ++r) bsum += sD[r * 129 + u];
+        // dW1[u][i], db1[u]
+#pragma unroll 2
+        for (int r = 0; r < kSmRows; ++r) {
+            const float2 dv = *reinterpret_cast<const float2*>(sD + r * kSmLdD + 2 * hp);
+            const float4* xr = reinterpret_cast<const float4*>(sX + r * ldxs + i0);
+            if (q == 0) { bsum0 += dv.x; bsum1 += dv.y; }
 #pragma unroll
-        for (int g = 0; g < kSmMaxHalf / 8; ++g) {
-            const int i = i0 + 8 * g;
-            if (i < i1) {
-                for (int r = 0; r < kSmRows; ++r) {
-                    const float dv = sD[r * 129 + u];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (i + j < i1) acc[g][j] = fmaf(dv, sX[r * ldxs + i + j], acc[g][j]);
+            for (int j4 = 0; j4 < kSmPer / 4; ++j4) {
+                if (4 * j4 < per) {
+                    const float4 xv = xr[j4];
+                    acc0[4 * j4 + 0] = fmaf(dv.x, xv.x, acc0[4 * j4 + 0]); acc1[4 * j4 + 0] = fmaf(dv.y, xv.x, acc1[4 * j4 + 0]);
+                    acc0[4 * j4 + 1] = fmaf(dv.x, xv.y, acc0[4 * j4 + 1]); acc1[4 * j4 + 1] = fmaf(dv.y, xv.y, acc1[4 * j4 + 1]);
+                    acc0[4 * j4 + 2] = fmaf(dv.x, xv.z, acc0[4 * j4 + 2]); acc1[4 * j4 + 2] = fmaf(dv.y, xv.z, acc1[4 * j4 + 2]);
+                    acc0[4 * j4 + 3] = fmaf(dv.x, xv.w, acc0[4 * j4 + 3]); acc1[4 * j4 + 3] = fmaf(dv.y, xv.w, acc1[4 * j4 + 3]);
                 }
             }
         }
@@ -420,20 +424,21 @@ __global__ void __launch_bounds__(256) bw_small_kernel(const BwArgs a) {
             if (row0 + r < a.B) {
                 for (int i = threadIdx.x >> 6; i < a.in; i += 4) {
                     float s_ = 0.f;
-                    for (int n = 0; n < kBwH; ++n) s_ = fmaf(sD[r * 129 + n], sW[n * ldxs + i], s_);
+                    for (int n = 0; n < kBwH; ++n) s_ = fmaf(sD[r * kSmLdD + n], sW[n * ldw + i], s_);
                     a.dx[(row0 + r) * a.lddx + i] = s_;
                 }
             }
         }
     }
 #pragma unroll
-    for (int g = 0; g < kSmMaxHalf / 8; ++g)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int i = i0 + 8 * g + j;
-            if (i < i1) red_add(a.dW1 + (size_t)u * a.in + i, acc[g][j]);
+    for (int j = 0; j < kSmPer; ++j) {
+        const int i = i0 + j;
+        if (j < per && i < a.in) {
+            red_add(a.dW1 + (size_t)(2 * hp) * a.in + i, acc0[j]);
+            red_add(a.dW1 + (size_t)(2 * hp + 1) * a.in + i, acc1[j]);
         }
-    if (half == 0) red_add(a.db1 + u, bsum);
+    }
+    if (q == 0) { red_add(a.db1 + 2 * hp, bsum0); red_add(a.db1 + 2 * hp + 1, bsum1); }
 }
 
 }  // namespace jf

@@ -76,8 +76,8 @@ int launch_mlp_bwd(BwArgs a, void* workspace, cudaStream_t st) {
         bw_dw2_kernel<<<dim3((unsigned)n_pt, (unsigned)splits), kBwThreads, kW2Smem, st>>>(a, tmapG128);
     }
     {
-        const int ldxs = a.in | 1;
-        const int smem = (kSmRows * 129 + kSmRows * ldxs + kBwH * ldxs) * 4;
+        const int ldxs = ((a.in + 3) / 4) * 4 + 4 * ((kSmPer + 3) / 4);
+        const int smem = (kSmRows * kSmLdD + kSmRows * ldxs + kBwH * (a.in | 1)) * 4;
         e = cudaFuncSetAttribute(bw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         const int64_t n_tiles = (a.B + kSmRows - 1) / kSmRows;
