@@ -109,3 +109,24 @@ def test_amortize_everything_structure():
     with pytest.raises(Exception):           # CPU tensors are rejected: there is no fallback
         import torch
         p(torch.zeros(4, 4, dtype=torch.float64), amortization_parameters=init.double().unsqueeze(0).repeat(4, 1))
+
+
+def test_backward_path_selection():
+    """which pdfs take the differentiable path of pdf.forward / pdf.sample(allow_gradients=True) (host logic only): default
+    "g" chains incl. rotation none and "t" layers, every non-Euclidean layer in its closed-form direction; everything else
+    raises NotImplementedError at backward time instead of falling back"""
+    from jammy_flows_b200 import engine
+    yes = [("e3", "ggg", {}), ("e3", "ggt", {}), ("e2+s2+e2", "gg+f+gg", {}), ("s2", "v", {}), ("s1+i1", "o+r", {}), ("s1", "m", {}),
+           ("e2", "gg", {"g": {"rotation_mode": "none", "fit_normalization": 0}}),
+           ("s2", "f", {"f": {"add_vertical_rq_spline_flow": 1, "add_circular_rq_spline_flow": 1}})]
+    no = [("e2", "gg", {"g": {"rotation_mode": "angles"}}), ("e2", "gg", {"g": {"add_skewness": 1}}),
+          ("e2", "gg", {"g": {"nonlinear_stretch_type": "rq_splines"}}), ("e2", "gg", {"g": {"inverse_function_type": "inormal_full_pade"}}),
+          ("s2", "v", {"v": {"natural_direction": 1}}), ("s1", "m", {"m": {"natural_direction": 1}})]
+    for pd, fd, opts in yes:
+        p = jfb.pdf(pd, fd, options_overwrite=opts)
+        assert engine.supports_backward(p) and engine.supports_sample_backward(p), (pd, fd, opts)
+    for pd, fd, opts in no:
+        p = jfb.pdf(pd, fd, options_overwrite=opts)
+        assert not engine.supports_backward(p), (pd, fd, opts)
+    p = jfb.pdf("e2", "gg", conditional_input_dim=2, amortization_mlp_use_custom_mode=True)
+    assert not engine.supports_backward(p)          # AmortizableMLP generators: staged inference path only
