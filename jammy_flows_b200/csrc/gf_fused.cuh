@@ -102,8 +102,10 @@ __host__ __device__ inline int64_t fu_prep_bytes(int n_layers) {
 }
 
 // source row of W2 / b2 (index into the sub-pdf's raw parameter vector) of slot s of (layer, dimension cg); -1: zero column.
-//   sampling  w[0..9], n[0..9], v_0[j] .. v_3[j], mean[0..9], offset_j, padding   (widths and norms first: their regulators
-//             run while the tensor pipe produces the rest)
+//   sampling  w[0..9], n[0..9], mean[0..9], v_0[j] .. v_3[j], offset_j, padding   (widths and norms first: their regulators
+//             run while the tensor pipe produces the rest; everything the root finder needs sits in the first four
+//             tiles, so the solve starts while the tile with the reflection components and the offset -- only needed
+//             AFTER the solve -- is still being produced)
 //   log_pdf   v_0[j] .. v_3[j], offset_j, (mean, log_w, log_n)[0], [1], one pad, then the triples 2..9 (12 slots per tile:
 //             no triple straddles a tile)
 __host__ __device__ inline int fu_source_param(const FuLayerC& c, int d, int direction, int cg, int s) {
@@ -121,8 +123,8 @@ __host__ __device__ inline int fu_source_param(const FuLayerC& c, int d, int dir
     }
     if (s < 10) return off_w + s * d + cg;
     if (s < 20) return off_n + (s - 10) * d + cg;
-    if (s < 24) return (s - 20) < c.hh_iter ? off_hh + (s - 20) * d + cg : -1;
-    if (s < 34) return off_m + (s - 24) * d + cg;
+    if (s < 30) return off_m + (s - 20) * d + cg;
+    if (s < 34) return (s - 30) < c.hh_iter ? off_hh + (s - 30) * d + cg : -1;
     if (s == 34) return c.has_offset ? c.raw_off + cg : -1;
     return -1;
 }
@@ -684,31 +686,33 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     xj = y;
                     logd_prev = logd;
                 } else {
-                    // slots of the sampling layout: w[0..9] | n[0..9] | v_0..3 | mean[0..9] | offset | padding.  The regulated
+                    // slots of the sampling layout: w[0..9] | n[0..9] | mean[0..9] | v_0..3 | offset | padding.  The regulated
                     // kernels go to this worker's shared-memory slots ([field][k][worker], conflict free), where the root
                     // finder of csrc/gf.cuh (rolled loops over k, out of line) reads them.
                     double* slot_m = sSlots + tid, * slot_iw = slot_m + kFuK * kFuWorkers, * slot_n = slot_iw + kFuK * kFuWorkers;
                     double off = 0.0, nsum = 0.0, mmin = Num<double>::big, mmax = -Num<double>::big;
                     double hh[4] = {0.0, 0.0, 0.0, 0.0};        // this dimension's Householder components: exchanged after the solve
+                    // slot s of this (layer, dimension): w[0..9] | n[0..9] | mean[0..9] | v_0..3 | offset | padding
+                    auto take = [&](int s, double val) {
+                        if (JF_FU_DBG & 2) { off += val; return; }
+                        if (s < 10) slot_iw[s * kFuWorkers] = regulate_inv_width(val, lc.w_min, lc.inv_w_max);
+                        else if (s < 20) {
+                            const double g = regulate_norm(val, lc.n_min, lc.n_max);
+                            nsum += g;
+                            slot_n[(s - 10) * kFuWorkers] = g;
+                        } else if (s < 30) {
+                            slot_m[(s - 20) * kFuWorkers] = val;
+                            mmin = tmin(mmin, val);
+                            mmax = tmax(mmax, val);
+                        } else if (s < 34) hh[s < 34 ? s - 30 : 0] = val;
+                        else if (s == 34) off = val;
+                    };
+                    static_assert(DIR != JF_DIR_SAMPLE || (TPL - 1) * SPT >= 30, "the root finder's parameters must fit into the first TPL - 1 tiles");
 #pragma unroll
-                    for (int part = 0; part < TPL; ++part) {
+                    for (int part = 0; part < TPL - 1; ++part) {
                         next_tile(v);
 #pragma unroll
-                        for (int i = 0; i < SPT; ++i) {
-                            const int s = part * SPT + i;
-                            if (JF_FU_DBG & 2) { off += v[i]; continue; }
-                            if (s < 10) slot_iw[s * kFuWorkers] = regulate_inv_width(v[i], lc.w_min, lc.inv_w_max);
-                            else if (s < 20) {
-                                const double g = regulate_norm(v[i], lc.n_min, lc.n_max);
-                                nsum += g;
-                                slot_n[(s - 10) * kFuWorkers] = g;
-                            } else if (s < 24) hh[s < 24 ? s - 20 : 0] = v[i];
-                            else if (s < 34) {
-                                slot_m[(s - 24) * kFuWorkers] = v[i];
-                                mmin = tmin(mmin, v[i]);
-                                mmax = tmax(mmax, v[i]);
-                            } else if (s == 34) off = v[i];
-                        }
+                        for (int i = 0; i < SPT; ++i) take(part * SPT + i, v[i]);
                     }
                     double logd = 0.0;
                     int ev = 0;
@@ -729,6 +733,11 @@ __global__ void __launch_bounds__(kFuThreads, 1) gf_fused_kernel(const __grid_co
                     FU_T(6);
                     n_evals += ev;
                     n_unconv += conv ? 0 : 1;
+                    // the last tile of the layer (the remaining reflection components and the offset) was produced while
+                    // this worker was solving
+                    next_tile(v);
+#pragma unroll
+                    for (int i = 0; i < SPT; ++i) take((TPL - 1) * SPT + i, v[i]);
                     exw[0] = xj;                                // (own mean slots: the solve is over)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) exw[(1 + i) * exF] = hh[i];
